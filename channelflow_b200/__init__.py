@@ -1,0 +1,490 @@
+"""channelflow_b200 -- B200 (sm_100a) implementation of Channelflow's DNS time-step hot path.
+
+This Python module is only a thin ctypes view of the two native libraries (it exists for the tests and bench.py):
+
+  libcfgpu.so        CUDA kernels + the C-ABI of include/cfgpu.h
+  libchflow_b200.so  C++ host classes mirroring the reference API (chflow::FlowField / DNS / DNSFlags / NSE ...)
+                     on top of that C-ABI, plus a flat C driver for them (host/capi.cpp)
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is visible, calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_GPU = os.path.join(_HERE, "libcfgpu.so")
+LIB_HOST = os.path.join(_HERE, "libchflow_b200.so")
+
+PHYSICAL, SPECTRAL = 0, 1
+
+# every symbol include/cfgpu.h declares
+CFGPU_SYMBOLS = """cfgpu_last_error cfgpu_version cfgpu_init cfgpu_finalize cfgpu_sync cfgpu_launch_count cfgpu_timer_start
+cfgpu_timer_stop cfgpu_graph_begin cfgpu_graph_end cfgpu_graph_launch cfgpu_field_create cfgpu_field_destroy
+cfgpu_field_upload cfgpu_field_download cfgpu_field_copy cfgpu_field_swap cfgpu_field_zero cfgpu_field_set_state
+cfgpu_field_get_state cfgpu_field_set_padded cfgpu_field_get_padded cfgpu_field_device_ptr cfgpu_field_axpby
+cfgpu_field_scale cfgpu_field_get_profile cfgpu_field_add_profile cfgpu_field_zero_padded_modes
+cfgpu_field_make_physical_y cfgpu_field_make_spectral_y cfgpu_field_make_physical_xz cfgpu_field_make_spectral_xz
+cfgpu_field_make_physical cfgpu_field_make_spectral cfgpu_l2norm2 cfgpu_l2dist2 cfgpu_l2ip cfgpu_nse_create
+cfgpu_nse_destroy cfgpu_nse_set_constraint cfgpu_nse_reset_lambda cfgpu_nse_nonlinear cfgpu_nse_solve
+cfgpu_nse_linear cfgpu_nse_cflfactor cfgpu_nse_get_dPd""".split()
+
+
+class CfgpuError(RuntimeError):
+    pass
+
+
+class NseConfig(C.Structure):
+    _fields_ = [("nu", C.c_double), ("Vsuck", C.c_double), ("rotation", C.c_double), ("nonlinearity", C.c_int),
+                ("dealias_xz", C.c_int), ("dealias_y", C.c_int), ("taucorrection", C.c_int), ("constraint", C.c_int),
+                ("dPdxRef", C.c_double), ("dPdzRef", C.c_double), ("UbulkRef_minus_base", C.c_double),
+                ("WbulkRef_minus_base", C.c_double)]
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class GpuLib:
+    """ctypes view of the C-ABI (include/cfgpu.h)."""
+
+    def __init__(self, path=None):
+        path = path or LIB_GPU
+        if not os.path.exists(path):
+            raise CfgpuError("CUDA library %s is missing: run `python __graft_entry__.py` (there is no CPU fallback)" % path)
+        self.path = path
+        self.L = L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        vp, d, i, dpt = C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double)
+        L.cfgpu_last_error.restype = C.c_char_p
+        L.cfgpu_version.restype = C.c_char_p
+        L.cfgpu_init.argtypes = [i, C.POINTER(vp)]
+        L.cfgpu_finalize.argtypes = [vp]
+        L.cfgpu_sync.argtypes = [vp]
+        L.cfgpu_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+        L.cfgpu_timer_start.argtypes = [vp]
+        L.cfgpu_timer_stop.argtypes = [vp, dpt]
+        L.cfgpu_graph_begin.argtypes = [vp]
+        L.cfgpu_graph_end.argtypes = [vp, C.POINTER(i)]
+        L.cfgpu_graph_launch.argtypes = [vp, i]
+        L.cfgpu_field_create.argtypes = [vp, i, i, i, i, d, d, d, d, C.POINTER(vp)]
+        for n in ("destroy", "zero", "zero_padded_modes", "make_physical_y", "make_spectral_y", "make_physical_xz",
+                  "make_spectral_xz", "make_physical", "make_spectral"):
+            getattr(L, "cfgpu_field_" + n).argtypes = [vp]
+        L.cfgpu_field_upload.argtypes = [vp, dpt, i, i]
+        L.cfgpu_field_download.argtypes = [vp, dpt]
+        L.cfgpu_field_copy.argtypes = [vp, vp]
+        L.cfgpu_field_swap.argtypes = [vp, vp]
+        L.cfgpu_field_set_state.argtypes = [vp, i, i]
+        L.cfgpu_field_get_state.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+        L.cfgpu_field_set_padded.argtypes = [vp, i]
+        L.cfgpu_field_get_padded.argtypes = [vp, C.POINTER(i)]
+        L.cfgpu_field_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_longlong)]
+        L.cfgpu_field_axpby.argtypes = [vp, d, vp, d, vp]
+        L.cfgpu_field_scale.argtypes = [vp, d]
+        L.cfgpu_field_get_profile.argtypes = [vp, i, i, i, dpt]
+        L.cfgpu_field_add_profile.argtypes = [vp, i, i, i, dpt, d]
+        L.cfgpu_l2norm2.argtypes = [vp, i, dpt]
+        L.cfgpu_l2dist2.argtypes = [vp, vp, i, dpt]
+        L.cfgpu_l2ip.argtypes = [vp, vp, i, dpt]
+        L.cfgpu_nse_create.argtypes = [vp, i, i, i, d, d, d, d, C.POINTER(NseConfig), dpt, dpt, C.POINTER(vp)]
+        L.cfgpu_nse_destroy.argtypes = [vp]
+        L.cfgpu_nse_set_constraint.argtypes = [vp, i, d, d, d, d]
+        L.cfgpu_nse_reset_lambda.argtypes = [vp, dpt, i]
+        L.cfgpu_nse_nonlinear.argtypes = [vp, vp, vp]
+        L.cfgpu_nse_solve.argtypes = [vp, i, i, dpt, C.POINTER(vp), vp, vp]
+        L.cfgpu_nse_linear.argtypes = [vp, vp, vp, vp]
+        L.cfgpu_nse_cflfactor.argtypes = [vp, vp, dpt]
+        L.cfgpu_nse_get_dPd.argtypes = [vp, dpt, dpt]
+
+    def check(self, status):
+        if status != 0:
+            raise CfgpuError(self.L.cfgpu_last_error().decode())
+
+    def missing_symbols(self):
+        return [s for s in CFGPU_SYMBOLS if not hasattr(self.L, s)]
+
+
+class Context:
+    def __init__(self, lib=None, device=0):
+        self.lib = lib or GpuLib()
+        self.h = C.c_void_p()
+        self.lib.check(self.lib.L.cfgpu_init(device, C.byref(self.h)))
+
+    def sync(self):
+        self.lib.check(self.lib.L.cfgpu_sync(self.h))
+
+    def launch_count(self):
+        n = C.c_longlong()
+        self.lib.check(self.lib.L.cfgpu_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def timer_start(self):
+        self.lib.check(self.lib.L.cfgpu_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self.lib.check(self.lib.L.cfgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def field(self, Nx, Ny, Nz, Nd, Lx, Lz, a=-1.0, b=1.0):
+        return Field(self, Nx, Ny, Nz, Nd, Lx, Lz, a, b)
+
+
+class Field:
+    """Device-resident FlowField storage (reference serial layout [Nd][Ny][Nx][Nzpad])."""
+
+    def __init__(self, ctx, Nx, Ny, Nz, Nd, Lx, Lz, a=-1.0, b=1.0):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.Nx, self.Ny, self.Nz, self.Nd, self.Lx, self.Lz, self.a, self.b = Nx, Ny, Nz, Nd, Lx, Lz, a, b
+        self.Mz = Nz // 2 + 1
+        self.h = C.c_void_p()
+        self.lib.check(self.lib.L.cfgpu_field_create(ctx.h, Nx, Ny, Nz, Nd, Lx, Lz, a, b, C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.L.cfgpu_field_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        return (self.Nd, self.Ny, self.Nx, 2 * self.Mz)
+
+    def like(self, Nd=None):
+        return Field(self.ctx, self.Nx, self.Ny, self.Nz, self.Nd if Nd is None else Nd, self.Lx, self.Lz, self.a, self.b)
+
+    def upload(self, arr, xz=SPECTRAL, y=SPECTRAL, padded=None):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.size == int(np.prod(self.shape)), (arr.shape, self.shape)
+        self.lib.check(self.lib.L.cfgpu_field_upload(self.h, _dp(arr), xz, y))
+        if padded is not None:
+            self.set_padded(padded)
+        return self
+
+    def download(self):
+        out = np.empty(self.shape, dtype=np.float64)
+        self.lib.check(self.lib.L.cfgpu_field_download(self.h, _dp(out)))
+        return out
+
+    def set_padded(self, p):
+        self.lib.check(self.lib.L.cfgpu_field_set_padded(self.h, 1 if p else 0))
+
+    def state(self):
+        a, b = C.c_int(), C.c_int()
+        self.lib.check(self.lib.L.cfgpu_field_get_state(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def copy_from(self, o): self.lib.check(self.lib.L.cfgpu_field_copy(self.h, o.h))
+    def swap(self, o): self.lib.check(self.lib.L.cfgpu_field_swap(self.h, o.h))
+    def zero(self): self.lib.check(self.lib.L.cfgpu_field_zero(self.h))
+    def axpby(self, a, x, b=0.0, z=None): self.lib.check(self.lib.L.cfgpu_field_axpby(self.h, a, x.h, b, z.h if z else None))
+    def scale(self, s): self.lib.check(self.lib.L.cfgpu_field_scale(self.h, s))
+    def zero_padded_modes(self): self.lib.check(self.lib.L.cfgpu_field_zero_padded_modes(self.h))
+    def make_physical(self): self.lib.check(self.lib.L.cfgpu_field_make_physical(self.h))
+    def make_spectral(self): self.lib.check(self.lib.L.cfgpu_field_make_spectral(self.h))
+    def make_physical_y(self): self.lib.check(self.lib.L.cfgpu_field_make_physical_y(self.h))
+    def make_spectral_y(self): self.lib.check(self.lib.L.cfgpu_field_make_spectral_y(self.h))
+    def make_physical_xz(self): self.lib.check(self.lib.L.cfgpu_field_make_physical_xz(self.h))
+    def make_spectral_xz(self): self.lib.check(self.lib.L.cfgpu_field_make_spectral_xz(self.h))
+
+    def get_profile(self, mx, mz, i):
+        out = np.empty(2 * self.Ny)
+        self.lib.check(self.lib.L.cfgpu_field_get_profile(self.h, mx, mz, i, _dp(out)))
+        return out[0::2] + 1j * out[1::2]
+
+    def add_profile(self, mx, mz, i, prof, scale=1.0):
+        p = np.empty(2 * self.Ny)
+        p[0::2], p[1::2] = np.real(prof), np.imag(prof)
+        self.lib.check(self.lib.L.cfgpu_field_add_profile(self.h, mx, mz, i, _dp(p), scale))
+
+    def l2norm2(self, normalize=True):
+        v = C.c_double()
+        self.lib.check(self.lib.L.cfgpu_l2norm2(self.h, 1 if normalize else 0, C.byref(v)))
+        return v.value
+
+    def l2norm(self, normalize=True):
+        return float(np.sqrt(self.l2norm2(normalize)))
+
+    def l2dist(self, o, normalize=True):
+        v = C.c_double()
+        self.lib.check(self.lib.L.cfgpu_l2dist2(self.h, o.h, 1 if normalize else 0, C.byref(v)))
+        return float(np.sqrt(v.value))
+
+    def l2ip(self, o, normalize=True):
+        v = C.c_double()
+        self.lib.check(self.lib.L.cfgpu_l2ip(self.h, o.h, 1 if normalize else 0, C.byref(v)))
+        return v.value
+
+
+class Nse:
+    """Device NSE operator (cfgpu_nse_*): nonlinear term, batched tau solve, linear term, CFL."""
+
+    def __init__(self, ctx, Nx, Ny, Nz, Lx, Lz, a, b, Ubase=None, Wbase=None, nu=0.0025, Vsuck=0.0, rotation=0.0,
+                 nonlinearity=0, dealias_xz=True, dealias_y=False, taucorrection=True, constraint=0, dPdxRef=0.0,
+                 dPdzRef=0.0, UbulkRef_minus_base=0.0, WbulkRef_minus_base=0.0):
+        self.ctx, self.lib = ctx, ctx.lib
+        cfg = NseConfig(nu, Vsuck, rotation, nonlinearity, int(dealias_xz), int(dealias_y), int(taucorrection), constraint,
+                        dPdxRef, dPdzRef, UbulkRef_minus_base, WbulkRef_minus_base)
+        U = np.ascontiguousarray(Ubase, dtype=np.float64) if Ubase is not None else None
+        W = np.ascontiguousarray(Wbase, dtype=np.float64) if Wbase is not None else None
+        self.h = C.c_void_p()
+        self.lib.check(self.lib.L.cfgpu_nse_create(ctx.h, Nx, Ny, Nz, Lx, Lz, a, b, C.byref(cfg),
+                                                   _dp(U) if U is not None else None,
+                                                   _dp(W) if W is not None else None, C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.L.cfgpu_nse_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def reset_lambda(self, lambda_t):
+        lt = np.ascontiguousarray(lambda_t, dtype=np.float64)
+        self.lib.check(self.lib.L.cfgpu_nse_reset_lambda(self.h, _dp(lt), lt.size))
+
+    def nonlinear(self, u, f):
+        self.lib.check(self.lib.L.cfgpu_nse_nonlinear(self.h, u.h, f.h))
+
+    def solve(self, s, coefs, terms, uout, qout):
+        c = np.ascontiguousarray(coefs, dtype=np.float64)
+        arr = (C.c_void_p * len(terms))(*[t.h for t in terms])
+        self.lib.check(self.lib.L.cfgpu_nse_solve(self.h, s, len(terms), _dp(c), arr, uout.h, qout.h))
+
+    def linear(self, u, q, L):
+        self.lib.check(self.lib.L.cfgpu_nse_linear(self.h, u.h, q.h, L.h))
+
+    def cflfactor(self, u):
+        v = C.c_double()
+        self.lib.check(self.lib.L.cfgpu_nse_cflfactor(self.h, u.h, C.byref(v)))
+        return v.value
+
+    def get_dPd(self):
+        a, b = C.c_double(), C.c_double()
+        self.lib.check(self.lib.L.cfgpu_nse_get_dPd(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def check_symbols(path=None):
+    """The C-ABI library loads and exports every symbol include/cfgpu.h declares (no GPU needed)."""
+    lib = GpuLib(path)
+    miss = lib.missing_symbols()
+    if miss:
+        raise CfgpuError("libcfgpu.so is missing symbols: " + ", ".join(miss))
+    return True
+
+
+# =====================================================================================================================
+# Host classes (libchflow_b200.so): chflow::FlowField / NSE / DNS over the C-ABI, driven through host/capi.cpp
+# =====================================================================================================================
+BASEFLOW = dict(zero=0, linear=1, parabolic=2, laminar=3, suction=4, arbitrary=5)
+CONSTRAINT = dict(gradp=0, bulkv=1)
+STEPPER = dict(cnfe1=0, cnab2=1, cnrk2=2, smrk2=3, sbdf1=4, sbdf2=5, sbdf3=6, sbdf4=7)
+NONLIN = dict(rot=0, conv=1, div=2, skew=3, alt=4, alt_=5, linear=6)
+DEALIAS = dict(none=0, xz=1, y=2, xyz=3)
+
+
+class Flags(C.Structure):
+    """DNSFlags subset passed to the C drivers (same layout as oracle/ref_driver.cpp's RefFlags)."""
+    _fields_ = [(n, C.c_double) for n in
+                ("nu", "dPdx", "dPdz", "Ubulk", "Wbulk", "ulowerwall", "uupperwall", "wlowerwall", "wupperwall",
+                 "Vsuck", "rotation", "t0", "dt")] + \
+               [(n, C.c_int) for n in
+                ("baseflow", "constraint", "timestepping", "initstepping", "nonlinearity", "dealiasing",
+                 "taucorrection")]
+
+
+def make_flags(nu=0.0025, dPdx=0.0, dPdz=0.0, Ubulk=0.0, Wbulk=0.0, ulowerwall=0.0, uupperwall=0.0, wlowerwall=0.0,
+               wupperwall=0.0, Vsuck=0.0, rotation=0.0, t0=0.0, dt=0.03125, baseflow="laminar", constraint="gradp",
+               timestepping="sbdf3", initstepping="smrk2", nonlinearity="rot", dealiasing="xz", taucorrection=True):
+    """Defaults of DNSFlags::DNSFlags (reference dnsflags.h:84-94)."""
+    f = Flags()
+    f.nu, f.dPdx, f.dPdz, f.Ubulk, f.Wbulk = nu, dPdx, dPdz, Ubulk, Wbulk
+    f.ulowerwall, f.uupperwall, f.wlowerwall, f.wupperwall = ulowerwall, uupperwall, wlowerwall, wupperwall
+    f.Vsuck, f.rotation, f.t0, f.dt = Vsuck, rotation, t0, dt
+    f.baseflow, f.constraint = BASEFLOW[baseflow], CONSTRAINT[constraint]
+    f.timestepping, f.initstepping = STEPPER[timestepping], STEPPER[initstepping]
+    f.nonlinearity, f.dealiasing = NONLIN[nonlinearity], DEALIAS[dealiasing]
+    f.taucorrection = 1 if taucorrection else 0
+    return f
+
+
+class HostLib:
+    """ctypes view of libchflow_b200.so (host/capi.cpp).  `gpu_path` must be the CUDA library it was linked to."""
+
+    def __init__(self, path=None, gpu_path=None):
+        path = path or LIB_HOST
+        self.gpu = GpuLib(gpu_path)  # loads libcfgpu first (RTLD_GLOBAL) and fails loudly if it is missing
+        if not os.path.exists(path):
+            raise CfgpuError("host library %s is missing: run `python __graft_entry__.py`" % path)
+        self.L = L = C.CDLL(path)
+        vp, d, i, dpt = C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double)
+        L.cf_field_create.restype = vp
+        L.cf_field_create.argtypes = [i, i, i, i, d, d, d, d]
+        L.cf_field_load.restype = vp
+        L.cf_field_load.argtypes = [C.c_char_p]
+        L.cf_field_save.argtypes = [vp, C.c_char_p]
+        L.cf_field_nloc.restype = C.c_long
+        for n in ("cf_field_free", "cf_field_nloc", "cf_field_zero", "cf_make_physical", "cf_make_spectral",
+                  "cf_make_physical_y", "cf_make_spectral_y", "cf_make_physical_xz", "cf_make_spectral_xz",
+                  "cf_zero_padded_modes", "cf_l2norm", "cf_field_padded", "cf_dns_free", "cf_dns_cfl", "cf_dns_time",
+                  "cf_dns_dPdx", "cf_dns_Ubulk", "cf_timestep_free", "cf_timestep_n", "cf_timestep_N", "cf_timestep_dt",
+                  "cf_timestep_dT", "cf_timestep_CFL"):
+            getattr(L, n).argtypes = [vp]
+        for n in ("cf_l2norm", "cf_l2dist", "cf_l2ip", "cf_l2norm2", "cf_dns_cfl", "cf_dns_time", "cf_dns_dPdx",
+                  "cf_dns_Ubulk", "cf_timer_stop", "cf_timestep_dt", "cf_timestep_dT", "cf_timestep_CFL", "cf_cmplx_get"):
+            getattr(L, n).restype = d
+        L.cf_field_upload.argtypes = [vp, dpt]
+        L.cf_field_download.argtypes = [vp, dpt]
+        L.cf_field_set_state.argtypes = [vp, i, i]
+        L.cf_field_get_state.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+        L.cf_field_set_padded.argtypes = [vp, i]
+        L.cf_field_copy.argtypes = [vp, vp]
+        L.cf_cmplx_get.argtypes = [vp, i, i, i, i, i]
+        L.cf_cmplx_set.argtypes = [vp, i, i, i, i, d, d]
+        L.cf_l2norm2.argtypes = [vp, i]
+        L.cf_l2dist.argtypes = [vp, vp]
+        L.cf_l2ip.argtypes = [vp, vp]
+        L.cf_field_axpby.argtypes = [vp, d, vp, d, vp]
+        L.cf_field_scale.argtypes = [vp, d]
+        L.cf_nonlinear.argtypes = [vp, vp, C.POINTER(Flags)]
+        L.cf_base_profiles.argtypes = [vp, C.POINTER(Flags), dpt, dpt]
+        L.cf_dns_create.restype = vp
+        L.cf_dns_create.argtypes = [vp, vp, C.POINTER(Flags)]
+        L.cf_dns_advance.argtypes = [vp, i]
+        L.cf_dns_get.argtypes = [vp, vp, vp]
+        L.cf_dns_set.argtypes = [vp, vp, vp]
+        L.cf_dns_reset_dt.argtypes = [vp, d]
+        L.cf_launch_count.restype = C.c_longlong
+        L.cf_laminar_profile.argtypes = [C.POINTER(Flags), d, d, i, dpt]
+        L.cf_timestep_create.restype = vp
+        L.cf_timestep_create.argtypes = [d, d, d, d, d, d, i]
+        L.cf_timestep_adjust.argtypes = [vp, d]
+        L.cf_timestep_adjust_for_T.argtypes = [vp, d]
+
+    def sync(self): self.L.cf_sync()
+    def launch_count(self): return self.L.cf_launch_count()
+    def timer_start(self): self.L.cf_timer_start()
+    def timer_stop(self): return self.L.cf_timer_stop()
+
+
+class FlowField:
+    """chflow::FlowField of this package (device resident)."""
+
+    def __init__(self, lib, Nx, Ny, Nz, Nd, Lx, Lz, a=-1.0, b=1.0, handle=None):
+        self.lib = lib
+        self.Nx, self.Ny, self.Nz, self.Nd, self.Lx, self.Lz, self.a, self.b = Nx, Ny, Nz, Nd, Lx, Lz, a, b
+        self.Mz = Nz // 2 + 1
+        self.h = handle if handle is not None else lib.L.cf_field_create(Nx, Ny, Nz, Nd, Lx, Lz, a, b)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.L.cf_field_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        return (self.Nd, self.Ny, self.Nx, 2 * self.Mz)
+
+    def like(self, Nd=None):
+        return FlowField(self.lib, self.Nx, self.Ny, self.Nz, self.Nd if Nd is None else Nd, self.Lx, self.Lz, self.a, self.b)
+
+    def set(self, arr, xz=SPECTRAL, y=SPECTRAL, padded=None):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.size == int(np.prod(self.shape))
+        self.lib.L.cf_field_set_state(self.h, xz, y)
+        self.lib.L.cf_field_upload(self.h, _dp(arr))
+        if padded is not None:
+            self.lib.L.cf_field_set_padded(self.h, 1 if padded else 0)
+        return self
+
+    def get(self):
+        out = np.empty(self.shape)
+        self.lib.L.cf_field_download(self.h, _dp(out))
+        return out
+
+    def copy(self):
+        o = self.like()
+        self.lib.L.cf_field_copy(o.h, self.h)
+        return o
+
+    def state(self):
+        a, b = C.c_int(), C.c_int()
+        self.lib.L.cf_field_get_state(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def set_padded(self, p): self.lib.L.cf_field_set_padded(self.h, 1 if p else 0)
+    def padded(self): return bool(self.lib.L.cf_field_padded(self.h))
+    def make_physical(self): self.lib.L.cf_make_physical(self.h)
+    def make_spectral(self): self.lib.L.cf_make_spectral(self.h)
+    def make_physical_y(self): self.lib.L.cf_make_physical_y(self.h)
+    def make_spectral_y(self): self.lib.L.cf_make_spectral_y(self.h)
+    def make_physical_xz(self): self.lib.L.cf_make_physical_xz(self.h)
+    def make_spectral_xz(self): self.lib.L.cf_make_spectral_xz(self.h)
+    def zero_padded_modes(self): self.lib.L.cf_zero_padded_modes(self.h)
+    def l2norm(self): return self.lib.L.cf_l2norm(self.h)
+    def l2dist(self, o): return self.lib.L.cf_l2dist(self.h, o.h)
+    def l2ip(self, o): return self.lib.L.cf_l2ip(self.h, o.h)
+    def cmplx(self, mx, my, mz, i): return complex(self.lib.L.cf_cmplx_get(self.h, mx, my, mz, i, 0), self.lib.L.cf_cmplx_get(self.h, mx, my, mz, i, 1))
+    def set_cmplx(self, mx, my, mz, i, v): self.lib.L.cf_cmplx_set(self.h, mx, my, mz, i, v.real, v.imag)
+    def save(self, filebase): self.lib.L.cf_field_save(self.h, filebase.encode())
+    def axpby(self, a, x, b=0.0, z=None): self.lib.L.cf_field_axpby(self.h, a, x.h, b, z.h if z is not None else None)
+    def scale(self, s): self.lib.L.cf_field_scale(self.h, s)
+
+
+class DNS:
+    """chflow::DNS of this package (reference dns.cpp:22-163 semantics) owning copies of (u, q)."""
+
+    def __init__(self, u, flags, q=None):
+        self.lib, self.geom = u.lib, u
+        if q is None:
+            q = u.like(Nd=1)
+        self.flags = flags
+        self.h = self.lib.L.cf_dns_create(u.h, q.h, C.byref(flags))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.L.cf_dns_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def advance(self, n): self.lib.L.cf_dns_advance(self.h, n)
+
+    def get(self):
+        u, q = self.geom.like(), self.geom.like(Nd=1)
+        self.lib.L.cf_dns_get(self.h, u.h, q.h)
+        return u, q
+
+    def set(self, u=None, q=None): self.lib.L.cf_dns_set(self.h, u.h if u else None, q.h if q else None)
+    def cfl(self): return self.lib.L.cf_dns_cfl(self.h)
+    def reset_dt(self, dt): self.lib.L.cf_dns_reset_dt(self.h, dt)
+    def time(self): return self.lib.L.cf_dns_time(self.h)
+    def dPdx(self): return self.lib.L.cf_dns_dPdx(self.h)
+    def Ubulk(self): return self.lib.L.cf_dns_Ubulk(self.h)
+
+
+def nonlinear(u, flags):
+    f = u.like()
+    u.lib.L.cf_nonlinear(u.h, f.h, C.byref(flags))
+    return f
+
+
+def base_profiles(u, flags):
+    U, W = np.zeros(u.Ny), np.zeros(u.Ny)
+    u.lib.L.cf_base_profiles(u.h, C.byref(flags), _dp(U), _dp(W))
+    return U, W
+
+
+def laminar_profile(lib, flags, a, b, Ny):
+    U = np.zeros(Ny)
+    lib.L.cf_laminar_profile(C.byref(flags), a, b, Ny, _dp(U))
+    return U

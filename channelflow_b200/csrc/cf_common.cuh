@@ -1,0 +1,103 @@
+// Common device/host helpers for the cfgpu kernels (sm_100a).
+//
+// All kernels are launched through CF_LAUNCH so that the same sources can also be compiled by g++ with
+// -DCF_EMU -Itests/emu (fiber-based CPU emulation, test infrastructure only -- see tests/emu/cuda_runtime.h).
+// The product build is nvcc -gencode arch=compute_100a,code=sm_100a; there is no CPU code path in it.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+
+namespace cfgpu {
+extern long long g_launches;  // kernels launched by this library (reported by cfgpu_launch_count)
+}
+
+#ifdef CF_EMU
+#define CF_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (++cfgpu::g_launches, cfemu::launch(grid, block, smem, [=]() { kernel(__VA_ARGS__); }))
+#else
+#define CF_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (++cfgpu::g_launches, kernel<<<grid, block, smem, stream>>>(__VA_ARGS__))
+#endif
+
+namespace cfgpu {
+
+// ---- error plumbing (C-ABI returns int status; message via cfgpu_last_error) ----
+void set_last_error(const std::string& msg);
+inline int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
+    if (e == cudaSuccess) return 0;
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+    set_last_error(buf);
+    return 1;
+}
+#define CF_CUDA(expr)                                                        \
+    do {                                                                     \
+        if (cfgpu::check_cuda((expr), #expr, __FILE__, __LINE__)) return 1;  \
+    } while (0)
+#define CF_KERNEL_CHECK() CF_CUDA(cudaGetLastError())
+#define CF_TRY(expr)             \
+    do {                         \
+        if ((expr) != 0) return 1; \
+    } while (0)
+
+// ---- dynamic shared memory base ----
+template <class T>
+__device__ __forceinline__ T* dyn_smem() {
+#ifdef CF_EMU
+    return reinterpret_cast<T*>(cfemu::t_dyn_smem);
+#else
+    extern __shared__ __align__(16) unsigned char cf_dyn_smem_raw[];
+    return reinterpret_cast<T*>(cf_dyn_smem_raw);
+#endif
+}
+
+// ---- FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4 ----
+// fragment layout (PTX ISA, mma.m8n8k4 .f64): a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// c0,c1 = C[lane/4][2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+#ifdef CF_EMU
+    cfemu::dmma884(c0, c1, a, b);
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+#endif
+}
+
+// ---- atomic max on a double (signed compare, as the reference's CFL max has no abs) ----
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *p;
+    while (__longlong_as_double((long long)old) < v) {
+        unsigned long long assumed = old;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+struct cplx {
+    double re, im;
+};
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.re - b.re, a.im - b.im}; }
+
+inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace cfgpu

@@ -1,0 +1,514 @@
+// Implementation of the C-ABI declared in include/cfgpu.h (context, FlowField storage, transforms, norms).
+// The NSE operator entry points are in cfgpu_nse.cu.
+#include <cmath>
+#include <cstring>
+
+#include "cfgpu_internal.h"
+#include "fieldops.cuh"
+
+namespace cfgpu {
+
+long long g_launches = 0;
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+static const long double PIl = 3.141592653589793238462643383279502884L;
+
+int ws_reserve(Workspace& w, size_t bytes) {
+    if (bytes <= w.bytes) return 0;
+    if (w.ptr) CF_CUDA(cudaFree(w.ptr));
+    w.ptr = nullptr;
+    w.bytes = 0;
+    CF_CUDA(cudaMalloc((void**)&w.ptr, bytes));
+    w.bytes = bytes;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- plan builders
+static int upload(const std::vector<double>& h, double** d) {
+    CF_CUDA(cudaMalloc((void**)d, h.size() * sizeof(double)));
+    CF_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static long double cos_pi_frac(long num, long den) {
+    // cos(pi * num / den) with exact argument reduction
+    num %= 2 * den;
+    if (num < 0) num += 2 * den;
+    if (num > den) num = 2 * den - num;  // cos(2pi - x) = cos x
+    if (2 * num == den) return 0.0L;
+    if (2 * num > den) return -cosl(PIl * (long double)(den - num) / (long double)den);
+    return cosl(PIl * (long double)num / (long double)den);
+}
+
+int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out) {
+    auto key = std::make_tuple(N, a, b);
+    auto it = ctx->yplans.find(key);
+    if (it != ctx->yplans.end()) {
+        *out = &it->second;
+        return 0;
+    }
+    if (N < 2) {
+        set_last_error("y transform needs Ny >= 2");
+        return 1;
+    }
+    YPlan pl;
+    pl.N = N; pl.a = a; pl.b = b;
+    const int Nb = N - 1;
+    pl.Nh = (N + 1) / 2;
+    pl.Ne = Nb / 2 + 1;
+    pl.No = N - pl.Ne;
+    const int Nh = pl.Nh, Ne = pl.Ne, No = pl.No;
+    auto r8 = [](int x) { return (x + 7) & ~7; };
+    auto r4 = [](int x) { return (x + 3) & ~3; };
+    pl.invMp = r8(Nh); pl.invK1p = r4(Ne); pl.invK2p = r4(No > 0 ? No : 1);
+    pl.fwdMp = r8(Ne > No ? Ne : No); pl.fwdKp = r4(Nh);
+
+    // C[j][n] = cos(pi j n / Nb) ; derivative operator on coefficients (chebyshev.cpp:672-697)
+    std::vector<long double> C((size_t)N * N), CD((size_t)N * N, 0.0L);
+    for (int j = 0; j < N; ++j)
+        for (int n = 0; n < N; ++n) C[(size_t)j * N + n] = cos_pi_frac((long)j * n, Nb);
+    const long double scale = 4.0L / ((long double)b - (long double)a);
+    for (int j = 0; j < N; ++j)
+        for (int m = 0; m < N; ++m) {
+            long double s = 0.0L;
+            for (int n = (m - 1); n >= 0; n -= 2) s += C[(size_t)j * N + n] * (n == 0 ? 0.5L : 1.0L);
+            CD[(size_t)j * N + m] = s * scale * (long double)m;
+        }
+    std::vector<double> Ce((size_t)pl.invMp * pl.invK1p, 0.0), Co((size_t)pl.invMp * pl.invK2p, 0.0);
+    std::vector<double> CDe(Ce.size(), 0.0), CDo(Co.size(), 0.0);
+    for (int j = 0; j < Nh; ++j) {
+        for (int r = 0; r < Ne; ++r) {
+            Ce[(size_t)j * pl.invK1p + r] = (double)C[(size_t)j * N + 2 * r];
+            CDe[(size_t)j * pl.invK1p + r] = (double)CD[(size_t)j * N + 2 * r];
+        }
+        for (int r = 0; r < No; ++r) {
+            Co[(size_t)j * pl.invK2p + r] = (double)C[(size_t)j * N + 2 * r + 1];
+            CDo[(size_t)j * pl.invK2p + r] = (double)CD[(size_t)j * N + 2 * r + 1];
+        }
+    }
+    // forward: c_n = w_n sum_j g_j cos(pi j n/Nb) x_j  (flowfield.cpp:1913-1934)
+    std::vector<double> Fe((size_t)pl.fwdMp * pl.fwdKp, 0.0), Fo(Fe.size(), 0.0);
+    for (int n = 0; n < N; ++n) {
+        const long double wn = ((n == 0 || n == Nb) ? 0.5L : 1.0L) / (long double)Nb;
+        for (int j = 0; j < Nh; ++j) {
+            const long double gj = (j == 0 || j == Nb) ? 1.0L : 2.0L;
+            const double v = (double)(wn * gj * C[(size_t)j * N + n]);
+            if (n % 2 == 0) Fe[(size_t)(n / 2) * pl.fwdKp + j] = v;
+            else Fo[(size_t)(n / 2) * pl.fwdKp + j] = v;
+        }
+    }
+    // Gram weights <T_m,T_n> (chebyshev.cpp:758-802), FP64 arithmetic (the reference's int version overflows for Ny > 215)
+    std::vector<double> W((size_t)N * N, 0.0);
+    for (int m = 0; m < N; ++m)
+        for (int n = m % 2; n < N; n += 2) {
+            const double e = 1.0, dm = m, dn = n;
+            W[(size_t)m * N + n] = (e - dm * dm - dn * dn) / ((e + dm - dn) * (e - dm + dn) * (e + dm + dn) * (e - dm - dn));
+        }
+    CF_TRY(upload(Ce, &pl.Ce)); CF_TRY(upload(Co, &pl.Co)); CF_TRY(upload(CDe, &pl.CDe)); CF_TRY(upload(CDo, &pl.CDo));
+    CF_TRY(upload(Fe, &pl.Fe)); CF_TRY(upload(Fo, &pl.Fo)); CF_TRY(upload(W, &pl.Wgram));
+    auto res = ctx->yplans.emplace(key, pl);
+    *out = &res.first->second;
+    return 0;
+}
+
+int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out) {
+    auto it = ctx->fftplans.find(N);
+    if (it != ctx->fftplans.end()) {
+        *out = &it->second.dev;
+        return 0;
+    }
+    FftPlanHost pl;
+    pl.dev.N = N;
+    pl.dev.npass = 0;
+    int m = N;
+    while (m > 1) {
+        int r;
+        if (m % 4 == 0) r = 4;
+        else if (m % 2 == 0) r = 2;
+        else if (m % 3 == 0) r = 3;
+        else if (m % 5 == 0) r = 5;
+        else {
+            set_last_error("FFT length must factor into 2,3,5: " + std::to_string(N));
+            return 1;
+        }
+        if (pl.dev.npass >= FFT_MAXPASS) { set_last_error("FFT length too large"); return 1; }
+        pl.dev.radix[pl.dev.npass++] = r;
+        m /= r;
+    }
+    std::vector<double> tw(2 * (size_t)N);
+    for (int t = 0; t < N; ++t) {
+        // exp(-2 pi i t / N) = cos(pi 2t/N) - i sin(pi 2t/N); sin x = cos(x - pi/2)
+        tw[2 * t] = (double)cos_pi_frac(2L * t * 2, 2L * N);
+        tw[2 * t + 1] = (double)(-cos_pi_frac(2L * t * 2 - N, 2L * N));
+    }
+    double* d = nullptr;
+    CF_TRY(upload(tw, &d));
+    pl.tw = reinterpret_cast<double2*>(d);
+    pl.dev.tw = pl.tw;
+    auto res = ctx->fftplans.emplace(N, pl);
+    *out = &res.first->second.dev;
+    return 0;
+}
+
+int get_box(cfgpu_ctx ctx, int Nx, int Nz, int Kx, int Kz, const ModeBox** out) {
+    auto key = std::make_tuple(Nx, Nz, Kx, Kz);
+    auto it = ctx->boxes.find(key);
+    if (it != ctx->boxes.end()) {
+        *out = &it->second;
+        return 0;
+    }
+    ModeBox bx;
+    bx.Nx = Nx; bx.Nz = Nz; bx.Kx = Kx; bx.Kz = Kz;
+    const int nmx = 2 * Kx + 1, Nzpad = 2 * (Nz / 2 + 1);
+    std::vector<long> rs(nmx);
+    for (int mxi = 0; mxi < nmx; ++mxi) {
+        const int kx = mxi <= Kx ? mxi : mxi - nmx;
+        const int mx = kx >= 0 ? kx : Nx + kx;
+        rs[mxi] = (long)mx * Nzpad;
+    }
+    CF_CUDA(cudaMalloc((void**)&bx.runstart_full, nmx * sizeof(long)));
+    CF_CUDA(cudaMemcpy(bx.runstart_full, rs.data(), nmx * sizeof(long), cudaMemcpyHostToDevice));
+    auto res = ctx->boxes.emplace(key, bx);
+    *out = &res.first->second;
+    return 0;
+}
+
+void cheb_diff_host(const std::vector<double>& u, std::vector<double>& d, double a, double b) {
+    const int N = (int)u.size(), Nb = N - 1;
+    d.assign(N, 0.0);
+    if (Nb <= 0) return;
+    const double scale = 4.0 / (b - a);
+    d[Nb] = 0.0;
+    d[Nb - 1] = scale * Nb * u[Nb];
+    for (int n = Nb - 2; n >= 0; --n) d[n] = d[n + 2] + scale * (n + 1) * u[n + 1];
+    d[0] *= 0.5;
+}
+void cheb_to_physical_host(const std::vector<double>& c, std::vector<double>& u) {
+    const int N = (int)c.size(), Nb = N - 1;
+    u.assign(N, 0.0);
+    for (int j = 0; j < N; ++j) {
+        long double s = 0.0L;
+        for (int n = 0; n < N; ++n) s += (long double)c[n] * cos_pi_frac((long)j * n, Nb > 0 ? Nb : 1);
+        u[j] = (double)s;
+    }
+}
+
+}  // namespace cfgpu
+
+using namespace cfgpu;
+
+#define CF_ARG(cond, msg)            \
+    do {                             \
+        if (!(cond)) {               \
+            set_last_error(msg);     \
+            return 1;                \
+        }                            \
+    } while (0)
+
+extern "C" {
+
+const char* cfgpu_last_error(void) { return g_last_error.c_str(); }
+const char* cfgpu_version(void) {
+#ifdef CF_EMU
+    return "cfgpu 0.1 (CPU emulation build: tests only)";
+#else
+    return "cfgpu 0.1 (sm_100a)";
+#endif
+}
+
+int cfgpu_init(int device, cfgpu_ctx* out) {
+    CF_ARG(out, "cfgpu_init: null out");
+    int ndev = 0;
+    CF_CUDA(cudaGetDeviceCount(&ndev));
+    CF_ARG(ndev > 0, "cfgpu_init: no CUDA device visible (this library has no CPU fallback)");
+    CF_ARG(device >= 0 && device < ndev, "cfgpu_init: bad device index");
+    CF_CUDA(cudaSetDevice(device));
+    cfgpu_ctx ctx = new cfgpu_ctx_s();
+    ctx->device = device;
+    CF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CF_CUDA(cudaEventCreate(&ctx->ev0));
+    CF_CUDA(cudaEventCreate(&ctx->ev1));
+    *out = ctx;
+    return 0;
+}
+
+int cfgpu_finalize(cfgpu_ctx ctx) {
+    if (!ctx) return 0;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->yplans) {
+        YPlan& p = kv.second;
+        cudaFree(p.Ce); cudaFree(p.Co); cudaFree(p.CDe); cudaFree(p.CDo); cudaFree(p.Fe); cudaFree(p.Fo); cudaFree(p.Wgram);
+    }
+    for (auto& kv : ctx->fftplans) cudaFree(kv.second.tw);
+    for (auto& kv : ctx->boxes) cudaFree(kv.second.runstart_full);
+    if (ctx->ws_P.ptr) cudaFree(ctx->ws_P.ptr);
+    if (ctx->ws_Q.ptr) cudaFree(ctx->ws_Q.ptr);
+    if (ctx->ws_red.ptr) cudaFree(ctx->ws_red.ptr);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int cfgpu_sync(cfgpu_ctx ctx) {
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cfgpu_launch_count(cfgpu_ctx, long long* n) {
+    *n = g_launches;
+    return 0;
+}
+int cfgpu_timer_start(cfgpu_ctx ctx) {
+    CF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    return 0;
+}
+int cfgpu_timer_stop(cfgpu_ctx ctx, double* ms) {
+    CF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    CF_CUDA(cudaEventSynchronize(ctx->ev1));
+    float f = 0;
+    CF_CUDA(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+    *ms = f;
+    return 0;
+}
+
+#ifndef CF_EMU
+int cfgpu_graph_begin(cfgpu_ctx ctx) {
+    CF_ARG(!ctx->capturing, "graph capture already active");
+    CF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    return 0;
+}
+int cfgpu_graph_end(cfgpu_ctx ctx, int* graph_id) {
+    CF_ARG(ctx->capturing, "no graph capture active");
+    cudaGraph_t g = nullptr;
+    ctx->capturing = false;
+    CF_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+    cudaGraphExec_t ge = nullptr;
+    CF_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    ctx->graphs.push_back((void*)ge);
+    *graph_id = (int)ctx->graphs.size() - 1;
+    return 0;
+}
+int cfgpu_graph_launch(cfgpu_ctx ctx, int graph_id) {
+    CF_ARG(graph_id >= 0 && graph_id < (int)ctx->graphs.size(), "bad graph id");
+    CF_CUDA(cudaGraphLaunch((cudaGraphExec_t)ctx->graphs[graph_id], ctx->stream));
+    return 0;
+}
+#else
+int cfgpu_graph_begin(cfgpu_ctx) { set_last_error("graphs unavailable in the emulation build"); return 1; }
+int cfgpu_graph_end(cfgpu_ctx, int*) { set_last_error("graphs unavailable in the emulation build"); return 1; }
+int cfgpu_graph_launch(cfgpu_ctx, int) { set_last_error("graphs unavailable in the emulation build"); return 1; }
+#endif
+
+// ------------------------------------------------------------------------------------------------ fields
+int cfgpu_field_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, int Nd, double Lx, double Lz, double a, double b,
+                       cfgpu_field* out) {
+    CF_ARG(ctx && out, "cfgpu_field_create: null argument");
+    CF_ARG(Nx > 0 && Ny > 0 && Nz > 0 && Nd > 0, "cfgpu_field_create: bad dimensions");
+    cfgpu_field f = new cfgpu_field_s();
+    f->ctx = ctx;
+    f->Nx = Nx; f->Ny = Ny; f->Nz = Nz; f->Nd = Nd;
+    f->Lx = Lx; f->Lz = Lz; f->a = a; f->b = b;
+    f->n = (long long)Nx * Ny * f->Nzpad() * Nd;
+    if (cudaMalloc((void**)&f->d, f->n * sizeof(double)) != cudaSuccess) {
+        delete f;
+        set_last_error("cfgpu_field_create: cudaMalloc failed");
+        return 1;
+    }
+    CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), ctx->stream));
+    f->clean_Kx = 0; f->clean_Kz = 0;  // all zero
+    *out = f;
+    return 0;
+}
+int cfgpu_field_destroy(cfgpu_field f) {
+    if (!f) return 0;
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->d);
+    delete f;
+    return 0;
+}
+int cfgpu_field_upload(cfgpu_field f, const double* h, int xz, int y) {
+    CF_CUDA(cudaMemcpyAsync(f->d, h, f->n * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    f->xzstate = xz; f->ystate = y;
+    f->clean_Kx = f->clean_Kz = -1;
+    return 0;
+}
+int cfgpu_field_download(cfgpu_field f, double* h) {
+    CF_CUDA(cudaMemcpyAsync(h, f->d, f->n * sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return 0;
+}
+static bool same_shape(cfgpu_field a, cfgpu_field b) {
+    return a->Nx == b->Nx && a->Ny == b->Ny && a->Nz == b->Nz && a->Nd == b->Nd;
+}
+int cfgpu_field_copy(cfgpu_field dst, cfgpu_field src) {
+    CF_ARG(same_shape(dst, src), "cfgpu_field_copy: shape mismatch");
+    CF_CUDA(cudaMemcpyAsync(dst->d, src->d, src->n * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    dst->xzstate = src->xzstate; dst->ystate = src->ystate; dst->padded = src->padded;
+    dst->Lx = src->Lx; dst->Lz = src->Lz; dst->a = src->a; dst->b = src->b;
+    dst->clean_Kx = src->clean_Kx; dst->clean_Kz = src->clean_Kz;
+    return 0;
+}
+int cfgpu_field_swap(cfgpu_field a, cfgpu_field b) {
+    CF_ARG(same_shape(a, b), "cfgpu_field_swap: shape mismatch");
+    std::swap(a->d, b->d);
+    std::swap(a->xzstate, b->xzstate); std::swap(a->ystate, b->ystate); std::swap(a->padded, b->padded);
+    std::swap(a->clean_Kx, b->clean_Kx); std::swap(a->clean_Kz, b->clean_Kz);
+    return 0;
+}
+int cfgpu_field_zero(cfgpu_field f) {
+    CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), f->ctx->stream));
+    f->clean_Kx = 0; f->clean_Kz = 0;
+    return 0;
+}
+int cfgpu_field_set_state(cfgpu_field f, int xz, int y) { f->xzstate = xz; f->ystate = y; return 0; }
+int cfgpu_field_get_state(cfgpu_field f, int* xz, int* y) { *xz = f->xzstate; *y = f->ystate; return 0; }
+int cfgpu_field_set_padded(cfgpu_field f, int p) { f->padded = p; return 0; }
+int cfgpu_field_get_padded(cfgpu_field f, int* p) { *p = f->padded; return 0; }
+int cfgpu_field_device_ptr(cfgpu_field f, double** d, long long* n) { *d = f->d; if (n) *n = f->n; return 0; }
+
+int cfgpu_field_axpby(cfgpu_field y, double a, cfgpu_field x, double b, cfgpu_field z) {
+    CF_ARG(same_shape(y, x) && (!z || same_shape(y, z)), "cfgpu_field_axpby: shape mismatch");
+    CF_TRY(axpby_launch(y->d, a, x->d, b, z ? z->d : nullptr, (long)y->n, y->ctx->stream));
+    auto mrg = [](int p, int q) { return (p < 0 || q < 0) ? -1 : (p > q ? p : q); };
+    y->clean_Kx = mrg(y->clean_Kx, x->clean_Kx); y->clean_Kz = mrg(y->clean_Kz, x->clean_Kz);
+    if (z) { y->clean_Kx = mrg(y->clean_Kx, z->clean_Kx); y->clean_Kz = mrg(y->clean_Kz, z->clean_Kz); }
+    return 0;
+}
+int cfgpu_field_scale(cfgpu_field y, double s) {
+    CF_TRY(scale_launch(y->d, s, (long)y->n, y->ctx->stream));
+    return 0;
+}
+
+int cfgpu_field_get_profile(cfgpu_field f, int mx, int mz, int i, double* out_h) {
+    CF_ARG(mx >= 0 && mx < f->Nx && mz >= 0 && mz < f->Mz() && i >= 0 && i < f->Nd, "cfgpu_field_get_profile: index");
+    cfgpu_ctx ctx = f->ctx;
+    CF_TRY(ws_reserve(ctx->ws_red, 1 << 20));
+    const long off0 = (long)i * f->Ny * f->Nx * f->Mz() + mz + (long)f->Mz() * mx;
+    CF_TRY(profile_get_launch(f->d, off0, (long)f->Nx * f->Mz(), f->Ny, ctx->ws_red.ptr, ctx->stream));
+    CF_CUDA(cudaMemcpyAsync(out_h, ctx->ws_red.ptr, 2 * f->Ny * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cfgpu_field_add_profile(cfgpu_field f, int mx, int mz, int i, const double* in_h, double scale) {
+    CF_ARG(mx >= 0 && mx < f->Nx && mz >= 0 && mz < f->Mz() && i >= 0 && i < f->Nd, "cfgpu_field_add_profile: index");
+    cfgpu_ctx ctx = f->ctx;
+    CF_TRY(ws_reserve(ctx->ws_red, 1 << 20));
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    CF_CUDA(cudaMemcpyAsync(ctx->ws_red.ptr, in_h, 2 * f->Ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const long off0 = (long)i * f->Ny * f->Nx * f->Mz() + mz + (long)f->Mz() * mx;
+    CF_TRY(profile_add_launch(f->d, off0, (long)f->Nx * f->Mz(), f->Ny, ctx->ws_red.ptr, scale, ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cfgpu_field_zero_padded_modes(cfgpu_field f) {
+    const int Kx = f->Nx / 3 - 1, Kz = f->Nz / 3 - 1;  // flowfield.h:578-584
+    CF_TRY(zero_padded_launch(f->d, f->Nx, f->Ny, f->Nz, f->Nd, Kx, Kz, f->ctx->stream));
+    f->padded = 1;
+    f->clean_Kx = Kx; f->clean_Kz = Kz;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ generic y transform
+static int y_transform(cfgpu_field f, int mode) {
+    const YPlan* pl;
+    CF_TRY(get_yplan(f->ctx, f->Ny, f->a, f->b, &pl));
+    const long ncols = f->rowstride();
+    for (int i0 = 0; i0 < f->Nd; i0 += YG_MAXJOB) {
+        YGemmParams p;
+        memset(&p, 0, sizeof p);
+        p.N = f->Ny; p.mode = mode;
+        if (mode == 0) {
+            p.M = p.M2 = pl->Nh; p.K1 = pl->Ne; p.K2 = pl->No; p.K1p = pl->invK1p; p.K2p = pl->invK2p;
+            p.A1[0] = pl->Ce; p.A2[0] = pl->Co; p.sgn[0] = 1.0;
+        } else {
+            p.M = pl->Ne; p.M2 = pl->No; p.K1 = p.K2 = pl->Nh; p.K1p = p.K2p = pl->fwdKp;
+            p.A1[0] = pl->Fe; p.A2[0] = pl->Fo; p.sgn[0] = 1.0;
+        }
+        p.ncols = ncols;
+        p.in_runlen = 1; p.in_runstart = nullptr; p.in_ld = ncols;
+        p.out_runlen = 1; p.out_runstart = nullptr; p.out_ld = ncols;
+        p.njobs = 0;
+        for (int i = i0; i < f->Nd && p.njobs < YG_MAXJOB; ++i) {
+            YGemmJob& j = p.job[p.njobs++];
+            j.in = f->d + i * f->compstride();
+            j.out[0] = f->d + i * f->compstride();
+            j.nmat = 1; j.mat0 = 0;
+        }
+        CF_TRY(ygemm_launch(p, f->ctx->stream));
+    }
+    f->clean_Kx = f->clean_Kz = -1;
+    return 0;
+}
+int cfgpu_field_make_physical_y(cfgpu_field f) {
+    if (f->ystate == CFGPU_PHYSICAL) return 0;
+    if (f->Ny >= 2) CF_TRY(y_transform(f, 0));
+    f->ystate = CFGPU_PHYSICAL;
+    return 0;
+}
+int cfgpu_field_make_spectral_y(cfgpu_field f) {
+    if (f->ystate == CFGPU_SPECTRAL) return 0;
+    if (f->Ny >= 2) CF_TRY(y_transform(f, 1));
+    f->ystate = CFGPU_SPECTRAL;
+    return 0;
+}
+
+// generic xz transforms live in cfgpu_xzgen.cu
+int cfgpu_xz_generic(cfgpu_field f, int to_physical);
+int cfgpu_field_make_physical_xz(cfgpu_field f) {
+    if (f->xzstate == CFGPU_PHYSICAL) return 0;
+    CF_TRY(cfgpu_xz_generic(f, 1));
+    f->xzstate = CFGPU_PHYSICAL;
+    f->clean_Kx = f->clean_Kz = -1;
+    return 0;
+}
+int cfgpu_field_make_spectral_xz(cfgpu_field f) {
+    if (f->xzstate == CFGPU_SPECTRAL) return 0;
+    CF_TRY(cfgpu_xz_generic(f, 0));
+    f->xzstate = CFGPU_SPECTRAL;
+    f->clean_Kx = f->clean_Kz = -1;
+    return 0;
+}
+int cfgpu_field_make_physical(cfgpu_field f) {
+    CF_TRY(cfgpu_field_make_physical_y(f));
+    return cfgpu_field_make_physical_xz(f);
+}
+int cfgpu_field_make_spectral(cfgpu_field f) {
+    CF_TRY(cfgpu_field_make_spectral_xz(f));
+    return cfgpu_field_make_spectral_y(f);
+}
+
+// ------------------------------------------------------------------------------------------------ norms
+static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool padded, double* out_h) {
+    CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "L2 norm: field must be spectral");
+    cfgpu_ctx ctx = u->ctx;
+    const YPlan* pl;
+    CF_TRY(get_yplan(ctx, u->Ny, u->a, u->b, &pl));
+    CF_TRY(ws_reserve(ctx->ws_red, 1 << 20));
+    double scale = 1.0;
+    if (!normalize) scale = (u->b - u->a) * u->Lx * u->Lz;
+    const int Kx = u->Nx / 3 - 1, Kz = u->Nz / 3 - 1;
+    double* out_dev = ctx->ws_red.ptr;
+    double* partial = ctx->ws_red.ptr + 8;
+    const size_t cap = ctx->ws_red.bytes / sizeof(double) - 8;
+    CF_TRY(l2form_launch(u->d, v ? v->d : nullptr, mode, pl->Wgram, u->Ny, u->Nx, u->Nz, u->Nd, Kx, Kz, padded ? 0 : 1, scale,
+                         partial, cap, out_dev, ctx->stream));
+    CF_CUDA(cudaMemcpyAsync(out_h, out_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cfgpu_l2norm2(cfgpu_field u, int normalize, double* out_h) { return l2form(u, nullptr, 0, normalize, u->padded != 0, out_h); }
+int cfgpu_l2dist2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h) {
+    CF_ARG(same_shape(u, v), "L2Dist2: shape mismatch");
+    return l2form(u, v, 1, normalize, u->padded && v->padded, out_h);
+}
+int cfgpu_l2ip(cfgpu_field u, cfgpu_field v, int normalize, double* out_h) {
+    CF_ARG(same_shape(u, v), "L2InnerProduct: shape mismatch");
+    return l2form(u, v, 2, normalize, u->padded || v->padded, out_h);
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// Internal structures behind the opaque C-ABI handles of include/cfgpu.h.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/cfgpu.h"
+#include "cf_common.cuh"
+#include "fft_smem.cuh"
+#include "tau.cuh"
+#include "xzpass.cuh"
+#include "ygemm.cuh"
+
+namespace cfgpu {
+
+struct YPlan {
+    int N = 0;
+    double a = 0, b = 0;
+    int Nh = 0, Ne = 0, No = 0;
+    int invMp = 0, invK1p = 0, invK2p = 0;
+    int fwdMp = 0, fwdKp = 0;
+    double *Ce = nullptr, *Co = nullptr, *CDe = nullptr, *CDo = nullptr, *Fe = nullptr, *Fo = nullptr;
+    double* Wgram = nullptr;  // [N][N] Chebyshev Gram weights for the L2 norms
+};
+
+struct FftPlanHost {
+    FftPlanDev dev;
+    double2* tw = nullptr;
+};
+
+// retained-mode bookkeeping for one (Nx,Nz,Kx,Kz)
+struct ModeBox {
+    int Nx, Nz, Kx, Kz;
+    long* runstart_full = nullptr;  // device [2Kx+1]: offset (doubles) of the kz-run of retained mx in a field row
+};
+
+struct Workspace {
+    size_t bytes = 0;
+    double* ptr = nullptr;
+};
+
+}  // namespace cfgpu
+
+struct cfgpu_ctx_s {
+    int device = 0;
+    cudaStream_t stream = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::map<std::tuple<int, double, double>, cfgpu::YPlan> yplans;
+    std::map<int, cfgpu::FftPlanHost> fftplans;
+    std::map<std::tuple<int, int, int, int>, cfgpu::ModeBox> boxes;
+    cfgpu::Workspace ws_P, ws_Q, ws_red;
+    std::vector<void*> graphs;  // cudaGraphExec_t
+    bool capturing = false;
+};
+
+struct cfgpu_field_s {
+    cfgpu_ctx ctx = nullptr;
+    int Nx = 0, Ny = 0, Nz = 0, Nd = 0;
+    double Lx = 0, Lz = 0, a = 0, b = 0;
+    int xzstate = CFGPU_SPECTRAL, ystate = CFGPU_SPECTRAL;
+    int padded = 0;
+    int clean_Kx = -1, clean_Kz = -1;  // all modes outside this box are known to be exactly zero (-1: unknown)
+    double* d = nullptr;
+    long long n = 0;  // doubles
+    int Nzpad() const { return 2 * (Nz / 2 + 1); }
+    int Mz() const { return Nz / 2 + 1; }
+    long long rowstride() const { return (long long)Nx * Nzpad(); }
+    long long compstride() const { return rowstride() * Ny; }
+};
+
+struct cfgpu_nse_s {
+    cfgpu_ctx ctx = nullptr;
+    int Nx = 0, Ny = 0, Nz = 0;
+    double Lx = 0, Lz = 0, a = 0, b = 0;
+    cfgpu_nse_config cfg;
+    int Nyd = 0, Kx = 0, Kz = 0;
+    int nq = 0, ldq = 0;
+    cfgpu::ModeGeom geom;
+    double* d_base = nullptr;   // device: Ubaseyy[Ny], Wbaseyy[Ny], phys U,U',W,W' [4*Ny], inv_dy[Ny]
+    bool has_Ubaseyy = false, has_Wbaseyy = false;
+    double lin_base_dPdx = 0, lin_base_dPdz = 0;  // nu*(Ubase'(b)-Ubase'(a))/Ly (nse.cpp:464-469)
+    double* d_scal = nullptr;   // device scalars: [0] cfl max, [1] dPdxAct, [2] dPdzAct
+    std::vector<double> lambda_t;
+    std::vector<cfgpu::TauData> tau;  // one per substep
+    int TM_solve = 8, TM_setup = 8;
+};
+
+namespace cfgpu {
+int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out);
+int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out);
+int get_box(cfgpu_ctx ctx, int Nx, int Nz, int Kx, int Kz, const ModeBox** out);
+int ws_reserve(Workspace& w, size_t bytes);
+// host-side Chebyshev helpers (long double internally)
+void cheb_diff_host(const std::vector<double>& u, std::vector<double>& d, double a, double b);
+void cheb_to_physical_host(const std::vector<double>& c, std::vector<double>& u);
+}  // namespace cfgpu

@@ -1,0 +1,350 @@
+// NSE operator entry points of the C-ABI (include/cfgpu.h): nonlinear term pipeline, batched tau solve,
+// linear term, CFL.  Host orchestration only; the kernels are in ygemm.cu, xzpass.cu, tau.cu.
+#include <cmath>
+#include <cstring>
+
+#include "cfgpu_internal.h"
+#include "fieldops.cuh"
+
+using namespace cfgpu;
+
+#define CF_ARG(cond, msg)        \
+    do {                         \
+        if (!(cond)) {           \
+            set_last_error(msg); \
+            return 1;            \
+        }                        \
+    } while (0)
+
+namespace cfgpu {
+int linear_launch(const TauSolveParams& p, const double* u, const double* q, double* L, cudaStream_t stream);
+}
+
+static int pick_TZ(int Nx) {
+    int tz = 2304 / Nx;
+    int p = 16;
+    while (p > tz && p > 2) p >>= 1;
+    return p;
+}
+static int pick_TL(int Nx, int Nz, int npair) {
+    // 2 buffers * Nz * npair*TL * 16 B <= ~96 KB
+    int tl = 16;
+    while (tl > 1 && (size_t)2 * Nz * npair * tl * 16 > 96 * 1024) tl >>= 1;
+    while (tl > 1 && Nx % tl) tl >>= 1;
+    return tl;
+}
+
+// spectral u (3 comps, reference layout) -> compact pencils P[0..nout) (y physical), then Q (x physical)
+static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
+    cfgpu_ctx ctx = nse->ctx;
+    const YPlan* yp;
+    const ModeBox* bx;
+    const FftPlanDev* fx;
+    CF_TRY(get_yplan(ctx, nse->Ny, nse->a, nse->b, &yp));
+    CF_TRY(get_box(ctx, nse->Nx, nse->Nz, nse->Kx, nse->Kz, &bx));
+    CF_TRY(get_fftplan(ctx, nse->Nx, &fx));
+    const int nmx = 2 * nse->Kx + 1, nkz = nse->Kz + 1;
+    const size_t Pf = (size_t)nse->Ny * nmx * nkz * 2;      // doubles per pencil field P
+    const size_t Qf = (size_t)nse->Ny * nse->Nx * nkz * 2;  // doubles per pencil field Q
+    CF_TRY(ws_reserve(ctx->ws_P, 5 * Pf * sizeof(double)));
+    CF_TRY(ws_reserve(ctx->ws_Q, 7 * Qf * sizeof(double)));
+    double* P = ctx->ws_P.ptr;
+
+    YGemmParams p;
+    memset(&p, 0, sizeof p);
+    p.N = nse->Ny; p.mode = 0;
+    p.M = p.M2 = yp->Nh; p.K1 = yp->Ne; p.K2 = yp->No; p.K1p = yp->invK1p; p.K2p = yp->invK2p;
+    p.A1[0] = yp->Ce; p.A2[0] = yp->Co; p.sgn[0] = 1.0;
+    p.A1[1] = yp->CDe; p.A2[1] = yp->CDo; p.sgn[1] = -1.0;
+    p.ncols = (long)nmx * nkz * 2;
+    p.in_runlen = 2 * nkz; p.in_runstart = bx->runstart_full; p.in_ld = u->rowstride();
+    p.out_runlen = 1; p.out_runstart = nullptr; p.out_ld = (long)nmx * nkz * 2;
+    p.njobs = 3;
+    for (int i = 0; i < 3; ++i) {
+        p.job[i].in = u->d + i * u->compstride();
+        p.job[i].out[0] = P + i * Pf;
+        p.job[i].nmat = 1; p.job[i].mat0 = 0;
+    }
+    if (with_derivs) {
+        p.job[0].nmat = 2; p.job[0].out[1] = P + 3 * Pf;  // du/dy
+        p.job[2].nmat = 2; p.job[2].out[1] = P + 4 * Pf;  // dw/dy
+    }
+    CF_TRY(ygemm_launch(p, ctx->stream));
+
+    XPassParams xp;
+    memset(&xp, 0, sizeof xp);
+    xp.Nx = nse->Nx; xp.Ny = nse->Ny; xp.Kx = nse->Kx; xp.Kz = nse->Kz;
+    xp.TZ = pick_TZ(nse->Nx);
+    xp.Lx = nse->Lx;
+    xp.plan = *fx;
+    xp.in = reinterpret_cast<const double2*>(P);
+    xp.out = reinterpret_cast<double2*>(ctx->ws_Q.ptr);
+    xp.ny0 = 0; xp.nyn = nse->Ny;
+    if (with_derivs) {
+        const int src[7] = {0, 1, 2, 3, 4, 1, 2}, ddx[7] = {0, 0, 0, 0, 0, 1, 1};
+        xp.nfields = 7;
+        for (int i = 0; i < 7; ++i) { xp.src[i] = src[i]; xp.ddx[i] = ddx[i]; }
+    } else {
+        xp.nfields = 3;
+        for (int i = 0; i < 3; ++i) { xp.src[i] = i; xp.ddx[i] = 0; }
+    }
+    CF_TRY(xpass_inverse_launch(xp, ctx->stream));
+    return 0;
+}
+
+static int fill_zpass(cfgpu_nse nse, ZPassParams& zp, int mode) {
+    const FftPlanDev* fz;
+    CF_TRY(get_fftplan(nse->ctx, nse->Nz, &fz));
+    memset(&zp, 0, sizeof zp);
+    zp.Nx = nse->Nx; zp.Ny = nse->Ny; zp.Nz = nse->Nz; zp.Kz = nse->Kz;
+    zp.mode = mode;
+    zp.TL = pick_TL(nse->Nx, nse->Nz, mode == ZP_ROTATIONAL ? 5 : 2);
+    zp.Lx = nse->Lx; zp.Lz = nse->Lz;
+    zp.scale = 1.0 / ((double)nse->Nx * (double)nse->Nz);
+    zp.Vsuck = nse->cfg.Vsuck;
+    zp.rotation = nse->cfg.rotation;
+    zp.plan = *fz;
+    zp.Q = reinterpret_cast<const double2*>(nse->ctx->ws_Q.ptr);
+    zp.F = reinterpret_cast<double2*>(nse->ctx->ws_Q.ptr);  // in place: a CTA overwrites only lines it has consumed
+    zp.Uy = nse->d_base + 2 * nse->Ny;
+    zp.inv_dy = nse->d_base + 6 * nse->Ny;
+    zp.cfl_max = nse->d_scal;
+    zp.ny0 = 0; zp.nyn = nse->Ny;
+    return 0;
+}
+
+extern "C" {
+
+int cfgpu_nse_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, double Lx, double Lz, double a, double b,
+                     const cfgpu_nse_config* cfg, const double* Ubase_h, const double* Wbase_h, cfgpu_nse* out) {
+    CF_ARG(ctx && cfg && out, "cfgpu_nse_create: null argument");
+    CF_ARG(Ny % 2 == 1 && Ny >= 5, "cfgpu_nse_create: Ny must be odd and >= 5 (helmholtz.cpp:31)");
+    CF_ARG(cfg->nonlinearity == 0, "cfgpu_nse_create: only the Rotational nonlinearity is implemented in this build");
+    cfgpu_nse nse = new cfgpu_nse_s();
+    nse->ctx = ctx;
+    nse->Nx = Nx; nse->Ny = Ny; nse->Nz = Nz; nse->Lx = Lx; nse->Lz = Lz; nse->a = a; nse->b = b;
+    nse->cfg = *cfg;
+    nse->Nyd = cfg->dealias_y ? 2 * (Ny - 1) / 3 + 1 : Ny;              // nse.cpp:228
+    nse->Kx = cfg->dealias_xz ? Nx / 3 - 1 : Nx / 2 - 1;                // nse.cpp:229-230, 498 (kxmax mode is skipped)
+    nse->Kz = cfg->dealias_xz ? Nz / 3 - 1 : Nz / 2 - 1;
+    if (Nx % 2 == 1 && !cfg->dealias_xz) nse->Kx = Nx / 2 - 1;
+    CF_ARG(nse->Kx >= 0 && nse->Kz >= 0, "cfgpu_nse_create: grid too small");
+    CF_ARG(nse->Nyd % 2 == 1, "cfgpu_nse_create: dealiased Ny must be odd");
+    nse->nq = (2 * nse->Kx + 1) * (nse->Kz + 1);
+    nse->ldq = (nse->nq + 31) & ~31;
+    nse->geom.Nx = Nx; nse->geom.Ny = Ny; nse->geom.Nz = Nz; nse->geom.Kx = nse->Kx; nse->geom.Kz = nse->Kz;
+    nse->geom.Lx = Lx; nse->geom.Lz = Lz;
+    nse->TM_solve = tau_pick_TM(nse->Nyd, 6 * 2 * 8);
+    nse->TM_setup = tau_pick_TM(nse->Nyd, 3 * 8);
+
+    // base-flow data: Ubaseyy, Wbaseyy (spectral), physical U,U',W,W', 1/dy
+    std::vector<double> U(Ny, 0.0), W(Ny, 0.0), Uy, Uyy, Wy, Wyy, t;
+    if (Ubase_h) U.assign(Ubase_h, Ubase_h + Ny);
+    if (Wbase_h) W.assign(Wbase_h, Wbase_h + Ny);
+    cheb_diff_host(U, Uy, a, b); cheb_diff_host(Uy, Uyy, a, b);
+    cheb_diff_host(W, Wy, a, b); cheb_diff_host(Wy, Wyy, a, b);
+    {
+        double ub = 0, ua = 0, wb = 0, wa = 0;
+        for (int n = Ny - 1; n >= 0; --n) {
+            ub += Uy[n]; ua += Uy[n] * ((n % 2 == 0) ? 1 : -1);
+            wb += Wy[n]; wa += Wy[n] * ((n % 2 == 0) ? 1 : -1);
+        }
+        nse->lin_base_dPdx = Ubase_h ? cfg->nu * (ub - ua) / (b - a) : 0.0;
+        nse->lin_base_dPdz = Wbase_h ? cfg->nu * (wb - wa) / (b - a) : 0.0;
+    }
+    nse->has_Ubaseyy = Ubase_h != nullptr;
+    nse->has_Wbaseyy = Wbase_h != nullptr;
+    std::vector<double> hb(7 * (size_t)Ny, 0.0);
+    for (int n = 0; n < Ny; ++n) { hb[n] = Uyy[n]; hb[Ny + n] = Wyy[n]; }
+    cheb_to_physical_host(U, t);  for (int n = 0; n < Ny; ++n) hb[2 * Ny + n] = t[n];
+    cheb_to_physical_host(Uy, t); for (int n = 0; n < Ny; ++n) hb[3 * Ny + n] = t[n];
+    cheb_to_physical_host(W, t);  for (int n = 0; n < Ny; ++n) hb[4 * Ny + n] = t[n];
+    cheb_to_physical_host(Wy, t); for (int n = 0; n < Ny; ++n) hb[5 * Ny + n] = t[n];
+    {
+        const double pi = 3.14159265358979323846;
+        std::vector<double> y(Ny);
+        for (int n = 0; n < Ny; ++n) y[n] = 0.5 * ((b + a) + (b - a) * cos(pi * n / (Ny - 1)));  // flowfield.h:483
+        for (int n = 0; n < Ny; ++n) {
+            const double dy = (n == 0 || n == Ny - 1) ? y[0] - y[1] : (y[n - 1] - y[n + 1]) / 2.0;  // flowfield.cpp:4051
+            hb[6 * Ny + n] = 1.0 / dy;
+        }
+    }
+    if (cudaMalloc((void**)&nse->d_base, hb.size() * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&nse->d_scal, 8 * sizeof(double)) != cudaSuccess) {
+        set_last_error("cfgpu_nse_create: cudaMalloc failed");
+        delete nse;
+        return 1;
+    }
+    CF_CUDA(cudaMemcpy(nse->d_base, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CF_CUDA(cudaMemset(nse->d_scal, 0, 8 * sizeof(double)));
+    *out = nse;
+    return 0;
+}
+
+int cfgpu_nse_destroy(cfgpu_nse nse) {
+    if (!nse) return 0;
+    cudaStreamSynchronize(nse->ctx->stream);
+    for (auto& t : nse->tau) cudaFree(t.base);
+    cudaFree(nse->d_base);
+    cudaFree(nse->d_scal);
+    delete nse;
+    return 0;
+}
+
+int cfgpu_nse_set_constraint(cfgpu_nse nse, int constraint, double dPdxRef, double dPdzRef, double UbR, double WbR) {
+    nse->cfg.constraint = constraint;
+    nse->cfg.dPdxRef = dPdxRef; nse->cfg.dPdzRef = dPdzRef;
+    nse->cfg.UbulkRef_minus_base = UbR; nse->cfg.WbulkRef_minus_base = WbR;
+    return 0;
+}
+
+int cfgpu_nse_reset_lambda(cfgpu_nse nse, const double* lambda_t_h, int nsub) {
+    CF_ARG(nsub > 0, "cfgpu_nse_reset_lambda: nsub");
+    cfgpu_ctx ctx = nse->ctx;
+    while ((int)nse->tau.size() < nsub) {
+        TauData td;
+        td.N = nse->Nyd; td.nq = nse->nq; td.ldq = nse->ldq; td.nu = nse->cfg.nu; td.a = nse->a; td.b = nse->b;
+        const size_t n = TauData::doubles(td.N, td.ldq);
+        if (cudaMalloc((void**)&td.base, n * sizeof(double)) != cudaSuccess) {
+            set_last_error("cfgpu_nse_reset_lambda: cudaMalloc failed");
+            return 1;
+        }
+        CF_CUDA(cudaMemsetAsync(td.base, 0, n * sizeof(double), ctx->stream));
+        nse->tau.push_back(td);
+    }
+    nse->lambda_t.assign(lambda_t_h, lambda_t_h + nsub);
+    for (int s = 0; s < nsub; ++s) {
+        nse->tau[s].nu = nse->cfg.nu;
+        CF_TRY(tau_setup_launch(nse->tau[s], nse->geom, lambda_t_h[s], nse->TM_setup, ctx->stream));
+    }
+    return 0;
+}
+
+int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
+    CF_ARG(u->Nd == 3 && f->Nd == 3, "cfgpu_nse_nonlinear: fields must have 3 components");
+    CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "cfgpu_nse_nonlinear: u must be spectral");
+    cfgpu_ctx ctx = nse->ctx;
+    CF_TRY(inverse_to_Q(nse, u, true));
+
+    ZPassParams zp;
+    CF_TRY(fill_zpass(nse, zp, ZP_ROTATIONAL));
+    CF_CUDA(cudaMemsetAsync(nse->d_scal, 0, sizeof(double), ctx->stream));
+    CF_TRY(zpass_launch(zp, ctx->stream));
+
+    const FftPlanDev* fx;
+    CF_TRY(get_fftplan(ctx, nse->Nx, &fx));
+    XPassParams xp;
+    memset(&xp, 0, sizeof xp);
+    xp.Nx = nse->Nx; xp.Ny = nse->Ny; xp.Kx = nse->Kx; xp.Kz = nse->Kz;
+    xp.TZ = pick_TZ(nse->Nx);
+    xp.Lx = nse->Lx;
+    xp.plan = *fx;
+    xp.nfields = 3;
+    xp.in = reinterpret_cast<const double2*>(ctx->ws_Q.ptr);
+    xp.out = reinterpret_cast<double2*>(ctx->ws_P.ptr);
+    xp.ny0 = 0; xp.nyn = nse->Ny;
+    CF_TRY(xpass_forward_launch(xp, ctx->stream));
+
+    // aliased modes of f must be exactly zero (FlowField::zeroPaddedModes, nse.cpp:389-390); the kernels below
+    // only ever write retained modes
+    if (!(f->clean_Kx >= 0 && f->clean_Kx <= nse->Kx && f->clean_Kz >= 0 && f->clean_Kz <= nse->Kz))
+        CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), ctx->stream));
+
+    const YPlan* yp;
+    const ModeBox* bx;
+    CF_TRY(get_yplan(ctx, nse->Ny, nse->a, nse->b, &yp));
+    CF_TRY(get_box(ctx, nse->Nx, nse->Nz, nse->Kx, nse->Kz, &bx));
+    const int nmx = 2 * nse->Kx + 1, nkz = nse->Kz + 1;
+    const size_t Pf = (size_t)nse->Ny * nmx * nkz * 2;
+    YGemmParams p;
+    memset(&p, 0, sizeof p);
+    p.N = nse->Ny; p.mode = 1;
+    p.M = yp->Ne; p.M2 = yp->No; p.K1 = p.K2 = yp->Nh; p.K1p = p.K2p = yp->fwdKp;
+    p.A1[0] = yp->Fe; p.A2[0] = yp->Fo; p.sgn[0] = 1.0;
+    p.ncols = (long)nmx * nkz * 2;
+    p.in_runlen = 1; p.in_runstart = nullptr; p.in_ld = (long)nmx * nkz * 2;
+    p.out_runlen = 2 * nkz; p.out_runstart = bx->runstart_full; p.out_ld = f->rowstride();
+    p.njobs = 3;
+    for (int i = 0; i < 3; ++i) {
+        p.job[i].in = ctx->ws_P.ptr + i * Pf;
+        p.job[i].out[0] = f->d + i * f->compstride();
+        p.job[i].nmat = 1; p.job[i].mat0 = 0;
+    }
+    CF_TRY(ygemm_launch(p, ctx->stream));
+    f->xzstate = CFGPU_SPECTRAL; f->ystate = CFGPU_SPECTRAL;
+    f->clean_Kx = nse->Kx; f->clean_Kz = nse->Kz;
+    if (nse->cfg.dealias_xz) f->padded = 1;
+    return 0;
+}
+
+static int fill_tau_params(cfgpu_nse nse, int s, TauSolveParams& tp) {
+    CF_ARG(s >= 0 && s < (int)nse->tau.size() && s < (int)nse->lambda_t.size(), "substep index out of range (call reset_lambda first)");
+    memset(&tp, 0, sizeof tp);
+    tp.td = nse->tau[s];
+    tp.g = nse->geom;
+    tp.TM = nse->TM_solve;
+    tp.taucorr = nse->cfg.taucorrection;
+    tp.Ubaseyy = nse->has_Ubaseyy ? nse->d_base : nullptr;
+    tp.Wbaseyy = nse->has_Wbaseyy ? nse->d_base + nse->Ny : nullptr;
+    tp.constraint = nse->cfg.constraint;
+    tp.dPdxRef = nse->cfg.dPdxRef; tp.dPdzRef = nse->cfg.dPdzRef;
+    tp.umean_target = nse->cfg.UbulkRef_minus_base; tp.wmean_target = nse->cfg.WbulkRef_minus_base;
+    tp.dPd_act = nse->d_scal + 1;
+    tp.lin_base_dPdx = nse->lin_base_dPdx; tp.lin_base_dPdz = nse->lin_base_dPdz;
+    return 0;
+}
+
+int cfgpu_nse_solve(cfgpu_nse nse, int s, int nterms, const double* coef_h, const cfgpu_field* terms, cfgpu_field uout,
+                    cfgpu_field qout) {
+    CF_ARG(nterms >= 1 && nterms <= TAU_MAXTERMS, "cfgpu_nse_solve: 1..10 terms");
+    CF_ARG(uout->Nd == 3 && qout->Nd == 1, "cfgpu_nse_solve: uout must have 3 components, qout 1");
+    TauSolveParams tp;
+    CF_TRY(fill_tau_params(nse, s, tp));
+    tp.nterms = nterms;
+    for (int j = 0; j < nterms; ++j) {
+        CF_ARG(terms[j]->Nd == 3 && terms[j]->Nx == nse->Nx && terms[j]->Ny == nse->Ny && terms[j]->Nz == nse->Nz,
+               "cfgpu_nse_solve: term shape mismatch");
+        tp.term[j] = terms[j]->d;
+        tp.coef[j] = coef_h[j];
+    }
+    tp.uout = uout->d;
+    tp.qout = qout->d;
+    CF_TRY(tau_solve_launch(tp, nse->ctx->stream));
+    uout->xzstate = uout->ystate = qout->xzstate = qout->ystate = CFGPU_SPECTRAL;
+    return 0;
+}
+
+int cfgpu_nse_linear(cfgpu_nse nse, cfgpu_field u, cfgpu_field q, cfgpu_field L) {
+    CF_ARG(u->Nd == 3 && q->Nd == 1 && L->Nd == 3, "cfgpu_nse_linear: shapes");
+    CF_ARG(!nse->tau.empty(), "cfgpu_nse_linear: call reset_lambda first");
+    TauSolveParams tp;
+    CF_TRY(fill_tau_params(nse, 0, tp));
+    CF_TRY(linear_launch(tp, u->d, q->d, L->d, nse->ctx->stream));
+    L->xzstate = L->ystate = CFGPU_SPECTRAL;
+    return 0;
+}
+
+int cfgpu_nse_cflfactor(cfgpu_nse nse, cfgpu_field u, double* out_h) {
+    CF_ARG(u->Nd == 3, "cfgpu_nse_cflfactor: 3 components");
+    CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "cfgpu_nse_cflfactor: u must be spectral");
+    cfgpu_ctx ctx = nse->ctx;
+    CF_TRY(inverse_to_Q(nse, u, false));
+    ZPassParams zp;
+    CF_TRY(fill_zpass(nse, zp, ZP_CFL));
+    CF_CUDA(cudaMemsetAsync(nse->d_scal, 0, sizeof(double), ctx->stream));
+    CF_TRY(zpass_launch(zp, ctx->stream));
+    CF_CUDA(cudaMemcpyAsync(out_h, nse->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int cfgpu_nse_get_dPd(cfgpu_nse nse, double* dPdx_h, double* dPdz_h) {
+    double v[2];
+    CF_CUDA(cudaMemcpyAsync(v, nse->d_scal + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, nse->ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(nse->ctx->stream));
+    *dPdx_h = v[0];
+    *dPdz_h = v[1];
+    return 0;
+}
+
+}  // extern "C"

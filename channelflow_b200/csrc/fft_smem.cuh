@@ -1,0 +1,119 @@
+// Shared-memory Stockham FFT used by the x- and z-pass kernels (replaces the FFTW rank-2 r2c/c2r plans of the
+// reference, flowfield.cpp:624-649, executed at :1853 and :1883).
+//
+// Data layout in shared memory: buf[n * C + c], n = position along the transformed direction, c = one of C
+// independent transforms handled by the CTA ("columns").  Threads are mapped (butterfly j, column c) with c
+// fastest, so every load/store of a pass touches consecutive 16-byte words.  Mixed radix 4/2/3/5, autosort
+// (no bit reversal), ping-pong between two buffers.  Twiddles come from a table exp(-2 pi i t / N) computed on
+// the host in long double (read through the read-only cache); the inverse transform conjugates them.
+// Unnormalised, FFTW sign convention: DIR=-1 forward (exp(-i..)), DIR=+1 backward.
+#pragma once
+#include "cf_common.cuh"
+
+namespace cfgpu {
+
+constexpr int FFT_MAXPASS = 16;
+
+struct FftPlanDev {
+    int N;
+    int npass;
+    int radix[FFT_MAXPASS];
+    const double2* tw;  // N entries
+};
+
+template <int DIR>
+__device__ __forceinline__ double2 tw_mul(double2 v, double2 w) {
+    // v * w (forward) or v * conj(w) (backward)
+    if (DIR < 0) return make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+    return make_double2(v.x * w.x + v.y * w.y, v.y * w.x - v.x * w.y);
+}
+// multiply by -i (forward) / +i (backward)
+template <int DIR>
+__device__ __forceinline__ double2 rot90(double2 v) {
+    if (DIR < 0) return make_double2(v.y, -v.x);
+    return make_double2(-v.y, v.x);
+}
+__device__ __forceinline__ double2 operator+(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 operator-(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 operator*(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+
+// One Stockham pass of radix R over all C columns. Ns = product of the radices of the previous passes.
+template <int DIR, int R>
+__device__ __forceinline__ void fft_pass(const double2* __restrict__ a, double2* __restrict__ b, const FftPlanDev& pl,
+                                         int Ns, int C, int tid, int nthreads) {
+    const int N = pl.N;
+    const int nb = N / R;
+    const int tstep = N / (Ns * R);
+    const int total = nb * C;
+    for (int idx = tid; idx < total; idx += nthreads) {
+        const int j = idx / C, c = idx - j * C;
+        const int k = j % Ns;
+        double2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = a[(j + r * nb) * C + c];
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = tw_mul<DIR>(v[r], __ldg(&pl.tw[r * k * tstep]));
+        }
+        if (R == 2) {
+            double2 t = v[0] - v[1];
+            v[0] = v[0] + v[1];
+            v[1] = t;
+        } else if (R == 4) {
+            double2 s02 = v[0] + v[2], d02 = v[0] - v[2], s13 = v[1] + v[3], d13 = rot90<DIR>(v[1] - v[3]);
+            v[0] = s02 + s13;
+            v[1] = d02 + d13;
+            v[2] = s02 - s13;
+            v[3] = d02 - d13;
+        } else if (R == 3) {
+            const double wi = (DIR < 0 ? -1.0 : 1.0) * 0.86602540378443864676372317075294;  // sin(2 pi/3)
+            double2 s = v[1] + v[2], d = v[1] - v[2];
+            double2 t = make_double2(v[0].x - 0.5 * s.x, v[0].y - 0.5 * s.y);
+            double2 u = make_double2(-wi * d.y, wi * d.x);
+            v[0] = v[0] + s;
+            v[1] = t + u;
+            v[2] = t - u;
+        } else if (R == 5) {
+            const double c1 = 0.30901699437494742410229341718282, c2 = -0.80901699437494742410229341718282;
+            const double sg = (DIR < 0 ? -1.0 : 1.0);
+            const double s1 = sg * 0.95105651629515357211643933337938, s2 = sg * 0.58778525229247312916870595463907;
+            double2 s14 = v[1] + v[4], d14 = v[1] - v[4], s23 = v[2] + v[3], d23 = v[2] - v[3];
+            double2 t1 = make_double2(v[0].x + c1 * s14.x + c2 * s23.x, v[0].y + c1 * s14.y + c2 * s23.y);
+            double2 t2 = make_double2(v[0].x + c2 * s14.x + c1 * s23.x, v[0].y + c2 * s14.y + c1 * s23.y);
+            double2 q1 = make_double2(s1 * d14.x + s2 * d23.x, s1 * d14.y + s2 * d23.y);
+            double2 q2 = make_double2(s2 * d14.x - s1 * d23.x, s2 * d14.y - s1 * d23.y);
+            double2 u1 = make_double2(-q1.y, q1.x), u2 = make_double2(-q2.y, q2.x);
+            v[0] = v[0] + s14 + s23;
+            v[1] = t1 + u1;
+            v[4] = t1 - u1;
+            v[2] = t2 + u2;
+            v[3] = t2 - u2;
+        }
+        const int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) b[(j0 + r * Ns) * C + c] = v[r];
+    }
+}
+
+// Full transform of C columns. `a` holds the input; returns the buffer (a or b) holding the result.
+// Ends with a __syncthreads(); the caller must have synchronised after filling `a`.
+template <int DIR>
+__device__ __forceinline__ double2* fft_smem(double2* a, double2* b, const FftPlanDev& pl, int C, int tid,
+                                             int nthreads) {
+    int Ns = 1;
+    for (int p = 0; p < pl.npass; ++p) {
+        const int R = pl.radix[p];
+        if (R == 4) fft_pass<DIR, 4>(a, b, pl, Ns, C, tid, nthreads);
+        else if (R == 2) fft_pass<DIR, 2>(a, b, pl, Ns, C, tid, nthreads);
+        else if (R == 3) fft_pass<DIR, 3>(a, b, pl, Ns, C, tid, nthreads);
+        else fft_pass<DIR, 5>(a, b, pl, Ns, C, tid, nthreads);
+        __syncthreads();
+        double2* t = a;
+        a = b;
+        b = t;
+        Ns *= R;
+    }
+    return a;
+}
+
+}  // namespace cfgpu

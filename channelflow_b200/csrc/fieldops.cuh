@@ -1,0 +1,14 @@
+// Elementwise FlowField kernels and L2 forms -- see fieldops.cu.
+#pragma once
+#include "cf_common.cuh"
+
+namespace cfgpu {
+int axpby_launch(double* y, double a, const double* x, double b, const double* z, long n, cudaStream_t st);
+int scale_launch(double* y, double s, long n, cudaStream_t st);
+int zero_padded_launch(double* d, int Nx, int Ny, int Nz, int Nd, int Kx, int Kz, cudaStream_t st);
+int profile_get_launch(const double* d, long off0_cplx, long rs_cplx, int Ny, double* out_dev, cudaStream_t st);
+int profile_add_launch(double* d, long off0_cplx, long rs_cplx, int Ny, const double* in_dev, double s, cudaStream_t st);
+// mode: 0 = sum |u|^2, 1 = sum |u-v|^2, 2 = <u,v>; result (times scale) written to out_dev
+int l2form_launch(const double* u, const double* v, int mode, const double* W, int N, int Nx, int Nz, int Nd, int Kx, int Kz, int fullbox,
+                  double scale, double* partial_dev, size_t partial_cap, double* out_dev, cudaStream_t st);
+}  // namespace cfgpu

@@ -1,0 +1,256 @@
+// x-pass / z-pass kernels: batched complex FFTs in x, paired real FFTs in z fused with the pointwise nonlinear
+// term.  See xzpass.cuh.  All three are HBM-bound streaming kernels (each pencil element read once, written
+// once, 16-byte accesses contiguous along kz); the FFT itself runs out of shared memory.
+#include "xzpass.cuh"
+
+namespace cfgpu {
+
+namespace {
+constexpr int XZ_THREADS = 256;
+constexpr double TWO_PI = 6.283185307179586476925286766559;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ x inverse
+// grid = (ceil(nkz/TZ), nyn, nfields)   P[src][yl][mxi][kz] -> Q[f][yl][nx][kz], optional d/dx = i 2 pi kx / Lx
+__global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassParams p) {
+    const int Nx = p.Nx, Kx = p.Kx, TZ = p.TZ;
+    const int nmx = 2 * Kx + 1, nkz = p.Kz + 1;
+    double2* a = dyn_smem<double2>();
+    double2* b = a + (size_t)Nx * TZ;
+    const int tid = threadIdx.x;
+    const int f = blockIdx.z, yl = blockIdx.y, kz0 = blockIdx.x * TZ;
+    const int s = p.src[f];
+    const bool ddx = p.ddx[f] != 0;
+
+    // zero the aliased rows Kx+1 .. Nx-Kx-1
+    const int nzero = (Nx - nmx) * TZ;
+    for (int idx = tid; idx < nzero; idx += XZ_THREADS) a[(Kx + 1) * TZ + idx] = make_double2(0.0, 0.0);
+    const double2* __restrict__ in = p.in + ((size_t)s * p.nyn + yl) * nmx * nkz;
+    for (int idx = tid; idx < nmx * TZ; idx += XZ_THREADS) {
+        const int mxi = idx / TZ, c = idx - mxi * TZ;
+        const int kz = kz0 + c;
+        const int kx = mxi <= Kx ? mxi : mxi - nmx;
+        const int mx = kx >= 0 ? kx : Nx + kx;
+        double2 v = make_double2(0.0, 0.0);
+        if (kz < nkz) v = in[(size_t)mxi * nkz + kz];
+        if (ddx) {
+            const double k = TWO_PI * kx / p.Lx;
+            v = make_double2(-k * v.y, k * v.x);
+        }
+        a[mx * TZ + c] = v;
+    }
+    __syncthreads();
+    const double2* res = fft_smem<+1>(a, b, p.plan, TZ, tid, XZ_THREADS);
+    double2* __restrict__ out = p.out + ((size_t)f * p.nyn + yl) * Nx * nkz;
+    for (int idx = tid; idx < Nx * TZ; idx += XZ_THREADS) {
+        const int nx = idx / TZ, c = idx - nx * TZ;
+        const int kz = kz0 + c;
+        if (kz < nkz) out[(size_t)nx * nkz + kz] = res[idx];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ x forward
+// grid = (ceil(nkz/TZ), nyn, nfields)   Q[f][yl][nx][kz] -> P[f][yl][mxi][kz]   (aliased kx are dropped)
+__global__ void __launch_bounds__(XZ_THREADS) xpass_forward_kernel(const XPassParams p) {
+    const int Nx = p.Nx, Kx = p.Kx, TZ = p.TZ;
+    const int nmx = 2 * Kx + 1, nkz = p.Kz + 1;
+    double2* a = dyn_smem<double2>();
+    double2* b = a + (size_t)Nx * TZ;
+    const int tid = threadIdx.x;
+    const int f = blockIdx.z, yl = blockIdx.y, kz0 = blockIdx.x * TZ;
+    const double2* __restrict__ in = p.in + ((size_t)f * p.nyn + yl) * Nx * nkz;
+    for (int idx = tid; idx < Nx * TZ; idx += XZ_THREADS) {
+        const int nx = idx / TZ, c = idx - nx * TZ;
+        const int kz = kz0 + c;
+        a[idx] = kz < nkz ? in[(size_t)nx * nkz + kz] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const double2* res = fft_smem<-1>(a, b, p.plan, TZ, tid, XZ_THREADS);
+    double2* __restrict__ out = p.out + ((size_t)f * p.nyn + yl) * nmx * nkz;
+    for (int idx = tid; idx < nmx * TZ; idx += XZ_THREADS) {
+        const int mxi = idx / TZ, c = idx - mxi * TZ;
+        const int kz = kz0 + c;
+        const int kx = mxi <= Kx ? mxi : mxi - nmx;
+        const int mx = kx >= 0 ? kx : Nx + kx;
+        if (kz < nkz) out[(size_t)mxi * nkz + kz] = res[mx * TZ + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ z pass
+// grid = (ceil(Nx/TL), nyn).  Two real fields share one complex transform (Z = A + iB with the Hermitian
+// extension written explicitly), so the rotational term needs 5 inverse + 2 forward complex FFTs per line.
+__global__ void __launch_bounds__(XZ_THREADS) zpass_kernel(const ZPassParams p) {
+    const int Nx = p.Nx, Nz = p.Nz, TL = p.TL;
+    const int nkz = p.Kz + 1;
+    const bool rot = p.mode == ZP_ROTATIONAL;
+    const int npair = rot ? 5 : 2;
+    const int CA = npair * TL;
+    double2* A = dyn_smem<double2>();
+    double2* B = A + (size_t)Nz * CA;
+    __shared__ double red[XZ_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int yl = blockIdx.y, ny = p.ny0 + yl, nx0 = blockIdx.x * TL;
+    const size_t fstride = (size_t)p.nyn * Nx * nkz;  // field stride of Q and F
+
+    for (int idx = tid; idx < Nz * CA; idx += XZ_THREADS) A[idx] = make_double2(0.0, 0.0);
+    __syncthreads();
+
+    const double2* __restrict__ Q = p.Q + (size_t)yl * Nx * nkz;
+    for (int idx = tid; idx < TL * nkz; idx += XZ_THREADS) {
+        const int l = idx / nkz, k = idx - l * nkz;
+        const int nx = nx0 + l;
+        if (nx >= Nx) continue;
+        const size_t off = (size_t)nx * nkz + k;
+        double2 fa[5], fb[5];
+        if (rot) {
+            const double2 u = Q[off], v = Q[fstride + off], w = Q[2 * fstride + off];
+            const double2 uy = Q[3 * fstride + off], wy = Q[4 * fstride + off];
+            const double2 vx = Q[5 * fstride + off], wx = Q[6 * fstride + off];
+            const double kzz = TWO_PI * k / p.Lz;
+            fa[0] = u;  fb[0] = v;
+            fa[1] = w;  fb[1] = uy;
+            fa[2] = wy; fb[2] = vx;
+            fa[3] = wx; fb[3] = make_double2(-kzz * u.y, kzz * u.x);  // du/dz
+            fa[4] = make_double2(-kzz * v.y, kzz * v.x);              // dv/dz
+            fb[4] = make_double2(0.0, 0.0);
+        } else {
+            fa[0] = Q[off];               fb[0] = Q[fstride + off];
+            fa[1] = Q[2 * fstride + off]; fb[1] = make_double2(0.0, 0.0);
+        }
+        for (int q = 0; q < npair; ++q) {
+            double2 a = fa[q], b = fb[q];
+            if (k == 0) { a.y = 0.0; b.y = 0.0; }  // c2r ignores the imaginary part of the mean mode
+            A[(size_t)k * CA + q * TL + l] = make_double2(a.x - b.y, a.y + b.x);
+            if (k > 0) A[(size_t)(Nz - k) * CA + q * TL + l] = make_double2(a.x + b.y, b.x - a.y);
+        }
+    }
+    __syncthreads();
+    double2* res = fft_smem<+1>(A, B, p.plan, CA, tid, XZ_THREADS);
+    double2* other = (res == A) ? B : A;
+
+    // pointwise stage
+    double U = 0.0, Uy = 0.0, W = 0.0, Wy = 0.0;
+    if (p.Uy) {
+        U = p.Uy[ny];
+        Uy = p.Uy[p.Ny + ny];
+        W = p.Uy[2 * p.Ny + ny];
+        Wy = p.Uy[3 * p.Ny + ny];
+    }
+    const double idx_ = (double)Nx / p.Lx, idz_ = (double)Nz / p.Lz, idy_ = p.inv_dy ? p.inv_dy[ny] : 0.0;
+    double cmax = 0.0;
+    const int CF = 2 * TL;
+    for (int idx = tid; idx < Nz * TL; idx += XZ_THREADS) {
+        const int z = idx / TL, l = idx - z * TL;
+        if (nx0 + l >= Nx) {
+            if (rot) {
+                other[(size_t)z * CF + l] = make_double2(0.0, 0.0);
+                other[(size_t)z * CF + TL + l] = make_double2(0.0, 0.0);
+            }
+            continue;
+        }
+        const double2* r = res + (size_t)z * CA + l;
+        if (rot) {
+            const double2 z0 = r[0], z1 = r[TL], z2 = r[2 * TL], z3 = r[3 * TL], z4 = r[4 * TL];
+            const double u = z0.x, v = z0.y, w = z1.x, uy = z1.y, wy = z2.x, vx = z2.y, wx = z3.x, uz = z3.y, vz = z4.x;
+            const double ut = u + U, vt = v - p.Vsuck, wt = w + W;
+            const double ox = (wy + Wy) - vz;
+            const double oy = uz - wx;
+            const double oz = vx - (uy + Uy);
+            double fx = oy * wt - oz * vt;
+            double fy = oz * ut - ox * wt;
+            const double fz = ox * vt - oy * ut;
+            if (p.rotation != 0.0) {
+                fx -= p.rotation * vt;
+                fy += p.rotation * ut;
+            }
+            other[(size_t)z * CF + l] = make_double2(fx, fy);
+            other[(size_t)z * CF + TL + l] = make_double2(fz, 0.0);
+            double m = ut * idx_;
+            const double m2 = v * idy_, m3 = wt * idz_;
+            m = m2 > m ? m2 : m;
+            m = m3 > m ? m3 : m;
+            cmax = m > cmax ? m : cmax;
+        } else {
+            const double2 z0 = r[0], z1 = r[TL];
+            double m = (z0.x + U) * idx_;
+            const double m2 = z0.y * idy_, m3 = (z1.x + W) * idz_;
+            m = m2 > m ? m2 : m;
+            m = m3 > m ? m3 : m;
+            cmax = m > cmax ? m : cmax;
+        }
+    }
+    if (p.cfl_max) {
+        cmax = warp_max(cmax);
+        if ((tid & 31) == 0) red[tid >> 5] = cmax;
+        __syncthreads();
+        if (tid < 32) {
+            double v = tid < XZ_THREADS / 32 ? red[tid] : 0.0;
+            v = warp_max(v);
+            if (tid == 0 && v > 0.0) atomic_max_double(p.cfl_max, v);
+        }
+    }
+    if (!rot) return;
+    __syncthreads();
+    const double2* g = fft_smem<-1>(other, res, p.plan, CF, tid, XZ_THREADS);
+
+    double2* __restrict__ F = p.F + (size_t)yl * Nx * nkz;
+    const double sc = p.scale, hs = 0.5 * p.scale;
+    for (int idx = tid; idx < TL * nkz; idx += XZ_THREADS) {
+        const int l = idx / nkz, k = idx - l * nkz;
+        const int nx = nx0 + l;
+        if (nx >= Nx) continue;
+        const int kn = k == 0 ? 0 : Nz - k;
+        const double2 gk = g[(size_t)k * CF + l], gn = g[(size_t)kn * CF + l], hk = g[(size_t)k * CF + TL + l];
+        const size_t off = (size_t)nx * nkz + k;
+        F[off] = make_double2(hs * (gk.x + gn.x), hs * (gk.y - gn.y));
+        F[fstride + off] = make_double2(hs * (gk.y + gn.y), -hs * (gk.x - gn.x));
+        F[2 * fstride + off] = make_double2(sc * hk.x, sc * hk.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static int set_smem(const void* fn, size_t bytes, size_t& configured) {
+    if (bytes > configured) {
+        CF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    return 0;
+}
+
+int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream) {
+    const int nkz = p.Kz + 1;
+    const size_t smem = 2 * (size_t)p.Nx * p.TZ * sizeof(double2);
+    static size_t configured = 0;
+    auto kfn = xpass_inverse_kernel;
+    CF_TRY(set_smem((const void*)kfn, smem, configured));
+    dim3 grid((nkz + p.TZ - 1) / p.TZ, p.nyn, p.nfields);
+    CF_LAUNCH(kfn, grid, dim3(XZ_THREADS), smem, stream, p);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
+int xpass_forward_launch(const XPassParams& p, cudaStream_t stream) {
+    const int nkz = p.Kz + 1;
+    const size_t smem = 2 * (size_t)p.Nx * p.TZ * sizeof(double2);
+    static size_t configured = 0;
+    auto kfn = xpass_forward_kernel;
+    CF_TRY(set_smem((const void*)kfn, smem, configured));
+    dim3 grid((nkz + p.TZ - 1) / p.TZ, p.nyn, p.nfields);
+    CF_LAUNCH(kfn, grid, dim3(XZ_THREADS), smem, stream, p);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
+int zpass_launch(const ZPassParams& p, cudaStream_t stream) {
+    const int npair = p.mode == ZP_ROTATIONAL ? 5 : 2;
+    const size_t smem = 2 * (size_t)p.Nz * npair * p.TL * sizeof(double2);
+    static size_t configured = 0;
+    auto kfn = zpass_kernel;
+    CF_TRY(set_smem((const void*)kfn, smem, configured));
+    dim3 grid((p.Nx + p.TL - 1) / p.TL, p.nyn);
+    CF_LAUNCH(kfn, grid, dim3(XZ_THREADS), smem, stream, p);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
+}  // namespace cfgpu

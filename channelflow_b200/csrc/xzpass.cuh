@@ -1,0 +1,51 @@
+// x-pass and z-pass kernels of the fused nonlinear-term pipeline (see DESIGN.md "Pipeline").
+//
+// Intermediate ("pencil") arrays are compact: only the retained (de-aliased) modes are stored.
+//   P[f][ny][mxi][kz]   complex, mxi = 0..2Kx   (kx = 0..Kx, -Kx..-1), kz = 0..Kz   (x,z spectral, y physical)
+//   Q[f][ny][nx ][kz]   complex, nx  = 0..Nx-1                                       (x physical, z spectral)
+// Replaces FlowField::makePhysical_xz / makeSpectral_xz (flowfield.cpp:1850-1886) for the DNS path, the x/z
+// derivative factors of curl (diffops.cpp:2318-2332), cross (diffops.cpp:2588-2606), the Coriolis term and
+// base-flow handling of navierstokesNL (nse.cpp:28-36,63-88), zeroPaddedModes (flowfield.cpp:2235-2255; aliased
+// modes are simply never produced) and the CFL maximum (flowfield.cpp:4035-4068).
+#pragma once
+#include "cf_common.cuh"
+#include "fft_smem.cuh"
+
+namespace cfgpu {
+
+struct XPassParams {
+    int Nx, Ny, Kx, Kz;   // Kx,Kz: retained |kx|<=Kx, kz<=Kz ; nmx = 2Kx+1, nkz = Kz+1
+    int TZ;               // kz columns per CTA
+    double Lx;
+    FftPlanDev plan;      // length Nx
+    // inverse: nout outputs, each from src[out] with optional d/dx
+    int nfields;
+    int src[9];
+    int ddx[9];
+    const double2* in;    // inverse: P (field stride Ny*nmx*nkz); forward: Q (field stride Ny*Nx*nkz)
+    double2* out;         // inverse: Q ; forward: P
+    int ny0, nyn;         // y range handled (physical slab)
+};
+int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream);
+int xpass_forward_launch(const XPassParams& p, cudaStream_t stream);
+
+enum ZPassMode { ZP_ROTATIONAL = 0, ZP_CFL = 1 };
+
+struct ZPassParams {
+    int Nx, Ny, Nz, Kz;
+    int TL;               // x-lines per CTA
+    int mode;
+    double Lx, Lz;
+    double scale;         // 1/(Nx*Nz)
+    double Vsuck, rotation;
+    FftPlanDev plan;      // length Nz
+    const double2* Q;     // inputs  [nin][ny][nx][kz]
+    double2* F;           // outputs [3][ny][nx][kz]
+    const double* Uy;     // physical-space base profiles at the Ny Gauss-Lobatto points: U, U', W, W' (4*Ny) or null
+    const double* inv_dy; // 1/dy[ny] for the CFL maximum (Ny)
+    double* cfl_max;      // device scalar: max over grid of (u_i + U_i)/dx_i  (signed, as in the reference)
+    int ny0, nyn;
+};
+int zpass_launch(const ZPassParams& p, cudaStream_t stream);
+
+}  // namespace cfgpu

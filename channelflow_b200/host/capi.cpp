@@ -1,0 +1,173 @@
+// Flat C driver over the host classes (chflow::FlowField / NSE / DNS): the same entry points, with the same
+// argument meaning, as oracle/ref_driver.cpp offers over the reference's classes, so the parity tests can run
+// one script against both libraries.  Prefix cf_ (reference driver: ref_).
+#include <cstring>
+#include <sstream>
+
+#include "channelflow/diffops.h"
+#include "channelflow/dns.h"
+
+using namespace chflow;
+
+extern "C" {
+
+struct CfFlags {
+    double nu, dPdx, dPdz, Ubulk, Wbulk, ulowerwall, uupperwall, wlowerwall, wupperwall, Vsuck, rotation, t0, dt;
+    int baseflow, constraint, timestepping, initstepping, nonlinearity, dealiasing, taucorrection;
+};
+
+static std::ostringstream g_sink;
+
+static DNSFlags to_flags(const CfFlags* f) {
+    DNSFlags fl;
+    fl.nu = f->nu; fl.dPdx = f->dPdx; fl.dPdz = f->dPdz; fl.Ubulk = f->Ubulk; fl.Wbulk = f->Wbulk;
+    fl.ulowerwall = f->ulowerwall; fl.uupperwall = f->uupperwall; fl.wlowerwall = f->wlowerwall; fl.wupperwall = f->wupperwall;
+    fl.Vsuck = f->Vsuck; fl.rotation = f->rotation; fl.t0 = f->t0; fl.dt = f->dt;
+    fl.baseflow = (BaseFlow)f->baseflow;
+    fl.constraint = (MeanConstraint)f->constraint;
+    fl.timestepping = (TimeStepMethod)f->timestepping;
+    fl.initstepping = (TimeStepMethod)f->initstepping;
+    fl.nonlinearity = (NonlinearMethod)f->nonlinearity;
+    fl.dealiasing = (Dealiasing)f->dealiasing;
+    fl.taucorrection = f->taucorrection != 0;
+    fl.verbosity = Silent;
+    fl.logstream = &g_sink;
+    return fl;
+}
+
+void* cf_field_create(int Nx, int Ny, int Nz, int Nd, double Lx, double Lz, double a, double b) {
+    return new FlowField(Nx, Ny, Nz, Nd, Lx, Lz, a, b);
+}
+void cf_field_free(void* h) { delete (FlowField*)h; }
+long cf_field_nloc(void* h) { return (long)((FlowField*)h)->Nloc(); }
+void cf_field_upload(void* h, const double* data) { ((FlowField*)h)->raw_upload(data); }
+void cf_field_download(void* h, double* data) { ((FlowField*)h)->raw_download(data); }
+void cf_field_set_state(void* h, int xz, int y) { ((FlowField*)h)->setState((fieldstate)xz, (fieldstate)y); }
+void cf_field_get_state(void* h, int* xz, int* y) {
+    *xz = (int)((FlowField*)h)->xzstate();
+    *y = (int)((FlowField*)h)->ystate();
+}
+void cf_field_set_padded(void* h, int p) { ((FlowField*)h)->setPadded(p != 0); }
+int cf_field_padded(void* h) { return ((FlowField*)h)->padded() ? 1 : 0; }
+void cf_field_copy(void* dst, void* src) { *(FlowField*)dst = *(FlowField*)src; }
+void cf_field_zero(void* h) { ((FlowField*)h)->setToZero(); }
+void cf_make_physical(void* h) { ((FlowField*)h)->makePhysical(); }
+void cf_make_spectral(void* h) { ((FlowField*)h)->makeSpectral(); }
+void cf_make_physical_y(void* h) { ((FlowField*)h)->makePhysical_y(); }
+void cf_make_spectral_y(void* h) { ((FlowField*)h)->makeSpectral_y(); }
+void cf_make_physical_xz(void* h) { ((FlowField*)h)->makePhysical_xz(); }
+void cf_make_spectral_xz(void* h) { ((FlowField*)h)->makeSpectral_xz(); }
+void cf_zero_padded_modes(void* h) { ((FlowField*)h)->zeroPaddedModes(); }
+double cf_cmplx_get(void* h, int mx, int my, int mz, int i, int part) {
+    const FlowField& u = *(FlowField*)h;
+    const Complex c = u.cmplx(mx, my, mz, i);
+    return part ? c.imag() : c.real();
+}
+void cf_cmplx_set(void* h, int mx, int my, int mz, int i, double re, double im) {
+    ((FlowField*)h)->cmplx(mx, my, mz, i) = Complex(re, im);
+}
+void cf_field_save(void* h, const char* filebase) { ((FlowField*)h)->binarySave(filebase); }
+void* cf_field_load(const char* filebase) { return new FlowField(std::string(filebase)); }
+
+double cf_l2norm(void* h) { return L2Norm(*(FlowField*)h); }
+double cf_l2norm2(void* h, int normalize) { return L2Norm2(*(FlowField*)h, normalize != 0); }
+double cf_l2dist(void* a, void* b) { return L2Dist(*(FlowField*)a, *(FlowField*)b); }
+double cf_l2ip(void* a, void* b) { return L2InnerProduct(*(FlowField*)a, *(FlowField*)b); }
+void cf_field_axpby(void* y, double a, void* x, double b, void* z) {
+    if (z) ((FlowField*)y)->add(a, *(FlowField*)x, b, *(FlowField*)z);
+    else ((FlowField*)y)->add(a, *(FlowField*)x);
+}
+void cf_field_scale(void* y, double s) { *(FlowField*)y *= s; }
+
+void cf_nonlinear(void* uh, void* fh, const CfFlags* rf) {
+    DNSFlags flags = to_flags(rf);
+    FlowField& u = *(FlowField*)uh;
+    FlowField q(u.Nx(), u.Ny(), u.Nz(), 1, u.Lx(), u.Lz(), u.a(), u.b());
+    std::vector<FlowField> fields = {u, q};
+    NSE nse(fields, flags);
+    std::vector<FlowField> out = {*(FlowField*)fh};
+    nse.nonlinear(fields, out);
+    *(FlowField*)fh = out[0];
+}
+void cf_base_profiles(void* uh, const CfFlags* rf, double* Ubase, double* Wbase) {
+    DNSFlags flags = to_flags(rf);
+    FlowField& u = *(FlowField*)uh;
+    FlowField q(u.Nx(), u.Ny(), u.Nz(), 1, u.Lx(), u.Lz(), u.a(), u.b());
+    std::vector<FlowField> fields = {u, q};
+    NSE nse(fields, flags);
+    for (int n = 0; n < u.Ny(); ++n) {
+        Ubase[n] = nse.Ubase()[n];
+        Wbase[n] = nse.Wbase()[n];
+    }
+}
+
+struct CfDNS {
+    std::vector<FlowField> fields;
+    DNS* dns;
+};
+void* cf_dns_create(void* uh, void* qh, const CfFlags* rf) {
+    CfDNS* d = new CfDNS();
+    d->fields = {*(FlowField*)uh, *(FlowField*)qh};
+    d->dns = new DNS(d->fields, to_flags(rf));
+    return d;
+}
+void cf_dns_free(void* h) {
+    CfDNS* d = (CfDNS*)h;
+    delete d->dns;
+    delete d;
+}
+void cf_dns_advance(void* h, int n) {
+    CfDNS* d = (CfDNS*)h;
+    d->dns->advance(d->fields, n);
+}
+void cf_dns_get(void* h, void* uh, void* qh) {
+    CfDNS* d = (CfDNS*)h;
+    if (uh) *(FlowField*)uh = d->fields[0];
+    if (qh) *(FlowField*)qh = d->fields[1];
+}
+void cf_dns_set(void* h, void* uh, void* qh) {
+    CfDNS* d = (CfDNS*)h;
+    if (uh) d->fields[0] = *(FlowField*)uh;
+    if (qh) d->fields[1] = *(FlowField*)qh;
+}
+double cf_dns_cfl(void* h) {
+    CfDNS* d = (CfDNS*)h;
+    return d->dns->CFL(d->fields[0]);
+}
+void cf_dns_reset_dt(void* h, double dt) { ((CfDNS*)h)->dns->reset_dt(dt); }
+double cf_dns_time(void* h) { return ((CfDNS*)h)->dns->time(); }
+double cf_dns_dPdx(void* h) { return ((CfDNS*)h)->dns->dPdx(); }
+double cf_dns_Ubulk(void* h) { return ((CfDNS*)h)->dns->Ubulk(); }
+void cf_sync() { cfgpu_sync(cfgpu_context()); }
+long long cf_launch_count() {
+    long long n = 0;
+    cfgpu_launch_count(cfgpu_context(), &n);
+    return n;
+}
+void cf_timer_start() { cfgpu_timer_start(cfgpu_context()); }
+double cf_timer_stop() {
+    double ms = 0;
+    cfgpu_timer_stop(cfgpu_context(), &ms);
+    return ms;
+}
+
+void cf_laminar_profile(const CfFlags* rf, double a, double b, int Ny, double* U) {
+    DNSFlags flags = to_flags(rf);
+    ChebyCoeff u = laminarProfile(flags, a, b, Ny);
+    for (int n = 0; n < Ny; ++n) U[n] = u[n];
+}
+
+// TimeStep (dnsflags.cpp:749-975) for the host-logic tests
+void* cf_timestep_create(double dt, double dtmin, double dtmax, double dT, double CFLmin, double CFLmax, int variable) {
+    return new TimeStep(dt, dtmin, dtmax, dT, CFLmin, CFLmax, variable != 0);
+}
+void cf_timestep_free(void* h) { delete (TimeStep*)h; }
+int cf_timestep_adjust(void* h, double cfl) { return ((TimeStep*)h)->adjust(cfl, false) ? 1 : 0; }
+int cf_timestep_adjust_for_T(void* h, double T) { return ((TimeStep*)h)->adjust_for_T(T, false) ? 1 : 0; }
+int cf_timestep_n(void* h) { return ((TimeStep*)h)->n(); }
+int cf_timestep_N(void* h) { return ((TimeStep*)h)->N(); }
+double cf_timestep_dt(void* h) { return ((TimeStep*)h)->dt(); }
+double cf_timestep_dT(void* h) { return ((TimeStep*)h)->dT(); }
+double cf_timestep_CFL(void* h) { return ((TimeStep*)h)->CFL(); }
+
+}  // extern "C"

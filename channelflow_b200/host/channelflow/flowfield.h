@@ -1,0 +1,192 @@
+// chflow::FlowField -- Fourier x Chebyshev x Fourier field whose storage lives in B200 HBM.
+//
+// Same public surface as the hot-path part of the reference's channelflow/flowfield.h:52-345 (constructors,
+// element access, transforms, state protocol, arithmetic, swap, dealiasing, geometry queries, .ff I/O), so that
+// code written against Channelflow's FlowField keeps compiling.  Differences in mechanism, not in behaviour:
+//   * data are an opaque cfgpu_field (include/cfgpu.h) in the reference's serial layout;
+//   * operator()/cmplx() return references into a lazily synchronised host mirror (downloaded on first host
+//     access after a device operation, uploaded before the next device operation);
+//   * transforms / arithmetic / norms run as CUDA kernels on the context's stream.
+#ifndef CFB200_FLOWFIELD_H
+#define CFB200_FLOWFIELD_H
+#include <cassert>
+#include <string>
+#include <vector>
+
+#include "cfbasics/mathdefs.h"
+#include "cfgpu.h"
+#include "channelflow/cfmpi.h"
+#include "channelflow/chebyshev.h"
+
+#ifndef FFTW_ESTIMATE
+#define FFTW_ESTIMATE (1U << 6)
+#define FFTW_MEASURE (0U)
+#define FFTW_PATIENT (1U << 5)
+#endif
+
+namespace chflow {
+
+cfgpu_ctx cfgpu_context();  // process-wide device context (device = $CFGPU_DEVICE, else $LOCAL_RANK, else 0)
+void cfgpu_check(int status, const char* where);
+
+class FlowField {
+   public:
+    FlowField();
+    FlowField(int Nx, int Ny, int Nz, int Nd, Real Lx, Real Lz, Real a, Real b, CfMPI* cfmpi = nullptr,
+              fieldstate xzstate = Spectral, fieldstate ystate = Spectral, uint fftw_flags = FFTW_ESTIMATE);
+    FlowField(const FlowField& u);
+    explicit FlowField(const std::string& filebase, CfMPI* cfmpi = nullptr);  // reads filebase.ff
+    ~FlowField();
+    FlowField& operator=(const FlowField& u);
+
+    void resize(int Nx, int Ny, int Nz, int Nd, Real Lx, Real Lz, Real a, Real b, CfMPI* cfmpi = nullptr,
+                uint fftw_flags = FFTW_ESTIMATE);
+    void reconfig(const FlowField& u, uint fftw_flags = FFTW_ESTIMATE);
+    void optimizeFFTW(uint = 0) {}
+
+    // element access (host mirror)
+    Real& operator()(int nx, int ny, int nz, int i);
+    const Real& operator()(int nx, int ny, int nz, int i) const;
+    Complex& cmplx(int mx, int my, int mz, int i);
+    const Complex& cmplx(int mx, int my, int mz, int i) const;
+    Real& operator()(int nx, int ny, int nz, int i, int j) { return (*this)(nx, ny, nz, i + Nd_ * j); }
+    Complex& cmplx(int mx, int my, int mz, int i, int j) { return cmplx(mx, my, mz, i + Nd_ * j); }
+
+    ComplexChebyCoeff profile(int mx, int mz, int i) const;
+
+    void makeSpectral_xz();
+    void makePhysical_xz();
+    void makeSpectral_y();
+    void makePhysical_y();
+    void makeSpectral();
+    void makePhysical();
+    void makeState(fieldstate xzstate, fieldstate ystate);
+
+    void setToZero();
+
+    int numXmodes() const { return Nx_; }
+    int numYmodes() const { return Ny_; }
+    int numZmodes() const { return Nz_ / 2 + 1; }
+    int numXgridpts() const { return Nx_; }
+    int numYgridpts() const { return Ny_; }
+    int numZgridpts() const { return Nz_; }
+    int vectorDim() const { return Nd_; }
+    int Nx() const { return Nx_; }
+    int Ny() const { return Ny_; }
+    int Nz() const { return Nz_; }
+    int Nd() const { return Nd_; }
+    int Mx() const { return Nx_; }
+    int My() const { return Ny_; }
+    int Mz() const { return Nz_ / 2 + 1; }
+    lint Nloc() const { return (lint)Nx_ * Ny_ * Nzpad() * Nd_; }
+    lint Nxloc() const { return Nx_; }
+    lint nxlocmin() const { return 0; }
+    lint Mxloc() const { return Nx_; }
+    lint mxlocmin() const { return 0; }
+    lint Nyloc() const { return Ny_; }
+    lint nylocmin() const { return 0; }
+    lint nylocmax() const { return Ny_; }
+    lint Mzloc() const { return Mz(); }
+    lint mzlocmin() const { return 0; }
+
+    int mx(int kx) const { return kx >= 0 ? kx : kx + Nx_; }
+    int mz(int kz) const { return kz; }
+    int kx(int mx) const { return mx <= Nx_ / 2 ? mx : mx - Nx_; }
+    int kz(int mz) const { return mz; }
+    int kxmax() const { return Nx_ / 2; }
+    int kzmax() const { return Nz_ / 2; }
+    int kxmin() const { return Nx_ / 2 + 1 - Nx_; }
+    int kzmin() const { return 0; }
+    int kxmaxDealiased() const { return Nx_ / 3 - 1; }
+    int kzmaxDealiased() const { return Nz_ / 3 - 1; }
+    int kxminDealiased() const { return -(Nx_ / 3 - 1); }
+    int kzminDealiased() const { return 0; }
+    bool isAliased(int kx, int kz) const { return std::abs(kx) > kxmaxDealiased() || std::abs(kz) > kzmaxDealiased(); }
+
+    Real Lx() const { return Lx_; }
+    Real Ly() const { return b_ - a_; }
+    Real Lz() const { return Lz_; }
+    Real a() const { return a_; }
+    Real b() const { return b_; }
+    Real x(int nx) const { return nx * Lx_ / Nx_; }
+    Real y(int ny) const { return 0.5 * ((b_ + a_) + (b_ - a_) * cos(pi * ny / (Ny_ - 1))); }
+    Real z(int nz) const { return nz * Lz_ / Nz_; }
+
+    int nproc0() const { return 1; }
+    int nproc1() const { return 1; }
+    int taskid() const { return 0; }
+    int numtasks() const { return 1; }
+    int task_coeff(int, int) const { return 0; }
+    CfMPI* cfmpi() const { return cfmpi_; }
+
+    Complex Dx(int mx) const;
+    Complex Dz(int mz) const;
+
+    FlowField& operator*=(Real x);
+    FlowField& operator+=(const ChebyCoeff& U);  // u(0,*,0,0) += U
+    FlowField& operator-=(const ChebyCoeff& U);
+    FlowField& operator+=(const std::vector<ChebyCoeff>& UW);
+    FlowField& operator-=(const std::vector<ChebyCoeff>& UW);
+    FlowField& operator+=(const FlowField& u);
+    FlowField& operator-=(const FlowField& u);
+    void add(const Real a, const FlowField& u);
+    void add(const Real a, const FlowField& u, const Real b, const FlowField& v);
+
+    bool geomCongruent(const FlowField& f, Real eps = 1e-13) const;
+    bool congruent(const FlowField& f, Real eps = 1e-13) const;
+    friend void swap(FlowField& f, FlowField& g);
+
+    void binarySave(const std::string& filebase) const;
+    void save(const std::string& filebase) const { binarySave(filebase); }
+
+    Real dudy_a() const;
+    Real dudy_b() const;
+    Real dwdy_a() const;
+    Real dwdy_b() const;
+    Real CFLfactor() const;
+    Real CFLfactor(ChebyCoeff Ubase, ChebyCoeff Wbase) const;
+
+    void setState(fieldstate xz, fieldstate y);
+    void assertState(fieldstate xz, fieldstate y) const;
+    fieldstate xzstate() const { return xzstate_; }
+    fieldstate ystate() const { return ystate_; }
+
+    void zeroPaddedModes();
+    void setPadded(bool b);
+    bool padded() const { return padded_; }
+
+    // ---- device side (used by NSE / diffops; not part of the reference API)
+    cfgpu_field device() const;          // device copy is current on return; host mirror stays valid
+    cfgpu_field device_mut();            // as above, and the host mirror is invalidated
+    void raw_upload(const Real* data);   // whole array, reference layout
+    void raw_download(Real* data) const;
+
+   private:
+    int Nx_ = 0, Ny_ = 0, Nz_ = 0, Nd_ = 0;
+    Real Lx_ = 0, Lz_ = 0, a_ = 0, b_ = 0;
+    bool padded_ = false;
+    fieldstate xzstate_ = Spectral, ystate_ = Spectral;
+    CfMPI* cfmpi_ = nullptr;
+
+    mutable cfgpu_field dev_ = nullptr;
+    mutable std::vector<Real> host_;
+    mutable bool host_valid_ = false;  // host mirror holds the current data
+    mutable bool dev_valid_ = true;    // device copy holds the current data
+
+    int Nzpad() const { return 2 * (Nz_ / 2 + 1); }
+    size_t flatten(int nx, int ny, int nz, int i) const { return nz + (size_t)Nzpad() * (nx + (size_t)Nx_ * (ny + (size_t)Ny_ * i)); }
+    size_t complex_flatten(int mx, int my, int mz, int i) const {
+        return mz + (size_t)(Nz_ / 2 + 1) * (mx + (size_t)Nx_ * (my + (size_t)Ny_ * i));
+    }
+    void host_sync() const;   // make the host mirror current
+    void host_dirty();        // host mirror current and modified => device stale
+    void push_state() const;  // copy state flags to the device object
+};
+
+FlowField operator*(const Real a, const FlowField& w);
+FlowField operator+(const FlowField& v, const FlowField& w);
+FlowField operator-(const FlowField& v, const FlowField& w);
+void swap(FlowField& f, FlowField& g);
+
+}  // namespace chflow
+#endif

@@ -1,0 +1,126 @@
+/* cfgpu.h -- C-ABI of the B200 (sm_100a) device layer behind Channelflow's FlowField / NSE / DNS classes.
+ *
+ * The reference (epfl-ecps/channelflow, pure C++/FFTW/MPI) has no FFI boundary of its own; its "plugin" surface
+ * is the C++ class API.  This header is the boundary a maintainer binds instead of FFTW + the scalar loops:
+ * each entry point names the reference code it replaces (paths relative to the reference root).
+ * Conventions: extern "C", opaque handles, plain pointers and sizes, `int` status (0 = ok, message via
+ * cfgpu_last_error()).  All field data stay resident in HBM in FP64; host pointers are suffixed _h.  Calls are
+ * asynchronous on the context's stream unless they return data to the host.
+ *
+ * Field storage is the reference's serial layout (channelflow/flowfield.h:370-402):
+ *   real    rdata[nz + Nzpad*(nx + Nx*(ny + Ny*i))],  Nzpad = 2*(Nz/2+1)
+ *   complex cdata[mz + Mz  *(mx + Nx*(my + Ny*i))],   Mz = Nz/2+1
+ * so upload/download are plain copies of FlowField::rdata_.
+ */
+#ifndef CFGPU_H
+#define CFGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cfgpu_ctx_s* cfgpu_ctx;
+typedef struct cfgpu_field_s* cfgpu_field;
+typedef struct cfgpu_nse_s* cfgpu_nse;
+
+enum { CFGPU_PHYSICAL = 0, CFGPU_SPECTRAL = 1 }; /* cfbasics/mathdefs.h: enum fieldstate */
+
+/* ---------------------------------------------------------------- context */
+const char* cfgpu_last_error(void);
+const char* cfgpu_version(void);
+/* replaces CfMPI::getInstance + FFTW planner state (channelflow/cfmpi.cpp:66-127, flowfield.cpp:577-667) */
+int cfgpu_init(int device, cfgpu_ctx* ctx);
+int cfgpu_finalize(cfgpu_ctx ctx);
+int cfgpu_sync(cfgpu_ctx ctx);
+/* number of kernels this library has launched since cfgpu_init (bench.py's gpu_launches) */
+int cfgpu_launch_count(cfgpu_ctx ctx, long long* n);
+/* time a region on the context's stream with CUDA events */
+int cfgpu_timer_start(cfgpu_ctx ctx);
+int cfgpu_timer_stop(cfgpu_ctx ctx, double* ms);
+/* CUDA-graph capture of a sequence of calls on the context's stream (launch-bound small grids) */
+int cfgpu_graph_begin(cfgpu_ctx ctx);
+int cfgpu_graph_end(cfgpu_ctx ctx, int* graph_id);
+int cfgpu_graph_launch(cfgpu_ctx ctx, int graph_id);
+
+/* ---------------------------------------------------------------- FlowField storage
+ * FlowField ctor/resize/copy/assign/swap/setToZero (flowfield.cpp:466-575, 96-102, 452-460, 4076-4090, 2229-2233) */
+int cfgpu_field_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, int Nd, double Lx, double Lz, double a, double b,
+                       cfgpu_field* out);
+int cfgpu_field_destroy(cfgpu_field f);
+int cfgpu_field_upload(cfgpu_field f, const double* data_h, int xzstate, int ystate);
+int cfgpu_field_download(cfgpu_field f, double* data_h);
+int cfgpu_field_copy(cfgpu_field dst, cfgpu_field src);
+int cfgpu_field_swap(cfgpu_field a, cfgpu_field b);
+int cfgpu_field_zero(cfgpu_field f);
+int cfgpu_field_set_state(cfgpu_field f, int xzstate, int ystate);
+int cfgpu_field_get_state(cfgpu_field f, int* xzstate, int* ystate);
+int cfgpu_field_set_padded(cfgpu_field f, int padded);
+int cfgpu_field_get_padded(cfgpu_field f, int* padded);
+int cfgpu_field_device_ptr(cfgpu_field f, double** dptr, long long* ndoubles);
+/* FlowField::add / operator*= / += / -= (flowfield.h:596-615, flowfield.cpp:1459-1469, 1759-1771):  y += a*x + b*z */
+int cfgpu_field_axpby(cfgpu_field y, double a, cfgpu_field x, double b, cfgpu_field z /* may be NULL */);
+int cfgpu_field_scale(cfgpu_field y, double s);
+/* one Fourier mode's Chebyshev profile: FlowField::profile / operator+=(ChebyCoeff) (flowfield.cpp:1473-1530) */
+int cfgpu_field_get_profile(cfgpu_field f, int mx, int mz, int i, double* re_im_h /* 2*Ny, interleaved */);
+int cfgpu_field_add_profile(cfgpu_field f, int mx, int mz, int i, const double* re_im_h, double scale);
+/* FlowField::zeroPaddedModes (flowfield.cpp:2235-2255) */
+int cfgpu_field_zero_padded_modes(cfgpu_field f);
+
+/* ---------------------------------------------------------------- transforms
+ * FlowField::makePhysical_y / makeSpectral_y (flowfield.cpp:1888-1987): DMMA DCT-I contraction
+ * FlowField::makePhysical_xz / makeSpectral_xz (flowfield.cpp:1850-1886): batched c2c-x + paired c2r/r2c-z */
+int cfgpu_field_make_physical_y(cfgpu_field f);
+int cfgpu_field_make_spectral_y(cfgpu_field f);
+int cfgpu_field_make_physical_xz(cfgpu_field f);
+int cfgpu_field_make_spectral_xz(cfgpu_field f);
+int cfgpu_field_make_physical(cfgpu_field f); /* y then xz (flowfield.cpp:1993-1997) */
+int cfgpu_field_make_spectral(cfgpu_field f); /* xz then y */
+
+/* ---------------------------------------------------------------- norms
+ * L2Norm2 / L2Dist2 / L2InnerProduct of FlowFields (diffops.cpp:417-487, 353-413, 489-541) with the Chebyshev
+ * Gram weights of chebyshev.cpp:758-802 (weights evaluated in FP64) */
+int cfgpu_l2norm2(cfgpu_field u, int normalize, double* out_h);
+int cfgpu_l2dist2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h);
+int cfgpu_l2ip(cfgpu_field u, cfgpu_field v, int normalize, double* out_h);
+
+/* ---------------------------------------------------------------- NSE operator (channelflow/nse.h:23-141)
+ * enums follow channelflow/dnsflags.h:24-41 */
+typedef struct {
+    double nu;
+    double Vsuck;
+    double rotation;
+    int nonlinearity;  /* NonlinearMethod: 0 Rotational, 1 Convection, 2 Divergence, 3 SkewSymmetric, 4/5 Alternating, 6 Linearized */
+    int dealias_xz;    /* DNSFlags::dealias_xz() */
+    int dealias_y;     /* DNSFlags::dealias_y()  */
+    int taucorrection;
+    int constraint;    /* MeanConstraint: 0 PressureGradient, 1 BulkVelocity */
+    double dPdxRef, dPdzRef;           /* NSE::dPdxRef_, dPdzRef_ */
+    double UbulkRef_minus_base;        /* UbulkRef_ - UbulkBase_ (nse.cpp:536-537) */
+    double WbulkRef_minus_base;
+} cfgpu_nse_config;
+
+/* NSE::NSE(fields, flags) (nse.cpp:212-289): geometry, base flow (Chebyshev coefficients, length Ny), work space */
+int cfgpu_nse_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, double Lx, double Lz, double a, double b,
+                     const cfgpu_nse_config* cfg, const double* Ubase_h, const double* Wbase_h, cfgpu_nse* out);
+int cfgpu_nse_destroy(cfgpu_nse nse);
+int cfgpu_nse_set_constraint(cfgpu_nse nse, int constraint, double dPdxRef, double dPdzRef,
+                             double UbulkRef_minus_base, double WbulkRef_minus_base);
+/* NSE::reset_lambda (nse.cpp:673-705): batched TauSolver/HelmholtzSolver/BandedTridiag setup for every retained mode */
+int cfgpu_nse_reset_lambda(cfgpu_nse nse, const double* lambda_t_h, int nsub);
+/* NSE::nonlinear = navierstokesNL + zeroPaddedModes (nse.cpp:12-91, 383-391); u is not modified */
+int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f);
+/* NSE::solve (nse.cpp:479-575) fused with the RHS accumulation of the time steppers (dnsalgo.cpp:217-224, 446-449,
+ * 668-673):  rhs = sum_j coef[j]*term[j] ;  solve nu u'' - lambda_s u - grad q = -rhs, div u = 0 per mode */
+int cfgpu_nse_solve(cfgpu_nse nse, int s, int nterms, const double* coef_h, const cfgpu_field* terms,
+                    cfgpu_field uout, cfgpu_field qout);
+/* NSE::linear (nse.cpp:393-477):  L = nu u'' - nu kappa^2 u - grad q (+ mean-mode constants) */
+int cfgpu_nse_linear(cfgpu_nse nse, cfgpu_field u, cfgpu_field q, cfgpu_field L);
+/* FlowField::CFLfactor(Ubase,Wbase) (flowfield.cpp:4035-4068): max over grid of (u_i+U_i)/dx_i (no abs) */
+int cfgpu_nse_cflfactor(cfgpu_nse nse, cfgpu_field u, double* out_h);
+/* dPdxAct_/dPdzAct_ computed by the bulk-velocity-constrained solve (nse.cpp:536) */
+int cfgpu_nse_get_dPd(cfgpu_nse nse, double* dPdx_h, double* dPdz_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
