@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py -- DNS time-step throughput of the B200 hot path (and of the reference's CPU path beside it).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c5|c2|c1|golden] [--impl reference]
+
+A "step" is one SBDF3 time step (rotational nonlinearity, 2/3 dealiasing) of the workload grid on synthetic input
+(divergence-free random perturbation of the laminar base flow, fixed seed).  One JSON line is printed by rank 0.
+
+  value   grid-point-steps/s with the fields resident in HBM (CUDA events around K steps on the launching stream)
+  e2e     the same metric through the public host API with HOST buffers: every step uploads the velocity field from
+          pinned host memory, advances one step, and downloads the result (host<->device copies inside the timed region)
+  roofline   dominant pipeline stage: algorithmic bytes (SURVEY.md 8(d), W = 8*Nx*Ny*2(Nz/2+1)) / measured stage time
+  cpu_baseline  the reference's own C++ (oracle/_ref: unmodified sources + in-repo FFT shim), 1 host core, on a bounded
+          sample grid with the same Ny (grid-point-steps/s is the size-independent unit)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs; Lx, Lz as in SURVEY.md 8(d)
+    "c4": dict(Nx=512, Ny=257, Nz=512, Lx=4 * np.pi, Lz=2 * np.pi, nu=1.0 / 4000, dt=0.002, desc="turbulent-channel grid 512x257x512"),
+    "c5": dict(Nx=256, Ny=129, Nz=256, Lx=4 * np.pi, Lz=2 * np.pi, nu=1.0 / 1000, dt=0.005, desc="256x129x256"),
+    "c2": dict(Nx=128, Ny=97, Nz=128, Lx=2 * np.pi, Lz=np.pi, nu=1.0 / 1800, dt=0.01, desc="128x97x128"),
+    "c1": dict(Nx=32, Ny=33, Nz=32, Lx=2 * np.pi, Lz=np.pi, nu=1.0 / 400, dt=0.02, desc="plane Couette 32x33x32"),
+    "golden": dict(Nx=48, Ny=35, Nz=48, Lx=2 * np.pi / 1.14, Lz=2 * np.pi / 2.5, nu=1.0 / 400, dt=0.025, desc="48x35x48"),
+}
+STAGES = ["inv_y_gemm", "inv_x_pass", "z_pass_nl", "fwd_x_pass", "fwd_y_gemm", "tau_solve", "linear", "tau_setup"]
+# algorithmic bytes per stage in units of W (rotational SBDF-k with k=3)
+STAGE_W = {"inv_y_gemm": 3 + 5, "inv_x_pass": 5 + 7, "z_pass_nl": 7 + 3, "fwd_x_pass": 3 + 3, "fwd_y_gemm": 3 + 3, "tau_solve": 15 + 4}
+
+
+def synthetic_field(w, seed=1, magn=0.1):
+    """Smooth divergence-free perturbation with no-slip walls, built directly in spectral space:
+    u = curl(psi e_y)-like modes (u = dpsi/dz, w = -dpsi/dx, v = 0) times (1-y^2)^2 -> Chebyshev coefficients."""
+    Nx, Ny, Nz = w["Nx"], w["Ny"], w["Nz"]
+    Mz = Nz // 2 + 1
+    rng = np.random.default_rng(seed)
+    u = np.zeros((3, Ny, Nx, Mz), dtype=np.complex128)
+    Kx, Kz = min(Nx // 3 - 1, 12), min(Nz // 3 - 1, 12)
+    # g(y) = (1-y^2)^2 = 3/8 T0 - 1/2 T2 + 1/8 T4
+    g = np.zeros(Ny); g[0], g[2], g[4] = 3.0 / 8, -0.5, 1.0 / 8
+    for kx in range(-Kx, Kx + 1):
+        for kz in range(0, Kz + 1):
+            if kx == 0 and kz == 0:
+                continue
+            if kz == 0 and kx < 0:
+                continue
+            amp = (rng.standard_normal() + 1j * rng.standard_normal()) * 0.6 ** (abs(kx) + kz)
+            a, c = 2 * np.pi * kx / w["Lx"], 2 * np.pi * kz / w["Lz"]
+            mx = kx % Nx
+            u[0, :, mx, kz] = 1j * c * amp * g
+            u[2, :, mx, kz] = -1j * a * amp * g
+            if kz == 0:  # keep the kz=0 plane Hermitian
+                u[0, :, (-kx) % Nx, 0] = np.conj(u[0, :, mx, 0])
+                u[2, :, (-kx) % Nx, 0] = np.conj(u[2, :, mx, 0])
+    arr = u.view(np.float64)
+    arr *= magn / max(np.sqrt(np.sum(np.abs(u) ** 2)), 1e-300)
+    return arr
+
+
+def flags_kw(w):
+    return dict(nu=w["nu"], dt=w["dt"], ulowerwall=-1.0, uupperwall=1.0, baseflow="laminar", constraint="gradp",
+                timestepping="sbdf3", initstepping="smrk2", nonlinearity="rot", dealiasing="xz")
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.reasons, self.stop_flag = device, [], set(), False
+        self.smax = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.smax = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def reference_steps(w_sample, steps, warmup):
+    """Times the reference's own DNS (oracle/_ref) on the sample grid: 1 core. Returns (ms_per_step, info)."""
+    from oracle import refcf
+    from tests import parity  # noqa: F401
+    rf = refcf.RefField(w_sample["Nx"], w_sample["Ny"], w_sample["Nz"], 3, w_sample["Lx"], w_sample["Lz"])
+    rf.data[...] = synthetic_field(w_sample)
+    rf.set_padded(True)
+    dns = refcf.RefDNS(rf, refcf.make_flags(**flags_kw(w_sample)))
+    dns.advance(2 + warmup)  # 2 SMRK2 initialisation steps of SBDF3 + warm-up
+    t0 = time.perf_counter()
+    dns.advance(steps)
+    dt = time.perf_counter() - t0
+    return 1e3 * dt / steps
+
+
+def sample_grid(w):
+    """Bounded CPU sample of the workload: same Ny (same per-mode solver cost), smaller Nx, Nz."""
+    s = dict(w)
+    while s["Nx"] * s["Ny"] * s["Nz"] > 3.5e6 and s["Nx"] > 32:
+        s["Nx"] //= 2
+        s["Nz"] //= 2
+    return s
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    gp = w["Nx"] * w["Ny"] * w["Nz"]
+    Wbytes = 8 * w["Nx"] * w["Ny"] * 2 * (w["Nz"] // 2 + 1)
+    config = {"workload": "%s: SBDF3, rotational NL, 2/3 dealiasing, FP64, dt=%g" % (w["desc"], w["dt"]), "grid": [w["Nx"], w["Ny"], w["Nz"]],
+              "l2": "working set (>= 34 W = %.1f MB) %s the 126 MB L2" % (34 * Wbytes / 1e6, "exceeds" if 34 * Wbytes > 126e6 else "fits in")}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ws = sample_grid(w)
+        steps = max(1, min(args.steps, 3))
+        ms = reference_steps(ws, steps, min(args.warmup, 1))
+        val = ws["Nx"] * ws["Ny"] * ws["Nz"] / (ms * 1e-3)
+        sample = "reference DNS (unmodified sources, FFT shim instead of FFTW), %dx%dx%d grid, %d SBDF3 steps" % (ws["Nx"], ws["Ny"], ws["Nz"], steps)
+        print(json.dumps({"impl": "reference", "metric": "dns_grid_point_steps_per_s", "value": val, "unit": "grid-pt-steps/s",
+                          "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms * gp / (ws["Nx"] * ws["Ny"] * ws["Nz"]),
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": config, "steps_per_s_at_workload": val / gp,
+                          "cpu_baseline": {"value": val, "unit": "grid-pt-steps/s", "cores": 1, "kind": "reference", "sample": sample},
+                          "e2e": {"value": val, "unit": "grid-pt-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import channelflow_b200 as cf
+    if world > 1:
+        raise SystemExit("multi-GPU slab decomposition is not wired into bench.py yet (see DESIGN.md)")
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("CFGPU_DEVICE", str(dev))
+    lib = cf.HostLib()
+    u0 = synthetic_field(w)
+    ug = cf.FlowField(lib, w["Nx"], w["Ny"], w["Nz"], 3, w["Lx"], w["Lz"]).set(u0, padded=True)
+    dns = cf.DNS(ug, cf.make_flags(**flags_kw(w)))
+    dns.advance(2)            # SMRK2 initialisation steps of SBDF3 (not part of the metric)
+    dns.advance(args.warmup)
+    lib.sync()
+
+    sampler = ClockSampler(dev)
+    sampler.start()
+    l0 = lib.launch_count()
+    lib.profile_enable(True)
+    lib.profile_read(reset=True)
+    lib.timer_start()
+    dns.advance(args.steps)
+    ms_total = lib.timer_stop()
+    stage_ms, stage_calls = lib.profile_read(reset=True)
+    lib.profile_enable(False)
+    launches = lib.launch_count() - l0
+    ms = ms_total / args.steps
+    value = gp / (ms * 1e-3)
+
+    # ---- end to end through the host API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        n = int(np.prod(ug.shape))
+        pin_in = torch.empty(n, dtype=torch.float64).pin_memory()
+        pin_out = torch.empty(n, dtype=torch.float64).pin_memory()
+        hin, hout = pin_in.numpy(), pin_out.numpy()
+        cur, _ = dns.get()
+        hin[:] = cur.get().ravel()
+        ke = max(2, min(args.steps, 5))
+        import ctypes as C
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+        lib.sync()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            lib.L.cf_field_upload(cur.h, dp(hin))      # H2D of this step's input (pinned)
+            dns.set(cur)
+            dns.advance(1)
+            lib.L.cf_dns_get(dns.h, cur.h, None)
+            lib.L.cf_field_download(cur.h, dp(hout))   # D2H of this step's result
+            hin, hout = hout, hin
+        lib.sync()
+        ems = 1e3 * (time.perf_counter() - t0) / ke
+        e2e = {"value": gp / (ems * 1e-3), "unit": "grid-pt-steps/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+               "ms_per_step": ems, "steps": ke}
+    clocks = sampler.result()
+
+    # ---- roofline of the dominant stage
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    stages = {}
+    for name, t, c in zip(STAGES, stage_ms, stage_calls):
+        if c:
+            per = t / args.steps
+            stages[name] = {"ms_per_step": per, "calls_per_step": c / args.steps}
+            if name in STAGE_W:
+                stages[name]["algorithmic_GBps"] = STAGE_W[name] * Wbytes / (per * 1e-3) / 1e9
+    dom = max((k for k in stages if k in STAGE_W), key=lambda k: stages[k]["ms_per_step"])
+    ach = stages[dom]["algorithmic_GBps"]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "whole_step_algorithmic_GBps": 61 * Wbytes / (ms * 1e-3) / 1e9, "whole_step_frac": 61 * Wbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                "y_gemm_TFLOPs": (8 * 2 * w["Ny"] * ((w["Ny"] + 1) // 2) * 2 * (w["Nx"] // 3 * 2 - 1) * (w["Nz"] // 3) * 2) /
+                ((stages.get("inv_y_gemm", {}).get("ms_per_step", 0) + stages.get("fwd_y_gemm", {}).get("ms_per_step", 0)) * 1e-3 + 1e-30) / 1e12}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and rank == 0:
+        ws = sample_grid(w)
+        cms = reference_steps(ws, 2, 0)
+        cval = ws["Nx"] * ws["Ny"] * ws["Nz"] / (cms * 1e-3)
+        cpu_baseline = {"value": cval, "unit": "grid-pt-steps/s", "cores": 1, "kind": "reference",
+                        "sample": "reference DNS (unmodified sources + FFT shim), %dx%dx%d grid, 2 SBDF3 steps after 2 init steps" % (ws["Nx"], ws["Ny"], ws["Nz"])}
+
+    print(json.dumps({"metric": "dns_grid_point_steps_per_s", "value": value, "unit": "grid-pt-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+                      "gpu_launches": launches, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline}))
+
+
+if __name__ == "__main__":
+    main()

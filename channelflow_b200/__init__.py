@@ -21,7 +21,7 @@ PHYSICAL, SPECTRAL = 0, 1
 
 # every symbol include/cfgpu.h declares
 CFGPU_SYMBOLS = """cfgpu_last_error cfgpu_version cfgpu_init cfgpu_finalize cfgpu_sync cfgpu_launch_count cfgpu_timer_start
-cfgpu_timer_stop cfgpu_graph_begin cfgpu_graph_end cfgpu_graph_launch cfgpu_field_create cfgpu_field_destroy
+cfgpu_timer_stop cfgpu_profile_enable cfgpu_profile_read cfgpu_graph_begin cfgpu_graph_end cfgpu_graph_launch cfgpu_field_create cfgpu_field_destroy
 cfgpu_field_upload cfgpu_field_download cfgpu_field_copy cfgpu_field_swap cfgpu_field_zero cfgpu_field_set_state
 cfgpu_field_get_state cfgpu_field_set_padded cfgpu_field_get_padded cfgpu_field_device_ptr cfgpu_field_axpby
 cfgpu_field_scale cfgpu_field_get_profile cfgpu_field_add_profile cfgpu_field_zero_padded_modes
@@ -54,7 +54,7 @@ class GpuLib:
         if not os.path.exists(path):
             raise CfgpuError("CUDA library %s is missing: run `python __graft_entry__.py` (there is no CPU fallback)" % path)
         self.path = path
-        self.L = L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.L = L = C.CDLL(path)  # RTLD_LOCAL: the test-only emulation build may live in the same process
         vp, d, i, dpt = C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double)
         L.cfgpu_last_error.restype = C.c_char_p
         L.cfgpu_version.restype = C.c_char_p
@@ -318,7 +318,7 @@ class HostLib:
 
     def __init__(self, path=None, gpu_path=None):
         path = path or LIB_HOST
-        self.gpu = GpuLib(gpu_path)  # loads libcfgpu first (RTLD_GLOBAL) and fails loudly if it is missing
+        self.gpu = GpuLib(gpu_path)  # fails loudly if the CUDA library is missing
         if not os.path.exists(path):
             raise CfgpuError("host library %s is missing: run `python __graft_entry__.py`" % path)
         self.L = L = C.CDLL(path)
@@ -367,6 +367,15 @@ class HostLib:
         L.cf_timestep_adjust_for_T.argtypes = [vp, d]
 
     def sync(self): self.L.cf_sync()
+
+    def profile_enable(self, on=True): self.L.cf_profile_enable(1 if on else 0)
+
+    def profile_read(self, reset=True):
+        ms = (C.c_double * 8)()
+        calls = (C.c_longlong * 8)()
+        self.L.cf_profile_read(ms, calls, 1 if reset else 0)
+        return list(ms), list(calls)
+
     def launch_count(self): return self.L.cf_launch_count()
     def timer_start(self): self.L.cf_timer_start()
     def timer_stop(self): return self.L.cf_timer_stop()

@@ -24,6 +24,38 @@ int ws_reserve(Workspace& w, size_t bytes) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------- stage profiler
+int stage_begin(cfgpu_ctx ctx, int st) {
+    if (!ctx->profiling || ctx->capturing) return 0;
+    if (ctx->prof_used[st] == ctx->prof_ev[st].size()) {
+        cudaEvent_t a, b;
+        CF_CUDA(cudaEventCreate(&a));
+        CF_CUDA(cudaEventCreate(&b));
+        ctx->prof_ev[st].push_back({a, b});
+    }
+    CF_CUDA(cudaEventRecord(ctx->prof_ev[st][ctx->prof_used[st]].first, ctx->stream));
+    return 0;
+}
+int stage_end(cfgpu_ctx ctx, int st) {
+    if (!ctx->profiling || ctx->capturing) return 0;
+    CF_CUDA(cudaEventRecord(ctx->prof_ev[st][ctx->prof_used[st]].second, ctx->stream));
+    ctx->prof_used[st]++;
+    ctx->prof_calls[st]++;
+    return 0;
+}
+static int prof_collect(cfgpu_ctx ctx) {
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int st = 0; st < CFGPU_NSTAGES; ++st) {
+        for (size_t i = 0; i < ctx->prof_used[st]; ++i) {
+            float ms = 0;
+            CF_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[st][i].first, ctx->prof_ev[st][i].second));
+            ctx->prof_ms[st] += ms;
+        }
+        ctx->prof_used[st] = 0;
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------- plan builders
 static int upload(const std::vector<double>& h, double** d) {
     CF_CUDA(cudaMalloc((void**)d, h.size() * sizeof(double)));
@@ -270,6 +302,21 @@ int cfgpu_timer_stop(cfgpu_ctx ctx, double* ms) {
     float f = 0;
     CF_CUDA(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
     *ms = f;
+    return 0;
+}
+
+int cfgpu_profile_enable(cfgpu_ctx ctx, int on) {
+    CF_TRY(prof_collect(ctx));
+    ctx->profiling = on != 0;
+    return 0;
+}
+int cfgpu_profile_read(cfgpu_ctx ctx, double* ms_h, long long* calls_h, int reset) {
+    CF_TRY(prof_collect(ctx));
+    for (int st = 0; st < CFGPU_NSTAGES; ++st) {
+        ms_h[st] = ctx->prof_ms[st];
+        calls_h[st] = ctx->prof_calls[st];
+        if (reset) { ctx->prof_ms[st] = 0; ctx->prof_calls[st] = 0; }
+    }
     return 0;
 }
 

@@ -53,6 +53,12 @@ struct cfgpu_ctx_s {
     cfgpu::Workspace ws_P, ws_Q, ws_red;
     std::vector<void*> graphs;  // cudaGraphExec_t
     bool capturing = false;
+    // stage profiler
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[CFGPU_NSTAGES];
+    size_t prof_used[CFGPU_NSTAGES] = {0};
+    double prof_ms[CFGPU_NSTAGES] = {0};
+    long long prof_calls[CFGPU_NSTAGES] = {0};
 };
 
 struct cfgpu_field_s {
@@ -92,6 +98,13 @@ int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out);
 int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out);
 int get_box(cfgpu_ctx ctx, int Nx, int Nz, int Kx, int Kz, const ModeBox** out);
 int ws_reserve(Workspace& w, size_t bytes);
+int stage_begin(cfgpu_ctx ctx, int stage);
+int stage_end(cfgpu_ctx ctx, int stage);
+struct StageTimer {  // RAII bracket around the launches of one pipeline stage
+    cfgpu_ctx ctx; int stage;
+    StageTimer(cfgpu_ctx c, int s) : ctx(c), stage(s) { stage_begin(ctx, stage); }
+    ~StageTimer() { stage_end(ctx, stage); }
+};
 // host-side Chebyshev helpers (long double internally)
 void cheb_diff_host(const std::vector<double>& u, std::vector<double>& d, double a, double b);
 void cheb_to_physical_host(const std::vector<double>& c, std::vector<double>& u);

@@ -69,7 +69,7 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         p.job[0].nmat = 2; p.job[0].out[1] = P + 3 * Pf;  // du/dy
         p.job[2].nmat = 2; p.job[2].out[1] = P + 4 * Pf;  // dw/dy
     }
-    CF_TRY(ygemm_launch(p, ctx->stream));
+    { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(p, ctx->stream)); }
 
     XPassParams xp;
     memset(&xp, 0, sizeof xp);
@@ -88,7 +88,7 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         xp.nfields = 3;
         for (int i = 0; i < 3; ++i) { xp.src[i] = i; xp.ddx[i] = 0; }
     }
-    CF_TRY(xpass_inverse_launch(xp, ctx->stream));
+    { StageTimer _t(ctx, 1); CF_TRY(xpass_inverse_launch(xp, ctx->stream)); }
     return 0;
 }
 
@@ -215,7 +215,7 @@ int cfgpu_nse_reset_lambda(cfgpu_nse nse, const double* lambda_t_h, int nsub) {
     nse->lambda_t.assign(lambda_t_h, lambda_t_h + nsub);
     for (int s = 0; s < nsub; ++s) {
         nse->tau[s].nu = nse->cfg.nu;
-        CF_TRY(tau_setup_launch(nse->tau[s], nse->geom, lambda_t_h[s], nse->TM_setup, ctx->stream));
+        { StageTimer _t(ctx, 7); CF_TRY(tau_setup_launch(nse->tau[s], nse->geom, lambda_t_h[s], nse->TM_setup, ctx->stream)); }
     }
     return 0;
 }
@@ -229,7 +229,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     ZPassParams zp;
     CF_TRY(fill_zpass(nse, zp, ZP_ROTATIONAL));
     CF_CUDA(cudaMemsetAsync(nse->d_scal, 0, sizeof(double), ctx->stream));
-    CF_TRY(zpass_launch(zp, ctx->stream));
+    { StageTimer _t(ctx, 2); CF_TRY(zpass_launch(zp, ctx->stream)); }
 
     const FftPlanDev* fx;
     CF_TRY(get_fftplan(ctx, nse->Nx, &fx));
@@ -243,7 +243,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     xp.in = reinterpret_cast<const double2*>(ctx->ws_Q.ptr);
     xp.out = reinterpret_cast<double2*>(ctx->ws_P.ptr);
     xp.ny0 = 0; xp.nyn = nse->Ny;
-    CF_TRY(xpass_forward_launch(xp, ctx->stream));
+    { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xp, ctx->stream)); }
 
     // aliased modes of f must be exactly zero (FlowField::zeroPaddedModes, nse.cpp:389-390); the kernels below
     // only ever write retained modes
@@ -270,7 +270,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         p.job[i].out[0] = f->d + i * f->compstride();
         p.job[i].nmat = 1; p.job[i].mat0 = 0;
     }
-    CF_TRY(ygemm_launch(p, ctx->stream));
+    { StageTimer _t(ctx, 4); CF_TRY(ygemm_launch(p, ctx->stream)); }
     f->xzstate = CFGPU_SPECTRAL; f->ystate = CFGPU_SPECTRAL;
     f->clean_Kx = nse->Kx; f->clean_Kz = nse->Kz;
     if (nse->cfg.dealias_xz) f->padded = 1;
@@ -309,7 +309,7 @@ int cfgpu_nse_solve(cfgpu_nse nse, int s, int nterms, const double* coef_h, cons
     }
     tp.uout = uout->d;
     tp.qout = qout->d;
-    CF_TRY(tau_solve_launch(tp, nse->ctx->stream));
+    { StageTimer _t(nse->ctx, 5); CF_TRY(tau_solve_launch(tp, nse->ctx->stream)); }
     uout->xzstate = uout->ystate = qout->xzstate = qout->ystate = CFGPU_SPECTRAL;
     return 0;
 }
@@ -319,7 +319,7 @@ int cfgpu_nse_linear(cfgpu_nse nse, cfgpu_field u, cfgpu_field q, cfgpu_field L)
     CF_ARG(!nse->tau.empty(), "cfgpu_nse_linear: call reset_lambda first");
     TauSolveParams tp;
     CF_TRY(fill_tau_params(nse, 0, tp));
-    CF_TRY(linear_launch(tp, u->d, q->d, L->d, nse->ctx->stream));
+    { StageTimer _t(nse->ctx, 6); CF_TRY(linear_launch(tp, u->d, q->d, L->d, nse->ctx->stream)); }
     L->xzstate = L->ystate = CFGPU_SPECTRAL;
     return 0;
 }

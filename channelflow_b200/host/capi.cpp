@@ -151,6 +151,9 @@ double cf_timer_stop() {
     return ms;
 }
 
+void cf_profile_enable(int on) { cfgpu_profile_enable(cfgpu_context(), on); }
+void cf_profile_read(double* ms, long long* calls, int reset) { cfgpu_profile_read(cfgpu_context(), ms, calls, reset); }
+
 void cf_laminar_profile(const CfFlags* rf, double a, double b, int Ny, double* U) {
     DNSFlags flags = to_flags(rf);
     ChebyCoeff u = laminarProfile(flags, a, b, Ny);

@@ -37,6 +37,12 @@ int cfgpu_launch_count(cfgpu_ctx ctx, long long* n);
 /* time a region on the context's stream with CUDA events */
 int cfgpu_timer_start(cfgpu_ctx ctx);
 int cfgpu_timer_stop(cfgpu_ctx ctx, double* ms);
+/* per-stage device timing of the DNS pipeline (CUDA events on the launching stream, accumulated per stage):
+ * stages: 0 inverse y-GEMM, 1 inverse x-pass, 2 z-pass+nonlinear, 3 forward x-pass, 4 forward y-GEMM,
+ *         5 tau solve (+fused RHS), 6 linear term, 7 tau setup */
+#define CFGPU_NSTAGES 8
+int cfgpu_profile_enable(cfgpu_ctx ctx, int on);
+int cfgpu_profile_read(cfgpu_ctx ctx, double* ms_h /* [CFGPU_NSTAGES] */, long long* calls_h /* [CFGPU_NSTAGES] */, int reset);
 /* CUDA-graph capture of a sequence of calls on the context's stream (launch-bound small grids) */
 int cfgpu_graph_begin(cfgpu_ctx ctx);
 int cfgpu_graph_end(cfgpu_ctx ctx, int* graph_id);

@@ -21,5 +21,5 @@ if [ ! -f "$o" ] || [ "$ROOT/tests/emu/cfemu.cpp" -nt "$o" ] || [ "$ROOT/tests/e
   pids+=($!)
 fi
 for p in "${pids[@]}"; do wait $p; done
-$CXX -shared -o "$OUT/libcfgpu_emu.so" "$OUT"/obj/*.o -lpthread
+$CXX -shared -Wl,-Bsymbolic -o "$OUT/libcfgpu_emu.so" "$OUT"/obj/*.o -lpthread
 echo "built $OUT/libcfgpu_emu.so"

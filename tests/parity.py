@@ -1,0 +1,190 @@
+"""Parity scenarios shared by the CPU-emulation tests (-m "not gpu") and the GPU tests (-m gpu).
+
+Every scenario runs the same inputs through (a) the oracle = the unmodified Channelflow reference compiled in
+oracle/_ref (oracle/refcf.py) and (b) this package's libraries, and returns error measures.  `lib` is a
+channelflow_b200.HostLib: the real CUDA build on the GPU box, or the emulation build (tests/_emu) on the CPU.
+"""
+import os
+
+import numpy as np
+
+import channelflow_b200 as cf
+from oracle import refcf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "_emu")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# BASELINE.json configs[0]: plane Couette Re=400, 32x33x32, Lx=2pi, Lz=pi, SBDF3, rotational, dealiased, dt=0.02
+C1 = dict(Nx=32, Ny=33, Nz=32, Lx=2 * np.pi, Lz=np.pi, a=-1.0, b=1.0,
+          flags=dict(nu=1.0 / 400, dt=0.02, ulowerwall=-1.0, uupperwall=1.0, baseflow="laminar", constraint="gradp",
+                     timestepping="sbdf3", initstepping="smrk2", nonlinearity="rot", dealiasing="xz"))
+
+
+def emu_lib():
+    import subprocess
+    subprocess.check_call([os.path.join(ROOT, "tests", "emu", "build_emu.sh")], stdout=subprocess.DEVNULL)
+    host = os.path.join(EMU_DIR, "libchflow_b200_emu.so")
+    srcs = [os.path.join(ROOT, "channelflow_b200", "host", f) for f in os.listdir(os.path.join(ROOT, "channelflow_b200", "host"))
+            if f.endswith(".cpp")]
+    hdrs = []
+    for d, _, fs in os.walk(os.path.join(ROOT, "channelflow_b200", "host")):
+        hdrs += [os.path.join(d, f) for f in fs if f.endswith(".h")]
+    newest = max(os.path.getmtime(p) for p in srcs + hdrs + [os.path.join(EMU_DIR, "libcfgpu_emu.so")])
+    if not os.path.exists(host) or os.path.getmtime(host) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I",
+                               os.path.join(ROOT, "channelflow_b200", "host"), "-o", host] + srcs +
+                              ["-L", EMU_DIR, "-lcfgpu_emu", "-Wl,-rpath,$ORIGIN", "-Wl,-Bsymbolic"])
+    return cf.HostLib(host, os.path.join(EMU_DIR, "libcfgpu_emu.so"))
+
+
+def gpu_lib():
+    return cf.HostLib()
+
+
+def ref_random(cfg, seed=1, magn=0.2, smooth=0.4):
+    """tools/randomfield.cpp rule (serial drand48) through the compiled reference."""
+    return refcf.RefField(cfg["Nx"], cfg["Ny"], cfg["Nz"], 3, cfg["Lx"], cfg["Lz"], cfg["a"], cfg["b"]).randomfield(seed, magn, smooth)
+
+
+def to_gpu(lib, rf, padded=True):
+    st = rf.state()
+    return cf.FlowField(lib, rf.Nx, rf.Ny, rf.Nz, rf.Nd, rf.Lx, rf.Lz, rf.a, rf.b).set(rf.data, st[0], st[1], padded=padded)
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def physical_mask(shape, Nz):
+    m = np.ones(shape, bool)
+    m[..., Nz:] = False  # the two padding reals per z-line are unspecified after c2r
+    return m
+
+
+# ------------------------------------------------------------------------------------------------ scenarios
+def transforms(lib, cfg, seed=2):
+    ur = ref_random(cfg, seed)
+    u0 = ur.data.copy()
+    ug = to_gpu(lib, ur)
+    out = {}
+    ur.make_physical_y(); ug.make_physical_y()
+    out["physical_y"] = rel_l2(ug.get(), ur.data)
+    ur.make_physical_xz(); ug.make_physical_xz()
+    m = physical_mask(ur.data.shape, cfg["Nz"])
+    out["physical"] = rel_l2(ug.get()[m], ur.data[m])
+    ur.make_spectral_xz(); ug.make_spectral_xz()
+    out["spectral_xz"] = rel_l2(ug.get(), ur.data)
+    ur.make_spectral_y(); ug.make_spectral_y()
+    out["roundtrip_vs_ref"] = rel_l2(ug.get(), ur.data)
+    out["roundtrip_vs_input"] = rel_l2(ug.get(), u0)
+    return out
+
+
+def norms(lib, cfg):
+    ur, vr = ref_random(cfg, 3), ref_random(cfg, 4, magn=0.1)
+    ug, vg = to_gpu(lib, ur), to_gpu(lib, vr)
+    out = {"l2norm": abs(ug.l2norm() - ur.l2norm()) / ur.l2norm(),
+           "l2dist": abs(ug.l2dist(vg) - ur.l2dist(vr)) / ur.l2dist(vr),
+           "l2ip": abs(ug.l2ip(vg) - ur.l2ip(vr)) / abs(ur.l2norm() * vr.l2norm())}
+    ur.set_padded(False); vr.set_padded(False); ug.set_padded(False); vg.set_padded(False)
+    out["l2norm_unpadded"] = abs(ug.l2norm() - ur.l2norm()) / ur.l2norm()
+    return out
+
+
+def nonlinear(lib, cfg, seed=1, **flag_over):
+    fl = dict(cfg["flags"]); fl.update(flag_over)
+    ur = ref_random(cfg, seed)
+    fr = refcf.nonlinear(ur, refcf.make_flags(**fl))
+    fg = cf.nonlinear(to_gpu(lib, ur), cf.make_flags(**fl))
+    a, b = fg.get().copy(), fr.data.copy()
+    if fl.get("dealiasing", "xz") in ("none", "y"):
+        # without xz-dealiasing the reference also fills the Nyquist modes kx = Nx/2, kz = Nz/2 of f; NSE::solve never
+        # reads them (nse.cpp:498 skips kxmax/kzmax), and this implementation does not produce them
+        for arr in (a, b):
+            c = arr.view(np.complex128)
+            c[:, :, cfg["Nx"] // 2, :] = 0
+            c[:, :, :, cfg["Nz"] // 2] = 0
+    return {"nonlinear": rel_l2(a, b), "scale": float(np.abs(fr.data).max())}
+
+
+def dns_steps(lib, cfg, checkpoints=(1, 10), seed=1, u0=None, **flag_over):
+    """Advance the same initial field with the reference DNS and with ours; relative L2 error of u at checkpoints."""
+    fl = dict(cfg["flags"]); fl.update(flag_over)
+    ur = u0 if u0 is not None else ref_random(cfg, seed)
+    rd = refcf.RefDNS(ur, refcf.make_flags(**fl))
+    gd = cf.DNS(to_gpu(lib, ur), cf.make_flags(**fl))
+    out, done = {"cfl0": abs(gd.cfl() - rd.cfl()) / max(abs(rd.cfl()), 1e-300)}, 0
+    for n in checkpoints:
+        rd.advance(n - done); gd.advance(n - done); done = n
+        u1, q1 = rd.get(); u2, q2 = gd.get()
+        out[n] = rel_l2(u2.get(), u1.data)
+        out["q%d" % n] = rel_l2(q2.get(), q1.data)
+    out["dPdx"] = abs(gd.dPdx() - rd.dPdx())
+    out["cfl_end"] = abs(gd.cfl() - rd.cfl()) / max(abs(rd.cfl()), 1e-300)
+    out["div"] = u2_div(u2)
+    return out
+
+
+def u2_div(ug):
+    """divergence + wall BC norm of a device field, evaluated by the reference's own divNorm/bcNorm."""
+    r = refcf.RefField(ug.Nx, ug.Ny, ug.Nz, ug.Nd, ug.Lx, ug.Lz, ug.a, ug.b)
+    r.data[...] = ug.get()
+    r.set_padded(True)
+    return (r.divnorm(), r.bcnorm())
+
+
+def tausolve_modes(lib, cfg, lam_t=11.0 / 6 / 0.02, nu=1.0 / 400, seed=5):
+    """C-ABI cfgpu_nse_solve against the reference TauSolver, mode by mode."""
+    ctx = cf.Context(lib.gpu)
+    Nx, Ny, Nz, Lx, Lz, a, b = (cfg[k] for k in ("Nx", "Ny", "Nz", "Lx", "Lz", "a", "b"))
+    nse = cf.Nse(ctx, Nx, Ny, Nz, Lx, Lz, a, b, Ubase=np.zeros(Ny), Wbase=np.zeros(Ny), nu=nu)
+    nse.reset_lambda([lam_t])
+    R = ref_random(cfg, seed, magn=1.0)
+    Rg = ctx.field(Nx, Ny, Nz, 3, Lx, Lz, a, b).upload(R.data, padded=True)
+    uo, qo = Rg.like(), Rg.like(Nd=1)
+    nse.solve(0, [1.0], [Rg], uo, qo)
+    du, dq, Rc = uo.download().view(np.complex128), qo.download().view(np.complex128), R.cdata
+    Kx, Kz = Nx // 3 - 1, Nz // 3 - 1
+    err, scale = 0.0, 0.0
+    for kx in range(-Kx, Kx + 1):
+        for kz in range(0, Kz + 1):
+            mx = kx % Nx
+            lam = lam_t + 4 * np.pi ** 2 * nu * ((kx / Lx) ** 2 + (kz / Lz) ** 2)
+            sol = refcf.tausolve(kx, kz, Lx, Lz, a, b, lam, nu, Ny, *(Rc[i, :, mx, kz].copy() for i in range(3)))
+            if kx == 0 and kz == 0:
+                sol = tuple(x.real + 0j for x in sol)
+            mine = (du[0, :, mx, kz], du[1, :, mx, kz], du[2, :, mx, kz], dq[0, :, mx, kz])
+            for s_, m_ in zip(sol, mine):
+                err = max(err, float(np.abs(s_ - m_).max()))
+                scale = max(scale, float(np.abs(s_).max()))
+    return {"tau_abs_err": err, "scale": scale}
+
+
+def golden_pair(lib, nsteps=440):
+    """tests/timeIntegrationTest.cpp: uinit -> 440 SBDF3 steps (11 x advance(40)) -> compare with ufinal (L2Dist)."""
+    g = np.load(os.path.join(GOLDEN, "golden_pair.npz"))
+    geo = dict(Nx=int(g["Nx"]), Ny=int(g["Ny"]), Nz=int(g["Nz"]), Lx=float(g["Lx"]), Lz=float(g["Lz"]), a=float(g["a"]), b=float(g["b"]))
+    ur = refcf.RefField(geo["Nx"], geo["Ny"], geo["Nz"], 3, geo["Lx"], geo["Lz"], geo["a"], geo["b"]).load_padded_physical(g["uinit"])
+    vr = ur.like().load_padded_physical(g["ufinal"])
+    fl = dict(nu=1.0 / 400, Vsuck=1.0 / 400, dt=1.0 / 40, baseflow="suction", constraint="gradp", dPdx=0.0)
+    gd = cf.DNS(to_gpu(lib, ur), cf.make_flags(**fl))
+    done = 0
+    while done < nsteps:
+        n = min(40, nsteps - done)
+        gd.cfl()
+        gd.advance(n)
+        done += n
+    u2, _ = gd.get()
+    out = {"l2dist_to_ufinal": to_gpu(lib, vr).l2dist(u2), "norm_final": u2.l2norm(), "norm_ufinal": vr.l2norm()}
+    return out, ur, u2
+
+
+def smoke(cf_module=None):
+    """One small DNS step of the hot path on cuda:0, checked against the oracle (used by __graft_entry__.smoke)."""
+    lib = gpu_lib()
+    cfg = dict(C1, Nx=16, Ny=17, Nz=16)
+    r = dns_steps(lib, cfg, checkpoints=(1, 3))
+    assert r[1] < 1e-12 and r[3] < 1e-12, r
+    print("smoke ok:", r, "kernel launches:", lib.launch_count())
+    return r

@@ -1,0 +1,130 @@
+"""CPU tests (-m "not gpu"): the CUDA sources compiled for the fiber emulator (tests/emu) are run against the
+oracle on small grids -- kernel logic (indexing, shared-memory staging, barriers, DMMA fragment layout) and the C++
+host classes are exercised here; numbers measured on a GPU come only from the -m gpu tests."""
+import numpy as np
+import pytest
+
+import channelflow_b200 as cf
+from oracle import refcf
+from tests import parity
+
+pytestmark = pytest.mark.skipif(not refcf.available(), reason="oracle/_ref not built")
+
+SMALL = dict(parity.C1, Nx=16, Ny=17, Nz=12)
+ODD = dict(parity.C1, Nx=12, Ny=21, Nz=18, Lx=5.5, Lz=2.5, a=-1.0, b=1.0)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return parity.emu_lib()
+
+
+def test_cabi_symbols_product_library():
+    """libcfgpu.so (the nvcc build) loads without a GPU and exports every symbol include/cfgpu.h declares."""
+    import os
+    if not os.path.exists(cf.LIB_GPU):
+        pytest.skip("libcfgpu.so not built yet (python __graft_entry__.py)")
+    assert cf.check_symbols()
+
+
+def test_product_library_has_no_cpu_fallback():
+    import os
+    if not os.path.exists(cf.LIB_GPU):
+        pytest.skip("libcfgpu.so not built yet")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cf.CfgpuError):
+        cf.Context(cf.GpuLib())
+
+
+@pytest.mark.parametrize("cfg", [SMALL, ODD])
+def test_transforms(lib, cfg):
+    r = parity.transforms(lib, cfg)
+    assert max(r.values()) < 1e-14, r
+
+
+def test_norms(lib):
+    r = parity.norms(lib, SMALL)
+    assert max(r.values()) < 1e-14, r
+
+
+@pytest.mark.parametrize("over", [dict(), dict(Vsuck=0.0025, baseflow="suction"), dict(rotation=0.1), dict(dealiasing="none")])
+def test_nonlinear(lib, over):
+    r = parity.nonlinear(lib, SMALL, **over)
+    assert r["nonlinear"] < 1e-14, r
+
+
+def test_tausolve_bitwise(lib):
+    r = parity.tausolve_modes(lib, SMALL)
+    assert r["tau_abs_err"] <= 1e-15 * max(r["scale"], 1.0), r
+
+
+@pytest.mark.parametrize("stepper", ["sbdf3", "sbdf1", "sbdf2", "sbdf4", "cnfe1", "cnab2", "smrk2", "cnrk2"])
+def test_dns_steppers(lib, stepper):
+    r = parity.dns_steps(lib, SMALL, checkpoints=(1, 5), timestepping=stepper)
+    assert r[1] < 1e-12 and r[5] < 1e-12 and r["cfl0"] < 1e-13, r
+
+
+def test_dns_bulk_velocity_constraint(lib):
+    r = parity.dns_steps(lib, SMALL, checkpoints=(1, 4), constraint="bulkv", Ubulk=0.0)
+    assert r[1] < 1e-12 and r[4] < 1e-12 and r["dPdx"] < 1e-12, r
+
+
+def test_dns_poiseuille_bulkv(lib):
+    r = parity.dns_steps(lib, ODD, checkpoints=(1, 4), constraint="bulkv", Ubulk=2.0 / 3, ulowerwall=0.0, uupperwall=0.0,
+                         nu=1 / 1800.0)
+    assert r[1] < 1e-12 and r[4] < 1e-12 and r["dPdx"] < 1e-11, r
+
+
+def test_dns_suction_golden_flags(lib):
+    r = parity.dns_steps(lib, ODD, checkpoints=(1, 4), nu=1 / 400, Vsuck=1 / 400, dt=1 / 40, baseflow="suction")
+    assert r[1] < 1e-12 and r[4] < 1e-12, r
+
+
+def test_dns_c1_one_step(lib):
+    """north_star gate on configs[0] (32x33x32): relative L2 <= 1e-12 after one step."""
+    r = parity.dns_steps(lib, parity.C1, checkpoints=(1, 3))
+    assert r[1] < 1e-12 and r[3] < 1e-12, r
+    assert r["div"][0] < 1e-12 and r["div"][1] < 1e-12, r
+
+
+def test_ff_file_roundtrip(lib, tmp_path):
+    ur = parity.ref_random(SMALL, 7)
+    ug = parity.to_gpu(lib, ur)
+    ug.zero_padded_modes()  # the padded .ff format stores the retained modes only
+    ug.save(str(tmp_path / "u"))
+    h = lib.L.cf_field_load(str(tmp_path / "u").encode())
+    v = cf.FlowField(lib, ug.Nx, ug.Ny, ug.Nz, 3, ug.Lx, ug.Lz, handle=h)
+    assert np.abs(v.get() - ug.get()).max() == 0.0
+
+
+def test_element_access_mirror(lib):
+    ur = parity.ref_random(SMALL, 8)
+    ug = parity.to_gpu(lib, ur)
+    c = ug.cmplx(1, 3, 2, 0)
+    assert c == ur.cdata[0, 3, 1, 2]
+    ug.set_cmplx(1, 3, 2, 0, c + 1.0)
+    ug.make_physical_y(); ug.make_spectral_y()
+    assert abs(ug.cmplx(1, 3, 2, 0) - (c + 1.0)) < 1e-14
+
+
+def test_timestep_logic(lib):
+    """TimeStep::adjust / adjust_for_T (reference tests/gtest/timesteptest.cpp semantics)."""
+    L = lib.L
+    ts = L.cf_timestep_create(0.03125, 0.001, 0.2, 1.0, 0.4, 0.6, 1)
+    assert L.cf_timestep_n(ts) == 32 and abs(L.cf_timestep_dt(ts) - 1 / 32) < 1e-16
+    assert L.cf_timestep_adjust(ts, 0.5) == 0
+    assert L.cf_timestep_adjust(ts, 1.0) == 1 and L.cf_timestep_n(ts) == 64
+    assert L.cf_timestep_adjust(ts, 0.1) == 1 and L.cf_timestep_n(ts) == 13
+    L.cf_timestep_adjust_for_T(ts, 10.5)
+    assert L.cf_timestep_N(ts) == 11 and abs(L.cf_timestep_dT(ts) * 11 - 10.5) < 1e-13
+    L.cf_timestep_free(ts)
+
+
+def test_laminar_profiles(lib):
+    for kw in (dict(ulowerwall=-1, uupperwall=1), dict(constraint="bulkv", Ubulk=2 / 3.0), dict(Vsuck=0.0025, baseflow="suction"),
+               dict(Vsuck=1e-5, ulowerwall=0, uupperwall=1), dict(dPdx=-0.01)):
+        a = cf.laminar_profile(lib, cf.make_flags(**kw), -1.0, 1.0, 33)
+        b = refcf.laminar_profile(refcf.make_flags(**kw), -1.0, 1.0, 33)
+        assert np.abs(a - b).max() < 1e-14, kw

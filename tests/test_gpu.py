@@ -1,0 +1,131 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI / host classes, against the oracle
+(the unmodified reference compiled in oracle/_ref, shipped prebuilt to the GPU box) and the committed golden
+fixtures.  Tolerances are the ones BASELINE.json's north_star states: relative L2 <= 1e-12 after one step,
+<= 1e-9 after 100 steps, golden pair L2Dist <= 1e-13 (timeIntegrationTest.cpp:42)."""
+import numpy as np
+import pytest
+
+import channelflow_b200 as cf
+from oracle import refcf
+from tests import parity
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refcf.available(), reason="oracle/_ref missing")]
+
+SMALL = dict(parity.C1, Nx=16, Ny=17, Nz=12)
+ODD = dict(parity.C1, Nx=12, Ny=21, Nz=18, Lx=5.5, Lz=2.5)
+MID = dict(parity.C1, Nx=48, Ny=49, Nz=48, Lx=2 * np.pi / 1.14, Lz=2 * np.pi / 2.5)
+BIG = dict(parity.C1, Nx=96, Ny=97, Nz=64)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return parity.gpu_lib()
+
+
+def test_native_library_is_cuda(lib):
+    assert b"sm_100a" in lib.gpu.L.cfgpu_version()
+    assert not lib.gpu.missing_symbols()
+
+
+@pytest.mark.parametrize("cfg", [SMALL, ODD, parity.C1, MID, BIG])
+def test_transforms(lib, cfg):
+    r = parity.transforms(lib, cfg)
+    assert max(r.values()) < 1e-13, r
+
+
+@pytest.mark.parametrize("cfg", [SMALL, MID])
+def test_norms(lib, cfg):
+    r = parity.norms(lib, cfg)
+    assert max(r.values()) < 1e-13, r
+
+
+@pytest.mark.parametrize("over", [dict(), dict(Vsuck=0.0025, baseflow="suction"), dict(rotation=0.1), dict(dealiasing="none")])
+@pytest.mark.parametrize("cfg", [SMALL, MID])
+def test_nonlinear(lib, cfg, over):
+    r = parity.nonlinear(lib, cfg, **over)
+    assert r["nonlinear"] < 1e-13, r
+
+
+@pytest.mark.parametrize("cfg", [SMALL, parity.C1])
+def test_tausolve_modes(lib, cfg):
+    r = parity.tausolve_modes(lib, cfg)
+    assert r["tau_abs_err"] <= 1e-13 * max(r["scale"], 1.0), r
+
+
+@pytest.mark.parametrize("stepper", ["sbdf3", "sbdf1", "sbdf2", "sbdf4", "cnfe1", "cnab2", "smrk2", "cnrk2"])
+def test_dns_steppers(lib, stepper):
+    r = parity.dns_steps(lib, SMALL, checkpoints=(1, 5), timestepping=stepper)
+    assert r[1] < 1e-12 and r[5] < 1e-12 and r["cfl0"] < 1e-12, r
+
+
+def test_dns_bulk_velocity(lib):
+    r = parity.dns_steps(lib, ODD, checkpoints=(1, 4), constraint="bulkv", Ubulk=2.0 / 3, ulowerwall=0.0, uupperwall=0.0,
+                         nu=1 / 1800.0)
+    assert r[1] < 1e-12 and r[4] < 1e-12 and r["dPdx"] < 1e-11, r
+
+
+def test_c1_one_step_and_100_steps(lib):
+    """BASELINE.json configs[0]: plane Couette Re=400, 32x33x32, SBDF3, rotational, dealiased, dt=0.02."""
+    r = parity.dns_steps(lib, parity.C1, checkpoints=(1, 100))
+    assert r[1] <= 1e-12, r
+    assert r[100] <= 1e-9, r
+    assert r["div"][0] < 1e-12 and r["div"][1] < 1e-12, r
+
+
+def test_mid_grid_steps(lib):
+    r = parity.dns_steps(lib, MID, checkpoints=(1, 10), nu=1 / 400, Vsuck=1 / 400, dt=1 / 40, baseflow="suction")
+    assert r[1] <= 1e-12 and r[10] <= 1e-11, r
+
+
+def test_golden_pair(lib):
+    """tests/data/uinit.nc -> 440 SBDF3 steps -> ufinal.nc, L2Dist <= 1e-13 (the reference's own regression test)."""
+    r, _, _ = parity.golden_pair(lib)
+    assert r["l2dist_to_ufinal"] <= 1e-13, r
+
+
+def test_full_size_band_limited_consistency(lib):
+    """Size-independent property at the bench grid (512x257x512): a field that only excites the modes retained by a
+    coarse 48x257x48 grid must, after one step on the fine grid, agree on those modes with the reference's step on
+    the coarse grid (the dealiased quadratic term is exact on both)."""
+    coarse = dict(parity.C1, Nx=48, Ny=257, Nz=48)
+    fine = dict(coarse, Nx=512, Nz=512)
+    ur = parity.ref_random(coarse, seed=11)
+    fl = dict(coarse["flags"], timestepping="sbdf1")
+    rd = refcf.RefDNS(ur, refcf.make_flags(**fl))
+    rd.advance(1)
+    u1, _ = rd.get()
+    # embed the coarse spectrum into the fine grid
+    Mzc, Mzf = coarse["Nz"] // 2 + 1, fine["Nz"] // 2 + 1
+    big = np.zeros((3, 257, fine["Nx"], Mzf), dtype=np.complex128)
+    Kx, Kz = coarse["Nx"] // 3 - 1, coarse["Nz"] // 3 - 1
+    src = ur.cdata
+    for kx in range(-Kx, Kx + 1):
+        big[:, :, kx % fine["Nx"], :Kz + 1] = src[:, :, kx % coarse["Nx"], :Kz + 1]
+    ug = cf.FlowField(lib, fine["Nx"], 257, fine["Nz"], 3, fine["Lx"], fine["Lz"]).set(big.view(np.float64), padded=True)
+    gd = cf.DNS(ug, cf.make_flags(**fl))
+    gd.advance(1)
+    u2, _ = gd.get()
+    out = u2.get().view(np.complex128)
+    ref = u1.cdata
+    num = den = 0.0
+    for kx in range(-Kx, Kx + 1):
+        d = out[:, :, kx % fine["Nx"], :Kz + 1] - ref[:, :, kx % coarse["Nx"], :Kz + 1]
+        num += float(np.sum(np.abs(d) ** 2))
+        den += float(np.sum(np.abs(ref[:, :, kx % coarse["Nx"], :Kz + 1]) ** 2))
+    assert np.sqrt(num / den) < 1e-11, np.sqrt(num / den)
+
+
+def test_full_size_roundtrip(lib):
+    """makePhysical -> makeSpectral is the identity at 512x257x512 (idempotence)."""
+    rng = np.random.default_rng(0)
+    u = cf.FlowField(lib, 512, 257, 512, 1, 4 * np.pi, 2 * np.pi)
+    a = np.zeros(u.shape)
+    c = a.view(np.complex128)
+    c[:, :40, :20, :20] = rng.standard_normal((1, 40, 20, 20)) + 1j * rng.standard_normal((1, 40, 20, 20))
+    c[:, :, 0, 0] = c[:, :, 0, 0].real
+    c[:, :, 1:20, 0] = 0  # keep the kz=0 plane Hermitian without building conjugates
+    u.set(a)
+    u.make_physical()
+    u.make_spectral()
+    b = u.get()
+    assert parity.rel_l2(b, a) < 1e-13
