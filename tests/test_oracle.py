@@ -15,12 +15,12 @@ REFBIN = os.path.join(parity.ROOT, "oracle", "_ref", "bin")
 
 
 @pytest.mark.parametrize("prog", ["tridiagTest", "chebyTest", "helmholtzTest", "tausolverTest", "poissonTest", "laminarTest"])
-def test_reference_unit_programs_pass_on_shim(prog):
+def test_reference_unit_programs_pass_on_shim(prog, tmp_path):
     """The reference's own test programs (tests/*.cpp, own tolerances 1e-12..1e-9) linked against our FFTW shim."""
     exe = os.path.join(REFBIN, prog)
     if not os.path.exists(exe):
         pytest.skip("reference test binaries not built (make -C oracle reftests)")
-    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, cwd=str(tmp_path))  # some write *.asc dumps
     assert r.returncode == 0, r.stdout.decode()[-2000:]
 
 
