@@ -82,7 +82,7 @@ struct cfgpu_nse_s {
     double Lx = 0, Lz = 0, a = 0, b = 0;
     cfgpu_nse_config cfg;
     int Nyd = 0, Kx = 0, Kz = 0;
-    int nq = 0, ldq = 0;
+    int nq = 0;
     cfgpu::ModeGeom geom;
     double* d_base = nullptr;   // device: Ubaseyy[Ny], Wbaseyy[Ny], phys U,U',W,W' [4*Ny], inv_dy[Ny]
     bool has_Ubaseyy = false, has_Wbaseyy = false;
@@ -90,7 +90,7 @@ struct cfgpu_nse_s {
     double* d_scal = nullptr;   // device scalars: [0] cfl max, [1] dPdxAct, [2] dPdzAct
     std::vector<double> lambda_t;
     std::vector<cfgpu::TauData> tau;  // one per substep
-    int TM_solve = 8, TM_setup = 8;
+    int TM_solve = 8, TM_lin = 8;
 };
 
 namespace cfgpu {

@@ -131,11 +131,10 @@ int cfgpu_nse_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, double Lx, double Lz
     CF_ARG(nse->Kx >= 0 && nse->Kz >= 0, "cfgpu_nse_create: grid too small");
     CF_ARG(nse->Nyd % 2 == 1, "cfgpu_nse_create: dealiased Ny must be odd");
     nse->nq = (2 * nse->Kx + 1) * (nse->Kz + 1);
-    nse->ldq = (nse->nq + 31) & ~31;
     nse->geom.Nx = Nx; nse->geom.Ny = Ny; nse->geom.Nz = Nz; nse->geom.Kx = nse->Kx; nse->geom.Kz = nse->Kz;
     nse->geom.Lx = Lx; nse->geom.Lz = Lz;
-    nse->TM_solve = tau_pick_TM(nse->Nyd, 6 * 2 * 8);
-    nse->TM_setup = tau_pick_TM(nse->Nyd, 3 * 8);
+    nse->TM_solve = tau_pick_TM_solve(nse->Nyd);
+    nse->TM_lin = tau_pick_TM(nse->Nyd, 5 * 2 * 8);
 
     // base-flow data: Ubaseyy, Wbaseyy (spectral), physical U,U',W,W', 1/dy
     std::vector<double> U(Ny, 0.0), W(Ny, 0.0), Uy, Uyy, Wy, Wyy, t;
@@ -203,19 +202,24 @@ int cfgpu_nse_reset_lambda(cfgpu_nse nse, const double* lambda_t_h, int nsub) {
     cfgpu_ctx ctx = nse->ctx;
     while ((int)nse->tau.size() < nsub) {
         TauData td;
-        td.N = nse->Nyd; td.nq = nse->nq; td.ldq = nse->ldq; td.nu = nse->cfg.nu; td.a = nse->a; td.b = nse->b;
-        const size_t n = TauData::doubles(td.N, td.ldq);
+        td.N = nse->Nyd; td.nq = nse->nq; td.TM = nse->TM_solve; td.ntiles = TauData::num_tiles(td.nq, td.TM);
+        td.nu = nse->cfg.nu; td.a = nse->a; td.b = nse->b;
+        const size_t n = TauData::doubles(td.N, td.nq, td.TM);
         if (cudaMalloc((void**)&td.base, n * sizeof(double)) != cudaSuccess) {
             set_last_error("cfgpu_nse_reset_lambda: cudaMalloc failed");
             return 1;
         }
         CF_CUDA(cudaMemsetAsync(td.base, 0, n * sizeof(double), ctx->stream));
+        std::vector<double> bt(3 * (size_t)td.N);
+        tau_btab_host(td.N, bt.data());
+        CF_CUDA(cudaMemcpyAsync(td.btab(), bt.data(), bt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CF_CUDA(cudaStreamSynchronize(ctx->stream));
         nse->tau.push_back(td);
     }
     nse->lambda_t.assign(lambda_t_h, lambda_t_h + nsub);
     for (int s = 0; s < nsub; ++s) {
         nse->tau[s].nu = nse->cfg.nu;
-        { StageTimer _t(ctx, 7); CF_TRY(tau_setup_launch(nse->tau[s], nse->geom, lambda_t_h[s], nse->TM_setup, ctx->stream)); }
+        { StageTimer _t(ctx, 7); CF_TRY(tau_setup_launch(nse->tau[s], nse->geom, lambda_t_h[s], ctx->stream)); }
     }
     return 0;
 }
@@ -282,7 +286,7 @@ static int fill_tau_params(cfgpu_nse nse, int s, TauSolveParams& tp) {
     memset(&tp, 0, sizeof tp);
     tp.td = nse->tau[s];
     tp.g = nse->geom;
-    tp.TM = nse->TM_solve;
+    tp.TM_lin = nse->TM_lin;
     tp.taucorr = nse->cfg.taucorrection;
     tp.Ubaseyy = nse->has_Ubaseyy ? nse->d_base : nullptr;
     tp.Wbaseyy = nse->has_Wbaseyy ? nse->d_base + nse->Ny : nullptr;

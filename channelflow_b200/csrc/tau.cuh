@@ -7,26 +7,37 @@
 // multistep right-hand-side accumulation (dnsalgo.cpp:217-224, FlowField::add flowfield.h:606-615), which is fused
 // into the solve kernel as a linear combination of history fields.
 //
-// Storage (HBM): every per-mode array is [row n][mode q] with q fastest ("SoA"), so a warp touching one row reads
-// consecutive doubles.  Per mode and substep: 12*N + NSC doubles (UL factors of the pressure and velocity
-// Helmholtz operators, the 6 precomputed profiles P+-, v+-, P0, v0, and scalars).
+// Storage (HBM): tile-major.  The retained modes are grouped into tiles of TM consecutive modes (the unit of work of
+// one CTA of the solve kernel); tile 0 holds the (0,0) mode alone, tile 1+(q-1)/TM holds mode q >= 1 at position
+// (q-1)%TM.  Per tile: 12 arrays [n][TM] (UL factors of the pressure and velocity Helmholtz operators, the six
+// precomputed profiles P+-, v+-, P0, v0) followed by TSC_COUNT scalars [TM] -- one contiguous block, so a CTA
+// streams its factors with fully coalesced loads.  A mode-independent table of the C&H 5.1.24 "B" rows follows.
 #pragma once
 #include "cf_common.cuh"
 
 namespace cfgpu {
 
 enum { TSC_LAMP = 0, TSC_LAMV, TSC_KXX, TSC_KZZ, TSC_I00, TSC_I01, TSC_I10, TSC_I11, TSC_S0NB1, TSC_S0NB, TSC_COUNT };
+// which: 0 upP 1 invP 2 bandP 3 upV 4 invV 5 bandV 6 Pp 7 vp 8 Pm 9 vm 10 P0 11 v0
+enum { TAR_UPP = 0, TAR_INVP, TAR_BANDP, TAR_UPV, TAR_INVV, TAR_BANDV, TAR_PP, TAR_VP, TAR_PM, TAR_VM, TAR_P0, TAR_V0, TAR_COUNT };
 
 struct TauData {
     int N;       // number of Chebyshev modes in the solve (Nyd)
     int nq;      // retained modes, q = mxi*(Kz+1) + kz ; q = 0 is the (0,0) mode
-    int ldq;     // nq rounded up to 32
+    int TM;      // modes per tile
+    int ntiles;  // 1 + ceil((nq-1)/TM)
     double nu, a, b;
     double* base;  // single allocation
-    __host__ __device__ double* arr(int which) const { return base + (size_t)which * N * ldq; }
-    // which: 0 upP 1 invP 2 bandP 3 upV 4 invV 5 bandV 6 Pp 7 vp 8 Pm 9 vm 10 P0 11 v0
-    __host__ __device__ double* sc(int which) const { return base + (size_t)12 * N * ldq + (size_t)which * ldq; }
-    static size_t doubles(int N, int ldq) { return (size_t)(12 * N + TSC_COUNT) * ldq; }
+    __host__ __device__ size_t tile_doubles() const { return (size_t)(TAR_COUNT * N + TSC_COUNT) * TM; }
+    __host__ __device__ double* tile(int tl) const { return base + (size_t)tl * tile_doubles(); }
+    __host__ __device__ double* tile_arr(int tl, int which) const { return tile(tl) + (size_t)which * N * TM; }   // [n][TM]
+    __host__ __device__ double* tile_sc(int tl, int which) const { return tile(tl) + (size_t)TAR_COUNT * N * TM + (size_t)which * TM; }
+    __host__ __device__ double* btab() const { return base + (size_t)ntiles * tile_doubles(); }  // [3][N]: B_lo, B_dg, B_up
+    __host__ __device__ static int tile_of(int q, int TM) { return q == 0 ? 0 : 1 + (q - 1) / TM; }
+    __host__ __device__ static int pos_of(int q, int TM) { return q == 0 ? 0 : (q - 1) % TM; }
+    __host__ __device__ double& scq(int which, int q) const { return tile_sc(tile_of(q, TM), which)[pos_of(q, TM)]; }
+    static int num_tiles(int nq, int TM) { return 1 + (nq - 1 + TM - 1) / TM; }
+    static size_t doubles(int N, int nq, int TM) { return (size_t)num_tiles(nq, TM) * (TAR_COUNT * N + TSC_COUNT) * TM + 3 * (size_t)N; }
 };
 
 struct ModeGeom {
@@ -39,7 +50,7 @@ constexpr int TAU_MAXTERMS = 10;
 struct TauSolveParams {
     TauData td;
     ModeGeom g;
-    int TM;            // modes per CTA
+    int TM_lin;        // modes per CTA of the linear-term kernel
     int taucorr;
     int nterms;
     const double* term[TAU_MAXTERMS];  // 3-component fields, reference layout
@@ -56,8 +67,10 @@ struct TauSolveParams {
     double lin_base_dPdx, lin_base_dPdz;
 };
 
-int tau_setup_launch(const TauData& td, const ModeGeom& g, double lambda_t, int TM, cudaStream_t stream);
+int tau_setup_launch(const TauData& td, const ModeGeom& g, double lambda_t, cudaStream_t stream);
+void tau_btab_host(int N, double* tab /* [3*N] */);
 int tau_solve_launch(const TauSolveParams& p, cudaStream_t stream);
 int tau_pick_TM(int N, int narrays_bytes_per_mode_row);
+int tau_pick_TM_solve(int N);
 
 }  // namespace cfgpu
