@@ -66,6 +66,15 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 #endif
 }
 
+// ---- L2 prefetch of one 128-byte line ----
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef CF_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // ---- atomic max on a double (signed compare, as the reference's CFL max has no abs) ----
 __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
     unsigned long long* p = reinterpret_cast<unsigned long long*>(addr);

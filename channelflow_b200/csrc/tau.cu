@@ -57,14 +57,14 @@ __device__ __forceinline__ void ul_solve_chain(double* g, int N, int TT, int t, 
                                                const double* inv, const double* band, int TM, int m, double lam) {
     const int Nb = N - 1;
     const int nl = par ? Nb - 1 : Nb;
-    for (int n = nl - 2; n >= par + 2; n -= 2) g[n * TT + t] -= up[n * TM + m] * g[(n + 2) * TT + t];
+    for (int n = nl - 2; n >= par + 2; n -= 2) g[n * TT + t] -= up[m * N + n] * g[(n + 2) * TT + t];
     double acc = g[par * TT + t];
-    for (int n = par + 2; n <= nl; n += 2) acc -= band[n * TM + m] * g[n * TT + t];
-    acc /= inv[par * TM + m];  // slot `par` of inv holds diag(0) of this parity block
+    for (int n = par + 2; n <= nl; n += 2) acc -= band[m * N + n] * g[n * TT + t];
+    acc /= inv[m * N + par];  // slot `par` of inv holds diag(0) of this parity block
     g[par * TT + t] = acc;
     double prev = acc;
     for (int n = par + 2; n <= nl; n += 2) {
-        const double v = (g[n * TT + t] - A_lo(n, Nb, lam) * prev) * inv[n * TM + m];
+        const double v = (g[n * TT + t] - A_lo(n, Nb, lam) * prev) * inv[m * N + n];
         g[n * TT + t] = v;
         prev = v;
     }
@@ -118,77 +118,218 @@ __device__ __forceinline__ void tile_modes(int tl, int TM, int nq, int& q0, int&
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One Helmholtz solve  A x = B r  (+ boundary row value bc) for the real and imaginary parts of one (mode, parity),
-// fully fused (helmholtz.cpp:79-95 + bandedtridiag.cpp:232-277):
-//   backward sweep, n = nl .. par+2:  g_n = B_lo r_{n-2} + B_dg r_n + B_up r_{n+2} ;  x_n = g_n - up_n x_{n+2} ;
-//                                     acc -= band_n x_n            (row 0 of the bordered system)
-//   row 0:                            x_par = (bc + acc) / diag0
-//   forward sweep, n = par+2 .. nl:   x_n = (x_n - lo_n x_{n-2}) inv_n
-// rhs(n, re, im) is called for n = nl, nl-2, .., par in strictly descending order (it may carry running sums) and may
-// read X at rows < n' for any n' not yet written (rows are written in descending order, one step behind the reads),
-// which is what allows the in-place use.  X points at the (re) column of the mode: X[n*TT], X[n*TT+1].
-// Optionally accumulates S = sum_n n^2 x_n (wall derivative of the solution, see the influence-matrix step).
-template <class RhsF>
-__device__ __forceinline__ void helm_chain(double* __restrict__ X, const int N, const int TT, const int par, const double* __restrict__ up,
-                                           const double* __restrict__ inv, const double* __restrict__ band, const double* __restrict__ lo,
-                                           const int TM, const double* __restrict__ btab, const double bc_re, const double bc_im,
-                                           RhsF rhs, double* wall_re, double* wall_im) {
+// Warp-parallel column solver.  One warp owns one real "column" (the real or imaginary part of one mode's Chebyshev
+// profile); lane l holds the E consecutive coefficients n = l*E .. l*E+E-1 in registers (E even, so the slot parity
+// is the parity of n and the even/odd blocks of the quasi-tridiagonal system interleave in the slots).
+// Every recurrence of the reference (derivative recurrence chebyshev.cpp:672-697, UL back/forward substitution
+// bandedtridiag.cpp:258-273) is a first-order linear recurrence x_n = a_n x_{n+-2} + b_n, evaluated as a blocked
+// scan: compose the lane-local affine map, combine the 32 lane maps with a log-step shuffle scan, then redo the
+// local recurrence from the exact incoming value with the reference's own formula.
+// Shared-memory columns are stored skewed, addr(n) = n + n/E, i.e. lane l starts at l*(E+1): consecutive lanes are
+// an odd number of 8-byte words apart, which makes the per-lane contiguous accesses bank-conflict free.
+
+template <int E>
+__device__ __forceinline__ int col_addr(int n) { return n + n / E; }
+
+template <int E>
+__device__ __forceinline__ void col_load(const double* __restrict__ col, int lane, int N, double (&v)[E]) {
+    const double* p = col + lane * (E + 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = (lane * E + e < N) ? p[e] : 0.0;
+}
+template <int E>
+__device__ __forceinline__ void col_store(double* __restrict__ col, int lane, int N, const double (&v)[E]) {
+    double* p = col + lane * (E + 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (lane * E + e < N) p[e] = v[e];
+}
+
+__device__ __forceinline__ double shfl_down_or(double v, int d, int lane, double fill) {
+    const double t = __shfl_down_sync(0xffffffffu, v, d);
+    return lane + d < 32 ? t : fill;
+}
+__device__ __forceinline__ double shfl_up_or(double v, int d, int lane, double fill) {
+    const double t = __shfl_up_sync(0xffffffffu, v, d);
+    return lane >= d ? t : fill;
+}
+
+// d = du/dy (chebyshev.cpp:672-697): d_n = sum_{m > n, m-n odd} (scale*m) u_m, d_0 *= 1/2.  u, d in lane registers.
+template <int E>
+__device__ __forceinline__ void col_deriv(const double (&u)[E], double (&d)[E], double scale, int lane) {
+    double c[E];
+    double tot[2] = {0.0, 0.0};  // lane totals of the even-m / odd-m terms
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e) {
+        c[e] = scale * (lane * E + e) * u[e];
+        tot[e & 1] = tot[e & 1] + c[e];
+    }
+    // inclusive suffix sum over lanes, then shift to exclusive
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const double t0 = __shfl_down_sync(0xffffffffu, tot[0], s), t1 = __shfl_down_sync(0xffffffffu, tot[1], s);
+        if (lane + s < 32) {
+            tot[0] += t0;
+            tot[1] += t1;
+        }
+    }
+    double run[2];
+    run[0] = shfl_down_or(tot[0], 1, lane, 0.0);
+    run[1] = shfl_down_or(tot[1], 1, lane, 0.0);
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e) {
+        d[e] = run[(e & 1) ^ 1];
+        run[e & 1] = run[e & 1] + c[e];
+    }
+    if (lane == 0) d[0] *= 0.5;
+}
+
+// Solve  A x = B r  with boundary-row values bc (both parity blocks of one Helmholtz operator, helmholtz.cpp:79-95):
+//   g_n = B_lo r_{n-2} + B_dg r_n + B_up r_{n+2}  (n >= 2)
+//   back substitution   x_n = g_n - up_n x_{n+2}         n = nl .. par+2          (bandedtridiag.cpp:258-262)
+//   bordered row        x_par = (bc - sum band_n x_n) / diag0                      (:263-268; diag0 in slot `par` of inv)
+//   forward elimination x_n = (x_n - lo_n x_{n-2}) inv_n  n = par+2 .. nl          (:269-273), lo_n = A_lo(n, lambda)
+// r (in) and x (out) are lane registers; up/inv/band/lo are skewed shared-memory columns, bt the B rows in HBM (L1).  If wall != nullptr the
+// sums  S_p = sum_{n = p mod 2} n^2 x_n  are returned in wall[0..1] (all lanes).
+template <int E>
+__device__ __forceinline__ void col_solve(const double (&r)[E], double (&x)[E], const double* __restrict__ up,
+                                          const double* __restrict__ inv, const double* __restrict__ band,
+                                          const double* __restrict__ lo, const double* __restrict__ bt, const int N, const int lane,
+                                          const double bc0, const double bc1, double* wall) {
     const int Nb = N - 1;
-    const int nl = par ? Nb - 1 : Nb;
-    const double* __restrict__ Blo = btab;
-    const double* __restrict__ Bdg = btab + N;
-    const double* __restrict__ Bup = btab + 2 * N;
-    double rc_re, rc_im, rp_re = 0.0, rp_im = 0.0;
-    rhs(nl, rc_re, rc_im);
-    double xr = 0.0, xi = 0.0, acc_re = bc_re, acc_im = bc_im;
-#pragma unroll 2
-    for (int n = nl; n >= par + 2; n -= 2) {
-        double rm_re, rm_im;
-        rhs(n - 2, rm_re, rm_im);
-        const double blo = Blo[n], bdg = Bdg[n];
-        double g_re = blo * rm_re + bdg * rc_re;
-        double g_im = blo * rm_im + bdg * rc_im;
-        if (n + 2 <= Nb) {
-            const double bup = Bup[n];
-            g_re += bup * rp_re;
-            g_im += bup * rp_im;
+    const int n0 = lane * E, a0 = lane * (E + 1);
+    double g[E];
+    {
+        // neighbours two rows away (other lanes at the block edges)
+        double lo2[2], hi2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            lo2[e] = shfl_up_or(r[E - 2 + e], 1, lane, 0.0);
+            hi2[e] = shfl_down_or(r[e], 1, lane, 0.0);
         }
-        if (n != nl) {
-            const double u = up[n * TM];
-            g_re -= u * xr;
-            g_im -= u * xi;
-        }
-        xr = g_re;
-        xi = g_im;
-        X[n * TT] = xr;
-        X[n * TT + 1] = xi;
-        const double bd = band[n * TM];
-        acc_re -= bd * xr;
-        acc_im -= bd * xi;
-        rp_re = rc_re; rp_im = rc_im;
-        rc_re = rm_re; rc_im = rm_im;
-    }
-    const double d0 = inv[par * TM];  // slot `par` of inv holds diag(0) of this parity block
-    double pr = acc_re / d0, pi = acc_im / d0;
-    X[par * TT] = pr;
-    X[par * TT + 1] = pi;
-    double sr = (double)(par * par) * pr, si = (double)(par * par) * pi;
-#pragma unroll 2
-    for (int n = par + 2; n <= nl; n += 2) {
-        const double l = lo[n * TM], iv = inv[n * TM];
-        const double vr = (X[n * TT] - l * pr) * iv;
-        const double vi = (X[n * TT + 1] - l * pi) * iv;
-        X[n * TT] = vr;
-        X[n * TT + 1] = vi;
-        pr = vr;
-        pi = vi;
-        if (wall_re) {
-            const double n2 = (double)(n * n);
-            sr += n2 * vr;
-            si += n2 * vi;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int n = n0 + e;
+            const double rm = e >= 2 ? r[e >= 2 ? e - 2 : 0] : lo2[e & 1];
+            const double rp = e < E - 2 ? r[e < E - 2 ? e + 2 : 0] : hi2[e & 1];
+            double v = 0.0;
+            if (n >= 2 && n < N) {
+                v = __ldg(&bt[n]) * rm + __ldg(&bt[N + n]) * r[e];
+                v += __ldg(&bt[2 * N + n]) * rp;
+            }
+            g[e] = v;
         }
     }
-    if (wall_re) { *wall_re = sr; *wall_im = si; }
+    // ---- back substitution
+    double u[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int n = n0 + e;
+        u[e] = (n >= 2 && n + 2 <= Nb) ? up[a0 + e] : 0.0;
+    }
+    {
+        double A[2] = {1.0, 1.0}, B[2] = {0.0, 0.0};
+#pragma unroll
+        for (int e = E - 1; e >= 0; --e) {
+            const int p = e & 1;
+            B[p] = g[e] - u[e] * B[p];
+            A[p] = -(u[e] * A[p]);
+        }
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const double A2 = __shfl_down_sync(0xffffffffu, A[p], s), B2 = __shfl_down_sync(0xffffffffu, B[p], s);
+                if (lane + s < 32) {
+                    B[p] = A[p] * B2 + B[p];
+                    A[p] = A[p] * A2;
+                }
+            }
+        }
+        double xin[2];
+        xin[0] = shfl_down_or(B[0], 1, lane, 0.0);
+        xin[1] = shfl_down_or(B[1], 1, lane, 0.0);
+#pragma unroll
+        for (int e = E - 1; e >= 0; --e) {
+            const int p = e & 1;
+            x[e] = g[e] - u[e] * xin[p];
+            xin[p] = x[e];
+        }
+    }
+    // ---- bordered row
+    double xpar[2];
+    {
+        double s[2] = {0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int n = n0 + e;
+            if (n >= 2 && n < N) s[e & 1] += band[a0 + e] * x[e];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+            s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+        }
+        xpar[0] = (bc0 - s[0]) / inv[0];
+        xpar[1] = (bc1 - s[1]) / inv[1];
+    }
+    // ---- forward elimination
+    {
+        double l[E], iv[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int n = n0 + e;
+            const bool in = n >= 2 && n < N;
+            l[e] = in ? lo[a0 + e] : 0.0;
+            iv[e] = in ? inv[a0 + e] : 0.0;
+        }
+        double A[2] = {1.0, 1.0}, B[2] = {0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int p = e & 1;
+            if (lane == 0 && e < 2) {
+                A[p] = 0.0;
+                B[p] = xpar[p];
+            } else {
+                B[p] = (x[e] - l[e] * B[p]) * iv[e];
+                A[p] = -(l[e] * A[p]) * iv[e];
+            }
+        }
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const double A2 = __shfl_up_sync(0xffffffffu, A[p], s), B2 = __shfl_up_sync(0xffffffffu, B[p], s);
+                if (lane >= s) {
+                    B[p] = A[p] * B2 + B[p];
+                    A[p] = A[p] * A2;
+                }
+            }
+        }
+        double vin[2];
+        vin[0] = shfl_up_or(B[0], 1, lane, 0.0);
+        vin[1] = shfl_up_or(B[1], 1, lane, 0.0);
+        double ws[2] = {0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int p = e & 1, n = n0 + e;
+            double v;
+            if (lane == 0 && e < 2) v = xpar[p];
+            else v = (x[e] - l[e] * vin[p]) * iv[e];
+            x[e] = v;
+            vin[p] = v;
+            if (wall) ws[p] += (double)(n * n) * v;
+        }
+        if (wall) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ws[0] += __shfl_xor_sync(0xffffffffu, ws[0], o);
+                ws[1] += __shfl_xor_sync(0xffffffffu, ws[1], o);
+            }
+            wall[0] = ws[0];
+            wall[1] = ws[1];
+        }
+    }
 }
 
 }  // namespace
@@ -257,21 +398,21 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_setup_kernel(const TauD
         double bandk = 1.0;
         for (int n = nl; n >= par + 4; n -= 2) {
             const double Akk = dgk;
-            inv[n * TM + m] = 1.0 / Akk;
+            inv[m * N + n] = 1.0 / Akk;
             const double w = A_lo(n, Nb, lam);
             const double upm = A_up(n - 2, Nb, lam) / Akk;
-            up[(n - 2) * TM + m] = upm;
+            up[m * N + n - 2] = upm;
             const double dprev = A_dg(n - 2, Nb, lam, nus) - w * upm;
             const double bk = bandk / Akk;
-            band[n * TM + m] = bk;
+            band[m * N + n] = bk;
             bandk = 1.0 - w * bk;
             dgk = dprev;
         }
         const int n1 = par + 2;
-        inv[n1 * TM + m] = 1.0 / dgk;
+        inv[m * N + n1] = 1.0 / dgk;
         const double b1 = bandk / dgk;
-        band[n1 * TM + m] = b1;
-        inv[par * TM + m] = 1.0 - A_lo(n1, Nb, lam) * b1;  // diag(0) == band(0)
+        band[m * N + n1] = b1;
+        inv[m * N + par] = 1.0 - A_lo(n1, Nb, lam) * b1;  // diag(0) == band(0)
     }
     __syncthreads();
 
@@ -300,8 +441,9 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_setup_kernel(const TauD
         double* gP = pm == 0 ? gPp : gPm;
         double* gv = pm == 0 ? gvp : gvm;
         for (int idx = tid; idx < N * TM; idx += NT) {
-            gP[idx] = A1[idx];
-            gv[idx] = A3[idx];
+            const int n = idx / TM, m = idx - n * TM;
+            gP[m * N + n] = A1[idx];
+            gv[m * N + n] = A3[idx];
         }
         if (tid < TM) {
             double vb, va;
@@ -358,14 +500,14 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_setup_kernel(const TauD
     }
     __syncthreads();
     for (int idx = tid; idx < N * TM; idx += NT) {
-        const int m = idx % TM;
+        const int n = idx / TM, m = idx - n * TM, gi = m * N + n;
         const double dp = s_w[4 * TM + m], dm = s_w[5 * TM + m];
-        const double P0 = A2[idx] + (dp * gPp[idx] + dm * gPm[idx]);
-        const double v0 = A1[idx] + (dp * gvp[idx] + dm * gvm[idx]);
+        const double P0 = A2[idx] + (dp * gPp[gi] + dm * gPm[gi]);
+        const double v0 = A1[idx] + (dp * gvp[gi] + dm * gvm[gi]);
         A2[idx] = P0;
         A1[idx] = v0;
-        gP0[idx] = P0;
-        gv0[idx] = v0;
+        gP0[gi] = P0;
+        gv0[gi] = v0;
     }
     __syncthreads();
     if (tid < TM) {
@@ -378,23 +520,28 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_setup_kernel(const TauD
 
 // =================================================================================================== solve
 // grid = ntiles ; CTA 0 handles the (0,0) mode (real parts, mean-flow constraint).
-__global__ void __launch_bounds__(TAU_THREADS) tau_solve_kernel(const TauSolveParams p) {
+// Shared memory: profile columns D[4][TT][NP] (Rx, Ry, Rz, P; column t = 2*mode + re/im, skewed in n), factor columns
+// F[3][TM][NP] (up, inv, band of the operator in use), the B rows [3][NP], scalars.
+template <int E, int NTERMS>
+__global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kernel(const TauSolveParams p) {
     const TauData& td = p.td;
     const int N = td.N, Nb = N - 1, TM = td.TM, TT = 2 * TM;
-    const int tid = threadIdx.x, NT = TAU_THREADS;
+    const int tid = threadIdx.x, NT = TAU_THREADS, lane = tid & 31, warp = tid >> 5, NW = TAU_THREADS / 32;
     const int tl = blockIdx.x;
     const bool is00 = tl == 0;
     const double scale = 4.0 / (td.b - td.a);
     const long rs = (long)p.g.Nx * (2 * (p.g.Nz / 2 + 1));  // row (ny) stride in doubles
     const long cs = rs * p.g.Ny;                            // component stride
-    const int AS = N * TT;                                  // doubles per profile array
-    const int FS = N * TM;                                  // doubles per factor array
+    const int NP = tau_col_pitch(N, E);                     // column pitch (doubles)
+    const int AS = TT * NP;                                 // doubles per profile array
+    const int FS = TM * NP;                                 // doubles per factor array
+    const int NM = N * TM;
 
     double* Rx = dyn_smem<double>();
     double* Ry = Rx + AS; double* Rz = Ry + AS; double* Pq = Rz + AS;
     double* Fup = Pq + AS; double* Finv = Fup + FS; double* Fband = Finv + FS; double* Flo = Fband + FS;
-    double* s_bt = Flo + FS;                     // [3][N] B rows
-    double* s_sc = s_bt + 3 * N;                 // [TSC_COUNT][TM]
+    double* s_sc = Flo + FS;                     // [TSC_COUNT][TM]
+    const double* __restrict__ bt = td.btab();   // B rows [3][N] (mode independent, L1 resident)
     double* s_w = s_sc + TSC_COUNT * TM;         // [8][TT]
     long* s_off = reinterpret_cast<long*>(s_w + 8 * TT);  // [TM]
     int q0, nvalid;
@@ -406,107 +553,133 @@ __global__ void __launch_bounds__(TAU_THREADS) tau_solve_kernel(const TauSolvePa
         s_off[tid] = off;
     }
     for (int i = tid; i < TSC_COUNT * TM; i += NT) s_sc[i] = td.tile_sc(tl, 0)[i];
-    for (int i = tid; i < 3 * N; i += NT) s_bt[i] = td.btab()[i];
+    {   // pull this tile's factor block (contiguous) towards L2 while the history fields stream in
+        const char* blk = reinterpret_cast<const char*>(td.tile(tl));
+        const size_t bytes = td.tile_doubles() * sizeof(double);
+        for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)NT * 128) prefetch_l2(blk + o);
+    }
     __syncthreads();
 
-    // ---- S1: right-hand side = linear combination of history fields (dnsalgo.cpp:217-224), complex elements
+    // ---- S1: right-hand side = linear combination of history fields (dnsalgo.cpp:217-224), complex elements.
+    // Thread -> (mode m, row slot j): rows n = j, j + NT/TM, ..; all loads of two rows are issued before their use.
     {
-        const int nel = 3 * N * TM;
-        for (int e = tid; e < nel; e += NT) {
-            const int comp = e / FS, r = e - comp * FS;
-            const int n = r / TM, m = r - n * TM;
-            const long off = s_off[m];
-            double are = 0.0, aim = 0.0;
-            if (off >= 0) {
-                const long go = comp * cs + n * rs + off;
-                double2 v[TAU_MAXTERMS];
+        const int m = tid % TM, j0 = tid / TM, JS = NT / TM;   // NT % TM == 0 is guaranteed by the launcher
+        const long off = s_off[m];
+        const int nterms = NTERMS > 0 ? NTERMS : p.nterms;
+        if (off >= 0 && j0 < JS) {
+            for (int comp = 0; comp < 3; ++comp) {
+                const long gbase = comp * cs + off;
+                double* dre = Rx + comp * AS + (2 * m) * NP;  // Rx,Ry,Rz contiguous
+                for (int n0 = j0; n0 < N; n0 += 2 * JS) {
+                    const int n1 = n0 + JS;
+                    const bool has1 = n1 < N;
+                    double2 v0[NTERMS > 0 ? NTERMS : TAU_MAXTERMS], v1[NTERMS > 0 ? NTERMS : TAU_MAXTERMS];
 #pragma unroll
-                for (int j = 0; j < TAU_MAXTERMS; ++j)
-                    if (j < p.nterms) v[j] = *reinterpret_cast<const double2*>(p.term[j] + go);
-#pragma unroll
-                for (int j = 0; j < TAU_MAXTERMS; ++j)
-                    if (j < p.nterms) { are += p.coef[j] * v[j].x; aim += p.coef[j] * v[j].y; }
-                if (is00) {
-                    // mean mode: base-flow diffusion and the imposed pressure gradient (nse.cpp:512-530); real parts only
-                    if (comp == 0 && p.Ubaseyy) are += td.nu * p.Ubaseyy[n];
-                    if (comp == 2 && p.Wbaseyy) are += td.nu * p.Wbaseyy[n];
-                    if (p.constraint == 0 && n == 0) {
-                        if (comp == 0) are -= p.dPdxRef;
-                        if (comp == 2) are -= p.dPdzRef;
+                    for (int j = 0; j < (NTERMS > 0 ? NTERMS : TAU_MAXTERMS); ++j) {
+                        if (j < nterms) {
+                            v0[j] = *reinterpret_cast<const double2*>(p.term[j] + gbase + n0 * rs);
+                            if (has1) v1[j] = *reinterpret_cast<const double2*>(p.term[j] + gbase + n1 * rs);
+                        }
                     }
-                    aim = 0.0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && !has1) break;
+                        const int n = h ? n1 : n0;
+                        double are = 0.0, aim = 0.0;
+#pragma unroll
+                        for (int j = 0; j < (NTERMS > 0 ? NTERMS : TAU_MAXTERMS); ++j)
+                            if (j < nterms) {
+                                const double2 v = h ? v1[j] : v0[j];
+                                are += p.coef[j] * v.x;
+                                aim += p.coef[j] * v.y;
+                            }
+                        if (is00) {
+                            // mean mode: base-flow diffusion and the imposed pressure gradient (nse.cpp:512-530); real parts only
+                            if (comp == 0 && p.Ubaseyy) are += td.nu * p.Ubaseyy[n];
+                            if (comp == 2 && p.Wbaseyy) are += td.nu * p.Wbaseyy[n];
+                            if (p.constraint == 0 && n == 0) {
+                                if (comp == 0) are -= p.dPdxRef;
+                                if (comp == 2) are -= p.dPdzRef;
+                            }
+                            aim = 0.0;
+                        }
+                        const int a = col_addr<E>(n);
+                        dre[a] = are;
+                        dre[NP + a] = aim;
+                    }
                 }
             }
-            *reinterpret_cast<double2*>(&Rx[comp * AS + n * TT + 2 * m]) = make_double2(are, aim);  // Rx,Ry,Rz contiguous
         }
-        // pressure-operator factors of this tile (upP, invP, bandP are contiguous) and its sub-diagonal
+        // pressure-operator factors of this tile (upP, invP, bandP are contiguous, [m][n]) and its sub-diagonal
         const double* fsrc = td.tile_arr(tl, TAR_UPP);
-        for (int i = tid; i < 3 * FS; i += NT) Fup[i] = fsrc[i];
-        for (int i = tid; i < FS; i += NT) {
-            const int n = i / TM, m = i - n * TM;
-            Flo[i] = n >= 2 ? A_lo(n, Nb, s_sc[TSC_LAMP * TM + m]) : 0.0;
+        for (int i = tid; i < 3 * NM; i += NT) {
+            const int am = i / N, n = i - am * N;
+            Fup[am * NP + col_addr<E>(n)] = fsrc[i];
+        }
+        for (int i = tid; i < NM; i += NT) {
+            const int mm = i / N, n = i - mm * N;
+            Flo[mm * NP + col_addr<E>(n)] = n >= 2 ? A_lo(n, Nb, s_sc[TSC_LAMP * TM + mm]) : 0.0;
         }
     }
     __syncthreads();
 
     // ---- S2: pressure Helmholtz  P'' - kappa^2 P = dRy/dy + i (kxx Rx + kzz Rz), P(+-1) = 0  (tausolver.cpp:357-366, 193-201)
-    if (tid < 2 * TM) {
-        const int m = tid % TM, par = tid / TM;
-        if (m < nvalid) {
+    for (int col = warp; col < TT; col += NW) {
+        const int m = col >> 1, ri = col & 1;
+        if (m >= nvalid) continue;
+        double r[E], x[E];
+        {
+            double y[E], d[E], ox[E], oz[E];
+            col_load<E>(Ry + col * NP, lane, N, y);
+            col_deriv<E>(y, d, scale, lane);
+            col_load<E>(Rx + (col ^ 1) * NP, lane, N, ox);
+            col_load<E>(Rz + (col ^ 1) * NP, lane, N, oz);
             const double kxx = s_sc[TSC_KXX * TM + m], kzz = s_sc[TSC_KZZ * TM + m];
-            const double* ry = Ry + 2 * m; const double* rx = Rx + 2 * m; const double* rz = Rz + 2 * m;
-            double run_re = 0.0, run_im = 0.0;
-            auto rhs = [&](int n, double& re, double& im) {
-                if (n + 1 <= Nb) {
-                    const double f = scale * (n + 1);
-                    run_re = run_re + f * ry[(n + 1) * TT];
-                    run_im = run_im + f * ry[(n + 1) * TT + 1];
-                }
-                double dre = run_re, dim = run_im;
-                if (n == 0) { dre *= 0.5; dim *= 0.5; }
-                re = dre - (kxx * rx[n * TT + 1] + kzz * rz[n * TT + 1]);
-                im = dim + (kxx * rx[n * TT] + kzz * rz[n * TT]);
-            };
-            helm_chain(Pq + 2 * m, N, TT, par, Fup + m, Finv + m, Fband + m, Flo + m, TM, s_bt, 0.0, 0.0, rhs, nullptr, nullptr);
+#pragma unroll
+            for (int e = 0; e < E; ++e) r[e] = ri ? d[e] + (kxx * ox[e] + kzz * oz[e]) : d[e] - (kxx * ox[e] + kzz * oz[e]);
         }
+        col_solve<E>(r, x, Fup + m * NP, Finv + m * NP, Fband + m * NP, Flo + m * NP, bt, N, lane, 0.0, 0.0, nullptr);
+        col_store<E>(Pq + col * NP, lane, N, x);
     }
     __syncthreads();
 
     // ---- velocity-operator factors replace the pressure ones
     {
         const double* fsrc = td.tile_arr(tl, TAR_UPV);
-        for (int i = tid; i < 3 * FS; i += NT) Fup[i] = fsrc[i];
-        for (int i = tid; i < FS; i += NT) {
-            const int n = i / TM, m = i - n * TM;
-            Flo[i] = n >= 2 ? A_lo(n, Nb, s_sc[TSC_LAMV * TM + m]) : 0.0;
+        for (int i = tid; i < 3 * NM; i += NT) {
+            const int am = i / N, n = i - am * N;
+            Fup[am * NP + col_addr<E>(n)] = fsrc[i];
+        }
+        for (int i = tid; i < NM; i += NT) {
+            const int mm = i / N, n = i - mm * N;
+            Flo[mm * NP + col_addr<E>(n)] = n >= 2 ? A_lo(n, Nb, s_sc[TSC_LAMV * TM + mm]) : 0.0;
         }
     }
     __syncthreads();
 
     if (!is00) {
         // ---- S3: v particular solution  nu v'' - lambda v = P' - Ry, v(+-1) = 0, in place in Ry  (tausolver.cpp:203-210)
-        if (tid < 2 * TM) {
-            const int m = tid % TM, par = tid / TM;
-            if (m < nvalid) {
-                double* ry = Ry + 2 * m; const double* pq = Pq + 2 * m;
-                const int ntop = par ? Nb - 1 : Nb;  // Ry[Nb], Ry[Nb-1] are needed again by the tau correction
-                s_w[(4 + par) * TT + 2 * m] = ry[ntop * TT];
-                s_w[(4 + par) * TT + 2 * m + 1] = ry[ntop * TT + 1];
-                double run_re = 0.0, run_im = 0.0;
-                auto rhs = [&](int n, double& re, double& im) {
-                    if (n + 1 <= Nb) {
-                        const double f = scale * (n + 1);
-                        run_re = run_re + f * pq[(n + 1) * TT];
-                        run_im = run_im + f * pq[(n + 1) * TT + 1];
-                    }
-                    double dre = run_re, dim = run_im;
-                    if (n == 0) { dre *= 0.5; dim *= 0.5; }
-                    re = dre - ry[n * TT];
-                    im = dim - ry[n * TT + 1];
-                };
-                helm_chain(ry, N, TT, par, Fup + m, Finv + m, Fband + m, Flo + m, TM, s_bt, 0.0, 0.0, rhs,
-                           &s_w[(6 + par) * TT + 2 * m], &s_w[(6 + par) * TT + 2 * m + 1]);
+        for (int col = warp; col < TT; col += NW) {
+            const int m = col >> 1;
+            if (m >= nvalid) continue;
+            double r[E], x[E];
+            {
+                double pq[E], d[E], y[E];
+                col_load<E>(Pq + col * NP, lane, N, pq);
+                col_deriv<E>(pq, d, scale, lane);
+                col_load<E>(Ry + col * NP, lane, N, y);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    r[e] = d[e] - y[e];
+                    const int n = lane * E + e;  // Ry[Nb], Ry[Nb-1] are needed again by the tau correction
+                    if (n == Nb) s_w[4 * TT + col] = y[e];
+                    if (n == Nb - 1) s_w[5 * TT + col] = y[e];
+                }
             }
+            double wall[2];
+            col_solve<E>(r, x, Fup + m * NP, Finv + m * NP, Fband + m * NP, Flo + m * NP, bt, N, lane, 0.0, 0.0, wall);
+            col_store<E>(Ry + col * NP, lane, N, x);
+            if (lane == 0) { s_w[6 * TT + col] = wall[0]; s_w[7 * TT + col] = wall[1]; }
         }
         __syncthreads();
         // ---- S4: influence-matrix (tausolver.cpp:178-191) and tau (tausolver.cpp:215-244) correction amplitudes.
@@ -525,10 +698,11 @@ __global__ void __launch_bounds__(TAU_THREADS) tau_solve_kernel(const TauSolvePa
                 s_w[TT + tid] = dm;
                 if (p.taucorr) {
                     const double lam = s_sc[TSC_LAMV * TM + m];
-                    const int iNb = Nb * TM + m, iNb1 = (Nb - 1) * TM + m;
-                    const double vNb = Ry[Nb * TT + tid] + (dp * gvp[iNb] + dm * gvm[iNb]);
-                    const double vNb1 = Ry[(Nb - 1) * TT + tid] + (dp * gvp[iNb1] + dm * gvm[iNb1]);
-                    const double pNb = Pq[Nb * TT + tid] + (dp * gPp[iNb] + dm * gPm[iNb]);
+                    const int iNb = m * N + Nb, iNb1 = m * N + Nb - 1;
+                    const int aNb = tid * NP + col_addr<E>(Nb), aNb1 = tid * NP + col_addr<E>(Nb - 1);
+                    const double vNb = Ry[aNb] + (dp * gvp[iNb] + dm * gvm[iNb]);
+                    const double vNb1 = Ry[aNb1] + (dp * gvp[iNb1] + dm * gvm[iNb1]);
+                    const double pNb = Pq[aNb] + (dp * gPp[iNb] + dm * gPm[iNb]);
                     // v'' has zero coefficients at Nb-1, Nb; P'[Nb] = 0, P'[Nb-1] = scale Nb P[Nb]
                     const double s1nb = lam * vNb - s_w[4 * TT + tid];
                     double s1nb1 = lam * vNb1 - s_w[5 * TT + tid];
@@ -539,98 +713,130 @@ __global__ void __launch_bounds__(TAU_THREADS) tau_solve_kernel(const TauSolvePa
             }
         }
         __syncthreads();
-        for (int e = tid; e < FS; e += NT) {
-            const int n = e / TM, m = e - n * TM;
-            if (m >= nvalid) continue;
-            const double pp = gPp[e], vp = gvp[e], pm = gPm[e], vm = gvm[e];
-            double2 P = *reinterpret_cast<double2*>(&Pq[n * TT + 2 * m]);
-            double2 V = *reinterpret_cast<double2*>(&Ry[n * TT + 2 * m]);
-            const double dpr = s_w[2 * m], dpi = s_w[2 * m + 1], dmr = s_w[TT + 2 * m], dmi = s_w[TT + 2 * m + 1];
-            P.x += dpr * pp + dmr * pm;
-            P.y += dpi * pp + dmi * pm;
-            V.x += dpr * vp + dmr * vm;
-            V.y += dpi * vp + dmi * vm;
-            if (p.taucorr) {
-                const double p0 = gP0[e], v0 = gv0[e];
-                const double sNbr = s_w[2 * TT + 2 * m], sNbi = s_w[2 * TT + 2 * m + 1];
-                const double sNb1r = s_w[3 * TT + 2 * m], sNb1i = s_w[3 * TT + 2 * m + 1];
-                const bool ev = (n & 1) == 0;
-                P.x += (ev ? sNb1r : sNbr) * p0;
-                P.y += (ev ? sNb1i : sNbi) * p0;
-                V.x += (ev ? sNbr : sNb1r) * v0;
-                V.y += (ev ? sNbi : sNb1i) * v0;
+        for (int e0 = tid; e0 < NM; e0 += 4 * NT) {
+            double gq[4][6];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int e = e0 + h * NT;
+                if (e < NM) {
+                    gq[h][0] = gPp[e]; gq[h][1] = gvp[e]; gq[h][2] = gPm[e]; gq[h][3] = gvm[e];
+                    if (p.taucorr) { gq[h][4] = gP0[e]; gq[h][5] = gv0[e]; }
+                }
             }
-            *reinterpret_cast<double2*>(&Pq[n * TT + 2 * m]) = P;
-            *reinterpret_cast<double2*>(&Ry[n * TT + 2 * m]) = V;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int e = e0 + h * NT;
+                if (e >= NM) break;
+                const int m = e / N, n = e - m * N;
+                if (m >= nvalid) continue;
+                const double pp = gq[h][0], vp = gq[h][1], pm = gq[h][2], vm = gq[h][3];
+                const int a = (2 * m) * NP + col_addr<E>(n);
+                double Pr = Pq[a], Pi = Pq[a + NP], Vr = Ry[a], Vi = Ry[a + NP];
+                const double dpr = s_w[2 * m], dpi = s_w[2 * m + 1], dmr = s_w[TT + 2 * m], dmi = s_w[TT + 2 * m + 1];
+                Pr += dpr * pp + dmr * pm;
+                Pi += dpi * pp + dmi * pm;
+                Vr += dpr * vp + dmr * vm;
+                Vi += dpi * vp + dmi * vm;
+                if (p.taucorr) {
+                    const double p0 = gq[h][4], v0 = gq[h][5];
+                    const double sNbr = s_w[2 * TT + 2 * m], sNbi = s_w[2 * TT + 2 * m + 1];
+                    const double sNb1r = s_w[3 * TT + 2 * m], sNb1i = s_w[3 * TT + 2 * m + 1];
+                    const bool ev = (n & 1) == 0;
+                    Pr += (ev ? sNb1r : sNbr) * p0;
+                    Pi += (ev ? sNb1i : sNbi) * p0;
+                    Vr += (ev ? sNbr : sNb1r) * v0;
+                    Vi += (ev ? sNbi : sNb1i) * v0;
+                }
+                Pq[a] = Pr; Pq[a + NP] = Pi;
+                Ry[a] = Vr; Ry[a + NP] = Vi;
+            }
         }
         __syncthreads();
     } else if (p.constraint == 1) {
-        // mean mode with the bulk-velocity constraint (helmholtz.cpp:158-213): keep the right-hand sides, v = 0 anyway
+        // mean mode with the bulk-velocity constraint (helmholtz.cpp:158-213): keep the right-hand sides (v = 0 anyway)
         for (int n = tid; n < N; n += NT) {
-            Ry[n * TT] = Rx[n * TT];
-            Ry[n * TT + 1] = Rz[n * TT];
+            const int a = col_addr<E>(n);
+            Ry[a] = Rx[a];
+            Ry[NP + a] = Rz[a];
         }
         __syncthreads();
     }
 
     // ---- S5: u, w from the x/z momentum equations  nu u'' - lambda u = i kxx P - Rx, in place in Rx, Rz (tausolver.cpp:368-384).
-    // Mean mode + bulk velocity: the imaginary slot carries the solve with right-hand side nu*T0 instead ("uc").
+    // Mean mode + bulk velocity: the imaginary column carries the solve with right-hand side nu*T0 instead ("uc").
     const bool bulk00 = is00 && p.constraint == 1;
-    if (tid < 4 * TM) {
-        const int m = tid % TM, par = (tid / TM) & 1, which = tid / (2 * TM);
-        if (m < nvalid) {
+    for (int c2 = warp; c2 < 2 * TT; c2 += NW) {
+        const int which = c2 / TT, col = c2 - which * TT, m = col >> 1, ri = col & 1;
+        if (m >= nvalid) continue;
+        double* R = which ? Rz : Rx;
+        double r[E], x[E];
+        {
+            double po[E], rr[E];
+            col_load<E>(Pq + (col ^ 1) * NP, lane, N, po);
+            col_load<E>(R + col * NP, lane, N, rr);
             const double k = s_sc[(which ? TSC_KZZ : TSC_KXX) * TM + m];
-            double* rr = (which ? Rz : Rx) + 2 * m; const double* pq = Pq + 2 * m;
-            const double nu = td.nu;
-            auto rhs = [&](int n, double& re, double& im) {
-                re = -k * pq[n * TT + 1] - rr[n * TT];
-                im = k * pq[n * TT] - rr[n * TT + 1];
-                if (bulk00) im = n == 0 ? nu : 0.0;
-            };
-            helm_chain(rr, N, TT, par, Fup + m, Finv + m, Fband + m, Flo + m, TM, s_bt, 0.0, 0.0, rhs, nullptr, nullptr);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                r[e] = ri ? k * po[e] - rr[e] : -k * po[e] - rr[e];
+                if (bulk00 && ri) r[e] = (lane * E + e == 0) ? td.nu : 0.0;
+            }
         }
+        col_solve<E>(r, x, Fup + m * NP, Finv + m * NP, Fband + m * NP, Flo + m * NP, bt, N, lane, 0.0, 0.0, nullptr);
+        col_store<E>(R + col * NP, lane, N, x);
     }
     __syncthreads();
     if (bulk00) {
-        if (tid < 2) {
-            const double* ua = tid == 0 ? Rx : Rz;  // re: solution for the actual rhs, im: uc
-            double uam = ua[0], ucm = ua[1];
-            for (int n = 2; n < N; n += 2) { uam -= ua[n * TT] / (double)(n * n - 1); ucm -= ua[n * TT + 1] / (double)(n * n - 1); }
-            const double target = tid == 0 ? p.umean_target : p.wmean_target;
-            const double mu = td.nu * (target - uam) / ucm;
-            s_w[tid] = mu;
-            if (p.dPd_act) p.dPd_act[tid] = mu;
+        if (warp < 2) {
+            // mean(u) = u_0 - sum_{n even >= 2} u_n/(n^2-1)  (chebyshev.cpp:505-512) of the solution (re) and of uc (im)
+            const double* R = warp ? Rz : Rx;
+            double ua[E], uc[E];
+            col_load<E>(R, lane, N, ua);
+            col_load<E>(R + NP, lane, N, uc);
+            double sa = 0.0, sc = 0.0;
+#pragma unroll
+            for (int e = 0; e < E; e += 2) {
+                const int n = lane * E + e;
+                if (n >= 2 && n < N) { sa += ua[e] / (double)(n * n - 1); sc += uc[e] / (double)(n * n - 1); }
+            }
+            sa = warp_sum(sa); sc = warp_sum(sc);
+            if (lane == 0) {
+                const double uam = ua[0] - sa, ucm = uc[0] - sc;
+                const double target = warp == 0 ? p.umean_target : p.wmean_target;
+                const double mu = td.nu * (target - uam) / ucm;
+                s_w[warp] = mu;
+                if (p.dPd_act) p.dPd_act[warp] = mu;
+            }
         }
         __syncthreads();
-        if (tid < 4) {
-            const int par = tid & 1, which = tid >> 1;
-            double* rr = which ? Rz : Rx;
-            const double* saved = Ry + which;  // Ry.re = original Rx, Ry.im = original Rz
-            const double mu = s_w[which];
-            auto rhs = [&](int n, double& re, double& im) {
-                re = -saved[n * TT] + (n == 0 ? mu : 0.0);
-                im = 0.0;
-            };
-            helm_chain(rr, N, TT, par, Fup, Finv, Fband, Flo, TM, s_bt, 0.0, 0.0, rhs, nullptr, nullptr);
+        if (warp < 2) {
+            double* R = warp ? Rz : Rx;
+            double r[E], x[E], sv[E];
+            col_load<E>(Ry + warp * NP, lane, N, sv);  // Ry.re = original Rx, Ry.im = original Rz
+            const double mu = s_w[warp];
+#pragma unroll
+            for (int e = 0; e < E; ++e) r[e] = -sv[e] + ((lane * E + e == 0) ? mu : 0.0);
+            col_solve<E>(r, x, Fup, Finv, Fband, Flo, bt, N, lane, 0.0, 0.0, nullptr);
+            col_store<E>(R, lane, N, x);
+#pragma unroll
+            for (int e = 0; e < E; ++e) x[e] = 0.0;
+            col_store<E>(R + NP, lane, N, x);
         }
         __syncthreads();
     }
 
     // ---- S6: scatter (nse.cpp:566-572)
-    for (int e = tid; e < FS; e += NT) {
+    for (int e = tid; e < NM; e += NT) {
         const int n = e / TM, m = e - n * TM;
         const long off = s_off[m];
         if (off < 0) continue;
         const long go = n * rs + off;
-        const double2 U = *reinterpret_cast<double2*>(&Rx[n * TT + 2 * m]);
-        double2 V = *reinterpret_cast<double2*>(&Ry[n * TT + 2 * m]);
-        const double2 W = *reinterpret_cast<double2*>(&Rz[n * TT + 2 * m]);
-        const double2 P = *reinterpret_cast<double2*>(&Pq[n * TT + 2 * m]);
+        const int a = (2 * m) * NP + col_addr<E>(n);
+        double2 V = make_double2(Ry[a], Ry[a + NP]);
         if (is00) V = make_double2(0.0, 0.0);
-        *reinterpret_cast<double2*>(&p.uout[go]) = U;
+        *reinterpret_cast<double2*>(&p.uout[go]) = make_double2(Rx[a], Rx[a + NP]);
         *reinterpret_cast<double2*>(&p.uout[cs + go]) = V;
-        *reinterpret_cast<double2*>(&p.uout[2 * cs + go]) = W;
-        *reinterpret_cast<double2*>(&p.qout[go]) = P;
+        *reinterpret_cast<double2*>(&p.uout[2 * cs + go]) = make_double2(Rz[a], Rz[a + NP]);
+        *reinterpret_cast<double2*>(&p.qout[go]) = make_double2(Pq[a], Pq[a + NP]);
     }
 }
 
@@ -723,16 +929,27 @@ int tau_pick_TM(int N, int bytes_per_mode_row) {
     return TM;
 }
 
+// lane block size of the warp-parallel column solver: smallest instantiated even E with 32*E >= N
+int tau_pick_E(int N) {
+    const int need = 2 * ((N + 63) / 64);
+    const int avail[] = {2, 4, 6, 8, 10, 12, 16, 20};
+    for (int e : avail)
+        if (e >= need) return e;
+    return 0;
+}
+
 static size_t solve_smem(int N, int TM) {
-    const int TT = 2 * TM;
-    return ((size_t)4 * N * TT + 4 * N * TM + 3 * N + TSC_COUNT * TM + 8 * TT) * sizeof(double) + TM * sizeof(long);
+    const int E = tau_pick_E(N);
+    if (!E) return (size_t)1 << 30;
+    const size_t NP = tau_col_pitch(N, E);
+    return ((size_t)12 * TM * NP + TSC_COUNT * TM + 16 * TM) * sizeof(double) + TM * sizeof(long);
 }
 
 // modes per tile of the solve kernel: two CTAs per SM when the profiles are long (one streams while the other
-// walks its recurrences), at most 8 modes (128-byte runs of the history fields)
+// solves), at most 8 modes (128-byte runs of the history fields)
 int tau_pick_TM_solve(int N) {
     int TM = 8;
-    while (TM > 1 && solve_smem(N, TM) > 110 * 1024) --TM;
+    while (TM > 1 && (solve_smem(N, TM) > 112 * 1024 || TAU_THREADS % TM)) --TM;
     return TM;
 }
 
@@ -765,14 +982,10 @@ int linear_launch(const TauSolveParams& p, const double* u, const double* q, dou
     return 0;
 }
 
-int tau_solve_launch(const TauSolveParams& p, cudaStream_t stream) {
-    const size_t smem = solve_smem(p.td.N, p.td.TM);
-    if (smem > 227 * 1024) {
-        set_last_error("tau_solve: Ny too large for the shared-memory tile");
-        return 1;
-    }
+template <int E, int NTERMS>
+static int solve_launch_en(const TauSolveParams& p, size_t smem, cudaStream_t stream) {
     static size_t configured = 0;
-    auto kfn = tau_solve_kernel;
+    auto kfn = tau_solve_kernel<E, NTERMS>;
     if (smem > configured) {
         CF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -781,6 +994,37 @@ int tau_solve_launch(const TauSolveParams& p, cudaStream_t stream) {
     CF_LAUNCH(kfn, grid, dim3(TAU_THREADS), smem, stream, p);
     CF_KERNEL_CHECK();
     return 0;
+}
+// term counts of the reference's steppers get their own instantiation: 2k for SBDF-k (6 = SBDF3), 4 for the
+// CNAB/SMRK/CNRK substeps; anything else runs the generic (predicated) variant
+template <int E>
+static int solve_launch_e(const TauSolveParams& p, size_t smem, cudaStream_t stream) {
+    switch (p.nterms) {
+        case 1: return solve_launch_en<E, 1>(p, smem, stream);
+        case 4: return solve_launch_en<E, 4>(p, smem, stream);
+        case 6: return solve_launch_en<E, 6>(p, smem, stream);
+        default: return solve_launch_en<E, 0>(p, smem, stream);
+    }
+}
+
+int tau_solve_launch(const TauSolveParams& p, cudaStream_t stream) {
+    const size_t smem = solve_smem(p.td.N, p.td.TM);
+    if (smem > 227 * 1024 || TAU_THREADS % p.td.TM) {
+        set_last_error("tau_solve: Ny too large for the shared-memory tile");
+        return 1;
+    }
+    switch (tau_pick_E(p.td.N)) {
+        case 2: return solve_launch_e<2>(p, smem, stream);
+        case 4: return solve_launch_e<4>(p, smem, stream);
+        case 6: return solve_launch_e<6>(p, smem, stream);
+        case 8: return solve_launch_e<8>(p, smem, stream);
+        case 10: return solve_launch_e<10>(p, smem, stream);
+        case 12: return solve_launch_e<12>(p, smem, stream);
+        case 16: return solve_launch_e<16>(p, smem, stream);
+        case 20: return solve_launch_e<20>(p, smem, stream);
+    }
+    set_last_error("tau_solve: unsupported Ny");
+    return 1;
 }
 
 }  // namespace cfgpu

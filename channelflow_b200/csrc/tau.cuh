@@ -40,6 +40,10 @@ struct TauData {
     static size_t doubles(int N, int nq, int TM) { return (size_t)num_tiles(nq, TM) * (TAR_COUNT * N + TSC_COUNT) * TM + 3 * (size_t)N; }
 };
 
+// pitch (doubles) of a skewed shared-memory column of the solve kernel: addr(n) = n + n/E, made odd so that the
+// columns of a tile start in different banks
+__host__ __device__ inline int tau_col_pitch(int N, int E) { return ((N - 1) + (N - 1) / E + 1) | 1; }
+
 struct ModeGeom {
     int Nx, Ny, Nz, Kx, Kz;  // field grid and retained box
     double Lx, Lz;
@@ -72,5 +76,6 @@ void tau_btab_host(int N, double* tab /* [3*N] */);
 int tau_solve_launch(const TauSolveParams& p, cudaStream_t stream);
 int tau_pick_TM(int N, int narrays_bytes_per_mode_row);
 int tau_pick_TM_solve(int N);
+int tau_pick_E(int N);
 
 }  // namespace cfgpu

@@ -52,6 +52,12 @@ def test_tausolve_modes(lib, cfg):
     assert r["tau_abs_err"] <= 1e-13 * max(r["scale"], 1.0), r
 
 
+@pytest.mark.parametrize("Ny", [65, 97, 129, 257, 385, 513])
+def test_tausolve_lane_block_sizes(lib, Ny):
+    r = parity.tausolve_modes(lib, dict(parity.C1, Nx=12, Ny=Ny, Nz=12))
+    assert r["tau_abs_err"] <= 1e-13 * max(r["scale"], 1.0), r
+
+
 @pytest.mark.parametrize("stepper", ["sbdf3", "sbdf1", "sbdf2", "sbdf4", "cnfe1", "cnab2", "smrk2", "cnrk2"])
 def test_dns_steppers(lib, stepper):
     r = parity.dns_steps(lib, SMALL, checkpoints=(1, 5), timestepping=stepper)
