@@ -21,6 +21,26 @@ extern long long g_launches;  // kernels launched by this library (reported by c
     (++cfgpu::g_launches, kernel<<<grid, block, smem, stream>>>(__VA_ARGS__))
 #endif
 
+// Launch with a thread-block cluster of `cluster` CTAs along x (co-scheduled on one GPC, started together).
+#ifdef CF_EMU
+#define CF_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cluster, ...) CF_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
+#else
+namespace cfgpu {
+template <class... KArgs, class... Args>
+inline void launch_cluster(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
+}
+}  // namespace cfgpu
+#define CF_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cluster, ...) \
+    (++cfgpu::g_launches, cfgpu::launch_cluster(kernel, grid, block, smem, stream, cluster, __VA_ARGS__))
+#endif
+
 namespace cfgpu {
 
 // ---- error plumbing (C-ABI returns int status; message via cfgpu_last_error) ----
