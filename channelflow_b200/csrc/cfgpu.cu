@@ -156,7 +156,8 @@ int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out) {
     int m = N;
     while (m > 1) {
         int r;
-        if (m % 4 == 0) r = 4;
+        if (m % 8 == 0) r = 8;
+        else if (m % 4 == 0) r = 4;
         else if (m % 2 == 0) r = 2;
         else if (m % 3 == 0) r = 3;
         else if (m % 5 == 0) r = 5;

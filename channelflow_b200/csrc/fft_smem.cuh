@@ -3,7 +3,7 @@
 //
 // Data layout in shared memory: buf[n * C + c], n = position along the transformed direction, c = one of C
 // independent transforms handled by the CTA ("columns").  Threads are mapped (butterfly j, column c) with c
-// fastest, so every load/store of a pass touches consecutive 16-byte words.  Mixed radix 4/2/3/5, autosort
+// fastest, so every load/store of a pass touches consecutive 16-byte words.  Mixed radix 8/4/2/3/5, autosort
 // (no bit reversal), ping-pong between two buffers.  Twiddles come from a table exp(-2 pi i t / N) computed on
 // the host in long double (read through the read-only cache); the inverse transform conjugates them.
 // Unnormalised, FFTW sign convention: DIR=-1 forward (exp(-i..)), DIR=+1 backward.
@@ -65,6 +65,35 @@ __device__ __forceinline__ void fft_pass(const double2* __restrict__ a, double2*
             v[1] = d02 + d13;
             v[2] = s02 - s13;
             v[3] = d02 - d13;
+        } else if (R == 8) {
+            // radix-2 split (r, r+4), twiddles W8^r on the odd half, then two radix-4 butterflies
+            const double h = 0.70710678118654752440084436210485;
+            double2 a[8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                a[r] = v[r] + v[r + 4];
+                a[r + 4] = v[r] - v[r + 4];
+            }
+            {
+                const double2 t5 = a[5], t7 = a[7];
+                if (DIR < 0) {
+                    a[5] = make_double2(h * (t5.x + t5.y), h * (t5.y - t5.x));
+                    a[7] = make_double2(h * (t7.y - t7.x), -h * (t7.x + t7.y));
+                } else {
+                    a[5] = make_double2(h * (t5.x - t5.y), h * (t5.x + t5.y));
+                    a[7] = make_double2(-h * (t7.x + t7.y), h * (t7.x - t7.y));
+                }
+                a[6] = rot90<DIR>(a[6]);
+            }
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const double2 b0 = a[4 * o], b1 = a[4 * o + 1], b2 = a[4 * o + 2], b3 = a[4 * o + 3];
+                const double2 s02 = b0 + b2, d02 = b0 - b2, s13 = b1 + b3, d13 = rot90<DIR>(b1 - b3);
+                v[o] = s02 + s13;
+                v[o + 2] = d02 + d13;
+                v[o + 4] = s02 - s13;
+                v[o + 6] = d02 - d13;
+            }
         } else if (R == 3) {
             const double wi = (DIR < 0 ? -1.0 : 1.0) * 0.86602540378443864676372317075294;  // sin(2 pi/3)
             double2 s = v[1] + v[2], d = v[1] - v[2];
@@ -103,7 +132,8 @@ __device__ __forceinline__ double2* fft_smem(double2* a, double2* b, const FftPl
     int Ns = 1;
     for (int p = 0; p < pl.npass; ++p) {
         const int R = pl.radix[p];
-        if (R == 4) fft_pass<DIR, 4>(a, b, pl, Ns, C, tid, nthreads);
+        if (R == 8) fft_pass<DIR, 8>(a, b, pl, Ns, C, tid, nthreads);
+        else if (R == 4) fft_pass<DIR, 4>(a, b, pl, Ns, C, tid, nthreads);
         else if (R == 2) fft_pass<DIR, 2>(a, b, pl, Ns, C, tid, nthreads);
         else if (R == 3) fft_pass<DIR, 3>(a, b, pl, Ns, C, tid, nthreads);
         else fft_pass<DIR, 5>(a, b, pl, Ns, C, tid, nthreads);

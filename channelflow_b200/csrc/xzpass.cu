@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_forward_kernel(const XPassPa
 // ------------------------------------------------------------------------------------------------ z pass
 // grid = (ceil(Nx/TL), nyn).  Two real fields share one complex transform (Z = A + iB with the Hermitian
 // extension written explicitly), so the rotational term needs 5 inverse + 2 forward complex FFTs per line.
-__global__ void __launch_bounds__(XZ_THREADS) zpass_kernel(const ZPassParams p) {
+__global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
     const int Nx = p.Nx, Nz = p.Nz, TL = p.TL;
     const int nkz = p.Kz + 1;
     const bool rot = p.mode == ZP_ROTATIONAL;
@@ -87,16 +87,16 @@ __global__ void __launch_bounds__(XZ_THREADS) zpass_kernel(const ZPassParams p) 
     const int CA = npair * TL;
     double2* A = dyn_smem<double2>();
     double2* B = A + (size_t)Nz * CA;
-    __shared__ double red[XZ_THREADS / 32];
-    const int tid = threadIdx.x;
+    __shared__ double red[32];
+    const int tid = threadIdx.x, NT = blockDim.x;
     const int yl = blockIdx.y, ny = p.ny0 + yl, nx0 = blockIdx.x * TL;
     const size_t fstride = (size_t)p.nyn * Nx * nkz;  // field stride of Q and F
 
-    for (int idx = tid; idx < Nz * CA; idx += XZ_THREADS) A[idx] = make_double2(0.0, 0.0);
-    __syncthreads();
+    // rows nkz .. Nz-nkz (the de-aliased band and the Nyquist mode) are not written by the packing loop below
+    for (int idx = tid; idx < (Nz - 2 * nkz + 1) * CA; idx += NT) A[(size_t)nkz * CA + idx] = make_double2(0.0, 0.0);
 
     const double2* __restrict__ Q = p.Q + (size_t)yl * Nx * nkz;
-    for (int idx = tid; idx < TL * nkz; idx += XZ_THREADS) {
+    for (int idx = tid; idx < TL * nkz; idx += NT) {
         const int l = idx / nkz, k = idx - l * nkz;
         const int nx = nx0 + l;
         if (nx >= Nx) continue;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(XZ_THREADS) zpass_kernel(const ZPassParams p) 
         }
     }
     __syncthreads();
-    double2* res = fft_smem<+1>(A, B, p.plan, CA, tid, XZ_THREADS);
+    double2* res = fft_smem<+1>(A, B, p.plan, CA, tid, NT);
     double2* other = (res == A) ? B : A;
 
     // pointwise stage
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(XZ_THREADS) zpass_kernel(const ZPassParams p) 
     const double idx_ = (double)Nx / p.Lx, idz_ = (double)Nz / p.Lz, idy_ = p.inv_dy ? p.inv_dy[ny] : 0.0;
     double cmax = 0.0;
     const int CF = 2 * TL;
-    for (int idx = tid; idx < Nz * TL; idx += XZ_THREADS) {
+    for (int idx = tid; idx < Nz * TL; idx += NT) {
         const int z = idx / TL, l = idx - z * TL;
         if (nx0 + l >= Nx) {
             if (rot) {
@@ -184,18 +184,18 @@ __global__ void __launch_bounds__(XZ_THREADS) zpass_kernel(const ZPassParams p) 
         if ((tid & 31) == 0) red[tid >> 5] = cmax;
         __syncthreads();
         if (tid < 32) {
-            double v = tid < XZ_THREADS / 32 ? red[tid] : 0.0;
+            double v = tid < (NT >> 5) ? red[tid] : 0.0;
             v = warp_max(v);
             if (tid == 0 && v > 0.0) atomic_max_double(p.cfl_max, v);
         }
     }
     if (!rot) return;
     __syncthreads();
-    const double2* g = fft_smem<-1>(other, res, p.plan, CF, tid, XZ_THREADS);
+    const double2* g = fft_smem<-1>(other, res, p.plan, CF, tid, NT);
 
     double2* __restrict__ F = p.F + (size_t)yl * Nx * nkz;
     const double sc = p.scale, hs = 0.5 * p.scale;
-    for (int idx = tid; idx < TL * nkz; idx += XZ_THREADS) {
+    for (int idx = tid; idx < TL * nkz; idx += NT) {
         const int l = idx / nkz, k = idx - l * nkz;
         const int nx = nx0 + l;
         if (nx >= Nx) continue;
@@ -248,7 +248,11 @@ int zpass_launch(const ZPassParams& p, cudaStream_t stream) {
     auto kfn = zpass_kernel;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
     dim3 grid((p.Nx + p.TL - 1) / p.TL, p.nyn);
-    CF_LAUNCH(kfn, grid, dim3(XZ_THREADS), smem, stream, p);
+    // one first-pass butterfly per thread: Nz/R0 butterflies for each of the npair*TL columns
+    const int R0 = p.plan.npass ? p.plan.radix[0] : 1;
+    int nt = ((p.Nz / R0) * npair * p.TL + 31) & ~31;
+    nt = nt < 128 ? 128 : (nt > 512 ? 512 : nt);
+    CF_LAUNCH(kfn, grid, dim3(nt), smem, stream, p);
     CF_KERNEL_CHECK();
     return 0;
 }
