@@ -86,6 +86,29 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 #endif
 }
 
+// ---- cp.async (SASS LDGSTS): 16-byte global -> shared copies that bypass registers ----
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+#ifdef CF_EMU
+    memcpy(smem_dst, gmem_src, 16);
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+#endif
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+#ifdef CF_EMU
+    memcpy(smem_dst, gmem_src, 8);
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef CF_EMU
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 // ---- L2 prefetch of one 128-byte line ----
 __device__ __forceinline__ void prefetch_l2(const void* p) {
 #ifndef CF_EMU

@@ -91,7 +91,7 @@ int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out) {
     pl.Ne = Nb / 2 + 1;
     pl.No = N - pl.Ne;
     const int Nh = pl.Nh, Ne = pl.Ne, No = pl.No;
-    auto r8 = [](int x) { return (x + 7) & ~7; };
+    auto r8 = [](int x) { return (x + 31) & ~31; };  // matrices are zero padded to whole 32-row warp tiles
     auto r4 = [](int x) { return (x + 3) & ~3; };
     pl.invMp = r8(Nh); pl.invK1p = r4(Ne); pl.invK2p = r4(No > 0 ? No : 1);
     pl.fwdMp = r8(Ne > No ? Ne : No); pl.fwdKp = r4(Nh);

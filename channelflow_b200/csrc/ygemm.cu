@@ -2,20 +2,28 @@
 //
 // Tiling: one CTA owns BN (64/32/16) columns (= consecutive doubles: re/im of consecutive kz modes) of one field
 // component and ALL Ny rows: it stages the even/odd (or sum/difference) operand tiles in shared memory once
-// (each HBM element is read exactly once, coalesced 512-byte rows), then its 8 warps sweep the output rows in
-// 32-row tiles issuing mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) with A fragments served from L1/L2 (the matrices
-// are a few hundred KB and shared by every CTA) and B fragments from shared memory (row pitch BN+4 doubles =>
-// conflict-free fragment loads).  Each output element is written exactly once.
+// (each HBM element is read exactly once, 512-byte runs; inverse mode uses cp.async so that the whole tile is in
+// flight at once), then its 8 warps -- 4 along the output rows, 2 along the columns -- each own a 32-row x (BN/2)-column
+// output tile of BOTH parity products (E and O accumulators in registers) and issue mma.sync.m8n8k4.f64 (SASS
+// DMMA.8x8x4): per k-step of 4 a warp loads 4 A fragments and BN/16 B fragments for 4*BN/16 DMMAs.  A fragments come
+// from L1/L2 (the matrices are a few hundred KB, shared by every CTA) and are register double-buffered one k-step
+// ahead; B fragments come from shared memory (row pitch BN+4 doubles => conflict-free fragment loads).
+// A trailing remainder of at most 2 rows (Ny = 2^k+1 gives 32*m + 1 rows: the self-paired middle point / last
+// coefficient) is not worth a 32-row tile and is evaluated as plain dot products instead.
+// Each output element is written exactly once.
 // Roofline: tensor (FP64) for Ny >~ 49, HBM below; algorithmic flops = 2*Ny*ceil(Ny/2)*2 per column per output.
 #include "ygemm.cuh"
 
 namespace cfgpu {
 
+namespace {
+constexpr int YG_THREADS = 256;
+}
+
 template <int BN>
-__global__ void __launch_bounds__(256) ygemm_kernel(const YGemmParams p) {
+__global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams p) {
     constexpr int LD = BN + 4;
-    constexpr int NWN = BN / 16;  // warps along the column direction (16 columns each)
-    constexpr int NWM = 8 / NWN;  // warps along the row direction
+    constexpr int NT = BN / 16;   // 8-column n-tiles per warp (2 warps along the columns)
     double* B1 = dyn_smem<double>();
     double* B2 = B1 + (size_t)p.K1p * LD;
     long* cin = reinterpret_cast<long*>(B2 + (size_t)p.K2p * LD);
@@ -40,52 +48,71 @@ __global__ void __launch_bounds__(256) ygemm_kernel(const YGemmParams p) {
     const int N = p.N, Nb = N - 1;
     const double* __restrict__ in = job.in;
     if (p.mode == 0) {
-        // rows 0..K1p-1 of B1 hold even n = 2r, rows of B2 hold odd n = 2r+1; zero padded
-        const int total = (p.K1p + p.K2p) * BN;
-        for (int idx = tid; idx < total; idx += 256) {
-            const int r = idx / BN, c = idx % BN;
+        // rows 0..K1p-1 of B1 hold even n = 2r, rows of B2 hold odd n = 2r+1; zero padded.  Columns come in (re,im)
+        // pairs (all run lengths are even), so 16-byte cp.async copies are aligned on both sides.
+        const int HB = BN / 2;
+        const int total = (p.K1p + p.K2p) * HB;
+        for (int idx = tid; idx < total; idx += YG_THREADS) {
+            const int r = idx / HB, c = 2 * (idx - r * HB);
             const long off = cin[c];
-            double v = 0.0;
-            if (r < p.K1p) {
-                if (r < p.K1 && off >= 0) v = in[(long)(2 * r) * p.in_ld + off];
-                B1[r * LD + c] = v;
-            } else {
-                const int r2 = r - p.K1p;
-                if (r2 < p.K2 && off >= 0) v = in[(long)(2 * r2 + 1) * p.in_ld + off];
-                B2[r2 * LD + c] = v;
-            }
+            const bool odd = r >= p.K1p;
+            const int rr = odd ? r - p.K1p : r;
+            double* dst = (odd ? B2 : B1) + rr * LD + c;
+            const int n = odd ? 2 * rr + 1 : 2 * rr;
+            if (rr < (odd ? p.K2 : p.K1) && off >= 0) cp_async16(dst, in + (long)n * p.in_ld + off);
+            else *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
         }
+        cp_async_wait_all();
     } else {
         // forward: B1[j] = x[j] + x[Nb-j], B2[j] = x[j] - x[Nb-j]  (self-paired middle row: B1 = x, B2 = 0)
-        const int total = p.K1p * BN;
-        for (int idx = tid; idx < total; idx += 256) {
-            const int j = idx / BN, c = idx % BN;
-            const long off = cin[c];
-            double s = 0.0, d = 0.0;
-            if (j < p.K1 && off >= 0) {
-                const int jj = Nb - j;
-                const double a = in[(long)j * p.in_ld + off];
-                if (jj != j) {
-                    const double b = in[(long)jj * p.in_ld + off];
-                    s = a + b;
-                    d = a - b;
-                } else {
-                    s = a;
+        const int HB = BN / 2;
+        const int total = p.K1p * HB;
+        for (int i0 = tid; i0 < total; i0 += 4 * YG_THREADS) {
+            double2 a[4], b[4];
+            int jj[4], cc[4];
+            bool ok[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int idx = i0 + h * YG_THREADS;
+                const int j = idx / HB, c = 2 * (idx - j * HB);
+                jj[h] = j; cc[h] = c;
+                const long off = idx < total ? cin[c] : -1;
+                ok[h] = idx < total && j < p.K1 && off >= 0;
+                a[h] = b[h] = make_double2(0.0, 0.0);
+                if (ok[h]) {
+                    a[h] = *reinterpret_cast<const double2*>(in + (long)j * p.in_ld + off);
+                    if (Nb - j != j) b[h] = *reinterpret_cast<const double2*>(in + (long)(Nb - j) * p.in_ld + off);
                 }
             }
-            B1[j * LD + c] = s;
-            if (j < p.K2p) B2[j * LD + c] = d;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                if (i0 + h * YG_THREADS >= total) break;
+                const int j = jj[h], c = cc[h];
+                double2 s = make_double2(0.0, 0.0), d = s;
+                if (ok[h]) {
+                    if (Nb - j != j) {
+                        s = make_double2(a[h].x + b[h].x, a[h].y + b[h].y);
+                        d = make_double2(a[h].x - b[h].x, a[h].y - b[h].y);
+                    } else {
+                        s = a[h];
+                    }
+                }
+                *reinterpret_cast<double2*>(&B1[j * LD + c]) = s;
+                if (j < p.K2p) *reinterpret_cast<double2*>(&B2[j * LD + c]) = d;
+            }
         }
     }
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
-    const int wn = warp % NWN, wm = warp / NWN;
+    const int wn = warp & 1, wm = warp >> 1;  // 2 warps along the columns, 4 along the rows
     const int lr = lane >> 2, lk = lane & 3;  // fragment row / k (A), n / k (B)
     const int Mmax = p.M > p.M2 ? p.M : p.M2;
-    const int Mp = (Mmax + 7) & ~7;
-    const int Mtiles = (Mp + 31) / 32;
-    const int ncb = wn * 16;
+    const int rem = Mmax & 31;
+    const int Mgemm = (rem >= 1 && rem <= 2) ? Mmax - rem : Mmax;  // rows done on the tensor pipe
+    const int Mtiles = (Mgemm + 31) / 32;
+    const int ncb = wn * (BN / 2);
+    const int nk1 = p.K1p / 4, nk2 = p.K2p / 4;
 
     for (int mi = 0; mi < job.nmat; ++mi) {
         const int mat = job.mat0 + mi;
@@ -93,38 +120,55 @@ __global__ void __launch_bounds__(256) ygemm_kernel(const YGemmParams p) {
         const double* __restrict__ A2 = p.A2[mat];
         double* __restrict__ out = job.out[mi];
         const double sgn = p.sgn[mat];
-        for (int mt = wm; mt < Mtiles; mt += NWM) {
+        for (int mt = wm; mt < Mtiles; mt += 4) {
             const int row0 = mt * 32;
-            double e[4][2][2], o[4][2][2];
+            double e[4][NT][2], o[4][NT][2];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int t = 0; t < 2; ++t) e[i][t][0] = e[i][t][1] = o[i][t][0] = o[i][t][1] = 0.0;
-
-            for (int k = 0; k < p.K1p; k += 4) {
-                double b[2];
+                for (int t = 0; t < NT; ++t) e[i][t][0] = e[i][t][1] = o[i][t][0] = o[i][t][1] = 0.0;
+            {
+                const double* __restrict__ ap = A1 + (size_t)(row0 + lr) * p.K1p + lk;
+                const double* __restrict__ bp = B1 + lk * LD + ncb + lr;
+                double a[4], an[4];
 #pragma unroll
-                for (int t = 0; t < 2; ++t) b[t] = B1[(k + lk) * LD + ncb + t * 8 + lr];
+                for (int i = 0; i < 4; ++i) a[i] = __ldg(ap + (size_t)(8 * i) * p.K1p);
+                for (int ks = 0; ks < nk1; ++ks) {
+                    if (ks + 1 < nk1) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (row0 + i * 8 < Mp) {
-                        const double a = __ldg(&A1[(size_t)(row0 + i * 8 + lr) * p.K1p + k + lk]);
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) dmma_m8n8k4(e[i][t][0], e[i][t][1], a, b[t]);
+                        for (int i = 0; i < 4; ++i) an[i] = __ldg(ap + (size_t)(8 * i) * p.K1p + 4 * (ks + 1));
                     }
+                    double b[NT];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) b[t] = bp[(4 * ks) * LD + t * 8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) dmma_m8n8k4(e[i][t][0], e[i][t][1], a[i], b[t]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = an[i];
                 }
             }
-            for (int k = 0; k < p.K2p; k += 4) {
-                double b[2];
+            {
+                const double* __restrict__ ap = A2 + (size_t)(row0 + lr) * p.K2p + lk;
+                const double* __restrict__ bp = B2 + lk * LD + ncb + lr;
+                double a[4], an[4];
 #pragma unroll
-                for (int t = 0; t < 2; ++t) b[t] = B2[(k + lk) * LD + ncb + t * 8 + lr];
+                for (int i = 0; i < 4; ++i) a[i] = __ldg(ap + (size_t)(8 * i) * p.K2p);
+                for (int ks = 0; ks < nk2; ++ks) {
+                    if (ks + 1 < nk2) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (row0 + i * 8 < Mp) {
-                        const double a = __ldg(&A2[(size_t)(row0 + i * 8 + lr) * p.K2p + k + lk]);
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) dmma_m8n8k4(o[i][t][0], o[i][t][1], a, b[t]);
+                        for (int i = 0; i < 4; ++i) an[i] = __ldg(ap + (size_t)(8 * i) * p.K2p + 4 * (ks + 1));
                     }
+                    double b[NT];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) b[t] = bp[(4 * ks) * LD + t * 8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) dmma_m8n8k4(o[i][t][0], o[i][t][1], a[i], b[t]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = an[i];
                 }
             }
 
@@ -133,10 +177,10 @@ __global__ void __launch_bounds__(256) ygemm_kernel(const YGemmParams p) {
             for (int i = 0; i < 4; ++i) {
                 const int r = row0 + i * 8 + lr;
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
+                for (int t = 0; t < NT; ++t) {
                     const int cc = ncb + t * 8 + 2 * lk;
                     const long off = cout[cc];
-                    if (off < 0) continue;
+                    if (off < 0 || r >= Mgemm) continue;
                     if (p.mode == 0) {
                         if (r < p.M) {
                             const double E0 = e[i][t][0], E1 = e[i][t][1], O0 = o[i][t][0], O1 = o[i][t][1];
@@ -157,6 +201,31 @@ __global__ void __launch_bounds__(256) ygemm_kernel(const YGemmParams p) {
                 }
             }
         }
+        // remainder rows (at most 2) as dot products: thread -> (row, column)
+        for (int idx = tid; idx < (Mmax - Mgemm) * BN; idx += YG_THREADS) {
+            const int r = Mgemm + idx / BN, c = idx % BN;
+            const long off = cout[c];
+            if (off < 0) continue;
+            double E = 0.0, O = 0.0;
+            if (r < p.M) {
+                const double* __restrict__ ar = A1 + (size_t)r * p.K1p;
+                for (int k = 0; k < p.K1; ++k) E += __ldg(ar + k) * B1[k * LD + c];
+            }
+            if (r < p.M2) {
+                const double* __restrict__ ar = A2 + (size_t)r * p.K2p;
+                for (int k = 0; k < p.K2; ++k) O += __ldg(ar + k) * B2[k * LD + c];
+            }
+            if (p.mode == 0) {
+                if (r < p.M) {
+                    out[(long)r * p.out_ld + off] = E + O;
+                    const int rr = Nb - r;
+                    if (rr != r) out[(long)rr * p.out_ld + off] = sgn * (E - O);
+                }
+            } else {
+                if (r < p.M) out[(long)(2 * r) * p.out_ld + off] = E;
+                if (r < p.M2) out[(long)(2 * r + 1) * p.out_ld + off] = O;
+            }
+        }
     }
 }
 
@@ -170,13 +239,17 @@ static int launch_bn(const YGemmParams& p, cudaStream_t stream) {
         configured = smem;
     }
     dim3 grid((unsigned)((p.ncols + BN - 1) / BN), (unsigned)p.njobs);
-    CF_LAUNCH(kfn, grid, dim3(256), smem, stream, p);
+    CF_LAUNCH(kfn, grid, dim3(YG_THREADS), smem, stream, p);
     CF_KERNEL_CHECK();
     return 0;
 }
 
 int ygemm_launch(const YGemmParams& p, cudaStream_t stream) {
     if (p.ncols <= 0 || p.njobs <= 0) return 0;
+    if ((p.in_runstart && (p.in_runlen & 1)) || (p.out_runstart && (p.out_runlen & 1)) || (p.in_ld & 1) || (p.out_ld & 1)) {
+        set_last_error("ygemm: column runs must be (re,im) pairs");
+        return 1;
+    }
     const size_t rows = (size_t)(p.K1p + p.K2p);
     const size_t limit = 220 * 1024;
     if (rows * 68 * 8 + 1024 <= limit) return launch_bn<64>(p, stream);
