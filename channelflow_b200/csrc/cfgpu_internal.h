@@ -84,13 +84,14 @@ struct cfgpu_nse_s {
     int Nyd = 0, Kx = 0, Kz = 0;
     int nq = 0;
     cfgpu::ModeGeom geom;
-    double* d_base = nullptr;   // device: Ubaseyy[Ny], Wbaseyy[Ny], phys U,U',W,W' [4*Ny], inv_dy[Ny]
+    double* d_base = nullptr;   // device: Ubaseyy[Ny], Wbaseyy[Ny], phys U,U',W,W' [4*Ny], inv_dy[Ny], Ubase[Ny], Wbase[Ny]
     bool has_Ubaseyy = false, has_Wbaseyy = false;
     double lin_base_dPdx = 0, lin_base_dPdz = 0;  // nu*(Ubase'(b)-Ubase'(a))/Ly (nse.cpp:464-469)
     double* d_scal = nullptr;   // device scalars: [0] cfl max, [1] dPdxAct, [2] dPdzAct
     std::vector<double> lambda_t;
     std::vector<cfgpu::TauData> tau;  // one per substep
     int TM_solve = 8, TM_lin = 8;
+    cfgpu_field s_u = nullptr, s_t = nullptr;  // scratch fields of the non-rotational nonlinear terms (3 and 9 components)
 };
 
 namespace cfgpu {

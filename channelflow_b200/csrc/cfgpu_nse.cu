@@ -5,6 +5,7 @@
 
 #include "cfgpu_internal.h"
 #include "fieldops.cuh"
+#include "nlgen.cuh"
 
 using namespace cfgpu;
 
@@ -119,7 +120,7 @@ int cfgpu_nse_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, double Lx, double Lz
                      const cfgpu_nse_config* cfg, const double* Ubase_h, const double* Wbase_h, cfgpu_nse* out) {
     CF_ARG(ctx && cfg && out, "cfgpu_nse_create: null argument");
     CF_ARG(Ny % 2 == 1 && Ny >= 5, "cfgpu_nse_create: Ny must be odd and >= 5 (helmholtz.cpp:31)");
-    CF_ARG(cfg->nonlinearity == 0, "cfgpu_nse_create: only the Rotational nonlinearity is implemented in this build");
+    CF_ARG(cfg->nonlinearity >= 0 && cfg->nonlinearity <= 6, "cfgpu_nse_create: unknown nonlinearity (LinearAboutField is not supported)");
     cfgpu_nse nse = new cfgpu_nse_s();
     nse->ctx = ctx;
     nse->Nx = Nx; nse->Ny = Ny; nse->Nz = Nz; nse->Lx = Lx; nse->Lz = Lz; nse->a = a; nse->b = b;
@@ -153,8 +154,8 @@ int cfgpu_nse_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, double Lx, double Lz
     }
     nse->has_Ubaseyy = Ubase_h != nullptr;
     nse->has_Wbaseyy = Wbase_h != nullptr;
-    std::vector<double> hb(7 * (size_t)Ny, 0.0);
-    for (int n = 0; n < Ny; ++n) { hb[n] = Uyy[n]; hb[Ny + n] = Wyy[n]; }
+    std::vector<double> hb(9 * (size_t)Ny, 0.0);
+    for (int n = 0; n < Ny; ++n) { hb[n] = Uyy[n]; hb[Ny + n] = Wyy[n]; hb[7 * Ny + n] = U[n]; hb[8 * Ny + n] = W[n]; }
     cheb_to_physical_host(U, t);  for (int n = 0; n < Ny; ++n) hb[2 * Ny + n] = t[n];
     cheb_to_physical_host(Uy, t); for (int n = 0; n < Ny; ++n) hb[3 * Ny + n] = t[n];
     cheb_to_physical_host(W, t);  for (int n = 0; n < Ny; ++n) hb[4 * Ny + n] = t[n];
@@ -184,6 +185,8 @@ int cfgpu_nse_destroy(cfgpu_nse nse) {
     if (!nse) return 0;
     cudaStreamSynchronize(nse->ctx->stream);
     for (auto& t : nse->tau) cudaFree(t.base);
+    if (nse->s_u) cfgpu_field_destroy(nse->s_u);
+    if (nse->s_t) cfgpu_field_destroy(nse->s_t);
     cudaFree(nse->d_base);
     cudaFree(nse->d_scal);
     delete nse;
@@ -224,9 +227,70 @@ int cfgpu_nse_reset_lambda(cfgpu_nse nse, const double* lambda_t_h, int nsub) {
     return 0;
 }
 
+// Convection / Divergence / SkewSymmetric / Alternating / LinearAboutProfile (nse.cpp:12-91 -> diffops.cpp): the
+// reference's own sequence on scratch copies (u itself is never modified), generic full-grid transforms in between.
+static int nonlinear_generic(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
+    cfgpu_ctx ctx = nse->ctx;
+    if (!nse->s_u) CF_TRY(cfgpu_field_create(ctx, nse->Nx, nse->Ny, nse->Nz, 3, nse->Lx, nse->Lz, nse->a, nse->b, &nse->s_u));
+    cfgpu_field su = nse->s_u;
+    FieldGeom g{nse->Nx, nse->Ny, nse->Nz, nse->Lx, nse->Lz, nse->a, nse->b};
+    const long nreal = (long)su->compstride();
+    CF_TRY(cfgpu_field_copy(su, u));
+    int method = nse->cfg.nonlinearity;
+    if (method == 6) {  // LinearAboutProfile (diffops.cpp:3288-3365)
+        CF_TRY(cfgpu_field_make_physical_y(su));
+        CF_TRY(linearized_launch(su->d, f->d, nse->d_base + 2 * nse->Ny, g, ctx->stream));
+        f->xzstate = CFGPU_SPECTRAL; f->ystate = CFGPU_PHYSICAL; f->clean_Kx = f->clean_Kz = -1;
+        CF_TRY(cfgpu_field_make_spectral_y(f));
+    } else {
+        if (method == 4) { method = 2; nse->cfg.nonlinearity = 5; }       // Alternating: divergence now, convection next
+        else if (method == 5) { method = 1; nse->cfg.nonlinearity = 4; }  // Alternating_
+        if (!nse->s_t) CF_TRY(cfgpu_field_create(ctx, nse->Nx, nse->Ny, nse->Nz, 9, nse->Lx, nse->Lz, nse->a, nse->b, &nse->s_t));
+        cfgpu_field st = nse->s_t;
+        const double rot = nse->cfg.rotation;
+        // u_tot = u + Ubase e_x + Wbase e_z - Vsuck e_y on the (0,0) mode (nse.cpp:28-36)
+        CF_TRY(add_base00_launch(su->d, nse->has_Ubaseyy ? nse->d_base + 7 * nse->Ny : nullptr,
+                                 nse->has_Wbaseyy ? nse->d_base + 8 * nse->Ny : nullptr, nse->cfg.Vsuck, 1.0, g, ctx->stream));
+        if (method == 1 || method == 3) {  // grad(u) (diffops.cpp:3169-3173, 3606-3609)
+            CF_TRY(grad3_launch(su->d, st->d, g, ctx->stream));
+            st->xzstate = st->ystate = CFGPU_SPECTRAL; st->clean_Kx = st->clean_Kz = -1;
+            CF_TRY(cfgpu_field_make_physical(st));
+        }
+        CF_TRY(cfgpu_field_make_physical(su));
+        if (method == 1) {         // convectionNL = dotgrad(u,u) (diffops.cpp:2883-2885, 3586-3643)
+            CF_TRY(pointwise_nl_launch(su->d, st->d, f->d, 1.0, 0, 0.0, nreal, ctx->stream));
+            f->xzstate = f->ystate = CFGPU_PHYSICAL; f->clean_Kx = f->clean_Kz = -1;
+            CF_TRY(cfgpu_field_make_spectral(f));
+            // REFERENCE QUIRK, reproduced: dotgrad ignores `finalstate` and returns f spectral, yet navierstokesNL then adds
+            // the Coriolis term of the physical u to f's raw array and its closing f.makeSpectral() is a no-op
+            // (nse.cpp:63-79 after diffops.cpp:3640).  Only the rotational and skew-symmetric forms honour finalstate.
+            if (rot != 0.0) CF_TRY(coriolis_launch(su->d, f->d, rot, nreal, nse->Nz, ctx->stream));
+        } else if (method == 3) {  // skewsymmetricNL (diffops.cpp:3142-3286)
+            CF_TRY(pointwise_nl_launch(su->d, st->d, f->d, 0.5, 1, rot, nreal, ctx->stream));
+            f->xzstate = f->ystate = CFGPU_PHYSICAL; f->clean_Kx = f->clean_Kz = -1;
+            st->xzstate = st->ystate = CFGPU_PHYSICAL;
+            CF_TRY(cfgpu_field_make_spectral(st));
+            CF_TRY(cfgpu_field_make_spectral(f));
+            CF_TRY(div9_launch(st->d, f->d, 0.5, 1, g, ctx->stream));
+        } else {                   // divergenceNL (diffops.cpp:3110-3134)
+            CF_TRY(pointwise_nl_launch(su->d, st->d, f->d, 0.0, 1, 0.0, nreal, ctx->stream));
+            st->xzstate = st->ystate = CFGPU_PHYSICAL; st->clean_Kx = st->clean_Kz = -1;
+            CF_TRY(cfgpu_field_make_spectral(st));
+            CF_TRY(div9_launch(st->d, f->d, 1.0, 0, g, ctx->stream));
+            f->xzstate = f->ystate = CFGPU_SPECTRAL; f->clean_Kx = f->clean_Kz = -1;
+            // same reference quirk as for the convection form: div(uu, f, Physical) leaves f spectral (diffops.cpp:2555-2557)
+            if (rot != 0.0) CF_TRY(coriolis_launch(su->d, f->d, rot, nreal, nse->Nz, ctx->stream));
+        }
+    }
+    f->xzstate = f->ystate = CFGPU_SPECTRAL;
+    if (nse->cfg.dealias_xz) CF_TRY(cfgpu_field_zero_padded_modes(f));  // nse.cpp:389-390
+    return 0;
+}
+
 int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     CF_ARG(u->Nd == 3 && f->Nd == 3, "cfgpu_nse_nonlinear: fields must have 3 components");
     CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "cfgpu_nse_nonlinear: u must be spectral");
+    if (nse->cfg.nonlinearity != 0) return nonlinear_generic(nse, u, f);
     cfgpu_ctx ctx = nse->ctx;
     CF_TRY(inverse_to_Q(nse, u, true));
 

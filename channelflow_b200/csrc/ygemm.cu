@@ -209,10 +209,12 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
             double E = 0.0, O = 0.0;
             if (r < p.M) {
                 const double* __restrict__ ar = A1 + (size_t)r * p.K1p;
+#pragma unroll 8
                 for (int k = 0; k < p.K1; ++k) E += __ldg(ar + k) * B1[k * LD + c];
             }
             if (r < p.M2) {
                 const double* __restrict__ ar = A2 + (size_t)r * p.K2p;
+#pragma unroll 8
                 for (int k = 0; k < p.K2; ++k) O += __ldg(ar + k) * B2[k * LD + c];
             }
             if (p.mode == 0) {

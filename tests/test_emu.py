@@ -55,6 +55,22 @@ def test_nonlinear(lib, over):
     assert r["nonlinear"] < 1e-14, r
 
 
+@pytest.mark.parametrize("nl", ["conv", "div", "skew", "alt", "linear"])
+@pytest.mark.parametrize("over", [dict(), dict(rotation=0.1, Vsuck=0.0025, baseflow="suction"), dict(dealiasing="none")])
+def test_nonlinear_methods(lib, nl, over):
+    """convection / divergence / skew-symmetric / alternating / linearized-about-profile terms (nse.cpp:12-91)."""
+    if nl == "linear" and over.get("rotation"):
+        pytest.skip("reference leaves f in the physical state for LinearAboutProfile with rotation != 0 (nse.cpp:17-25): undefined")
+    r = parity.nonlinear(lib, SMALL, nonlinearity=nl, **over)
+    assert r["nonlinear"] < 1e-12, r
+
+
+@pytest.mark.parametrize("nl", ["skew", "conv", "div", "alt", "linear"])
+def test_dns_nonlinear_methods(lib, nl):
+    r = parity.dns_steps(lib, SMALL, checkpoints=(1, 4), nonlinearity=nl)
+    assert r[1] < 1e-12 and r[4] < 1e-12, r
+
+
 @pytest.mark.parametrize("cfg", [SMALL, ODD])
 def test_tausolve_modes(lib, cfg):
     """Every retained mode against the reference TauSolver; the right-hand sides are O(1), so 1e-14 absolute is a few
