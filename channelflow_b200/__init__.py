@@ -28,7 +28,8 @@ cfgpu_field_scale cfgpu_field_get_profile cfgpu_field_add_profile cfgpu_field_ze
 cfgpu_field_make_physical_y cfgpu_field_make_spectral_y cfgpu_field_make_physical_xz cfgpu_field_make_spectral_xz
 cfgpu_field_make_physical cfgpu_field_make_spectral cfgpu_l2norm2 cfgpu_l2dist2 cfgpu_l2ip cfgpu_nse_create
 cfgpu_nse_destroy cfgpu_nse_set_constraint cfgpu_nse_reset_lambda cfgpu_nse_nonlinear cfgpu_nse_solve
-cfgpu_nse_linear cfgpu_nse_cflfactor cfgpu_nse_get_dPd""".split()
+cfgpu_nse_linear cfgpu_nse_cflfactor cfgpu_nse_get_dPd cfgpu_comm_unique_id cfgpu_comm_init_nccl
+cfgpu_comm_init_external cfgpu_comm_rank cfgpu_comm_ranges cfgpu_field_allgather""".split()
 
 
 class CfgpuError(RuntimeError):
@@ -338,6 +339,10 @@ class HostLib:
         for n in ("cf_l2norm", "cf_l2dist", "cf_l2ip", "cf_l2norm2", "cf_dns_cfl", "cf_dns_time", "cf_dns_dPdx",
                   "cf_dns_Ubulk", "cf_timer_stop", "cf_timestep_dt", "cf_timestep_dT", "cf_timestep_CFL", "cf_cmplx_get"):
             getattr(L, n).restype = d
+        L.cf_comm_unique_id.argtypes = [vp]
+        L.cf_comm_init_nccl.argtypes = [i, i, vp]
+        L.cf_comm_ranges.argtypes = [i, i, i, C.POINTER(i)]
+        L.cf_field_allgather.argtypes = [vp]
         L.cf_field_upload.argtypes = [vp, dpt]
         L.cf_field_download.argtypes = [vp, dpt]
         L.cf_field_set_state.argtypes = [vp, i, i]
@@ -368,11 +373,57 @@ class HostLib:
 
     def sync(self): self.L.cf_sync()
 
+    # ---- multi-GPU (one process per GPU)
+    def comm_init_nccl(self, rank, nranks, id_bytes):
+        """id_bytes: the 128-byte NCCL unique id created by rank 0 (comm_unique_id) and broadcast by the launcher."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(id_bytes))
+        self.L.cf_comm_init_nccl(rank, nranks, buf)
+
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        if self.L.cf_comm_unique_id(buf) != 0:
+            raise CfgpuError(self.gpu.L.cfgpu_last_error().decode())
+        return bytes(buf)
+
+    def comm_init_external(self, rank, nranks, exchange, allreduce):
+        """Host-supplied collectives (CPU tests): exchange(peers, sendbufs, recvbufs) / allreduce(buf, op) on numpy views."""
+        EX = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
+                         C.POINTER(C.c_void_p), C.POINTER(C.c_longlong))
+        AR = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int)
+
+        def _ex(user, n, peer, sp, sb, rp, rb):
+            try:
+                sends = [(peer[i], np.ctypeslib.as_array((C.c_ubyte * sb[i]).from_address(sp[i])) if sb[i] else np.empty(0, np.uint8)) for i in range(n)]
+                recvs = [(peer[i], np.ctypeslib.as_array((C.c_ubyte * rb[i]).from_address(rp[i])) if rb[i] else np.empty(0, np.uint8)) for i in range(n)]
+                exchange(sends, recvs)
+                return 0
+            except Exception:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        def _ar(user, buf, n, op):
+            try:
+                allreduce(np.ctypeslib.as_array(buf, shape=(n,)), op)
+                return 0
+            except Exception:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._cb = (EX(_ex), AR(_ar))  # keep alive
+        self.L.cf_comm_init_external(rank, nranks, self._cb[0], self._cb[1])
+
+    def comm_ranges(self, nmx, Ny, rank):
+        r = (C.c_int * 4)()
+        self.L.cf_comm_ranges(nmx, Ny, rank, r)
+        return tuple(r)
+
     def profile_enable(self, on=True): self.L.cf_profile_enable(1 if on else 0)
 
     def profile_read(self, reset=True):
-        ms = (C.c_double * 8)()
-        calls = (C.c_longlong * 8)()
+        ms = (C.c_double * 9)()
+        calls = (C.c_longlong * 9)()
         self.L.cf_profile_read(ms, calls, 1 if reset else 0)
         return list(ms), list(calls)
 
@@ -443,6 +494,7 @@ class FlowField:
     def l2ip(self, o): return self.lib.L.cf_l2ip(self.h, o.h)
     def cmplx(self, mx, my, mz, i): return complex(self.lib.L.cf_cmplx_get(self.h, mx, my, mz, i, 0), self.lib.L.cf_cmplx_get(self.h, mx, my, mz, i, 1))
     def set_cmplx(self, mx, my, mz, i, v): self.lib.L.cf_cmplx_set(self.h, mx, my, mz, i, v.real, v.imag)
+    def allgather(self): self.lib.L.cf_field_allgather(self.h)
     def save(self, filebase): self.lib.L.cf_field_save(self.h, filebase.encode())
     def axpby(self, a, x, b=0.0, z=None): self.lib.L.cf_field_axpby(self.h, a, x.h, b, z.h if z is not None else None)
     def scale(self, s): self.lib.L.cf_field_scale(self.h, s)

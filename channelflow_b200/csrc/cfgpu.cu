@@ -278,6 +278,8 @@ int cfgpu_finalize(cfgpu_ctx ctx) {
     if (ctx->ws_P.ptr) cudaFree(ctx->ws_P.ptr);
     if (ctx->ws_Q.ptr) cudaFree(ctx->ws_Q.ptr);
     if (ctx->ws_red.ptr) cudaFree(ctx->ws_red.ptr);
+    if (ctx->ws_S.ptr) cudaFree(ctx->ws_S.ptr);
+    comm_destroy(ctx->comm);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -350,6 +352,65 @@ int cfgpu_graph_begin(cfgpu_ctx) { set_last_error("graphs unavailable in the emu
 int cfgpu_graph_end(cfgpu_ctx, int*) { set_last_error("graphs unavailable in the emulation build"); return 1; }
 int cfgpu_graph_launch(cfgpu_ctx, int) { set_last_error("graphs unavailable in the emulation build"); return 1; }
 #endif
+
+// ------------------------------------------------------------------------------------------------ multi-GPU
+int cfgpu_comm_unique_id(void* id128_h) { return comm_unique_id(id128_h); }
+int cfgpu_comm_init_nccl(cfgpu_ctx ctx, int rank, int nranks, const void* id128_h) {
+    CF_ARG(ctx && id128_h, "cfgpu_comm_init_nccl: null argument");
+    return comm_init_nccl(ctx->comm, rank, nranks, id128_h);
+}
+int cfgpu_comm_init_external(cfgpu_ctx ctx, int rank, int nranks, cfgpu_exchange_fn ex, cfgpu_allreduce_fn ar, void* user) {
+    CF_ARG(ctx && ex && ar, "cfgpu_comm_init_external: null argument");
+    CF_ARG(nranks >= 1 && nranks <= COMM_MAXRANKS && rank >= 0 && rank < nranks, "cfgpu_comm_init_external: bad rank / world size");
+    ctx->comm.rank = rank; ctx->comm.nranks = nranks;
+    ctx->comm.ext_exchange = ex; ctx->comm.ext_allreduce = ar; ctx->comm.ext_user = user;
+    return 0;
+}
+int cfgpu_comm_rank(cfgpu_ctx ctx, int* rank, int* nranks) {
+    if (rank) *rank = ctx->comm.rank;
+    if (nranks) *nranks = ctx->comm.nranks;
+    return 0;
+}
+int cfgpu_comm_ranges(cfgpu_ctx ctx, int nmx, int Ny, int rank, int* x0, int* x1, int* y0, int* y1) {
+    CF_ARG(rank >= 0 && rank < ctx->comm.nranks, "cfgpu_comm_ranges: bad rank");
+    int a, b;
+    part_range(nmx, ctx->comm.nranks, rank, a, b);
+    if (x0) *x0 = a;
+    if (x1) *x1 = b;
+    part_range(Ny, ctx->comm.nranks, rank, a, b);
+    if (y0) *y0 = a;
+    if (y1) *y1 = b;
+    return 0;
+}
+// All-gather of the owned kx rows of a spectral, de-aliased field.  Staging layout per owner s: [i][my][mxi in X_s][kz<=Kz].
+int cfgpu_field_allgather(cfgpu_field f) {
+    cfgpu_ctx ctx = f->ctx;
+    Comm& cm = ctx->comm;
+    if (cm.nranks == 1) return 0;
+    CF_ARG(f->xzstate == CFGPU_SPECTRAL, "cfgpu_field_allgather: field must be xz-spectral");
+    const int Kx = f->Nx / 3 - 1, Kz = f->Nz / 3 - 1, nmx = 2 * Kx + 1, nkz = Kz + 1;
+    const size_t rows = (size_t)f->Nd * f->Ny;
+    CF_TRY(ws_reserve(ctx->ws_S, rows * nmx * nkz * 2 * sizeof(double)));
+    double2* S = reinterpret_cast<double2*>(ctx->ws_S.ptr);
+    int x0, x1;
+    part_range(nmx, cm.nranks, cm.rank, x0, x1);
+    CF_TRY(rows_pack_launch(f->d, reinterpret_cast<double*>(S + rows * nkz * x0), f->Nx, f->Nz, (int)rows, Kx, Kz, x0, x1, 0, ctx->stream));
+    std::vector<ExchangeMsg> msgs;
+    for (int r = 0; r < cm.nranks; ++r) {
+        if (r == cm.rank) continue;
+        int a, b;
+        part_range(nmx, cm.nranks, r, a, b);
+        msgs.push_back({r, S + rows * nkz * x0, (long long)(rows * nkz * (x1 - x0) * 16), S + rows * nkz * a, (long long)(rows * nkz * (b - a) * 16)});
+    }
+    CF_TRY(comm_exchange(cm, msgs.data(), (int)msgs.size(), ctx->stream));
+    for (int r = 0; r < cm.nranks; ++r) {
+        if (r == cm.rank) continue;
+        int a, b;
+        part_range(nmx, cm.nranks, r, a, b);
+        CF_TRY(rows_pack_launch(f->d, reinterpret_cast<double*>(S + rows * nkz * a), f->Nx, f->Nz, (int)rows, Kx, Kz, a, b, 1, ctx->stream));
+    }
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ fields
 int cfgpu_field_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, int Nd, double Lx, double Lz, double a, double b,
@@ -543,8 +604,14 @@ static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool pa
     double* out_dev = ctx->ws_red.ptr;
     double* partial = ctx->ws_red.ptr + 8;
     const size_t cap = ctx->ws_red.bytes / sizeof(double) - 8;
-    CF_TRY(l2form_launch(u->d, v ? v->d : nullptr, mode, pl->Wgram, u->Ny, u->Nx, u->Nz, u->Nd, Kx, Kz, padded ? 0 : 1, scale,
+    int x0 = 0, x1 = padded ? 2 * Kx + 1 : u->Nx;
+    if (ctx->comm.nranks > 1) {
+        CF_ARG(padded, "L2 norm: multi-GPU norms need de-aliased (padded) fields");
+        part_range(2 * Kx + 1, ctx->comm.nranks, ctx->comm.rank, x0, x1);
+    }
+    CF_TRY(l2form_launch(u->d, v ? v->d : nullptr, mode, pl->Wgram, u->Ny, u->Nx, u->Nz, u->Nd, Kx, Kz, padded ? 0 : 1, x0, x1, scale,
                          partial, cap, out_dev, ctx->stream));
+    CF_TRY(comm_allreduce(ctx->comm, out_dev, 1, 0, ctx->stream));
     CF_CUDA(cudaMemcpyAsync(out_h, out_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CF_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;

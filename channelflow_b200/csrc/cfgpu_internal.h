@@ -8,6 +8,7 @@
 
 #include "../../include/cfgpu.h"
 #include "cf_common.cuh"
+#include "comm.cuh"
 #include "fft_smem.cuh"
 #include "tau.cuh"
 #include "xzpass.cuh"
@@ -50,7 +51,8 @@ struct cfgpu_ctx_s {
     std::map<std::tuple<int, double, double>, cfgpu::YPlan> yplans;
     std::map<int, cfgpu::FftPlanHost> fftplans;
     std::map<std::tuple<int, int, int, int>, cfgpu::ModeBox> boxes;
-    cfgpu::Workspace ws_P, ws_Q, ws_red;
+    cfgpu::Workspace ws_P, ws_Q, ws_S, ws_red;
+    cfgpu::Comm comm;  // rank / world size / collectives (single rank by default)
     std::vector<void*> graphs;  // cudaGraphExec_t
     bool capturing = false;
     // stage profiler
@@ -82,7 +84,8 @@ struct cfgpu_nse_s {
     double Lx = 0, Lz = 0, a = 0, b = 0;
     cfgpu_nse_config cfg;
     int Nyd = 0, Kx = 0, Kz = 0;
-    int nq = 0;
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;  // owned kx rows (mxi) and y planes of this rank (whole ranges on one GPU)
+    int nq = 0;                          // owned retained modes
     cfgpu::ModeGeom geom;
     double* d_base = nullptr;   // device: Ubaseyy[Ny], Wbaseyy[Ny], phys U,U',W,W' [4*Ny], inv_dy[Ny], Ubase[Ny], Wbase[Ny]
     bool has_Ubaseyy = false, has_Wbaseyy = false;

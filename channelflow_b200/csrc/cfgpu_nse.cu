@@ -2,6 +2,7 @@
 // linear term, CFL.  Host orchestration only; the kernels are in ygemm.cu, xzpass.cu, tau.cu.
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "cfgpu_internal.h"
 #include "fieldops.cuh"
@@ -35,7 +36,47 @@ static int pick_TL(int Nx, int Nz, int npair) {
     return tl;
 }
 
-// spectral u (3 comps, reference layout) -> compact pencils P[0..nout) (y physical), then Q (x physical)
+// all-to-all between the kx-slab pencils P[f][Ny][mxi in X_rank][kz] and the y-slab staging
+// S[s][f][y in Y_rank][mxi in X_s][kz] (comm.cuh); dir 0: P -> S (inverse transform), 1: S -> P (forward)
+static int slab_exchange(cfgpu_nse nse, int nf, int dir) {
+    cfgpu_ctx ctx = nse->ctx;
+    Comm& cm = ctx->comm;
+    if (cm.nranks == 1) return 0;
+    const int nmx = 2 * nse->Kx + 1, nkz = nse->Kz + 1;
+    const int nxl = nse->x1 - nse->x0, nyl = nse->y1 - nse->y0;
+    double2* P = reinterpret_cast<double2*>(ctx->ws_P.ptr);
+    double2* S = reinterpret_cast<double2*>(ctx->ws_S.ptr);
+    std::vector<ExchangeMsg> msgs;
+    for (int r = 0; r < cm.nranks; ++r) {
+        int xa, xb, ya, yb;
+        part_range(nmx, cm.nranks, r, xa, xb);
+        part_range(nse->Ny, cm.nranks, r, ya, yb);
+        for (int f = 0; f < nf; ++f) {
+            double2* pp = P + ((size_t)f * nse->Ny + ya) * nxl * nkz;                                     // my rows, r's planes
+            const long long pb = (long long)(yb - ya) * nxl * nkz * 16;
+            double2* sp = S + (size_t)nkz * ((size_t)nf * nyl * xa + (size_t)f * nyl * (xb - xa));          // r's rows, my planes
+            const long long sb = (long long)nyl * (xb - xa) * nkz * 16;
+            if (dir == 0) msgs.push_back({r, pp, pb, sp, sb});
+            else msgs.push_back({r, sp, sb, pp, pb});
+        }
+    }
+    return comm_exchange(cm, msgs.data(), (int)msgs.size(), ctx->stream);
+}
+
+static void fill_xsplit(cfgpu_nse nse, XPassParams& xp, int nstage) {
+    const Comm& cm = nse->ctx->comm;
+    xp.nranks = cm.nranks;
+    xp.nstage = nstage;
+    for (int r = 0; r < cm.nranks; ++r) {
+        int a, b;
+        part_range(2 * nse->Kx + 1, cm.nranks, r, a, b);
+        xp.xsplit[r] = a;
+        xp.xsplit[r + 1] = b;
+    }
+}
+
+// spectral u (3 comps, reference layout; this rank's kx rows) -> compact pencils P[0..nout) (y physical), all-to-all,
+// then Q (x physical) for this rank's y planes
 static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     cfgpu_ctx ctx = nse->ctx;
     const YPlan* yp;
@@ -45,11 +86,16 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     CF_TRY(get_box(ctx, nse->Nx, nse->Nz, nse->Kx, nse->Kz, &bx));
     CF_TRY(get_fftplan(ctx, nse->Nx, &fx));
     const int nmx = 2 * nse->Kx + 1, nkz = nse->Kz + 1;
-    const size_t Pf = (size_t)nse->Ny * nmx * nkz * 2;      // doubles per pencil field P
-    const size_t Qf = (size_t)nse->Ny * nse->Nx * nkz * 2;  // doubles per pencil field Q
+    const int nxl = nse->x1 - nse->x0, nyl = nse->y1 - nse->y0;
+    const bool multi = ctx->comm.nranks > 1;
+    const size_t Pf = (size_t)nse->Ny * nxl * nkz * 2;     // doubles per pencil field P (kx slab)
+    const size_t Sf = (size_t)nyl * nmx * nkz * 2;          // doubles per staged field (y slab)
+    const size_t Qf = (size_t)nyl * nse->Nx * nkz * 2;      // doubles per pencil field Q (y slab)
     CF_TRY(ws_reserve(ctx->ws_P, 5 * Pf * sizeof(double)));
+    if (multi) CF_TRY(ws_reserve(ctx->ws_S, 5 * Sf * sizeof(double)));
     CF_TRY(ws_reserve(ctx->ws_Q, 7 * Qf * sizeof(double)));
     double* P = ctx->ws_P.ptr;
+    const int nfP = with_derivs ? 5 : 3;
 
     YGemmParams p;
     memset(&p, 0, sizeof p);
@@ -57,9 +103,9 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     p.M = p.M2 = yp->Nh; p.K1 = yp->Ne; p.K2 = yp->No; p.K1p = yp->invK1p; p.K2p = yp->invK2p;
     p.A1[0] = yp->Ce; p.A2[0] = yp->Co; p.sgn[0] = 1.0;
     p.A1[1] = yp->CDe; p.A2[1] = yp->CDo; p.sgn[1] = -1.0;
-    p.ncols = (long)nmx * nkz * 2;
-    p.in_runlen = 2 * nkz; p.in_runstart = bx->runstart_full; p.in_ld = u->rowstride();
-    p.out_runlen = 1; p.out_runstart = nullptr; p.out_ld = (long)nmx * nkz * 2;
+    p.ncols = (long)nxl * nkz * 2;
+    p.in_runlen = 2 * nkz; p.in_runstart = bx->runstart_full + nse->x0; p.in_ld = u->rowstride();
+    p.out_runlen = 1; p.out_runstart = nullptr; p.out_ld = (long)nxl * nkz * 2;
     p.njobs = 3;
     for (int i = 0; i < 3; ++i) {
         p.job[i].in = u->d + i * u->compstride();
@@ -71,6 +117,7 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         p.job[2].nmat = 2; p.job[2].out[1] = P + 4 * Pf;  // dw/dy
     }
     { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(p, ctx->stream)); }
+    { StageTimer _t(ctx, 8); CF_TRY(slab_exchange(nse, nfP, 0)); }
 
     XPassParams xp;
     memset(&xp, 0, sizeof xp);
@@ -78,9 +125,10 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     xp.TZ = pick_TZ(nse->Nx);
     xp.Lx = nse->Lx;
     xp.plan = *fx;
-    xp.in = reinterpret_cast<const double2*>(P);
+    xp.in = reinterpret_cast<const double2*>(multi ? ctx->ws_S.ptr : P);
     xp.out = reinterpret_cast<double2*>(ctx->ws_Q.ptr);
-    xp.ny0 = 0; xp.nyn = nse->Ny;
+    xp.ny0 = nse->y0; xp.nyn = nyl;
+    fill_xsplit(nse, xp, nfP);
     if (with_derivs) {
         const int src[7] = {0, 1, 2, 3, 4, 1, 2}, ddx[7] = {0, 0, 0, 0, 0, 1, 1};
         xp.nfields = 7;
@@ -110,7 +158,7 @@ static int fill_zpass(cfgpu_nse nse, ZPassParams& zp, int mode) {
     zp.Uy = nse->d_base + 2 * nse->Ny;
     zp.inv_dy = nse->d_base + 6 * nse->Ny;
     zp.cfl_max = nse->d_scal;
-    zp.ny0 = 0; zp.nyn = nse->Ny;
+    zp.ny0 = nse->y0; zp.nyn = nse->y1 - nse->y0;
     return 0;
 }
 
@@ -131,7 +179,11 @@ int cfgpu_nse_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, double Lx, double Lz
     if (Nx % 2 == 1 && !cfg->dealias_xz) nse->Kx = Nx / 2 - 1;
     CF_ARG(nse->Kx >= 0 && nse->Kz >= 0, "cfgpu_nse_create: grid too small");
     CF_ARG(nse->Nyd % 2 == 1, "cfgpu_nse_create: dealiased Ny must be odd");
-    nse->nq = (2 * nse->Kx + 1) * (nse->Kz + 1);
+    part_range(2 * nse->Kx + 1, ctx->comm.nranks, ctx->comm.rank, nse->x0, nse->x1);
+    part_range(Ny, ctx->comm.nranks, ctx->comm.rank, nse->y0, nse->y1);
+    CF_ARG(nse->x1 > nse->x0 && nse->y1 > nse->y0, "cfgpu_nse_create: more ranks than kx rows or y planes");
+    nse->nq = (nse->x1 - nse->x0) * (nse->Kz + 1);
+    nse->geom.mx0 = nse->x0;
     nse->geom.Nx = Nx; nse->geom.Ny = Ny; nse->geom.Nz = Nz; nse->geom.Kx = nse->Kx; nse->geom.Kz = nse->Kz;
     nse->geom.Lx = Lx; nse->geom.Lz = Lz;
     nse->TM_solve = tau_pick_TM_solve(nse->Nyd);
@@ -205,9 +257,10 @@ int cfgpu_nse_reset_lambda(cfgpu_nse nse, const double* lambda_t_h, int nsub) {
     cfgpu_ctx ctx = nse->ctx;
     while ((int)nse->tau.size() < nsub) {
         TauData td;
-        td.N = nse->Nyd; td.nq = nse->nq; td.TM = nse->TM_solve; td.ntiles = TauData::num_tiles(td.nq, td.TM);
+        td.N = nse->Nyd; td.nq = nse->nq; td.has00 = nse->x0 == 0 ? 1 : 0; td.TM = nse->TM_solve;
+        td.ntiles = TauData::num_tiles(td.nq, td.TM, td.has00);
         td.nu = nse->cfg.nu; td.a = nse->a; td.b = nse->b;
-        const size_t n = TauData::doubles(td.N, td.nq, td.TM);
+        const size_t n = TauData::doubles(td.N, td.nq, td.TM, td.has00);
         if (cudaMalloc((void**)&td.base, n * sizeof(double)) != cudaSuccess) {
             set_last_error("cfgpu_nse_reset_lambda: cudaMalloc failed");
             return 1;
@@ -231,6 +284,7 @@ int cfgpu_nse_reset_lambda(cfgpu_nse nse, const double* lambda_t_h, int nsub) {
 // reference's own sequence on scratch copies (u itself is never modified), generic full-grid transforms in between.
 static int nonlinear_generic(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     cfgpu_ctx ctx = nse->ctx;
+    CF_ARG(ctx->comm.nranks == 1, "only the rotational nonlinearity is distributed over several GPUs in this build");
     if (!nse->s_u) CF_TRY(cfgpu_field_create(ctx, nse->Nx, nse->Ny, nse->Nz, 3, nse->Lx, nse->Lz, nse->a, nse->b, &nse->s_u));
     cfgpu_field su = nse->s_u;
     FieldGeom g{nse->Nx, nse->Ny, nse->Nz, nse->Lx, nse->Lz, nse->a, nse->b};
@@ -308,10 +362,13 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     xp.Lx = nse->Lx;
     xp.plan = *fx;
     xp.nfields = 3;
+    const bool multi = ctx->comm.nranks > 1;
     xp.in = reinterpret_cast<const double2*>(ctx->ws_Q.ptr);
-    xp.out = reinterpret_cast<double2*>(ctx->ws_P.ptr);
-    xp.ny0 = 0; xp.nyn = nse->Ny;
+    xp.out = reinterpret_cast<double2*>(multi ? ctx->ws_S.ptr : ctx->ws_P.ptr);
+    xp.ny0 = nse->y0; xp.nyn = nse->y1 - nse->y0;
+    fill_xsplit(nse, xp, 3);
     { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xp, ctx->stream)); }
+    { StageTimer _t(ctx, 8); CF_TRY(slab_exchange(nse, 3, 1)); }
 
     // aliased modes of f must be exactly zero (FlowField::zeroPaddedModes, nse.cpp:389-390); the kernels below
     // only ever write retained modes
@@ -322,16 +379,16 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     const ModeBox* bx;
     CF_TRY(get_yplan(ctx, nse->Ny, nse->a, nse->b, &yp));
     CF_TRY(get_box(ctx, nse->Nx, nse->Nz, nse->Kx, nse->Kz, &bx));
-    const int nmx = 2 * nse->Kx + 1, nkz = nse->Kz + 1;
-    const size_t Pf = (size_t)nse->Ny * nmx * nkz * 2;
+    const int nxl = nse->x1 - nse->x0, nkz = nse->Kz + 1;
+    const size_t Pf = (size_t)nse->Ny * nxl * nkz * 2;
     YGemmParams p;
     memset(&p, 0, sizeof p);
     p.N = nse->Ny; p.mode = 1;
     p.M = yp->Ne; p.M2 = yp->No; p.K1 = p.K2 = yp->Nh; p.K1p = p.K2p = yp->fwdKp;
     p.A1[0] = yp->Fe; p.A2[0] = yp->Fo; p.sgn[0] = 1.0;
-    p.ncols = (long)nmx * nkz * 2;
-    p.in_runlen = 1; p.in_runstart = nullptr; p.in_ld = (long)nmx * nkz * 2;
-    p.out_runlen = 2 * nkz; p.out_runstart = bx->runstart_full; p.out_ld = f->rowstride();
+    p.ncols = (long)nxl * nkz * 2;
+    p.in_runlen = 1; p.in_runstart = nullptr; p.in_ld = (long)nxl * nkz * 2;
+    p.out_runlen = 2 * nkz; p.out_runstart = bx->runstart_full + nse->x0; p.out_ld = f->rowstride();
     p.njobs = 3;
     for (int i = 0; i < 3; ++i) {
         p.job[i].in = ctx->ws_P.ptr + i * Pf;
@@ -401,6 +458,7 @@ int cfgpu_nse_cflfactor(cfgpu_nse nse, cfgpu_field u, double* out_h) {
     CF_TRY(fill_zpass(nse, zp, ZP_CFL));
     CF_CUDA(cudaMemsetAsync(nse->d_scal, 0, sizeof(double), ctx->stream));
     CF_TRY(zpass_launch(zp, ctx->stream));
+    CF_TRY(comm_allreduce(ctx->comm, nse->d_scal, 1, 1, ctx->stream));
     CF_CUDA(cudaMemcpyAsync(out_h, nse->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CF_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -408,6 +466,11 @@ int cfgpu_nse_cflfactor(cfgpu_nse nse, cfgpu_field u, double* out_h) {
 
 int cfgpu_nse_get_dPd(cfgpu_nse nse, double* dPdx_h, double* dPdz_h) {
     double v[2];
+    if (nse->ctx->comm.nranks > 1) {  // only the owner of the (0,0) mode computed them; the others hold zeros
+        CF_CUDA(cudaMemcpyAsync(nse->d_scal + 4, nse->d_scal + 1, 2 * sizeof(double), cudaMemcpyDeviceToDevice, nse->ctx->stream));
+        CF_TRY(comm_allreduce(nse->ctx->comm, nse->d_scal + 4, 2, 0, nse->ctx->stream));
+        CF_CUDA(cudaMemcpyAsync(v, nse->d_scal + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, nse->ctx->stream));
+    } else
     CF_CUDA(cudaMemcpyAsync(v, nse->d_scal + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, nse->ctx->stream));
     CF_CUDA(cudaStreamSynchronize(nse->ctx->stream));
     *dPdx_h = v[0];

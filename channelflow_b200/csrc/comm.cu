@@ -1,0 +1,185 @@
+// See comm.cuh.
+#include "comm.cuh"
+
+#include <vector>
+#ifndef CF_EMU
+#include <dlfcn.h>
+#endif
+
+namespace cfgpu {
+
+#ifndef CF_EMU
+namespace {
+// the handful of NCCL entry points used, bound with dlsym (public API of nccl.h, NCCL >= 2.7)
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef int (*fn_GetUniqueId)(ncclUniqueId_t*);
+typedef int (*fn_CommInitRank)(void**, int, ncclUniqueId_t, int);
+typedef int (*fn_CommDestroy)(void*);
+typedef int (*fn_Group)(void);
+typedef int (*fn_Send)(const void*, size_t, int /*datatype*/, int, void*, cudaStream_t);
+typedef int (*fn_Recv)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_AllReduce)(const void*, void*, size_t, int, int /*op*/, void*, cudaStream_t);
+typedef const char* (*fn_GetErrorString)(int);
+constexpr int NCCL_INT8 = 0, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+
+struct NcclApi {
+    void* lib = nullptr;
+    fn_GetUniqueId GetUniqueId = nullptr;
+    fn_CommInitRank CommInitRank = nullptr;
+    fn_CommDestroy CommDestroy = nullptr;
+    fn_Group GroupStart = nullptr, GroupEnd = nullptr;
+    fn_Send Send = nullptr;
+    fn_Recv Recv = nullptr;
+    fn_AllReduce AllReduce = nullptr;
+    fn_GetErrorString GetErrorString = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.lib) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy torch (or anyone) already loaded
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        set_last_error("NCCL not found (libnccl.so.2): multi-GPU runs need it");
+        return 1;
+    }
+    g_nccl.GetUniqueId = (fn_GetUniqueId)dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (fn_CommInitRank)dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (fn_CommDestroy)dlsym(h, "ncclCommDestroy");
+    g_nccl.GroupStart = (fn_Group)dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (fn_Group)dlsym(h, "ncclGroupEnd");
+    g_nccl.Send = (fn_Send)dlsym(h, "ncclSend");
+    g_nccl.Recv = (fn_Recv)dlsym(h, "ncclRecv");
+    g_nccl.AllReduce = (fn_AllReduce)dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (fn_GetErrorString)dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.Send || !g_nccl.Recv ||
+        !g_nccl.AllReduce) {
+        set_last_error("libnccl.so.2 lacks a required symbol");
+        return 1;
+    }
+    g_nccl.lib = h;
+    return 0;
+}
+int nccl_check(int r, const char* what) {
+    if (r == 0) return 0;
+    set_last_error(std::string(what) + " failed: " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"));
+    return 1;
+}
+#define CF_NCCL(expr) CF_TRY(nccl_check((expr), #expr))
+}  // namespace
+#endif
+
+int comm_unique_id(void* out128) {
+#ifdef CF_EMU
+    set_last_error("NCCL is unavailable in the emulation build");
+    return 1;
+#else
+    CF_TRY(nccl_load());
+    ncclUniqueId_t id;
+    CF_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, 128);
+    return 0;
+#endif
+}
+
+int comm_init_nccl(Comm& c, int rank, int nranks, const void* id128) {
+#ifdef CF_EMU
+    set_last_error("NCCL is unavailable in the emulation build");
+    return 1;
+#else
+    if (nranks < 1 || nranks > COMM_MAXRANKS || rank < 0 || rank >= nranks) {
+        set_last_error("comm_init: bad rank / world size");
+        return 1;
+    }
+    CF_TRY(nccl_load());
+    ncclUniqueId_t id;
+    memcpy(&id, id128, 128);
+    void* comm = nullptr;
+    CF_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    c.rank = rank; c.nranks = nranks; c.nccl_comm = comm;
+    return 0;
+#endif
+}
+
+int comm_destroy(Comm& c) {
+#ifndef CF_EMU
+    if (c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.nccl_comm);
+#endif
+    c.nccl_comm = nullptr;
+    return 0;
+}
+
+int comm_exchange(Comm& c, const ExchangeMsg* msgs, int nmsg, cudaStream_t stream) {
+    for (int i = 0; i < nmsg; ++i) {
+        if (msgs[i].peer == c.rank) {
+            if (msgs[i].sendbytes != msgs[i].recvbytes) {
+                set_last_error("comm_exchange: self message size mismatch");
+                return 1;
+            }
+            if (msgs[i].sendbytes > 0 && msgs[i].send != msgs[i].recv)
+                CF_CUDA(cudaMemcpyAsync(msgs[i].recv, msgs[i].send, (size_t)msgs[i].sendbytes, cudaMemcpyDeviceToDevice, stream));
+        }
+    }
+    if (c.nranks == 1) return 0;
+    if (c.ext_exchange) {
+        std::vector<int> peer;
+        std::vector<const void*> sp;
+        std::vector<void*> rp;
+        std::vector<long long> sb, rb;
+        for (int i = 0; i < nmsg; ++i) {
+            if (msgs[i].peer == c.rank) continue;
+            peer.push_back(msgs[i].peer);
+            sp.push_back(msgs[i].send); sb.push_back(msgs[i].sendbytes);
+            rp.push_back(msgs[i].recv); rb.push_back(msgs[i].recvbytes);
+        }
+        CF_CUDA(cudaStreamSynchronize(stream));
+        if (c.ext_exchange(c.ext_user, (int)peer.size(), peer.data(), sp.data(), sb.data(), rp.data(), rb.data()) != 0) {
+            set_last_error("comm_exchange: external exchange callback failed");
+            return 1;
+        }
+        return 0;
+    }
+#ifndef CF_EMU
+    if (!c.nccl_comm) {
+        set_last_error("comm_exchange: no communicator (call cfgpu_comm_init_nccl)");
+        return 1;
+    }
+    CF_NCCL(g_nccl.GroupStart());
+    for (int i = 0; i < nmsg; ++i) {
+        if (msgs[i].peer == c.rank) continue;
+        if (msgs[i].sendbytes > 0) CF_NCCL(g_nccl.Send(msgs[i].send, (size_t)msgs[i].sendbytes, NCCL_INT8, msgs[i].peer, c.nccl_comm, stream));
+        if (msgs[i].recvbytes > 0) CF_NCCL(g_nccl.Recv(msgs[i].recv, (size_t)msgs[i].recvbytes, NCCL_INT8, msgs[i].peer, c.nccl_comm, stream));
+    }
+    CF_NCCL(g_nccl.GroupEnd());
+    return 0;
+#else
+    set_last_error("comm_exchange: no exchange callback installed");
+    return 1;
+#endif
+}
+
+int comm_allreduce(Comm& c, double* dev, int n, int op, cudaStream_t stream) {
+    if (c.nranks == 1) return 0;
+    if (c.ext_allreduce) {
+        CF_CUDA(cudaStreamSynchronize(stream));
+        if (c.ext_allreduce(c.ext_user, dev, n, op) != 0) {
+            set_last_error("comm_allreduce: external callback failed");
+            return 1;
+        }
+        return 0;
+    }
+#ifndef CF_EMU
+    if (!c.nccl_comm) {
+        set_last_error("comm_allreduce: no communicator");
+        return 1;
+    }
+    CF_NCCL(g_nccl.AllReduce(dev, dev, (size_t)n, NCCL_FLOAT64, op == 1 ? NCCL_MAX : NCCL_SUM, c.nccl_comm, stream));
+    return 0;
+#else
+    set_last_error("comm_allreduce: no callback installed");
+    return 1;
+#endif
+}
+
+}  // namespace cfgpu

@@ -1,0 +1,51 @@
+// Multi-GPU plumbing of the slab decomposition (replaces CfMPI + the FFTW-MPI transposes of the reference:
+// cfmpi.cpp:66-127, flowfield.cpp:577-667 plans, the Mzloc/Nyloc transposes inside makePhysical/makeSpectral).
+//
+// One process per GPU.  Spectral state: the retained kx rows (mxi = 0..2Kx) are split into contiguous ranges, one per
+// rank (y and kz local => y-transform, tau solve, norms are local); physical state: the Ny Gauss-Lobatto planes are
+// split into contiguous ranges (x, z local => x/z FFT passes and the pointwise nonlinear term are local).  Between
+// the two there is exactly one personalised all-to-all per direction, issued as grouped ncclSend/ncclRecv on the
+// context's stream straight from/into the pencil buffers (no packing kernels: the pencil layouts are chosen so that
+// every message is one contiguous block).  NCCL is bound at run time (dlopen of the libnccl.so.2 already loaded by
+// torch, else the system one), so single-GPU use has no NCCL dependency.  For the CPU tests (gloo, world size 2) the
+// exchange and all-reduce can instead be supplied by the host through callbacks (the emulation build's "device"
+// pointers are host pointers).
+#pragma once
+#include "../../include/cfgpu.h"
+#include "cf_common.cuh"
+
+namespace cfgpu {
+
+constexpr int COMM_MAXRANKS = 16;
+
+struct Comm {
+    int rank = 0, nranks = 1;
+    void* nccl_comm = nullptr;
+    cfgpu_exchange_fn ext_exchange = nullptr;
+    cfgpu_allreduce_fn ext_allreduce = nullptr;
+    void* ext_user = nullptr;
+};
+
+// balanced contiguous split of n items: rank r owns [lo, hi)
+inline void part_range(int n, int nranks, int r, int& lo, int& hi) {
+    lo = (int)((long)n * r / nranks);
+    hi = (int)((long)n * (r + 1) / nranks);
+}
+
+struct ExchangeMsg {
+    int peer;
+    const void* send;
+    long long sendbytes;
+    void* recv;
+    long long recvbytes;
+};
+
+int comm_unique_id(void* out128);
+int comm_init_nccl(Comm& c, int rank, int nranks, const void* id128);
+int comm_destroy(Comm& c);
+// personalised exchange on `stream`; messages to self are device-to-device copies
+int comm_exchange(Comm& c, const ExchangeMsg* msgs, int nmsg, cudaStream_t stream);
+// in-place all-reduce of n doubles in device memory; op: 0 = sum, 1 = max
+int comm_allreduce(Comm& c, double* dev, int n, int op, cudaStream_t stream);
+
+}  // namespace cfgpu

@@ -73,7 +73,7 @@ __global__ void profile_add_kernel(double2* __restrict__ c, long off0, long rs, 
 constexpr int NRM_THREADS = 256;
 __global__ void __launch_bounds__(NRM_THREADS) l2form_kernel(const double* __restrict__ u, const double* __restrict__ v, int mode /*0 norm,1 dist,2 ip*/,
                                                              const double* __restrict__ W, int N, int Nx, int Mz, int Kx, int Kz, int fullbox,
-                                                             int nq, int TMn, long rs, long cs, double* __restrict__ partial) {
+                                                             int qlo, int nq, int TMn, long rs, long cs, double* __restrict__ partial) {
     const int TT = 2 * TMn;
     double* X = dyn_smem<double>();
     double* Y = (mode == 2) ? X + (size_t)N * TT : X;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NRM_THREADS) l2form_kernel(const double* __res
         const int q = q0 + m;
         double xv = 0.0, yv = 0.0;
         if (q < nq) {
-            const int mxi = q / nkz, kz = q - mxi * nkz;
+            const int mxi = (qlo + q) / nkz, kz = (qlo + q) - mxi * nkz;
             int mx = mxi;
             if (!fullbox) {
                 const int kx = mxi <= Kx ? mxi : mxi - (2 * Kx + 1);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(NRM_THREADS) l2form_kernel(const double* __res
         }
         const int q = q0 + (t >> 1);
         if (q < nq) {
-            const int kz = q % nkz;
+            const int kz = (qlo + q) % nkz;
             if (kz > 0) sum *= 2.0;
         } else sum = 0.0;
     }
@@ -181,10 +181,38 @@ int profile_add_launch(double* d, long off0_cplx, long rs_cplx, int Ny, const do
     return 0;
 }
 
+__global__ void __launch_bounds__(EW_THREADS) rows_pack_kernel(double2* __restrict__ field, double2* __restrict__ buf, int Nx, int Mz,
+                                                               int Kx, int nkz, int x0, int nloc, long total, int dir) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    const int nmx = 2 * Kx + 1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int kz = (int)(i % nkz);
+        const int xl = (int)((i / nkz) % nloc);
+        const long row = i / ((long)nkz * nloc);
+        const int mxi = x0 + xl;
+        const int kx = mxi <= Kx ? mxi : mxi - nmx;
+        const int mx = kx >= 0 ? kx : Nx + kx;
+        const long fo = (row * Nx + mx) * Mz + kz;
+        if (dir == 0) buf[i] = field[fo];
+        else field[fo] = buf[i];
+    }
+}
+
+int rows_pack_launch(double* field, double* buf, int Nx, int Nz, int nrows, int Kx, int Kz, int x0, int x1, int dir, cudaStream_t st) {
+    const long total = (long)nrows * (x1 - x0) * (Kz + 1);
+    if (total <= 0) return 0;
+    CF_LAUNCH(rows_pack_kernel, dim3(grid_for(total)), dim3(EW_THREADS), 0, st, reinterpret_cast<double2*>(field),
+              reinterpret_cast<double2*>(buf), Nx, Nz / 2 + 1, Kx, Kz + 1, x0, x1 - x0, total, dir);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
 int l2form_launch(const double* u, const double* v, int mode, const double* W, int N, int Nx, int Nz, int Nd, int Kx, int Kz, int fullbox,
-                  double scale, double* partial_dev, size_t partial_cap, double* out_dev, cudaStream_t st) {
+                  int x0, int x1, double scale, double* partial_dev, size_t partial_cap, double* out_dev, cudaStream_t st) {
     const int Mz = Nz / 2 + 1;
-    const int nq = fullbox ? Nx * Mz : (2 * Kx + 1) * (Kz + 1);
+    const int nkz_ = fullbox ? Mz : Kz + 1;
+    const int qlo = x0 * nkz_;
+    const int nq = (x1 - x0) * nkz_;
     const int narr = mode == 2 ? 2 : 1;
     int TMn = 16;
     while (TMn > 1 && (size_t)N * 2 * TMn * narr * sizeof(double) > 160 * 1024) TMn >>= 1;
@@ -202,7 +230,7 @@ int l2form_launch(const double* u, const double* v, int mode, const double* W, i
         return 1;
     }
     const long rs = (long)Nx * 2 * Mz, cs = rs * N;
-    CF_LAUNCH(kfn, grid, dim3(NRM_THREADS), smem, st, u, v, mode, W, N, Nx, Mz, Kx, Kz, fullbox, nq, TMn, rs, cs, partial_dev);
+    CF_LAUNCH(kfn, grid, dim3(NRM_THREADS), smem, st, u, v, mode, W, N, Nx, Mz, Kx, Kz, fullbox, qlo, nq, TMn, rs, cs, partial_dev);
     CF_KERNEL_CHECK();
     CF_LAUNCH(sum_partials_kernel, dim3(1), dim3(256), 0, st, (const double*)partial_dev, nparts, scale, out_dev);
     CF_KERNEL_CHECK();

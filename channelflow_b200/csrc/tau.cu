@@ -103,17 +103,17 @@ __device__ __forceinline__ void dudy_at_walls(const double* u, int N, int TT, in
 
 __device__ __forceinline__ void mode_of_q(int q, const ModeGeom& g, int& kx, int& kz, long& off) {
     const int nkz = g.Kz + 1, nmx = 2 * g.Kx + 1;
-    const int mxi = q / nkz;
-    kz = q - mxi * nkz;
+    const int ml = q / nkz, mxi = g.mx0 + ml;
+    kz = q - ml * nkz;
     kx = mxi <= g.Kx ? mxi : mxi - nmx;
     const int mx = kx >= 0 ? kx : g.Nx + kx;
     off = 2L * (kz + (long)(g.Nz / 2 + 1) * mx);
 }
 
 // first mode of a tile and number of valid modes in it
-__device__ __forceinline__ void tile_modes(int tl, int TM, int nq, int& q0, int& nvalid) {
-    if (tl == 0) { q0 = 0; nvalid = 1; return; }
-    q0 = 1 + (tl - 1) * TM;
+__device__ __forceinline__ void tile_modes(int tl, int TM, int nq, int has00, int& q0, int& nvalid) {
+    if (tl == 0) { q0 = 0; nvalid = has00 ? 1 : 0; return; }
+    q0 = has00 + (tl - 1) * TM;
     nvalid = nq - q0 < TM ? nq - q0 : TM;
 }
 
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_setup_kernel(const TauD
     const int tid = threadIdx.x, NT = TAU_SETUP_THREADS;
     const int tl = blockIdx.x;
     int q0, nvalid;
-    tile_modes(tl, TM, td.nq, q0, nvalid);
+    tile_modes(tl, TM, td.nq, td.has00, q0, nvalid);
     double* A1 = dyn_smem<double>();
     double* A2 = A1 + (size_t)N * TM;
     double* A3 = A2 + (size_t)N * TM;
@@ -545,7 +545,8 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
     double* s_w = s_sc + TSC_COUNT * TM;         // [8][TT]
     long* s_off = reinterpret_cast<long*>(s_w + 8 * TT);  // [TM]
     int q0, nvalid;
-    tile_modes(tl, TM, td.nq, q0, nvalid);
+    tile_modes(tl, TM, td.nq, td.has00, q0, nvalid);
+    if (nvalid <= 0) return;  // tile 0 on a rank that does not own the (0,0) mode
 
     if (tid < TM) {
         long off = -1;
@@ -887,7 +888,7 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) linear_kernel(const TauSolv
         __syncthreads();
         for (int c = tid; c < 2 * TT; c += NT) diff_chain(X, T, N, TT, c % TT, c / TT, scale, nullptr);
         __syncthreads();
-        if (blockIdx.x == 0 && p.constraint == 1 && comp != 1 && tid == 0) {
+        if (td.has00 && blockIdx.x == 0 && p.constraint == 1 && comp != 1 && tid == 0) {
             // wall shear of nu*u for the (0,0) mode, real part (t = 0): eval_b - eval_a of d(nu u)/dy
             double sb = 0.0, sa = 0.0;
             for (int n = N - 1; n >= 0; --n) { sb += T[n * TT]; sa += T[n * TT] * ((n % 2 == 0) ? 1 : -1); }
@@ -907,7 +908,7 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) linear_kernel(const TauSolv
                 g = (t & 1) ? k * Pk[idx - 1] : -k * Pk[idx + 1];
             }
             double v = R[idx] - kap2 * X[idx] - g;
-            if (q0 + m == 0 && (t & 1) == 0) {
+            if (td.has00 && q0 + m == 0 && (t & 1) == 0) {
                 if (comp == 0 && p.Ubaseyy) v += td.nu * p.Ubaseyy[n];
                 if (comp == 2 && p.Wbaseyy) v += td.nu * p.Wbaseyy[n];
                 if (n == 0 && comp != 1) {

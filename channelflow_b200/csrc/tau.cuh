@@ -23,7 +23,8 @@ enum { TAR_UPP = 0, TAR_INVP, TAR_BANDP, TAR_UPV, TAR_INVV, TAR_BANDV, TAR_PP, T
 
 struct TauData {
     int N;       // number of Chebyshev modes in the solve (Nyd)
-    int nq;      // retained modes, q = mxi*(Kz+1) + kz ; q = 0 is the (0,0) mode
+    int nq;      // retained modes of this rank, q = (mxi - mx0)*(Kz+1) + kz ; with has00, q = 0 is the (0,0) mode
+    int has00;   // this rank owns kx row 0 (always true on a single GPU)
     int TM;      // modes per tile
     int ntiles;  // 1 + ceil((nq-1)/TM)
     double nu, a, b;
@@ -33,11 +34,14 @@ struct TauData {
     __host__ __device__ double* tile_arr(int tl, int which) const { return tile(tl) + (size_t)which * N * TM; }   // [n][TM]
     __host__ __device__ double* tile_sc(int tl, int which) const { return tile(tl) + (size_t)TAR_COUNT * N * TM + (size_t)which * TM; }
     __host__ __device__ double* btab() const { return base + (size_t)ntiles * tile_doubles(); }  // [3][N]: B_lo, B_dg, B_up
-    __host__ __device__ static int tile_of(int q, int TM) { return q == 0 ? 0 : 1 + (q - 1) / TM; }
-    __host__ __device__ static int pos_of(int q, int TM) { return q == 0 ? 0 : (q - 1) % TM; }
-    __host__ __device__ double& scq(int which, int q) const { return tile_sc(tile_of(q, TM), which)[pos_of(q, TM)]; }
-    static int num_tiles(int nq, int TM) { return 1 + (nq - 1 + TM - 1) / TM; }
-    static size_t doubles(int N, int nq, int TM) { return (size_t)num_tiles(nq, TM) * (TAR_COUNT * N + TSC_COUNT) * TM + 3 * (size_t)N; }
+    // tile 0 is reserved for the (0,0) mode (empty on ranks that do not own it); general modes start at q = has00
+    __host__ __device__ int tile_of(int q) const { return (has00 && q == 0) ? 0 : 1 + (q - has00) / TM; }
+    __host__ __device__ int pos_of(int q) const { return (has00 && q == 0) ? 0 : (q - has00) % TM; }
+    __host__ __device__ double& scq(int which, int q) const { return tile_sc(tile_of(q), which)[pos_of(q)]; }
+    static int num_tiles(int nq, int TM, int has00) { return 1 + (nq - has00 + TM - 1) / TM; }
+    static size_t doubles(int N, int nq, int TM, int has00) {
+        return (size_t)num_tiles(nq, TM, has00) * (TAR_COUNT * N + TSC_COUNT) * TM + 3 * (size_t)N;
+    }
 };
 
 // pitch (doubles) of a skewed shared-memory column of the solve kernel: addr(n) = n + n/E, made odd so that the
@@ -46,6 +50,7 @@ __host__ __device__ inline int tau_col_pitch(int N, int E) { return ((N - 1) + (
 
 struct ModeGeom {
     int Nx, Ny, Nz, Kx, Kz;  // field grid and retained box
+    int mx0;                 // first kx row (mxi) owned by this rank
     double Lx, Lz;
 };
 

@@ -25,14 +25,14 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassPa
     // zero the aliased rows Kx+1 .. Nx-Kx-1
     const int nzero = (Nx - nmx) * TZ;
     for (int idx = tid; idx < nzero; idx += XZ_THREADS) a[(Kx + 1) * TZ + idx] = make_double2(0.0, 0.0);
-    const double2* __restrict__ in = p.in + ((size_t)s * p.nyn + yl) * nmx * nkz;
+    const double2* __restrict__ in = p.in;
     for (int idx = tid; idx < nmx * TZ; idx += XZ_THREADS) {
         const int mxi = idx / TZ, c = idx - mxi * TZ;
         const int kz = kz0 + c;
         const int kx = mxi <= Kx ? mxi : mxi - nmx;
         const int mx = kx >= 0 ? kx : Nx + kx;
         double2 v = make_double2(0.0, 0.0);
-        if (kz < nkz) v = in[(size_t)mxi * nkz + kz];
+        if (kz < nkz) v = in[xpass_row_offset(p, s, yl, mxi, nkz) + kz];
         if (ddx) {
             const double k = TWO_PI * kx / p.Lx;
             v = make_double2(-k * v.y, k * v.x);
@@ -66,13 +66,13 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_forward_kernel(const XPassPa
     }
     __syncthreads();
     const double2* res = fft_smem<-1>(a, b, p.plan, TZ, tid, XZ_THREADS);
-    double2* __restrict__ out = p.out + ((size_t)f * p.nyn + yl) * nmx * nkz;
+    double2* __restrict__ out = p.out;
     for (int idx = tid; idx < nmx * TZ; idx += XZ_THREADS) {
         const int mxi = idx / TZ, c = idx - mxi * TZ;
         const int kz = kz0 + c;
         const int kx = mxi <= Kx ? mxi : mxi - nmx;
         const int mx = kx >= 0 ? kx : Nx + kx;
-        if (kz < nkz) out[(size_t)mxi * nkz + kz] = res[mx * TZ + c];
+        if (kz < nkz) out[xpass_row_offset(p, f, yl, mxi, nkz) + kz] = res[mx * TZ + c];
     }
 }
 

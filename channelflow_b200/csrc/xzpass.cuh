@@ -25,7 +25,19 @@ struct XPassParams {
     const double2* in;    // inverse: P (field stride Ny*nmx*nkz); forward: Q (field stride Ny*Nx*nkz)
     double2* out;         // inverse: Q ; forward: P
     int ny0, nyn;         // y range handled (physical slab)
+    // P-side layout: blocks by owner rank s of the kx rows, [s][field][yl][mxi - xsplit[s]][kz] (the all-to-all staging
+    // of the slab decomposition, comm.cuh); with one rank this is plain P[field][yl][mxi][kz]
+    int nranks;
+    int nstage;           // number of fields in the staging buffer
+    int xsplit[17];       // xsplit[s] .. xsplit[s+1] = kx rows of rank s
 };
+// offset (complex elements) of row (field f, plane yl, mxi) in the staged P-side layout
+__host__ __device__ inline size_t xpass_row_offset(const XPassParams& p, int f, int yl, int mxi, int nkz) {
+    int s = 0;
+    while (s + 1 < p.nranks && mxi >= p.xsplit[s + 1]) ++s;
+    const int x0 = p.xsplit[s], nloc = p.xsplit[s + 1] - x0;
+    return (size_t)nkz * ((size_t)p.nstage * p.nyn * x0 + ((size_t)f * p.nyn + yl) * nloc + (mxi - x0));
+}
 int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream);
 int xpass_forward_launch(const XPassParams& p, cudaStream_t stream);
 

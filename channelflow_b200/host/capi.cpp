@@ -139,6 +139,21 @@ double cf_dns_time(void* h) { return ((CfDNS*)h)->dns->time(); }
 double cf_dns_dPdx(void* h) { return ((CfDNS*)h)->dns->dPdx(); }
 double cf_dns_Ubulk(void* h) { return ((CfDNS*)h)->dns->Ubulk(); }
 void cf_sync() { cfgpu_sync(cfgpu_context()); }
+// ---- multi-GPU plumbing (one process per GPU; the launcher distributes the NCCL id)
+int cf_comm_unique_id(void* id128) { return cfgpu_comm_unique_id(id128); }
+void cf_comm_init_nccl(int rank, int nranks, const void* id128) {
+    cfgpu_check(cfgpu_comm_init_nccl(cfgpu_context(), rank, nranks, id128), "cfgpu_comm_init_nccl");
+}
+void cf_comm_init_external(int rank, int nranks, cfgpu_exchange_fn ex, cfgpu_allreduce_fn ar) {
+    cfgpu_check(cfgpu_comm_init_external(cfgpu_context(), rank, nranks, ex, ar, nullptr), "cfgpu_comm_init_external");
+}
+void cf_comm_ranges(int nmx, int Ny, int rank, int* r4) {
+    cfgpu_check(cfgpu_comm_ranges(cfgpu_context(), nmx, Ny, rank, r4, r4 + 1, r4 + 2, r4 + 3), "cfgpu_comm_ranges");
+}
+void cf_field_allgather(void* uh) {
+    FlowField& u = *(FlowField*)uh;
+    cfgpu_check(cfgpu_field_allgather(u.device_mut()), "cfgpu_field_allgather");
+}
 long long cf_launch_count() {
     long long n = 0;
     cfgpu_launch_count(cfgpu_context(), &n);

@@ -39,14 +39,32 @@ int cfgpu_timer_start(cfgpu_ctx ctx);
 int cfgpu_timer_stop(cfgpu_ctx ctx, double* ms);
 /* per-stage device timing of the DNS pipeline (CUDA events on the launching stream, accumulated per stage):
  * stages: 0 inverse y-GEMM, 1 inverse x-pass, 2 z-pass+nonlinear, 3 forward x-pass, 4 forward y-GEMM,
- *         5 tau solve (+fused RHS), 6 linear term, 7 tau setup */
-#define CFGPU_NSTAGES 8
+ *         5 tau solve (+fused RHS), 6 linear term, 7 tau setup, 8 slab all-to-all (multi-GPU) */
+#define CFGPU_NSTAGES 9
 int cfgpu_profile_enable(cfgpu_ctx ctx, int on);
 int cfgpu_profile_read(cfgpu_ctx ctx, double* ms_h /* [CFGPU_NSTAGES] */, long long* calls_h /* [CFGPU_NSTAGES] */, int reset);
 /* CUDA-graph capture of a sequence of calls on the context's stream (launch-bound small grids) */
 int cfgpu_graph_begin(cfgpu_ctx ctx);
 int cfgpu_graph_end(cfgpu_ctx ctx, int* graph_id);
 int cfgpu_graph_launch(cfgpu_ctx ctx, int graph_id);
+
+/* ---------------------------------------------------------------- multi-GPU (one process per GPU)
+ * replaces CfMPI (cfmpi.cpp:66-127) and the FFTW-MPI transposes inside makePhysical/makeSpectral (flowfield.cpp:577-667,
+ * 1850-1997): slab decomposition, kx rows distributed in the spectral state and y planes in the physical state, one
+ * all-to-all per direction inside cfgpu_nse_nonlinear / cfgpu_nse_cflfactor, all-reduce inside norms and CFL.
+ * Fields keep the full (serial) shape on every rank; a rank owns -- and keeps valid -- the kx rows of its range. */
+int cfgpu_comm_unique_id(void* id128_h /* 128 bytes, from rank 0, to be broadcast by the launcher */);
+int cfgpu_comm_init_nccl(cfgpu_ctx ctx, int rank, int nranks, const void* id128_h);
+/* host-supplied collectives (CPU tests of the decomposition logic: gloo); pointers are the library's device pointers */
+typedef int (*cfgpu_exchange_fn)(void* user, int nmsg, const int* peer, const void* const* sendbuf, const long long* sendbytes,
+                                 void* const* recvbuf, const long long* recvbytes);
+typedef int (*cfgpu_allreduce_fn)(void* user, double* buf, int n, int op /* 0 sum, 1 max */);
+int cfgpu_comm_init_external(cfgpu_ctx ctx, int rank, int nranks, cfgpu_exchange_fn ex, cfgpu_allreduce_fn ar, void* user);
+int cfgpu_comm_rank(cfgpu_ctx ctx, int* rank, int* nranks);
+/* owned ranges: retained kx rows mxi in [x0,x1) of 2Kx+1 (kx = 0..Kx, -Kx..-1) and y planes [y0,y1) */
+int cfgpu_comm_ranges(cfgpu_ctx ctx, int nmx, int Ny, int rank, int* x0, int* x1, int* y0, int* y1);
+/* make every rank's copy of a spectral, de-aliased field complete (all-gather of the owned kx rows): I/O, tests */
+int cfgpu_field_allgather(cfgpu_field f);
 
 /* ---------------------------------------------------------------- FlowField storage
  * FlowField ctor/resize/copy/assign/swap/setToZero (flowfield.cpp:466-575, 96-102, 452-460, 4076-4090, 2229-2233) */
