@@ -30,11 +30,12 @@ WORKLOADS = {
     # BASELINE.json configs; Lx, Lz as in SURVEY.md 8(d)
     "c4": dict(Nx=512, Ny=257, Nz=512, Lx=4 * np.pi, Lz=2 * np.pi, nu=1.0 / 4000, dt=0.002, desc="turbulent-channel grid 512x257x512"),
     "c5": dict(Nx=256, Ny=129, Nz=256, Lx=4 * np.pi, Lz=2 * np.pi, nu=1.0 / 1000, dt=0.005, desc="256x129x256"),
-    "c2": dict(Nx=128, Ny=97, Nz=128, Lx=2 * np.pi, Lz=np.pi, nu=1.0 / 1800, dt=0.01, desc="128x97x128"),
+    "c2": dict(Nx=128, Ny=97, Nz=128, Lx=2 * np.pi, Lz=np.pi, nu=1.0 / 1800, dt=0.01, desc="plane Poiseuille fixed flux 128x97x128",
+               flags=dict(ulowerwall=0.0, uupperwall=0.0, constraint="bulkv", Ubulk=2.0 / 3, nonlinearity="skew")),
     "c1": dict(Nx=32, Ny=33, Nz=32, Lx=2 * np.pi, Lz=np.pi, nu=1.0 / 400, dt=0.02, desc="plane Couette 32x33x32"),
     "golden": dict(Nx=48, Ny=35, Nz=48, Lx=2 * np.pi / 1.14, Lz=2 * np.pi / 2.5, nu=1.0 / 400, dt=0.025, desc="48x35x48"),
 }
-STAGES = ["inv_y_gemm", "inv_x_pass", "z_pass_nl", "fwd_x_pass", "fwd_y_gemm", "tau_solve", "linear", "tau_setup"]
+STAGES = ["inv_y_gemm", "inv_x_pass", "z_pass_nl", "fwd_x_pass", "fwd_y_gemm", "tau_solve", "linear", "tau_setup", "slab_alltoall"]
 # algorithmic bytes per stage in units of W (rotational SBDF-k with k=3)
 STAGE_W = {"inv_y_gemm": 3 + 5, "inv_x_pass": 5 + 7, "z_pass_nl": 7 + 3, "fwd_x_pass": 3 + 3, "fwd_y_gemm": 3 + 3, "tau_solve": 15 + 4}
 
@@ -69,8 +70,10 @@ def synthetic_field(w, seed=1, magn=0.1):
 
 
 def flags_kw(w):
-    return dict(nu=w["nu"], dt=w["dt"], ulowerwall=-1.0, uupperwall=1.0, baseflow="laminar", constraint="gradp",
-                timestepping="sbdf3", initstepping="smrk2", nonlinearity="rot", dealiasing="xz")
+    kw = dict(nu=w["nu"], dt=w["dt"], ulowerwall=-1.0, uupperwall=1.0, baseflow="laminar", constraint="gradp",
+              timestepping="sbdf3", initstepping="smrk2", nonlinearity="rot", dealiasing="xz")
+    kw.update(w.get("flags", {}))
+    return kw
 
 
 class ClockSampler(threading.Thread):
@@ -142,7 +145,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     gp = w["Nx"] * w["Ny"] * w["Nz"]
     Wbytes = 8 * w["Nx"] * w["Ny"] * 2 * (w["Nz"] // 2 + 1)
-    config = {"workload": "%s: SBDF3, rotational NL, 2/3 dealiasing, FP64, dt=%g" % (w["desc"], w["dt"]), "grid": [w["Nx"], w["Ny"], w["Nz"]],
+    nlname = {"rot": "rotational", "skew": "skew-symmetric"}.get(flags_kw(w)["nonlinearity"], flags_kw(w)["nonlinearity"])
+    config = {"workload": "%s: SBDF3, %s NL, 2/3 dealiasing, FP64, dt=%g" % (w["desc"], nlname, w["dt"]), "grid": [w["Nx"], w["Ny"], w["Nz"]],
               "l2": "working set (>= 34 W = %.1f MB) %s the 126 MB L2" % (34 * Wbytes / 1e6, "exceeds" if 34 * Wbytes > 126e6 else "fits in")}
 
     if args.impl == "reference":
@@ -163,17 +167,41 @@ def main():
 
     import torch
     import channelflow_b200 as cf
-    if world > 1:
-        raise SystemExit("multi-GPU slab decomposition is not wired into bench.py yet (see DESIGN.md)")
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("CFGPU_DEVICE", str(dev))
     lib = cf.HostLib()
+    dist = None
+    if world > 1:
+        # one process per GPU: torch.distributed (NCCL) is the plumbing (id broadcast, barriers, max over ranks); the
+        # data path's all-to-all / all-reduce are issued by libcfgpu.so on its own NCCL communicator
+        import torch.distributed as dist
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(lib.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        lib.comm_init_nccl(rank, world, bytes(idt.cpu().numpy().tobytes()))
+        config["parallelism"] = "kx-slab (spectral) / y-slab (physical) over %d GPUs, NCCL all-to-all" % world
+
+    def barrier():
+        lib.sync()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
     u0 = synthetic_field(w)
     ug = cf.FlowField(lib, w["Nx"], w["Ny"], w["Nz"], 3, w["Lx"], w["Lz"]).set(u0, padded=True)
     dns = cf.DNS(ug, cf.make_flags(**flags_kw(w)))
     dns.advance(2)            # SMRK2 initialisation steps of SBDF3 (not part of the metric)
     dns.advance(args.warmup)
-    lib.sync()
+    barrier()
 
     sampler = ClockSampler(dev)
     sampler.start()
@@ -183,6 +211,8 @@ def main():
     lib.timer_start()
     dns.advance(args.steps)
     ms_total = lib.timer_stop()
+    barrier()
+    ms_total = max_over_ranks(ms_total)
     stage_ms, stage_calls = lib.profile_read(reset=True)
     lib.profile_enable(False)
     launches = lib.launch_count() - l0
@@ -201,7 +231,11 @@ def main():
         ke = max(2, min(args.steps, 5))
         import ctypes as C
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
-        lib.sync()
+        n_box = n  # bytes that actually cross PCIe: de-aliased spectral fields travel as their retained box (own kx rows)
+        Kx_, Kz_ = w["Nx"] // 3 - 1, w["Nz"] // 3 - 1
+        x0_, x1_, _, _ = lib.comm_ranges(2 * Kx_ + 1, w["Ny"], rank)
+        n_box = 3 * w["Ny"] * (x1_ - x0_) * (Kz_ + 1) * 2
+        barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
             lib.L.cf_field_upload(cur.h, dp(hin))      # H2D of this step's input (pinned)
@@ -210,10 +244,11 @@ def main():
             lib.L.cf_dns_get(dns.h, cur.h, None)
             lib.L.cf_field_download(cur.h, dp(hout))   # D2H of this step's result
             hin, hout = hout, hin
-        lib.sync()
-        ems = 1e3 * (time.perf_counter() - t0) / ke
-        e2e = {"value": gp / (ems * 1e-3), "unit": "grid-pt-steps/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-               "ms_per_step": ems, "steps": ke}
+        barrier()
+        ems = max_over_ranks(1e3 * (time.perf_counter() - t0) / ke)
+        e2e = {"value": gp / (ems * 1e-3), "unit": "grid-pt-steps/s", "h2d_bytes_per_step": 8 * n_box, "d2h_bytes_per_step": 8 * n_box,
+               "ms_per_step": ems, "steps": ke,
+               "note": "per rank; the host FlowField arrays are full size, only the retained (de-aliased) modes of the rank's kx rows cross PCIe"}
     clocks = sampler.result()
 
     # ---- roofline of the dominant stage
@@ -229,17 +264,27 @@ def main():
             per = t / args.steps
             stages[name] = {"ms_per_step": per, "calls_per_step": c / args.steps}
             if name in STAGE_W:
-                stages[name]["algorithmic_GBps"] = STAGE_W[name] * Wbytes / (per * 1e-3) / 1e9
+                stages[name]["algorithmic_GBps"] = STAGE_W[name] * Wbytes / world / (per * 1e-3) / 1e9  # this rank's share
     dom = max((k for k in stages if k in STAGE_W), key=lambda k: stages[k]["ms_per_step"])
     ach = stages[dom]["algorithmic_GBps"]
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if world == 1:
+            traffic = tr.get(args.workload, {}).get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "whole_step_algorithmic_GBps": 61 * Wbytes / (ms * 1e-3) / 1e9, "whole_step_frac": 61 * Wbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "whole_step_algorithmic_GBps_per_gpu": 61 * Wbytes / world / (ms * 1e-3) / 1e9,
+                "whole_step_frac": 61 * Wbytes / world / (ms * 1e-3) / 1e9 / hbm_peak,
                 "y_gemm_TFLOPs": (8 * 2 * w["Ny"] * ((w["Ny"] + 1) // 2) * 2 * (w["Nx"] // 3 * 2 - 1) * (w["Nz"] // 3) * 2) /
                 ((stages.get("inv_y_gemm", {}).get("ms_per_step", 0) + stages.get("fwd_y_gemm", {}).get("ms_per_step", 0)) * 1e-3 + 1e-30) / 1e12}
 
+    if rank != 0:
+        return
     cpu_baseline = None
-    if not args.no_cpu_baseline and rank == 0:
+    if not args.no_cpu_baseline and world == 1:
         ws = sample_grid(w)
         cms = reference_steps(ws, 2, 0)
         cval = ws["Nx"] * ws["Ny"] * ws["Nz"] / (cms * 1e-3)

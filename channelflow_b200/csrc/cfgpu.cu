@@ -451,6 +451,51 @@ int cfgpu_field_download(cfgpu_field f, double* h) {
     CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
     return 0;
 }
+// pitched copies of the retained box (rows of this rank) between a host array and the device field, both in the
+// reference layout [i][my][mx][mz] complex
+static int box_copy(cfgpu_field f, double* h, bool to_device) {
+    cfgpu_ctx ctx = f->ctx;
+    const int Kx = f->Nx / 3 - 1, Kz = f->Nz / 3 - 1, nmx = 2 * Kx + 1;
+    int x0 = 0, x1 = nmx;
+    if (ctx->comm.nranks > 1) part_range(nmx, ctx->comm.nranks, ctx->comm.rank, x0, x1);
+    const size_t pitch = (size_t)f->Mz() * 16;
+    for (int part = 0; part < 2; ++part) {
+        // part 0: kx >= 0 (mxi = mx <= Kx); part 1: kx < 0 (mxi > Kx, mx = Nx - nmx + mxi)
+        const int a = part == 0 ? x0 : (x0 > Kx + 1 ? x0 : Kx + 1);
+        const int b = part == 0 ? (x1 < Kx + 1 ? x1 : Kx + 1) : x1;
+        if (b <= a) continue;
+        const int mx0 = part == 0 ? a : f->Nx - nmx + a;
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof p);
+        cudaPitchedPtr hp = make_cudaPitchedPtr((void*)h, pitch, pitch, (size_t)f->Nx);
+        cudaPitchedPtr dp = make_cudaPitchedPtr((void*)f->d, pitch, pitch, (size_t)f->Nx);
+        p.srcPtr = to_device ? hp : dp;
+        p.dstPtr = to_device ? dp : hp;
+        p.srcPos = make_cudaPos(0, (size_t)mx0, 0);
+        p.dstPos = p.srcPos;
+        p.extent = make_cudaExtent((size_t)(Kz + 1) * 16, (size_t)(b - a), (size_t)f->Nd * f->Ny);
+        p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        CF_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    }
+    return 0;
+}
+int cfgpu_field_upload_padded(cfgpu_field f, const double* h, int ystate) {
+    const int Kx = f->Nx / 3 - 1, Kz = f->Nz / 3 - 1;
+    CF_ARG(Kx >= 0 && Kz >= 0, "cfgpu_field_upload_padded: grid too small");
+    if (!(f->clean_Kx >= 0 && f->clean_Kx <= Kx && f->clean_Kz >= 0 && f->clean_Kz <= Kz))
+        CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), f->ctx->stream));
+    CF_TRY(box_copy(f, const_cast<double*>(h), true));
+    CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    f->xzstate = CFGPU_SPECTRAL; f->ystate = ystate; f->padded = 1;
+    f->clean_Kx = Kx; f->clean_Kz = Kz;
+    return 0;
+}
+int cfgpu_field_download_padded(cfgpu_field f, double* h) {
+    CF_ARG(f->xzstate == CFGPU_SPECTRAL, "cfgpu_field_download_padded: field must be xz-spectral");
+    CF_TRY(box_copy(f, h, false));
+    CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return 0;
+}
 static bool same_shape(cfgpu_field a, cfgpu_field b) {
     return a->Nx == b->Nx && a->Ny == b->Ny && a->Nz == b->Nz && a->Nd == b->Nd;
 }

@@ -156,6 +156,8 @@ class FlowField {
     bool padded() const { return padded_; }
 
     // ---- device side (used by NSE / diffops; not part of the reference API)
+    bool box_ok() const;
+    void upload_from(const Real* data) const;
     cfgpu_field device() const;          // device copy is current on return; host mirror stays valid
     cfgpu_field device_mut();            // as above, and the host mirror is invalidated
     void raw_upload(const Real* data);   // whole array, reference layout

@@ -86,7 +86,8 @@ void FlowField::push_state() const {
 void FlowField::host_sync() const {
     if (host_valid_) return;
     host_.resize((size_t)Nloc());
-    CK(cfgpu_field_download(dev_, host_.data()));
+    if (padded_ && xzstate_ == Spectral && box_ok()) CK(cfgpu_field_download_padded(dev_, host_.data()));
+    else CK(cfgpu_field_download(dev_, host_.data()));
     host_valid_ = true;
 }
 void FlowField::host_dirty() {
@@ -96,7 +97,7 @@ void FlowField::host_dirty() {
 cfgpu_field FlowField::device() const {
     if (!dev_) cferror("FlowField: operation on an empty field");
     if (!dev_valid_) {
-        CK(cfgpu_field_upload(dev_, host_.data(), xzstate_ == Spectral, ystate_ == Spectral));
+        upload_from(host_.data());
         dev_valid_ = true;
     }
     push_state();
@@ -107,12 +108,22 @@ cfgpu_field FlowField::device_mut() {
     host_valid_ = false;
     return d;
 }
+// de-aliased spectral fields travel as their retained box only (include/cfgpu.h: cfgpu_field_upload_padded)
+bool FlowField::box_ok() const { return Nx_ / 3 - 1 >= 0 && Nz_ / 3 - 1 >= 0; }
+void FlowField::upload_from(const Real* data) const {
+    if (padded_ && xzstate_ == Spectral && box_ok()) CK(cfgpu_field_upload_padded(dev_, data, ystate_ == Spectral));
+    else CK(cfgpu_field_upload(dev_, data, xzstate_ == Spectral, ystate_ == Spectral));
+}
 void FlowField::raw_upload(const Real* data) {
-    CK(cfgpu_field_upload(dev_, data, xzstate_ == Spectral, ystate_ == Spectral));
+    upload_from(data);
     dev_valid_ = true;
     host_valid_ = false;
 }
-void FlowField::raw_download(Real* data) const { CK(cfgpu_field_download(device(), data)); }
+void FlowField::raw_download(Real* data) const {
+    cfgpu_field d = device();
+    if (padded_ && xzstate_ == Spectral && box_ok()) CK(cfgpu_field_download_padded(d, data));
+    else CK(cfgpu_field_download(d, data));
+}
 
 Real& FlowField::operator()(int nx, int ny, int nz, int i) {
     assert(xzstate_ == Physical);

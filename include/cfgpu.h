@@ -73,6 +73,11 @@ int cfgpu_field_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, int Nd, double Lx,
 int cfgpu_field_destroy(cfgpu_field f);
 int cfgpu_field_upload(cfgpu_field f, const double* data_h, int xzstate, int ystate);
 int cfgpu_field_download(cfgpu_field f, double* data_h);
+/* Same for an xz-spectral, de-aliased ("padded", flowfield.h:578-584) field: only the retained box |kx| <= Nx/3-1,
+ * kz <= Nz/3-1 travels (44 % of the array; two pitched 3-D copies), the rest of the device field is zero / the rest of
+ * the host array is left untouched.  With several GPUs only the rank's own kx rows travel. */
+int cfgpu_field_upload_padded(cfgpu_field f, const double* data_h, int ystate);
+int cfgpu_field_download_padded(cfgpu_field f, double* data_h);
 int cfgpu_field_copy(cfgpu_field dst, cfgpu_field src);
 int cfgpu_field_swap(cfgpu_field a, cfgpu_field b);
 int cfgpu_field_zero(cfgpu_field f);

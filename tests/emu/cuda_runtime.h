@@ -125,6 +125,22 @@ template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { r
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memmove(d, s, n); return cudaSuccess; }
+struct cudaPitchedPtr { void* ptr; size_t pitch, xsize, ysize; };
+struct cudaPos { size_t x, y, z; };
+struct cudaExtent { size_t width, height, depth; };
+struct cudaMemcpy3DParms { cudaPitchedPtr srcPtr, dstPtr; cudaPos srcPos, dstPos; cudaExtent extent; cudaMemcpyKind kind; };
+static inline cudaPitchedPtr make_cudaPitchedPtr(void* p, size_t pitch, size_t xs, size_t ys) { cudaPitchedPtr r = {p, pitch, xs, ys}; return r; }
+static inline cudaPos make_cudaPos(size_t x, size_t y, size_t z) { cudaPos r = {x, y, z}; return r; }
+static inline cudaExtent make_cudaExtent(size_t w, size_t h, size_t d) { cudaExtent r = {w, h, d}; return r; }
+static inline cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms* p, cudaStream_t = 0) {
+    for (size_t z = 0; z < p->extent.depth; ++z)
+        for (size_t y = 0; y < p->extent.height; ++y) {
+            const char* s = (const char*)p->srcPtr.ptr + ((p->srcPos.z + z) * p->srcPtr.ysize + p->srcPos.y + y) * p->srcPtr.pitch + p->srcPos.x;
+            char* d = (char*)p->dstPtr.ptr + ((p->dstPos.z + z) * p->dstPtr.ysize + p->dstPos.y + y) * p->dstPtr.pitch + p->dstPos.x;
+            memmove(d, s, p->extent.width);
+        }
+    return cudaSuccess;
+}
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = 1; return cudaSuccess; }

@@ -63,6 +63,7 @@ def main():
     rows = [(m if m <= Kx else m - (2 * Kx + 1)) % cfg["Nx"] for m in range(x0, x1)]
     out["own_rows"] = float(np.abs(mine[:, :, rows, :Kz + 1] - ref[:, :, rows, :Kz + 1]).max() / np.abs(ref).max())
     u2.allgather()
+    u2.set_padded(False)  # full download (a padded download only fetches this rank's rows)
     full = u2.get().view(np.complex128)
     allrows = [(m if m <= Kx else m - (2 * Kx + 1)) % cfg["Nx"] for m in range(2 * Kx + 1)]
     out["gathered"] = float(np.abs(full[:, :, allrows, :Kz + 1] - ref[:, :, allrows, :Kz + 1]).max() / np.abs(ref).max())
