@@ -20,12 +20,21 @@ from tests import parity  # noqa: E402
 
 def main():
     os.environ["CFGPU_DEVICE"] = "0"  # the emulator has one "device"; on a GPU box the default is LOCAL_RANK
+    use_gpu = os.environ.get("CF_WORKER_BACKEND") == "nccl"  # GPU box: the product library over NCCL
+    if use_gpu:
+        os.environ["CFGPU_DEVICE"] = os.environ.get("LOCAL_RANK", "0")
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    lib = parity.emu_lib() if rank == 0 else None
-    dist.barrier()
-    if lib is None:
-        lib = parity.emu_lib()
+    if use_gpu:
+        lib = parity.gpu_lib()
+        ids = [lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        lib.comm_init_nccl(rank, world, ids[0])
+    else:
+        lib = parity.emu_lib() if rank == 0 else None
+        dist.barrier()
+        if lib is None:
+            lib = parity.emu_lib()
 
     def exchange(sends, recvs):
         reqs = []
@@ -41,9 +50,10 @@ def main():
     def allreduce(buf, op):
         dist.all_reduce(torch.from_numpy(buf), op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
 
-    lib.comm_init_external(rank, world, exchange, allreduce)
+    if not use_gpu:
+        lib.comm_init_external(rank, world, exchange, allreduce)
 
-    cfg = dict(parity.C1, Nx=16, Ny=17, Nz=12)
+    cfg = dict(parity.C1, Nx=16, Ny=17, Nz=12) if not use_gpu else dict(parity.C1, Nx=48, Ny=49, Nz=32)
     stepper = sys.argv[1] if len(sys.argv) > 1 else "sbdf3"
     fl = dict(cfg["flags"], timestepping=stepper)
     ur = parity.ref_random(cfg, 1)

@@ -151,3 +151,18 @@ def test_full_size_roundtrip(lib):
     u.make_spectral()
     b = u.get()
     assert parity.rel_l2(b, a) < 1e-13
+
+
+def test_slab_decomposition_nccl():
+    """2-GPU run of the slab decomposition over NCCL against the single-process oracle (skipped with < 2 GPUs)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(parity.ROOT, "tests", "mp_slab_worker.py"), "sbdf3"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, cwd=parity.ROOT,
+                       env=dict(os.environ, CF_WORKER_BACKEND="nccl"))
+    assert r.returncode == 0, r.stdout.decode()[-4000:]
