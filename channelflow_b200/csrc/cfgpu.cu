@@ -262,6 +262,11 @@ int cfgpu_init(int device, cfgpu_ctx* out) {
     CF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CF_CUDA(cudaEventCreate(&ctx->ev0));
     CF_CUDA(cudaEventCreate(&ctx->ev1));
+    CF_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) {
+        CF_CUDA(cudaEventCreateWithFlags(&ctx->ev_cmp[i], cudaEventDisableTiming));
+        CF_CUDA(cudaEventCreateWithFlags(&ctx->ev_com[i], cudaEventDisableTiming));
+    }
     *out = ctx;
     return 0;
 }
@@ -282,6 +287,9 @@ int cfgpu_finalize(cfgpu_ctx ctx) {
     comm_destroy(ctx->comm);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 4; ++i) { cudaEventDestroy(ctx->ev_cmp[i]); cudaEventDestroy(ctx->ev_com[i]); }
+    cudaStreamSynchronize(ctx->comm_stream);
+    cudaStreamDestroy(ctx->comm_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

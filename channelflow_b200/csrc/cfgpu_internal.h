@@ -48,6 +48,8 @@ struct cfgpu_ctx_s {
     int device = 0;
     cudaStream_t stream = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t comm_stream = 0;                 // all-to-all of the slab decomposition (overlaps the transforms)
+    cudaEvent_t ev_cmp[4] = {nullptr, nullptr, nullptr, nullptr}, ev_com[4] = {nullptr, nullptr, nullptr, nullptr};
     std::map<std::tuple<int, double, double>, cfgpu::YPlan> yplans;
     std::map<int, cfgpu::FftPlanHost> fftplans;
     std::map<std::tuple<int, int, int, int>, cfgpu::ModeBox> boxes;

@@ -38,7 +38,7 @@ static int pick_TL(int Nx, int Nz, int npair) {
 
 // all-to-all between the kx-slab pencils P[f][Ny][mxi in X_rank][kz] and the y-slab staging
 // S[s][f][y in Y_rank][mxi in X_s][kz] (comm.cuh); dir 0: P -> S (inverse transform), 1: S -> P (forward)
-static int slab_exchange(cfgpu_nse nse, int nf, int dir) {
+static int slab_exchange(cfgpu_nse nse, int nf, int dir, const int* fields, int nsel, cudaStream_t stream) {
     cfgpu_ctx ctx = nse->ctx;
     Comm& cm = ctx->comm;
     if (cm.nranks == 1) return 0;
@@ -51,7 +51,8 @@ static int slab_exchange(cfgpu_nse nse, int nf, int dir) {
         int xa, xb, ya, yb;
         part_range(nmx, cm.nranks, r, xa, xb);
         part_range(nse->Ny, cm.nranks, r, ya, yb);
-        for (int f = 0; f < nf; ++f) {
+        for (int k = 0; k < nsel; ++k) {
+            const int f = fields[k];
             double2* pp = P + ((size_t)f * nse->Ny + ya) * nxl * nkz;                                     // my rows, r's planes
             const long long pb = (long long)(yb - ya) * nxl * nkz * 16;
             double2* sp = S + (size_t)nkz * ((size_t)nf * nyl * xa + (size_t)f * nyl * (xb - xa));          // r's rows, my planes
@@ -60,7 +61,7 @@ static int slab_exchange(cfgpu_nse nse, int nf, int dir) {
             else msgs.push_back({r, sp, sb, pp, pb});
         }
     }
-    return comm_exchange(cm, msgs.data(), (int)msgs.size(), ctx->stream);
+    return comm_exchange(cm, msgs.data(), (int)msgs.size(), stream);
 }
 
 static void fill_xsplit(cfgpu_nse nse, XPassParams& xp, int nstage) {
@@ -116,8 +117,24 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         p.job[0].nmat = 2; p.job[0].out[1] = P + 3 * Pf;  // du/dy
         p.job[2].nmat = 2; p.job[2].out[1] = P + 4 * Pf;  // dw/dy
     }
-    { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(p, ctx->stream)); }
-    { StageTimer _t(ctx, 8); CF_TRY(slab_exchange(nse, nfP, 0)); }
+    if (!multi) {
+        StageTimer _t(ctx, 0);
+        CF_TRY(ygemm_launch(p, ctx->stream));
+    } else {
+        // per velocity component: y-GEMM on the compute stream, its all-to-all on the communication stream while the
+        // next component's y-GEMM runs
+        for (int c = 0; c < 3; ++c) {
+            YGemmParams pc = p;
+            pc.njobs = 1;
+            pc.job[0] = p.job[c];
+            { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(pc, ctx->stream)); }
+            CF_CUDA(cudaEventRecord(ctx->ev_cmp[c], ctx->stream));
+            CF_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_cmp[c], 0));
+            const int fl[2] = {c, c == 0 ? 3 : 4};
+            CF_TRY(slab_exchange(nse, nfP, 0, fl, (with_derivs && c != 1) ? 2 : 1, ctx->comm_stream));
+            CF_CUDA(cudaEventRecord(ctx->ev_com[c], ctx->comm_stream));
+        }
+    }
 
     XPassParams xp;
     memset(&xp, 0, sizeof xp);
@@ -132,12 +149,27 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     if (with_derivs) {
         const int src[7] = {0, 1, 2, 3, 4, 1, 2}, ddx[7] = {0, 0, 0, 0, 0, 1, 1};
         xp.nfields = 7;
-        for (int i = 0; i < 7; ++i) { xp.src[i] = src[i]; xp.ddx[i] = ddx[i]; }
+        for (int i = 0; i < 7; ++i) { xp.src[i] = src[i]; xp.ddx[i] = ddx[i]; xp.fsel[i] = i; }
     } else {
         xp.nfields = 3;
-        for (int i = 0; i < 3; ++i) { xp.src[i] = i; xp.ddx[i] = 0; }
+        for (int i = 0; i < 3; ++i) { xp.src[i] = i; xp.ddx[i] = 0; xp.fsel[i] = i; }
     }
-    { StageTimer _t(ctx, 1); CF_TRY(xpass_inverse_launch(xp, ctx->stream)); }
+    if (!multi) {
+        StageTimer _t(ctx, 1);
+        CF_TRY(xpass_inverse_launch(xp, ctx->stream));
+    } else {
+        // output slots fed by component c: u -> {u, u_y}; v -> {v, v_x}; w -> {w, w_y, w_x}
+        const int sel[3][3] = {{0, 3, -1}, {1, 5, -1}, {2, 4, 6}};
+        for (int c = 0; c < 3; ++c) {
+            CF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_com[c], 0));
+            XPassParams xc = xp;
+            xc.nfields = 0;
+            if (with_derivs) { for (int k = 0; k < 3; ++k) if (sel[c][k] >= 0) xc.fsel[xc.nfields++] = sel[c][k]; }
+            else xc.fsel[xc.nfields++] = c;
+            StageTimer _t(ctx, 1);
+            CF_TRY(xpass_inverse_launch(xc, ctx->stream));
+        }
+    }
     return 0;
 }
 
@@ -367,8 +399,22 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     xp.out = reinterpret_cast<double2*>(multi ? ctx->ws_S.ptr : ctx->ws_P.ptr);
     xp.ny0 = nse->y0; xp.nyn = nse->y1 - nse->y0;
     fill_xsplit(nse, xp, 3);
-    { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xp, ctx->stream)); }
-    { StageTimer _t(ctx, 8); CF_TRY(slab_exchange(nse, 3, 1)); }
+    for (int i = 0; i < 3; ++i) xp.fsel[i] = i;
+    if (!multi) {
+        StageTimer _t(ctx, 3);
+        CF_TRY(xpass_forward_launch(xp, ctx->stream));
+    } else {
+        for (int c = 0; c < 3; ++c) {  // x-pass of component c, then its all-to-all overlapping the next x-pass / y-GEMM
+            XPassParams xc = xp;
+            xc.nfields = 1;
+            xc.fsel[0] = c;
+            { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xc, ctx->stream)); }
+            CF_CUDA(cudaEventRecord(ctx->ev_cmp[c], ctx->stream));
+            CF_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_cmp[c], 0));
+            CF_TRY(slab_exchange(nse, 3, 1, &c, 1, ctx->comm_stream));
+            CF_CUDA(cudaEventRecord(ctx->ev_com[c], ctx->comm_stream));
+        }
+    }
 
     // aliased modes of f must be exactly zero (FlowField::zeroPaddedModes, nse.cpp:389-390); the kernels below
     // only ever write retained modes
@@ -395,7 +441,19 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         p.job[i].out[0] = f->d + i * f->compstride();
         p.job[i].nmat = 1; p.job[i].mat0 = 0;
     }
-    { StageTimer _t(ctx, 4); CF_TRY(ygemm_launch(p, ctx->stream)); }
+    if (!multi) {
+        StageTimer _t(ctx, 4);
+        CF_TRY(ygemm_launch(p, ctx->stream));
+    } else {
+        for (int c = 0; c < 3; ++c) {
+            CF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_com[c], 0));
+            YGemmParams pc = p;
+            pc.njobs = 1;
+            pc.job[0] = p.job[c];
+            StageTimer _t(ctx, 4);
+            CF_TRY(ygemm_launch(pc, ctx->stream));
+        }
+    }
     f->xzstate = CFGPU_SPECTRAL; f->ystate = CFGPU_SPECTRAL;
     f->clean_Kx = nse->Kx; f->clean_Kz = nse->Kz;
     if (nse->cfg.dealias_xz) f->padded = 1;

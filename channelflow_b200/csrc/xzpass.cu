@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassPa
     double2* a = dyn_smem<double2>();
     double2* b = a + (size_t)Nx * TZ;
     const int tid = threadIdx.x;
-    const int f = blockIdx.z, yl = blockIdx.y, kz0 = blockIdx.x * TZ;
+    const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
     const int s = p.src[f];
     const bool ddx = p.ddx[f] != 0;
 
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_forward_kernel(const XPassPa
     double2* a = dyn_smem<double2>();
     double2* b = a + (size_t)Nx * TZ;
     const int tid = threadIdx.x;
-    const int f = blockIdx.z, yl = blockIdx.y, kz0 = blockIdx.x * TZ;
+    const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
     const double2* __restrict__ in = p.in + ((size_t)f * p.nyn + yl) * Nx * nkz;
     for (int idx = tid; idx < Nx * TZ; idx += XZ_THREADS) {
         const int nx = idx / TZ, c = idx - nx * TZ;

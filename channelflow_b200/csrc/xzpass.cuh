@@ -19,8 +19,9 @@ struct XPassParams {
     double Lx;
     FftPlanDev plan;      // length Nx
     // inverse: nout outputs, each from src[out] with optional d/dx
-    int nfields;
-    int src[9];
+    int nfields;          // fields this launch handles: output slots fsel[0..nfields)
+    int fsel[9];
+    int src[9];           // indexed by output slot
     int ddx[9];
     const double2* in;    // inverse: P (field stride Ny*nmx*nkz); forward: Q (field stride Ny*Nx*nkz)
     double2* out;         // inverse: Q ; forward: P
