@@ -37,6 +37,74 @@ __device__ __forceinline__ double2 operator+(double2 a, double2 b) { return make
 __device__ __forceinline__ double2 operator-(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 operator*(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
 
+// In-register radix-R butterfly: v[q] <- sum_r v[r] W_R^{rq} (W_R = exp(-+2 pi i / R) for DIR = -1 / +1).
+template <int DIR, int R>
+__device__ __forceinline__ void radix_butterfly(double2 (&v)[R]) {
+    if (R == 2) {
+        double2 t = v[0] - v[1];
+        v[0] = v[0] + v[1];
+        v[1] = t;
+    } else if (R == 4) {
+        double2 s02 = v[0] + v[2], d02 = v[0] - v[2], s13 = v[1] + v[3], d13 = rot90<DIR>(v[1] - v[3]);
+        v[0] = s02 + s13;
+        v[1] = d02 + d13;
+        v[2] = s02 - s13;
+        v[3] = d02 - d13;
+    } else if (R == 8) {
+        // radix-2 split (r, r+4), twiddles W8^r on the odd half, then two radix-4 butterflies
+        const double h = 0.70710678118654752440084436210485;
+        double2 a[8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            a[r] = v[r] + v[r + 4];
+            a[r + 4] = v[r] - v[r + 4];
+        }
+        {
+            const double2 t5 = a[5], t7 = a[7];
+            if (DIR < 0) {
+                a[5] = make_double2(h * (t5.x + t5.y), h * (t5.y - t5.x));
+                a[7] = make_double2(h * (t7.y - t7.x), -h * (t7.x + t7.y));
+            } else {
+                a[5] = make_double2(h * (t5.x - t5.y), h * (t5.x + t5.y));
+                a[7] = make_double2(-h * (t7.x + t7.y), h * (t7.x - t7.y));
+            }
+            a[6] = rot90<DIR>(a[6]);
+        }
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const double2 b0 = a[4 * o], b1 = a[4 * o + 1], b2 = a[4 * o + 2], b3 = a[4 * o + 3];
+            const double2 s02 = b0 + b2, d02 = b0 - b2, s13 = b1 + b3, d13 = rot90<DIR>(b1 - b3);
+            v[o] = s02 + s13;
+            v[o + 2] = d02 + d13;
+            v[o + 4] = s02 - s13;
+            v[o + 6] = d02 - d13;
+        }
+    } else if (R == 3) {
+        const double wi = (DIR < 0 ? -1.0 : 1.0) * 0.86602540378443864676372317075294;  // sin(2 pi/3)
+        double2 s = v[1] + v[2], d = v[1] - v[2];
+        double2 t = make_double2(v[0].x - 0.5 * s.x, v[0].y - 0.5 * s.y);
+        double2 u = make_double2(-wi * d.y, wi * d.x);
+        v[0] = v[0] + s;
+        v[1] = t + u;
+        v[2] = t - u;
+    } else if (R == 5) {
+        const double c1 = 0.30901699437494742410229341718282, c2 = -0.80901699437494742410229341718282;
+        const double sg = (DIR < 0 ? -1.0 : 1.0);
+        const double s1 = sg * 0.95105651629515357211643933337938, s2 = sg * 0.58778525229247312916870595463907;
+        double2 s14 = v[1] + v[4], d14 = v[1] - v[4], s23 = v[2] + v[3], d23 = v[2] - v[3];
+        double2 t1 = make_double2(v[0].x + c1 * s14.x + c2 * s23.x, v[0].y + c1 * s14.y + c2 * s23.y);
+        double2 t2 = make_double2(v[0].x + c2 * s14.x + c1 * s23.x, v[0].y + c2 * s14.y + c1 * s23.y);
+        double2 q1 = make_double2(s1 * d14.x + s2 * d23.x, s1 * d14.y + s2 * d23.y);
+        double2 q2 = make_double2(s2 * d14.x - s1 * d23.x, s2 * d14.y - s1 * d23.y);
+        double2 u1 = make_double2(-q1.y, q1.x), u2 = make_double2(-q2.y, q2.x);
+        v[0] = v[0] + s14 + s23;
+        v[1] = t1 + u1;
+        v[4] = t1 - u1;
+        v[2] = t2 + u2;
+        v[3] = t2 - u2;
+    }
+}
+
 // One Stockham pass of radix R over all C columns. Ns = product of the radices of the previous passes.
 template <int DIR, int R>
 __device__ __forceinline__ void fft_pass(const double2* __restrict__ a, double2* __restrict__ b, const FftPlanDev& pl,
@@ -55,69 +123,7 @@ __device__ __forceinline__ void fft_pass(const double2* __restrict__ a, double2*
 #pragma unroll
             for (int r = 1; r < R; ++r) v[r] = tw_mul<DIR>(v[r], __ldg(&pl.tw[r * k * tstep]));
         }
-        if (R == 2) {
-            double2 t = v[0] - v[1];
-            v[0] = v[0] + v[1];
-            v[1] = t;
-        } else if (R == 4) {
-            double2 s02 = v[0] + v[2], d02 = v[0] - v[2], s13 = v[1] + v[3], d13 = rot90<DIR>(v[1] - v[3]);
-            v[0] = s02 + s13;
-            v[1] = d02 + d13;
-            v[2] = s02 - s13;
-            v[3] = d02 - d13;
-        } else if (R == 8) {
-            // radix-2 split (r, r+4), twiddles W8^r on the odd half, then two radix-4 butterflies
-            const double h = 0.70710678118654752440084436210485;
-            double2 a[8];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                a[r] = v[r] + v[r + 4];
-                a[r + 4] = v[r] - v[r + 4];
-            }
-            {
-                const double2 t5 = a[5], t7 = a[7];
-                if (DIR < 0) {
-                    a[5] = make_double2(h * (t5.x + t5.y), h * (t5.y - t5.x));
-                    a[7] = make_double2(h * (t7.y - t7.x), -h * (t7.x + t7.y));
-                } else {
-                    a[5] = make_double2(h * (t5.x - t5.y), h * (t5.x + t5.y));
-                    a[7] = make_double2(-h * (t7.x + t7.y), h * (t7.x - t7.y));
-                }
-                a[6] = rot90<DIR>(a[6]);
-            }
-#pragma unroll
-            for (int o = 0; o < 2; ++o) {
-                const double2 b0 = a[4 * o], b1 = a[4 * o + 1], b2 = a[4 * o + 2], b3 = a[4 * o + 3];
-                const double2 s02 = b0 + b2, d02 = b0 - b2, s13 = b1 + b3, d13 = rot90<DIR>(b1 - b3);
-                v[o] = s02 + s13;
-                v[o + 2] = d02 + d13;
-                v[o + 4] = s02 - s13;
-                v[o + 6] = d02 - d13;
-            }
-        } else if (R == 3) {
-            const double wi = (DIR < 0 ? -1.0 : 1.0) * 0.86602540378443864676372317075294;  // sin(2 pi/3)
-            double2 s = v[1] + v[2], d = v[1] - v[2];
-            double2 t = make_double2(v[0].x - 0.5 * s.x, v[0].y - 0.5 * s.y);
-            double2 u = make_double2(-wi * d.y, wi * d.x);
-            v[0] = v[0] + s;
-            v[1] = t + u;
-            v[2] = t - u;
-        } else if (R == 5) {
-            const double c1 = 0.30901699437494742410229341718282, c2 = -0.80901699437494742410229341718282;
-            const double sg = (DIR < 0 ? -1.0 : 1.0);
-            const double s1 = sg * 0.95105651629515357211643933337938, s2 = sg * 0.58778525229247312916870595463907;
-            double2 s14 = v[1] + v[4], d14 = v[1] - v[4], s23 = v[2] + v[3], d23 = v[2] - v[3];
-            double2 t1 = make_double2(v[0].x + c1 * s14.x + c2 * s23.x, v[0].y + c1 * s14.y + c2 * s23.y);
-            double2 t2 = make_double2(v[0].x + c2 * s14.x + c1 * s23.x, v[0].y + c2 * s14.y + c1 * s23.y);
-            double2 q1 = make_double2(s1 * d14.x + s2 * d23.x, s1 * d14.y + s2 * d23.y);
-            double2 q2 = make_double2(s2 * d14.x - s1 * d23.x, s2 * d14.y - s1 * d23.y);
-            double2 u1 = make_double2(-q1.y, q1.x), u2 = make_double2(-q2.y, q2.x);
-            v[0] = v[0] + s14 + s23;
-            v[1] = t1 + u1;
-            v[4] = t1 - u1;
-            v[2] = t2 + u2;
-            v[3] = t2 - u2;
-        }
+        radix_butterfly<DIR, R>(v);
         const int j0 = (j / Ns) * Ns * R + k;
 #pragma unroll
         for (int r = 0; r < R; ++r) b[(j0 + r * Ns) * C + c] = v[r];
@@ -145,5 +151,84 @@ __device__ __forceinline__ double2* fft_smem(double2* a, double2* b, const FftPl
     }
     return a;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-private transform: one warp owns one length-N line in shared memory (skewed, addr(i) = i + i/8, so that the
+// stride-R stores of the first pass are bank-conflict free), in place: every lane reads the inputs of its butterflies
+// into registers, __syncwarp, writes the outputs.  No block barrier inside the transform.  Needs N/R <= 32*(16/R)
+// butterflies per pass (N <= 512 for radix 8/4/2, <= 480 with radix 3/5), see warp_fft_supported.
+__host__ __device__ inline int fft_skew(int i) { return i + (i >> 3); }
+__host__ __device__ inline int fft_skew_len(int N) { return N + (N >> 3) + 1; }
+
+template <int DIR, int R>
+__device__ __forceinline__ void warp_fft_pass(double2* __restrict__ buf, const double2* __restrict__ tw, int N, int Ns, int lane) {
+    constexpr int NBMAX = 16 / R;
+    const int nb = N / R;
+    const int tstep = N / (Ns * R);
+    double2 v[NBMAX][R];
+#pragma unroll
+    for (int i = 0; i < NBMAX; ++i) {
+        const int b = lane + 32 * i;
+        if (b < nb) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[i][r] = buf[fft_skew(b + r * nb)];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NBMAX; ++i) {
+        const int b = lane + 32 * i;
+        if (b < nb) {
+            const int k = b % Ns;
+            if (Ns > 1) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[i][r] = tw_mul<DIR>(v[i][r], tw[r * k * tstep]);
+            }
+            radix_butterfly<DIR, R>(v[i]);
+            const int j0 = (b / Ns) * Ns * R + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) buf[fft_skew(j0 + r * Ns)] = v[i][r];
+        }
+    }
+    __syncwarp();
+}
+
+template <int DIR>
+__device__ __forceinline__ void warp_fft(double2* buf, const FftPlanDev& pl, int lane) {
+    int Ns = 1;
+    for (int p = 0; p < pl.npass; ++p) {
+        const int R = pl.radix[p];
+        if (R == 8) warp_fft_pass<DIR, 8>(buf, pl.tw, pl.N, Ns, lane);
+        else if (R == 4) warp_fft_pass<DIR, 4>(buf, pl.tw, pl.N, Ns, lane);
+        else if (R == 2) warp_fft_pass<DIR, 2>(buf, pl.tw, pl.N, Ns, lane);
+        else if (R == 3) warp_fft_pass<DIR, 3>(buf, pl.tw, pl.N, Ns, lane);
+        else warp_fft_pass<DIR, 5>(buf, pl.tw, pl.N, Ns, lane);
+        Ns *= R;
+    }
+}
+
+// Compile-time plan for the power-of-two lengths (radix 8 passes, then one radix 4 or 2): straight-line code, the
+// butterflies' register arrays of the different passes are never live together.
+template <int DIR, int N>
+__device__ __forceinline__ void warp_fft_pow2(double2* buf, const double2* tw, int lane) {
+    static_assert(N >= 8 && N <= 512 && (N & (N - 1)) == 0, "power of two, 8..512");
+    int Ns = 1;
+    constexpr int L = N == 512 ? 9 : N == 256 ? 8 : N == 128 ? 7 : N == 64 ? 6 : N == 32 ? 5 : N == 16 ? 4 : 3;
+    constexpr int N8 = L / 3, REM = L % 3;
+#pragma unroll
+    for (int p = 0; p < N8; ++p) {
+        warp_fft_pass<DIR, 8>(buf, tw, N, Ns, lane);
+        Ns *= 8;
+    }
+    if (REM == 2) warp_fft_pass<DIR, 4>(buf, tw, N, Ns, lane);
+    if (REM == 1) warp_fft_pass<DIR, 2>(buf, tw, N, Ns, lane);
+}
+
+inline bool warp_fft_supported(const FftPlanDev& pl) {
+    for (int p = 0; p < pl.npass; ++p)
+        if (pl.N / pl.radix[p] > 32 * (16 / pl.radix[p])) return false;
+    return pl.npass > 0;
+}
+inline bool warp_fft_pow2_supported(int N) { return N >= 8 && N <= 512 && (N & (N - 1)) == 0; }
 
 }  // namespace cfgpu

@@ -3,6 +3,8 @@
 // once, 16-byte accesses contiguous along kz); the FFT itself runs out of shared memory.
 #include "xzpass.cuh"
 
+#include <cstdlib>
+
 namespace cfgpu {
 
 namespace {
@@ -208,6 +210,150 @@ __global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ z pass, warp-private FFTs
+// Same work as zpass_kernel for Nz <= 512: every complex transform (5 inverse + 2 forward per x-line for the rotational
+// form) is owned by ONE warp and runs in place in its own skewed shared-memory line without block barriers
+// (fft_smem.cuh: warp_fft); the CTA only synchronises between pack / inverse / pointwise / forward / store.
+// grid = (ceil(Nx/TL), nyn), block = 32 * npair * TL threads.  NZ = Nz (power of two, compile-time FFT plan).
+template <int NZ>
+__global__ void __launch_bounds__(320, 2) zpass_warp_kernel(const ZPassParams p) {
+    const int Nx = p.Nx, Nz = NZ, TL = p.TL;
+    const int nkz = p.Kz + 1;
+    const bool rot = p.mode == ZP_ROTATIONAL;
+    const int npair = rot ? 5 : 2;
+    const int njobs = npair * TL;           // job j = q * TL + l : transform q of line l
+    const int NP = fft_skew_len(Nz);
+    double2* buf = dyn_smem<double2>();     // [njobs][NP]
+    double2* tws = buf + (size_t)njobs * NP; // twiddle table exp(-2 pi i t / Nz), t < Nz
+    __shared__ double red[32];
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int yl = blockIdx.y, ny = p.ny0 + yl, nx0 = blockIdx.x * TL;
+    const size_t fstride = (size_t)p.nyn * Nx * nkz;  // field stride of Q and F
+
+    for (int t = tid; t < Nz; t += NT) tws[t] = __ldg(&p.plan.tw[t]);
+    // rows nkz .. Nz-nkz (the de-aliased band and the Nyquist mode) are not written by the packing loop below
+    const int nzero = Nz - 2 * nkz + 1;
+    for (int idx = tid; idx < nzero * njobs; idx += NT) {
+        const int j = idx / nzero, k = nkz + (idx - j * nzero);
+        buf[(size_t)j * NP + fft_skew(k)] = make_double2(0.0, 0.0);
+    }
+    const double2* __restrict__ Q = p.Q + (size_t)yl * Nx * nkz;
+    for (int idx = tid; idx < TL * nkz; idx += NT) {
+        const int l = idx / nkz, k = idx - l * nkz;
+        const int nx = nx0 + l;
+        double2 fa[5], fb[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) fa[q] = fb[q] = make_double2(0.0, 0.0);
+        if (nx < Nx) {
+            const size_t off = (size_t)nx * nkz + k;
+            if (rot) {
+                const double2 u = Q[off], v = Q[fstride + off], w = Q[2 * fstride + off];
+                const double2 uy = Q[3 * fstride + off], wy = Q[4 * fstride + off];
+                const double2 vx = Q[5 * fstride + off], wx = Q[6 * fstride + off];
+                const double kzz = TWO_PI * k / p.Lz;
+                fa[0] = u;  fb[0] = v;
+                fa[1] = w;  fb[1] = uy;
+                fa[2] = wy; fb[2] = vx;
+                fa[3] = wx; fb[3] = make_double2(-kzz * u.y, kzz * u.x);  // du/dz
+                fa[4] = make_double2(-kzz * v.y, kzz * v.x);              // dv/dz
+            } else {
+                fa[0] = Q[off];               fb[0] = Q[fstride + off];
+                fa[1] = Q[2 * fstride + off];
+            }
+        }
+        const int ka = fft_skew(k), kb = fft_skew(k > 0 ? Nz - k : 0);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            if (q >= npair) break;
+            double2 a = fa[q], b = fb[q];
+            if (k == 0) { a.y = 0.0; b.y = 0.0; }  // c2r ignores the imaginary part of the mean mode
+            double2* line = buf + (size_t)(q * TL + l) * NP;
+            line[ka] = make_double2(a.x - b.y, a.y + b.x);
+            if (k > 0) line[kb] = make_double2(a.x + b.y, b.x - a.y);
+        }
+    }
+    __syncthreads();
+    for (int j = warp; j < njobs; j += (NT >> 5)) warp_fft_pow2<+1, NZ>(buf + (size_t)j * NP, tws, lane);
+    __syncthreads();
+
+    // pointwise stage: (line l, point z); the products overwrite transforms 0 and 1 of the same line
+    double U = 0.0, Uy = 0.0, W = 0.0, Wy = 0.0;
+    if (p.Uy) {
+        U = p.Uy[ny];
+        Uy = p.Uy[p.Ny + ny];
+        W = p.Uy[2 * p.Ny + ny];
+        Wy = p.Uy[3 * p.Ny + ny];
+    }
+    const double idx_ = (double)Nx / p.Lx, idz_ = (double)Nz / p.Lz, idy_ = p.inv_dy ? p.inv_dy[ny] : 0.0;
+    double cmax = 0.0;
+    for (int idx = tid; idx < Nz * TL; idx += NT) {
+        const int l = idx / Nz, z = idx - l * Nz;
+        if (nx0 + l >= Nx) continue;
+        const int zs = fft_skew(z);
+        double2* r = buf + (size_t)l * NP + zs;
+        const size_t js = (size_t)TL * NP;  // stride between transforms of one line
+        if (rot) {
+            const double2 z0 = r[0], z1 = r[js], z2 = r[2 * js], z3 = r[3 * js], z4 = r[4 * js];
+            const double u = z0.x, v = z0.y, w = z1.x, uy = z1.y, wy = z2.x, vx = z2.y, wx = z3.x, uz = z3.y, vz = z4.x;
+            const double ut = u + U, vt = v - p.Vsuck, wt = w + W;
+            const double ox = (wy + Wy) - vz;
+            const double oy = uz - wx;
+            const double oz = vx - (uy + Uy);
+            double fx = oy * wt - oz * vt;
+            double fy = oz * ut - ox * wt;
+            const double fz = ox * vt - oy * ut;
+            if (p.rotation != 0.0) {
+                fx -= p.rotation * vt;
+                fy += p.rotation * ut;
+            }
+            r[0] = make_double2(fx, fy);
+            r[js] = make_double2(fz, 0.0);
+            double m = ut * idx_;
+            const double m2 = v * idy_, m3 = wt * idz_;
+            m = m2 > m ? m2 : m;
+            m = m3 > m ? m3 : m;
+            cmax = m > cmax ? m : cmax;
+        } else {
+            const double2 z0 = r[0], z1 = r[js];
+            double m = (z0.x + U) * idx_;
+            const double m2 = z0.y * idy_, m3 = (z1.x + W) * idz_;
+            m = m2 > m ? m2 : m;
+            m = m3 > m ? m3 : m;
+            cmax = m > cmax ? m : cmax;
+        }
+    }
+    if (p.cfl_max) {
+        cmax = warp_max(cmax);
+        if (lane == 0) red[warp] = cmax;
+        __syncthreads();
+        if (tid < 32) {
+            double v = tid < (NT >> 5) ? red[tid] : 0.0;
+            v = warp_max(v);
+            if (tid == 0 && v > 0.0) atomic_max_double(p.cfl_max, v);
+        }
+    }
+    if (!rot) return;
+    __syncthreads();
+    for (int j = warp; j < 2 * TL; j += (NT >> 5)) warp_fft_pow2<-1, NZ>(buf + (size_t)j * NP, tws, lane);
+    __syncthreads();
+
+    double2* __restrict__ F = p.F + (size_t)yl * Nx * nkz;
+    const double sc = p.scale, hs = 0.5 * p.scale;
+    for (int idx = tid; idx < TL * nkz; idx += NT) {
+        const int l = idx / nkz, k = idx - l * nkz;
+        const int nx = nx0 + l;
+        if (nx >= Nx) continue;
+        const double2* g = buf + (size_t)l * NP;                // transform 0 of line l: fx + i fy
+        const double2* h = buf + (size_t)(TL + l) * NP;         // transform 1: fz
+        const int ks = fft_skew(k), kn = fft_skew(k == 0 ? 0 : Nz - k);
+        const double2 gk = g[ks], gn = g[kn], hk = h[ks];
+        const size_t off = (size_t)nx * nkz + k;
+        F[off] = make_double2(hs * (gk.x + gn.x), hs * (gk.y - gn.y));
+        F[fstride + off] = make_double2(hs * (gk.y + gn.y), -hs * (gk.x - gn.x));
+        F[2 * fstride + off] = make_double2(sc * hk.x, sc * hk.y);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 static int set_smem(const void* fn, size_t bytes, size_t& configured) {
     if (bytes > configured) {
@@ -241,7 +387,39 @@ int xpass_forward_launch(const XPassParams& p, cudaStream_t stream) {
     return 0;
 }
 
+template <int NZ>
+static int zpass_warp_launch(const ZPassParams& p0, cudaStream_t stream) {
+    ZPassParams p = p0;
+    const int npair = p.mode == ZP_ROTATIONAL ? 5 : 2;
+    // lines per CTA: small CTAs (one line = 5 warps at Nz = 512, four CTAs per SM) interleave their pack / FFT / store phases
+    // better than fewer large ones (measured 4.17 -> 3.88 ms at 512x257x512)
+    const size_t per_line = (size_t)npair * fft_skew_len(p.Nz) * sizeof(double2);
+    int TL = 1;
+    const size_t cap = (size_t)(getenv("CF_ZP_SMEM_KB") ? atoi(getenv("CF_ZP_SMEM_KB")) : 50) * 1024;
+    while (TL < 8 && (size_t)(TL + 1) * per_line <= cap && npair * (TL + 1) <= 10 && TL + 1 <= p.Nx) ++TL;
+    p.TL = TL;
+    const size_t smem = (size_t)TL * per_line + (size_t)p.Nz * sizeof(double2);
+    static size_t configured = 0;
+    auto kfn = zpass_warp_kernel<NZ>;
+    CF_TRY(set_smem((const void*)kfn, smem, configured));
+    dim3 grid((p.Nx + TL - 1) / TL, p.nyn);
+    int nt = 32 * npair * TL;
+    if (nt < 128) nt = 128;
+    CF_LAUNCH(kfn, grid, dim3(nt), smem, stream, p);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
 int zpass_launch(const ZPassParams& p, cudaStream_t stream) {
+    switch (p.Nz) {  // warp-private transforms for the power-of-two lengths
+        case 16: return zpass_warp_launch<16>(p, stream);
+        case 32: return zpass_warp_launch<32>(p, stream);
+        case 64: return zpass_warp_launch<64>(p, stream);
+        case 128: return zpass_warp_launch<128>(p, stream);
+        case 256: return zpass_warp_launch<256>(p, stream);
+        case 512: return zpass_warp_launch<512>(p, stream);
+        default: break;
+    }
     const int npair = p.mode == ZP_ROTATIONAL ? 5 : 2;
     const size_t smem = 2 * (size_t)p.Nz * npair * p.TL * sizeof(double2);
     static size_t configured = 0;

@@ -23,11 +23,13 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
 #define __align__(n) alignas(n)
 #define __constant__ static
+#define __grid_constant__
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
