@@ -495,6 +495,22 @@ class FlowField:
     def cmplx(self, mx, my, mz, i): return complex(self.lib.L.cf_cmplx_get(self.h, mx, my, mz, i, 0), self.lib.L.cf_cmplx_get(self.h, mx, my, mz, i, 1))
     def set_cmplx(self, mx, my, mz, i, v): self.lib.L.cf_cmplx_set(self.h, mx, my, mz, i, v.real, v.imag)
     def allgather(self): self.lib.L.cf_field_allgather(self.h)
+
+    def to_vector(self):
+        """field2vector (reference flowfield.cpp:4481-4563)."""
+        self.lib.L.cf_field2vector_size.argtypes = [C.c_void_p]
+        n = self.lib.L.cf_field2vector_size(self.h)
+        x = np.zeros(n)
+        self.lib.L.cf_field2vector.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self.lib.L.cf_field2vector(self.h, _dp(x))
+        return x
+
+    def from_vector(self, x):
+        """vector2field (reference flowfield.cpp:4565-4752)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.lib.L.cf_vector2field.argtypes = [C.POINTER(C.c_double), C.c_void_p]
+        self.lib.L.cf_vector2field(_dp(x), self.h)
+        return self
     def save(self, filebase): self.lib.L.cf_field_save(self.h, filebase.encode())
     def axpby(self, a, x, b=0.0, z=None): self.lib.L.cf_field_axpby(self.h, a, x.h, b, z.h if z is not None else None)
     def scale(self, s): self.lib.L.cf_field_scale(self.h, s)

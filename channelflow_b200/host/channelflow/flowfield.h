@@ -190,5 +190,27 @@ FlowField operator+(const FlowField& v, const FlowField& w);
 FlowField operator-(const FlowField& v, const FlowField& w);
 void swap(FlowField& f, FlowField& g);
 
+// The field2vector and vector2field functions assume zero divergence and no-slip BCs (reference flowfield.h:617-621).
+// Raw-pointer forms plus adaptors for any vector type with size()/resize()/data() (Eigen::VectorXd, std::vector).
+int field2vector_size(const FlowField& u);
+void field2vector(const FlowField& u, Real* a);
+void vector2field(const Real* a, FlowField& u);
+void fixdivnoslip(FlowField& u);
+template <class Vec>
+inline auto field2vector(const FlowField& u, Vec& v) -> decltype(v.resize(1), void()) {
+    const int N = field2vector_size(u);
+    if ((int)v.size() < N) v.resize(N);
+    field2vector(u, v.data());
+}
+template <class Vec>
+inline auto vector2field(const Vec& v, FlowField& u) -> decltype(v.size(), void()) {
+    vector2field(v.data(), u);
+}
+// utilfuncs.h:76-81
+void fixDiri(ChebyCoeff& f);
+void fixDiriMean(ChebyCoeff& f);
+void fixDiri(ComplexChebyCoeff& f);
+void fixDiriMean(ComplexChebyCoeff& f);
+
 }  // namespace chflow
 #endif

@@ -182,6 +182,7 @@ class RefField:
     def from_vector(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         lib().ref_vector2field(_dp(x), x.size, self.h)
+        return self
 
 
 class RefDNS:

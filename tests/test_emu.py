@@ -154,3 +154,18 @@ def test_laminar_profiles(lib):
         a = cf.laminar_profile(lib, cf.make_flags(**kw), -1.0, 1.0, 33)
         b = refcf.laminar_profile(refcf.make_flags(**kw), -1.0, 1.0, 33)
         assert np.abs(a - b).max() < 1e-14, kw
+
+
+def test_field2vector_roundtrip(lib):
+    """field2vector / vector2field against the reference's (flowfield.cpp:4448-4752): same vector, same rebuilt field."""
+    ur = parity.ref_random(SMALL, 9)
+    ug = parity.to_gpu(lib, ur)
+    xr = ur.to_vector()
+    xg = ug.to_vector()
+    assert xg.shape == xr.shape and np.abs(xg - xr).max() == 0.0
+    rng = np.random.default_rng(3)
+    y = xr + 1e-3 * rng.standard_normal(xr.shape)
+    vr = ur.like().from_vector(y)
+    vg = ug.like().from_vector(y)
+    assert parity.rel_l2(vg.get(), vr.data) < 1e-14
+    assert vg.padded()

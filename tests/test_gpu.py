@@ -166,3 +166,13 @@ def test_slab_decomposition_nccl():
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, cwd=parity.ROOT,
                        env=dict(os.environ, CF_WORKER_BACKEND="nccl"))
     assert r.returncode == 0, r.stdout.decode()[-4000:]
+
+
+def test_field2vector_roundtrip(lib):
+    ur = parity.ref_random(MID, 9)
+    ug = parity.to_gpu(lib, ur)
+    xr, xg = ur.to_vector(), ug.to_vector()
+    assert xg.shape == xr.shape and np.abs(xg - xr).max() == 0.0
+    y = xr + 1e-3 * np.random.default_rng(3).standard_normal(xr.shape)
+    vr, vg = ur.like().from_vector(y), ug.like().from_vector(y)
+    assert parity.rel_l2(vg.get(), vr.data) < 1e-14
