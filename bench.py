@@ -37,7 +37,10 @@ WORKLOADS = {
 }
 STAGES = ["inv_y_gemm", "inv_x_pass", "z_pass_nl", "fwd_x_pass", "fwd_y_gemm", "tau_solve", "linear", "tau_setup", "slab_alltoall"]
 # algorithmic bytes per stage in units of W (rotational SBDF-k with k=3)
-STAGE_W = {"inv_y_gemm": 3 + 5, "inv_x_pass": 5 + 7, "z_pass_nl": 7 + 3, "fwd_x_pass": 3 + 3, "fwd_y_gemm": 3 + 3, "tau_solve": 15 + 4}
+# (the x/z passes move one field less than SURVEY's 61 W table: curl u is formed while the inverse x-pass loads, so
+# 6 fields -- u and curl u -- instead of 7 go through it; 59 W per step)
+STAGE_W = {"inv_y_gemm": 3 + 5, "inv_x_pass": 5 + 6, "z_pass_nl": 6 + 3, "fwd_x_pass": 3 + 3, "fwd_y_gemm": 3 + 3, "tau_solve": 15 + 4}
+STEP_W = 59
 
 
 def synthetic_field(w, seed=1, magn=0.1):
@@ -276,8 +279,8 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "whole_step_algorithmic_GBps_per_gpu": 61 * Wbytes / world / (ms * 1e-3) / 1e9,
-                "whole_step_frac": 61 * Wbytes / world / (ms * 1e-3) / 1e9 / hbm_peak,
+                "whole_step_algorithmic_GBps_per_gpu": STEP_W * Wbytes / world / (ms * 1e-3) / 1e9,
+                "whole_step_frac": STEP_W * Wbytes / world / (ms * 1e-3) / 1e9 / hbm_peak,
                 "y_gemm_TFLOPs": (8 * 2 * w["Ny"] * ((w["Ny"] + 1) // 2) * 2 * (w["Nx"] // 3 * 2 - 1) * (w["Nz"] // 3) * 2) /
                 ((stages.get("inv_y_gemm", {}).get("ms_per_step", 0) + stages.get("fwd_y_gemm", {}).get("ms_per_step", 0)) * 1e-3 + 1e-30) / 1e12}
 

@@ -94,7 +94,7 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     const size_t Qf = (size_t)nyl * nse->Nx * nkz * 2;      // doubles per pencil field Q (y slab)
     CF_TRY(ws_reserve(ctx->ws_P, 5 * Pf * sizeof(double)));
     if (multi) CF_TRY(ws_reserve(ctx->ws_S, 5 * Sf * sizeof(double)));
-    CF_TRY(ws_reserve(ctx->ws_Q, 7 * Qf * sizeof(double)));
+    CF_TRY(ws_reserve(ctx->ws_Q, 6 * Qf * sizeof(double)));
     double* P = ctx->ws_P.ptr;
     const int nfP = with_derivs ? 5 : 3;
 
@@ -146,20 +146,25 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     xp.out = reinterpret_cast<double2*>(ctx->ws_Q.ptr);
     xp.ny0 = nse->y0; xp.nyn = nyl;
     fill_xsplit(nse, xp, nfP);
+    xp.Lz = nse->Lz;
     if (with_derivs) {
-        const int src[7] = {0, 1, 2, 3, 4, 1, 2}, ddx[7] = {0, 0, 0, 0, 0, 1, 1};
-        xp.nfields = 7;
-        for (int i = 0; i < 7; ++i) { xp.src[i] = src[i]; xp.ddx[i] = ddx[i]; xp.fsel[i] = i; }
+        // P fields: 0 u, 1 v, 2 w, 3 du/dy, 4 dw/dy.  Q fields: u, v, w, omega_x = dw/dy - dv/dz,
+        // omega_y = du/dz - dw/dx, omega_z = dv/dx - du/dy  (curl, diffops.cpp:2229-2334)
+        const int src[6] = {0, 1, 2, 4, 0, 1}, opa[6] = {0, 0, 0, 0, 2, 1};
+        const int srcb[6] = {-1, -1, -1, 1, 2, 3}, opb[6] = {0, 0, 0, 2, 1, 0};
+        xp.nfields = 6;
+        for (int i = 0; i < 6; ++i) { xp.src[i] = src[i]; xp.opa[i] = opa[i]; xp.srcb[i] = srcb[i]; xp.opb[i] = opb[i]; xp.fsel[i] = i; }
     } else {
         xp.nfields = 3;
-        for (int i = 0; i < 3; ++i) { xp.src[i] = i; xp.ddx[i] = 0; xp.fsel[i] = i; }
+        for (int i = 0; i < 3; ++i) { xp.src[i] = i; xp.opa[i] = 0; xp.srcb[i] = -1; xp.opb[i] = 0; xp.fsel[i] = i; }
     }
     if (!multi) {
         StageTimer _t(ctx, 1);
         CF_TRY(xpass_inverse_launch(xp, ctx->stream));
     } else {
-        // output slots fed by component c: u -> {u, u_y}; v -> {v, v_x}; w -> {w, w_y, w_x}
-        const int sel[3][3] = {{0, 3, -1}, {1, 5, -1}, {2, 4, 6}};
+        // output slots that become computable when component c has arrived: u (+du/dy) -> {u}; v -> {v, omega_z};
+        // w (+dw/dy) -> {w, omega_x, omega_y}
+        const int sel[3][3] = {{0, -1, -1}, {1, 5, -1}, {2, 3, 4}};
         for (int c = 0; c < 3; ++c) {
             CF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_com[c], 0));
             XPassParams xc = xp;
@@ -179,7 +184,7 @@ static int fill_zpass(cfgpu_nse nse, ZPassParams& zp, int mode) {
     memset(&zp, 0, sizeof zp);
     zp.Nx = nse->Nx; zp.Ny = nse->Ny; zp.Nz = nse->Nz; zp.Kz = nse->Kz;
     zp.mode = mode;
-    zp.TL = pick_TL(nse->Nx, nse->Nz, mode == ZP_ROTATIONAL ? 5 : 2);
+    zp.TL = pick_TL(nse->Nx, nse->Nz, mode == ZP_ROTATIONAL ? 3 : 2);
     zp.Lx = nse->Lx; zp.Lz = nse->Lz;
     zp.scale = 1.0 / ((double)nse->Nx * (double)nse->Nz);
     zp.Vsuck = nse->cfg.Vsuck;

@@ -21,8 +21,7 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassPa
     double2* b = a + (size_t)Nx * TZ;
     const int tid = threadIdx.x;
     const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
-    const int s = p.src[f];
-    const bool ddx = p.ddx[f] != 0;
+    const int s = p.src[f], oa = p.opa[f], sb = p.srcb[f], ob = p.opb[f];
 
     // zero the aliased rows Kx+1 .. Nx-Kx-1
     const int nzero = (Nx - nmx) * TZ;
@@ -34,10 +33,20 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassPa
         const int kx = mxi <= Kx ? mxi : mxi - nmx;
         const int mx = kx >= 0 ? kx : Nx + kx;
         double2 v = make_double2(0.0, 0.0);
-        if (kz < nkz) v = in[xpass_row_offset(p, s, yl, mxi, nkz) + kz];
-        if (ddx) {
-            const double k = TWO_PI * kx / p.Lx;
-            v = make_double2(-k * v.y, k * v.x);
+        if (kz < nkz) {
+            v = in[xpass_row_offset(p, s, yl, mxi, nkz) + kz];
+            if (oa) {
+                const double k = oa == 1 ? TWO_PI * kx / p.Lx : TWO_PI * kz / p.Lz;
+                v = make_double2(-k * v.y, k * v.x);
+            }
+            if (sb >= 0) {
+                double2 w = in[xpass_row_offset(p, sb, yl, mxi, nkz) + kz];
+                if (ob) {
+                    const double k = ob == 1 ? TWO_PI * kx / p.Lx : TWO_PI * kz / p.Lz;
+                    w = make_double2(-k * w.y, k * w.x);
+                }
+                v = make_double2(v.x - w.x, v.y - w.y);
+            }
         }
         a[mx * TZ + c] = v;
     }
@@ -80,12 +89,12 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_forward_kernel(const XPassPa
 
 // ------------------------------------------------------------------------------------------------ z pass
 // grid = (ceil(Nx/TL), nyn).  Two real fields share one complex transform (Z = A + iB with the Hermitian
-// extension written explicitly), so the rotational term needs 5 inverse + 2 forward complex FFTs per line.
+// extension written explicitly), so the rotational term (u, v, w, curl u) needs 3 inverse + 2 forward complex FFTs per line.
 __global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
     const int Nx = p.Nx, Nz = p.Nz, TL = p.TL;
     const int nkz = p.Kz + 1;
     const bool rot = p.mode == ZP_ROTATIONAL;
-    const int npair = rot ? 5 : 2;
+    const int npair = rot ? 3 : 2;
     const int CA = npair * TL;
     double2* A = dyn_smem<double2>();
     double2* B = A + (size_t)Nz * CA;
@@ -103,18 +112,11 @@ __global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
         const int nx = nx0 + l;
         if (nx >= Nx) continue;
         const size_t off = (size_t)nx * nkz + k;
-        double2 fa[5], fb[5];
+        double2 fa[3], fb[3];
         if (rot) {
-            const double2 u = Q[off], v = Q[fstride + off], w = Q[2 * fstride + off];
-            const double2 uy = Q[3 * fstride + off], wy = Q[4 * fstride + off];
-            const double2 vx = Q[5 * fstride + off], wx = Q[6 * fstride + off];
-            const double kzz = TWO_PI * k / p.Lz;
-            fa[0] = u;  fb[0] = v;
-            fa[1] = w;  fb[1] = uy;
-            fa[2] = wy; fb[2] = vx;
-            fa[3] = wx; fb[3] = make_double2(-kzz * u.y, kzz * u.x);  // du/dz
-            fa[4] = make_double2(-kzz * v.y, kzz * v.x);              // dv/dz
-            fb[4] = make_double2(0.0, 0.0);
+            fa[0] = Q[off];               fb[0] = Q[fstride + off];       // u, v
+            fa[1] = Q[2 * fstride + off]; fb[1] = Q[3 * fstride + off];   // w, omega_x
+            fa[2] = Q[4 * fstride + off]; fb[2] = Q[5 * fstride + off];   // omega_y, omega_z
         } else {
             fa[0] = Q[off];               fb[0] = Q[fstride + off];
             fa[1] = Q[2 * fstride + off]; fb[1] = make_double2(0.0, 0.0);
@@ -152,12 +154,12 @@ __global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
         }
         const double2* r = res + (size_t)z * CA + l;
         if (rot) {
-            const double2 z0 = r[0], z1 = r[TL], z2 = r[2 * TL], z3 = r[3 * TL], z4 = r[4 * TL];
-            const double u = z0.x, v = z0.y, w = z1.x, uy = z1.y, wy = z2.x, vx = z2.y, wx = z3.x, uz = z3.y, vz = z4.x;
+            const double2 z0 = r[0], z1 = r[TL], z2 = r[2 * TL];
+            const double u = z0.x, v = z0.y, w = z1.x;
             const double ut = u + U, vt = v - p.Vsuck, wt = w + W;
-            const double ox = (wy + Wy) - vz;
-            const double oy = uz - wx;
-            const double oz = vx - (uy + Uy);
+            const double ox = z1.y + Wy;   // curl of the total velocity: the base flow adds (W', 0, -U')
+            const double oy = z2.x;
+            const double oz = z2.y - Uy;
             double fx = oy * wt - oz * vt;
             double fy = oz * ut - ox * wt;
             const double fz = ox * vt - oy * ut;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ z pass, warp-private FFTs
-// Same work as zpass_kernel for Nz <= 512: every complex transform (5 inverse + 2 forward per x-line for the rotational
+// Same work as zpass_kernel for Nz <= 512: every complex transform (3 inverse + 2 forward per x-line for the rotational
 // form) is owned by ONE warp and runs in place in its own skewed shared-memory line without block barriers
 // (fft_smem.cuh: warp_fft); the CTA only synchronises between pack / inverse / pointwise / forward / store.
 // grid = (ceil(Nx/TL), nyn), block = 32 * npair * TL threads.  NZ = Nz (power of two, compile-time FFT plan).
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(320, 2) zpass_warp_kernel(const ZPassParams p)
     const int Nx = p.Nx, Nz = NZ, TL = p.TL;
     const int nkz = p.Kz + 1;
     const bool rot = p.mode == ZP_ROTATIONAL;
-    const int npair = rot ? 5 : 2;
+    const int npair = rot ? 3 : 2;
     const int njobs = npair * TL;           // job j = q * TL + l : transform q of line l
     const int NP = fft_skew_len(Nz);
     double2* buf = dyn_smem<double2>();     // [njobs][NP]
@@ -241,21 +243,15 @@ __global__ void __launch_bounds__(320, 2) zpass_warp_kernel(const ZPassParams p)
     for (int idx = tid; idx < TL * nkz; idx += NT) {
         const int l = idx / nkz, k = idx - l * nkz;
         const int nx = nx0 + l;
-        double2 fa[5], fb[5];
+        double2 fa[3], fb[3];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) fa[q] = fb[q] = make_double2(0.0, 0.0);
+        for (int q = 0; q < 3; ++q) fa[q] = fb[q] = make_double2(0.0, 0.0);
         if (nx < Nx) {
             const size_t off = (size_t)nx * nkz + k;
             if (rot) {
-                const double2 u = Q[off], v = Q[fstride + off], w = Q[2 * fstride + off];
-                const double2 uy = Q[3 * fstride + off], wy = Q[4 * fstride + off];
-                const double2 vx = Q[5 * fstride + off], wx = Q[6 * fstride + off];
-                const double kzz = TWO_PI * k / p.Lz;
-                fa[0] = u;  fb[0] = v;
-                fa[1] = w;  fb[1] = uy;
-                fa[2] = wy; fb[2] = vx;
-                fa[3] = wx; fb[3] = make_double2(-kzz * u.y, kzz * u.x);  // du/dz
-                fa[4] = make_double2(-kzz * v.y, kzz * v.x);              // dv/dz
+                fa[0] = Q[off];               fb[0] = Q[fstride + off];       // u, v
+                fa[1] = Q[2 * fstride + off]; fb[1] = Q[3 * fstride + off];   // w, omega_x
+                fa[2] = Q[4 * fstride + off]; fb[2] = Q[5 * fstride + off];   // omega_y, omega_z
             } else {
                 fa[0] = Q[off];               fb[0] = Q[fstride + off];
                 fa[1] = Q[2 * fstride + off];
@@ -263,7 +259,7 @@ __global__ void __launch_bounds__(320, 2) zpass_warp_kernel(const ZPassParams p)
         }
         const int ka = fft_skew(k), kb = fft_skew(k > 0 ? Nz - k : 0);
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
+        for (int q = 0; q < 3; ++q) {
             if (q >= npair) break;
             double2 a = fa[q], b = fb[q];
             if (k == 0) { a.y = 0.0; b.y = 0.0; }  // c2r ignores the imaginary part of the mean mode
@@ -293,12 +289,12 @@ __global__ void __launch_bounds__(320, 2) zpass_warp_kernel(const ZPassParams p)
         double2* r = buf + (size_t)l * NP + zs;
         const size_t js = (size_t)TL * NP;  // stride between transforms of one line
         if (rot) {
-            const double2 z0 = r[0], z1 = r[js], z2 = r[2 * js], z3 = r[3 * js], z4 = r[4 * js];
-            const double u = z0.x, v = z0.y, w = z1.x, uy = z1.y, wy = z2.x, vx = z2.y, wx = z3.x, uz = z3.y, vz = z4.x;
+            const double2 z0 = r[0], z1 = r[js], z2 = r[2 * js];
+            const double u = z0.x, v = z0.y, w = z1.x;
             const double ut = u + U, vt = v - p.Vsuck, wt = w + W;
-            const double ox = (wy + Wy) - vz;
-            const double oy = uz - wx;
-            const double oz = vx - (uy + Uy);
+            const double ox = z1.y + Wy;   // curl of the total velocity: the base flow adds (W', 0, -U')
+            const double oy = z2.x;
+            const double oz = z2.y - Uy;
             double fx = oy * wt - oz * vt;
             double fy = oz * ut - ox * wt;
             const double fz = ox * vt - oy * ut;
@@ -390,7 +386,7 @@ int xpass_forward_launch(const XPassParams& p, cudaStream_t stream) {
 template <int NZ>
 static int zpass_warp_launch(const ZPassParams& p0, cudaStream_t stream) {
     ZPassParams p = p0;
-    const int npair = p.mode == ZP_ROTATIONAL ? 5 : 2;
+    const int npair = p.mode == ZP_ROTATIONAL ? 3 : 2;
     // lines per CTA: small CTAs (one line = 5 warps at Nz = 512, four CTAs per SM) interleave their pack / FFT / store phases
     // better than fewer large ones (measured 4.17 -> 3.88 ms at 512x257x512)
     const size_t per_line = (size_t)npair * fft_skew_len(p.Nz) * sizeof(double2);
@@ -420,7 +416,7 @@ int zpass_launch(const ZPassParams& p, cudaStream_t stream) {
         case 512: return zpass_warp_launch<512>(p, stream);
         default: break;
     }
-    const int npair = p.mode == ZP_ROTATIONAL ? 5 : 2;
+    const int npair = p.mode == ZP_ROTATIONAL ? 3 : 2;
     const size_t smem = 2 * (size_t)p.Nz * npair * p.TL * sizeof(double2);
     static size_t configured = 0;
     auto kfn = zpass_kernel;

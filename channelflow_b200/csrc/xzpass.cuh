@@ -3,6 +3,9 @@
 // Intermediate ("pencil") arrays are compact: only the retained (de-aliased) modes are stored.
 //   P[f][ny][mxi][kz]   complex, mxi = 0..2Kx   (kx = 0..Kx, -Kx..-1), kz = 0..Kz   (x,z spectral, y physical)
 //   Q[f][ny][nx ][kz]   complex, nx  = 0..Nx-1                                       (x physical, z spectral)
+// Rotational form: the vorticity is formed in spectral space while the x-pass loads its operands
+// (w_x = dw/dy - i kz v, w_y = i kz u - i kx w, w_z = i kx v - du/dy), so six fields (u, curl u) go through the inverse
+// x and z passes -- three paired c2r transforms per line -- and three (f) come back.
 // Replaces FlowField::makePhysical_xz / makeSpectral_xz (flowfield.cpp:1850-1886) for the DNS path, the x/z
 // derivative factors of curl (diffops.cpp:2318-2332), cross (diffops.cpp:2588-2606), the Coriolis term and
 // base-flow handling of navierstokesNL (nse.cpp:28-36,63-88), zeroPaddedModes (flowfield.cpp:2235-2255; aliased
@@ -21,8 +24,11 @@ struct XPassParams {
     // inverse: nout outputs, each from src[out] with optional d/dx
     int nfields;          // fields this launch handles: output slots fsel[0..nfields)
     int fsel[9];
-    int src[9];           // indexed by output slot
-    int ddx[9];
+    // inverse pass, indexed by output slot:  out = op_a(P[src]) - op_b(P[srcb])   (srcb < 0: no second term);
+    // op: 0 identity, 1 d/dx = i 2 pi kx/Lx, 2 d/dz = i 2 pi kz/Lz  -- this is where curl u is formed (diffops.cpp:2318-2332)
+    int src[9], opa[9];
+    int srcb[9], opb[9];
+    double Lz;
     const double2* in;    // inverse: P (field stride Ny*nmx*nkz); forward: Q (field stride Ny*Nx*nkz)
     double2* out;         // inverse: Q ; forward: P
     int ny0, nyn;         // y range handled (physical slab)
