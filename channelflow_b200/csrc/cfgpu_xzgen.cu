@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(XG_THREADS) xgen_kernel(double2* __restrict__ 
         a[idx] = (mz0 + cc < Mz) ? base[(size_t)mx * Mz + mz0 + cc] : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    const double2* res = fft_smem<DIR>(a, b, plan, TZ, tid, XG_THREADS);
+    const double2* res = fft_smem<DIR>(a, b, plan, plan.tw, TZ, tid, XG_THREADS);
     for (int idx = tid; idx < Nx * TZ; idx += XG_THREADS) {
         const int mx = idx / TZ, cc = idx - mx * TZ;
         if (mz0 + cc < Mz) base[(size_t)mx * Mz + mz0 + cc] = res[idx];
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(XG_THREADS) zgen_c2r_kernel(double* __restrict
         if (k > 0 && 2 * k != Nz) A[(size_t)(Nz - k) * TP + pr] = make_double2(a.x + b.y, b.x - a.y);
     }
     __syncthreads();
-    const double2* res = fft_smem<+1>(A, B, plan, TP, tid, XG_THREADS);
+    const double2* res = fft_smem<+1>(A, B, plan, plan.tw, TP, tid, XG_THREADS);
     for (int idx = tid; idx < TP * Nz; idx += XG_THREADS) {
         const int pr = idx / Nz, z = idx - pr * Nz;
         const long la = l0 + 2 * pr, lb = la + 1;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(XG_THREADS) zgen_r2c_kernel(double* __restrict
         A[(size_t)z * TP + pr] = make_double2(x, y);
     }
     __syncthreads();
-    const double2* g = fft_smem<-1>(A, B, plan, TP, tid, XG_THREADS);
+    const double2* g = fft_smem<-1>(A, B, plan, plan.tw, TP, tid, XG_THREADS);
     const double hs = 0.5 * scale;
     for (int idx = tid; idx < TP * Mz; idx += XG_THREADS) {
         const int pr = idx / Mz, k = idx - pr * Mz;

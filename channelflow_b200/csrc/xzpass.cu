@@ -19,39 +19,56 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassPa
     const int nmx = 2 * Kx + 1, nkz = p.Kz + 1;
     double2* a = dyn_smem<double2>();
     double2* b = a + (size_t)Nx * TZ;
+    double2* tws = b + (size_t)Nx * TZ;  // twiddle table in shared memory
     const int tid = threadIdx.x;
     const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
     const int s = p.src[f], oa = p.opa[f], sb = p.srcb[f], ob = p.opb[f];
 
+    for (int t = tid; t < Nx; t += XZ_THREADS) tws[t] = __ldg(&p.plan.tw[t]);
     // zero the aliased rows Kx+1 .. Nx-Kx-1
     const int nzero = (Nx - nmx) * TZ;
     for (int idx = tid; idx < nzero; idx += XZ_THREADS) a[(Kx + 1) * TZ + idx] = make_double2(0.0, 0.0);
     const double2* __restrict__ in = p.in;
-    for (int idx = tid; idx < nmx * TZ; idx += XZ_THREADS) {
-        const int mxi = idx / TZ, c = idx - mxi * TZ;
-        const int kz = kz0 + c;
-        const int kx = mxi <= Kx ? mxi : mxi - nmx;
-        const int mx = kx >= 0 ? kx : Nx + kx;
-        double2 v = make_double2(0.0, 0.0);
-        if (kz < nkz) {
-            v = in[xpass_row_offset(p, s, yl, mxi, nkz) + kz];
+    // four rows per thread in flight: all loads are issued before the first use
+    for (int i0 = tid; i0 < nmx * TZ; i0 += 4 * XZ_THREADS) {
+        double2 va[4], vb[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int idx = i0 + h * XZ_THREADS;
+            const int mxi = idx / TZ, c = idx - mxi * TZ;
+            const int kz = kz0 + c;
+            va[h] = vb[h] = make_double2(0.0, 0.0);
+            if (idx < nmx * TZ && kz < nkz) {
+                va[h] = in[xpass_row_offset(p, s, yl, mxi, nkz) + kz];
+                if (sb >= 0) vb[h] = in[xpass_row_offset(p, sb, yl, mxi, nkz) + kz];
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int idx = i0 + h * XZ_THREADS;
+            if (idx >= nmx * TZ) break;
+            const int mxi = idx / TZ, c = idx - mxi * TZ;
+            const int kz = kz0 + c;
+            const int kx = mxi <= Kx ? mxi : mxi - nmx;
+            const int mx = kx >= 0 ? kx : Nx + kx;
+            double2 v = va[h];
             if (oa) {
                 const double k = oa == 1 ? TWO_PI * kx / p.Lx : TWO_PI * kz / p.Lz;
                 v = make_double2(-k * v.y, k * v.x);
             }
             if (sb >= 0) {
-                double2 w = in[xpass_row_offset(p, sb, yl, mxi, nkz) + kz];
+                double2 w = vb[h];
                 if (ob) {
                     const double k = ob == 1 ? TWO_PI * kx / p.Lx : TWO_PI * kz / p.Lz;
                     w = make_double2(-k * w.y, k * w.x);
                 }
                 v = make_double2(v.x - w.x, v.y - w.y);
             }
+            a[mx * TZ + c] = v;
         }
-        a[mx * TZ + c] = v;
     }
     __syncthreads();
-    const double2* res = fft_smem<+1>(a, b, p.plan, TZ, tid, XZ_THREADS);
+    const double2* res = fft_smem<+1>(a, b, p.plan, tws, TZ, tid, XZ_THREADS);
     double2* __restrict__ out = p.out + ((size_t)f * p.nyn + yl) * Nx * nkz;
     for (int idx = tid; idx < Nx * TZ; idx += XZ_THREADS) {
         const int nx = idx / TZ, c = idx - nx * TZ;
@@ -76,7 +93,7 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_forward_kernel(const XPassPa
         a[idx] = kz < nkz ? in[(size_t)nx * nkz + kz] : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    const double2* res = fft_smem<-1>(a, b, p.plan, TZ, tid, XZ_THREADS);
+    const double2* res = fft_smem<-1>(a, b, p.plan, p.plan.tw, TZ, tid, XZ_THREADS);
     double2* __restrict__ out = p.out;
     for (int idx = tid; idx < nmx * TZ; idx += XZ_THREADS) {
         const int mxi = idx / TZ, c = idx - mxi * TZ;
@@ -129,7 +146,7 @@ __global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
         }
     }
     __syncthreads();
-    double2* res = fft_smem<+1>(A, B, p.plan, CA, tid, NT);
+    double2* res = fft_smem<+1>(A, B, p.plan, p.plan.tw, CA, tid, NT);
     double2* other = (res == A) ? B : A;
 
     // pointwise stage
@@ -195,7 +212,7 @@ __global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
     }
     if (!rot) return;
     __syncthreads();
-    const double2* g = fft_smem<-1>(other, res, p.plan, CF, tid, NT);
+    const double2* g = fft_smem<-1>(other, res, p.plan, p.plan.tw, CF, tid, NT);
 
     double2* __restrict__ F = p.F + (size_t)yl * Nx * nkz;
     const double sc = p.scale, hs = 0.5 * p.scale;
@@ -361,7 +378,7 @@ static int set_smem(const void* fn, size_t bytes, size_t& configured) {
 
 int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream) {
     const int nkz = p.Kz + 1;
-    const size_t smem = 2 * (size_t)p.Nx * p.TZ * sizeof(double2);
+    const size_t smem = (2 * (size_t)p.Nx * p.TZ + p.Nx) * sizeof(double2);
     static size_t configured = 0;
     auto kfn = xpass_inverse_kernel;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
