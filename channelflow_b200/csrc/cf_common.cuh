@@ -103,6 +103,17 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src));
 #endif
 }
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef CF_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {  // at most N committed groups still pending
+#ifndef CF_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async_wait_all() {
 #ifndef CF_EMU
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -115,6 +126,24 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #else
     (void)p;
+#endif
+}
+
+// ---- FP64 tensor-core MMA, the wide shape: D(16x8) += A(16x8, row) * B(8x8, col).  SASS: DMMA.16x8x8 ----
+// fragment layout (PTX ISA, mma.m16n8k8 .f64), g = lane/4, t = lane%4:
+//   a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4];  b0 = B[t][g], b1 = B[t+4][g];
+//   c0,c1 = C[g][2t + {0,1}], c2,c3 = C[g+8][2t + {0,1}]
+__device__ __forceinline__ void dmma_m16n8k8(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
+#ifdef CF_EMU
+    cfemu::dmma884(c[0], c[1], a[0], b[0]);
+    cfemu::dmma884(c[0], c[1], a[2], b[1]);
+    cfemu::dmma884(c[2], c[3], a[1], b[0]);
+    cfemu::dmma884(c[2], c[3], a[3], b[1]);
+#else
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 #endif
 }
 

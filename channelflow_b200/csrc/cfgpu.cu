@@ -92,7 +92,7 @@ int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out) {
     pl.No = N - pl.Ne;
     const int Nh = pl.Nh, Ne = pl.Ne, No = pl.No;
     auto r8 = [](int x) { return (x + 31) & ~31; };  // matrices are zero padded to whole 32-row warp tiles
-    auto r4 = [](int x) { return (x + 3) & ~3; };
+    auto r4 = [](int x) { return (x + 7) & ~7; };  // inner dimensions padded to whole k-steps of the 16x8x8 MMA
     pl.invMp = r8(Nh); pl.invK1p = r4(Ne); pl.invK2p = r4(No > 0 ? No : 1);
     pl.fwdMp = r8(Ne > No ? Ne : No); pl.fwdKp = r4(Nh);
 

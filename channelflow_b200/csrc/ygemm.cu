@@ -4,8 +4,9 @@
 // component and ALL Ny rows: it stages the even/odd (or sum/difference) operand tiles in shared memory once
 // (each HBM element is read exactly once, 512-byte runs; inverse mode uses cp.async so that the whole tile is in
 // flight at once), then its 8 warps -- 4 along the output rows, 2 along the columns -- each own a 32-row x (BN/2)-column
-// output tile of BOTH parity products (E and O accumulators in registers) and issue mma.sync.m8n8k4.f64 (SASS
-// DMMA.8x8x4): per k-step of 4 a warp loads 4 A fragments and BN/16 B fragments for 4*BN/16 DMMAs.  A fragments come
+// output tile of BOTH parity products (E and O accumulators in registers) and issue mma.sync.m16n8k8.f64 (SASS
+// DMMA.16x8x8, 8x fewer instructions than the legacy m8n8k4 shape): per k-step of 8 a warp loads 8 A and BN/8 B
+// fragment registers for BN/8 DMMAs.  A fragments come
 // from L1/L2 (the matrices are a few hundred KB, shared by every CTA) and are register double-buffered one k-step
 // ahead; B fragments come from shared memory (row pitch BN+4 doubles => conflict-free fragment loads).
 // A trailing remainder of at most 2 rows (Ny = 2^k+1 gives 32*m + 1 rows: the self-paired middle point / last
@@ -112,7 +113,6 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
     const int Mgemm = (rem >= 1 && rem <= 2) ? Mmax - rem : Mmax;  // rows done on the tensor pipe
     const int Mtiles = (Mgemm + 31) / 32;
     const int ncb = wn * (BN / 2);
-    const int nk1 = p.K1p / 4, nk2 = p.K2p / 4;
 
     for (int mi = 0; mi < job.nmat; ++mi) {
         const int mat = job.mat0 + mi;
@@ -122,81 +122,78 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
         const double sgn = p.sgn[mat];
         for (int mt = wm; mt < Mtiles; mt += 4) {
             const int row0 = mt * 32;
-            double e[4][NT][2], o[4][NT][2];
+            double e[2][NT][4], o[2][NT][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int t = 0; t < NT; ++t) e[i][t][0] = e[i][t][1] = o[i][t][0] = o[i][t][1] = 0.0;
-            {
-                const double* __restrict__ ap = A1 + (size_t)(row0 + lr) * p.K1p + lk;
-                const double* __restrict__ bp = B1 + lk * LD + ncb + lr;
-                double a[4], an[4];
+                for (int t = 0; t < NT; ++t)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = __ldg(ap + (size_t)(8 * i) * p.K1p);
-                for (int ks = 0; ks < nk1; ++ks) {
-                    if (ks + 1 < nk1) {
+                    for (int q = 0; q < 4; ++q) e[i][t][q] = o[i][t][q] = 0.0;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) an[i] = __ldg(ap + (size_t)(8 * i) * p.K1p + 4 * (ks + 1));
+            for (int half = 0; half < 2; ++half) {
+                const double* __restrict__ A = half ? A2 : A1;
+                const int Kp = half ? p.K2p : p.K1p;
+                const double* __restrict__ ap = A + (size_t)(row0 + lr) * Kp + lk;
+                const double* __restrict__ bp = (half ? B2 : B1) + lk * LD + ncb + lr;
+                const int nk = Kp / 8;
+                // A fragments of one k-step: [row block i][a0..a3] = rows lr / lr+8 of block i, columns lk / lk+4
+                double a[2][4], an[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) a[i][q] = __ldg(ap + (size_t)(16 * i + 8 * (q & 1)) * Kp + 4 * (q >> 1));
+                for (int ks = 0; ks < nk; ++ks) {
+                    if (ks + 1 < nk) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                an[i][q] = __ldg(ap + (size_t)(16 * i + 8 * (q & 1)) * Kp + 4 * (q >> 1) + 8 * (ks + 1));
                     }
-                    double b[NT];
+                    double b[NT][2];
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) b[t] = bp[(4 * ks) * LD + t * 8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int t = 0; t < NT; ++t) dmma_m8n8k4(e[i][t][0], e[i][t][1], a[i], b[t]);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) a[i] = an[i];
-                }
-            }
-            {
-                const double* __restrict__ ap = A2 + (size_t)(row0 + lr) * p.K2p + lk;
-                const double* __restrict__ bp = B2 + lk * LD + ncb + lr;
-                double a[4], an[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = __ldg(ap + (size_t)(8 * i) * p.K2p);
-                for (int ks = 0; ks < nk2; ++ks) {
-                    if (ks + 1 < nk2) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) an[i] = __ldg(ap + (size_t)(8 * i) * p.K2p + 4 * (ks + 1));
+                    for (int t = 0; t < NT; ++t) {
+                        b[t][0] = bp[(8 * ks) * LD + t * 8];
+                        b[t][1] = bp[(8 * ks + 4) * LD + t * 8];
                     }
-                    double b[NT];
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) b[t] = bp[(4 * ks) * LD + t * 8];
+                    for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                        for (int t = 0; t < NT; ++t) {
+                            if (half) dmma_m16n8k8(o[i][t], a[i], b[t]);
+                            else dmma_m16n8k8(e[i][t], a[i], b[t]);
+                        }
 #pragma unroll
-                        for (int t = 0; t < NT; ++t) dmma_m8n8k4(o[i][t][0], o[i][t][1], a[i], b[t]);
+                    for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) a[i] = an[i];
+                        for (int q = 0; q < 4; ++q) a[i][q] = an[i][q];
                 }
             }
 
-            // epilogue: c fragment = C[lr][2*lk + {0,1}]
+            // epilogue: c0,c1 = C[lr][2*lk + {0,1}], c2,c3 = C[lr+8][..] of each 16-row block
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = row0 + i * 8 + lr;
+            for (int i = 0; i < 2; ++i) {
 #pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    const int cc = ncb + t * 8 + 2 * lk;
-                    const long off = cout[cc];
-                    if (off < 0 || r >= Mgemm) continue;
-                    if (p.mode == 0) {
-                        if (r < p.M) {
-                            const double E0 = e[i][t][0], E1 = e[i][t][1], O0 = o[i][t][0], O1 = o[i][t][1];
-                            *reinterpret_cast<double2*>(&out[(long)r * p.out_ld + off]) = make_double2(E0 + O0, E1 + O1);
-                            const int rr = Nb - r;
-                            if (rr != r)
-                                *reinterpret_cast<double2*>(&out[(long)rr * p.out_ld + off]) =
-                                    make_double2(sgn * (E0 - O0), sgn * (E1 - O1));
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int r = row0 + i * 16 + hh * 8 + lr;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const int cc = ncb + t * 8 + 2 * lk;
+                        const long off = cout[cc];
+                        if (off < 0 || r >= Mgemm) continue;
+                        const double E0 = e[i][t][2 * hh], E1 = e[i][t][2 * hh + 1], O0 = o[i][t][2 * hh], O1 = o[i][t][2 * hh + 1];
+                        if (p.mode == 0) {
+                            if (r < p.M) {
+                                *reinterpret_cast<double2*>(&out[(long)r * p.out_ld + off]) = make_double2(E0 + O0, E1 + O1);
+                                const int rr = Nb - r;
+                                if (rr != r)
+                                    *reinterpret_cast<double2*>(&out[(long)rr * p.out_ld + off]) =
+                                        make_double2(sgn * (E0 - O0), sgn * (E1 - O1));
+                            }
+                        } else {
+                            if (r < p.M) *reinterpret_cast<double2*>(&out[(long)(2 * r) * p.out_ld + off]) = make_double2(E0, E1);
+                            if (r < p.M2) *reinterpret_cast<double2*>(&out[(long)(2 * r + 1) * p.out_ld + off]) = make_double2(O0, O1);
                         }
-                    } else {
-                        if (r < p.M)
-                            *reinterpret_cast<double2*>(&out[(long)(2 * r) * p.out_ld + off]) =
-                                make_double2(e[i][t][0], e[i][t][1]);
-                        if (r < p.M2)
-                            *reinterpret_cast<double2*>(&out[(long)(2 * r + 1) * p.out_ld + off]) =
-                                make_double2(o[i][t][0], o[i][t][1]);
                     }
                 }
             }
