@@ -257,32 +257,43 @@ __global__ void __launch_bounds__(320, 2) zpass_warp_kernel(const ZPassParams p)
         buf[(size_t)j * NP + fft_skew(k)] = make_double2(0.0, 0.0);
     }
     const double2* __restrict__ Q = p.Q + (size_t)yl * Nx * nkz;
-    for (int idx = tid; idx < TL * nkz; idx += NT) {
-        const int l = idx / nkz, k = idx - l * nkz;
-        const int nx = nx0 + l;
-        double2 fa[3], fb[3];
+    // two (line, kz) items per thread in flight: all loads are issued before the first use
+    for (int i0 = tid; i0 < TL * nkz; i0 += 2 * NT) {
+        double2 fa[2][3], fb[2][3];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) fa[q] = fb[q] = make_double2(0.0, 0.0);
-        if (nx < Nx) {
-            const size_t off = (size_t)nx * nkz + k;
-            if (rot) {
-                fa[0] = Q[off];               fb[0] = Q[fstride + off];       // u, v
-                fa[1] = Q[2 * fstride + off]; fb[1] = Q[3 * fstride + off];   // w, omega_x
-                fa[2] = Q[4 * fstride + off]; fb[2] = Q[5 * fstride + off];   // omega_y, omega_z
-            } else {
-                fa[0] = Q[off];               fb[0] = Q[fstride + off];
-                fa[1] = Q[2 * fstride + off];
+        for (int h = 0; h < 2; ++h) {
+            const int idx = i0 + h * NT;
+            const int l = idx / nkz, k = idx - l * nkz;
+            const int nx = nx0 + l;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) fa[h][q] = fb[h][q] = make_double2(0.0, 0.0);
+            if (idx < TL * nkz && nx < Nx) {
+                const size_t off = (size_t)nx * nkz + k;
+                if (rot) {
+                    fa[h][0] = Q[off];               fb[h][0] = Q[fstride + off];       // u, v
+                    fa[h][1] = Q[2 * fstride + off]; fb[h][1] = Q[3 * fstride + off];   // w, omega_x
+                    fa[h][2] = Q[4 * fstride + off]; fb[h][2] = Q[5 * fstride + off];   // omega_y, omega_z
+                } else {
+                    fa[h][0] = Q[off];               fb[h][0] = Q[fstride + off];
+                    fa[h][1] = Q[2 * fstride + off];
+                }
             }
         }
-        const int ka = fft_skew(k), kb = fft_skew(k > 0 ? Nz - k : 0);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            if (q >= npair) break;
-            double2 a = fa[q], b = fb[q];
-            if (k == 0) { a.y = 0.0; b.y = 0.0; }  // c2r ignores the imaginary part of the mean mode
-            double2* line = buf + (size_t)(q * TL + l) * NP;
-            line[ka] = make_double2(a.x - b.y, a.y + b.x);
-            if (k > 0) line[kb] = make_double2(a.x + b.y, b.x - a.y);
+        for (int h = 0; h < 2; ++h) {
+            const int idx = i0 + h * NT;
+            if (idx >= TL * nkz) break;
+            const int l = idx / nkz, k = idx - l * nkz;
+            const int ka = fft_skew(k), kb = fft_skew(k > 0 ? Nz - k : 0);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (q >= npair) break;
+                double2 a = fa[h][q], b = fb[h][q];
+                if (k == 0) { a.y = 0.0; b.y = 0.0; }  // c2r ignores the imaginary part of the mean mode
+                double2* line = buf + (size_t)(q * TL + l) * NP;
+                line[ka] = make_double2(a.x - b.y, a.y + b.x);
+                if (k > 0) line[kb] = make_double2(a.x + b.y, b.x - a.y);
+            }
         }
     }
     __syncthreads();
@@ -404,11 +415,11 @@ template <int NZ>
 static int zpass_warp_launch(const ZPassParams& p0, cudaStream_t stream) {
     ZPassParams p = p0;
     const int npair = p.mode == ZP_ROTATIONAL ? 3 : 2;
-    // lines per CTA: small CTAs (one line = 5 warps at Nz = 512, four CTAs per SM) interleave their pack / FFT / store phases
-    // better than fewer large ones (measured 4.17 -> 3.88 ms at 512x257x512)
+    // lines per CTA: small CTAs (two lines = 6 warps at Nz = 512, three CTAs per SM) interleave their pack / FFT / store
+    // phases better than fewer large ones (measured at 512x257x512: 1 line 2.83 ms, 2 lines 2.75 ms, 3 lines 2.97 ms)
     const size_t per_line = (size_t)npair * fft_skew_len(p.Nz) * sizeof(double2);
     int TL = 1;
-    const size_t cap = (size_t)(getenv("CF_ZP_SMEM_KB") ? atoi(getenv("CF_ZP_SMEM_KB")) : 50) * 1024;
+    const size_t cap = (size_t)(getenv("CF_ZP_SMEM_KB") ? atoi(getenv("CF_ZP_SMEM_KB")) : 60) * 1024;
     while (TL < 8 && (size_t)(TL + 1) * per_line <= cap && npair * (TL + 1) <= 10 && TL + 1 <= p.Nx) ++TL;
     p.TL = TL;
     const size_t smem = (size_t)TL * per_line + (size_t)p.Nz * sizeof(double2);
