@@ -130,6 +130,32 @@ int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out) {
             else Fo[(size_t)(n / 2) * pl.fwdKp + j] = v;
         }
     }
+    // GD = (d/dy on coefficients, chebyshev.cpp:672-697) o (forward transform): physical profile -> coefficients of its
+    // y-derivative, used by the divergence / skew-symmetric forms (diffops.cpp:2540-2549, 3266-3277)
+    std::vector<double> GDe[2], GDo[2];
+    {
+        std::vector<long double> Ff((size_t)N * N), GD((size_t)N * N, 0.0L);
+        for (int n = 0; n < N; ++n) {
+            const long double wn = ((n == 0 || n == Nb) ? 0.5L : 1.0L) / (long double)Nb;
+            for (int j = 0; j < N; ++j) Ff[(size_t)n * N + j] = wn * ((j == 0 || j == Nb) ? 1.0L : 2.0L) * C[(size_t)j * N + n];
+        }
+        for (int n = 0; n < N; ++n)
+            for (int m = n + 1; m < N; m += 2) {
+                const long double dm = scale * (long double)m * (n == 0 ? 0.5L : 1.0L);
+                for (int j = 0; j < N; ++j) GD[(size_t)n * N + j] += dm * Ff[(size_t)m * N + j];
+            }
+        for (int h = 0; h < 2; ++h) {
+            const long double cf = h ? 0.5L : 1.0L;
+            GDe[h].assign((size_t)pl.fwdMp * pl.fwdKp, 0.0);
+            GDo[h].assign((size_t)pl.fwdMp * pl.fwdKp, 0.0);
+            for (int n = 0; n < N; ++n)
+                for (int j = 0; j < Nh; ++j) {
+                    const bool mid = (2 * j == Nb);
+                    if (n % 2 == 0) { if (!mid) GDe[h][(size_t)(n / 2) * pl.fwdKp + j] = (double)(cf * GD[(size_t)n * N + j]); }
+                    else GDo[h][(size_t)(n / 2) * pl.fwdKp + j] = (double)(cf * GD[(size_t)n * N + j]);
+                }
+        }
+    }
     // Gram weights <T_m,T_n> (chebyshev.cpp:758-802), FP64 arithmetic (the reference's int version overflows for Ny > 215)
     std::vector<double> W((size_t)N * N, 0.0);
     for (int m = 0; m < N; ++m)
@@ -139,6 +165,7 @@ int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out) {
         }
     CF_TRY(upload(Ce, &pl.Ce)); CF_TRY(upload(Co, &pl.Co)); CF_TRY(upload(CDe, &pl.CDe)); CF_TRY(upload(CDo, &pl.CDo));
     CF_TRY(upload(Fe, &pl.Fe)); CF_TRY(upload(Fo, &pl.Fo)); CF_TRY(upload(W, &pl.Wgram));
+    for (int h = 0; h < 2; ++h) { CF_TRY(upload(GDe[h], &pl.GDe[h])); CF_TRY(upload(GDo[h], &pl.GDo[h])); }
     auto res = ctx->yplans.emplace(key, pl);
     *out = &res.first->second;
     return 0;
@@ -277,6 +304,7 @@ int cfgpu_finalize(cfgpu_ctx ctx) {
     for (auto& kv : ctx->yplans) {
         YPlan& p = kv.second;
         cudaFree(p.Ce); cudaFree(p.Co); cudaFree(p.CDe); cudaFree(p.CDo); cudaFree(p.Fe); cudaFree(p.Fo); cudaFree(p.Wgram);
+        for (int h = 0; h < 2; ++h) { cudaFree(p.GDe[h]); cudaFree(p.GDo[h]); }
     }
     for (auto& kv : ctx->fftplans) cudaFree(kv.second.tw);
     for (auto& kv : ctx->boxes) cudaFree(kv.second.runstart_full);

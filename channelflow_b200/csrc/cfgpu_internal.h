@@ -23,6 +23,9 @@ struct YPlan {
     int invMp = 0, invK1p = 0, invK2p = 0;
     int fwdMp = 0, fwdKp = 0;
     double *Ce = nullptr, *Co = nullptr, *CDe = nullptr, *CDo = nullptr, *Fe = nullptr, *Fo = nullptr;
+    // forward transform followed by d/dy of the coefficients: even rows act on the difference tile, odd rows on the sum
+    // tile ([0]: times 1, [1]: times 1/2 for the skew-symmetric form)
+    double *GDe[2] = {nullptr, nullptr}, *GDo[2] = {nullptr, nullptr};
     double* Wgram = nullptr;  // [N][N] Chebyshev Gram weights for the L2 norms
 };
 

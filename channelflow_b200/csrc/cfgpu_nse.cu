@@ -1,6 +1,7 @@
 // NSE operator entry points of the C-ABI (include/cfgpu.h): nonlinear term pipeline, batched tau solve,
 // linear term, CFL.  Host orchestration only; the kernels are in ygemm.cu, xzpass.cu, tau.cu.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -317,11 +318,138 @@ int cfgpu_nse_reset_lambda(cfgpu_nse nse, const double* lambda_t_h, int nsub) {
     return 0;
 }
 
+// Convection / divergence / skew-symmetric forms through the compact-pencil pipeline (single GPU, power-of-two Nz):
+//   y-GEMM (u and du/dy) -> x-pass (+ d/dx, d/dz factors) -> z-pass (c2r, u.grad u and/or the products u_i u_j, r2c,
+//   d/dz of u_i w) -> x-pass (+ d/dx of u_i u) -> y-GEMM (+ d/dy of u_i v through the derivative matrices GD).
+// method: 1 convection (dotgrad, diffops.cpp:3586-3643), 2 divergence (:3110-3134), 3 skew-symmetric (:3142-3286)
+static int nonlinear_fused_general(cfgpu_nse nse, cfgpu_field u, cfgpu_field f, int method) {
+    cfgpu_ctx ctx = nse->ctx;
+    const YPlan* yp;
+    const ModeBox* bx;
+    const FftPlanDev *fx, *fz;
+    CF_TRY(get_yplan(ctx, nse->Ny, nse->a, nse->b, &yp));
+    CF_TRY(get_box(ctx, nse->Nx, nse->Nz, nse->Kx, nse->Kz, &bx));
+    CF_TRY(get_fftplan(ctx, nse->Nx, &fx));
+    CF_TRY(get_fftplan(ctx, nse->Nz, &fz));
+    const bool grad = method != 2, prod = method != 1;
+    const double cc = method == 1 ? 1.0 : (method == 3 ? 0.5 : 0.0), cd = method == 2 ? 1.0 : (method == 3 ? 0.5 : 0.0);
+    const int nmx = 2 * nse->Kx + 1, nkz = nse->Kz + 1;
+    const size_t Pf = (size_t)nse->Ny * nmx * nkz * 2, Qf = (size_t)nse->Ny * nse->Nx * nkz * 2;
+    CF_TRY(ws_reserve(ctx->ws_P, 6 * Pf * sizeof(double)));
+    CF_TRY(ws_reserve(ctx->ws_Q, 12 * Qf * sizeof(double)));
+    double* P = ctx->ws_P.ptr;
+
+    {   // inverse y: u_i and (if needed) du_i/dy at the Gauss-Lobatto points
+        YGemmParams p;
+        memset(&p, 0, sizeof p);
+        p.N = nse->Ny; p.mode = 0;
+        p.M = p.M2 = yp->Nh; p.K1 = yp->Ne; p.K2 = yp->No; p.K1p = yp->invK1p; p.K2p = yp->invK2p;
+        p.A1[0] = yp->Ce; p.A2[0] = yp->Co; p.sgn[0] = 1.0;
+        p.A1[1] = yp->CDe; p.A2[1] = yp->CDo; p.sgn[1] = -1.0;
+        p.ncols = (long)nmx * nkz * 2;
+        p.in_runlen = 2 * nkz; p.in_runstart = bx->runstart_full; p.in_ld = u->rowstride();
+        p.out_runlen = 1; p.out_runstart = nullptr; p.out_ld = (long)nmx * nkz * 2;
+        p.njobs = 3;
+        for (int i = 0; i < 3; ++i) {
+            p.job[i].in = u->d + i * u->compstride();
+            p.job[i].out[0] = P + i * Pf;
+            p.job[i].out[1] = P + (3 + i) * Pf;
+            p.job[i].nmat = grad ? 2 : 1; p.job[i].mat0 = 0;
+        }
+        StageTimer _t(ctx, 0);
+        CF_TRY(ygemm_launch(p, ctx->stream));
+    }
+    XPassParams xp;
+    memset(&xp, 0, sizeof xp);
+    xp.Nx = nse->Nx; xp.Ny = nse->Ny; xp.Kx = nse->Kx; xp.Kz = nse->Kz;
+    xp.TZ = pick_TZ(nse->Nx);
+    xp.Lx = nse->Lx; xp.Lz = nse->Lz;
+    xp.plan = *fx;
+    xp.ny0 = 0; xp.nyn = nse->Ny;
+    {   // inverse x: Q = u (3), du/dy (3), du/dx (3), du/dz (3)
+        xp.in = reinterpret_cast<const double2*>(P);
+        xp.out = reinterpret_cast<double2*>(ctx->ws_Q.ptr);
+        fill_xsplit(nse, xp, grad ? 6 : 3);
+        xp.nfields = grad ? 12 : 3;
+        for (int i = 0; i < 12; ++i) {
+            xp.fsel[i] = i;
+            xp.src[i] = i < 6 ? i : i % 3;
+            xp.opa[i] = i < 6 ? 0 : (i < 9 ? 1 : 2);
+            xp.srcb[i] = -1; xp.opb[i] = 0;
+        }
+        StageTimer _t(ctx, 1);
+        CF_TRY(xpass_inverse_launch(xp, ctx->stream));
+    }
+    {
+        ZPassParams zp;
+        CF_TRY(fill_zpass(nse, zp, method == 1 ? ZP_CONVECTION : (method == 2 ? ZP_DIVERGENCE : ZP_SKEW)));
+        zp.cc = cc; zp.cd = cd;
+        zp.cfl_max = nullptr;
+        StageTimer _t(ctx, 2);
+        CF_TRY(zpass_launch(zp, ctx->stream));
+    }
+    {   // forward x: H_i = FFT(G_i) + cd d/dx FFT(u_i u)  and  C_i = FFT(u_i v)
+        xp.in = reinterpret_cast<const double2*>(ctx->ws_Q.ptr);
+        xp.out = reinterpret_cast<double2*>(P);
+        fill_xsplit(nse, xp, prod ? 6 : 3);
+        xp.nfields = prod ? 6 : 3;
+        xp.cb = cd;
+        const int t1src[3] = {4, 6, 7};  // u v, v v, v w
+        for (int i = 0; i < 6; ++i) {
+            xp.fsel[i] = i;
+            xp.src[i] = i < 3 ? i : t1src[i - 3];
+            xp.srcb[i] = (prod && i < 3) ? 3 + i : -1;
+            xp.opb[i] = 1;
+        }
+        if (prod) xp.TZ = xp.TZ > 1 ? xp.TZ / 2 : 1;
+        StageTimer _t(ctx, 3);
+        CF_TRY(xpass_forward_launch(xp, ctx->stream));
+    }
+    if (!(f->clean_Kx >= 0 && f->clean_Kx <= nse->Kx && f->clean_Kz >= 0 && f->clean_Kz <= nse->Kz))
+        CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), ctx->stream));
+    {   // forward y: f_i = F H_i + GD C_i
+        YGemmParams p;
+        memset(&p, 0, sizeof p);
+        p.N = nse->Ny; p.mode = 1;
+        p.M = yp->Ne; p.M2 = yp->No; p.K1 = p.K2 = yp->Nh; p.K1p = p.K2p = yp->fwdKp;
+        p.A1[0] = yp->Fe; p.A2[0] = yp->Fo; p.sgn[0] = 1.0;
+        p.A1b = yp->GDe[cd == 0.5 ? 1 : 0]; p.A2b = yp->GDo[cd == 0.5 ? 1 : 0];
+        p.ncols = (long)nmx * nkz * 2;
+        p.in_runlen = 1; p.in_runstart = nullptr; p.in_ld = (long)nmx * nkz * 2;
+        p.out_runlen = 2 * nkz; p.out_runstart = bx->runstart_full; p.out_ld = f->rowstride();
+        p.njobs = 3;
+        for (int i = 0; i < 3; ++i) {
+            p.job[i].in = P + i * Pf;
+            p.job[i].in2 = prod ? P + (3 + i) * Pf : nullptr;
+            p.job[i].out[0] = f->d + i * f->compstride();
+            p.job[i].nmat = 1; p.job[i].mat0 = 0;
+        }
+        StageTimer _t(ctx, 4);
+        CF_TRY(ygemm_launch(p, ctx->stream));
+    }
+    f->xzstate = CFGPU_SPECTRAL; f->ystate = CFGPU_SPECTRAL;
+    f->clean_Kx = nse->Kx; f->clean_Kz = nse->Kz;
+    if (nse->cfg.dealias_xz) f->padded = 1;
+    return 0;
+}
+
 // Convection / Divergence / SkewSymmetric / Alternating / LinearAboutProfile (nse.cpp:12-91 -> diffops.cpp): the
 // reference's own sequence on scratch copies (u itself is never modified), generic full-grid transforms in between.
 static int nonlinear_generic(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     cfgpu_ctx ctx = nse->ctx;
     CF_ARG(ctx->comm.nranks == 1, "only the rotational nonlinearity is distributed over several GPUs in this build");
+    {
+        const int method = nse->cfg.nonlinearity;
+        if (method >= 1 && method <= 5 && zpass_general_supported(nse->Nz) && !getenv("CFGPU_UNFUSED_NL")) {
+            // fused pipeline, unless the form/rotation combination is one of the reference's quirks reproduced below
+            const int m = method == 4 ? 2 : (method == 5 ? 1 : method);
+            if (nse->cfg.rotation == 0.0 || m == 3) {
+                if (method == 4) nse->cfg.nonlinearity = 5;
+                else if (method == 5) nse->cfg.nonlinearity = 4;
+                return nonlinear_fused_general(nse, u, f, m);
+            }
+        }
+    }
     if (!nse->s_u) CF_TRY(cfgpu_field_create(ctx, nse->Nx, nse->Ny, nse->Nz, 3, nse->Lx, nse->Lz, nse->a, nse->b, &nse->s_u));
     cfgpu_field su = nse->s_u;
     FieldGeom g{nse->Nx, nse->Ny, nse->Nz, nse->Lx, nse->Lz, nse->a, nse->b};
@@ -404,7 +532,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     xp.out = reinterpret_cast<double2*>(multi ? ctx->ws_S.ptr : ctx->ws_P.ptr);
     xp.ny0 = nse->y0; xp.nyn = nse->y1 - nse->y0;
     fill_xsplit(nse, xp, 3);
-    for (int i = 0; i < 3; ++i) xp.fsel[i] = i;
+    for (int i = 0; i < 3; ++i) { xp.fsel[i] = i; xp.src[i] = i; xp.srcb[i] = -1; }
     if (!multi) {
         StageTimer _t(ctx, 3);
         CF_TRY(xpass_forward_launch(xp, ctx->stream));

@@ -11,6 +11,7 @@ namespace {
 constexpr int XZ_THREADS = 256;
 constexpr double TWO_PI = 6.283185307179586476925286766559;
 }  // namespace
+static int set_smem(const void* fn, size_t bytes, size_t& configured);
 
 // ------------------------------------------------------------------------------------------------ x inverse
 // grid = (ceil(nkz/TZ), nyn, nfields)   P[src][yl][mxi][kz] -> Q[f][yl][nx][kz], optional d/dx = i 2 pi kx / Lx
@@ -82,25 +83,34 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassPa
 __global__ void __launch_bounds__(XZ_THREADS) xpass_forward_kernel(const XPassParams p) {
     const int Nx = p.Nx, Kx = p.Kx, TZ = p.TZ;
     const int nmx = 2 * Kx + 1, nkz = p.Kz + 1;
-    double2* a = dyn_smem<double2>();
-    double2* b = a + (size_t)Nx * TZ;
     const int tid = threadIdx.x;
     const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
-    const double2* __restrict__ in = p.in + ((size_t)f * p.nyn + yl) * Nx * nkz;
-    for (int idx = tid; idx < Nx * TZ; idx += XZ_THREADS) {
-        const int nx = idx / TZ, c = idx - nx * TZ;
-        const int kz = kz0 + c;
-        a[idx] = kz < nkz ? in[(size_t)nx * nkz + kz] : make_double2(0.0, 0.0);
+    const int sa = p.src[f], sb = p.srcb[f];
+    const int C = sb >= 0 ? 2 * TZ : TZ;  // columns: TZ of the first source, then TZ of the second
+    double2* a = dyn_smem<double2>();
+    double2* b = a + (size_t)Nx * C;
+    const double2* __restrict__ ina = p.in + ((size_t)sa * p.nyn + yl) * Nx * nkz;
+    const double2* __restrict__ inb = p.in + ((size_t)(sb >= 0 ? sb : 0) * p.nyn + yl) * Nx * nkz;
+    for (int idx = tid; idx < Nx * C; idx += XZ_THREADS) {
+        const int nx = idx / C, c = idx - nx * C;
+        const int kz = kz0 + (c < TZ ? c : c - TZ);
+        a[idx] = kz < nkz ? (c < TZ ? ina : inb)[(size_t)nx * nkz + kz] : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    const double2* res = fft_smem<-1>(a, b, p.plan, p.plan.tw, TZ, tid, XZ_THREADS);
-    double2* __restrict__ out = p.out;
+    const double2* res = fft_smem<-1>(a, b, p.plan, p.plan.tw, C, tid, XZ_THREADS);
     for (int idx = tid; idx < nmx * TZ; idx += XZ_THREADS) {
         const int mxi = idx / TZ, c = idx - mxi * TZ;
         const int kz = kz0 + c;
         const int kx = mxi <= Kx ? mxi : mxi - nmx;
         const int mx = kx >= 0 ? kx : Nx + kx;
-        if (kz < nkz) out[xpass_row_offset(p, f, yl, mxi, nkz) + kz] = res[mx * TZ + c];
+        if (kz >= nkz) continue;
+        double2 v = res[mx * C + c];
+        if (sb >= 0) {
+            const double2 w = res[mx * C + TZ + c];
+            const double k = p.cb * (p.opb[f] == 1 ? TWO_PI * kx / p.Lx : TWO_PI * kz / p.Lz);
+            v = make_double2(v.x - k * w.y, v.y + k * w.x);
+        }
+        p.out[xpass_row_offset(p, f, yl, mxi, nkz) + kz] = v;
     }
 }
 
@@ -378,6 +388,140 @@ __global__ void __launch_bounds__(320, 2) zpass_warp_kernel(const ZPassParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ z pass, other forms
+// Convection / divergence / skew-symmetric forms (see xzpass.cuh) for power-of-two Nz <= 512: one x-line per CTA, one
+// warp per complex transform (6 inverse c2r pairs for the 12 fields u, grad u; up to 5 forward pairs for u.grad u and
+// the 6 products u_i u_j).  grid = (Nx, nyn), block = 192 threads.
+template <int NZ>
+__global__ void __launch_bounds__(192, 2) zpass_general_kernel(const ZPassParams p) {
+    const int Nx = p.Nx, Nz = NZ;
+    const int nkz = p.Kz + 1;
+    const int mode = p.mode;
+    const bool need_grad = mode != ZP_DIVERGENCE, need_prod = mode != ZP_CONVECTION;
+    const int ninv = need_grad ? 6 : 2;
+    constexpr int NP = NZ + (NZ >> 3) + 1;
+    double2* buf = dyn_smem<double2>();  // [6][NP]
+    double2* tws = buf + 6 * NP;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
+    const int yl = blockIdx.y, ny = p.ny0 + yl, nx = blockIdx.x;
+    const size_t fstride = (size_t)p.nyn * Nx * nkz;
+
+    for (int t = tid; t < Nz; t += NT) tws[t] = __ldg(&p.plan.tw[t]);
+    const int nzero = Nz - 2 * nkz + 1;
+    for (int idx = tid; idx < nzero * ninv; idx += NT) {
+        const int j = idx / nzero, k = nkz + (idx - j * nzero);
+        buf[j * NP + fft_skew(k)] = make_double2(0.0, 0.0);
+    }
+    const double2* __restrict__ Q = p.Q + (size_t)yl * Nx * nkz + (size_t)nx * nkz;
+    for (int k = tid; k < nkz; k += NT) {
+        double2 q[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) q[i] = (i < 3 || need_grad) ? Q[i * fstride + k] : make_double2(0.0, 0.0);
+        const int ka = fft_skew(k), kb = fft_skew(k > 0 ? Nz - k : 0);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            if (j >= ninv) break;
+            double2 a = q[2 * j], b = (need_grad || j == 0) ? q[2 * j + 1] : make_double2(0.0, 0.0);
+            if (k == 0) { a.y = 0.0; b.y = 0.0; }
+            buf[j * NP + ka] = make_double2(a.x - b.y, a.y + b.x);
+            if (k > 0) buf[j * NP + kb] = make_double2(a.x + b.y, b.x - a.y);
+        }
+    }
+    __syncthreads();
+    for (int j = warp; j < ninv; j += NW) warp_fft_pow2<+1, NZ>(buf + j * NP, tws, lane);
+    __syncthreads();
+
+    double U = 0.0, Uy = 0.0, W = 0.0, Wy = 0.0;
+    if (p.Uy) {
+        U = p.Uy[ny];
+        Uy = p.Uy[p.Ny + ny];
+        W = p.Uy[2 * p.Ny + ny];
+        Wy = p.Uy[3 * p.Ny + ny];
+    }
+    for (int z = tid; z < Nz; z += NT) {
+        const int zs = fft_skew(z);
+        double v[3], g[3][3];  // g[i][j] = d u_i / d x_j
+        {
+            const double2 z0 = buf[zs], z1 = buf[NP + zs];
+            v[0] = z0.x + U; v[1] = z0.y - p.Vsuck; v[2] = z1.x + W;
+            if (need_grad) {
+                const double2 z2 = buf[2 * NP + zs], z3 = buf[3 * NP + zs], z4 = buf[4 * NP + zs], z5 = buf[5 * NP + zs];
+                g[0][1] = z1.y + Uy; g[1][1] = z2.x; g[2][1] = z2.y + Wy;   // d/dy of (u + U, v, w + W)
+                g[0][0] = z3.x; g[1][0] = z3.y; g[2][0] = z4.x;             // d/dx
+                g[0][2] = z4.y; g[1][2] = z5.x; g[2][2] = z5.y;             // d/dz
+            }
+        }
+        double c[3] = {0.0, 0.0, 0.0};
+        if (need_grad) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) s += p.cc * v[j] * g[i][j];
+                c[i] = s;
+            }
+            if (p.rotation != 0.0) {
+                c[0] -= p.rotation * v[1];
+                c[1] += p.rotation * v[0];
+            }
+        }
+        if (!need_prod) {
+            buf[zs] = make_double2(c[0], c[1]);
+            buf[NP + zs] = make_double2(c[2], 0.0);
+        } else {
+            buf[zs] = make_double2(c[0], c[1]);
+            buf[NP + zs] = make_double2(c[2], v[0] * v[0]);
+            buf[2 * NP + zs] = make_double2(v[0] * v[1], v[0] * v[2]);
+            buf[3 * NP + zs] = make_double2(v[1] * v[1], v[1] * v[2]);
+            buf[4 * NP + zs] = make_double2(v[2] * v[2], 0.0);
+        }
+    }
+    __syncthreads();
+    const int nfwd = need_prod ? 5 : 2;
+    for (int j = warp; j < nfwd; j += NW) warp_fft_pow2<-1, NZ>(buf + j * NP, tws, lane);
+    __syncthreads();
+
+    double2* __restrict__ F = p.F + (size_t)yl * Nx * nkz + (size_t)nx * nkz;
+    const double sc = p.scale;
+    for (int k = tid; k < nkz; k += NT) {
+        const int ks = fft_skew(k), kn = fft_skew(k == 0 ? 0 : Nz - k);
+        // transform j holds A + iB of two real lines: A_k = (g_k + conj g_{N-k})/2, B_k = (g_k - conj g_{N-k})/(2i)
+        double2 A[5], B[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            if (j >= nfwd) break;
+            const double2 gk = buf[j * NP + ks], gn = buf[j * NP + kn];
+            A[j] = make_double2(0.5 * sc * (gk.x + gn.x), 0.5 * sc * (gk.y - gn.y));
+            B[j] = make_double2(0.5 * sc * (gk.y + gn.y), -0.5 * sc * (gk.x - gn.x));
+        }
+        if (!need_prod) {
+            F[k] = A[0]; F[fstride + k] = B[0]; F[2 * fstride + k] = A[1];
+        } else {
+            // conv = A0, B0, A1 ; uu = B1, uv = A2, uw = B2, vv = A3, vw = B3, ww = A4
+            const double kzz = p.cd * TWO_PI * k / p.Lz;
+            const double2 cv[3] = {A[0], B[0], A[1]};
+            const double2 t2[3] = {B[2], B[3], A[4]};  // u_i w
+#pragma unroll
+            for (int i = 0; i < 3; ++i) F[i * fstride + k] = make_double2(cv[i].x - kzz * t2[i].y, cv[i].y + kzz * t2[i].x);
+            F[3 * fstride + k] = B[1]; F[4 * fstride + k] = A[2]; F[5 * fstride + k] = B[2];
+            F[6 * fstride + k] = A[3]; F[7 * fstride + k] = B[3];
+        }
+    }
+}
+
+template <int NZ>
+static int zpass_general_launch(const ZPassParams& p, cudaStream_t stream) {
+    const size_t smem = ((size_t)6 * (NZ + (NZ >> 3) + 1) + NZ) * sizeof(double2);
+    static size_t configured = 0;
+    auto kfn = zpass_general_kernel<NZ>;
+    CF_TRY(set_smem((const void*)kfn, smem, configured));
+    dim3 grid(p.Nx, p.nyn);
+    CF_LAUNCH(kfn, grid, dim3(192), smem, stream, p);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+bool zpass_general_supported(int Nz) { return Nz >= 16 && Nz <= 512 && (Nz & (Nz - 1)) == 0; }
+
 // ------------------------------------------------------------------------------------------------ launchers
 static int set_smem(const void* fn, size_t bytes, size_t& configured) {
     if (bytes > configured) {
@@ -401,7 +545,9 @@ int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream) {
 
 int xpass_forward_launch(const XPassParams& p, cudaStream_t stream) {
     const int nkz = p.Kz + 1;
-    const size_t smem = 2 * (size_t)p.Nx * p.TZ * sizeof(double2);
+    bool two = false;
+    for (int i = 0; i < p.nfields; ++i) two = two || p.srcb[p.fsel[i]] >= 0;
+    const size_t smem = 2 * (size_t)p.Nx * p.TZ * (two ? 2 : 1) * sizeof(double2);
     static size_t configured = 0;
     auto kfn = xpass_forward_kernel;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
@@ -435,6 +581,17 @@ static int zpass_warp_launch(const ZPassParams& p0, cudaStream_t stream) {
 }
 
 int zpass_launch(const ZPassParams& p, cudaStream_t stream) {
+    if (p.mode >= ZP_CONVECTION) {
+        switch (p.Nz) {
+            case 16: return zpass_general_launch<16>(p, stream);
+            case 32: return zpass_general_launch<32>(p, stream);
+            case 64: return zpass_general_launch<64>(p, stream);
+            case 128: return zpass_general_launch<128>(p, stream);
+            case 256: return zpass_general_launch<256>(p, stream);
+            case 512: return zpass_general_launch<512>(p, stream);
+            default: set_last_error("zpass: this nonlinear form needs a power-of-two Nz <= 512"); return 1;
+        }
+    }
     switch (p.Nz) {  // warp-private transforms for the power-of-two lengths
         case 16: return zpass_warp_launch<16>(p, stream);
         case 32: return zpass_warp_launch<32>(p, stream);

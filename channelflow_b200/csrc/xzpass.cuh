@@ -23,12 +23,14 @@ struct XPassParams {
     FftPlanDev plan;      // length Nx
     // inverse: nout outputs, each from src[out] with optional d/dx
     int nfields;          // fields this launch handles: output slots fsel[0..nfields)
-    int fsel[9];
+    int fsel[12];
     // inverse pass, indexed by output slot:  out = op_a(P[src]) - op_b(P[srcb])   (srcb < 0: no second term);
     // op: 0 identity, 1 d/dx = i 2 pi kx/Lx, 2 d/dz = i 2 pi kz/Lz  -- this is where curl u is formed (diffops.cpp:2318-2332)
-    int src[9], opa[9];
-    int srcb[9], opb[9];
+    int src[12], opa[12];
+    int srcb[12], opb[12];
     double Lz;
+    // forward pass, indexed by output slot:  out = FFT(Q[src]) + cb * op_b(FFT(Q[srcb]))  (srcb < 0: one source)
+    double cb;
     const double2* in;    // inverse: P (field stride Ny*nmx*nkz); forward: Q (field stride Ny*Nx*nkz)
     double2* out;         // inverse: Q ; forward: P
     int ny0, nyn;         // y range handled (physical slab)
@@ -48,7 +50,13 @@ __host__ __device__ inline size_t xpass_row_offset(const XPassParams& p, int f, 
 int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream);
 int xpass_forward_launch(const XPassParams& p, cudaStream_t stream);
 
-enum ZPassMode { ZP_ROTATIONAL = 0, ZP_CFL = 1 };
+// ZP_CONVECTION / ZP_DIVERGENCE / ZP_SKEW (zpass_general_kernel, power-of-two Nz <= 512):
+//   inputs  Q[0..2] = u,v,w; for convection and skew also Q[3..5] = d/dy, Q[6..8] = d/dx, Q[9..11] = d/dz of u,v,w
+//   outputs convection: F[0..2] = u_j d_j u_i;
+//           divergence / skew: F[0..2] = G_i = cc u_j d_j u_i + cd d/dz (u_i w), F[3..5] = u u, u v, u w, F[6..7] = v v, v w
+//   (u = total velocity incl. base flow; the x- and y-derivative parts of d_j (u_i u_j) are added by the forward x-pass
+//   and y-GEMM; diffops.cpp:3110-3134, 3142-3286, 3586-3643)
+enum ZPassMode { ZP_ROTATIONAL = 0, ZP_CFL = 1, ZP_CONVECTION = 2, ZP_DIVERGENCE = 3, ZP_SKEW = 4 };
 
 struct ZPassParams {
     int Nx, Ny, Nz, Kz;
@@ -57,6 +65,7 @@ struct ZPassParams {
     double Lx, Lz;
     double scale;         // 1/(Nx*Nz)
     double Vsuck, rotation;
+    double cc, cd;        // weights of the convective and divergence parts (1,0 / 0,1 / 1/2,1/2)
     FftPlanDev plan;      // length Nz
     const double2* Q;     // inputs  [nin][ny][nx][kz]
     double2* F;           // outputs [3][ny][nx][kz]
@@ -66,5 +75,6 @@ struct ZPassParams {
     int ny0, nyn;
 };
 int zpass_launch(const ZPassParams& p, cudaStream_t stream);
+bool zpass_general_supported(int Nz);
 
 }  // namespace cfgpu

@@ -25,12 +25,15 @@ template <int BN>
 __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams p) {
     constexpr int LD = BN + 4;
     constexpr int NT = BN / 16;   // 8-column n-tiles per warp (2 warps along the columns)
+    const YGemmJob& job = p.job[blockIdx.y];
+    const bool two = p.two_inputs != 0;  // launch-wide: second pair of tiles present in shared memory
     double* B1 = dyn_smem<double>();
     double* B2 = B1 + (size_t)p.K1p * LD;
-    long* cin = reinterpret_cast<long*>(B2 + (size_t)p.K2p * LD);
+    double* B1b = B2 + (size_t)p.K2p * LD;
+    double* B2b = B1b + (two ? (size_t)p.K1p * LD : 0);
+    long* cin = reinterpret_cast<long*>(B2b + (two ? (size_t)p.K2p * LD : 0));
     long* cout = cin + BN;
 
-    const YGemmJob& job = p.job[blockIdx.y];
     const int tid = threadIdx.x;
     const long c0 = (long)blockIdx.x * BN;
 
@@ -68,6 +71,10 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
         // forward: B1[j] = x[j] + x[Nb-j], B2[j] = x[j] - x[Nb-j]  (self-paired middle row: B1 = x, B2 = 0)
         const int HB = BN / 2;
         const int total = p.K1p * HB;
+        for (int which = 0; which < ((two && job.in2) ? 2 : 1); ++which) {
+        const double* __restrict__ in = which ? job.in2 : job.in;
+        double* B1 = which ? B1b : (dyn_smem<double>());
+        double* B2 = which ? B2b : (dyn_smem<double>() + (size_t)p.K1p * LD);
         for (int i0 = tid; i0 < total; i0 += 4 * YG_THREADS) {
             double2 a[4], b[4];
             int jj[4], cc[4];
@@ -102,6 +109,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
                 if (j < p.K2p) *reinterpret_cast<double2*>(&B2[j * LD + c]) = d;
             }
         }
+        }
     }
     __syncthreads();
 
@@ -129,12 +137,15 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
                 for (int t = 0; t < NT; ++t)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) e[i][t][q] = o[i][t][q] = 0.0;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const double* __restrict__ A = half ? A2 : A1;
-                const int Kp = half ? p.K2p : p.K1p;
+            const int nhalf = (two && job.in2 && p.mode == 1) ? 4 : 2;
+            for (int hq = 0; hq < nhalf; ++hq) {
+                // hq 0/1: even/odd products of the first input; hq 2/3: derivative matrices of the second input acting on
+                // its difference (-> even rows) / sum (-> odd rows) tiles
+                const int half = hq & 1;
+                const double* __restrict__ A = hq == 0 ? A1 : hq == 1 ? A2 : hq == 2 ? p.A1b : p.A2b;
+                const int Kp = hq == 1 ? p.K2p : p.K1p;
                 const double* __restrict__ ap = A + (size_t)(row0 + lr) * Kp + lk;
-                const double* __restrict__ bp = (half ? B2 : B1) + lk * LD + ncb + lr;
+                const double* __restrict__ bp = (hq == 0 ? B1 : hq == 1 ? B2 : hq == 2 ? B2b : B1b) + lk * LD + ncb + lr;
                 const int nk = Kp / 8;
                 // A fragments of one k-step: [row block i][a0..a3] = rows lr / lr+8 of block i, columns lk / lk+4
                 double a[2][4], an[2][4];
@@ -214,6 +225,18 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
 #pragma unroll 8
                 for (int k = 0; k < p.K2; ++k) O += __ldg(ar + k) * B2[k * LD + c];
             }
+            if (two && job.in2 && p.mode == 1) {
+                if (r < p.M) {
+                    const double* __restrict__ ar = p.A1b + (size_t)r * p.K1p;
+#pragma unroll 8
+                    for (int k = 0; k < p.K1; ++k) E += __ldg(ar + k) * B2b[k * LD + c];
+                }
+                if (r < p.M2) {
+                    const double* __restrict__ ar = p.A2b + (size_t)r * p.K1p;
+#pragma unroll 8
+                    for (int k = 0; k < p.K1; ++k) O += __ldg(ar + k) * B1b[k * LD + c];
+                }
+            }
             if (p.mode == 0) {
                 if (r < p.M) {
                     out[(long)r * p.out_ld + off] = E + O;
@@ -230,7 +253,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
 
 template <int BN>
 static int launch_bn(const YGemmParams& p, cudaStream_t stream) {
-    const size_t smem = (size_t)(p.K1p + p.K2p) * (BN + 4) * sizeof(double) + 2 * BN * sizeof(long);
+    const size_t smem = (size_t)(p.two_inputs ? 2 : 1) * (p.K1p + p.K2p) * (BN + 4) * sizeof(double) + 2 * BN * sizeof(long);
     auto kfn = ygemm_kernel<BN>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -243,13 +266,21 @@ static int launch_bn(const YGemmParams& p, cudaStream_t stream) {
     return 0;
 }
 
-int ygemm_launch(const YGemmParams& p, cudaStream_t stream) {
+int ygemm_launch(const YGemmParams& p0, cudaStream_t stream) {
+    YGemmParams p = p0;
     if (p.ncols <= 0 || p.njobs <= 0) return 0;
+    p.two_inputs = 0;
+    for (int j = 0; j < p.njobs; ++j)
+        if (p.job[j].in2) p.two_inputs = 1;
+    if (p.two_inputs && (p.mode != 1 || !p.A1b || !p.A2b)) {
+        set_last_error("ygemm: a second input needs the forward mode and the derivative matrices");
+        return 1;
+    }
     if ((p.in_runstart && (p.in_runlen & 1)) || (p.out_runstart && (p.out_runlen & 1)) || (p.in_ld & 1) || (p.out_ld & 1)) {
         set_last_error("ygemm: column runs must be (re,im) pairs");
         return 1;
     }
-    const size_t rows = (size_t)(p.K1p + p.K2p);
+    const size_t rows = (size_t)(p.K1p + p.K2p) * (p.two_inputs ? 2 : 1);
     const size_t limit = 220 * 1024;
     if (rows * 68 * 8 + 1024 <= limit) return launch_bn<64>(p, stream);
     if (rows * 36 * 8 + 512 <= limit) return launch_bn<32>(p, stream);

@@ -19,6 +19,8 @@ constexpr int YG_MAXMAT = 2;
 
 struct YGemmJob {
     const double* in;
+    const double* in2;   // forward mode only, may be null: second input whose y-DERIVATIVE coefficients are added to the
+                         // output (matrices A1b/A2b act on the swapped difference / sum tiles)
     double* out[YG_MAXMAT];
     int nmat;        // how many of the plan's matrices to apply to this input (inverse: 1 = value, 2 = value + d/dy)
     int mat0;        // first matrix index (inverse: 0 = value, 1 = derivative)
@@ -35,6 +37,8 @@ struct YGemmParams {
     const double* A1[YG_MAXMAT];  // [Mp x K1p] row major, Mp = M rounded up to 8, zero padded
     const double* A2[YG_MAXMAT];  // [Mp x K2p]
     double sgn[YG_MAXMAT];        // inverse: sign of the reflected row
+    const double* A1b;            // [Mp x K1p]: even output rows from the difference tile of in2
+    const double* A2b;            // [Mp x K1p]: odd output rows from the sum tile of in2
     long ncols;                   // number of (double) columns
     int in_runlen;                // column c lives at in_runstart[c / in_runlen] + c % in_runlen  (nullptr: identity)
     const long* in_runstart;
@@ -42,6 +46,7 @@ struct YGemmParams {
     int out_runlen;
     const long* out_runstart;
     long out_ld;
+    int two_inputs;               // some job has in2 (set by the launcher: doubles the operand tiles in shared memory)
     int njobs;
     YGemmJob job[YG_MAXJOB];
 };

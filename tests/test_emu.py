@@ -65,6 +65,24 @@ def test_nonlinear_methods(lib, nl, over):
     assert r["nonlinear"] < 1e-12, r
 
 
+POW2 = dict(parity.C1, Nx=16, Ny=17, Nz=16) if "emu" in __file__ else dict(parity.C1, Nx=64, Ny=49, Nz=64)
+
+
+@pytest.mark.parametrize("nl", ["conv", "div", "skew", "alt"])
+@pytest.mark.parametrize("over", [dict(), dict(rotation=0.1, Vsuck=0.0025, baseflow="suction"), dict(dealiasing="none")])
+def test_nonlinear_methods_fused(lib, nl, over):
+    """Power-of-two Nz: the fused compact-pencil pipeline for the convection / divergence / skew-symmetric forms."""
+    r = parity.nonlinear(lib, POW2, nonlinearity=nl, **over)
+    assert r["nonlinear"] < 1e-12, r
+
+
+def test_dns_skew_bulkv_fused(lib):
+    """BASELINE configs[1] in small: plane Poiseuille, fixed flux, skew-symmetric form."""
+    r = parity.dns_steps(lib, POW2, checkpoints=(1, 4), nonlinearity="skew", constraint="bulkv", Ubulk=2.0 / 3, ulowerwall=0.0,
+                         uupperwall=0.0, nu=1 / 1800.0)
+    assert r[1] < 1e-12 and r[4] < 1e-12 and r["dPdx"] < 1e-11, r
+
+
 @pytest.mark.parametrize("nl", ["skew", "conv", "div", "alt", "linear"])
 def test_dns_nonlinear_methods(lib, nl):
     r = parity.dns_steps(lib, SMALL, checkpoints=(1, 4), nonlinearity=nl)
