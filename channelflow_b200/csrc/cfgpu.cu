@@ -475,6 +475,15 @@ int cfgpu_field_destroy(cfgpu_field f) {
     delete f;
     return 0;
 }
+int cfgpu_host_alloc(void** p, unsigned long long bytes) {
+    CF_ARG(p, "cfgpu_host_alloc: null argument");
+    CF_CUDA(cudaMallocHost(p, (size_t)(bytes ? bytes : 8)));
+    return 0;
+}
+int cfgpu_host_free(void* p) {
+    if (p) CF_CUDA(cudaFreeHost(p));
+    return 0;
+}
 int cfgpu_field_upload(cfgpu_field f, const double* h, int xz, int y) {
     CF_CUDA(cudaMemcpyAsync(f->d, h, f->n * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
     CF_CUDA(cudaStreamSynchronize(f->ctx->stream));

@@ -29,6 +29,22 @@ namespace chflow {
 cfgpu_ctx cfgpu_context();  // process-wide device context (device = $CFGPU_DEVICE, else $LOCAL_RANK, else 0)
 void cfgpu_check(int status, const char* where);
 
+// std allocator over cfgpu_host_alloc: the host mirror lives in page-locked memory
+template <class T>
+struct PinnedAllocator {
+    typedef T value_type;
+    PinnedAllocator() {}
+    template <class U> PinnedAllocator(const PinnedAllocator<U>&) {}
+    T* allocate(std::size_t n) {
+        void* p = nullptr;
+        cfgpu_check(cfgpu_host_alloc(&p, (unsigned long long)(n * sizeof(T))), "cfgpu_host_alloc");
+        return static_cast<T*>(p);
+    }
+    void deallocate(T* p, std::size_t) { cfgpu_host_free(p); }
+    template <class U> bool operator==(const PinnedAllocator<U>&) const { return true; }
+    template <class U> bool operator!=(const PinnedAllocator<U>&) const { return false; }
+};
+
 class FlowField {
    public:
     FlowField();
@@ -171,7 +187,7 @@ class FlowField {
     CfMPI* cfmpi_ = nullptr;
 
     mutable cfgpu_field dev_ = nullptr;
-    mutable std::vector<Real> host_;
+    mutable std::vector<Real, PinnedAllocator<Real>> host_;
     mutable bool host_valid_ = false;  // host mirror holds the current data
     mutable bool dev_valid_ = true;    // device copy holds the current data
 

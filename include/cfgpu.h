@@ -71,6 +71,10 @@ int cfgpu_field_allgather(cfgpu_field f);
 int cfgpu_field_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, int Nd, double Lx, double Lz, double a, double b,
                        cfgpu_field* out);
 int cfgpu_field_destroy(cfgpu_field f);
+/* page-locked host memory for the FlowField host mirror (replaces fftw_malloc of the host array, flowfield.cpp:495-497):
+ * transfers from/to it run at full PCIe rate and can be asynchronous */
+int cfgpu_host_alloc(void** ptr_h, unsigned long long bytes);
+int cfgpu_host_free(void* ptr_h);
 int cfgpu_field_upload(cfgpu_field f, const double* data_h, int xzstate, int ystate);
 int cfgpu_field_download(cfgpu_field f, double* data_h);
 /* Same for an xz-spectral, de-aliased ("padded", flowfield.h:578-584) field: only the retained box |kx| <= Nx/3-1,

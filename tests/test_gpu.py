@@ -194,3 +194,24 @@ def test_field2vector_roundtrip(lib):
     y = xr + 1e-3 * np.random.default_rng(3).standard_normal(xr.shape)
     vr, vg = ur.like().from_vector(y), ug.like().from_vector(y)
     assert parity.rel_l2(vg.get(), vr.data) < 1e-14
+
+
+def test_full_size_properties(lib):
+    """BASELINE-size grid (C5, 256x129x256): size-independent properties instead of the (slow) CPU oracle --
+    transform round trip is the identity; one SBDF step of a solenoidal no-slip field stays solenoidal and no-slip
+    (vector2field(field2vector(u)) == u, reference flowfield.cpp:4754-4758); L2Norm is invariant under the round trip."""
+    import bench
+    w = bench.WORKLOADS["c5"]
+    u0 = bench.synthetic_field(w)
+    ug = cf.FlowField(lib, w["Nx"], w["Ny"], w["Nz"], 3, w["Lx"], w["Lz"]).set(u0, padded=True)
+    n0 = ug.l2norm()
+    v = ug.copy()
+    v.make_physical(); v.make_spectral()
+    assert ug.l2dist(v) <= 1e-13 * n0
+    dns = cf.DNS(ug, cf.make_flags(**bench.flags_kw(w)))
+    dns.advance(3)
+    u1, _ = dns.get()
+    x = u1.to_vector()
+    u2 = u1.like().from_vector(x)
+    assert u1.l2dist(u2) <= 1e-12 * u1.l2norm(), (u1.l2dist(u2), u1.l2norm())
+    assert abs(u1.l2norm() - n0) < 0.05 * n0
