@@ -137,17 +137,12 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
                 for (int t = 0; t < NT; ++t)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) e[i][t][q] = o[i][t][q] = 0.0;
-            const int nhalf = (two && job.in2 && p.mode == 1) ? 4 : 2;
-            for (int hq = 0; hq < nhalf; ++hq) {
-                // hq 0/1: even/odd products of the first input; hq 2/3: derivative matrices of the second input acting on
-                // its difference (-> even rows) / sum (-> odd rows) tiles
-                const int half = hq & 1;
-                const double* __restrict__ A = hq == 0 ? A1 : hq == 1 ? A2 : hq == 2 ? p.A1b : p.A2b;
-                const int Kp = hq == 1 ? p.K2p : p.K1p;
+            // acc += A[row0 .. row0+32][0 .. Kp) * Bt[0 .. Kp)[this warp's columns]; A fragments of one k-step:
+            // [row block i][a0..a3] = rows lr / lr+8 of block i, columns lk / lk+4, prefetched one k-step ahead
+            auto accumulate = [&](double (&acc)[2][NT][4], const double* __restrict__ A, const int Kp, const double* __restrict__ Bt) {
                 const double* __restrict__ ap = A + (size_t)(row0 + lr) * Kp + lk;
-                const double* __restrict__ bp = (hq == 0 ? B1 : hq == 1 ? B2 : hq == 2 ? B2b : B1b) + lk * LD + ncb + lr;
+                const double* __restrict__ bp = Bt + lk * LD + ncb + lr;
                 const int nk = Kp / 8;
-                // A fragments of one k-step: [row block i][a0..a3] = rows lr / lr+8 of block i, columns lk / lk+4
                 double a[2][4], an[2][4];
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
@@ -170,15 +165,19 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
 #pragma unroll
-                        for (int t = 0; t < NT; ++t) {
-                            if (half) dmma_m16n8k8(o[i][t], a[i], b[t]);
-                            else dmma_m16n8k8(e[i][t], a[i], b[t]);
-                        }
+                        for (int t = 0; t < NT; ++t) dmma_m16n8k8(acc[i][t], a[i], b[t]);
 #pragma unroll
                     for (int i = 0; i < 2; ++i)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) a[i][q] = an[i][q];
                 }
+            };
+            accumulate(e, A1, p.K1p, B1);
+            accumulate(o, A2, p.K2p, B2);
+            if (two && job.in2 && p.mode == 1) {
+                // derivative matrices of the second input: its difference tile feeds the even rows, its sum tile the odd rows
+                accumulate(e, p.A1b, p.K1p, B2b);
+                accumulate(o, p.A2b, p.K1p, B1b);
             }
 
             // epilogue: c0,c1 = C[lr][2*lk + {0,1}], c2,c3 = C[lr+8][..] of each 16-row block
