@@ -25,6 +25,13 @@ def test_cabi_symbols_product_library():
     if not os.path.exists(cf.LIB_GPU):
         pytest.skip("libcfgpu.so not built yet (python __graft_entry__.py)")
     assert cf.check_symbols()
+    # ... and the list checked is exactly what the header declares
+    import re
+    hdr = open(os.path.join(parity.ROOT, "include", "cfgpu.h")).read()
+    declared = set(re.findall(r"\b(cfgpu_[A-Za-z0-9_]+)\s*\(", hdr)) - {"cfgpu_exchange_fn", "cfgpu_allreduce_fn"}
+    assert declared == set(cf.CFGPU_SYMBOLS), declared ^ set(cf.CFGPU_SYMBOLS)
+    lib = cf.GpuLib()
+    assert all(hasattr(lib.L, s_) for s_ in declared)
 
 
 def test_product_library_has_no_cpu_fallback():
