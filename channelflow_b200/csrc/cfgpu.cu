@@ -311,6 +311,8 @@ int cfgpu_finalize(cfgpu_ctx ctx) {
     if (ctx->ws_P.ptr) cudaFree(ctx->ws_P.ptr);
     if (ctx->ws_Q.ptr) cudaFree(ctx->ws_Q.ptr);
     if (ctx->ws_red.ptr) cudaFree(ctx->ws_red.ptr);
+    if (ctx->peerP_base) comm_close_peers(ctx->comm, ctx->peerP);
+    if (ctx->peerS_base) comm_close_peers(ctx->comm, ctx->peerS);
     if (ctx->ws_S.ptr) cudaFree(ctx->ws_S.ptr);
     comm_destroy(ctx->comm);
     cudaEventDestroy(ctx->ev0);

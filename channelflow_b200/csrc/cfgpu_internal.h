@@ -58,6 +58,10 @@ struct cfgpu_ctx_s {
     std::map<std::tuple<int, int, int, int>, cfgpu::ModeBox> boxes;
     cfgpu::Workspace ws_P, ws_Q, ws_S, ws_red;
     cfgpu::Comm comm;  // rank / world size / collectives (single rank by default)
+    // peer mappings of the other ranks' ws_P / ws_S (CUDA IPC), valid for the local base pointers recorded beside them
+    void* peerP[cfgpu::COMM_MAXRANKS] = {nullptr};
+    void* peerS[cfgpu::COMM_MAXRANKS] = {nullptr};
+    void *peerP_base = nullptr, *peerS_base = nullptr;
     std::vector<void*> graphs;  // cudaGraphExec_t
     bool capturing = false;
     // stage profiler
@@ -99,6 +103,8 @@ struct cfgpu_nse_s {
     std::vector<double> lambda_t;
     std::vector<cfgpu::TauData> tau;  // one per substep
     int TM_solve = 8, TM_lin = 8;
+    double** d_rows[2] = {nullptr, nullptr};  // peer row tables of the inverse y-GEMM outputs (5- and 3-field staging)
+    void* rows_baseS = nullptr;
     cfgpu_field s_u = nullptr, s_t = nullptr;  // scratch fields of the non-rotational nonlinear terms (3 and 9 components)
 };
 

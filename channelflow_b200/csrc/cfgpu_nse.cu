@@ -65,6 +65,47 @@ static int slab_exchange(cfgpu_nse nse, int nf, int dir, const int* fields, int 
     return comm_exchange(cm, msgs.data(), (int)msgs.size(), stream);
 }
 
+// Peer-memory path (NCCL backend): map every rank's pencil (P) and staging (S) buffers, and build the tables that send
+// each output row of the inverse y-GEMM to the rank owning that y plane.
+static int ensure_peers(cfgpu_nse nse, size_t Pbytes, size_t Sbytes) {
+    cfgpu_ctx ctx = nse->ctx;
+    Comm& cm = ctx->comm;
+    CF_TRY(ws_reserve(ctx->ws_P, Pbytes));
+    CF_TRY(ws_reserve(ctx->ws_S, Sbytes));
+    if (ctx->peerP_base != ctx->ws_P.ptr) {  // (re)allocated: same decision on every rank (sizes depend on the geometry only)
+        if (ctx->peerP_base) CF_TRY(comm_close_peers(cm, ctx->peerP));
+        CF_TRY(comm_open_peers(cm, ctx->ws_P.ptr, ctx->peerP, ctx->stream));
+        ctx->peerP_base = ctx->ws_P.ptr;
+    }
+    if (ctx->peerS_base != ctx->ws_S.ptr) {
+        if (ctx->peerS_base) CF_TRY(comm_close_peers(cm, ctx->peerS));
+        CF_TRY(comm_open_peers(cm, ctx->ws_S.ptr, ctx->peerS, ctx->stream));
+        ctx->peerS_base = ctx->ws_S.ptr;
+    }
+    if (nse->rows_baseS != ctx->ws_S.ptr) {
+        const int nmx = 2 * nse->Kx + 1, nkz = nse->Kz + 1, nxl = nse->x1 - nse->x0;
+        for (int v = 0; v < 2; ++v) {
+            const int nf = v == 0 ? 5 : 3;
+            std::vector<double*> tab((size_t)nf * nse->Ny);
+            for (int r = 0; r < cm.nranks; ++r) {
+                int ya, yb;
+                part_range(nse->Ny, cm.nranks, r, ya, yb);
+                const int nyl = yb - ya;
+                double* Sr = reinterpret_cast<double*>(ctx->peerS[r]);
+                for (int f = 0; f < nf; ++f)
+                    for (int y = ya; y < yb; ++y)
+                        tab[(size_t)f * nse->Ny + y] = Sr + 2 * (size_t)nkz * ((size_t)nf * nyl * nse->x0 + ((size_t)f * nyl + (y - ya)) * nxl);
+            }
+            (void)nmx;
+            if (!nse->d_rows[v]) CF_CUDA(cudaMalloc((void**)&nse->d_rows[v], tab.size() * sizeof(double*)));
+            CF_CUDA(cudaMemcpyAsync(nse->d_rows[v], tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
+            CF_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        nse->rows_baseS = ctx->ws_S.ptr;
+    }
+    return 0;
+}
+
 static void fill_xsplit(cfgpu_nse nse, XPassParams& xp, int nstage) {
     const Comm& cm = nse->ctx->comm;
     xp.nranks = cm.nranks;
@@ -93,6 +134,8 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     const size_t Pf = (size_t)nse->Ny * nxl * nkz * 2;     // doubles per pencil field P (kx slab)
     const size_t Sf = (size_t)nyl * nmx * nkz * 2;          // doubles per staged field (y slab)
     const size_t Qf = (size_t)nyl * nse->Nx * nkz * 2;      // doubles per pencil field Q (y slab)
+    const bool peer = multi && comm_peer_capable(ctx->comm);
+    if (peer) CF_TRY(ensure_peers(nse, 5 * Pf * sizeof(double), 5 * Sf * sizeof(double)));
     CF_TRY(ws_reserve(ctx->ws_P, 5 * Pf * sizeof(double)));
     if (multi) CF_TRY(ws_reserve(ctx->ws_S, 5 * Sf * sizeof(double)));
     CF_TRY(ws_reserve(ctx->ws_Q, 6 * Qf * sizeof(double)));
@@ -118,7 +161,18 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         p.job[0].nmat = 2; p.job[0].out[1] = P + 3 * Pf;  // du/dy
         p.job[2].nmat = 2; p.job[2].out[1] = P + 4 * Pf;  // dw/dy
     }
-    if (!multi) {
+    if (peer) {
+        // every output row goes straight to the staging buffer of the rank that owns its y plane (stores over NVLink);
+        // barriers: the consumers are done with the previous contents / all rows have arrived
+        double** tab = nse->d_rows[with_derivs ? 0 : 1];
+        for (int i = 0; i < 3; ++i) {
+            p.job[i].out_rows[0] = tab + (size_t)i * nse->Ny;
+            if (p.job[i].nmat == 2) p.job[i].out_rows[1] = tab + (size_t)(i == 0 ? 3 : 4) * nse->Ny;
+        }
+        CF_TRY(comm_barrier(ctx->comm, ctx->stream));
+        { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(p, ctx->stream)); }
+        { StageTimer _t(ctx, 8); CF_TRY(comm_barrier(ctx->comm, ctx->stream)); }
+    } else if (!multi) {
         StageTimer _t(ctx, 0);
         CF_TRY(ygemm_launch(p, ctx->stream));
     } else {
@@ -159,7 +213,7 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         xp.nfields = 3;
         for (int i = 0; i < 3; ++i) { xp.src[i] = i; xp.opa[i] = 0; xp.srcb[i] = -1; xp.opb[i] = 0; xp.fsel[i] = i; }
     }
-    if (!multi) {
+    if (!multi || peer) {
         StageTimer _t(ctx, 1);
         CF_TRY(xpass_inverse_launch(xp, ctx->stream));
     } else {
@@ -275,6 +329,7 @@ int cfgpu_nse_destroy(cfgpu_nse nse) {
     if (!nse) return 0;
     cudaStreamSynchronize(nse->ctx->stream);
     for (auto& t : nse->tau) cudaFree(t.base);
+    for (int v = 0; v < 2; ++v) if (nse->d_rows[v]) cudaFree(nse->d_rows[v]);
     if (nse->s_u) cfgpu_field_destroy(nse->s_u);
     if (nse->s_t) cfgpu_field_destroy(nse->s_t);
     cudaFree(nse->d_base);
@@ -533,7 +588,14 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     xp.ny0 = nse->y0; xp.nyn = nse->y1 - nse->y0;
     fill_xsplit(nse, xp, 3);
     for (int i = 0; i < 3; ++i) { xp.fsel[i] = i; xp.src[i] = i; xp.srcb[i] = -1; }
-    if (!multi) {
+    const bool peer = multi && comm_peer_capable(ctx->comm);
+    if (peer) {
+        // each kx row is stored straight into its owner's pencil buffer; one barrier before the y-GEMM reads it
+        xp.peer_direct = 1;
+        for (int r = 0; r < ctx->comm.nranks; ++r) xp.peer_out[r] = reinterpret_cast<double2*>(ctx->peerP[r]);
+        { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xp, ctx->stream)); }
+        { StageTimer _t(ctx, 8); CF_TRY(comm_barrier(ctx->comm, ctx->stream)); }
+    } else if (!multi) {
         StageTimer _t(ctx, 3);
         CF_TRY(xpass_forward_launch(xp, ctx->stream));
     } else {
@@ -574,7 +636,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         p.job[i].out[0] = f->d + i * f->compstride();
         p.job[i].nmat = 1; p.job[i].mat0 = 0;
     }
-    if (!multi) {
+    if (!multi || peer) {
         StageTimer _t(ctx, 4);
         CF_TRY(ygemm_launch(p, ctx->stream));
     } else {

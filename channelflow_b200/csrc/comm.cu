@@ -1,6 +1,7 @@
 // See comm.cuh.
 #include "comm.cuh"
 
+#include <cstdlib>
 #include <vector>
 #ifndef CF_EMU
 #include <dlfcn.h>
@@ -107,6 +108,8 @@ int comm_destroy(Comm& c) {
     if (c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.nccl_comm);
 #endif
     c.nccl_comm = nullptr;
+    if (c.d_bar) cudaFree(c.d_bar);
+    c.d_bar = nullptr;
     return 0;
 }
 
@@ -157,6 +160,61 @@ int comm_exchange(Comm& c, const ExchangeMsg* msgs, int nmsg, cudaStream_t strea
     set_last_error("comm_exchange: no exchange callback installed");
     return 1;
 #endif
+}
+
+bool comm_peer_capable(const Comm& c) {
+#ifdef CF_EMU
+    return false;
+#else
+    return c.nranks > 1 && c.nccl_comm != nullptr && !getenv("CFGPU_NO_PEER");
+#endif
+}
+
+int comm_open_peers(Comm& c, void* local, void** peers, cudaStream_t stream) {
+#ifdef CF_EMU
+    set_last_error("peer memory is unavailable in the emulation build");
+    return 1;
+#else
+    // all-gather of the 64-byte IPC handles through the communicator itself (device staging, grouped send/recv)
+    cudaIpcMemHandle_t mine;
+    CF_CUDA(cudaIpcGetMemHandle(&mine, local));
+    char* d = nullptr;
+    CF_CUDA(cudaMalloc((void**)&d, (size_t)c.nranks * sizeof mine));
+    CF_CUDA(cudaMemcpyAsync(d + (size_t)c.rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));
+    std::vector<ExchangeMsg> msgs;
+    for (int r = 0; r < c.nranks; ++r)
+        if (r != c.rank)
+            msgs.push_back({r, d + (size_t)c.rank * sizeof mine, (long long)sizeof mine, d + (size_t)r * sizeof mine, (long long)sizeof mine});
+    CF_TRY(comm_exchange(c, msgs.data(), (int)msgs.size(), stream));
+    std::vector<cudaIpcMemHandle_t> all(c.nranks);
+    CF_CUDA(cudaMemcpyAsync(all.data(), d, (size_t)c.nranks * sizeof mine, cudaMemcpyDeviceToHost, stream));
+    CF_CUDA(cudaStreamSynchronize(stream));
+    CF_CUDA(cudaFree(d));
+    for (int r = 0; r < c.nranks; ++r) {
+        if (r == c.rank) { peers[r] = local; continue; }
+        CF_CUDA(cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+    }
+    return 0;
+#endif
+}
+
+int comm_close_peers(Comm& c, void** peers) {
+#ifndef CF_EMU
+    for (int r = 0; r < c.nranks; ++r) {
+        if (r != c.rank && peers[r]) cudaIpcCloseMemHandle(peers[r]);
+        peers[r] = nullptr;
+    }
+#endif
+    return 0;
+}
+
+int comm_barrier(Comm& c, cudaStream_t stream) {
+    if (c.nranks == 1) return 0;
+    if (!c.d_bar) {
+        CF_CUDA(cudaMalloc((void**)&c.d_bar, sizeof(double)));
+        CF_CUDA(cudaMemset(c.d_bar, 0, sizeof(double)));
+    }
+    return comm_allreduce(c, c.d_bar, 1, 1, stream);
 }
 
 int comm_allreduce(Comm& c, double* dev, int n, int op, cudaStream_t stream) {

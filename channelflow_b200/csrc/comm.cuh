@@ -21,6 +21,7 @@ constexpr int COMM_MAXRANKS = 16;
 struct Comm {
     int rank = 0, nranks = 1;
     void* nccl_comm = nullptr;
+    double* d_bar = nullptr;  // one double for the stream-ordered barrier
     cfgpu_exchange_fn ext_exchange = nullptr;
     cfgpu_allreduce_fn ext_allreduce = nullptr;
     void* ext_user = nullptr;
@@ -47,5 +48,15 @@ int comm_destroy(Comm& c);
 int comm_exchange(Comm& c, const ExchangeMsg* msgs, int nmsg, cudaStream_t stream);
 // in-place all-reduce of n doubles in device memory; op: 0 = sum, 1 = max
 int comm_allreduce(Comm& c, double* dev, int n, int op, cudaStream_t stream);
+
+// ---- peer memory (NVLink / NVSwitch): with the NCCL backend every rank can map the other ranks' pencil buffers
+// (CUDA IPC) and the transform kernels store straight into the consumer's memory -- the all-to-all is fused into the
+// y-GEMM epilogue and the forward x-pass store; only a stream-ordered barrier separates producer and consumer.
+bool comm_peer_capable(const Comm& c);
+// map `local` (a cudaMalloc'ed buffer of this rank) on every rank: peers[r] = address of rank r's buffer in this process
+int comm_open_peers(Comm& c, void* local, void** peers /* [nranks] */, cudaStream_t stream);
+int comm_close_peers(Comm& c, void** peers);
+// all ranks have executed everything enqueued on `stream` before this point (and their stores are visible)
+int comm_barrier(Comm& c, cudaStream_t stream);
 
 }  // namespace cfgpu

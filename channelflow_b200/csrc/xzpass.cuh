@@ -39,7 +39,18 @@ struct XPassParams {
     int nranks;
     int nstage;           // number of fields in the staging buffer
     int xsplit[17];       // xsplit[s] .. xsplit[s+1] = kx rows of rank s
+    // forward pass with peer memory: rank s's pencil buffer P_s[f][Ny][mxi - xsplit[s]][kz] mapped into this process; the
+    // x-pass stores each kx row straight into its owner's memory (the all-to-all fused into the store). null: staged.
+    double2* peer_out[16];
+    int peer_direct;
 };
+// offset (complex elements) of (field f, global plane y, mxi) inside owner rank s's kx-slab pencil buffer
+__host__ __device__ inline size_t xpass_peer_offset(const XPassParams& p, int f, int y, int mxi, int nkz, int& s) {
+    s = 0;
+    while (s + 1 < p.nranks && mxi >= p.xsplit[s + 1]) ++s;
+    const int x0 = p.xsplit[s], nloc = p.xsplit[s + 1] - x0;
+    return (size_t)nkz * (((size_t)f * p.Ny + y) * nloc + (mxi - x0));
+}
 // offset (complex elements) of row (field f, plane yl, mxi) in the staged P-side layout
 __host__ __device__ inline size_t xpass_row_offset(const XPassParams& p, int f, int yl, int mxi, int nkz) {
     int s = 0;

@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
         const double* __restrict__ A1 = p.A1[mat];
         const double* __restrict__ A2 = p.A2[mat];
         double* __restrict__ out = job.out[mi];
+        double* const* __restrict__ rows = job.out_rows[mi];
+        auto row_ptr = [&](int r) -> double* { return rows ? rows[r] : out + (long)r * p.out_ld; };
         const double sgn = p.sgn[mat];
         for (int mt = wm; mt < Mtiles; mt += 4) {
             const int row0 = mt * 32;
@@ -194,15 +196,14 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
                         const double E0 = e[i][t][2 * hh], E1 = e[i][t][2 * hh + 1], O0 = o[i][t][2 * hh], O1 = o[i][t][2 * hh + 1];
                         if (p.mode == 0) {
                             if (r < p.M) {
-                                *reinterpret_cast<double2*>(&out[(long)r * p.out_ld + off]) = make_double2(E0 + O0, E1 + O1);
+                                *reinterpret_cast<double2*>(row_ptr(r) + off) = make_double2(E0 + O0, E1 + O1);
                                 const int rr = Nb - r;
                                 if (rr != r)
-                                    *reinterpret_cast<double2*>(&out[(long)rr * p.out_ld + off]) =
-                                        make_double2(sgn * (E0 - O0), sgn * (E1 - O1));
+                                    *reinterpret_cast<double2*>(row_ptr(rr) + off) = make_double2(sgn * (E0 - O0), sgn * (E1 - O1));
                             }
                         } else {
-                            if (r < p.M) *reinterpret_cast<double2*>(&out[(long)(2 * r) * p.out_ld + off]) = make_double2(E0, E1);
-                            if (r < p.M2) *reinterpret_cast<double2*>(&out[(long)(2 * r + 1) * p.out_ld + off]) = make_double2(O0, O1);
+                            if (r < p.M) *reinterpret_cast<double2*>(row_ptr(2 * r) + off) = make_double2(E0, E1);
+                            if (r < p.M2) *reinterpret_cast<double2*>(row_ptr(2 * r + 1) + off) = make_double2(O0, O1);
                         }
                     }
                 }
@@ -238,13 +239,13 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
             }
             if (p.mode == 0) {
                 if (r < p.M) {
-                    out[(long)r * p.out_ld + off] = E + O;
+                    row_ptr(r)[off] = E + O;
                     const int rr = Nb - r;
-                    if (rr != r) out[(long)rr * p.out_ld + off] = sgn * (E - O);
+                    if (rr != r) row_ptr(rr)[off] = sgn * (E - O);
                 }
             } else {
-                if (r < p.M) out[(long)(2 * r) * p.out_ld + off] = E;
-                if (r < p.M2) out[(long)(2 * r + 1) * p.out_ld + off] = O;
+                if (r < p.M) row_ptr(2 * r)[off] = E;
+                if (r < p.M2) row_ptr(2 * r + 1)[off] = O;
             }
         }
     }

@@ -22,6 +22,8 @@ struct YGemmJob {
     const double* in2;   // forward mode only, may be null: second input whose y-DERIVATIVE coefficients are added to the
                          // output (matrices A1b/A2b act on the swapped difference / sum tiles)
     double* out[YG_MAXMAT];
+    double* const* out_rows[YG_MAXMAT];  // optional device table [N]: address of output row r (rows may live in another GPU's
+                                         // memory: the slab all-to-all fused into the epilogue); null: out + r*out_ld
     int nmat;        // how many of the plan's matrices to apply to this input (inverse: 1 = value, 2 = value + d/dy)
     int mat0;        // first matrix index (inverse: 0 = value, 1 = derivative)
     double add00[YG_MAXMAT];  // unused (reserved)
