@@ -188,3 +188,48 @@ def smoke(cf_module=None):
     assert r[1] < 1e-12 and r[3] < 1e-12, r
     print("smoke ok:", r, "kernel launches:", lib.launch_count())
     return r
+
+
+def orr_sommerfeld(lib, timestepping="sbdf3", nonlinearity="rot", T1=13.0, use_ref=False):
+    """tests/dnsOrrsommTest.cpp, velocity part: a small-amplitude Orr-Sommerfeld eigenfunction (kx=1, kz=0, Re=7500, 4x65x4,
+    golden fixture tests/data/os_ueig10_65.asc) on the parabolic base flow must evolve as exp(-i omega t) with the
+    tabulated eigenvalue; returns the accumulated L2Dist(u_numerical, u_linear) over the checkpoints (reference
+    tolerance for the sum of velocity and pressure errors with SBDF3: 2e-6)."""
+    g = np.load(os.path.join(GOLDEN, "os_eig.npz"))
+    Nx, Ny, Nz, Lx, Lz, a, b = 4, 65, 4, 2 * np.pi, np.pi, -1.0, 1.0
+    nu, dt, N, scale = 1.0 / 7500.0, 0.02, 50, 1e-4
+    omega = complex(g["omega"][0], g["omega"][1])
+    lam = -1j * omega
+    e = g["ueig"]
+    prof = [refcf.cheby_make_spectral(e[:, 2 * i].copy()) + 1j * refcf.cheby_make_spectral(e[:, 2 * i + 1].copy()) for i in range(3)]
+    Mz = Nz // 2 + 1
+
+    def field_of(amp):
+        c = np.zeros((3, Ny, Nx, Mz), dtype=np.complex128)
+        for i in range(3):
+            c[i, :, 1, 0] = amp * prof[i]
+            c[i, :, Nx - 1, 0] = np.conj(amp * prof[i])
+        return c.view(np.float64).reshape(3, Ny, Nx, 2 * Mz)
+
+    def mk(arr):
+        if use_ref:
+            r = refcf.RefField(Nx, Ny, Nz, 3, Lx, Lz, a, b)
+            r.data[...] = arr
+            return r
+        return cf.FlowField(lib, Nx, Ny, Nz, 3, Lx, Lz, a, b).set(arr)
+
+    par = np.zeros((3, Ny, Nx, 2 * Mz))
+    par[0, 0, 0, 0], par[0, 2, 0, 0] = 0.5, -0.5  # 1 - y^2 = T0/2 - T2/2
+    c0 = scale * mk(par).l2norm() / mk(field_of(1.0)).l2norm()
+    fl = dict(nu=nu, dt=dt, ulowerwall=0.0, uupperwall=0.0, baseflow="parabolic", constraint="bulkv", Ubulk=2.0 / 3, dPdx=-2 * nu,
+              timestepping=timestepping, initstepping="cnrk2", nonlinearity=nonlinearity, dealiasing="none")
+    un = mk(field_of(c0))
+    dns = (refcf.RefDNS(un, refcf.make_flags(**fl)) if use_ref else cf.DNS(un, cf.make_flags(**fl)))
+    err, t, amp = 0.0, 0.0, c0
+    while t <= T1 + 1e-12:
+        u, _ = dns.get()
+        err += u.l2dist(mk(field_of(amp)))
+        amp *= np.exp(lam * N * dt)
+        dns.advance(N)
+        t += N * dt
+    return {"err": err, "norm": mk(field_of(c0)).l2norm()}

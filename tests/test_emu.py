@@ -194,3 +194,27 @@ def test_field2vector_roundtrip(lib):
     vg = ug.like().from_vector(y)
     assert parity.rel_l2(vg.get(), vr.data) < 1e-14
     assert vg.padded()
+
+
+def test_orr_sommerfeld_known_answer(lib):
+    """tests/dnsOrrsommTest.cpp (golden eigenfunction + eigenvalue fixtures), shortened to T = 3 on the CPU emulator."""
+    r = parity.orr_sommerfeld(lib, T1=3.0)
+    assert r["err"] < 2e-6 and r["err"] < 1e-3 * r["norm"], r
+
+
+def test_zero_and_parabola_known_answers(lib):
+    """tests/dnsZeroTest.cpp / dnsParabolaTest.cpp: u = 0 stays 0 about the laminar base flow; the parabola 1 - y^2 carried
+    as a fluctuation about a zero base flow with dP/dx = -2 nu is steady (1e-13)."""
+    cfg = dict(parity.C1, Nx=8, Ny=17, Nz=8)
+    z = cf.FlowField(lib, cfg["Nx"], cfg["Ny"], cfg["Nz"], 3, cfg["Lx"], cfg["Lz"])
+    d = cf.DNS(z, cf.make_flags(**cfg["flags"]))
+    d.advance(5)
+    assert d.get()[0].l2norm() == 0.0
+    par = np.zeros(z.shape)
+    par[0, 0, 0, 0], par[0, 2, 0, 0] = 0.5, -0.5
+    p = z.like().set(par)
+    nu = 1.0 / 400
+    d = cf.DNS(p, cf.make_flags(nu=nu, dt=0.02, baseflow="zero", constraint="gradp", dPdx=-2 * nu, ulowerwall=0.0, uupperwall=0.0,
+                                 dealiasing="none"))
+    d.advance(10)
+    assert d.get()[0].l2dist(p) < 1e-13

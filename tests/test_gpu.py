@@ -215,3 +215,26 @@ def test_full_size_properties(lib):
     u2 = u1.like().from_vector(x)
     assert u1.l2dist(u2) <= 1e-12 * u1.l2norm(), (u1.l2dist(u2), u1.l2norm())
     assert abs(u1.l2norm() - n0) < 0.05 * n0
+
+
+@pytest.mark.parametrize("stepper,tol", [("sbdf3", 2e-6), ("cnrk2", 5e-6), ("sbdf2", 2e-4), ("cnab2", 4e-5)])
+def test_orr_sommerfeld_known_answer(lib, stepper, tol):
+    """tests/dnsOrrsommTest.cpp with the reference's own per-scheme tolerances (velocity part), full T = 13."""
+    r = parity.orr_sommerfeld(lib, timestepping=stepper)
+    assert r["err"] < tol, r
+
+
+def test_zero_and_parabola_known_answers(lib):
+    cfg = dict(parity.C1, Nx=8, Ny=17, Nz=8)
+    z = cf.FlowField(lib, cfg["Nx"], cfg["Ny"], cfg["Nz"], 3, cfg["Lx"], cfg["Lz"])
+    d = cf.DNS(z, cf.make_flags(**cfg["flags"]))
+    d.advance(5)
+    assert d.get()[0].l2norm() == 0.0
+    par = np.zeros(z.shape)
+    par[0, 0, 0, 0], par[0, 2, 0, 0] = 0.5, -0.5
+    p = z.like().set(par)
+    nu = 1.0 / 400
+    d = cf.DNS(p, cf.make_flags(nu=nu, dt=0.02, baseflow="zero", constraint="gradp", dPdx=-2 * nu, ulowerwall=0.0, uupperwall=0.0,
+                                 dealiasing="none"))
+    d.advance(10)
+    assert d.get()[0].l2dist(p) < 1e-13
