@@ -1,15 +1,15 @@
 // Batched tau-solver kernels (setup = factorisation + influence matrix, solve = fused RHS + Kleiser-Schumann).
 // See tau.cuh for what is replaced and for the tile-major storage of the per-mode factors.
 //
-// Solve kernel: one CTA owns one tile of TM consecutive retained modes.  Their Chebyshev profiles live in shared
-// memory as [n][t] (t = 2*mode + re/im, fastest) together with the tile's UL factors [n][mode], all staged with
-// coalesced loads by the whole CTA.  The bordered-tridiagonal solves are sequential recurrences in n; a "chain"
-// thread owns one (mode, parity) and carries the real and imaginary parts together (same factors, 2-way ILP),
-// with the recurrence state in registers and every operand coming from shared memory -- no global-memory access
-// sits on a dependent path.  The right-hand side of each Helmholtz problem (Chebyshev derivative recurrence,
-// i k P - R combinations) and the C&H "B" row multiply (helmholtz.cpp:81-85) are fused into the backward sweep,
-// so each solve is two sweeps over its N/2 rows and works in place.  Data-parallel stages (RHS accumulation from
-// the history fields, influence-matrix and tau corrections, scatter) use all threads.
+// Solve kernel: one CTA owns one tile of TM consecutive retained modes.  The whole CTA streams the history fields,
+// accumulates the right-hand side into shared memory as real columns (re or im part of one mode's Chebyshev profile,
+// stored skewed so that per-lane contiguous accesses are conflict free) and stages the tile's UL factors; then every
+// WARP owns one column: lane l holds E consecutive coefficients in registers and each recurrence of the reference
+// (derivative recurrence, UL back substitution, forward elimination) is evaluated as a blocked scan over warp
+// shuffles (col_deriv / col_solve below).  The C&H "B" row multiply (helmholtz.cpp:81-85) and the right-hand sides
+// of the four Helmholtz problems per mode are formed in registers; the influence-matrix and tau corrections and the
+// scatter are data-parallel passes of the whole CTA.
+// Setup kernel (rare: once per dt): one thread per (mode, parity) walks the reference's recurrences sequentially.
 // Roofline: HBM (history fields + factors are each read once, outputs written once).
 #include "tau.cuh"
 

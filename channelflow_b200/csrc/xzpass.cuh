@@ -21,7 +21,6 @@ struct XPassParams {
     int TZ;               // kz columns per CTA
     double Lx;
     FftPlanDev plan;      // length Nx
-    // inverse: nout outputs, each from src[out] with optional d/dx
     int nfields;          // fields this launch handles: output slots fsel[0..nfields)
     int fsel[12];
     // inverse pass, indexed by output slot:  out = op_a(P[src]) - op_b(P[srcb])   (srcb < 0: no second term);
