@@ -26,7 +26,7 @@ cfgpu_host_alloc cfgpu_host_free cfgpu_field_upload cfgpu_field_download cfgpu_f
 cfgpu_field_get_state cfgpu_field_set_padded cfgpu_field_get_padded cfgpu_field_device_ptr cfgpu_field_axpby
 cfgpu_field_scale cfgpu_field_get_profile cfgpu_field_add_profile cfgpu_field_zero_padded_modes
 cfgpu_field_make_physical_y cfgpu_field_make_spectral_y cfgpu_field_make_physical_xz cfgpu_field_make_spectral_xz
-cfgpu_field_make_physical cfgpu_field_make_spectral cfgpu_l2norm2 cfgpu_l2dist2 cfgpu_l2ip cfgpu_nse_create
+cfgpu_field_make_physical cfgpu_field_make_spectral cfgpu_l2norm2 cfgpu_l2norm2_3d cfgpu_l2dist2 cfgpu_l2ip cfgpu_nse_create
 cfgpu_nse_destroy cfgpu_nse_set_constraint cfgpu_nse_reset_lambda cfgpu_nse_nonlinear cfgpu_nse_solve
 cfgpu_nse_linear cfgpu_nse_cflfactor cfgpu_nse_get_dPd cfgpu_comm_unique_id cfgpu_comm_init_nccl
 cfgpu_comm_init_external cfgpu_comm_rank cfgpu_comm_ranges cfgpu_field_allgather""".split()
@@ -490,6 +490,11 @@ class FlowField:
     def make_spectral_xz(self): self.lib.L.cf_make_spectral_xz(self.h)
     def zero_padded_modes(self): self.lib.L.cf_zero_padded_modes(self.h)
     def l2norm(self): return self.lib.L.cf_l2norm(self.h)
+
+    def l2norm3d(self):
+        self.lib.L.cf_l2norm3d.restype = C.c_double
+        self.lib.L.cf_l2norm3d.argtypes = [C.c_void_p]
+        return self.lib.L.cf_l2norm3d(self.h)
     def l2dist(self, o): return self.lib.L.cf_l2dist(self.h, o.h)
     def l2ip(self, o): return self.lib.L.cf_l2ip(self.h, o.h)
     def cmplx(self, mx, my, mz, i): return complex(self.lib.L.cf_cmplx_get(self.h, mx, my, mz, i, 0), self.lib.L.cf_cmplx_get(self.h, mx, my, mz, i, 1))

@@ -684,7 +684,7 @@ int cfgpu_field_make_spectral(cfgpu_field f) {
 }
 
 // ------------------------------------------------------------------------------------------------ norms
-static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool padded, double* out_h) {
+static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool padded, double* out_h, bool skip_kx0 = false) {
     CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "L2 norm: field must be spectral");
     cfgpu_ctx ctx = u->ctx;
     const YPlan* pl;
@@ -701,6 +701,7 @@ static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool pa
         CF_ARG(padded, "L2 norm: multi-GPU norms need de-aliased (padded) fields");
         part_range(2 * Kx + 1, ctx->comm.nranks, ctx->comm.rank, x0, x1);
     }
+    if (skip_kx0 && x0 < 1) x0 = 1;  // row 0 is kx = 0 in both enumerations
     CF_TRY(l2form_launch(u->d, v ? v->d : nullptr, mode, pl->Wgram, u->Ny, u->Nx, u->Nz, u->Nd, Kx, Kz, padded ? 0 : 1, x0, x1, scale,
                          partial, cap, out_dev, ctx->stream));
     CF_TRY(comm_allreduce(ctx->comm, out_dev, 1, 0, ctx->stream));
@@ -709,6 +710,7 @@ static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool pa
     return 0;
 }
 int cfgpu_l2norm2(cfgpu_field u, int normalize, double* out_h) { return l2form(u, nullptr, 0, normalize, u->padded != 0, out_h); }
+int cfgpu_l2norm2_3d(cfgpu_field u, int normalize, double* out_h) { return l2form(u, nullptr, 0, normalize, u->padded != 0, out_h, true); }
 int cfgpu_l2dist2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h) {
     CF_ARG(same_shape(u, v), "L2Dist2: shape mismatch");
     return l2form(u, v, 1, normalize, u->padded && v->padded, out_h);

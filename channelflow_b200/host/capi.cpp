@@ -138,6 +138,7 @@ void cf_dns_reset_dt(void* h, double dt) { ((CfDNS*)h)->dns->reset_dt(dt); }
 double cf_dns_time(void* h) { return ((CfDNS*)h)->dns->time(); }
 double cf_dns_dPdx(void* h) { return ((CfDNS*)h)->dns->dPdx(); }
 double cf_dns_Ubulk(void* h) { return ((CfDNS*)h)->dns->Ubulk(); }
+double cf_l2norm3d(void* uh) { return L2Norm3d(*(FlowField*)uh); }
 int cf_field2vector_size(void* uh) { return field2vector_size(*(FlowField*)uh); }
 void cf_field2vector(void* uh, double* x) { field2vector(*(FlowField*)uh, x); }
 void cf_vector2field(const double* x, void* uh) { vector2field(x, *(FlowField*)uh); }

@@ -5,6 +5,8 @@
 
 namespace chflow {
 Real L2Norm2(const FlowField& u, bool normalize = true);
+Real L2Norm2_3d(const FlowField& u, bool normalize = true);  // without the kx = 0 modes (diffops.cpp:700-740)
+Real L2Norm3d(const FlowField& u, bool normalize = true);
 Real L2Norm(const FlowField& u, bool normalize = true);
 Real L2Dist2(const FlowField& u, const FlowField& v, bool normalize = true);
 Real L2Dist(const FlowField& u, const FlowField& v, bool normalize = true);

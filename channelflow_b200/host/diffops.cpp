@@ -9,6 +9,12 @@ Real L2Norm2(const FlowField& u, bool normalize) {
     return r;
 }
 Real L2Norm(const FlowField& u, bool normalize) { return sqrt(L2Norm2(u, normalize)); }
+Real L2Norm2_3d(const FlowField& u, bool normalize) {
+    double r = 0;
+    cfgpu_check(cfgpu_l2norm2_3d(u.device(), normalize ? 1 : 0, &r), "cfgpu_l2norm2_3d");
+    return r;
+}
+Real L2Norm3d(const FlowField& u, bool normalize) { return sqrt(L2Norm2_3d(u, normalize)); }
 Real L2Dist2(const FlowField& u, const FlowField& v, bool normalize) {
     Real r = 0;
     cfgpu_check(cfgpu_l2dist2(u.device(), v.device(), normalize ? 1 : 0, &r), "cfgpu_l2dist2");

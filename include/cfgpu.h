@@ -113,6 +113,8 @@ int cfgpu_field_make_spectral(cfgpu_field f); /* xz then y */
  * L2Norm2 / L2Dist2 / L2InnerProduct of FlowFields (diffops.cpp:417-487, 353-413, 489-541) with the Chebyshev
  * Gram weights of chebyshev.cpp:758-802 (weights evaluated in FP64) */
 int cfgpu_l2norm2(cfgpu_field u, int normalize, double* out_h);
+/* L2Norm2_3d (diffops.cpp:700-740): the same sum without the kx = 0 modes */
+int cfgpu_l2norm2_3d(cfgpu_field u, int normalize, double* out_h);
 int cfgpu_l2dist2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h);
 int cfgpu_l2ip(cfgpu_field u, cfgpu_field v, int normalize, double* out_h);
 

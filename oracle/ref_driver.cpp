@@ -127,6 +127,7 @@ void ref_load_padded_physical(void* h, const double* var, int Nx_io, int Nz_io) 
 
 double ref_l2norm(void* h) { return L2Norm(*(FlowField*)h); }
 double ref_l2norm2(void* h, int normalize) { return L2Norm2(*(FlowField*)h, normalize != 0); }
+double ref_l2norm3d(void* h) { return L2Norm3d(*(FlowField*)h); }
 double ref_l2dist(void* a, void* b) { return L2Dist(*(FlowField*)a, *(FlowField*)b); }
 double ref_l2ip(void* a, void* b) { return L2InnerProduct(*(FlowField*)a, *(FlowField*)b); }
 double ref_divnorm(void* h) { return divNorm(*(FlowField*)h); }

@@ -168,6 +168,11 @@ class RefField:
     def make_spectral_xz(self): lib().ref_make_spectral_xz(self.h)
     def zero_padded_modes(self): lib().ref_zero_padded_modes(self.h)
     def l2norm(self): return lib().ref_l2norm(self.h)
+    def l2norm3d(self):
+        lib().ref_l2norm3d.restype = C.c_double
+        lib().ref_l2norm3d.argtypes = [C.c_void_p]
+        return lib().ref_l2norm3d(self.h)
+
     def l2dist(self, o): return lib().ref_l2dist(self.h, o.h)
     def l2ip(self, o): return lib().ref_l2ip(self.h, o.h)
     def divnorm(self): return lib().ref_divnorm(self.h)

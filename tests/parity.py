@@ -87,7 +87,9 @@ def norms(lib, cfg):
     out = {"l2norm": abs(ug.l2norm() - ur.l2norm()) / ur.l2norm(),
            "l2dist": abs(ug.l2dist(vg) - ur.l2dist(vr)) / ur.l2dist(vr),
            "l2ip": abs(ug.l2ip(vg) - ur.l2ip(vr)) / abs(ur.l2norm() * vr.l2norm())}
+    out["l2norm3d"] = abs(ug.l2norm3d() - ur.l2norm3d()) / ur.l2norm3d()
     ur.set_padded(False); vr.set_padded(False); ug.set_padded(False); vg.set_padded(False)
+    out["l2norm3d_unpadded"] = abs(ug.l2norm3d() - ur.l2norm3d()) / ur.l2norm3d()
     out["l2norm_unpadded"] = abs(ug.l2norm() - ur.l2norm()) / ur.l2norm()
     return out
 
