@@ -196,12 +196,14 @@ def test_field2vector_roundtrip(lib):
     assert parity.rel_l2(vg.get(), vr.data) < 1e-14
 
 
-def test_full_size_properties(lib):
-    """BASELINE-size grid (C5, 256x129x256): size-independent properties instead of the (slow) CPU oracle --
-    transform round trip is the identity; one SBDF step of a solenoidal no-slip field stays solenoidal and no-slip
+@pytest.mark.parametrize("wname", ["c5", "mixed_radix"])
+def test_full_size_properties(lib, wname):
+    """BASELINE-size grid (C5, 256x129x256) and a large mixed-radix grid (384x161x192 = 3*2^7 x 161 x 3*2^6, the non
+    power-of-two FFT kernels and a 6-per-lane tau solver): size-independent properties instead of the (slow) CPU oracle --
+    transform round trip is the identity; SBDF steps of a solenoidal no-slip field stay solenoidal and no-slip
     (vector2field(field2vector(u)) == u, reference flowfield.cpp:4754-4758); L2Norm is invariant under the round trip."""
     import bench
-    w = bench.WORKLOADS["c5"]
+    w = bench.WORKLOADS["c5"] if wname == "c5" else dict(bench.WORKLOADS["c5"], Nx=384, Ny=161, Nz=192)
     u0 = bench.synthetic_field(w)
     ug = cf.FlowField(lib, w["Nx"], w["Ny"], w["Nz"], 3, w["Lx"], w["Lz"]).set(u0, padded=True)
     n0 = ug.l2norm()
