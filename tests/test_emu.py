@@ -218,3 +218,20 @@ def test_zero_and_parabola_known_answers(lib):
                                  dealiasing="none"))
     d.advance(10)
     assert d.get()[0].l2dist(p) < 1e-13
+
+
+def test_step_vs_numpy_restatement(lib):
+    """One SBDF1 step of the CUDA path against the second oracle tier (oracle/np_oracle.py, pinned to the compiled
+    reference in tests/test_oracle.py): independent of the compiled reference library."""
+    from oracle import np_oracle as npo
+    cfg = dict(parity.C1, Nx=12, Ny=17, Nz=12)
+    ur = parity.ref_random(cfg, 11)
+    c = ur.cdata.copy()
+    fl = dict(cfg["flags"], timestepping="sbdf1")
+    gd = cf.DNS(parity.to_gpu(lib, ur), cf.make_flags(**fl))
+    U, W = cf.base_profiles(parity.to_gpu(lib, ur), cf.make_flags(**fl))
+    gd.advance(1)
+    u2, q2 = gd.get()
+    un, qn = npo.sbdf1_step(c, fl["dt"], fl["nu"], U, W, cfg["Lx"], cfg["Lz"], cfg["a"], cfg["b"])
+    mine = u2.get().view(np.complex128)
+    assert np.abs(mine - un).max() < 1e-12 * np.abs(un).max()

@@ -57,3 +57,57 @@ def test_cheby_roundtrip_shim():
     direct = np.polynomial.chebyshev.chebval(y, c)
     assert np.abs(p - direct).max() < 1e-13
     assert np.abs(refcf.cheby_make_spectral(p) - c).max() < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------ NumPy restatement
+SMALLG = dict(parity.C1, Nx=12, Ny=17, Nz=12)
+
+
+def test_np_oracle_helmholtz_and_tausolver():
+    """oracle/np_oracle.py against the compiled reference: HelmholtzSolver and TauSolver, mode by mode."""
+    from oracle import np_oracle as npo
+    rng = np.random.default_rng(7)
+    N, a, b, nu = 17, -1.0, 1.0, 1 / 400.0
+    f = rng.standard_normal(N)
+    for lam in (0.7, 91.6):
+        h = npo.Helmholtz(N, a, b, lam, nu).solve(f, 0.3, -0.2)
+        assert np.abs(h - refcf.helmholtz(N, a, b, lam, nu, f, 0.3, -0.2)).max() < 1e-13
+    for kx, kz in ((0, 0), (1, 0), (0, 2), (-2, 1)):
+        R = [rng.standard_normal(N) + 1j * rng.standard_normal(N) for _ in range(3)]
+        if kx == 0 and kz == 0:
+            R = [r.real + 0j for r in R]
+        lam = 91.6 + 4 * np.pi ** 2 * nu * ((kx / 5.5) ** 2 + (kz / 2.5) ** 2)
+        mine = npo.TauSolver(kx, kz, 5.5, 2.5, a, b, lam, nu, N).solve(*R)
+        ref = refcf.tausolve(kx, kz, 5.5, 2.5, a, b, lam, nu, N, *R)
+        for m_, r_ in zip(mine, ref):
+            assert np.abs(m_ - r_).max() < 1e-12, (kx, kz)
+
+
+def test_np_oracle_transforms_nonlinear_and_step():
+    """NumPy restatement of makePhysical/makeSpectral, the rotational term and one SBDF1 step vs the compiled reference."""
+    from oracle import np_oracle as npo
+    cfg = SMALLG
+    ur = parity.ref_random(cfg, 11)
+    c = ur.cdata.copy()
+    fl = dict(cfg["flags"], timestepping="sbdf1")
+    U, W = refcf.base_profiles(ur, refcf.make_flags(**fl))
+    # transforms
+    phys = npo.to_physical(c, cfg["Nz"])
+    up = ur.like(); up.data[...] = ur.data; up.set_state(*ur.state()); up.make_physical()
+    assert np.abs(phys - up.data[..., :cfg["Nz"]]).max() < 1e-13
+    assert np.abs(npo.to_spectral(phys) - c).max() < 1e-14
+    # rotational term
+    fobj = refcf.nonlinear(ur, refcf.make_flags(**fl))  # keep the field alive: .cdata is a view of its memory
+    fr = fobj.cdata.copy()
+    fn = npo.rotational_nl(c, U, W, cfg["Lx"], cfg["Lz"], cfg["a"], cfg["b"])
+    assert np.abs(fn - fr).max() < 1e-13 * max(1.0, np.abs(fr).max())
+    # one SBDF1 step
+    rd = refcf.RefDNS(ur, refcf.make_flags(**fl))
+    rd.advance(1)
+    u1, q1 = rd.get()
+    u1c, q1c = u1.cdata.copy(), q1.cdata.copy()
+    un, qn = npo.sbdf1_step(c, fl["dt"], fl["nu"], U, W, cfg["Lx"], cfg["Lz"], cfg["a"], cfg["b"])
+    Kx, Kz = cfg["Nx"] // 3 - 1, cfg["Nz"] // 3 - 1
+    keep = [m for m in range(cfg["Nx"]) if abs(npo.kx_of(m, cfg["Nx"])) <= Kx]
+    assert np.abs(un[:, :, keep, :Kz + 1] - u1c[:, :, keep, :Kz + 1]).max() < 1e-12 * np.abs(u1c).max()
+    assert np.abs(qn[:, keep, :Kz + 1] - q1c[0][:, keep, :Kz + 1]).max() < 1e-11 * max(1.0, np.abs(q1c).max())
