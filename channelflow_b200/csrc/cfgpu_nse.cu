@@ -76,11 +76,17 @@ static int ensure_peers(cfgpu_nse nse, size_t Pbytes, size_t Sbytes) {
     if (ctx->peerP_base != ctx->ws_P.ptr) {  // (re)allocated: same decision on every rank (sizes depend on the geometry only)
         if (ctx->peerP_base) CF_TRY(comm_close_peers(cm, ctx->peerP));
         CF_TRY(comm_open_peers(cm, ctx->ws_P.ptr, ctx->peerP, ctx->stream));
+        if (cm.peer_failed) return 0;
         ctx->peerP_base = ctx->ws_P.ptr;
     }
     if (ctx->peerS_base != ctx->ws_S.ptr) {
         if (ctx->peerS_base) CF_TRY(comm_close_peers(cm, ctx->peerS));
         CF_TRY(comm_open_peers(cm, ctx->ws_S.ptr, ctx->peerS, ctx->stream));
+        if (cm.peer_failed) {
+            comm_close_peers(cm, ctx->peerP);
+            ctx->peerP_base = nullptr;
+            return 0;
+        }
         ctx->peerS_base = ctx->ws_S.ptr;
     }
     if (nse->rows_baseS != ctx->ws_S.ptr) {
@@ -135,8 +141,11 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     const size_t Pf = (size_t)nse->Ny * nxl * nkz * 2;     // doubles per pencil field P (kx slab)
     const size_t Sf = (size_t)nyl * nmx * nkz * 2;          // doubles per staged field (y slab)
     const size_t Qf = (size_t)nyl * nse->Nx * nkz * 2;      // doubles per pencil field Q (y slab)
-    const bool peer = multi && comm_peer_capable(ctx->comm);
-    if (peer) CF_TRY(ensure_peers(nse, 5 * Pf * sizeof(double), 5 * Sf * sizeof(double)));
+    bool peer = multi && comm_peer_capable(ctx->comm);
+    if (peer) {
+        CF_TRY(ensure_peers(nse, 5 * Pf * sizeof(double), 5 * Sf * sizeof(double)));
+        peer = comm_peer_capable(ctx->comm);  // mapping may have failed (collectively): staged exchange instead
+    }
     CF_TRY(ws_reserve(ctx->ws_P, 5 * Pf * sizeof(double)));
     if (multi) CF_TRY(ws_reserve(ctx->ws_S, 5 * Sf * sizeof(double)));
     CF_TRY(ws_reserve(ctx->ws_Q, 6 * Qf * sizeof(double)));

@@ -166,7 +166,7 @@ bool comm_peer_capable(const Comm& c) {
 #ifdef CF_EMU
     return false;
 #else
-    return c.nranks > 1 && c.nccl_comm != nullptr && !getenv("CFGPU_NO_PEER");
+    return c.nranks > 1 && c.nccl_comm != nullptr && !c.peer_failed && !getenv("CFGPU_NO_PEER");
 #endif
 }
 
@@ -190,9 +190,32 @@ int comm_open_peers(Comm& c, void* local, void** peers, cudaStream_t stream) {
     CF_CUDA(cudaMemcpyAsync(all.data(), d, (size_t)c.nranks * sizeof mine, cudaMemcpyDeviceToHost, stream));
     CF_CUDA(cudaStreamSynchronize(stream));
     CF_CUDA(cudaFree(d));
+    // map; whether it worked is agreed on collectively so that all ranks take the same path afterwards
+    double ok = 1.0;
     for (int r = 0; r < c.nranks; ++r) {
         if (r == c.rank) { peers[r] = local; continue; }
-        CF_CUDA(cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+        peers[r] = nullptr;
+        if (cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            peers[r] = nullptr;
+            ok = 0.0;
+        }
+    }
+    if (!c.d_bar) {
+        CF_CUDA(cudaMalloc((void**)&c.d_bar, sizeof(double)));
+    }
+    ok = -ok;  // all-reduce MAX of -ok == -min(ok)
+    CF_CUDA(cudaMemcpyAsync(c.d_bar, &ok, sizeof(double), cudaMemcpyHostToDevice, stream));
+    CF_TRY(comm_allreduce(c, c.d_bar, 1, 1, stream));
+    CF_CUDA(cudaMemcpyAsync(&ok, c.d_bar, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CF_CUDA(cudaStreamSynchronize(stream));
+    CF_CUDA(cudaMemsetAsync(c.d_bar, 0, sizeof(double), stream));
+    if (ok > -0.5) {
+        for (int r = 0; r < c.nranks; ++r) {
+            if (r != c.rank && peers[r]) cudaIpcCloseMemHandle(peers[r]);
+            peers[r] = nullptr;
+        }
+        c.peer_failed = true;
     }
     return 0;
 #endif

@@ -22,6 +22,7 @@ struct Comm {
     int rank = 0, nranks = 1;
     void* nccl_comm = nullptr;
     double* d_bar = nullptr;  // one double for the stream-ordered barrier
+    bool peer_failed = false; // mapping peer memory failed on some rank: every rank uses the staged exchange instead
     cfgpu_exchange_fn ext_exchange = nullptr;
     cfgpu_allreduce_fn ext_allreduce = nullptr;
     void* ext_user = nullptr;
