@@ -189,6 +189,7 @@ class FlowField {
     mutable cfgpu_field dev_ = nullptr;
     mutable std::vector<Real, PinnedAllocator<Real>> host_;
     mutable bool host_valid_ = false;  // host mirror holds the current data
+    mutable bool host_box_clean_ = false;  // host mirror is known to be zero outside the retained (de-aliased) box
     mutable bool dev_valid_ = true;    // device copy holds the current data
 
     int Nzpad() const { return 2 * (Nz_ / 2 + 1); }

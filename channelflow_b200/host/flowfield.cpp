@@ -1,6 +1,8 @@
 // chflow::FlowField over the cfgpu C-ABI.  See channelflow/flowfield.h.
 #include "channelflow/flowfield.h"
 
+#include <algorithm>
+
 #include <arpa/inet.h>
 
 #include <cstring>
@@ -85,13 +87,22 @@ void FlowField::push_state() const {
 }
 void FlowField::host_sync() const {
     if (host_valid_) return;
-    host_.resize((size_t)Nloc());
-    if (padded_ && xzstate_ == Spectral && box_ok()) CK(cfgpu_field_download_padded(dev_, host_.data()));
-    else CK(cfgpu_field_download(dev_, host_.data()));
+    const bool fresh = host_.empty();
+    host_.resize((size_t)Nloc());  // value-initialised: zeros
+    if (padded_ && xzstate_ == Spectral && box_ok()) {
+        // only the retained box travels; whatever an earlier (physical / un-padded) state left elsewhere must not survive
+        if (!fresh && !host_box_clean_) std::fill(host_.begin(), host_.end(), 0.0);
+        CK(cfgpu_field_download_padded(dev_, host_.data()));
+        host_box_clean_ = true;
+    } else {
+        CK(cfgpu_field_download(dev_, host_.data()));
+        host_box_clean_ = false;
+    }
     host_valid_ = true;
 }
 void FlowField::host_dirty() {
     host_sync();
+    host_box_clean_ = false;  // the caller may write anywhere
     dev_valid_ = false;
 }
 cfgpu_field FlowField::device() const {
@@ -269,6 +280,7 @@ void swap(FlowField& f, FlowField& g) {
     std::swap(f.dev_, g.dev_);
     std::swap(f.host_, g.host_);
     std::swap(f.host_valid_, g.host_valid_);
+    std::swap(f.host_box_clean_, g.host_box_clean_);
     std::swap(f.dev_valid_, g.dev_valid_);
 }
 
@@ -374,6 +386,7 @@ FlowField::FlowField(const std::string& filebase, CfMPI* cfmpi) {
     resize(Nx, Ny, Nz, Nd, Lx, Lz, a, b, cfmpi);
     xzstate_ = xz; ystate_ = ys; padded_ = padded;
     host_.assign((size_t)Nloc(), 0.0);
+    host_box_clean_ = false;
     if (padded && xz == Spectral) {
         const int Nxd = 2 * (Nx_ / 6), Nzd = 2 * (Nz_ / 3) + 1;
         for (int i = 0; i < Nd_; ++i)

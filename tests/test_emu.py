@@ -235,3 +235,20 @@ def test_step_vs_numpy_restatement(lib):
     un, qn = npo.sbdf1_step(c, fl["dt"], fl["nu"], U, W, cfg["Lx"], cfg["Lz"], cfg["a"], cfg["b"])
     mine = u2.get().view(np.complex128)
     assert np.abs(mine - un).max() < 1e-12 * np.abs(un).max()
+
+
+def test_host_mirror_after_state_change(lib):
+    """Element access after the field changed on the device: a de-aliased spectral field downloads its retained box only,
+    so what the host mirror held for an earlier state must not show through in the aliased modes."""
+    ur = parity.ref_random(SMALL, 12)
+    ug = parity.to_gpu(lib, ur, padded=False)
+    mx_alias = SMALL["Nx"] // 2
+    ug.set_cmplx(mx_alias, 3, 0, 0, 1.0 + 2.0j)            # host mirror now holds an aliased-mode value
+    assert ug.cmplx(mx_alias, 3, 0, 0) == 1.0 + 2.0j
+    keep = ug.cmplx(1, 3, 1, 0)
+    ug.zero_padded_modes()                                 # device-side; the field is now flagged de-aliased
+    assert ug.padded()
+    assert ug.cmplx(mx_alias, 3, 0, 0) == 0.0              # box download: the stale mirror entry must be gone
+    assert ug.cmplx(1, 3, 1, 0) == keep
+    c = ug.get().view(np.complex128)
+    assert c[0, 3, mx_alias, 0] == 0.0                      # serial layout [i][ny][nx][mz]
