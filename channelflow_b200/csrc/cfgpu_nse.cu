@@ -697,6 +697,10 @@ int cfgpu_nse_solve(cfgpu_nse nse, int s, int nterms, const double* coef_h, cons
     }
     tp.uout = uout->d;
     tp.qout = qout->d;
+    {
+        static const int experiment = getenv("CF_TAU_EXPERIMENT_TILE_LAYOUT") ? 1 : 0;  // timing experiment, wrong results
+        tp.experiment_tile_layout = experiment;
+    }
     { StageTimer _t(nse->ctx, 5); CF_TRY(tau_solve_launch(tp, nse->ctx->stream)); }
     uout->xzstate = uout->ystate = qout->xzstate = qout->ystate = CFGPU_SPECTRAL;
     return 0;

@@ -24,7 +24,11 @@ constexpr double PI = 3.14159265358979323846264338327950288;
 __host__ __device__ __forceinline__ double cN(int m, int Nb) { return (m == 0 || m == Nb) ? 2.0 : 1.0; }
 __host__ __device__ __forceinline__ int betaN(int n, int Nb) { return (n > Nb - 2) ? 0 : 1; }
 // C&H 5.1.24 rows n >= 2 of the quasi-tridiagonal systems (helmholtz.cpp:44-56)
-__device__ __forceinline__ double A_lo(int n, int Nb, double lam) { return -(cN(n - 2, Nb) * lam) / (double)(4 * n * (n - 1)); }
+// sub-diagonal of A = lambda-weighted B row (helmholtz.cpp:44-52).  Written as -(lambda * B_lo) everywhere -- setup and
+// solve -- so that the solve kernel gets it from the B table with one multiply instead of a division per element.
+__host__ __device__ __forceinline__ double B_lo(int n, int Nb);
+__device__ __forceinline__ double A_lo_from_B(double blo, double lam) { return -(lam * blo); }
+__device__ __forceinline__ double A_lo(int n, int Nb, double lam) { return A_lo_from_B(cN(n - 2, Nb) / (double)(4 * n * (n - 1)), lam); }
 __device__ __forceinline__ double A_dg(int n, int Nb, double lam, double nus) {
     return nus + (betaN(n, Nb) * lam) / (double)(2 * (n * n - 1));
 }
@@ -159,9 +163,10 @@ template <int E>
 __device__ __forceinline__ void col_deriv(const double (&u)[E], double (&d)[E], double scale, int lane) {
     double c[E];
     double tot[2] = {0.0, 0.0};  // lane totals of the even-m / odd-m terms
+    const double n0d = (double)(lane * E);
 #pragma unroll
     for (int e = E - 1; e >= 0; --e) {
-        c[e] = scale * (lane * E + e) * u[e];
+        c[e] = scale * (n0d + (double)e) * u[e];
         tot[e & 1] = tot[e & 1] + c[e];
     }
     // inclusive suffix sum over lanes, then shift to exclusive
@@ -189,16 +194,17 @@ __device__ __forceinline__ void col_deriv(const double (&u)[E], double (&d)[E], 
 //   back substitution   x_n = g_n - up_n x_{n+2}         n = nl .. par+2          (bandedtridiag.cpp:258-262)
 //   bordered row        x_par = (bc - sum band_n x_n) / diag0                      (:263-268; diag0 in slot `par` of inv)
 //   forward elimination x_n = (x_n - lo_n x_{n-2}) inv_n  n = par+2 .. nl          (:269-273), lo_n = A_lo(n, lambda)
-// r (in) and x (out) are lane registers; up/inv/band/lo are skewed shared-memory columns, bt the B rows in HBM (L1).  If wall != nullptr the
+// r (in) and x (out) are lane registers; up/inv/band are skewed shared-memory columns (SKEW) or plain rows in global
+// memory, bt the B rows in HBM (L1), lo_n = -(lambda * B_lo(n)) costs one multiply.  If wall != nullptr the
 // sums  S_p = sum_{n = p mod 2} n^2 x_n  are returned in wall[0..1] (all lanes).
-template <int E>
+template <int E, bool SKEW>
 __device__ __forceinline__ void col_solve(const double (&r)[E], double (&x)[E], const double* __restrict__ up,
                                           const double* __restrict__ inv, const double* __restrict__ band,
-                                          const double* __restrict__ lo, const double* __restrict__ bt, const int N, const int lane,
+                                          const double lam, const double* __restrict__ bt, const int N, const int lane,
                                           const double bc0, const double bc1, double* wall) {
     const int Nb = N - 1;
-    const int n0 = lane * E, a0 = lane * (E + 1);
-    double g[E];
+    const int n0 = lane * E, a0 = SKEW ? lane * (E + 1) : lane * E;
+    double g[E], l[E];
     {
         // neighbours two rows away (other lanes at the block edges)
         double lo2[2], hi2[2];
@@ -212,12 +218,15 @@ __device__ __forceinline__ void col_solve(const double (&r)[E], double (&x)[E], 
             const int n = n0 + e;
             const double rm = e >= 2 ? r[e >= 2 ? e - 2 : 0] : lo2[e & 1];
             const double rp = e < E - 2 ? r[e < E - 2 ? e + 2 : 0] : hi2[e & 1];
-            double v = 0.0;
+            double v = 0.0, lv = 0.0;
             if (n >= 2 && n < N) {
-                v = __ldg(&bt[n]) * rm + __ldg(&bt[N + n]) * r[e];
+                const double blo = __ldg(&bt[n]);
+                v = blo * rm + __ldg(&bt[N + n]) * r[e];
                 v += __ldg(&bt[2 * N + n]) * rp;
+                lv = A_lo_from_B(blo, lam);
             }
             g[e] = v;
+            l[e] = lv;
         }
     }
     // ---- back substitution
@@ -275,13 +284,11 @@ __device__ __forceinline__ void col_solve(const double (&r)[E], double (&x)[E], 
     }
     // ---- forward elimination
     {
-        double l[E], iv[E];
+        double iv[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int n = n0 + e;
-            const bool in = n >= 2 && n < N;
-            l[e] = in ? lo[a0 + e] : 0.0;
-            iv[e] = in ? inv[a0 + e] : 0.0;
+            iv[e] = (n >= 2 && n < N) ? inv[a0 + e] : 0.0;
         }
         double A[2] = {1.0, 1.0}, B[2] = {0.0, 0.0};
 #pragma unroll
@@ -310,15 +317,16 @@ __device__ __forceinline__ void col_solve(const double (&r)[E], double (&x)[E], 
         vin[0] = shfl_up_or(B[0], 1, lane, 0.0);
         vin[1] = shfl_up_or(B[1], 1, lane, 0.0);
         double ws[2] = {0.0, 0.0};
+        const double n0d = (double)n0;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const int p = e & 1, n = n0 + e;
+            const int p = e & 1;
             double v;
             if (lane == 0 && e < 2) v = xpar[p];
             else v = (x[e] - l[e] * vin[p]) * iv[e];
             x[e] = v;
             vin[p] = v;
-            if (wall) ws[p] += (double)(n * n) * v;
+            if (wall) ws[p] += (n0d + (double)e) * (n0d + (double)e) * v;
         }
         if (wall) {
 #pragma unroll
@@ -530,8 +538,8 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
     const int tl = blockIdx.x;
     const bool is00 = tl == 0;
     const double scale = 4.0 / (td.b - td.a);
-    const long rs = (long)p.g.Nx * (2 * (p.g.Nz / 2 + 1));  // row (ny) stride in doubles
-    const long cs = rs * p.g.Ny;                            // component stride
+    const long rs_ser = (long)p.g.Nx * (2 * (p.g.Nz / 2 + 1));  // row (ny) stride in doubles
+    const long cs_ser = rs_ser * p.g.Ny;                        // component stride
     const int NP = tau_col_pitch(N, E);                     // column pitch (doubles)
     const int AS = TT * NP;                                 // doubles per profile array
     const int FS = TM * NP;                                 // doubles per factor array
@@ -539,8 +547,8 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
 
     double* Rx = dyn_smem<double>();
     double* Ry = Rx + AS; double* Rz = Ry + AS; double* Pq = Rz + AS;
-    double* Fup = Pq + AS; double* Finv = Fup + FS; double* Fband = Finv + FS; double* Flo = Fband + FS;
-    double* s_sc = Flo + FS;                     // [TSC_COUNT][TM]
+    double* Fup = Pq + AS; double* Finv = Fup + FS; double* Fband = Finv + FS;   // velocity-operator factors
+    double* s_sc = Fband + FS;                   // [TSC_COUNT][TM]
     const double* __restrict__ bt = td.btab();   // B rows [3][N] (mode independent, L1 resident)
     double* s_w = s_sc + TSC_COUNT * TM;         // [8][TT]
     long* s_off = reinterpret_cast<long*>(s_w + 8 * TT);  // [TM]
@@ -554,10 +562,24 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
         s_off[tid] = off;
     }
     for (int i = tid; i < TSC_COUNT * TM; i += NT) s_sc[i] = td.tile_sc(tl, 0)[i];
-    {   // pull this tile's factor block (contiguous) towards L2 while the history fields stream in
-        const char* blk = reinterpret_cast<const char*>(td.tile(tl));
-        const size_t bytes = td.tile_doubles() * sizeof(double);
-        for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)NT * 128) prefetch_l2(blk + o);
+    {   // velocity-operator factors (upV, invV, bandV contiguous, [m][n]) -> skewed shared columns, asynchronously: they
+        // are first needed after the pressure solve.  One (array, mode) row per warp at a time, no index divisions.
+        const double* fsrc = td.tile_arr(tl, TAR_UPV);
+        for (int row = warp; row < 3 * TM; row += NW) {
+            const double* src = fsrc + (size_t)row * N;
+            double* dst = Fup + row * NP;
+            for (int n = lane; n < N; n += 32) cp_async8(dst + col_addr<E>(n), src + n);
+        }
+        cp_async_commit();
+        // pull the pressure-operator factors (read straight from global by the solving warps) towards L2
+        // ... and the six correction profiles, used last
+        const char* blk = reinterpret_cast<const char*>(td.tile_arr(tl, TAR_UPP));
+        const size_t bytes = (size_t)3 * NM * sizeof(double);
+        for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)NT * 128) {
+            prefetch_l2(blk + o);
+            prefetch_l2(blk + 2 * bytes + o);
+            prefetch_l2(blk + 3 * bytes + o);
+        }
     }
     __syncthreads();
 
@@ -565,7 +587,9 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
     // Thread -> (mode m, row slot j): rows n = j, j + NT/TM, ..; all loads of two rows are issued before their use.
     {
         const int m = tid % TM, j0 = tid / TM, JS = NT / TM;   // NT % TM == 0 is guaranteed by the launcher
-        const long off = s_off[m];
+        long off = s_off[m];
+        long rs = rs_ser, cs = cs_ser;
+        if (p.experiment_tile_layout && off >= 0) { off = ((long)tl * 3 * N * TM + m) * 2; cs = (long)N * TM * 2; rs = TM * 2; }
         const int nterms = NTERMS > 0 ? NTERMS : p.nterms;
         if (off >= 0 && j0 < JS) {
             for (int comp = 0; comp < 3; ++comp) {
@@ -611,20 +635,14 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
                 }
             }
         }
-        // pressure-operator factors of this tile (upP, invP, bandP are contiguous, [m][n]) and its sub-diagonal
-        const double* fsrc = td.tile_arr(tl, TAR_UPP);
-        for (int i = tid; i < 3 * NM; i += NT) {
-            const int am = i / N, n = i - am * N;
-            Fup[am * NP + col_addr<E>(n)] = fsrc[i];
-        }
-        for (int i = tid; i < NM; i += NT) {
-            const int mm = i / N, n = i - mm * N;
-            Flo[mm * NP + col_addr<E>(n)] = n >= 2 ? A_lo(n, Nb, s_sc[TSC_LAMP * TM + mm]) : 0.0;
-        }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- S2: pressure Helmholtz  P'' - kappa^2 P = dRy/dy + i (kxx Rx + kzz Rz), P(+-1) = 0  (tausolver.cpp:357-366, 193-201)
+    // ---- S3: v particular solution  nu v'' - lambda v = P' - Ry, v(+-1) = 0, in place in Ry  (tausolver.cpp:203-210)
+    // Both act on column `col` only, so a warp carries P from one to the other in registers.  The pressure factors are
+    // used by the two columns of a mode only and come straight from global memory ([m][n] rows, prefetched to L2).
     for (int col = warp; col < TT; col += NW) {
         const int m = col >> 1, ri = col & 1;
         if (m >= nvalid) continue;
@@ -639,50 +657,30 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
 #pragma unroll
             for (int e = 0; e < E; ++e) r[e] = ri ? d[e] + (kxx * ox[e] + kzz * oz[e]) : d[e] - (kxx * ox[e] + kzz * oz[e]);
         }
-        col_solve<E>(r, x, Fup + m * NP, Finv + m * NP, Fband + m * NP, Flo + m * NP, bt, N, lane, 0.0, 0.0, nullptr);
+        const double* fP = td.tile_arr(tl, TAR_UPP) + (size_t)m * N;
+        col_solve<E, false>(r, x, fP, fP + NM, fP + 2 * NM, s_sc[TSC_LAMP * TM + m], bt, N, lane, 0.0, 0.0, nullptr);
         col_store<E>(Pq + col * NP, lane, N, x);
-    }
-    __syncthreads();
-
-    // ---- velocity-operator factors replace the pressure ones
-    {
-        const double* fsrc = td.tile_arr(tl, TAR_UPV);
-        for (int i = tid; i < 3 * NM; i += NT) {
-            const int am = i / N, n = i - am * N;
-            Fup[am * NP + col_addr<E>(n)] = fsrc[i];
+        if (is00) continue;
+        {
+            double d[E], y[E];
+            col_deriv<E>(x, d, scale, lane);
+            col_load<E>(Ry + col * NP, lane, N, y);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                r[e] = d[e] - y[e];
+                const int n = lane * E + e;  // Ry[Nb], Ry[Nb-1] are needed again by the tau correction
+                if (n == Nb) s_w[4 * TT + col] = y[e];
+                if (n == Nb - 1) s_w[5 * TT + col] = y[e];
+            }
         }
-        for (int i = tid; i < NM; i += NT) {
-            const int mm = i / N, n = i - mm * N;
-            Flo[mm * NP + col_addr<E>(n)] = n >= 2 ? A_lo(n, Nb, s_sc[TSC_LAMV * TM + mm]) : 0.0;
-        }
+        double wall[2];
+        col_solve<E, true>(r, x, Fup + m * NP, Finv + m * NP, Fband + m * NP, s_sc[TSC_LAMV * TM + m], bt, N, lane, 0.0, 0.0, wall);
+        col_store<E>(Ry + col * NP, lane, N, x);
+        if (lane == 0) { s_w[6 * TT + col] = wall[0]; s_w[7 * TT + col] = wall[1]; }
     }
     __syncthreads();
 
     if (!is00) {
-        // ---- S3: v particular solution  nu v'' - lambda v = P' - Ry, v(+-1) = 0, in place in Ry  (tausolver.cpp:203-210)
-        for (int col = warp; col < TT; col += NW) {
-            const int m = col >> 1;
-            if (m >= nvalid) continue;
-            double r[E], x[E];
-            {
-                double pq[E], d[E], y[E];
-                col_load<E>(Pq + col * NP, lane, N, pq);
-                col_deriv<E>(pq, d, scale, lane);
-                col_load<E>(Ry + col * NP, lane, N, y);
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    r[e] = d[e] - y[e];
-                    const int n = lane * E + e;  // Ry[Nb], Ry[Nb-1] are needed again by the tau correction
-                    if (n == Nb) s_w[4 * TT + col] = y[e];
-                    if (n == Nb - 1) s_w[5 * TT + col] = y[e];
-                }
-            }
-            double wall[2];
-            col_solve<E>(r, x, Fup + m * NP, Finv + m * NP, Fband + m * NP, Flo + m * NP, bt, N, lane, 0.0, 0.0, wall);
-            col_store<E>(Ry + col * NP, lane, N, x);
-            if (lane == 0) { s_w[6 * TT + col] = wall[0]; s_w[7 * TT + col] = wall[1]; }
-        }
-        __syncthreads();
         // ---- S4: influence-matrix (tausolver.cpp:178-191) and tau (tausolver.cpp:215-244) correction amplitudes.
         // v'(b) = (2/L) sum n^2 v_n, v'(a) = (2/L) sum (-1)^(n+1) n^2 v_n  (closed form of eval_b/eval_a of diff(v))
         const double* gPp = td.tile_arr(tl, TAR_PP); const double* gvp = td.tile_arr(tl, TAR_VP);
@@ -714,42 +712,48 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
             }
         }
         __syncthreads();
-        for (int e0 = tid; e0 < NM; e0 += 4 * NT) {
-            double gq[4][6];
+        // one (mode, half of the rows) item per warp: rows n = lane + 32*half + 64*k, four of them in flight
+        for (int item = warp; item < 2 * TM; item += NW) {
+            const int m = item >> 1;
+            if (m >= nvalid) continue;
+            const double dpr = s_w[2 * m], dpi = s_w[2 * m + 1], dmr = s_w[TT + 2 * m], dmi = s_w[TT + 2 * m + 1];
+            const double sNbr = s_w[2 * TT + 2 * m], sNbi = s_w[2 * TT + 2 * m + 1];
+            const double sNb1r = s_w[3 * TT + 2 * m], sNb1i = s_w[3 * TT + 2 * m + 1];
+            const int gm = m * N;
+            double* Pc = Pq + (2 * m) * NP;
+            double* Vc = Ry + (2 * m) * NP;
+            for (int nb = lane + 32 * (item & 1); nb < N; nb += 256) {
+                double gq[4][6];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const int e = e0 + h * NT;
-                if (e < NM) {
-                    gq[h][0] = gPp[e]; gq[h][1] = gvp[e]; gq[h][2] = gPm[e]; gq[h][3] = gvm[e];
-                    if (p.taucorr) { gq[h][4] = gP0[e]; gq[h][5] = gv0[e]; }
+                for (int h = 0; h < 4; ++h) {
+                    const int n = nb + 64 * h;
+                    if (n < N) {
+                        gq[h][0] = gPp[gm + n]; gq[h][1] = gvp[gm + n]; gq[h][2] = gPm[gm + n]; gq[h][3] = gvm[gm + n];
+                        if (p.taucorr) { gq[h][4] = gP0[gm + n]; gq[h][5] = gv0[gm + n]; }
+                    }
                 }
-            }
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const int e = e0 + h * NT;
-                if (e >= NM) break;
-                const int m = e / N, n = e - m * N;
-                if (m >= nvalid) continue;
-                const double pp = gq[h][0], vp = gq[h][1], pm = gq[h][2], vm = gq[h][3];
-                const int a = (2 * m) * NP + col_addr<E>(n);
-                double Pr = Pq[a], Pi = Pq[a + NP], Vr = Ry[a], Vi = Ry[a + NP];
-                const double dpr = s_w[2 * m], dpi = s_w[2 * m + 1], dmr = s_w[TT + 2 * m], dmi = s_w[TT + 2 * m + 1];
-                Pr += dpr * pp + dmr * pm;
-                Pi += dpi * pp + dmi * pm;
-                Vr += dpr * vp + dmr * vm;
-                Vi += dpi * vp + dmi * vm;
-                if (p.taucorr) {
-                    const double p0 = gq[h][4], v0 = gq[h][5];
-                    const double sNbr = s_w[2 * TT + 2 * m], sNbi = s_w[2 * TT + 2 * m + 1];
-                    const double sNb1r = s_w[3 * TT + 2 * m], sNb1i = s_w[3 * TT + 2 * m + 1];
-                    const bool ev = (n & 1) == 0;
-                    Pr += (ev ? sNb1r : sNbr) * p0;
-                    Pi += (ev ? sNb1i : sNbi) * p0;
-                    Vr += (ev ? sNbr : sNb1r) * v0;
-                    Vi += (ev ? sNbi : sNb1i) * v0;
+                for (int h = 0; h < 4; ++h) {
+                    const int n = nb + 64 * h;
+                    if (n >= N) break;
+                    const double pp = gq[h][0], vp = gq[h][1], pm = gq[h][2], vm = gq[h][3];
+                    const int a = col_addr<E>(n);
+                    double Pr = Pc[a], Pi = Pc[a + NP], Vr = Vc[a], Vi = Vc[a + NP];
+                    Pr += dpr * pp + dmr * pm;
+                    Pi += dpi * pp + dmi * pm;
+                    Vr += dpr * vp + dmr * vm;
+                    Vi += dpi * vp + dmi * vm;
+                    if (p.taucorr) {
+                        const double p0 = gq[h][4], v0 = gq[h][5];
+                        const bool ev = (n & 1) == 0;
+                        Pr += (ev ? sNb1r : sNbr) * p0;
+                        Pi += (ev ? sNb1i : sNbi) * p0;
+                        Vr += (ev ? sNbr : sNb1r) * v0;
+                        Vi += (ev ? sNbi : sNb1i) * v0;
+                    }
+                    Pc[a] = Pr; Pc[a + NP] = Pi;
+                    Vc[a] = Vr; Vc[a + NP] = Vi;
                 }
-                Pq[a] = Pr; Pq[a + NP] = Pi;
-                Ry[a] = Vr; Ry[a + NP] = Vi;
             }
         }
         __syncthreads();
@@ -782,7 +786,7 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
                 if (bulk00 && ri) r[e] = (lane * E + e == 0) ? td.nu : 0.0;
             }
         }
-        col_solve<E>(r, x, Fup + m * NP, Finv + m * NP, Fband + m * NP, Flo + m * NP, bt, N, lane, 0.0, 0.0, nullptr);
+        col_solve<E, true>(r, x, Fup + m * NP, Finv + m * NP, Fband + m * NP, s_sc[TSC_LAMV * TM + m], bt, N, lane, 0.0, 0.0, nullptr);
         col_store<E>(R + col * NP, lane, N, x);
     }
     __syncthreads();
@@ -816,7 +820,7 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
             const double mu = s_w[warp];
 #pragma unroll
             for (int e = 0; e < E; ++e) r[e] = -sv[e] + ((lane * E + e == 0) ? mu : 0.0);
-            col_solve<E>(r, x, Fup, Finv, Fband, Flo, bt, N, lane, 0.0, 0.0, nullptr);
+            col_solve<E, true>(r, x, Fup, Finv, Fband, s_sc[TSC_LAMV * TM], bt, N, lane, 0.0, 0.0, nullptr);
             col_store<E>(R, lane, N, x);
 #pragma unroll
             for (int e = 0; e < E; ++e) x[e] = 0.0;
@@ -826,10 +830,13 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
     }
 
     // ---- S6: scatter (nse.cpp:566-572)
+    const int tms = __ffs(TM) - 1;  // TM divides TAU_THREADS = 256: a power of two
     for (int e = tid; e < NM; e += NT) {
-        const int n = e / TM, m = e - n * TM;
-        const long off = s_off[m];
+        const int n = e >> tms, m = e & (TM - 1);
+        long off = s_off[m];
         if (off < 0) continue;
+        long rs = rs_ser, cs = cs_ser;
+        if (p.experiment_tile_layout) { off = ((long)tl * 3 * N * TM + m) * 2; cs = (long)N * TM * 2; rs = TM * 2; }
         const long go = n * rs + off;
         const int a = (2 * m) * NP + col_addr<E>(n);
         double2 V = make_double2(Ry[a], Ry[a + NP]);
@@ -837,7 +844,8 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
         *reinterpret_cast<double2*>(&p.uout[go]) = make_double2(Rx[a], Rx[a + NP]);
         *reinterpret_cast<double2*>(&p.uout[cs + go]) = V;
         *reinterpret_cast<double2*>(&p.uout[2 * cs + go]) = make_double2(Rz[a], Rz[a + NP]);
-        *reinterpret_cast<double2*>(&p.qout[go]) = make_double2(Pq[a], Pq[a + NP]);
+        const long goq = p.experiment_tile_layout ? ((long)tl * N * TM + m) * 2 + n * rs : go;
+        *reinterpret_cast<double2*>(&p.qout[goq]) = make_double2(Pq[a], Pq[a + NP]);
     }
 }
 
@@ -943,7 +951,7 @@ static size_t solve_smem(int N, int TM) {
     const int E = tau_pick_E(N);
     if (!E) return (size_t)1 << 30;
     const size_t NP = tau_col_pitch(N, E);
-    return ((size_t)12 * TM * NP + TSC_COUNT * TM + 16 * TM) * sizeof(double) + TM * sizeof(long);
+    return ((size_t)11 * TM * NP + TSC_COUNT * TM + 16 * TM) * sizeof(double) + TM * sizeof(long);
 }
 
 // modes per tile of the solve kernel: two CTAs per SM when the profiles are long (one streams while the other

@@ -74,6 +74,9 @@ struct TauSolveParams {
     double* dPd_act;   // device [2]: dPdxAct, dPdzAct written by the bulk-velocity solve
     // NSE::linear, bulk-velocity branch (nse.cpp:456-472): nu*(Ubase'(b)-Ubase'(a))/Ly and same for W
     double lin_base_dPdx, lin_base_dPdz;
+    // TIMING EXPERIMENT ONLY (env CF_TAU_EXPERIMENT_TILE_LAYOUT, results are meaningless): address the history fields
+    // and the outputs as if they were stored tile-major [tile][comp][n][TM], to measure what that layout would buy.
+    int experiment_tile_layout;
 };
 
 int tau_setup_launch(const TauData& td, const ModeGeom& g, double lambda_t, cudaStream_t stream);

@@ -76,6 +76,7 @@ static inline double __shfl_up_sync(unsigned, double v, int d, int = 32) {
     return cfemu::shfl_exchange_d(v, l - d >= 0 ? l - d : l);
 }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 template <class T> static inline T __ldcs(const T* p) { return *p; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
