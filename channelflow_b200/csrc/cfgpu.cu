@@ -421,7 +421,67 @@ int cfgpu_comm_ranges(cfgpu_ctx ctx, int nmx, int Ny, int rank, int* x0, int* x1
     return 0;
 }
 // All-gather of the owned kx rows of a spectral, de-aliased field.  Staging layout per owner s: [i][my][mxi in X_s][kz<=Kz].
+}  // extern "C"
+
+namespace cfgpu {
+// ------------------------------------------------------------------------------------------------ field layouts
+static int tile_alloc(cfgpu_field f, const TileGeom& g) {
+    const long long need = g.ntiles() * (long long)f->Ny * g.TM * 2 * f->Nd;
+    if (!f->dtile || f->ntile < need) {
+        if (f->dtile) { CF_CUDA(cudaStreamSynchronize(f->ctx->stream)); cudaFree(f->dtile); f->dtile = nullptr; }
+        if (cudaMalloc((void**)&f->dtile, need * sizeof(double)) != cudaSuccess) {
+            set_last_error("field: cudaMalloc of the tile-major buffer failed");
+            return 1;
+        }
+        f->ntile = need;
+        CF_CUDA(cudaMemsetAsync(f->dtile, 0, need * sizeof(double), f->ctx->stream));
+    }
+    f->tg = g;
+    return 0;
+}
+static bool layout_trace() {
+    static const bool on = getenv("CFGPU_LAYOUT_TRACE") != nullptr;  // report every layout conversion (they should not
+    return on;                                                      // occur inside the time-stepping loop)
+}
+int field_serial(cfgpu_field f) {
+    if (f->layout == 0) return 0;
+    if (layout_trace()) fprintf(stderr, "[cfgpu] field %p: tile-major -> serial\n", (void*)f);
+    const TileGeom& g = f->tg;
+    if (f->tile_outside_zero) {
+        if (!(f->clean_Kx >= 0 && f->clean_Kx <= g.Kx && f->clean_Kz >= 0 && f->clean_Kz <= g.Kz))
+            CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), f->ctx->stream));
+        f->clean_Kx = g.Kx; f->clean_Kz = g.Kz;
+    }
+    CF_TRY(tile_convert_launch(f->dser, f->dtile, f->Nx, f->Ny, f->Nz, f->Nd, g.Kx, g.Kz, g.x0, g.nq(), g.TM, 1, f->ctx->stream));
+    f->layout = 0;
+    return 0;
+}
+int field_tile(cfgpu_field f, const TileGeom& g) {
+    if (f->layout == 1 && f->tg.same(g)) return 0;
+    CF_TRY(field_serial(f));
+    CF_TRY(tile_alloc(f, g));
+    if (layout_trace()) fprintf(stderr, "[cfgpu] field %p: serial -> tile-major\n", (void*)f);
+    CF_TRY(tile_convert_launch(f->dser, f->dtile, f->Nx, f->Ny, f->Nz, f->Nd, g.Kx, g.Kz, g.x0, g.nq(), g.TM, 0, f->ctx->stream));
+    f->layout = 1;
+    f->tile_outside_zero = false;  // outside the box the serial buffer stays authoritative
+    return 0;
+}
+int field_tile_output(cfgpu_field f, const TileGeom& g, bool outside_zero) {
+    if (!(f->layout == 1 && f->tg.same(g))) {
+        // the serial buffer keeps defining the field outside the box unless the caller overwrites that with zeros
+        if (f->layout == 1 && !outside_zero) CF_TRY(field_serial(f));
+        CF_TRY(tile_alloc(f, g));
+        f->tile_outside_zero = false;
+    }
+    f->layout = 1;
+    if (outside_zero) f->tile_outside_zero = true;
+    return 0;
+}
+}  // namespace cfgpu
+
+extern "C" {
 int cfgpu_field_allgather(cfgpu_field f) {
+    CF_TRY(field_serial(f));
     cfgpu_ctx ctx = f->ctx;
     Comm& cm = ctx->comm;
     if (cm.nranks == 1) return 0;
@@ -432,7 +492,7 @@ int cfgpu_field_allgather(cfgpu_field f) {
     double2* S = reinterpret_cast<double2*>(ctx->ws_S.ptr);
     int x0, x1;
     part_range(nmx, cm.nranks, cm.rank, x0, x1);
-    CF_TRY(rows_pack_launch(f->d, reinterpret_cast<double*>(S + rows * nkz * x0), f->Nx, f->Nz, (int)rows, Kx, Kz, x0, x1, 0, ctx->stream));
+    CF_TRY(rows_pack_launch(f->dser, reinterpret_cast<double*>(S + rows * nkz * x0), f->Nx, f->Nz, (int)rows, Kx, Kz, x0, x1, 0, ctx->stream));
     std::vector<ExchangeMsg> msgs;
     for (int r = 0; r < cm.nranks; ++r) {
         if (r == cm.rank) continue;
@@ -445,7 +505,7 @@ int cfgpu_field_allgather(cfgpu_field f) {
         if (r == cm.rank) continue;
         int a, b;
         part_range(nmx, cm.nranks, r, a, b);
-        CF_TRY(rows_pack_launch(f->d, reinterpret_cast<double*>(S + rows * nkz * a), f->Nx, f->Nz, (int)rows, Kx, Kz, a, b, 1, ctx->stream));
+        CF_TRY(rows_pack_launch(f->dser, reinterpret_cast<double*>(S + rows * nkz * a), f->Nx, f->Nz, (int)rows, Kx, Kz, a, b, 1, ctx->stream));
     }
     return 0;
 }
@@ -460,12 +520,12 @@ int cfgpu_field_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, int Nd, double Lx,
     f->Nx = Nx; f->Ny = Ny; f->Nz = Nz; f->Nd = Nd;
     f->Lx = Lx; f->Lz = Lz; f->a = a; f->b = b;
     f->n = (long long)Nx * Ny * f->Nzpad() * Nd;
-    if (cudaMalloc((void**)&f->d, f->n * sizeof(double)) != cudaSuccess) {
+    if (cudaMalloc((void**)&f->dser, f->n * sizeof(double)) != cudaSuccess) {
         delete f;
         set_last_error("cfgpu_field_create: cudaMalloc failed");
         return 1;
     }
-    CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), ctx->stream));
+    CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), ctx->stream));
     f->clean_Kx = 0; f->clean_Kz = 0;  // all zero
     *out = f;
     return 0;
@@ -473,7 +533,8 @@ int cfgpu_field_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, int Nd, double Lx,
 int cfgpu_field_destroy(cfgpu_field f) {
     if (!f) return 0;
     cudaStreamSynchronize(f->ctx->stream);
-    cudaFree(f->d);
+    cudaFree(f->dser);
+    if (f->dtile) cudaFree(f->dtile);
     delete f;
     return 0;
 }
@@ -487,14 +548,16 @@ int cfgpu_host_free(void* p) {
     return 0;
 }
 int cfgpu_field_upload(cfgpu_field f, const double* h, int xz, int y) {
-    CF_CUDA(cudaMemcpyAsync(f->d, h, f->n * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
+    f->layout = 0;  // everything is overwritten
+    CF_CUDA(cudaMemcpyAsync(f->dser, h, f->n * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
     CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
     f->xzstate = xz; f->ystate = y;
     f->clean_Kx = f->clean_Kz = -1;
     return 0;
 }
 int cfgpu_field_download(cfgpu_field f, double* h) {
-    CF_CUDA(cudaMemcpyAsync(h, f->d, f->n * sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
+    CF_TRY(field_serial(f));
+    CF_CUDA(cudaMemcpyAsync(h, f->dser, f->n * sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
     CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
     return 0;
 }
@@ -515,7 +578,7 @@ static int box_copy(cfgpu_field f, double* h, bool to_device) {
         cudaMemcpy3DParms p;
         memset(&p, 0, sizeof p);
         cudaPitchedPtr hp = make_cudaPitchedPtr((void*)h, pitch, pitch, (size_t)f->Nx);
-        cudaPitchedPtr dp = make_cudaPitchedPtr((void*)f->d, pitch, pitch, (size_t)f->Nx);
+        cudaPitchedPtr dp = make_cudaPitchedPtr((void*)f->dser, pitch, pitch, (size_t)f->Nx);
         p.srcPtr = to_device ? hp : dp;
         p.dstPtr = to_device ? dp : hp;
         p.srcPos = make_cudaPos(0, (size_t)mx0, 0);
@@ -527,10 +590,11 @@ static int box_copy(cfgpu_field f, double* h, bool to_device) {
     return 0;
 }
 int cfgpu_field_upload_padded(cfgpu_field f, const double* h, int ystate) {
+    f->layout = 0;  // the box is overwritten, everything else zeroed (below, unless the serial buffer is known clean)
     const int Kx = f->Nx / 3 - 1, Kz = f->Nz / 3 - 1;
     CF_ARG(Kx >= 0 && Kz >= 0, "cfgpu_field_upload_padded: grid too small");
     if (!(f->clean_Kx >= 0 && f->clean_Kx <= Kx && f->clean_Kz >= 0 && f->clean_Kz <= Kz))
-        CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), f->ctx->stream));
+        CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), f->ctx->stream));
     CF_TRY(box_copy(f, const_cast<double*>(h), true));
     CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
     f->xzstate = CFGPU_SPECTRAL; f->ystate = ystate; f->padded = 1;
@@ -539,6 +603,7 @@ int cfgpu_field_upload_padded(cfgpu_field f, const double* h, int ystate) {
 }
 int cfgpu_field_download_padded(cfgpu_field f, double* h) {
     CF_ARG(f->xzstate == CFGPU_SPECTRAL, "cfgpu_field_download_padded: field must be xz-spectral");
+    CF_TRY(field_serial(f));
     CF_TRY(box_copy(f, h, false));
     CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
     return 0;
@@ -548,21 +613,41 @@ static bool same_shape(cfgpu_field a, cfgpu_field b) {
 }
 int cfgpu_field_copy(cfgpu_field dst, cfgpu_field src) {
     CF_ARG(same_shape(dst, src), "cfgpu_field_copy: shape mismatch");
-    CF_CUDA(cudaMemcpyAsync(dst->d, src->d, src->n * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    if (dst == src) return 0;
+    if (src->layout == 1) {
+        // the retained box lives in the tile buffer; outside it the field is zero (by flag, or because the serial buffer is
+        // known to be clean there) or what the serial buffer holds
+        const bool zero_out = src->tile_outside_zero || (src->clean_Kx >= 0 && src->clean_Kx <= src->tg.Kx &&
+                                                         src->clean_Kz >= 0 && src->clean_Kz <= src->tg.Kz);
+        CF_TRY(field_tile_output(dst, src->tg, zero_out));
+        CF_CUDA(cudaMemcpyAsync(dst->dtile, src->dtile, src->tg.ntiles() * src->tile_stride() * sizeof(double),
+                                cudaMemcpyDeviceToDevice, dst->ctx->stream));
+        dst->tile_outside_zero = zero_out;
+        if (!zero_out) {
+            CF_CUDA(cudaMemcpyAsync(dst->dser, src->dser, src->n * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
+            dst->clean_Kx = src->clean_Kx; dst->clean_Kz = src->clean_Kz;
+        }
+    } else {
+        dst->layout = 0;
+        CF_CUDA(cudaMemcpyAsync(dst->dser, src->dser, src->n * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
+        dst->clean_Kx = src->clean_Kx; dst->clean_Kz = src->clean_Kz;
+    }
     dst->xzstate = src->xzstate; dst->ystate = src->ystate; dst->padded = src->padded;
     dst->Lx = src->Lx; dst->Lz = src->Lz; dst->a = src->a; dst->b = src->b;
-    dst->clean_Kx = src->clean_Kx; dst->clean_Kz = src->clean_Kz;
     return 0;
 }
 int cfgpu_field_swap(cfgpu_field a, cfgpu_field b) {
     CF_ARG(same_shape(a, b), "cfgpu_field_swap: shape mismatch");
-    std::swap(a->d, b->d);
+    std::swap(a->dser, b->dser);
+    std::swap(a->dtile, b->dtile); std::swap(a->ntile, b->ntile); std::swap(a->layout, b->layout);
+    std::swap(a->tile_outside_zero, b->tile_outside_zero); std::swap(a->tg, b->tg);
     std::swap(a->xzstate, b->xzstate); std::swap(a->ystate, b->ystate); std::swap(a->padded, b->padded);
     std::swap(a->clean_Kx, b->clean_Kx); std::swap(a->clean_Kz, b->clean_Kz);
     return 0;
 }
 int cfgpu_field_zero(cfgpu_field f) {
-    CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), f->ctx->stream));
+    f->layout = 0;
+    CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), f->ctx->stream));
     f->clean_Kx = 0; f->clean_Kz = 0;
     return 0;
 }
@@ -570,45 +655,50 @@ int cfgpu_field_set_state(cfgpu_field f, int xz, int y) { f->xzstate = xz; f->ys
 int cfgpu_field_get_state(cfgpu_field f, int* xz, int* y) { *xz = f->xzstate; *y = f->ystate; return 0; }
 int cfgpu_field_set_padded(cfgpu_field f, int p) { f->padded = p; return 0; }
 int cfgpu_field_get_padded(cfgpu_field f, int* p) { *p = f->padded; return 0; }
-int cfgpu_field_device_ptr(cfgpu_field f, double** d, long long* n) { *d = f->d; if (n) *n = f->n; return 0; }
+int cfgpu_field_device_ptr(cfgpu_field f, double** d, long long* n) { CF_TRY(field_serial(f)); *d = f->dser; if (n) *n = f->n; return 0; }
 
 int cfgpu_field_axpby(cfgpu_field y, double a, cfgpu_field x, double b, cfgpu_field z) {
     CF_ARG(same_shape(y, x) && (!z || same_shape(y, z)), "cfgpu_field_axpby: shape mismatch");
-    CF_TRY(axpby_launch(y->d, a, x->d, b, z ? z->d : nullptr, (long)y->n, y->ctx->stream));
+    CF_TRY(field_serial(y)); CF_TRY(field_serial(x)); if (z) CF_TRY(field_serial(z));
+    CF_TRY(axpby_launch(y->dser, a, x->dser, b, z ? z->dser : nullptr, (long)y->n, y->ctx->stream));
     auto mrg = [](int p, int q) { return (p < 0 || q < 0) ? -1 : (p > q ? p : q); };
     y->clean_Kx = mrg(y->clean_Kx, x->clean_Kx); y->clean_Kz = mrg(y->clean_Kz, x->clean_Kz);
     if (z) { y->clean_Kx = mrg(y->clean_Kx, z->clean_Kx); y->clean_Kz = mrg(y->clean_Kz, z->clean_Kz); }
     return 0;
 }
 int cfgpu_field_scale(cfgpu_field y, double s) {
-    CF_TRY(scale_launch(y->d, s, (long)y->n, y->ctx->stream));
+    CF_TRY(field_serial(y));
+    CF_TRY(scale_launch(y->dser, s, (long)y->n, y->ctx->stream));
     return 0;
 }
 
 int cfgpu_field_get_profile(cfgpu_field f, int mx, int mz, int i, double* out_h) {
     CF_ARG(mx >= 0 && mx < f->Nx && mz >= 0 && mz < f->Mz() && i >= 0 && i < f->Nd, "cfgpu_field_get_profile: index");
+    CF_TRY(field_serial(f));
     cfgpu_ctx ctx = f->ctx;
     CF_TRY(ws_reserve(ctx->ws_red, 1 << 20));
     const long off0 = (long)i * f->Ny * f->Nx * f->Mz() + mz + (long)f->Mz() * mx;
-    CF_TRY(profile_get_launch(f->d, off0, (long)f->Nx * f->Mz(), f->Ny, ctx->ws_red.ptr, ctx->stream));
+    CF_TRY(profile_get_launch(f->dser, off0, (long)f->Nx * f->Mz(), f->Ny, ctx->ws_red.ptr, ctx->stream));
     CF_CUDA(cudaMemcpyAsync(out_h, ctx->ws_red.ptr, 2 * f->Ny * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CF_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 int cfgpu_field_add_profile(cfgpu_field f, int mx, int mz, int i, const double* in_h, double scale) {
     CF_ARG(mx >= 0 && mx < f->Nx && mz >= 0 && mz < f->Mz() && i >= 0 && i < f->Nd, "cfgpu_field_add_profile: index");
+    CF_TRY(field_serial(f));
     cfgpu_ctx ctx = f->ctx;
     CF_TRY(ws_reserve(ctx->ws_red, 1 << 20));
     CF_CUDA(cudaStreamSynchronize(ctx->stream));
     CF_CUDA(cudaMemcpyAsync(ctx->ws_red.ptr, in_h, 2 * f->Ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     const long off0 = (long)i * f->Ny * f->Nx * f->Mz() + mz + (long)f->Mz() * mx;
-    CF_TRY(profile_add_launch(f->d, off0, (long)f->Nx * f->Mz(), f->Ny, ctx->ws_red.ptr, scale, ctx->stream));
+    CF_TRY(profile_add_launch(f->dser, off0, (long)f->Nx * f->Mz(), f->Ny, ctx->ws_red.ptr, scale, ctx->stream));
     CF_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 int cfgpu_field_zero_padded_modes(cfgpu_field f) {
+    CF_TRY(field_serial(f));
     const int Kx = f->Nx / 3 - 1, Kz = f->Nz / 3 - 1;  // flowfield.h:578-584
-    CF_TRY(zero_padded_launch(f->d, f->Nx, f->Ny, f->Nz, f->Nd, Kx, Kz, f->ctx->stream));
+    CF_TRY(zero_padded_launch(f->dser, f->Nx, f->Ny, f->Nz, f->Nd, Kx, Kz, f->ctx->stream));
     f->padded = 1;
     f->clean_Kx = Kx; f->clean_Kz = Kz;
     return 0;
@@ -616,6 +706,7 @@ int cfgpu_field_zero_padded_modes(cfgpu_field f) {
 
 // ------------------------------------------------------------------------------------------------ generic y transform
 static int y_transform(cfgpu_field f, int mode) {
+    CF_TRY(field_serial(f));
     const YPlan* pl;
     CF_TRY(get_yplan(f->ctx, f->Ny, f->a, f->b, &pl));
     const long ncols = f->rowstride();
@@ -636,8 +727,8 @@ static int y_transform(cfgpu_field f, int mode) {
         p.njobs = 0;
         for (int i = i0; i < f->Nd && p.njobs < YG_MAXJOB; ++i) {
             YGemmJob& j = p.job[p.njobs++];
-            j.in = f->d + i * f->compstride();
-            j.out[0] = f->d + i * f->compstride();
+            j.in = f->dser + i * f->compstride();
+            j.out[0] = f->dser + i * f->compstride();
             j.nmat = 1; j.mat0 = 0;
         }
         CF_TRY(ygemm_launch(p, f->ctx->stream));
@@ -661,6 +752,7 @@ int cfgpu_field_make_spectral_y(cfgpu_field f) {
 // generic xz transforms live in cfgpu_xzgen.cu
 int cfgpu_xz_generic(cfgpu_field f, int to_physical);
 int cfgpu_field_make_physical_xz(cfgpu_field f) {
+    CF_TRY(field_serial(f));
     if (f->xzstate == CFGPU_PHYSICAL) return 0;
     CF_TRY(cfgpu_xz_generic(f, 1));
     f->xzstate = CFGPU_PHYSICAL;
@@ -668,6 +760,7 @@ int cfgpu_field_make_physical_xz(cfgpu_field f) {
     return 0;
 }
 int cfgpu_field_make_spectral_xz(cfgpu_field f) {
+    CF_TRY(field_serial(f));
     if (f->xzstate == CFGPU_SPECTRAL) return 0;
     CF_TRY(cfgpu_xz_generic(f, 0));
     f->xzstate = CFGPU_SPECTRAL;
@@ -685,6 +778,7 @@ int cfgpu_field_make_spectral(cfgpu_field f) {
 
 // ------------------------------------------------------------------------------------------------ norms
 static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool padded, double* out_h, bool skip_kx0 = false) {
+    CF_TRY(field_serial(u)); if (v) CF_TRY(field_serial(v));
     CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "L2 norm: field must be spectral");
     cfgpu_ctx ctx = u->ctx;
     const YPlan* pl;
@@ -702,7 +796,7 @@ static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool pa
         part_range(2 * Kx + 1, ctx->comm.nranks, ctx->comm.rank, x0, x1);
     }
     if (skip_kx0 && x0 < 1) x0 = 1;  // row 0 is kx = 0 in both enumerations
-    CF_TRY(l2form_launch(u->d, v ? v->d : nullptr, mode, pl->Wgram, u->Ny, u->Nx, u->Nz, u->Nd, Kx, Kz, padded ? 0 : 1, x0, x1, scale,
+    CF_TRY(l2form_launch(u->dser, v ? v->dser : nullptr, mode, pl->Wgram, u->Ny, u->Nx, u->Nz, u->Nd, Kx, Kz, padded ? 0 : 1, x0, x1, scale,
                          partial, cap, out_dev, ctx->stream));
     CF_TRY(comm_allreduce(ctx->comm, out_dev, 1, 0, ctx->stream));
     CF_CUDA(cudaMemcpyAsync(out_h, out_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

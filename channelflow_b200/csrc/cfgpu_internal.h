@@ -40,6 +40,16 @@ struct ModeBox {
     long* runstart_full = nullptr;  // device [2Kx+1]: offset (doubles) of the kz-run of retained mx in a field row
 };
 
+// Tile-major field layout of de-aliased spectral fields: [tile][component][ny][TM] complex over the retained modes
+// q = (mxi - x0)*(Kz+1) + kz of this rank in natural order, TM per tile (the tiling of the tau solver, tau.cuh).  What a CTA
+// of the tau solve reads of the six history fields is then contiguous instead of 64-byte pieces a row apart.
+struct TileGeom {
+    int TM = 0, Kx = 0, Kz = 0, x0 = 0, x1 = 0;
+    int nq() const { return (x1 - x0) * (Kz + 1); }
+    long ntiles() const { return (nq() + TM - 1) / TM; }
+    bool same(const TileGeom& o) const { return TM == o.TM && Kx == o.Kx && Kz == o.Kz && x0 == o.x0 && x1 == o.x1; }
+};
+
 struct Workspace {
     size_t bytes = 0;
     double* ptr = nullptr;
@@ -79,8 +89,20 @@ struct cfgpu_field_s {
     int xzstate = CFGPU_SPECTRAL, ystate = CFGPU_SPECTRAL;
     int padded = 0;
     int clean_Kx = -1, clean_Kz = -1;  // all modes outside this box are known to be exactly zero (-1: unknown)
-    double* d = nullptr;
+    // The data lives in one of two buffers.  `dser` is the reference's serial layout [i][my][mx][mz] (always allocated);
+    // `dtile` (lazily allocated) is the tile-major layout of the retained box, produced and consumed by the DNS hot path
+    // (cfgpu_nse_solve / cfgpu_nse_nonlinear).  layout says which one is current for the retained box; outside the box
+    // the field is zero if tile_outside_zero, else whatever dser holds there.  Everything but the hot path goes through
+    // field_serial(), which converts back on demand.
+    double* dser = nullptr;
     long long n = 0;  // doubles
+    double* dtile = nullptr;
+    long long ntile = 0;
+    int layout = 0;   // 0: dser current, 1: dtile current
+    bool tile_outside_zero = false;
+    cfgpu::TileGeom tg;
+    long long tile_compstride() const { return (long long)Ny * tg.TM * 2; }
+    long long tile_stride() const { return tile_compstride() * Nd; }
     int Nzpad() const { return 2 * (Nz / 2 + 1); }
     int Mz() const { return Nz / 2 + 1; }
     long long rowstride() const { return (long long)Nx * Nzpad(); }
@@ -103,12 +125,18 @@ struct cfgpu_nse_s {
     std::vector<double> lambda_t;
     std::vector<cfgpu::TauData> tau;  // one per substep
     int TM_solve = 8, TM_lin = 8;
+    bool use_tile = false;       // hot-path fields (solve outputs, nonlinear term) are kept tile-major
+    cfgpu::TileGeom tg;
+    long* d_tilestart = nullptr; // device [ntiles]: offset of tile t of a 3-component tile-major field
     double** d_rows[2] = {nullptr, nullptr};  // peer row tables of the inverse y-GEMM outputs (5- and 3-field staging)
     void* rows_baseS = nullptr;
     cfgpu_field s_u = nullptr, s_t = nullptr;  // scratch fields of the non-rotational nonlinear terms (3 and 9 components)
 };
 
 namespace cfgpu {
+int field_serial(cfgpu_field f);                                           // make dser current (tile -> serial if needed)
+int field_tile(cfgpu_field f, const TileGeom& g);                          // make dtile current (serial -> tile if needed)
+int field_tile_output(cfgpu_field f, const TileGeom& g, bool outside_zero);  // dtile becomes current, contents to be written
 int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out);
 int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out);
 int get_box(cfgpu_ctx ctx, int Nx, int Nz, int Kx, int Kz, const ModeBox** out);

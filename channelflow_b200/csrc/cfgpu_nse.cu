@@ -125,6 +125,28 @@ static void fill_xsplit(cfgpu_nse nse, XPassParams& xp, int nstage) {
     }
 }
 
+// Spectral side of a y-GEMM on a 3-component field in either layout: columns are the rank's retained modes in natural
+// order; the serial layout has one run of kz per kx row, the tile-major layout one run of TM modes per tile.
+struct SpecAddr { int runlen; const long* runstart; long ld; long compstride; double* base; };
+static SpecAddr spec_addr(cfgpu_nse nse, cfgpu_field f, const ModeBox* bx) {
+    if (f->layout == 1)
+        return {2 * f->tg.TM, nse->d_tilestart, 2L * f->tg.TM, (long)f->tile_compstride(), f->dtile};
+    return {2 * (nse->Kz + 1), bx->runstart_full + nse->x0, (long)f->rowstride(), (long)f->compstride(), f->dser};
+}
+// input of the hot path: tile-major data of another geometry goes back to the serial layout first
+static int spec_input(cfgpu_nse nse, cfgpu_field u) {
+    if (u->layout == 1 && !u->tg.same(nse->tg)) return field_serial(u);
+    return 0;
+}
+// output of the hot path (all retained modes are written, everything else is zero): tile-major when enabled
+static int spec_output(cfgpu_nse nse, cfgpu_field f) {
+    if (nse->use_tile) return field_tile_output(f, nse->tg, true);
+    f->layout = 0;
+    if (!(f->clean_Kx >= 0 && f->clean_Kx <= nse->Kx && f->clean_Kz >= 0 && f->clean_Kz <= nse->Kz))
+        CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), nse->ctx->stream));
+    return 0;
+}
+
 // spectral u (3 comps, reference layout; this rank's kx rows) -> compact pencils P[0..nout) (y physical), all-to-all,
 // then Q (x physical) for this rank's y planes
 static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
@@ -159,11 +181,13 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     p.A1[0] = yp->Ce; p.A2[0] = yp->Co; p.sgn[0] = 1.0;
     p.A1[1] = yp->CDe; p.A2[1] = yp->CDo; p.sgn[1] = -1.0;
     p.ncols = (long)nxl * nkz * 2;
-    p.in_runlen = 2 * nkz; p.in_runstart = bx->runstart_full + nse->x0; p.in_ld = u->rowstride();
+    CF_TRY(spec_input(nse, u));
+    const SpecAddr ua = spec_addr(nse, u, bx);
+    p.in_runlen = ua.runlen; p.in_runstart = ua.runstart; p.in_ld = ua.ld;
     p.out_runlen = 1; p.out_runstart = nullptr; p.out_ld = (long)nxl * nkz * 2;
     p.njobs = 3;
     for (int i = 0; i < 3; ++i) {
-        p.job[i].in = u->d + i * u->compstride();
+        p.job[i].in = ua.base + i * ua.compstride;
         p.job[i].out[0] = P + i * Pf;
         p.job[i].nmat = 1; p.job[i].mat0 = 0;
     }
@@ -290,6 +314,15 @@ int cfgpu_nse_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, double Lx, double Lz
     nse->geom.Lx = Lx; nse->geom.Lz = Lz;
     nse->TM_solve = tau_pick_TM_solve(nse->Nyd);
     nse->TM_lin = tau_pick_TM(nse->Nyd, 5 * 2 * 8);
+    // tile-major layout of the hot-path fields: de-aliased runs only (the retained box is then all a field holds)
+    nse->tg.TM = nse->TM_solve; nse->tg.Kx = nse->Kx; nse->tg.Kz = nse->Kz; nse->tg.x0 = nse->x0; nse->tg.x1 = nse->x1;
+    nse->use_tile = cfg->dealias_xz && nse->Nyd == Ny && !getenv("CFGPU_SERIAL_LAYOUT");
+    if (nse->use_tile) {
+        std::vector<long> ts((size_t)nse->tg.ntiles());
+        for (size_t t = 0; t < ts.size(); ++t) ts[t] = (long)t * 3 * Ny * nse->tg.TM * 2;
+        CF_CUDA(cudaMalloc((void**)&nse->d_tilestart, ts.size() * sizeof(long)));
+        CF_CUDA(cudaMemcpy(nse->d_tilestart, ts.data(), ts.size() * sizeof(long), cudaMemcpyHostToDevice));
+    }
 
     // base-flow data: Ubaseyy, Wbaseyy (spectral), physical U,U',W,W', 1/dy
     std::vector<double> U(Ny, 0.0), W(Ny, 0.0), Uy, Uyy, Wy, Wyy, t;
@@ -344,6 +377,7 @@ int cfgpu_nse_destroy(cfgpu_nse nse) {
     if (nse->s_t) cfgpu_field_destroy(nse->s_t);
     cudaFree(nse->d_base);
     cudaFree(nse->d_scal);
+    if (nse->d_tilestart) cudaFree(nse->d_tilestart);
     delete nse;
     return 0;
 }
@@ -412,11 +446,13 @@ static int nonlinear_fused_general(cfgpu_nse nse, cfgpu_field u, cfgpu_field f, 
         p.A1[0] = yp->Ce; p.A2[0] = yp->Co; p.sgn[0] = 1.0;
         p.A1[1] = yp->CDe; p.A2[1] = yp->CDo; p.sgn[1] = -1.0;
         p.ncols = (long)nmx * nkz * 2;
-        p.in_runlen = 2 * nkz; p.in_runstart = bx->runstart_full; p.in_ld = u->rowstride();
+        CF_TRY(spec_input(nse, u));
+        const SpecAddr ua = spec_addr(nse, u, bx);
+        p.in_runlen = ua.runlen; p.in_runstart = ua.runstart; p.in_ld = ua.ld;
         p.out_runlen = 1; p.out_runstart = nullptr; p.out_ld = (long)nmx * nkz * 2;
         p.njobs = 3;
         for (int i = 0; i < 3; ++i) {
-            p.job[i].in = u->d + i * u->compstride();
+            p.job[i].in = ua.base + i * ua.compstride;
             p.job[i].out[0] = P + i * Pf;
             p.job[i].out[1] = P + (3 + i) * Pf;
             p.job[i].nmat = grad ? 2 : 1; p.job[i].mat0 = 0;
@@ -470,8 +506,8 @@ static int nonlinear_fused_general(cfgpu_nse nse, cfgpu_field u, cfgpu_field f, 
         StageTimer _t(ctx, 3);
         CF_TRY(xpass_forward_launch(xp, ctx->stream));
     }
-    if (!(f->clean_Kx >= 0 && f->clean_Kx <= nse->Kx && f->clean_Kz >= 0 && f->clean_Kz <= nse->Kz))
-        CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), ctx->stream));
+    CF_TRY(spec_output(nse, f));
+    const SpecAddr fa = spec_addr(nse, f, bx);
     {   // forward y: f_i = F H_i + GD C_i
         YGemmParams p;
         memset(&p, 0, sizeof p);
@@ -481,19 +517,19 @@ static int nonlinear_fused_general(cfgpu_nse nse, cfgpu_field u, cfgpu_field f, 
         p.A1b = yp->GDe[cd == 0.5 ? 1 : 0]; p.A2b = yp->GDo[cd == 0.5 ? 1 : 0];
         p.ncols = (long)nmx * nkz * 2;
         p.in_runlen = 1; p.in_runstart = nullptr; p.in_ld = (long)nmx * nkz * 2;
-        p.out_runlen = 2 * nkz; p.out_runstart = bx->runstart_full; p.out_ld = f->rowstride();
+        p.out_runlen = fa.runlen; p.out_runstart = fa.runstart; p.out_ld = fa.ld;
         p.njobs = 3;
         for (int i = 0; i < 3; ++i) {
             p.job[i].in = P + i * Pf;
             p.job[i].in2 = prod ? P + (3 + i) * Pf : nullptr;
-            p.job[i].out[0] = f->d + i * f->compstride();
+            p.job[i].out[0] = fa.base + i * fa.compstride;
             p.job[i].nmat = 1; p.job[i].mat0 = 0;
         }
         StageTimer _t(ctx, 4);
         CF_TRY(ygemm_launch(p, ctx->stream));
     }
     f->xzstate = CFGPU_SPECTRAL; f->ystate = CFGPU_SPECTRAL;
-    f->clean_Kx = nse->Kx; f->clean_Kz = nse->Kz;
+    if (f->layout == 0) { f->clean_Kx = nse->Kx; f->clean_Kz = nse->Kz; }  // (the flags describe the serial buffer)
     if (nse->cfg.dealias_xz) f->padded = 1;
     return 0;
 }
@@ -515,6 +551,8 @@ static int nonlinear_generic(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
             }
         }
     }
+    CF_TRY(field_serial(u));
+    f->layout = 0;  // written in the serial layout below
     if (!nse->s_u) CF_TRY(cfgpu_field_create(ctx, nse->Nx, nse->Ny, nse->Nz, 3, nse->Lx, nse->Lz, nse->a, nse->b, &nse->s_u));
     cfgpu_field su = nse->s_u;
     FieldGeom g{nse->Nx, nse->Ny, nse->Nz, nse->Lx, nse->Lz, nse->a, nse->b};
@@ -523,7 +561,7 @@ static int nonlinear_generic(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     int method = nse->cfg.nonlinearity;
     if (method == 6) {  // LinearAboutProfile (diffops.cpp:3288-3365)
         CF_TRY(cfgpu_field_make_physical_y(su));
-        CF_TRY(linearized_launch(su->d, f->d, nse->d_base + 2 * nse->Ny, g, ctx->stream));
+        CF_TRY(linearized_launch(su->dser, f->dser, nse->d_base + 2 * nse->Ny, g, ctx->stream));
         f->xzstate = CFGPU_SPECTRAL; f->ystate = CFGPU_PHYSICAL; f->clean_Kx = f->clean_Kz = -1;
         CF_TRY(cfgpu_field_make_spectral_y(f));
     } else {
@@ -533,37 +571,37 @@ static int nonlinear_generic(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         cfgpu_field st = nse->s_t;
         const double rot = nse->cfg.rotation;
         // u_tot = u + Ubase e_x + Wbase e_z - Vsuck e_y on the (0,0) mode (nse.cpp:28-36)
-        CF_TRY(add_base00_launch(su->d, nse->has_Ubaseyy ? nse->d_base + 7 * nse->Ny : nullptr,
+        CF_TRY(add_base00_launch(su->dser, nse->has_Ubaseyy ? nse->d_base + 7 * nse->Ny : nullptr,
                                  nse->has_Wbaseyy ? nse->d_base + 8 * nse->Ny : nullptr, nse->cfg.Vsuck, 1.0, g, ctx->stream));
         if (method == 1 || method == 3) {  // grad(u) (diffops.cpp:3169-3173, 3606-3609)
-            CF_TRY(grad3_launch(su->d, st->d, g, ctx->stream));
+            CF_TRY(grad3_launch(su->dser, st->dser, g, ctx->stream));
             st->xzstate = st->ystate = CFGPU_SPECTRAL; st->clean_Kx = st->clean_Kz = -1;
             CF_TRY(cfgpu_field_make_physical(st));
         }
         CF_TRY(cfgpu_field_make_physical(su));
         if (method == 1) {         // convectionNL = dotgrad(u,u) (diffops.cpp:2883-2885, 3586-3643)
-            CF_TRY(pointwise_nl_launch(su->d, st->d, f->d, 1.0, 0, 0.0, nreal, ctx->stream));
+            CF_TRY(pointwise_nl_launch(su->dser, st->dser, f->dser, 1.0, 0, 0.0, nreal, ctx->stream));
             f->xzstate = f->ystate = CFGPU_PHYSICAL; f->clean_Kx = f->clean_Kz = -1;
             CF_TRY(cfgpu_field_make_spectral(f));
             // REFERENCE QUIRK, reproduced: dotgrad ignores `finalstate` and returns f spectral, yet navierstokesNL then adds
             // the Coriolis term of the physical u to f's raw array and its closing f.makeSpectral() is a no-op
             // (nse.cpp:63-79 after diffops.cpp:3640).  Only the rotational and skew-symmetric forms honour finalstate.
-            if (rot != 0.0) CF_TRY(coriolis_launch(su->d, f->d, rot, nreal, nse->Nz, ctx->stream));
+            if (rot != 0.0) CF_TRY(coriolis_launch(su->dser, f->dser, rot, nreal, nse->Nz, ctx->stream));
         } else if (method == 3) {  // skewsymmetricNL (diffops.cpp:3142-3286)
-            CF_TRY(pointwise_nl_launch(su->d, st->d, f->d, 0.5, 1, rot, nreal, ctx->stream));
+            CF_TRY(pointwise_nl_launch(su->dser, st->dser, f->dser, 0.5, 1, rot, nreal, ctx->stream));
             f->xzstate = f->ystate = CFGPU_PHYSICAL; f->clean_Kx = f->clean_Kz = -1;
             st->xzstate = st->ystate = CFGPU_PHYSICAL;
             CF_TRY(cfgpu_field_make_spectral(st));
             CF_TRY(cfgpu_field_make_spectral(f));
-            CF_TRY(div9_launch(st->d, f->d, 0.5, 1, g, ctx->stream));
+            CF_TRY(div9_launch(st->dser, f->dser, 0.5, 1, g, ctx->stream));
         } else {                   // divergenceNL (diffops.cpp:3110-3134)
-            CF_TRY(pointwise_nl_launch(su->d, st->d, f->d, 0.0, 1, 0.0, nreal, ctx->stream));
+            CF_TRY(pointwise_nl_launch(su->dser, st->dser, f->dser, 0.0, 1, 0.0, nreal, ctx->stream));
             st->xzstate = st->ystate = CFGPU_PHYSICAL; st->clean_Kx = st->clean_Kz = -1;
             CF_TRY(cfgpu_field_make_spectral(st));
-            CF_TRY(div9_launch(st->d, f->d, 1.0, 0, g, ctx->stream));
+            CF_TRY(div9_launch(st->dser, f->dser, 1.0, 0, g, ctx->stream));
             f->xzstate = f->ystate = CFGPU_SPECTRAL; f->clean_Kx = f->clean_Kz = -1;
             // same reference quirk as for the convection form: div(uu, f, Physical) leaves f spectral (diffops.cpp:2555-2557)
-            if (rot != 0.0) CF_TRY(coriolis_launch(su->d, f->d, rot, nreal, nse->Nz, ctx->stream));
+            if (rot != 0.0) CF_TRY(coriolis_launch(su->dser, f->dser, rot, nreal, nse->Nz, ctx->stream));
         }
     }
     f->xzstate = f->ystate = CFGPU_SPECTRAL;
@@ -623,8 +661,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
 
     // aliased modes of f must be exactly zero (FlowField::zeroPaddedModes, nse.cpp:389-390); the kernels below
     // only ever write retained modes
-    if (!(f->clean_Kx >= 0 && f->clean_Kx <= nse->Kx && f->clean_Kz >= 0 && f->clean_Kz <= nse->Kz))
-        CF_CUDA(cudaMemsetAsync(f->d, 0, f->n * sizeof(double), ctx->stream));
+    CF_TRY(spec_output(nse, f));
 
     const YPlan* yp;
     const ModeBox* bx;
@@ -639,11 +676,12 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     p.A1[0] = yp->Fe; p.A2[0] = yp->Fo; p.sgn[0] = 1.0;
     p.ncols = (long)nxl * nkz * 2;
     p.in_runlen = 1; p.in_runstart = nullptr; p.in_ld = (long)nxl * nkz * 2;
-    p.out_runlen = 2 * nkz; p.out_runstart = bx->runstart_full + nse->x0; p.out_ld = f->rowstride();
+    const SpecAddr fa = spec_addr(nse, f, bx);
+    p.out_runlen = fa.runlen; p.out_runstart = fa.runstart; p.out_ld = fa.ld;
     p.njobs = 3;
     for (int i = 0; i < 3; ++i) {
         p.job[i].in = ctx->ws_P.ptr + i * Pf;
-        p.job[i].out[0] = f->d + i * f->compstride();
+        p.job[i].out[0] = fa.base + i * fa.compstride;
         p.job[i].nmat = 1; p.job[i].mat0 = 0;
     }
     if (!multi || peer) {
@@ -660,7 +698,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         }
     }
     f->xzstate = CFGPU_SPECTRAL; f->ystate = CFGPU_SPECTRAL;
-    f->clean_Kx = nse->Kx; f->clean_Kz = nse->Kz;
+    if (f->layout == 0) { f->clean_Kx = nse->Kx; f->clean_Kz = nse->Kz; }  // (the flags describe the serial buffer)
     if (nse->cfg.dealias_xz) f->padded = 1;
     return 0;
 }
@@ -692,15 +730,22 @@ int cfgpu_nse_solve(cfgpu_nse nse, int s, int nterms, const double* coef_h, cons
     for (int j = 0; j < nterms; ++j) {
         CF_ARG(terms[j]->Nd == 3 && terms[j]->Nx == nse->Nx && terms[j]->Ny == nse->Ny && terms[j]->Nz == nse->Nz,
                "cfgpu_nse_solve: term shape mismatch");
-        tp.term[j] = terms[j]->d;
+        if (nse->use_tile) CF_TRY(field_tile(terms[j], nse->tg));
+        else CF_TRY(field_serial(terms[j]));
+        tp.term[j] = nse->use_tile ? terms[j]->dtile : terms[j]->dser;
         tp.coef[j] = coef_h[j];
     }
-    tp.uout = uout->d;
-    tp.qout = qout->d;
-    {
-        static const int experiment = getenv("CF_TAU_EXPERIMENT_TILE_LAYOUT") ? 1 : 0;  // timing experiment, wrong results
-        tp.experiment_tile_layout = experiment;
+    // only the retained box of the outputs is written; whatever they hold outside it stays (nse.cpp:566-572)
+    if (nse->use_tile) {
+        CF_TRY(field_tile_output(uout, nse->tg, false));
+        CF_TRY(field_tile_output(qout, nse->tg, false));
+    } else {
+        CF_TRY(field_serial(uout));
+        CF_TRY(field_serial(qout));
     }
+    tp.uout = nse->use_tile ? uout->dtile : uout->dser;
+    tp.qout = nse->use_tile ? qout->dtile : qout->dser;
+    tp.tile_layout = nse->use_tile ? 1 : 0;
     { StageTimer _t(nse->ctx, 5); CF_TRY(tau_solve_launch(tp, nse->ctx->stream)); }
     uout->xzstate = uout->ystate = qout->xzstate = qout->ystate = CFGPU_SPECTRAL;
     return 0;
@@ -711,7 +756,8 @@ int cfgpu_nse_linear(cfgpu_nse nse, cfgpu_field u, cfgpu_field q, cfgpu_field L)
     CF_ARG(!nse->tau.empty(), "cfgpu_nse_linear: call reset_lambda first");
     TauSolveParams tp;
     CF_TRY(fill_tau_params(nse, 0, tp));
-    { StageTimer _t(nse->ctx, 6); CF_TRY(linear_launch(tp, u->d, q->d, L->d, nse->ctx->stream)); }
+    CF_TRY(field_serial(u)); CF_TRY(field_serial(q)); CF_TRY(field_serial(L));
+    { StageTimer _t(nse->ctx, 6); CF_TRY(linear_launch(tp, u->dser, q->dser, L->dser, nse->ctx->stream)); }
     L->xzstate = L->ystate = CFGPU_SPECTRAL;
     return 0;
 }

@@ -112,21 +112,21 @@ extern "C" int cfgpu_xz_generic(cfgpu_field f, int to_physical) {
     if (to_physical) {
         auto kx = xgen_kernel<+1>;
         if (smx > cfg_xi) { CF_CUDA(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smx)); cfg_xi = smx; }
-        CF_LAUNCH(kx, gx, dim3(XG_THREADS), smx, ctx->stream, reinterpret_cast<double2*>(f->d), f->Nx, Mz, TZ, *fx);
+        CF_LAUNCH(kx, gx, dim3(XG_THREADS), smx, ctx->stream, reinterpret_cast<double2*>(f->dser), f->Nx, Mz, TZ, *fx);
         CF_KERNEL_CHECK();
         auto kz = zgen_c2r_kernel;
         if (smz > cfg_zc) { CF_CUDA(cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smz)); cfg_zc = smz; }
-        CF_LAUNCH(kz, gz, dim3(XG_THREADS), smz, ctx->stream, f->d, nlines, f->Nz, TP, *fz);
+        CF_LAUNCH(kz, gz, dim3(XG_THREADS), smz, ctx->stream, f->dser, nlines, f->Nz, TP, *fz);
         CF_KERNEL_CHECK();
     } else {
         auto kz = zgen_r2c_kernel;
         if (smz > cfg_zr) { CF_CUDA(cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smz)); cfg_zr = smz; }
         const double scale = 1.0 / ((double)f->Nx * (double)f->Nz);
-        CF_LAUNCH(kz, gz, dim3(XG_THREADS), smz, ctx->stream, f->d, nlines, f->Nz, TP, scale, *fz);
+        CF_LAUNCH(kz, gz, dim3(XG_THREADS), smz, ctx->stream, f->dser, nlines, f->Nz, TP, scale, *fz);
         CF_KERNEL_CHECK();
         auto kx = xgen_kernel<-1>;
         if (smx > cfg_xf) { CF_CUDA(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smx)); cfg_xf = smx; }
-        CF_LAUNCH(kx, gx, dim3(XG_THREADS), smx, ctx->stream, reinterpret_cast<double2*>(f->d), f->Nx, Mz, TZ, *fx);
+        CF_LAUNCH(kx, gx, dim3(XG_THREADS), smx, ctx->stream, reinterpret_cast<double2*>(f->dser), f->Nx, Mz, TZ, *fx);
         CF_KERNEL_CHECK();
     }
     return 0;

@@ -207,6 +207,39 @@ int rows_pack_launch(double* field, double* buf, int Nx, int Nz, int nrows, int 
     return 0;
 }
 
+// serial [i][ny][mx][mz] <-> tile-major [tile][i][ny][TM] (complex), retained modes q = (mxi - x0)*(Kz+1) + kz of this
+// rank in natural order, TM per tile.  dir 0: serial -> tile (slots past nq are zero filled), dir 1: tile -> serial.
+__global__ void __launch_bounds__(EW_THREADS) tile_convert_kernel(double2* __restrict__ ser, double2* __restrict__ tile, int Nx, int Ny,
+                                                                  int Mz, int Nd, int Kx, int nkz, int x0, int nq, int TM, int dir) {
+    const int t = blockIdx.x, comp = blockIdx.y;
+    const int nmx = 2 * Kx + 1;
+    const long rs = (long)Nx * Mz, cs = rs * Ny;
+    double2* tb = tile + ((long)t * Nd + comp) * Ny * TM;
+    for (int e = threadIdx.x; e < Ny * TM; e += blockDim.x) {
+        const int n = e / TM, m = e - n * TM, q = t * TM + m;
+        if (q >= nq) {
+            if (dir == 0) tb[e] = make_double2(0.0, 0.0);
+            continue;
+        }
+        const int ml = q / nkz, kz = q - ml * nkz, mxi = x0 + ml;
+        const int kx = mxi <= Kx ? mxi : mxi - nmx;
+        const int mx = kx >= 0 ? kx : Nx + kx;
+        const long so = comp * cs + n * rs + (long)mx * Mz + kz;
+        if (dir == 0) tb[e] = ser[so];
+        else ser[so] = tb[e];
+    }
+}
+
+int tile_convert_launch(double* ser, double* tile, int Nx, int Ny, int Nz, int Nd, int Kx, int Kz, int x0, int nq, int TM, int dir,
+                        cudaStream_t st) {
+    const int ntiles = (nq + TM - 1) / TM;
+    if (ntiles <= 0) return 0;
+    CF_LAUNCH(tile_convert_kernel, dim3(ntiles, Nd), dim3(EW_THREADS), 0, st, reinterpret_cast<double2*>(ser),
+              reinterpret_cast<double2*>(tile), Nx, Ny, Nz / 2 + 1, Nd, Kx, Kz + 1, x0, nq, TM, dir);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
 int l2form_launch(const double* u, const double* v, int mode, const double* W, int N, int Nx, int Nz, int Nd, int Kx, int Kz, int fullbox,
                   int x0, int x1, double scale, double* partial_dev, size_t partial_cap, double* out_dev, cudaStream_t st) {
     const int Mz = Nz / 2 + 1;

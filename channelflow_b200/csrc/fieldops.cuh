@@ -14,5 +14,7 @@ int l2form_launch(const double* u, const double* v, int mode, const double* W, i
                   int x0, int x1, double scale, double* partial_dev, size_t partial_cap, double* out_dev, cudaStream_t st);
 // copy the retained rows mxi in [x0,x1), kz <= Kz of every (component, my) plane between a field (reference layout) and
 // a compact buffer [row][mxi-x0][kz]; dir 0: field -> buffer, 1: buffer -> field
+int tile_convert_launch(double* ser, double* tile, int Nx, int Ny, int Nz, int Nd, int Kx, int Kz, int x0, int nq, int TM, int dir,
+                        cudaStream_t st);
 int rows_pack_launch(double* field, double* buf, int Nx, int Nz, int nrows, int Kx, int Kz, int x0, int x1, int dir, cudaStream_t st);
 }  // namespace cfgpu

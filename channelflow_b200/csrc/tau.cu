@@ -114,11 +114,14 @@ __device__ __forceinline__ void mode_of_q(int q, const ModeGeom& g, int& kx, int
     off = 2L * (kz + (long)(g.Nz / 2 + 1) * mx);
 }
 
-// first mode of a tile and number of valid modes in it
-__device__ __forceinline__ void tile_modes(int tl, int TM, int nq, int has00, int& q0, int& nvalid) {
-    if (tl == 0) { q0 = 0; nvalid = has00 ? 1 : 0; return; }
-    q0 = has00 + (tl - 1) * TM;
-    nvalid = nq - q0 < TM ? nq - q0 : TM;
+// modes of factor tile tl: q0 + m for m in [mfirst, mend); is00: the (0,0) mode's own tile (field data in tile 0, slot 0)
+__device__ __forceinline__ void tile_modes(int tl, const TauData& td, int& q0, int& mfirst, int& mend, bool& is00) {
+    const int ngen = td.ntiles - td.has00;
+    is00 = td.has00 && tl == ngen;
+    if (is00) { q0 = 0; mfirst = 0; mend = 1; return; }
+    q0 = tl * td.TM;
+    mfirst = (td.has00 && tl == 0) ? 1 : 0;
+    mend = td.nq - q0 < td.TM ? td.nq - q0 : td.TM;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -357,8 +360,9 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_setup_kernel(const TauD
     const int N = td.N, Nb = N - 1, TM = td.TM;
     const int tid = threadIdx.x, NT = TAU_SETUP_THREADS;
     const int tl = blockIdx.x;
-    int q0, nvalid;
-    tile_modes(tl, TM, td.nq, td.has00, q0, nvalid);
+    int q0, mfirst, mend;
+    bool is00_;
+    tile_modes(tl, td, q0, mfirst, mend, is00_);   // masked slots are set up as harmless kx = kz = 0 modes
     double* A1 = dyn_smem<double>();
     double* A2 = A1 + (size_t)N * TM;
     double* A3 = A2 + (size_t)N * TM;
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_setup_kernel(const TauD
         const int q = q0 + tid;
         int kx = 0, kz = 0;
         long off;
-        if (tid < nvalid) mode_of_q(q, g, kx, kz, off);
+        if (tid >= mfirst && tid < mend) mode_of_q(q, g, kx, kz, off);
         const double kxL = kx / g.Lx, kzL = kz / g.Lz;
         const double kappa2 = 4 * (PI * PI) * (kxL * kxL + kzL * kzL);
         const double c = 4.0 * (PI * PI) * td.nu;
@@ -536,7 +540,6 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
     const int N = td.N, Nb = N - 1, TM = td.TM, TT = 2 * TM;
     const int tid = threadIdx.x, NT = TAU_THREADS, lane = tid & 31, warp = tid >> 5, NW = TAU_THREADS / 32;
     const int tl = blockIdx.x;
-    const bool is00 = tl == 0;
     const double scale = 4.0 / (td.b - td.a);
     const long rs_ser = (long)p.g.Nx * (2 * (p.g.Nz / 2 + 1));  // row (ny) stride in doubles
     const long cs_ser = rs_ser * p.g.Ny;                        // component stride
@@ -552,13 +555,15 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
     const double* __restrict__ bt = td.btab();   // B rows [3][N] (mode independent, L1 resident)
     double* s_w = s_sc + TSC_COUNT * TM;         // [8][TT]
     long* s_off = reinterpret_cast<long*>(s_w + 8 * TT);  // [TM]
-    int q0, nvalid;
-    tile_modes(tl, TM, td.nq, td.has00, q0, nvalid);
-    if (nvalid <= 0) return;  // tile 0 on a rank that does not own the (0,0) mode
+    int q0, mfirst, mend;
+    bool is00;
+    tile_modes(tl, td, q0, mfirst, mend, is00);
+    if (mfirst >= mend) return;        // tile 0 holding nothing but the masked (0,0) slot
+    const int ftile = is00 ? 0 : tl;   // tile of the FIELD data (tile-major layout): the (0,0) mode lives in slot 0 of tile 0
 
     if (tid < TM) {
         long off = -1;
-        if (tid < nvalid) { int kx, kz; mode_of_q(q0 + tid, p.g, kx, kz, off); }
+        if (tid >= mfirst && tid < mend) { int kx, kz; mode_of_q(q0 + tid, p.g, kx, kz, off); }
         s_off[tid] = off;
     }
     for (int i = tid; i < TSC_COUNT * TM; i += NT) s_sc[i] = td.tile_sc(tl, 0)[i];
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
         const int m = tid % TM, j0 = tid / TM, JS = NT / TM;   // NT % TM == 0 is guaranteed by the launcher
         long off = s_off[m];
         long rs = rs_ser, cs = cs_ser;
-        if (p.experiment_tile_layout && off >= 0) { off = ((long)tl * 3 * N * TM + m) * 2; cs = (long)N * TM * 2; rs = TM * 2; }
+        if (p.tile_layout && off >= 0) { off = ((long)ftile * 3 * N * TM + m) * 2; cs = (long)N * TM * 2; rs = TM * 2; }
         const int nterms = NTERMS > 0 ? NTERMS : p.nterms;
         if (off >= 0 && j0 < JS) {
             for (int comp = 0; comp < 3; ++comp) {
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
     // used by the two columns of a mode only and come straight from global memory ([m][n] rows, prefetched to L2).
     for (int col = warp; col < TT; col += NW) {
         const int m = col >> 1, ri = col & 1;
-        if (m >= nvalid) continue;
+        if (m < mfirst || m >= mend) continue;
         double r[E], x[E];
         {
             double y[E], d[E], ox[E], oz[E];
@@ -688,7 +693,7 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
         const double* gP0 = td.tile_arr(tl, TAR_P0); const double* gv0 = td.tile_arr(tl, TAR_V0);
         if (tid < TT) {
             const int m = tid >> 1;
-            if (m < nvalid) {
+            if (m >= mfirst && m < mend) {
                 const double Se = s_w[6 * TT + tid], So = s_w[7 * TT + tid];
                 const double vb = 0.5 * scale * (So + Se), va = 0.5 * scale * (So - Se);
                 const double dp = -s_sc[TSC_I00 * TM + m] * vb - s_sc[TSC_I01 * TM + m] * va;
@@ -715,7 +720,7 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
         // one (mode, half of the rows) item per warp: rows n = lane + 32*half + 64*k, four of them in flight
         for (int item = warp; item < 2 * TM; item += NW) {
             const int m = item >> 1;
-            if (m >= nvalid) continue;
+            if (m < mfirst || m >= mend) continue;
             const double dpr = s_w[2 * m], dpi = s_w[2 * m + 1], dmr = s_w[TT + 2 * m], dmi = s_w[TT + 2 * m + 1];
             const double sNbr = s_w[2 * TT + 2 * m], sNbi = s_w[2 * TT + 2 * m + 1];
             const double sNb1r = s_w[3 * TT + 2 * m], sNb1i = s_w[3 * TT + 2 * m + 1];
@@ -772,7 +777,7 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
     const bool bulk00 = is00 && p.constraint == 1;
     for (int c2 = warp; c2 < 2 * TT; c2 += NW) {
         const int which = c2 / TT, col = c2 - which * TT, m = col >> 1, ri = col & 1;
-        if (m >= nvalid) continue;
+        if (m < mfirst || m >= mend) continue;
         double* R = which ? Rz : Rx;
         double r[E], x[E];
         {
@@ -836,7 +841,7 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
         long off = s_off[m];
         if (off < 0) continue;
         long rs = rs_ser, cs = cs_ser;
-        if (p.experiment_tile_layout) { off = ((long)tl * 3 * N * TM + m) * 2; cs = (long)N * TM * 2; rs = TM * 2; }
+        if (p.tile_layout) { off = ((long)ftile * 3 * N * TM + m) * 2; cs = (long)N * TM * 2; rs = TM * 2; }
         const long go = n * rs + off;
         const int a = (2 * m) * NP + col_addr<E>(n);
         double2 V = make_double2(Ry[a], Ry[a + NP]);
@@ -844,7 +849,7 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
         *reinterpret_cast<double2*>(&p.uout[go]) = make_double2(Rx[a], Rx[a + NP]);
         *reinterpret_cast<double2*>(&p.uout[cs + go]) = V;
         *reinterpret_cast<double2*>(&p.uout[2 * cs + go]) = make_double2(Rz[a], Rz[a + NP]);
-        const long goq = p.experiment_tile_layout ? ((long)tl * N * TM + m) * 2 + n * rs : go;
+        const long goq = p.tile_layout ? ((long)ftile * N * TM + m) * 2 + n * rs : go;
         *reinterpret_cast<double2*>(&p.qout[goq]) = make_double2(Pq[a], Pq[a + NP]);
     }
 }
@@ -896,7 +901,7 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) linear_kernel(const TauSolv
         __syncthreads();
         for (int c = tid; c < 2 * TT; c += NT) diff_chain(X, T, N, TT, c % TT, c / TT, scale, nullptr);
         __syncthreads();
-        if (td.has00 && blockIdx.x == 0 && p.constraint == 1 && comp != 1 && tid == 0) {
+        if (td.has00 && blockIdx.x == 0 && p.constraint == 1 && comp != 1 && tid == 0) {  // q = 0 is slot 0 of block 0
             // wall shear of nu*u for the (0,0) mode, real part (t = 0): eval_b - eval_a of d(nu u)/dy
             double sb = 0.0, sa = 0.0;
             for (int n = N - 1; n >= 0; --n) { sb += T[n * TT]; sa += T[n * TT] * ((n % 2 == 0) ? 1 : -1); }

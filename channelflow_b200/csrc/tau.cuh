@@ -7,11 +7,14 @@
 // multistep right-hand-side accumulation (dnsalgo.cpp:217-224, FlowField::add flowfield.h:606-615), which is fused
 // into the solve kernel as a linear combination of history fields.
 //
-// Storage (HBM): tile-major.  The retained modes are grouped into tiles of TM consecutive modes (the unit of work of
-// one CTA of the solve kernel); tile 0 holds the (0,0) mode alone, tile 1+(q-1)/TM holds mode q >= 1 at position
-// (q-1)%TM.  Per tile: 12 arrays [n][TM] (UL factors of the pressure and velocity Helmholtz operators, the six
-// precomputed profiles P+-, v+-, P0, v0) followed by TSC_COUNT scalars [TM] -- one contiguous block, so a CTA
-// streams its factors with fully coalesced loads.  A mode-independent table of the C&H 5.1.24 "B" rows follows.
+// Storage (HBM): tile-major.  The retained modes q = (mxi - mx0)*(Kz+1) + kz of this rank are grouped, in that natural
+// order, into tiles of TM consecutive modes (the unit of work of one CTA of the solve kernel): tile t holds
+// q = t*TM .. t*TM+TM-1.  The (0,0) mode (q = 0 on the rank that owns kx row 0) needs the mean-flow treatment and gets a
+// tile of its own at the END (index ngen = ceil(nq/TM)); its slot in tile 0 is masked.  Per tile: 12 arrays [m][n] (UL
+// factors of the pressure and velocity Helmholtz operators, the six precomputed profiles P+-, v+-, P0, v0) followed by
+// TSC_COUNT scalars [TM] -- one contiguous block, so a CTA streams its factors with fully coalesced loads.  A
+// mode-independent table of the C&H 5.1.24 "B" rows follows.  The same tiling is the tile-major FIELD layout
+// (TileGeom, cfgpu_internal.h): [tile][component][n][TM] complex, in which a CTA's history data is contiguous.
 #pragma once
 #include "cf_common.cuh"
 
@@ -26,19 +29,19 @@ struct TauData {
     int nq;      // retained modes of this rank, q = (mxi - mx0)*(Kz+1) + kz ; with has00, q = 0 is the (0,0) mode
     int has00;   // this rank owns kx row 0 (always true on a single GPU)
     int TM;      // modes per tile
-    int ntiles;  // 1 + ceil((nq-1)/TM)
+    int ntiles;  // ceil(nq/TM) + has00
     double nu, a, b;
     double* base;  // single allocation
     __host__ __device__ size_t tile_doubles() const { return (size_t)(TAR_COUNT * N + TSC_COUNT) * TM; }
     __host__ __device__ double* tile(int tl) const { return base + (size_t)tl * tile_doubles(); }
-    __host__ __device__ double* tile_arr(int tl, int which) const { return tile(tl) + (size_t)which * N * TM; }   // [n][TM]
+    __host__ __device__ double* tile_arr(int tl, int which) const { return tile(tl) + (size_t)which * N * TM; }   // [m][n]
     __host__ __device__ double* tile_sc(int tl, int which) const { return tile(tl) + (size_t)TAR_COUNT * N * TM + (size_t)which * TM; }
     __host__ __device__ double* btab() const { return base + (size_t)ntiles * tile_doubles(); }  // [3][N]: B_lo, B_dg, B_up
-    // tile 0 is reserved for the (0,0) mode (empty on ranks that do not own it); general modes start at q = has00
-    __host__ __device__ int tile_of(int q) const { return (has00 && q == 0) ? 0 : 1 + (q - has00) / TM; }
-    __host__ __device__ int pos_of(int q) const { return (has00 && q == 0) ? 0 : (q - has00) % TM; }
+    __host__ __device__ int ngen() const { return ntiles - has00; }   // general tiles; tile ngen() is the (0,0) mode's
+    __host__ __device__ int tile_of(int q) const { return (has00 && q == 0) ? ngen() : q / TM; }
+    __host__ __device__ int pos_of(int q) const { return (has00 && q == 0) ? 0 : q % TM; }
     __host__ __device__ double& scq(int which, int q) const { return tile_sc(tile_of(q), which)[pos_of(q)]; }
-    static int num_tiles(int nq, int TM, int has00) { return 1 + (nq - has00 + TM - 1) / TM; }
+    static int num_tiles(int nq, int TM, int has00) { return (nq + TM - 1) / TM + has00; }
     static size_t doubles(int N, int nq, int TM, int has00) {
         return (size_t)num_tiles(nq, TM, has00) * (TAR_COUNT * N + TSC_COUNT) * TM + 3 * (size_t)N;
     }
@@ -74,9 +77,9 @@ struct TauSolveParams {
     double* dPd_act;   // device [2]: dPdxAct, dPdzAct written by the bulk-velocity solve
     // NSE::linear, bulk-velocity branch (nse.cpp:456-472): nu*(Ubase'(b)-Ubase'(a))/Ly and same for W
     double lin_base_dPdx, lin_base_dPdz;
-    // TIMING EXPERIMENT ONLY (env CF_TAU_EXPERIMENT_TILE_LAYOUT, results are meaningless): address the history fields
-    // and the outputs as if they were stored tile-major [tile][comp][n][TM], to measure what that layout would buy.
-    int experiment_tile_layout;
+    // 1: the history fields and the outputs are tile-major, [tile][component][n][TM] complex (TileGeom, cfgpu_internal.h;
+    // qout has one component); 0: the reference's serial layout
+    int tile_layout;
 };
 
 int tau_setup_launch(const TauData& td, const ModeGeom& g, double lambda_t, cudaStream_t stream);
