@@ -746,6 +746,10 @@ int cfgpu_nse_solve(cfgpu_nse nse, int s, int nterms, const double* coef_h, cons
     tp.uout = nse->use_tile ? uout->dtile : uout->dser;
     tp.qout = nse->use_tile ? qout->dtile : qout->dser;
     tp.tile_layout = nse->use_tile ? 1 : 0;
+    {
+        static const int pf = getenv("CF_TAU_PREFETCH") ? atoi(getenv("CF_TAU_PREFETCH")) : 1;
+        tp.prefetch_terms = pf;
+    }
     { StageTimer _t(nse->ctx, 5); CF_TRY(tau_solve_launch(tp, nse->ctx->stream)); }
     uout->xzstate = uout->ystate = qout->xzstate = qout->ystate = CFGPU_SPECTRAL;
     return 0;

@@ -198,7 +198,7 @@ __device__ __forceinline__ void col_deriv(const double (&u)[E], double (&d)[E], 
 //   bordered row        x_par = (bc - sum band_n x_n) / diag0                      (:263-268; diag0 in slot `par` of inv)
 //   forward elimination x_n = (x_n - lo_n x_{n-2}) inv_n  n = par+2 .. nl          (:269-273), lo_n = A_lo(n, lambda)
 // r (in) and x (out) are lane registers; up/inv/band are skewed shared-memory columns (SKEW) or plain rows in global
-// memory, bt the B rows in HBM (L1), lo_n = -(lambda * B_lo(n)) costs one multiply.  If wall != nullptr the
+// memory, bt the B rows (three skewed shared-memory columns), lo_n = -(lambda * B_lo(n)) costs one multiply.  If wall != nullptr the
 // sums  S_p = sum_{n = p mod 2} n^2 x_n  are returned in wall[0..1] (all lanes).
 template <int E, bool SKEW>
 __device__ __forceinline__ void col_solve(const double (&r)[E], double (&x)[E], const double* __restrict__ up,
@@ -207,6 +207,7 @@ __device__ __forceinline__ void col_solve(const double (&r)[E], double (&x)[E], 
                                           const double bc0, const double bc1, double* wall) {
     const int Nb = N - 1;
     const int n0 = lane * E, a0 = SKEW ? lane * (E + 1) : lane * E;
+    const int btl = lane * (E + 1), btp = tau_col_pitch(N, E);  // B rows: three skewed shared-memory columns
     double g[E], l[E];
     {
         // neighbours two rows away (other lanes at the block edges)
@@ -223,9 +224,9 @@ __device__ __forceinline__ void col_solve(const double (&r)[E], double (&x)[E], 
             const double rp = e < E - 2 ? r[e < E - 2 ? e + 2 : 0] : hi2[e & 1];
             double v = 0.0, lv = 0.0;
             if (n >= 2 && n < N) {
-                const double blo = __ldg(&bt[n]);
-                v = blo * rm + __ldg(&bt[N + n]) * r[e];
-                v += __ldg(&bt[2 * N + n]) * rp;
+                const double blo = bt[btl + e];
+                v = blo * rm + bt[btp + btl + e] * r[e];
+                v += bt[2 * btp + btl + e] * rp;
                 lv = A_lo_from_B(blo, lam);
             }
             g[e] = v;
@@ -552,9 +553,9 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
     double* Ry = Rx + AS; double* Rz = Ry + AS; double* Pq = Rz + AS;
     double* Fup = Pq + AS; double* Finv = Fup + FS; double* Fband = Finv + FS;   // velocity-operator factors
     double* s_sc = Fband + FS;                   // [TSC_COUNT][TM]
-    const double* __restrict__ bt = td.btab();   // B rows [3][N] (mode independent, L1 resident)
     double* s_w = s_sc + TSC_COUNT * TM;         // [8][TT]
     long* s_off = reinterpret_cast<long*>(s_w + 8 * TT);  // [TM]
+    double* bt = reinterpret_cast<double*>(s_off + TM);   // B rows [3][NP] (mode independent), skewed like the columns
     int q0, mfirst, mend;
     bool is00;
     tile_modes(tl, td, q0, mfirst, mend, is00);
@@ -575,7 +576,25 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
             double* dst = Fup + row * NP;
             for (int n = lane; n < N; n += 32) cp_async8(dst + col_addr<E>(n), src + n);
         }
+        {
+            const double* src = td.btab();
+            for (int i = tid; i < 3 * N; i += NT) {
+                const int r = i >= 2 * N ? 2 : (i >= N ? 1 : 0), n = i - r * N;
+                cp_async8(bt + r * NP + col_addr<E>(n), src + i);
+            }
+        }
         cp_async_commit();
+        if (p.tile_layout && p.prefetch_terms) {
+            // tile-major history fields: this CTA's 3 x N x TM block of every term is contiguous -- request all of it now
+            const size_t bytes = (size_t)3 * NM * 2 * sizeof(double);
+            const int nterms = NTERMS > 0 ? NTERMS : p.nterms;
+            // (fetching for the CTA some tiles ahead instead was measured: 2.3-2.6 ms against 1.9 ms, the blocks do not survive
+            // in L2 until they are used)
+            for (int j = 0; j < nterms; ++j) {
+                const char* blk = reinterpret_cast<const char*>(p.term[j] + (size_t)ftile * 3 * NM * 2);
+                for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)NT * 128) prefetch_l2(blk + o);
+            }
+        }
         // pull the pressure-operator factors (read straight from global by the solving warps) towards L2
         // ... and the six correction profiles, used last
         const char* blk = reinterpret_cast<const char*>(td.tile_arr(tl, TAR_UPP));
@@ -956,7 +975,7 @@ static size_t solve_smem(int N, int TM) {
     const int E = tau_pick_E(N);
     if (!E) return (size_t)1 << 30;
     const size_t NP = tau_col_pitch(N, E);
-    return ((size_t)11 * TM * NP + TSC_COUNT * TM + 16 * TM) * sizeof(double) + TM * sizeof(long);
+    return ((size_t)11 * TM * NP + 3 * NP + TSC_COUNT * TM + 16 * TM) * sizeof(double) + TM * sizeof(long);
 }
 
 // modes per tile of the solve kernel: two CTAs per SM when the profiles are long (one streams while the other

@@ -80,6 +80,7 @@ struct TauSolveParams {
     // 1: the history fields and the outputs are tile-major, [tile][component][n][TM] complex (TileGeom, cfgpu_internal.h;
     // qout has one component); 0: the reference's serial layout
     int tile_layout;
+    int prefetch_terms;   // tile layout: L2-prefetch the CTA's whole history block at kernel start
 };
 
 int tau_setup_launch(const TauData& td, const ModeGeom& g, double lambda_t, cudaStream_t stream);

@@ -1,5 +1,5 @@
 #!/bin/bash
-# tau-solve A/B on the C4 bench: product kernel vs the tile-major addressing experiment (timing only), then GPU tests.
+# layout A/B on the C4 bench (tile-major hot-path fields vs CFGPU_SERIAL_LAYOUT=1), then GPU tests.
 mkdir -p gpurun_out
 run() {  # tag env...
   tag=$1; shift
@@ -13,7 +13,7 @@ except Exception as e:
     print("$tag ERR", e); print(open("gpurun_out/tau_$tag.err").read()[-800:])
 PY
 }
-run base X=1
-run tilelayout CF_TAU_EXPERIMENT_TILE_LAYOUT=1
+run tile X=1
+run serial CFGPU_SERIAL_LAYOUT=1
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
