@@ -27,6 +27,18 @@ __device__ __forceinline__ double2 tw_mul(double2 v, double2 w) {
     if (DIR < 0) return make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
     return make_double2(v.x * w.x + v.y * w.y, v.y * w.x - v.x * w.y);
 }
+// w[r] = w1^r, r = 1..R-1, by a shallow product tree: one table load per butterfly instead of R-1 (the loads, not
+// the FP64 pipe, are what the shared-memory transforms are short of); costs a few ulp in the higher powers
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <int R>
+__device__ __forceinline__ void twiddle_powers(double2 w1, double2 (&w)[R]) {
+    w[1] = w1;
+    if (R > 2) w[2] = cmul(w1, w1);
+    if (R > 3) w[3] = cmul(w[2], w1);
+    if (R > 4) w[4] = cmul(w[2], w[2]);
+#pragma unroll
+    for (int r = 5; r < R; ++r) w[r] = cmul(w[4], w[r - 4]);
+}
 // multiply by -i (forward) / +i (backward)
 template <int DIR>
 __device__ __forceinline__ double2 rot90(double2 v) {
@@ -182,8 +194,10 @@ __device__ __forceinline__ void warp_fft_pass(double2* __restrict__ buf, const d
         if (b < nb) {
             const int k = b % Ns;
             if (Ns > 1) {
+                double2 w[R];
+                twiddle_powers<R>(tw[k * tstep], w);
 #pragma unroll
-                for (int r = 1; r < R; ++r) v[i][r] = tw_mul<DIR>(v[i][r], tw[r * k * tstep]);
+                for (int r = 1; r < R; ++r) v[i][r] = tw_mul<DIR>(v[i][r], w[r]);
             }
             radix_butterfly<DIR, R>(v[i]);
             const int j0 = (b / Ns) * Ns * R + k;

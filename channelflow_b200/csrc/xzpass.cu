@@ -250,8 +250,9 @@ __global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
 // form) is owned by ONE warp and runs in place in its own skewed shared-memory line without block barriers
 // (fft_smem.cuh: warp_fft); the CTA only synchronises between pack / inverse / pointwise / forward / store.
 // grid = (ceil(Nx/TL), nyn), block = 32 * npair * TL threads.  NZ = Nz (power of two, compile-time FFT plan).
+// (at Nz = 512 two lines = 6 warps per CTA and three CTAs per SM: the register budget is set for exactly that)
 template <int NZ>
-__global__ void __launch_bounds__(320, 2) zpass_warp_kernel(const ZPassParams p) {
+__global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 3 : 2) zpass_warp_kernel(const ZPassParams p) {
     const int Nx = p.Nx, Nz = NZ, TL = p.TL;
     const int nkz = p.Kz + 1;
     const bool rot = p.mode == ZP_ROTATIONAL;
@@ -572,7 +573,7 @@ static int zpass_warp_launch(const ZPassParams& p0, cudaStream_t stream) {
     const size_t per_line = (size_t)npair * fft_skew_len(p.Nz) * sizeof(double2);
     int TL = 1;
     const size_t cap = (size_t)(getenv("CF_ZP_SMEM_KB") ? atoi(getenv("CF_ZP_SMEM_KB")) : 60) * 1024;
-    while (TL < 8 && (size_t)(TL + 1) * per_line <= cap && npair * (TL + 1) <= 10 && TL + 1 <= p.Nx) ++TL;
+    while (TL < 8 && (size_t)(TL + 1) * per_line <= cap && npair * (TL + 1) <= (NZ == 512 ? 6 : 10) && TL + 1 <= p.Nx) ++TL;
     p.TL = TL;
     const size_t smem = (size_t)TL * per_line + (size_t)p.Nz * sizeof(double2);
     static size_t configured = 0;
