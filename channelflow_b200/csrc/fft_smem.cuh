@@ -118,7 +118,9 @@ __device__ __forceinline__ void radix_butterfly(double2 (&v)[R]) {
 }
 
 // One Stockham pass of radix R over all C columns. Ns = product of the radices of the previous passes.
-template <int DIR, int R>
+// TWPOW: twiddles w^(r k) from one table load and a product tree (pays when the table is in global memory / L1;
+// with a shared-memory table and few columns per CTA the R-1 loads are the cheaper way -- both measured, x-pass at 512)
+template <int DIR, int R, bool TWPOW>
 __device__ __forceinline__ void fft_pass(const double2* __restrict__ a, double2* __restrict__ b, const FftPlanDev& pl,
                                          const double2* __restrict__ tw, int Ns, int C, int tid, int nthreads) {
     const int N = pl.N;
@@ -132,8 +134,15 @@ __device__ __forceinline__ void fft_pass(const double2* __restrict__ a, double2*
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = a[(j + r * nb) * C + c];
         if (Ns > 1) {
+            if (TWPOW) {
+                double2 w[R];
+                twiddle_powers<R>(tw[k * tstep], w);
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[r] = tw_mul<DIR>(v[r], tw[r * k * tstep]);
+                for (int r = 1; r < R; ++r) v[r] = tw_mul<DIR>(v[r], w[r]);
+            } else {
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[r] = tw_mul<DIR>(v[r], tw[r * k * tstep]);
+            }
         }
         radix_butterfly<DIR, R>(v);
         const int j0 = (j / Ns) * Ns * R + k;
@@ -145,17 +154,17 @@ __device__ __forceinline__ void fft_pass(const double2* __restrict__ a, double2*
 // Full transform of C columns. `a` holds the input; returns the buffer (a or b) holding the result.
 // Ends with a __syncthreads(); the caller must have synchronised after filling `a`.
 // `tw` = twiddle table (pl.tw in HBM/L1, or a copy the caller staged in shared memory).
-template <int DIR>
+template <int DIR, bool TWPOW = true>
 __device__ __forceinline__ double2* fft_smem(double2* a, double2* b, const FftPlanDev& pl, const double2* tw, int C, int tid,
                                              int nthreads) {
     int Ns = 1;
     for (int p = 0; p < pl.npass; ++p) {
         const int R = pl.radix[p];
-        if (R == 8) fft_pass<DIR, 8>(a, b, pl, tw, Ns, C, tid, nthreads);
-        else if (R == 4) fft_pass<DIR, 4>(a, b, pl, tw, Ns, C, tid, nthreads);
-        else if (R == 2) fft_pass<DIR, 2>(a, b, pl, tw, Ns, C, tid, nthreads);
-        else if (R == 3) fft_pass<DIR, 3>(a, b, pl, tw, Ns, C, tid, nthreads);
-        else fft_pass<DIR, 5>(a, b, pl, tw, Ns, C, tid, nthreads);
+        if (R == 8) fft_pass<DIR, 8, TWPOW>(a, b, pl, tw, Ns, C, tid, nthreads);
+        else if (R == 4) fft_pass<DIR, 4, TWPOW>(a, b, pl, tw, Ns, C, tid, nthreads);
+        else if (R == 2) fft_pass<DIR, 2, TWPOW>(a, b, pl, tw, Ns, C, tid, nthreads);
+        else if (R == 3) fft_pass<DIR, 3, TWPOW>(a, b, pl, tw, Ns, C, tid, nthreads);
+        else fft_pass<DIR, 5, TWPOW>(a, b, pl, tw, Ns, C, tid, nthreads);
         __syncthreads();
         double2* t = a;
         a = b;

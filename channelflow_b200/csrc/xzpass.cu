@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassPa
         }
     }
     __syncthreads();
-    const double2* res = fft_smem<+1>(a, b, p.plan, tws, TZ, tid, XZ_THREADS);
+    const double2* res = fft_smem<+1, false>(a, b, p.plan, tws, TZ, tid, XZ_THREADS);
     double2* __restrict__ out = p.out + ((size_t)f * p.nyn + yl) * Nx * nkz;
     for (int idx = tid; idx < Nx * TZ; idx += XZ_THREADS) {
         const int nx = idx / TZ, c = idx - nx * TZ;
