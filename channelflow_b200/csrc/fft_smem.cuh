@@ -248,6 +248,85 @@ __device__ __forceinline__ void warp_fft_pow2(double2* buf, const double2* tw, i
     if (REM == 1) warp_fft_pass<DIR, 2>(buf, tw, N, Ns, lane);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// In-place warp-private transforms with digit-reversed data on one side (power-of-two N, radix-8 passes of stride
+// 1, 8, 64 and a last radix-4/2 pass): a butterfly reads and writes the same R locations, so a lane needs one
+// butterfly in registers at a time (the Stockham variant above holds all of its butterflies of a pass).
+//   warp_fft_dit: input at fft_digit_rev<N>(n), output in natural order  (decimation in time, twiddles before)
+//   warp_fft_dif: input in natural order, output k at fft_digit_rev<N>(k) (decimation in frequency, twiddles after)
+// Callers write/read the reversed side with the index they compute anyway.  Skew addr(i) = i + i/8 + i/64 keeps every
+// quarter-warp of the stride-1/8/64 accesses AND of consecutive reversed indices (stride 64) on distinct banks.
+__host__ __device__ inline int fft_skew2(int i) { return i + (i >> 3) + (i >> 6); }
+__host__ __device__ inline int fft_skew2_len(int N) { return N + (N >> 3) + (N >> 6) + 1; }
+
+template <int N>
+struct WarpFftShape {
+    static constexpr int L = N == 512 ? 9 : N == 256 ? 8 : N == 128 ? 7 : N == 64 ? 6 : N == 32 ? 5 : N == 16 ? 4 : 3;
+    static constexpr int N8 = L / 3, REM = L % 3;
+    static constexpr int RL = REM == 2 ? 4 : (REM == 1 ? 2 : 1);  // radix of the last pass (1: none)
+    static constexpr int NS_LAST = N / RL;                        // its stride = 8^N8
+};
+
+template <int N>
+__host__ __device__ inline int fft_digit_rev(int n) {
+    using S = WarpFftShape<N>;
+    int pos = 0, span = N;
+    if (S::RL > 1) { span /= S::RL; pos += (n % S::RL) * span; n /= S::RL; }
+#pragma unroll
+    for (int p = 0; p < S::N8; ++p) { span >>= 3; pos += (n & 7) * span; n >>= 3; }
+    return pos;
+}
+
+template <int DIR, int R, int N, int NS, bool DIF>
+__device__ __forceinline__ void warp_fft_inplace_pass(double2* __restrict__ buf, const double2* __restrict__ tw, int lane) {
+    constexpr int nb = N / R;
+    constexpr int tstep = N / (NS * R);
+#pragma unroll
+    for (int i = 0; i < (nb + 31) / 32; ++i) {
+        const int b = lane + 32 * i;
+        if ((nb % 32 == 0) || b < nb) {
+            const int k = b % NS;
+            const int base = (b / NS) * NS * R + k;
+            double2 v[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = buf[fft_skew2(base + r * NS)];
+            double2 w[R];
+            if (NS > 1) twiddle_powers<R>(tw[k * tstep], w);
+            if (!DIF && NS > 1) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[r] = tw_mul<DIR>(v[r], w[r]);
+            }
+            radix_butterfly<DIR, R>(v);
+            if (DIF && NS > 1) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[r] = tw_mul<DIR>(v[r], w[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) buf[fft_skew2(base + r * NS)] = v[r];
+        }
+    }
+    __syncwarp();
+}
+
+template <int DIR, int N>
+__device__ __forceinline__ void warp_fft_dit(double2* buf, const double2* tw, int lane) {
+    using S = WarpFftShape<N>;
+    if (S::N8 >= 1) warp_fft_inplace_pass<DIR, 8, N, 1, false>(buf, tw, lane);
+    if (S::N8 >= 2) warp_fft_inplace_pass<DIR, 8, N, 8, false>(buf, tw, lane);
+    if (S::N8 >= 3) warp_fft_inplace_pass<DIR, 8, N, 64, false>(buf, tw, lane);
+    if (S::RL == 4) warp_fft_inplace_pass<DIR, 4, N, S::NS_LAST, false>(buf, tw, lane);
+    if (S::RL == 2) warp_fft_inplace_pass<DIR, 2, N, S::NS_LAST, false>(buf, tw, lane);
+}
+template <int DIR, int N>
+__device__ __forceinline__ void warp_fft_dif(double2* buf, const double2* tw, int lane) {
+    using S = WarpFftShape<N>;
+    if (S::RL == 4) warp_fft_inplace_pass<DIR, 4, N, S::NS_LAST, true>(buf, tw, lane);
+    if (S::RL == 2) warp_fft_inplace_pass<DIR, 2, N, S::NS_LAST, true>(buf, tw, lane);
+    if (S::N8 >= 3) warp_fft_inplace_pass<DIR, 8, N, 64, true>(buf, tw, lane);
+    if (S::N8 >= 2) warp_fft_inplace_pass<DIR, 8, N, 8, true>(buf, tw, lane);
+    if (S::N8 >= 1) warp_fft_inplace_pass<DIR, 8, N, 1, true>(buf, tw, lane);
+}
+
 inline bool warp_fft_supported(const FftPlanDev& pl) {
     for (int p = 0; p < pl.npass; ++p)
         if (pl.N / pl.radix[p] > 32 * (16 / pl.radix[p])) return false;

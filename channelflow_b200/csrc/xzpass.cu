@@ -258,20 +258,21 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 3 : 2) zpas
     const bool rot = p.mode == ZP_ROTATIONAL;
     const int npair = rot ? 3 : 2;
     const int njobs = npair * TL;           // job j = q * TL + l : transform q of line l
-    const int NP = fft_skew_len(Nz);
+    const int NP = fft_skew2_len(Nz);
+    constexpr int NTW = NZ / (WarpFftShape<NZ>::RL > 1 ? WarpFftShape<NZ>::RL : 8);  // twiddles the in-place passes touch
     double2* buf = dyn_smem<double2>();     // [njobs][NP]
-    double2* tws = buf + (size_t)njobs * NP; // twiddle table exp(-2 pi i t / Nz), t < Nz
+    double2* tws = buf + (size_t)njobs * NP; // twiddle table exp(-2 pi i t / Nz), t < NTW
     __shared__ double red[32];
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int yl = blockIdx.y, ny = p.ny0 + yl, nx0 = blockIdx.x * TL;
     const size_t fstride = (size_t)p.nyn * Nx * nkz;  // field stride of Q and F
 
-    for (int t = tid; t < Nz; t += NT) tws[t] = __ldg(&p.plan.tw[t]);
+    for (int t = tid; t < NTW; t += NT) tws[t] = __ldg(&p.plan.tw[t]);
     // rows nkz .. Nz-nkz (the de-aliased band and the Nyquist mode) are not written by the packing loop below
     const int nzero = Nz - 2 * nkz + 1;
     for (int idx = tid; idx < nzero * njobs; idx += NT) {
         const int j = idx / nzero, k = nkz + (idx - j * nzero);
-        buf[(size_t)j * NP + fft_skew(k)] = make_double2(0.0, 0.0);
+        buf[(size_t)j * NP + fft_skew2(fft_digit_rev<NZ>(k))] = make_double2(0.0, 0.0);
     }
     const double2* __restrict__ Q = p.Q + (size_t)yl * Nx * nkz;
     // two (line, kz) items per thread in flight: all loads are issued before the first use
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 3 : 2) zpas
             const int idx = i0 + h * NT;
             if (idx >= TL * nkz) break;
             const int l = idx / nkz, k = idx - l * nkz;
-            const int ka = fft_skew(k), kb = fft_skew(k > 0 ? Nz - k : 0);
+            const int ka = fft_skew2(fft_digit_rev<NZ>(k)), kb = fft_skew2(fft_digit_rev<NZ>(k > 0 ? Nz - k : 0));  // inputs of the DIT transform
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 if (q >= npair) break;
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 3 : 2) zpas
         }
     }
     __syncthreads();
-    for (int j = warp; j < njobs; j += (NT >> 5)) warp_fft_pow2<+1, NZ>(buf + (size_t)j * NP, tws, lane);
+    for (int j = warp; j < njobs; j += (NT >> 5)) warp_fft_dit<+1, NZ>(buf + (size_t)j * NP, tws, lane);
     __syncthreads();
 
     // pointwise stage: (line l, point z); the products overwrite transforms 0 and 1 of the same line
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 3 : 2) zpas
     for (int idx = tid; idx < Nz * TL; idx += NT) {
         const int l = idx / Nz, z = idx - l * Nz;
         if (nx0 + l >= Nx) continue;
-        const int zs = fft_skew(z);
+        const int zs = fft_skew2(z);
         double2* r = buf + (size_t)l * NP + zs;
         const size_t js = (size_t)TL * NP;  // stride between transforms of one line
         if (rot) {
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 3 : 2) zpas
     }
     if (!rot) return;
     __syncthreads();
-    for (int j = warp; j < 2 * TL; j += (NT >> 5)) warp_fft_pow2<-1, NZ>(buf + (size_t)j * NP, tws, lane);
+    for (int j = warp; j < 2 * TL; j += (NT >> 5)) warp_fft_dif<-1, NZ>(buf + (size_t)j * NP, tws, lane);
     __syncthreads();
 
     double2* __restrict__ F = p.F + (size_t)yl * Nx * nkz;
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 3 : 2) zpas
         if (nx >= Nx) continue;
         const double2* g = buf + (size_t)l * NP;                // transform 0 of line l: fx + i fy
         const double2* h = buf + (size_t)(TL + l) * NP;         // transform 1: fz
-        const int ks = fft_skew(k), kn = fft_skew(k == 0 ? 0 : Nz - k);
+        const int ks = fft_skew2(fft_digit_rev<NZ>(k)), kn = fft_skew2(fft_digit_rev<NZ>(k == 0 ? 0 : Nz - k));  // DIF outputs
         const double2 gk = g[ks], gn = g[kn], hk = h[ks];
         const size_t off = (size_t)nx * nkz + k;
         F[off] = make_double2(hs * (gk.x + gn.x), hs * (gk.y - gn.y));
@@ -570,12 +571,13 @@ static int zpass_warp_launch(const ZPassParams& p0, cudaStream_t stream) {
     const int npair = p.mode == ZP_ROTATIONAL ? 3 : 2;
     // lines per CTA: small CTAs (two lines = 6 warps at Nz = 512, three CTAs per SM) interleave their pack / FFT / store
     // phases better than fewer large ones (measured at 512x257x512: 1 line 2.83 ms, 2 lines 2.75 ms, 3 lines 2.97 ms)
-    const size_t per_line = (size_t)npair * fft_skew_len(p.Nz) * sizeof(double2);
+    const size_t per_line = (size_t)npair * fft_skew2_len(p.Nz) * sizeof(double2);
     int TL = 1;
     const size_t cap = (size_t)(getenv("CF_ZP_SMEM_KB") ? atoi(getenv("CF_ZP_SMEM_KB")) : 60) * 1024;
     while (TL < 8 && (size_t)(TL + 1) * per_line <= cap && npair * (TL + 1) <= (NZ == 512 ? 6 : 10) && TL + 1 <= p.Nx) ++TL;
     p.TL = TL;
-    const size_t smem = (size_t)TL * per_line + (size_t)p.Nz * sizeof(double2);
+    constexpr int NTW = NZ / (WarpFftShape<NZ>::RL > 1 ? WarpFftShape<NZ>::RL : 8);
+    const size_t smem = (size_t)TL * per_line + (size_t)NTW * sizeof(double2);
     static size_t configured = 0;
     auto kfn = zpass_warp_kernel<NZ>;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
