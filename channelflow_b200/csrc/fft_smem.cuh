@@ -257,7 +257,7 @@ __device__ __forceinline__ void warp_fft_pow2(double2* buf, const double2* tw, i
 // Callers write/read the reversed side with the index they compute anyway.  Skew addr(i) = i + i/8 + i/64 keeps every
 // quarter-warp of the stride-1/8/64 accesses AND of consecutive reversed indices (stride 64) on distinct banks.
 __host__ __device__ inline int fft_skew2(int i) { return i + (i >> 3) + (i >> 6); }
-__host__ __device__ inline int fft_skew2_len(int N) { return N + (N >> 3) + (N >> 6) + 1; }
+__host__ __device__ inline int fft_skew2_len(int N) { return fft_skew2(N - 1) + 1; }
 
 template <int N>
 struct WarpFftShape {

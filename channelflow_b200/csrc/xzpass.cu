@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(512) zpass_kernel(const ZPassParams p) {
 // grid = (ceil(Nx/TL), nyn), block = 32 * npair * TL threads.  NZ = Nz (power of two, compile-time FFT plan).
 // (at Nz = 512 two lines = 6 warps per CTA and three CTAs per SM: the register budget is set for exactly that)
 template <int NZ>
-__global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 3 : 2) zpass_warp_kernel(const ZPassParams p) {
+__global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 4 : 2) zpass_warp_kernel(const ZPassParams p) {
     const int Nx = p.Nx, Nz = NZ, TL = p.TL;
     const int nkz = p.Kz + 1;
     const bool rot = p.mode == ZP_ROTATIONAL;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 3 : 2) zpas
     constexpr int NTW = NZ / (WarpFftShape<NZ>::RL > 1 ? WarpFftShape<NZ>::RL : 8);  // twiddles the in-place passes touch
     double2* buf = dyn_smem<double2>();     // [njobs][NP]
     double2* tws = buf + (size_t)njobs * NP; // twiddle table exp(-2 pi i t / Nz), t < NTW
-    __shared__ double red[32];
+    double* red = reinterpret_cast<double*>(tws + NTW);  // [warps]
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int yl = blockIdx.y, ny = p.ny0 + yl, nx0 = blockIdx.x * TL;
     const size_t fstride = (size_t)p.nyn * Nx * nkz;  // field stride of Q and F
@@ -577,7 +577,7 @@ static int zpass_warp_launch(const ZPassParams& p0, cudaStream_t stream) {
     while (TL < 8 && (size_t)(TL + 1) * per_line <= cap && npair * (TL + 1) <= (NZ == 512 ? 6 : 10) && TL + 1 <= p.Nx) ++TL;
     p.TL = TL;
     constexpr int NTW = NZ / (WarpFftShape<NZ>::RL > 1 ? WarpFftShape<NZ>::RL : 8);
-    const size_t smem = (size_t)TL * per_line + (size_t)NTW * sizeof(double2);
+    const size_t smem = (size_t)TL * per_line + (size_t)NTW * sizeof(double2) + 16 * sizeof(double);
     static size_t configured = 0;
     auto kfn = zpass_warp_kernel<NZ>;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
