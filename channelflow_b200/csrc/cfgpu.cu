@@ -206,6 +206,15 @@ int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out) {
     CF_TRY(upload(tw, &d));
     pl.tw = reinterpret_cast<double2*>(d);
     pl.dev.tw = pl.tw;
+    {
+        pl.dev.rev = nullptr;
+        std::vector<int> rev((size_t)N);
+        for (int n = 0; n < N; ++n) rev[n] = fft_plan_rev(pl.dev, n);
+        int* dr = nullptr;
+        CF_CUDA(cudaMalloc((void**)&dr, rev.size() * sizeof(int)));
+        CF_CUDA(cudaMemcpy(dr, rev.data(), rev.size() * sizeof(int), cudaMemcpyHostToDevice));
+        pl.dev.rev = dr;
+    }
     auto res = ctx->fftplans.emplace(N, pl);
     *out = &res.first->second.dev;
     return 0;

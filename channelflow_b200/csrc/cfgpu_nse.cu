@@ -23,8 +23,19 @@ namespace cfgpu {
 int linear_launch(const TauSolveParams& p, const double* u, const double* q, double* L, cudaStream_t stream);
 }
 
-// kz columns per x-pass CTA (measured at Nx = 512: 2 -> 1.93 ms, 4 -> 1.77 ms, 6 -> 1.87 ms, 8 -> 2.70 ms)
+// kz columns per x-pass CTA.  The transforms run in place (one shared-memory buffer), so 8 columns = 128-byte pieces
+// of the pencil rows fit three CTAs per SM at Nx = 512.
 static int pick_TZ(int Nx) {
+    static const int forced = getenv("CF_XP_TZ") ? atoi(getenv("CF_XP_TZ")) : 0;
+    if (forced > 0) return forced;
+    int tz = 4608 / Nx;
+    int p = 16;
+    while (p > tz && p > 2) p >>= 1;
+    return p;
+}
+// ... the forward x-pass keeps the two-buffer Stockham transform (its in-place variant measured slower: 0.92 against
+// 0.67 ms) and therefore half the columns (measured at Nx = 512: 2 -> 1.93 ms, 4 -> 1.77 ms, 6 -> 1.87 ms, 8 -> 2.70 ms)
+static int pick_TZ_forward(int Nx) {
     int tz = 2304 / Nx;
     int p = 16;
     while (p > tz && p > 2) p >>= 1;
@@ -502,6 +513,7 @@ static int nonlinear_fused_general(cfgpu_nse nse, cfgpu_field u, cfgpu_field f, 
             xp.srcb[i] = (prod && i < 3) ? 3 + i : -1;
             xp.opb[i] = 1;
         }
+        xp.TZ = pick_TZ_forward(nse->Nx);
         if (prod) xp.TZ = xp.TZ > 1 ? xp.TZ / 2 : 1;
         StageTimer _t(ctx, 3);
         CF_TRY(xpass_forward_launch(xp, ctx->stream));
@@ -626,7 +638,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     XPassParams xp;
     memset(&xp, 0, sizeof xp);
     xp.Nx = nse->Nx; xp.Ny = nse->Ny; xp.Kx = nse->Kx; xp.Kz = nse->Kz;
-    xp.TZ = pick_TZ(nse->Nx);
+    xp.TZ = pick_TZ_forward(nse->Nx);
     xp.Lx = nse->Lx;
     xp.plan = *fx;
     xp.nfields = 3;

@@ -19,6 +19,7 @@ struct FftPlanDev {
     int npass;
     int radix[FFT_MAXPASS];
     const double2* tw;  // N entries
+    const int* rev;     // N entries: fft_plan_rev(n), the digit-reversed row of the in-place transforms
 };
 
 template <int DIR>
@@ -172,6 +173,79 @@ __device__ __forceinline__ double2* fft_smem(double2* a, double2* b, const FftPl
         Ns *= R;
     }
     return a;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// In-place block transform of C columns, a[n * C + c], any plan (radix 8/4/2/3/5): a butterfly reads and writes the same
+// R rows, so one buffer is enough (half the shared memory of the Stockham version: twice the columns per CTA).
+//   DIF = false (decimation in time):      input row n at fft_plan_rev(pl, n), output in natural order
+//   DIF = true  (decimation in frequency): input in natural order, output row k at fft_plan_rev(pl, k)
+// With C a multiple of 8 every quarter-warp touches one contiguous 128-byte piece of a row: no bank conflicts at any stride.
+__host__ __device__ inline int fft_plan_rev(const FftPlanDev& pl, int n) {
+    int pos = 0, span = pl.N;
+    for (int p = pl.npass - 1; p >= 0; --p) {
+        const int R = pl.radix[p];
+        span /= R;
+        pos += (n % R) * span;
+        n /= R;
+    }
+    return pos;
+}
+
+template <int DIR, int R, bool DIF, bool TWPOW>
+__device__ __forceinline__ void fft_inplace_pass(double2* __restrict__ a, const FftPlanDev& pl, const double2* __restrict__ tw,
+                                                 int Ns, int C, int tid, int nthreads) {
+    const int N = pl.N;
+    const int nb = N / R;
+    const int tstep = N / (Ns * R);
+    const int total = nb * C;
+    for (int idx = tid; idx < total; idx += nthreads) {
+        const int j = idx / C, c = idx - j * C;
+        const int k = j % Ns;
+        double2* e = a + (size_t)((j / Ns) * Ns * R + k) * C + c;
+        const int es = Ns * C;
+        double2 v[R], w[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = e[r * es];
+        if (Ns > 1) {
+            if (TWPOW) twiddle_powers<R>(tw[k * tstep], w);
+            else {
+#pragma unroll
+                for (int r = 1; r < R; ++r) w[r] = tw[r * k * tstep];
+            }
+            if (!DIF) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[r] = tw_mul<DIR>(v[r], w[r]);
+            }
+        }
+        radix_butterfly<DIR, R>(v);
+        if (DIF && Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = tw_mul<DIR>(v[r], w[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) e[r * es] = v[r];
+    }
+}
+
+// Ends with a __syncthreads(); the caller must have synchronised after filling `a`.
+template <int DIR, bool DIF, bool TWPOW>
+__device__ __forceinline__ void fft_smem_inplace(double2* a, const FftPlanDev& pl, const double2* tw, int C, int tid, int nthreads) {
+    int Ns = 1;
+    if (DIF)
+        for (int p = 0; p < pl.npass; ++p) Ns *= pl.radix[p];
+    for (int q = 0; q < pl.npass; ++q) {
+        const int p = DIF ? pl.npass - 1 - q : q;
+        const int R = pl.radix[p];
+        if (DIF) Ns /= R;
+        if (R == 8) fft_inplace_pass<DIR, 8, DIF, TWPOW>(a, pl, tw, Ns, C, tid, nthreads);
+        else if (R == 4) fft_inplace_pass<DIR, 4, DIF, TWPOW>(a, pl, tw, Ns, C, tid, nthreads);
+        else if (R == 2) fft_inplace_pass<DIR, 2, DIF, TWPOW>(a, pl, tw, Ns, C, tid, nthreads);
+        else if (R == 3) fft_inplace_pass<DIR, 3, DIF, TWPOW>(a, pl, tw, Ns, C, tid, nthreads);
+        else fft_inplace_pass<DIR, 5, DIF, TWPOW>(a, pl, tw, Ns, C, tid, nthreads);
+        __syncthreads();
+        if (!DIF) Ns *= R;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

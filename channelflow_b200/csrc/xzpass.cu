@@ -15,20 +15,27 @@ static int set_smem(const void* fn, size_t bytes, size_t& configured);
 
 // ------------------------------------------------------------------------------------------------ x inverse
 // grid = (ceil(nkz/TZ), nyn, nfields)   P[src][yl][mxi][kz] -> Q[f][yl][nx][kz], optional d/dx = i 2 pi kx / Lx
-__global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassParams p) {
+__global__ void __launch_bounds__(XZ_THREADS, 3) xpass_inverse_kernel(const XPassParams p) {
     const int Nx = p.Nx, Kx = p.Kx, TZ = p.TZ;
     const int nmx = 2 * Kx + 1, nkz = p.Kz + 1;
-    double2* a = dyn_smem<double2>();
-    double2* b = a + (size_t)Nx * TZ;
-    double2* tws = b + (size_t)Nx * TZ;  // twiddle table in shared memory
+    double2* a = dyn_smem<double2>();                 // [Nx][TZ], transformed in place
+    double2* tws = a + (size_t)Nx * TZ;               // twiddle table in shared memory
+    int* rev = reinterpret_cast<int*>(tws + Nx);      // digit-reversed row of mode row mx (input side of the DIT transform)
     const int tid = threadIdx.x;
     const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
     const int s = p.src[f], oa = p.opa[f], sb = p.srcb[f], ob = p.opb[f];
 
-    for (int t = tid; t < Nx; t += XZ_THREADS) tws[t] = __ldg(&p.plan.tw[t]);
+    for (int t = tid; t < Nx; t += XZ_THREADS) {
+        tws[t] = __ldg(&p.plan.tw[t]);
+        rev[t] = __ldg(&p.plan.rev[t]);
+    }
+    __syncthreads();
     // zero the aliased rows Kx+1 .. Nx-Kx-1
     const int nzero = (Nx - nmx) * TZ;
-    for (int idx = tid; idx < nzero; idx += XZ_THREADS) a[(Kx + 1) * TZ + idx] = make_double2(0.0, 0.0);
+    for (int idx = tid; idx < nzero; idx += XZ_THREADS) {
+        const int r = idx / TZ, c = idx - r * TZ;
+        a[rev[Kx + 1 + r] * TZ + c] = make_double2(0.0, 0.0);
+    }
     const double2* __restrict__ in = p.in;
     // four rows per thread in flight: all loads are issued before the first use
     for (int i0 = tid; i0 < nmx * TZ; i0 += 4 * XZ_THREADS) {
@@ -65,16 +72,16 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_inverse_kernel(const XPassPa
                 }
                 v = make_double2(v.x - w.x, v.y - w.y);
             }
-            a[mx * TZ + c] = v;
+            a[rev[mx] * TZ + c] = v;
         }
     }
     __syncthreads();
-    const double2* res = fft_smem<+1, false>(a, b, p.plan, tws, TZ, tid, XZ_THREADS);
+    fft_smem_inplace<+1, false, true>(a, p.plan, tws, TZ, tid, XZ_THREADS);
     double2* __restrict__ out = p.out + ((size_t)f * p.nyn + yl) * Nx * nkz;
     for (int idx = tid; idx < Nx * TZ; idx += XZ_THREADS) {
         const int nx = idx / TZ, c = idx - nx * TZ;
         const int kz = kz0 + c;
-        if (kz < nkz) out[(size_t)nx * nkz + kz] = res[idx];
+        if (kz < nkz) out[(size_t)nx * nkz + kz] = a[idx];
     }
 }
 
@@ -541,7 +548,7 @@ static int set_smem(const void* fn, size_t bytes, size_t& configured) {
 
 int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream) {
     const int nkz = p.Kz + 1;
-    const size_t smem = (2 * (size_t)p.Nx * p.TZ + p.Nx) * sizeof(double2);
+    const size_t smem = ((size_t)p.Nx * p.TZ + p.Nx) * sizeof(double2) + (size_t)p.Nx * sizeof(int);
     static size_t configured = 0;
     auto kfn = xpass_inverse_kernel;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
