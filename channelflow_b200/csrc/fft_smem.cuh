@@ -199,10 +199,13 @@ __device__ __forceinline__ void fft_inplace_pass(double2* __restrict__ a, const 
     const int nb = N / R;
     const int tstep = N / (Ns * R);
     const int total = nb * C;
+    const bool pow2 = ((C & (C - 1)) | (Ns & (Ns - 1))) == 0;   // CTA-uniform: shifts instead of integer divisions
+    const int cs = __ffs(C) - 1, nss = __ffs(Ns) - 1;
     for (int idx = tid; idx < total; idx += nthreads) {
-        const int j = idx / C, c = idx - j * C;
-        const int k = j % Ns;
-        double2* e = a + (size_t)((j / Ns) * Ns * R + k) * C + c;
+        int j, c, k, jb;
+        if (pow2) { j = idx >> cs; c = idx & (C - 1); k = j & (Ns - 1); jb = j >> nss; }
+        else { j = idx / C; c = idx - j * C; k = j % Ns; jb = j / Ns; }
+        double2* e = a + (size_t)(jb * Ns * R + k) * C + c;
         const int es = Ns * C;
         double2 v[R], w[R];
 #pragma unroll

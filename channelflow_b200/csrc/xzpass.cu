@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(XZ_THREADS, 3) xpass_inverse_kernel(const XPas
     const int nmx = 2 * Kx + 1, nkz = p.Kz + 1;
     double2* a = dyn_smem<double2>();                 // [Nx][TZ], transformed in place
     double2* tws = a + (size_t)Nx * TZ;               // twiddle table in shared memory
-    int* rev = reinterpret_cast<int*>(tws + Nx);      // digit-reversed row of mode row mx (input side of the DIT transform)
+    double* kxf = reinterpret_cast<double*>(tws + Nx);  // 2 pi kx / Lx of pencil row mxi
+    int* rev = reinterpret_cast<int*>(kxf + Nx);       // digit-reversed row of mode row mx (input side of the DIT transform)
     const int tid = threadIdx.x;
     const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
     const int s = p.src[f], oa = p.opa[f], sb = p.srcb[f], ob = p.opb[f];
@@ -29,45 +30,46 @@ __global__ void __launch_bounds__(XZ_THREADS, 3) xpass_inverse_kernel(const XPas
         tws[t] = __ldg(&p.plan.tw[t]);
         rev[t] = __ldg(&p.plan.rev[t]);
     }
-    __syncthreads();
-    // zero the aliased rows Kx+1 .. Nx-Kx-1
-    const int nzero = (Nx - nmx) * TZ;
-    for (int idx = tid; idx < nzero; idx += XZ_THREADS) {
-        const int r = idx / TZ, c = idx - r * TZ;
-        a[rev[Kx + 1 + r] * TZ + c] = make_double2(0.0, 0.0);
+    for (int mxi = tid; mxi < nmx; mxi += XZ_THREADS) {
+        const int kx = mxi <= Kx ? mxi : mxi - nmx;
+        kxf[mxi] = TWO_PI * kx / p.Lx;
     }
+    __syncthreads();
+    // TZ is a power of two dividing the block size: a thread keeps its column c and walks the pencil rows
+    const int tzs = __ffs(TZ) - 1;
+    const int c = tid & (TZ - 1), kz = kz0 + c;
+    const int mstep = XZ_THREADS >> tzs;
+    // zero the aliased rows Kx+1 .. Nx-Kx-1
+    for (int r = tid >> tzs; r < Nx - nmx; r += mstep) a[rev[Kx + 1 + r] * TZ + c] = make_double2(0.0, 0.0);
     const double2* __restrict__ in = p.in;
+    const double kzf = TWO_PI * kz / p.Lz;
+    const bool live = kz < nkz;
     // four rows per thread in flight: all loads are issued before the first use
-    for (int i0 = tid; i0 < nmx * TZ; i0 += 4 * XZ_THREADS) {
+    for (int m0 = tid >> tzs; m0 < nmx; m0 += 4 * mstep) {
         double2 va[4], vb[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-            const int idx = i0 + h * XZ_THREADS;
-            const int mxi = idx / TZ, c = idx - mxi * TZ;
-            const int kz = kz0 + c;
+            const int mxi = m0 + h * mstep;
             va[h] = vb[h] = make_double2(0.0, 0.0);
-            if (idx < nmx * TZ && kz < nkz) {
+            if (mxi < nmx && live) {
                 va[h] = in[xpass_row_offset(p, s, yl, mxi, nkz) + kz];
                 if (sb >= 0) vb[h] = in[xpass_row_offset(p, sb, yl, mxi, nkz) + kz];
             }
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-            const int idx = i0 + h * XZ_THREADS;
-            if (idx >= nmx * TZ) break;
-            const int mxi = idx / TZ, c = idx - mxi * TZ;
-            const int kz = kz0 + c;
-            const int kx = mxi <= Kx ? mxi : mxi - nmx;
-            const int mx = kx >= 0 ? kx : Nx + kx;
+            const int mxi = m0 + h * mstep;
+            if (mxi >= nmx) break;
+            const int mx = mxi <= Kx ? mxi : Nx - nmx + mxi;
             double2 v = va[h];
             if (oa) {
-                const double k = oa == 1 ? TWO_PI * kx / p.Lx : TWO_PI * kz / p.Lz;
+                const double k = oa == 1 ? kxf[mxi] : kzf;
                 v = make_double2(-k * v.y, k * v.x);
             }
             if (sb >= 0) {
                 double2 w = vb[h];
                 if (ob) {
-                    const double k = ob == 1 ? TWO_PI * kx / p.Lx : TWO_PI * kz / p.Lz;
+                    const double k = ob == 1 ? kxf[mxi] : kzf;
                     w = make_double2(-k * w.y, k * w.x);
                 }
                 v = make_double2(v.x - w.x, v.y - w.y);
@@ -78,11 +80,8 @@ __global__ void __launch_bounds__(XZ_THREADS, 3) xpass_inverse_kernel(const XPas
     __syncthreads();
     fft_smem_inplace<+1, false, true>(a, p.plan, tws, TZ, tid, XZ_THREADS);
     double2* __restrict__ out = p.out + ((size_t)f * p.nyn + yl) * Nx * nkz;
-    for (int idx = tid; idx < Nx * TZ; idx += XZ_THREADS) {
-        const int nx = idx / TZ, c = idx - nx * TZ;
-        const int kz = kz0 + c;
-        if (kz < nkz) out[(size_t)nx * nkz + kz] = a[idx];
-    }
+    if (live)
+        for (int nx = tid >> tzs; nx < Nx; nx += mstep) out[(size_t)nx * nkz + kz] = a[nx * TZ + c];
 }
 
 // ------------------------------------------------------------------------------------------------ x forward
@@ -548,7 +547,8 @@ static int set_smem(const void* fn, size_t bytes, size_t& configured) {
 
 int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream) {
     const int nkz = p.Kz + 1;
-    const size_t smem = ((size_t)p.Nx * p.TZ + p.Nx) * sizeof(double2) + (size_t)p.Nx * sizeof(int);
+    if (p.TZ & (p.TZ - 1) || XZ_THREADS % p.TZ) { set_last_error("xpass_inverse: TZ must be a power of two"); return 1; }
+    const size_t smem = ((size_t)p.Nx * p.TZ + p.Nx) * sizeof(double2) + (size_t)p.Nx * (sizeof(int) + sizeof(double));
     static size_t configured = 0;
     auto kfn = xpass_inverse_kernel;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
