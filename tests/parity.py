@@ -235,3 +235,43 @@ def orr_sommerfeld(lib, timestepping="sbdf3", nonlinearity="rot", T1=13.0, use_r
         dns.advance(N)
         t += N * dt
     return {"err": err, "norm": mk(field_of(c0)).l2norm()}
+
+
+def layout_equivalence(lib, cfg, nsteps=4, junk=True, **flag_over):
+    """The tile-major layout of the hot-path fields is an internal representation: a DNS run with it and one with
+    CFGPU_SERIAL_LAYOUT=1 must give the same bits.  With `junk`, the initial field carries non-zero aliased modes and is
+    not flagged padded: NSE::solve writes retained modes only (nse.cpp:566-572), so the junk must survive the steps
+    untouched in both layouts (it never enters the de-aliased nonlinear term of this implementation)."""
+    import os
+    fl = dict(cfg["flags"]); fl.update(flag_over)
+    ur = ref_random(cfg, 7)
+    u0 = ur.data.copy()
+    st = ur.state()
+    Nx, Nz = cfg["Nx"], cfg["Nz"]
+    Kx, Kz = Nx // 3 - 1, Nz // 3 - 1
+    c0 = u0.view(np.complex128)
+    alias = np.zeros(c0.shape, bool)
+    alias[:, :, Kx + 1:Nx - Kx, :] = True
+    alias[..., Kz + 1:] = True
+    if junk:
+        rng = np.random.default_rng(3)
+        c0[alias] = 1e-3 * (rng.standard_normal(int(alias.sum())) + 1j * rng.standard_normal(int(alias.sum())))
+    res = {}
+    for mode in ("tile", "serial"):
+        if mode == "serial":
+            os.environ["CFGPU_SERIAL_LAYOUT"] = "1"
+        try:
+            ug = cf.FlowField(lib, ur.Nx, ur.Ny, ur.Nz, 3, ur.Lx, ur.Lz, ur.a, ur.b).set(u0, st[0], st[1], padded=not junk)
+            gd = cf.DNS(ug, cf.make_flags(**fl))
+            gd.advance(nsteps)
+            u, q = gd.get()
+            res[mode] = (u.get().copy(), q.get().copy())
+        finally:
+            os.environ.pop("CFGPU_SERIAL_LAYOUT", None)
+    ut, us = res["tile"][0].view(np.complex128), res["serial"][0].view(np.complex128)
+    return {"u_equal": bool(np.array_equal(res["tile"][0], res["serial"][0])),
+            "q_equal": bool(np.array_equal(res["tile"][1], res["serial"][1])),
+            # (without junk the field is uploaded as its retained box: the aliased modes are exactly zero on the device)
+            "junk_kept": bool(np.array_equal(ut[alias], c0[alias] if junk else 0 * c0[alias])) and
+                         bool(np.array_equal(us[alias], c0[alias] if junk else 0 * c0[alias])),
+            "moved": float(np.abs(ut[~alias] - c0[~alias]).max())}

@@ -252,3 +252,13 @@ def test_host_mirror_after_state_change(lib):
     assert ug.cmplx(1, 3, 1, 0) == keep
     c = ug.get().view(np.complex128)
     assert c[0, 3, mx_alias, 0] == 0.0                      # serial layout [i][ny][nx][mz]
+
+
+@pytest.mark.parametrize("junk", [False, True])
+def test_tile_layout_is_transparent(lib, junk):
+    """Tile-major hot-path fields vs CFGPU_SERIAL_LAYOUT=1: identical bits; aliased-mode content of an un-padded initial
+    field survives the steps untouched (NSE::solve writes retained modes only, nse.cpp:566-572)."""
+    r = parity.layout_equivalence(lib, SMALL, nsteps=4, junk=junk)
+    assert r["u_equal"] and r["q_equal"] and r["junk_kept"] and r["moved"] > 0, r
+    r = parity.layout_equivalence(lib, parity.C1, nsteps=3, junk=junk, timestepping="cnab2")
+    assert r["u_equal"] and r["q_equal"] and r["junk_kept"], r

@@ -240,3 +240,13 @@ def test_zero_and_parabola_known_answers(lib):
                                  dealiasing="none"))
     d.advance(10)
     assert d.get()[0].l2dist(p) < 1e-13
+
+
+@pytest.mark.parametrize("junk", [False, True])
+def test_tile_layout_is_transparent(lib, junk):
+    """Tile-major hot-path fields vs CFGPU_SERIAL_LAYOUT=1: identical bits; aliased-mode content of an un-padded initial
+    field survives the steps untouched (NSE::solve writes retained modes only, nse.cpp:566-572)."""
+    r = parity.layout_equivalence(lib, MID, nsteps=4, junk=junk)
+    assert r["u_equal"] and r["q_equal"] and r["junk_kept"] and r["moved"] > 0, r
+    r = parity.layout_equivalence(lib, parity.C1, nsteps=3, junk=junk, timestepping="cnab2")
+    assert r["u_equal"] and r["q_equal"] and r["junk_kept"], r
