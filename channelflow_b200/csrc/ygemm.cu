@@ -209,43 +209,62 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
                 }
             }
         }
-        // remainder rows (at most 2) as dot products: thread -> (row, column)
-        for (int idx = tid; idx < (Mmax - Mgemm) * BN; idx += YG_THREADS) {
-            const int r = Mgemm + idx / BN, c = idx % BN;
+        // remainder rows (at most 2) as dot products.  Every warp takes BN/8 columns and splits K over its lanes
+        // (lane = slice * CW + column), partial sums combined with shuffles: no block barrier, all 8 warps busy, a quarter
+        // (BN = 64) of the K loop per lane.  (One thread per column on two warps kept the other six -- and the tensor
+        // pipe of the SM, one CTA being resident -- waiting for ~45 % of the CTA's life time: ncu r01f.)
+        {
+            constexpr int CW = BN / (YG_THREADS / 32);   // columns per warp
+            constexpr int NSL = 32 / CW;                 // K slices per column
+            static_assert(CW >= 1 && CW * NSL == 32, "BN must be a multiple of the warp count and divide 32 per warp");
+            const int cc = lane % CW, sl = lane / CW;
+            const int c = warp * CW + cc;
             const long off = cout[c];
-            if (off < 0) continue;
-            double E = 0.0, O = 0.0;
-            if (r < p.M) {
-                const double* __restrict__ ar = A1 + (size_t)r * p.K1p;
+            for (int r = Mgemm; r < Mmax; ++r) {
+                double E = 0.0, O = 0.0;
+                {   // both parity products in one loop: two independent chains, twice the loads in flight
+                    const bool hasE = r < p.M, hasO = r < p.M2;
+                    const double* __restrict__ a1 = A1 + (size_t)r * p.K1p;
+                    const double* __restrict__ a2 = A2 + (size_t)r * p.K2p;
+                    const int K1 = hasE ? p.K1 : 0, K2 = hasO ? p.K2 : 0;
+                    const int Kc = K1 < K2 ? K1 : K2;
+                    int k = sl;
 #pragma unroll 8
-                for (int k = 0; k < p.K1; ++k) E += __ldg(ar + k) * B1[k * LD + c];
-            }
-            if (r < p.M2) {
-                const double* __restrict__ ar = A2 + (size_t)r * p.K2p;
-#pragma unroll 8
-                for (int k = 0; k < p.K2; ++k) O += __ldg(ar + k) * B2[k * LD + c];
-            }
-            if (two && job.in2 && p.mode == 1) {
-                if (r < p.M) {
-                    const double* __restrict__ ar = p.A1b + (size_t)r * p.K1p;
-#pragma unroll 8
-                    for (int k = 0; k < p.K1; ++k) E += __ldg(ar + k) * B2b[k * LD + c];
+                    for (; k < Kc; k += NSL) {
+                        E += __ldg(a1 + k) * B1[k * LD + c];
+                        O += __ldg(a2 + k) * B2[k * LD + c];
+                    }
+                    for (int k1 = k; k1 < K1; k1 += NSL) E += __ldg(a1 + k1) * B1[k1 * LD + c];
+                    for (int k2 = k; k2 < K2; k2 += NSL) O += __ldg(a2 + k2) * B2[k2 * LD + c];
                 }
-                if (r < p.M2) {
-                    const double* __restrict__ ar = p.A2b + (size_t)r * p.K1p;
-#pragma unroll 8
-                    for (int k = 0; k < p.K1; ++k) O += __ldg(ar + k) * B1b[k * LD + c];
+                if (two && job.in2 && p.mode == 1) {
+                    if (r < p.M) {
+                        const double* __restrict__ ar = p.A1b + (size_t)r * p.K1p;
+#pragma unroll 4
+                        for (int k = sl; k < p.K1; k += NSL) E += __ldg(ar + k) * B2b[k * LD + c];
+                    }
+                    if (r < p.M2) {
+                        const double* __restrict__ ar = p.A2b + (size_t)r * p.K1p;
+#pragma unroll 4
+                        for (int k = sl; k < p.K1; k += NSL) O += __ldg(ar + k) * B1b[k * LD + c];
+                    }
                 }
-            }
-            if (p.mode == 0) {
-                if (r < p.M) {
-                    row_ptr(r)[off] = E + O;
-                    const int rr = Nb - r;
-                    if (rr != r) row_ptr(rr)[off] = sgn * (E - O);
+#pragma unroll
+                for (int d = CW; d < 32; d <<= 1) {
+                    E += __shfl_xor_sync(0xffffffffu, E, d);
+                    O += __shfl_xor_sync(0xffffffffu, O, d);
                 }
-            } else {
-                if (r < p.M) row_ptr(2 * r)[off] = E;
-                if (r < p.M2) row_ptr(2 * r + 1)[off] = O;
+                if (sl != 0 || off < 0) continue;
+                if (p.mode == 0) {
+                    if (r < p.M) {
+                        row_ptr(r)[off] = E + O;
+                        const int rr = Nb - r;
+                        if (rr != r) row_ptr(rr)[off] = sgn * (E - O);
+                    }
+                } else {
+                    if (r < p.M) row_ptr(2 * r)[off] = E;
+                    if (r < p.M2) row_ptr(2 * r + 1)[off] = O;
+                }
             }
         }
     }
