@@ -181,6 +181,13 @@ __device__ __forceinline__ double2* fft_smem(double2* a, double2* b, const FftPl
 //   DIF = false (decimation in time):      input row n at fft_plan_rev(pl, n), output in natural order
 //   DIF = true  (decimation in frequency): input in natural order, output row k at fft_plan_rev(pl, k)
 // With C a multiple of 8 every quarter-warp touches one contiguous 128-byte piece of a row: no bank conflicts at any stride.
+// number of leading twiddle-table entries the product-tree passes touch: tw[k * tstep] with k * tstep < N / R_p
+__host__ __device__ inline int fft_plan_ntw(const FftPlanDev& pl) {
+    int rmin = 0;
+    for (int p = 1; p < pl.npass; ++p)
+        if (rmin == 0 || pl.radix[p] < rmin) rmin = pl.radix[p];
+    return rmin ? pl.N / rmin : 1;
+}
 __host__ __device__ inline int fft_plan_rev(const FftPlanDev& pl, int n) {
     int pos = 0, span = pl.N;
     for (int p = pl.npass - 1; p >= 0; --p) {

@@ -19,15 +19,18 @@ __global__ void __launch_bounds__(XZ_THREADS, 3) xpass_inverse_kernel(const XPas
     const int Nx = p.Nx, Kx = p.Kx, TZ = p.TZ;
     const int nmx = 2 * Kx + 1, nkz = p.Kz + 1;
     double2* a = dyn_smem<double2>();                 // [Nx][TZ], transformed in place
-    double2* tws = a + (size_t)Nx * TZ;               // twiddle table in shared memory
-    double* kxf = reinterpret_cast<double*>(tws + Nx);  // 2 pi kx / Lx of pencil row mxi
-    int* rev = reinterpret_cast<int*>(kxf + Nx);       // digit-reversed row of mode row mx (input side of the DIT transform)
+    // the in-place passes with product-tree twiddles only touch the head of the table (64 entries at Nx = 512): small
+    // enough that three CTAs fit an SM
+    const int ntw = fft_plan_ntw(p.plan);
+    double2* tws = a + (size_t)Nx * TZ;                 // twiddle table in shared memory
+    double* kxf = reinterpret_cast<double*>(tws + ntw);  // 2 pi kx / Lx of pencil row mxi
+    int* rev = reinterpret_cast<int*>(kxf + nmx);       // digit-reversed row of mode row mx (input side of the DIT transform)
     const int tid = threadIdx.x;
     const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
     const int s = p.src[f], oa = p.opa[f], sb = p.srcb[f], ob = p.opb[f];
 
     for (int t = tid; t < Nx; t += XZ_THREADS) {
-        tws[t] = __ldg(&p.plan.tw[t]);
+        if (t < ntw) tws[t] = __ldg(&p.plan.tw[t]);
         rev[t] = __ldg(&p.plan.rev[t]);
     }
     for (int mxi = tid; mxi < nmx; mxi += XZ_THREADS) {
@@ -548,7 +551,8 @@ static int set_smem(const void* fn, size_t bytes, size_t& configured) {
 int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream) {
     const int nkz = p.Kz + 1;
     if (p.TZ & (p.TZ - 1) || XZ_THREADS % p.TZ) { set_last_error("xpass_inverse: TZ must be a power of two"); return 1; }
-    const size_t smem = ((size_t)p.Nx * p.TZ + p.Nx) * sizeof(double2) + (size_t)p.Nx * (sizeof(int) + sizeof(double));
+    const int ntw = fft_plan_ntw(p.plan);
+    const size_t smem = ((size_t)p.Nx * p.TZ + ntw) * sizeof(double2) + (size_t)(2 * p.Kx + 1) * sizeof(double) + (size_t)p.Nx * sizeof(int);
     static size_t configured = 0;
     auto kfn = xpass_inverse_kernel;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
