@@ -772,8 +772,17 @@ int cfgpu_nse_linear(cfgpu_nse nse, cfgpu_field u, cfgpu_field q, cfgpu_field L)
     CF_ARG(!nse->tau.empty(), "cfgpu_nse_linear: call reset_lambda first");
     TauSolveParams tp;
     CF_TRY(fill_tau_params(nse, 0, tp));
-    CF_TRY(field_serial(u)); CF_TRY(field_serial(q)); CF_TRY(field_serial(L));
-    { StageTimer _t(nse->ctx, 6); CF_TRY(linear_launch(tp, u->dser, q->dser, L->dser, nse->ctx->stream)); }
+    if (nse->use_tile) {
+        // same policy as the solve: hot-path fields are tile-major; only the retained box of L is written (nse.cpp:393-477)
+        CF_TRY(field_tile(u, nse->tg)); CF_TRY(field_tile(q, nse->tg)); CF_TRY(field_tile_output(L, nse->tg, false));
+        tp.tile_layout = 1;
+        StageTimer _t(nse->ctx, 6);
+        CF_TRY(linear_launch(tp, u->dtile, q->dtile, L->dtile, nse->ctx->stream));
+    } else {
+        CF_TRY(field_serial(u)); CF_TRY(field_serial(q)); CF_TRY(field_serial(L));
+        StageTimer _t(nse->ctx, 6);
+        CF_TRY(linear_launch(tp, u->dser, q->dser, L->dser, nse->ctx->stream));
+    }
     L->xzstate = L->ystate = CFGPU_SPECTRAL;
     return 0;
 }

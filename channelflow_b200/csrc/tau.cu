@@ -882,21 +882,34 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) linear_kernel(const TauSolv
     const int N = td.N;
     const int tid = threadIdx.x, NT = TAU_SETUP_THREADS;
     const double scale = 4.0 / (td.b - td.a);
-    const long rs = (long)p.g.Nx * (2 * (p.g.Nz / 2 + 1));
-    const long cs = rs * p.g.Ny;
+    // u, q, L in the reference layout, or all three tile-major with td.TM modes per tile (q: one component)
+    const bool tiled = p.tile_layout != 0;
+    const long rs = tiled ? 2L * td.TM : (long)p.g.Nx * (2 * (p.g.Nz / 2 + 1));
+    const long cs = tiled ? (long)N * td.TM * 2 : rs * p.g.Ny;
     const int TM = p.TM_lin, TT = 2 * TM;
     const size_t AS = (size_t)N * TT;
     double* Pk = dyn_smem<double>();
     double* Pyk = Pk + AS; double* X = Pyk + AS; double* T = X + AS; double* R = T + AS;
     double* s_k = R + AS;  // [3][TM]: kappa2, kxx, kzz
-    long* s_off = reinterpret_cast<long*>(s_k + 3 * TM);
+    long* s_off = reinterpret_cast<long*>(s_k + 3 * TM);   // mode offset in a 3-component field (u, L); -1: no mode
+    long* s_offq = s_off + TM;                              // ... in the 1-component field q
     __shared__ double s_shear[2];
     const int q0 = blockIdx.x * TM;
     if (tid < TM) {
         const int qq = q0 + tid;
-        long off = -1;
-        if (qq < td.nq) { int kx, kz; mode_of_q(qq, p.g, kx, kz, off); }
+        long off = -1, offq = -1;
+        if (qq < td.nq) {
+            int kx, kz;
+            mode_of_q(qq, p.g, kx, kz, off);
+            offq = off;
+            if (tiled) {
+                const long t = qq / td.TM, pos = qq % td.TM;
+                off = t * 3 * N * td.TM * 2 + pos * 2;
+                offq = t * N * td.TM * 2 + pos * 2;
+            }
+        }
         s_off[tid] = off;
+        s_offq[tid] = offq;
         const int qs = qq < td.nq ? qq : 0;
         s_k[tid] = td.scq(TSC_LAMP, qs);
         s_k[TM + tid] = td.scq(TSC_KXX, qs);
@@ -905,7 +918,7 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) linear_kernel(const TauSolv
     __syncthreads();
     for (int idx = tid; idx < (int)AS; idx += NT) {
         const int n = idx / TT, t = idx - n * TT;
-        const long off = s_off[t >> 1];
+        const long off = s_offq[t >> 1];
         Pk[idx] = off >= 0 ? q[n * rs + off + (t & 1)] : 0.0;
     }
     __syncthreads();
@@ -1002,7 +1015,7 @@ int tau_setup_launch(const TauData& td, const ModeGeom& g, double lambda_t, cuda
 
 int linear_launch(const TauSolveParams& p, const double* u, const double* q, double* L, cudaStream_t stream) {
     const int TT = 2 * p.TM_lin;
-    const size_t smem = ((size_t)5 * p.td.N * TT + 3 * p.TM_lin) * sizeof(double) + p.TM_lin * sizeof(long);
+    const size_t smem = ((size_t)5 * p.td.N * TT + 3 * p.TM_lin) * sizeof(double) + 2 * p.TM_lin * sizeof(long);
     static size_t configured = 0;
     auto kfn = linear_kernel;
     if (smem > configured) {
