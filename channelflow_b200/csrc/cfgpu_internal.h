@@ -91,7 +91,7 @@ struct cfgpu_field_s {
     int clean_Kx = -1, clean_Kz = -1;  // all modes outside this box are known to be exactly zero (-1: unknown)
     // The data lives in one of two buffers.  `dser` is the reference's serial layout [i][my][mx][mz] (always allocated);
     // `dtile` (lazily allocated) is the tile-major layout of the retained box, produced and consumed by the DNS hot path
-    // (cfgpu_nse_solve / cfgpu_nse_nonlinear).  layout says which one is current for the retained box; outside the box
+    // (cfgpu_nse_solve / cfgpu_nse_nonlinear / cfgpu_nse_linear).  layout says which one is current for the retained box; outside the box
     // the field is zero if tile_outside_zero, else whatever dser holds there.  Everything but the hot path goes through
     // field_serial(), which converts back on demand.
     double* dser = nullptr;

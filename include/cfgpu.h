@@ -89,6 +89,10 @@ int cfgpu_field_set_state(cfgpu_field f, int xzstate, int ystate);
 int cfgpu_field_get_state(cfgpu_field f, int* xzstate, int* ystate);
 int cfgpu_field_set_padded(cfgpu_field f, int padded);
 int cfgpu_field_get_padded(cfgpu_field f, int* padded);
+/* Device pointer to the data in the reference's serial layout (flowfield.h:370-402).  Fields produced by the time-stepping
+ * calls (cfgpu_nse_solve / _nonlinear / _linear) may live in an internal tile-major layout; this call -- like every
+ * call that is not one of those three -- converts back first.  The pointer is valid until the next cfgpu_nse_* call on
+ * the field. */
 int cfgpu_field_device_ptr(cfgpu_field f, double** dptr, long long* ndoubles);
 /* FlowField::add / operator*= / += / -= (flowfield.h:596-615, flowfield.cpp:1459-1469, 1759-1771):  y += a*x + b*z */
 int cfgpu_field_axpby(cfgpu_field y, double a, cfgpu_field x, double b, cfgpu_field z /* may be NULL */);
