@@ -181,6 +181,8 @@ __device__ __forceinline__ double2* fft_smem(double2* a, double2* b, const FftPl
 //   DIF = false (decimation in time):      input row n at fft_plan_rev(pl, n), output in natural order
 //   DIF = true  (decimation in frequency): input in natural order, output row k at fft_plan_rev(pl, k)
 // With C a multiple of 8 every quarter-warp touches one contiguous 128-byte piece of a row: no bank conflicts at any stride.
+// (Used by the inverse x-pass.  The DIF variant in the forward x-pass measured slower than the Stockham transform there
+// -- 0.92 against 0.67 ms at 512x257x512 -- so that kernel keeps two buffers; the variant stays for the next attempt.)
 // number of leading twiddle-table entries the product-tree passes touch: tw[k * tstep] with k * tstep < N / R_p
 __host__ __device__ inline int fft_plan_ntw(const FftPlanDev& pl) {
     int rmin = 0;
