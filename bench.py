@@ -39,8 +39,17 @@ STAGES = ["inv_y_gemm", "inv_x_pass", "z_pass_nl", "fwd_x_pass", "fwd_y_gemm", "
 # algorithmic bytes per stage in units of W (rotational SBDF-k with k=3)
 # (the x/z passes move one field less than SURVEY's 61 W table: curl u is formed while the inverse x-pass loads, so
 # 6 fields -- u and curl u -- instead of 7 go through it; 59 W per step)
-STAGE_W = {"inv_y_gemm": 3 + 5, "inv_x_pass": 5 + 6, "z_pass_nl": 6 + 3, "fwd_x_pass": 3 + 3, "fwd_y_gemm": 3 + 3, "tau_solve": 15 + 4}
-STEP_W = 59
+# Algorithmic bytes per stage in units of W: SURVEY.md 8(d)'s tables, SBDF3 (k = 3).  Rotational form, 61 W per step of which
+# the transforms + nonlinear term are 36 W (the kernels move one field less through the x/z passes -- curl u is formed
+# while the inverse x-pass loads -- but the contract figure is SURVEY's).  Skew-symmetric (and the other non-rotational
+# forms, same pipeline): 91 W, transforms + nonlinear term 72 W.
+STAGE_W_ROT = {"inv_y_gemm": 3 + 5, "inv_x_pass": 5 + 7, "z_pass_nl": 7 + 3, "fwd_x_pass": 3 + 3, "fwd_y_gemm": 3 + 3, "tau_solve": 15 + 4}
+STAGE_W_SKEW = {"inv_y_gemm": 3 + 6, "inv_x_pass": 6 + 9, "z_pass_nl": 9 + 9, "fwd_x_pass": 9 + 9, "fwd_y_gemm": 9 + 3, "tau_solve": 15 + 4}
+TRANSFORM_STAGES = ("inv_y_gemm", "inv_x_pass", "z_pass_nl", "fwd_x_pass", "fwd_y_gemm")
+
+
+def stage_table(nonlinearity):
+    return STAGE_W_SKEW if nonlinearity in ("skew", "conv", "div", "alt") else STAGE_W_ROT
 
 
 def synthetic_field(w, seed=1, magn=0.1):
@@ -70,6 +79,19 @@ def synthetic_field(w, seed=1, magn=0.1):
     arr = u.view(np.float64)
     arr *= magn / max(np.sqrt(np.sum(np.abs(u) ** 2)), 1e-300)
     return arr
+
+
+def make_input(cf, lib, w):
+    """Initial field of the workload: the reference's `randomfield` rule (tools/randomfield.cpp:50-67: serial drand48
+    sequence, seed 1, Gaussian coefficients with spectral decay 0.6 over the whole retained box, divergence-free, no-slip,
+    rescaled to L2Norm 0.2) generated by this package's own FlowField::addPerturbations; falls back to the band-limited
+    synthetic field when the host library predates it."""
+    if hasattr(cf, "randomfield") and os.environ.get("CF_BENCH_INPUT", "randomfield") == "randomfield":
+        try:
+            return cf.randomfield(lib, w["Nx"], w["Ny"], w["Nz"], w["Lx"], w["Lz"], seed=1, magn=0.2, smooth=0.4).get()
+        except AttributeError:
+            pass
+    return synthetic_field(w)
 
 
 def flags_kw(w):
@@ -133,6 +155,63 @@ def sample_grid(w):
     return s
 
 
+def box_rows(arr, Nx, Nz, x0, x1):
+    """retained-box rows mxi in [x0, x1) (kx = 0..Kx, -Kx..-1) of a field array [Nd][Ny][Nx][2 Mz] as complex [Nd][Ny][rows][Kz+1]"""
+    Kx, Kz = Nx // 3 - 1, Nz // 3 - 1
+    c = arr.view(np.complex128)
+    rows = [(m if m <= Kx else m - (2 * Kx + 1)) % Nx for m in range(x0, x1)]
+    return c[:, :, rows, :Kz + 1]
+
+
+def small_case_parity(cf, lib, rank, world):
+    """The 48x49x32 plane-Couette case of tests/mp_slab_worker.py, 4 SBDF3 steps on all ranks, against the committed
+    fixture tests/golden/mp_slab_48x49x32.npz (computed by the compiled reference, tests/golden/make_mp_fixture.py):
+    once over the peer-memory exchange (stores over NVLink inside the kernels) and once over the staged NCCL
+    send/recv exchange (CFGPU_NO_PEER=1).  Relative L2 error of the all-gathered field, CFL, L2Norm."""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "mp_slab_48x49x32.npz"))
+    Nx, Ny, Nz = int(fx["Nx"]), int(fx["Ny"]), int(fx["Nz"])
+    Kx, Kz = Nx // 3 - 1, Nz // 3 - 1
+    from tests import parity as _p  # C1 flags (no oracle call below: parity.py only holds the case definition)
+    flags = dict(_p.C1["flags"])
+    Mz = Nz // 2 + 1
+    u0 = np.zeros((3, Ny, Nx, Mz), dtype=np.complex128)
+    rows = [(m if m <= Kx else m - (2 * Kx + 1)) % Nx for m in range(2 * Kx + 1)]
+    u0[:, :, rows, :Kz + 1] = fx["u0"]
+    out = {}
+    for leg in ("peer", "staged"):
+        if leg == "staged":
+            os.environ["CFGPU_NO_PEER"] = "1"
+        try:
+            ug = cf.FlowField(lib, Nx, Ny, Nz, 3, float(fx["Lx"]), float(fx["Lz"]), float(fx["a"]), float(fx["b"])).set(u0.view(np.float64), padded=True)
+            dns = cf.DNS(ug, cf.make_flags(**flags))
+            cfl0 = dns.cfl()
+            dns.advance(int(fx["nsteps"]))
+            u1, _ = dns.get()
+            norm = u1.l2norm()
+            cfl4 = dns.cfl()
+            u1.allgather()
+            u1.set_padded(False)  # full download: every rank holds the complete field after the gather
+            got = box_rows(u1.get(), Nx, Nz, 0, 2 * Kx + 1)
+            ref = fx["u4"]
+            out[leg] = {"rel_l2": float(np.linalg.norm((got - ref).ravel()) / np.linalg.norm(ref.ravel())),
+                        "cfl0_rel": abs(cfl0 - float(fx["cfl0"])) / float(fx["cfl0"]), "cfl_rel": abs(cfl4 - float(fx["cfl4"])) / float(fx["cfl4"]),
+                        "norm_rel": abs(norm - float(fx["norm4"])) / float(fx["norm4"])}
+            del dns, ug, u1
+        finally:
+            os.environ.pop("CFGPU_NO_PEER", None)
+    return out
+
+
+def state_signature(lib, dns, Nx, Ny, Nz, rank):
+    """L2Norm, CFL and a per-kx-row checksum (sum |u|^2 over components, y, kz) of the DNS state: this rank's rows."""
+    u, _ = dns.get()
+    norm, cfl = u.l2norm(), dns.cfl()
+    Kx = Nx // 3 - 1
+    x0, x1, _, _ = lib.comm_ranges(2 * Kx + 1, Ny, rank)
+    rows = box_rows(u.get(), Nx, Nz, x0, x1)  # a padded download only fetches this rank's rows
+    return norm, cfl, np.sum(np.abs(rows) ** 2, axis=(0, 1, 3)), (x0, x1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,16 +219,32 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="weak: Nx of the workload grid grows with the number of GPUs (per-GPU work fixed)")
+    ap.add_argument("--stepper", default=None, help="time stepping scheme (default: the workload's, sbdf3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity block (N > 1)")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "weak" and world > 1:
+        w["Nx"] *= world
+        w["Lx"] *= world
+        w["desc"] = "%dx%dx%d (weak scaling: Nx, Lx x %d)" % (w["Nx"], w["Ny"], w["Nz"], world)
+    if args.stepper:
+        w.setdefault("flags", {})
+        w["flags"] = dict(w["flags"], timestepping=args.stepper)
+    fkw = flags_kw(w)
+    STAGE_W = stage_table(fkw["nonlinearity"])
+    STEP_W = sum(STAGE_W.values())
+    TRANS_W = sum(STAGE_W[k] for k in TRANSFORM_STAGES)
     gp = w["Nx"] * w["Ny"] * w["Nz"]
     Wbytes = 8 * w["Nx"] * w["Ny"] * 2 * (w["Nz"] // 2 + 1)
-    nlname = {"rot": "rotational", "skew": "skew-symmetric"}.get(flags_kw(w)["nonlinearity"], flags_kw(w)["nonlinearity"])
-    config = {"workload": "%s: SBDF3, %s NL, 2/3 dealiasing, FP64, dt=%g" % (w["desc"], nlname, w["dt"]), "grid": [w["Nx"], w["Ny"], w["Nz"]],
+    nlname = {"rot": "rotational", "skew": "skew-symmetric"}.get(fkw["nonlinearity"], fkw["nonlinearity"])
+    config = {"workload": "%s: %s, %s NL, 2/3 dealiasing, FP64, dt=%g" % (w["desc"], fkw["timestepping"].upper(), nlname, w["dt"]),
+              "grid": [w["Nx"], w["Ny"], w["Nz"]],
               "l2": "working set (>= 34 W = %.1f MB) %s the 126 MB L2" % (34 * Wbytes / 1e6, "exceeds" if 34 * Wbytes > 126e6 else "fits in")}
 
     if args.impl == "reference":
@@ -159,10 +254,15 @@ def main():
         steps = max(1, min(args.steps, 3))
         ms = reference_steps(ws, steps, min(args.warmup, 1))
         val = ws["Nx"] * ws["Ny"] * ws["Nz"] / (ms * 1e-3)
-        sample = "reference DNS (unmodified sources, FFT shim instead of FFTW), %dx%dx%d grid, %d SBDF3 steps" % (ws["Nx"], ws["Ny"], ws["Nz"], steps)
+        sample = "reference DNS (unmodified sources, FFT shim instead of FFTW), %dx%dx%d sample grid (same Ny, Nx and Nz reduced), %d %s steps, 1 host core" % (
+            ws["Nx"], ws["Ny"], ws["Nz"], steps, fkw["timestepping"].upper())
+        config["workload"] += " -- reference arm timed on a bounded %dx%dx%d sample of it; ms_per_step is per SAMPLE step, " \
+                              "value (grid-pt-steps/s) is the size-independent unit" % (ws["Nx"], ws["Ny"], ws["Nz"])
+        config["sample_grid"] = [ws["Nx"], ws["Ny"], ws["Nz"]]
         print(json.dumps({"impl": "reference", "metric": "dns_grid_point_steps_per_s", "value": val, "unit": "grid-pt-steps/s",
-                          "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms * gp / (ws["Nx"] * ws["Ny"] * ws["Nz"]),
-                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+                          "ms_per_step_extrapolated_to_workload": ms * gp / (ws["Nx"] * ws["Ny"] * ws["Nz"]),
+                          "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": config, "steps_per_s_at_workload": val / gp,
                           "cpu_baseline": {"value": val, "unit": "grid-pt-steps/s", "cores": 1, "kind": "reference", "sample": sample},
                           "e2e": {"value": val, "unit": "grid-pt-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -174,9 +274,24 @@ def main():
     os.environ.setdefault("CFGPU_DEVICE", str(dev))
     lib = cf.HostLib()
     dist = None
+    u0 = make_input(cf, lib, w)
+
+    # ---- multi-GPU parity, part 1: the same steps on ONE GPU (every rank runs them on its own device before the
+    # communicator exists), to be compared with the N-rank result after the timed region
+    parity_block = None
+    nsteps_total = 2 + args.warmup + args.steps
+    sig1 = None
+    if world > 1 and not args.no_parity and args.scaling == "strong":
+        ug1 = cf.FlowField(lib, w["Nx"], w["Ny"], w["Nz"], 3, w["Lx"], w["Lz"]).set(u0, padded=True)
+        dns1 = cf.DNS(ug1, cf.make_flags(**fkw))
+        dns1.advance(nsteps_total)
+        n1, c1, rows1, _ = state_signature(lib, dns1, w["Nx"], w["Ny"], w["Nz"], 0)
+        sig1 = (n1, c1, rows1)
+        del dns1, ug1
+
     if world > 1:
         # one process per GPU: torch.distributed (NCCL) is the plumbing (id broadcast, barriers, max over ranks); the
-        # data path's all-to-all / all-reduce are issued by libcfgpu.so on its own NCCL communicator
+        # data path's exchange / all-reduce are issued by libcfgpu.so (peer-memory stores over NVLink, its own NCCL communicator)
         import torch.distributed as dist
         torch.cuda.set_device(dev)
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
@@ -185,7 +300,7 @@ def main():
             idt.copy_(torch.frombuffer(bytearray(lib.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         lib.comm_init_nccl(rank, world, bytes(idt.cpu().numpy().tobytes()))
-        config["parallelism"] = "kx-slab (spectral) / y-slab (physical) over %d GPUs, NCCL all-to-all" % world
+        config["parallelism"] = "kx-slab (spectral) / y-slab (physical) over %d GPUs, all-to-all fused into the kernels' stores over NVLink peer memory" % world
 
     def barrier():
         lib.sync()
@@ -199,9 +314,12 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
-    u0 = synthetic_field(w)
+
+    if world > 1 and not args.no_parity:
+        parity_block = {"small_case_48x49x32_vs_reference": small_case_parity(cf, lib, rank, world), "tolerance": 1e-12}
+
     ug = cf.FlowField(lib, w["Nx"], w["Ny"], w["Nz"], 3, w["Lx"], w["Lz"]).set(u0, padded=True)
-    dns = cf.DNS(ug, cf.make_flags(**flags_kw(w)))
+    dns = cf.DNS(ug, cf.make_flags(**fkw))
     dns.advance(2)            # SMRK2 initialisation steps of SBDF3 (not part of the metric)
     dns.advance(args.warmup)
     barrier()
@@ -222,6 +340,23 @@ def main():
     ms = ms_total / args.steps
     value = gp / (ms * 1e-3)
 
+    # ---- multi-GPU parity, part 2: the N-rank state after the timed steps against the 1-rank run of the same steps
+    if parity_block is not None and sig1 is not None:
+        nN, cN, rowsN, (x0, x1) = state_signature(lib, dns, w["Nx"], w["Ny"], w["Nz"], rank)
+        ref_rows = sig1[2][x0:x1]
+        err_rows = float(np.max(np.abs(rowsN - ref_rows) / np.maximum(np.abs(ref_rows), 1e-300 + 1e-13 * np.max(sig1[2]))))
+        err_rows = max_over_ranks(err_rows)
+        parity_block["c4_state_vs_1rank_same_steps"] = {
+            "steps": nsteps_total, "l2norm_rel": abs(nN - sig1[0]) / sig1[0], "cfl_rel": abs(cN - sig1[1]) / abs(sig1[1]),
+            "kx_row_checksum_max_rel": err_rows, "kx_rows_checked": int(len(sig1[2]))}
+    if parity_block is not None:
+        sm = parity_block["small_case_48x49x32_vs_reference"]
+        ok = all(v < 1e-12 for leg in sm.values() for v in leg.values())
+        big = parity_block.get("c4_state_vs_1rank_same_steps")
+        if big:
+            ok = ok and big["l2norm_rel"] < 1e-11 and big["cfl_rel"] < 1e-11 and big["kx_row_checksum_max_rel"] < 1e-9
+        parity_block["ok"] = bool(ok)
+
     # ---- end to end through the host API with host buffers
     e2e = None
     if not args.no_e2e:
@@ -234,10 +369,9 @@ def main():
         ke = max(2, min(args.steps, 5))
         import ctypes as C
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
-        n_box = n  # bytes that actually cross PCIe: de-aliased spectral fields travel as their retained box (own kx rows)
         Kx_, Kz_ = w["Nx"] // 3 - 1, w["Nz"] // 3 - 1
         x0_, x1_, _, _ = lib.comm_ranges(2 * Kx_ + 1, w["Ny"], rank)
-        n_box = 3 * w["Ny"] * (x1_ - x0_) * (Kz_ + 1) * 2
+        n_box = 3 * w["Ny"] * (x1_ - x0_) * (Kz_ + 1) * 2  # what crosses PCIe: the retained box of this rank's kx rows
         barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
@@ -254,7 +388,7 @@ def main():
                "note": "per rank; the host FlowField arrays are full size, only the retained (de-aliased) modes of the rank's kx rows cross PCIe"}
     clocks = sampler.result()
 
-    # ---- roofline of the dominant stage
+    # ---- roofline
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -271,57 +405,61 @@ def main():
     # y-GEMM stages are FP64 tensor-pipe (DMMA) work: flops of the even/odd-split contractions the kernels perform
     Kx_, Kz_ = w["Nx"] // 3 - 1, w["Nz"] // 3 - 1
     ncols = 2 * (2 * Kx_ + 1) * (Kz_ + 1) / world            # real columns of this rank
-    gemm_flops = {"inv_y_gemm": 5, "fwd_y_gemm": 3}          # matrices applied: u,v,w + du/dy,dw/dy ; f_x,f_y,f_z
+    rot = STAGE_W is STAGE_W_ROT
+    gemm_flops = {"inv_y_gemm": 5 if rot else 6, "fwd_y_gemm": 3 if rot else 6}   # matrices applied per step
     for k_, nm in gemm_flops.items():
         if k_ in stages:
             fl = nm * 2.0 * w["Ny"] * ((w["Ny"] + 1) // 2) * ncols
             stages[k_]["TFLOPs"] = fl / (stages[k_]["ms_per_step"] * 1e-3) / 1e12
-    dom = max((k for k in stages if k in STAGE_W), key=lambda k: stages[k]["ms_per_step"])
-    traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if world == 1:
-            traffic = tr.get(args.workload, {}).get(dom)
-    except Exception:
-        pass
-    if dom in gemm_flops:
-        # FP64 tensor work: MEASURED_PEAKS.json has no FP64 figure, so the yard-stick is cuBLAS DGEMM measured here
-        def dgemm_peak(n=8192, reps=5):
-            a = torch.randn(n, n, dtype=torch.float64, device="cuda")
-            b = torch.randn(n, n, dtype=torch.float64, device="cuda")
-            for _ in range(2):
-                c = a @ b
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                c = a @ b  # noqa: F841
-            e1.record()
-            torch.cuda.synchronize()
-            return 2.0 * n ** 3 / (e0.elapsed_time(e1) / reps * 1e-3) / 1e12
-        try:
-            f64_peak = dgemm_peak()
-            src = "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 tensor figure)"
-        except Exception:
-            f64_peak, src = 40.0, "fallback: nominal B200 FP64 tensor rate"
-        ach = stages[dom]["TFLOPs"]
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s", "frac": ach / f64_peak,
-                    "traffic": traffic, "peak_source": src, "precision": "fp64 (DMMA m16n8k8)"}
-    else:
-        ach = stages[dom]["algorithmic_GBps"]
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}
-    if traffic:  # what the kernel really moved (ncu), next to the algorithmic figure: SURVEY's byte counts charge full
-        # padded arrays although only the retained 44 % of the modes are touched, and leave the solver's factors out
-        roofline["dram_GBps"] = traffic / (stages[dom]["ms_per_step"] * 1e-3) / 1e9
-        roofline["dram_frac"] = roofline["dram_GBps"] / hbm_peak
-    roofline["hbm_peak_GBps"] = hbm_peak
+    # The roofline object describes the quantity the target is stated on: transforms + nonlinear term (36 W of
+    # the 61 W rotational step) against the HBM roofline; `kernel` names the slowest of those stages.  Every stage's own
+    # figure is in `stages`.
+    tstages = [k for k in TRANSFORM_STAGES if k in stages]
+    t_trans = sum(stages[k]["ms_per_step"] for k in tstages)
+    dom = max(tstages, key=lambda k: stages[k]["ms_per_step"])
+    trans_GBps = TRANS_W * Wbytes / world / (t_trans * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "transforms+nonlinear term (%s); slowest stage: %s" % ("+".join(tstages), dom),
+                "achieved": trans_GBps, "peak": hbm_peak, "unit": "GB/s", "frac": trans_GBps / hbm_peak,
+                "traffic": None,  # dram bytes come from ncu captures (profiles/r02_*), never from a run under the profiler
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "algorithmic_bytes": "SURVEY.md 8(d): %d W of the %d W step, W = 8*Nx*Ny*2(Nz/2+1) = %.1f MB%s" % (
+                    TRANS_W, STEP_W, Wbytes / 1e6, ", this rank's 1/%d share" % world if world > 1 else ""),
+                "transforms_nl_ms": t_trans, "transforms_nl_frac": trans_GBps / hbm_peak,
+                "slowest_stage": dom, "slowest_stage_GBps": stages[dom].get("algorithmic_GBps"),
+                "hbm_peak_GBps": hbm_peak}
     roofline["whole_step_algorithmic_GBps_per_gpu"] = STEP_W * Wbytes / world / (ms * 1e-3) / 1e9
     roofline["whole_step_frac"] = roofline["whole_step_algorithmic_GBps_per_gpu"] / hbm_peak
     for k_ in stages:  # every stage against its own bound, so the next kernel to work on can be read off the line
         if k_ in STAGE_W and k_ not in gemm_flops:
             stages[k_]["frac_of_hbm_peak"] = stages[k_]["algorithmic_GBps"] / hbm_peak
+    if world == 1 and not args.no_cpu_baseline:
+        # FP64 tensor yard-stick for the y-GEMM stages: cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no FP64 figure)
+        try:
+            n_ = 8192
+            a_ = torch.randn(n_, n_, dtype=torch.float64, device="cuda")
+            b_ = torch.randn(n_, n_, dtype=torch.float64, device="cuda")
+            for _ in range(2):
+                c_ = a_ @ b_
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                c_ = a_ @ b_  # noqa: F841
+            e1.record()
+            torch.cuda.synchronize()
+            f64_peak = 2.0 * n_ ** 3 / (e0.elapsed_time(e1) / 3 * 1e-3) / 1e12
+            roofline["fp64_tensor_yardstick_TFLOPs"] = f64_peak
+            for k_ in gemm_flops:
+                if k_ in stages:
+                    stages[k_]["frac_of_cublas_dgemm"] = stages[k_]["TFLOPs"] / f64_peak
+            del a_, b_, c_
+        except Exception:
+            pass
 
+    if parity_block is not None and not parity_block["ok"]:
+        if rank == 0:
+            print(json.dumps({"metric": "dns_grid_point_steps_per_s", "error": "multi-GPU parity failed", "multi_gpu_parity": parity_block}))
+        sys.exit(3)
     if rank != 0:
         return
     cpu_baseline = None
@@ -330,12 +468,16 @@ def main():
         cms = reference_steps(ws, 2, 0)
         cval = ws["Nx"] * ws["Ny"] * ws["Nz"] / (cms * 1e-3)
         cpu_baseline = {"value": cval, "unit": "grid-pt-steps/s", "cores": 1, "kind": "reference",
-                        "sample": "reference DNS (unmodified sources + FFT shim), %dx%dx%d grid, 2 SBDF3 steps after 2 init steps" % (ws["Nx"], ws["Ny"], ws["Nz"])}
+                        "sample": "reference DNS (unmodified sources + FFT shim), %dx%dx%d grid, 2 %s steps after 2 init steps" % (
+                            ws["Nx"], ws["Ny"], ws["Nz"], fkw["timestepping"].upper())}
 
-    print(json.dumps({"metric": "dns_grid_point_steps_per_s", "value": value, "unit": "grid-pt-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "higher_is_better": True, "scaling": "strong",
-                      "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-                      "gpu_launches": launches, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline}))
+    line = {"metric": "dns_grid_point_steps_per_s", "value": value, "unit": "grid-pt-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline}
+    if parity_block is not None:
+        line["multi_gpu_parity"] = parity_block
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -16,11 +16,18 @@ static const long double PIl = 3.141592653589793238462643383279502884L;
 
 int ws_reserve(Workspace& w, size_t bytes) {
     if (bytes <= w.bytes) return 0;
+    if (w.exported) {
+        // other ranks hold CUDA-IPC mappings of this buffer: it may only be replaced through ensure_peers (cfgpu_nse.cu),
+        // which closes the mappings collectively first
+        set_last_error("internal: a peer-mapped workspace must be resized collectively");
+        return 1;
+    }
     if (w.ptr) CF_CUDA(cudaFree(w.ptr));
     w.ptr = nullptr;
     w.bytes = 0;
     CF_CUDA(cudaMalloc((void**)&w.ptr, bytes));
     w.bytes = bytes;
+    ++w.gen;  // every (re)allocation gets a new generation: cached peer mappings / row tables are keyed on it, not on the address
     return 0;
 }
 
@@ -320,8 +327,9 @@ int cfgpu_finalize(cfgpu_ctx ctx) {
     if (ctx->ws_P.ptr) cudaFree(ctx->ws_P.ptr);
     if (ctx->ws_Q.ptr) cudaFree(ctx->ws_Q.ptr);
     if (ctx->ws_red.ptr) cudaFree(ctx->ws_red.ptr);
-    if (ctx->peerP_base) comm_close_peers(ctx->comm, ctx->peerP);
-    if (ctx->peerS_base) comm_close_peers(ctx->comm, ctx->peerS);
+    if (ctx->ws_G.ptr) cudaFree(ctx->ws_G.ptr);
+    if (ctx->peerP_gen) comm_close_peers(ctx->comm, ctx->peerP);
+    if (ctx->peerS_gen) comm_close_peers(ctx->comm, ctx->peerS);
     if (ctx->ws_S.ptr) cudaFree(ctx->ws_S.ptr);
     comm_destroy(ctx->comm);
     cudaEventDestroy(ctx->ev0);
@@ -434,6 +442,25 @@ int cfgpu_comm_ranges(cfgpu_ctx ctx, int nmx, int Ny, int rank, int* x0, int* x1
 
 namespace cfgpu {
 // ------------------------------------------------------------------------------------------------ field layouts
+// The serial buffer is allocated on first use: hot-path fields of a multi-GPU run live in their tile-major buffer only
+// (this rank's modes), so a rank's footprint scales with 1/nranks.  A field without a serial buffer is all zero outside
+// whatever its tile buffer holds.
+int field_ser_alloc(cfgpu_field f) {
+    if (f->dser) return 0;
+    if (cudaMalloc((void**)&f->dser, f->n * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("field: cudaMalloc of the serial buffer failed");
+        return 1;
+    }
+    CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), f->ctx->stream));
+    f->clean_Kx = 0; f->clean_Kz = 0;  // all zero
+    return 0;
+}
+int field_serial_output(cfgpu_field f) {
+    CF_TRY(field_ser_alloc(f));
+    f->layout = 0;
+    return 0;
+}
 static int tile_alloc(cfgpu_field f, const TileGeom& g) {
     const long long need = g.ntiles() * (long long)f->Ny * g.TM * 2 * f->Nd;
     if (!f->dtile || f->ntile < need) {
@@ -453,6 +480,7 @@ static bool layout_trace() {
     return on;                                                      // occur inside the time-stepping loop)
 }
 int field_serial(cfgpu_field f) {
+    CF_TRY(field_ser_alloc(f));
     if (f->layout == 0) return 0;
     if (layout_trace()) fprintf(stderr, "[cfgpu] field %p: tile-major -> serial\n", (void*)f);
     const TileGeom& g = f->tg;
@@ -467,6 +495,13 @@ int field_serial(cfgpu_field f) {
 }
 int field_tile(cfgpu_field f, const TileGeom& g) {
     if (f->layout == 1 && f->tg.same(g)) return 0;
+    if (f->layout == 0 && !f->dser) {  // never written: all zero in any layout
+        CF_TRY(tile_alloc(f, g));
+        CF_CUDA(cudaMemsetAsync(f->dtile, 0, f->ntile * sizeof(double), f->ctx->stream));
+        f->layout = 1;
+        f->tile_outside_zero = true;
+        return 0;
+    }
     CF_TRY(field_serial(f));
     CF_TRY(tile_alloc(f, g));
     if (layout_trace()) fprintf(stderr, "[cfgpu] field %p: serial -> tile-major\n", (void*)f);
@@ -483,7 +518,7 @@ int field_tile_output(cfgpu_field f, const TileGeom& g, bool outside_zero) {
         f->tile_outside_zero = false;
     }
     f->layout = 1;
-    if (outside_zero) f->tile_outside_zero = true;
+    if (outside_zero || !f->dser) f->tile_outside_zero = true;  // no serial buffer: nothing but zeros outside the box
     return 0;
 }
 }  // namespace cfgpu
@@ -495,10 +530,12 @@ int cfgpu_field_allgather(cfgpu_field f) {
     Comm& cm = ctx->comm;
     if (cm.nranks == 1) return 0;
     CF_ARG(f->xzstate == CFGPU_SPECTRAL, "cfgpu_field_allgather: field must be xz-spectral");
+    CF_ARG(f->padded, "cfgpu_field_allgather: the kx-slab partition is defined on the de-aliased box; the field must be padded");
     const int Kx = f->Nx / 3 - 1, Kz = f->Nz / 3 - 1, nmx = 2 * Kx + 1, nkz = Kz + 1;
     const size_t rows = (size_t)f->Nd * f->Ny;
-    CF_TRY(ws_reserve(ctx->ws_S, rows * nmx * nkz * 2 * sizeof(double)));
-    double2* S = reinterpret_cast<double2*>(ctx->ws_S.ptr);
+    // a workspace of its own: ws_S may be mapped by the other ranks (peer-memory all-to-all) and must not be replaced here
+    CF_TRY(ws_reserve(ctx->ws_G, rows * nmx * nkz * 2 * sizeof(double)));
+    double2* S = reinterpret_cast<double2*>(ctx->ws_G.ptr);
     int x0, x1;
     part_range(nmx, cm.nranks, cm.rank, x0, x1);
     CF_TRY(rows_pack_launch(f->dser, reinterpret_cast<double*>(S + rows * nkz * x0), f->Nx, f->Nz, (int)rows, Kx, Kz, x0, x1, 0, ctx->stream));
@@ -529,20 +566,14 @@ int cfgpu_field_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, int Nd, double Lx,
     f->Nx = Nx; f->Ny = Ny; f->Nz = Nz; f->Nd = Nd;
     f->Lx = Lx; f->Lz = Lz; f->a = a; f->b = b;
     f->n = (long long)Nx * Ny * f->Nzpad() * Nd;
-    if (cudaMalloc((void**)&f->dser, f->n * sizeof(double)) != cudaSuccess) {
-        delete f;
-        set_last_error("cfgpu_field_create: cudaMalloc failed");
-        return 1;
-    }
-    CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), ctx->stream));
-    f->clean_Kx = 0; f->clean_Kz = 0;  // all zero
+    f->clean_Kx = 0; f->clean_Kz = 0;  // all zero; the serial buffer is allocated on first use (field_ser_alloc)
     *out = f;
     return 0;
 }
 int cfgpu_field_destroy(cfgpu_field f) {
     if (!f) return 0;
     cudaStreamSynchronize(f->ctx->stream);
-    cudaFree(f->dser);
+    if (f->dser) cudaFree(f->dser);
     if (f->dtile) cudaFree(f->dtile);
     delete f;
     return 0;
@@ -557,7 +588,7 @@ int cfgpu_host_free(void* p) {
     return 0;
 }
 int cfgpu_field_upload(cfgpu_field f, const double* h, int xz, int y) {
-    f->layout = 0;  // everything is overwritten
+    CF_TRY(field_serial_output(f));  // everything is overwritten
     CF_CUDA(cudaMemcpyAsync(f->dser, h, f->n * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
     CF_CUDA(cudaStreamSynchronize(f->ctx->stream));
     f->xzstate = xz; f->ystate = y;
@@ -599,7 +630,7 @@ static int box_copy(cfgpu_field f, double* h, bool to_device) {
     return 0;
 }
 int cfgpu_field_upload_padded(cfgpu_field f, const double* h, int ystate) {
-    f->layout = 0;  // the box is overwritten, everything else zeroed (below, unless the serial buffer is known clean)
+    CF_TRY(field_serial_output(f));  // the box is overwritten, everything else zeroed (below, unless the serial buffer is known clean)
     const int Kx = f->Nx / 3 - 1, Kz = f->Nz / 3 - 1;
     CF_ARG(Kx >= 0 && Kz >= 0, "cfgpu_field_upload_padded: grid too small");
     if (!(f->clean_Kx >= 0 && f->clean_Kx <= Kx && f->clean_Kz >= 0 && f->clean_Kz <= Kz))
@@ -633,11 +664,14 @@ int cfgpu_field_copy(cfgpu_field dst, cfgpu_field src) {
                                 cudaMemcpyDeviceToDevice, dst->ctx->stream));
         dst->tile_outside_zero = zero_out;
         if (!zero_out) {
+            CF_TRY(field_ser_alloc(dst));
             CF_CUDA(cudaMemcpyAsync(dst->dser, src->dser, src->n * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
             dst->clean_Kx = src->clean_Kx; dst->clean_Kz = src->clean_Kz;
         }
+    } else if (!src->dser) {  // never written: all zero
+        CF_TRY(cfgpu_field_zero(dst));
     } else {
-        dst->layout = 0;
+        CF_TRY(field_serial_output(dst));
         CF_CUDA(cudaMemcpyAsync(dst->dser, src->dser, src->n * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
         dst->clean_Kx = src->clean_Kx; dst->clean_Kz = src->clean_Kz;
     }
@@ -656,7 +690,7 @@ int cfgpu_field_swap(cfgpu_field a, cfgpu_field b) {
 }
 int cfgpu_field_zero(cfgpu_field f) {
     f->layout = 0;
-    CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), f->ctx->stream));
+    if (f->dser) CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), f->ctx->stream));
     f->clean_Kx = 0; f->clean_Kz = 0;
     return 0;
 }

@@ -53,6 +53,8 @@ struct TileGeom {
 struct Workspace {
     size_t bytes = 0;
     double* ptr = nullptr;
+    unsigned long long gen = 0;  // bumped on every (re)allocation
+    bool exported = false;       // mapped by other ranks through CUDA IPC: resized only collectively (ensure_peers)
 };
 
 }  // namespace cfgpu
@@ -66,12 +68,12 @@ struct cfgpu_ctx_s {
     std::map<std::tuple<int, double, double>, cfgpu::YPlan> yplans;
     std::map<int, cfgpu::FftPlanHost> fftplans;
     std::map<std::tuple<int, int, int, int>, cfgpu::ModeBox> boxes;
-    cfgpu::Workspace ws_P, ws_Q, ws_S, ws_red;
+    cfgpu::Workspace ws_P, ws_Q, ws_S, ws_red, ws_G;  // ws_G: cfgpu_field_allgather staging
     cfgpu::Comm comm;  // rank / world size / collectives (single rank by default)
     // peer mappings of the other ranks' ws_P / ws_S (CUDA IPC), valid for the local base pointers recorded beside them
     void* peerP[cfgpu::COMM_MAXRANKS] = {nullptr};
     void* peerS[cfgpu::COMM_MAXRANKS] = {nullptr};
-    void *peerP_base = nullptr, *peerS_base = nullptr;
+    unsigned long long peerP_gen = 0, peerS_gen = 0;  // generation of ws_P / ws_S the mappings belong to (0: none)
     std::vector<void*> graphs;  // cudaGraphExec_t
     bool capturing = false;
     // stage profiler
@@ -89,7 +91,8 @@ struct cfgpu_field_s {
     int xzstate = CFGPU_SPECTRAL, ystate = CFGPU_SPECTRAL;
     int padded = 0;
     int clean_Kx = -1, clean_Kz = -1;  // all modes outside this box are known to be exactly zero (-1: unknown)
-    // The data lives in one of two buffers.  `dser` is the reference's serial layout [i][my][mx][mz] (always allocated);
+    // The data lives in one of two buffers.  `dser` is the reference's serial layout [i][my][mx][mz] (allocated on first use: a field
+    // without it is zero wherever its tile buffer does not say otherwise);
     // `dtile` (lazily allocated) is the tile-major layout of the retained box, produced and consumed by the DNS hot path
     // (cfgpu_nse_solve / cfgpu_nse_nonlinear / cfgpu_nse_linear).  layout says which one is current for the retained box; outside the box
     // the field is zero if tile_outside_zero, else whatever dser holds there.  Everything but the hot path goes through
@@ -129,12 +132,15 @@ struct cfgpu_nse_s {
     cfgpu::TileGeom tg;
     long* d_tilestart = nullptr; // device [ntiles]: offset of tile t of a 3-component tile-major field
     double** d_rows[2] = {nullptr, nullptr};  // peer row tables of the inverse y-GEMM outputs (5- and 3-field staging)
-    void* rows_baseS = nullptr;
+    unsigned long long rows_genS = 0;  // generation of ws_S the row tables were built for
+    int rows_nranks = 0;
     cfgpu_field s_u = nullptr, s_t = nullptr;  // scratch fields of the non-rotational nonlinear terms (3 and 9 components)
 };
 
 namespace cfgpu {
 int field_serial(cfgpu_field f);                                           // make dser current (tile -> serial if needed)
+int field_ser_alloc(cfgpu_field f);                                        // allocate the (zero-filled) serial buffer if absent
+int field_serial_output(cfgpu_field f);                                    // dser becomes current, contents to be written
 int field_tile(cfgpu_field f, const TileGeom& g);                          // make dtile current (serial -> tile if needed)
 int field_tile_output(cfgpu_field f, const TileGeom& g, bool outside_zero);  // dtile becomes current, contents to be written
 int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out);

@@ -19,6 +19,11 @@ using namespace cfgpu;
         }                        \
     } while (0)
 
+// every field handed to an NSE entry point must have the operator's grid: the kernels index with the operator's strides
+static bool shape_ok(const cfgpu_nse nse, const cfgpu_field f, int Nd) {
+    return f && f->Nx == nse->Nx && f->Ny == nse->Ny && f->Nz == nse->Nz && f->Nd == Nd;
+}
+
 namespace cfgpu {
 int linear_launch(const TauSolveParams& p, const double* u, const double* q, double* L, cudaStream_t stream);
 }
@@ -79,29 +84,48 @@ static int slab_exchange(cfgpu_nse nse, int nf, int dir, const int* fields, int 
 
 // Peer-memory path (NCCL backend): map every rank's pencil (P) and staging (S) buffers, and build the tables that send
 // each output row of the inverse y-GEMM to the rank owning that y plane.
+// A peer-mapped buffer is only ever replaced collectively: every rank has finished with the old one (barrier), all
+// mappings of it are closed (second barrier), then it is freed, re-allocated and mapped again.  The decision is the same
+// on every rank because the sizes depend on the geometry only.
+static int peer_workspace(cfgpu_ctx ctx, Workspace& w, size_t bytes, void** peers, unsigned long long& mapped_gen) {
+    Comm& cm = ctx->comm;
+    if (bytes > w.bytes) {
+        if (mapped_gen) {
+            CF_TRY(comm_barrier(cm, ctx->stream));
+            CF_CUDA(cudaStreamSynchronize(ctx->stream));
+            CF_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+            CF_TRY(comm_close_peers(cm, peers));
+            mapped_gen = 0;
+            CF_TRY(comm_barrier(cm, ctx->stream));
+            CF_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        w.exported = false;
+        CF_TRY(ws_reserve(w, bytes));
+    }
+    if (mapped_gen != w.gen) {
+        if (mapped_gen) CF_TRY(comm_close_peers(cm, peers));
+        mapped_gen = 0;
+        CF_TRY(comm_open_peers(cm, w.ptr, peers, ctx->stream));
+        if (cm.peer_failed) return 0;
+        mapped_gen = w.gen;
+        w.exported = true;
+    }
+    return 0;
+}
 static int ensure_peers(cfgpu_nse nse, size_t Pbytes, size_t Sbytes) {
     cfgpu_ctx ctx = nse->ctx;
     Comm& cm = ctx->comm;
-    CF_TRY(ws_reserve(ctx->ws_P, Pbytes));
-    CF_TRY(ws_reserve(ctx->ws_S, Sbytes));
-    if (ctx->peerP_base != ctx->ws_P.ptr) {  // (re)allocated: same decision on every rank (sizes depend on the geometry only)
-        if (ctx->peerP_base) CF_TRY(comm_close_peers(cm, ctx->peerP));
-        CF_TRY(comm_open_peers(cm, ctx->ws_P.ptr, ctx->peerP, ctx->stream));
-        if (cm.peer_failed) return 0;
-        ctx->peerP_base = ctx->ws_P.ptr;
+    CF_TRY(peer_workspace(ctx, ctx->ws_P, Pbytes, ctx->peerP, ctx->peerP_gen));
+    if (cm.peer_failed) return 0;
+    CF_TRY(peer_workspace(ctx, ctx->ws_S, Sbytes, ctx->peerS, ctx->peerS_gen));
+    if (cm.peer_failed) {
+        comm_close_peers(cm, ctx->peerP);
+        ctx->peerP_gen = 0;
+        ctx->ws_P.exported = false;
+        return 0;
     }
-    if (ctx->peerS_base != ctx->ws_S.ptr) {
-        if (ctx->peerS_base) CF_TRY(comm_close_peers(cm, ctx->peerS));
-        CF_TRY(comm_open_peers(cm, ctx->ws_S.ptr, ctx->peerS, ctx->stream));
-        if (cm.peer_failed) {
-            comm_close_peers(cm, ctx->peerP);
-            ctx->peerP_base = nullptr;
-            return 0;
-        }
-        ctx->peerS_base = ctx->ws_S.ptr;
-    }
-    if (nse->rows_baseS != ctx->ws_S.ptr) {
-        const int nmx = 2 * nse->Kx + 1, nkz = nse->Kz + 1, nxl = nse->x1 - nse->x0;
+    if (nse->rows_genS != ctx->ws_S.gen || nse->rows_nranks != cm.nranks) {
+        const int nkz = nse->Kz + 1, nxl = nse->x1 - nse->x0;
         for (int v = 0; v < 2; ++v) {
             const int nf = v == 0 ? 5 : 3;
             std::vector<double*> tab((size_t)nf * nse->Ny);
@@ -114,12 +138,12 @@ static int ensure_peers(cfgpu_nse nse, size_t Pbytes, size_t Sbytes) {
                     for (int y = ya; y < yb; ++y)
                         tab[(size_t)f * nse->Ny + y] = Sr + 2 * (size_t)nkz * ((size_t)nf * nyl * nse->x0 + ((size_t)f * nyl + (y - ya)) * nxl);
             }
-            (void)nmx;
             if (!nse->d_rows[v]) CF_CUDA(cudaMalloc((void**)&nse->d_rows[v], tab.size() * sizeof(double*)));
             CF_CUDA(cudaMemcpyAsync(nse->d_rows[v], tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
             CF_CUDA(cudaStreamSynchronize(ctx->stream));
         }
-        nse->rows_baseS = ctx->ws_S.ptr;
+        nse->rows_genS = ctx->ws_S.gen;
+        nse->rows_nranks = cm.nranks;
     }
     return 0;
 }
@@ -147,12 +171,13 @@ static SpecAddr spec_addr(cfgpu_nse nse, cfgpu_field f, const ModeBox* bx) {
 // input of the hot path: tile-major data of another geometry goes back to the serial layout first
 static int spec_input(cfgpu_nse nse, cfgpu_field u) {
     if (u->layout == 1 && !u->tg.same(nse->tg)) return field_serial(u);
+    if (u->layout == 0) return field_ser_alloc(u);
     return 0;
 }
 // output of the hot path (all retained modes are written, everything else is zero): tile-major when enabled
 static int spec_output(cfgpu_nse nse, cfgpu_field f) {
     if (nse->use_tile) return field_tile_output(f, nse->tg, true);
-    f->layout = 0;
+    CF_TRY(field_serial_output(f));
     if (!(f->clean_Kx >= 0 && f->clean_Kx <= nse->Kx && f->clean_Kz >= 0 && f->clean_Kz <= nse->Kz))
         CF_CUDA(cudaMemsetAsync(f->dser, 0, f->n * sizeof(double), nse->ctx->stream));
     return 0;
@@ -313,7 +338,11 @@ int cfgpu_nse_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, double Lx, double Lz
     nse->Nyd = cfg->dealias_y ? 2 * (Ny - 1) / 3 + 1 : Ny;              // nse.cpp:228
     nse->Kx = cfg->dealias_xz ? Nx / 3 - 1 : Nx / 2 - 1;                // nse.cpp:229-230, 498 (kxmax mode is skipped)
     nse->Kz = cfg->dealias_xz ? Nz / 3 - 1 : Nz / 2 - 1;
-    if (Nx % 2 == 1 && !cfg->dealias_xz) nse->Kx = Nx / 2 - 1;
+    // (odd Nx without de-aliasing: the reference skips kx == kxmax only and still advances kx = -(Nx-1)/2; here both rows
+    // lie outside the symmetric box and are left untouched -- documented difference)
+    CF_ARG(ctx->comm.nranks == 1 || cfg->dealias_xz,
+           "cfgpu_nse_create: multi-GPU runs need 2/3 de-aliasing in x,z (the kx-slab partition, the gathers and the padded "
+           "transfers are defined on the de-aliased box)");
     CF_ARG(nse->Kx >= 0 && nse->Kz >= 0, "cfgpu_nse_create: grid too small");
     CF_ARG(nse->Nyd % 2 == 1, "cfgpu_nse_create: dealiased Ny must be odd");
     part_range(2 * nse->Kx + 1, ctx->comm.nranks, ctx->comm.rank, nse->x0, nse->x1);
@@ -564,12 +593,13 @@ static int nonlinear_generic(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         }
     }
     CF_TRY(field_serial(u));
-    f->layout = 0;  // written in the serial layout below
+    CF_TRY(field_serial_output(f));  // written in the serial layout below
     if (!nse->s_u) CF_TRY(cfgpu_field_create(ctx, nse->Nx, nse->Ny, nse->Nz, 3, nse->Lx, nse->Lz, nse->a, nse->b, &nse->s_u));
     cfgpu_field su = nse->s_u;
     FieldGeom g{nse->Nx, nse->Ny, nse->Nz, nse->Lx, nse->Lz, nse->a, nse->b};
     const long nreal = (long)su->compstride();
     CF_TRY(cfgpu_field_copy(su, u));
+    CF_TRY(field_ser_alloc(su));
     int method = nse->cfg.nonlinearity;
     if (method == 6) {  // LinearAboutProfile (diffops.cpp:3288-3365)
         CF_TRY(cfgpu_field_make_physical_y(su));
@@ -581,6 +611,7 @@ static int nonlinear_generic(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         else if (method == 5) { method = 1; nse->cfg.nonlinearity = 4; }  // Alternating_
         if (!nse->s_t) CF_TRY(cfgpu_field_create(ctx, nse->Nx, nse->Ny, nse->Nz, 9, nse->Lx, nse->Lz, nse->a, nse->b, &nse->s_t));
         cfgpu_field st = nse->s_t;
+        CF_TRY(field_serial_output(st));
         const double rot = nse->cfg.rotation;
         // u_tot = u + Ubase e_x + Wbase e_z - Vsuck e_y on the (0,0) mode (nse.cpp:28-36)
         CF_TRY(add_base00_launch(su->dser, nse->has_Ubaseyy ? nse->d_base + 7 * nse->Ny : nullptr,
@@ -622,7 +653,7 @@ static int nonlinear_generic(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
 }
 
 int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
-    CF_ARG(u->Nd == 3 && f->Nd == 3, "cfgpu_nse_nonlinear: fields must have 3 components");
+    CF_ARG(nse && shape_ok(nse, u, 3) && shape_ok(nse, f, 3), "cfgpu_nse_nonlinear: u and f must be 3-component fields on the operator's grid");
     CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "cfgpu_nse_nonlinear: u must be spectral");
     if (nse->cfg.nonlinearity != 0) return nonlinear_generic(nse, u, f);
     cfgpu_ctx ctx = nse->ctx;
@@ -735,13 +766,12 @@ static int fill_tau_params(cfgpu_nse nse, int s, TauSolveParams& tp) {
 int cfgpu_nse_solve(cfgpu_nse nse, int s, int nterms, const double* coef_h, const cfgpu_field* terms, cfgpu_field uout,
                     cfgpu_field qout) {
     CF_ARG(nterms >= 1 && nterms <= TAU_MAXTERMS, "cfgpu_nse_solve: 1..10 terms");
-    CF_ARG(uout->Nd == 3 && qout->Nd == 1, "cfgpu_nse_solve: uout must have 3 components, qout 1");
+    CF_ARG(nse && shape_ok(nse, uout, 3) && shape_ok(nse, qout, 1), "cfgpu_nse_solve: uout (3 components) and qout (1) must be on the operator's grid");
     TauSolveParams tp;
     CF_TRY(fill_tau_params(nse, s, tp));
     tp.nterms = nterms;
     for (int j = 0; j < nterms; ++j) {
-        CF_ARG(terms[j]->Nd == 3 && terms[j]->Nx == nse->Nx && terms[j]->Ny == nse->Ny && terms[j]->Nz == nse->Nz,
-               "cfgpu_nse_solve: term shape mismatch");
+        CF_ARG(shape_ok(nse, terms[j], 3), "cfgpu_nse_solve: term shape mismatch");
         if (nse->use_tile) CF_TRY(field_tile(terms[j], nse->tg));
         else CF_TRY(field_serial(terms[j]));
         tp.term[j] = nse->use_tile ? terms[j]->dtile : terms[j]->dser;
@@ -768,7 +798,7 @@ int cfgpu_nse_solve(cfgpu_nse nse, int s, int nterms, const double* coef_h, cons
 }
 
 int cfgpu_nse_linear(cfgpu_nse nse, cfgpu_field u, cfgpu_field q, cfgpu_field L) {
-    CF_ARG(u->Nd == 3 && q->Nd == 1 && L->Nd == 3, "cfgpu_nse_linear: shapes");
+    CF_ARG(nse && shape_ok(nse, u, 3) && shape_ok(nse, q, 1) && shape_ok(nse, L, 3), "cfgpu_nse_linear: u, L (3 components) and q (1) must be on the operator's grid");
     CF_ARG(!nse->tau.empty(), "cfgpu_nse_linear: call reset_lambda first");
     TauSolveParams tp;
     CF_TRY(fill_tau_params(nse, 0, tp));
@@ -788,7 +818,7 @@ int cfgpu_nse_linear(cfgpu_nse nse, cfgpu_field u, cfgpu_field q, cfgpu_field L)
 }
 
 int cfgpu_nse_cflfactor(cfgpu_nse nse, cfgpu_field u, double* out_h) {
-    CF_ARG(u->Nd == 3, "cfgpu_nse_cflfactor: 3 components");
+    CF_ARG(nse && shape_ok(nse, u, 3), "cfgpu_nse_cflfactor: u must be a 3-component field on the operator's grid");
     CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "cfgpu_nse_cflfactor: u must be spectral");
     cfgpu_ctx ctx = nse->ctx;
     CF_TRY(inverse_to_Q(nse, u, false));
