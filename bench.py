@@ -239,7 +239,10 @@ def main():
     fkw = flags_kw(w)
     STAGE_W = stage_table(fkw["nonlinearity"])
     STEP_W = sum(STAGE_W.values())
-    TRANS_W = sum(STAGE_W[k] for k in TRANSFORM_STAGES)
+    # "transforms + nonlinear term" = 36 W of the rotational step (66 W skew-symmetric): the forward y-pass bytes
+    # are booked with the solve there.  The time below is nevertheless that of ALL FIVE transform stages (the round-1
+    # review's convention: 36 W / (inv y + inv x + z + fwd x + fwd y)), so the fraction is a lower bound.
+    TRANS_W = 36 if STAGE_W is STAGE_W_ROT else 66
     gp = w["Nx"] * w["Ny"] * w["Nz"]
     Wbytes = 8 * w["Nx"] * w["Ny"] * 2 * (w["Nz"] // 2 + 1)
     nlname = {"rot": "rotational", "skew": "skew-symmetric"}.get(fkw["nonlinearity"], fkw["nonlinearity"])
@@ -388,6 +391,19 @@ def main():
                "note": "per rank; the host FlowField arrays are full size, only the retained (de-aliased) modes of the rank's kx rows cross PCIe"}
     clocks = sampler.result()
 
+    # ---- tau-solver setup (NSE::reset_lambda: once per dt change, every cfDSI evaluation): timed outside the step loop
+    setup_info = None
+    try:
+        lib.profile_enable(True)
+        lib.profile_read(reset=True)
+        dns.reset_dt(w["dt"])
+        sms, scalls = lib.profile_read(reset=True)
+        lib.profile_enable(False)
+        if scalls[7]:
+            setup_info = {"ms_per_lambda": sms[7] / scalls[7], "lambdas": scalls[7]}
+    except Exception:
+        pass
+
     # ---- roofline
     peaks = {}
     try:
@@ -477,6 +493,8 @@ def main():
             "gpu_launches": launches, "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline}
     if parity_block is not None:
         line["multi_gpu_parity"] = parity_block
+    if setup_info is not None:
+        line["tau_setup"] = setup_info
     print(json.dumps(line))
 
 

@@ -129,7 +129,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #endif
 }
 
-// ---- FP64 tensor-core MMA, the wide shape: D(16x8) += A(16x8, row) * B(8x8, col).  SASS: DMMA.16x8x8 ----
+// ---- FP64 tensor-core MMA, the wide shape: D(16x8) += A(16x8, row) * B(8x8, col).  SASS on sm_100a: 4 x DMMA.8x8x4 ----
 // fragment layout (PTX ISA, mma.m16n8k8 .f64), g = lane/4, t = lane%4:
 //   a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4];  b0 = B[t][g], b1 = B[t+4][g];
 //   c0,c1 = C[g][2t + {0,1}], c2,c3 = C[g+8][2t + {0,1}]

@@ -9,7 +9,8 @@
 // shuffles (col_deriv / col_solve below).  The C&H "B" row multiply (helmholtz.cpp:81-85) and the right-hand sides
 // of the four Helmholtz problems per mode are formed in registers; the influence-matrix and tau corrections and the
 // scatter are data-parallel passes of the whole CTA.
-// Setup kernel (rare: once per dt): one thread per (mode, parity) walks the reference's recurrences sequentially.
+// Setup (once per dt / lambda): factorisation chains one per thread, profile solves one mode per warp on the same
+// column solver (tau_factor_kernel, tau_profiles_kernel).
 // Roofline: HBM (history fields + factors are each read once, outputs written once).
 #include "tau.cuh"
 
@@ -38,72 +39,6 @@ __device__ __forceinline__ double A_up(int n, int Nb, double lam) {
 __host__ __device__ __forceinline__ double B_lo(int n, int Nb) { return cN(n - 2, Nb) / (double)(4 * n * (n - 1)); }
 __host__ __device__ __forceinline__ double B_dg(int n, int Nb) { return -((double)betaN(n, Nb)) / (double)(2 * (n * n - 1)); }
 __host__ __device__ __forceinline__ double B_up(int n, int Nb) { return betaN(n + 2, Nb) ? 1.0 / (double)(4 * n * (n + 1)) : 0.0; }
-
-// g = B f (helmholtz.cpp:81-85, bandedtridiag.cpp:315-333), boundary rows set to bc0 (n=0) / bc1 (n=1).
-__device__ __forceinline__ void bmul(const double* f, double* g, int N, int TT, double bc0, double bc1, int tid, int NT) {
-    const int Nb = N - 1;
-    for (int idx = tid; idx < N * TT; idx += NT) {
-        const int n = idx / TT;
-        double v;
-        if (n == 0) v = bc0;
-        else if (n == 1) v = bc1;
-        else {
-            v = B_lo(n, Nb) * f[idx - 2 * TT] + B_dg(n, Nb) * f[idx];
-            if (n + 2 <= Nb) v += B_up(n, Nb) * f[idx + 2 * TT];
-        }
-        g[idx] = v;
-    }
-}
-
-// UL solve of one parity block in place (bandedtridiag.cpp:258-273), reference operation order.  Used by the
-// (rare) setup kernel only; factor arrays are the tile's [n][TM] arrays in HBM.
-__device__ __forceinline__ void ul_solve_chain(double* g, int N, int TT, int t, int par, const double* up,
-                                               const double* inv, const double* band, int TM, int m, double lam) {
-    const int Nb = N - 1;
-    const int nl = par ? Nb - 1 : Nb;
-    for (int n = nl - 2; n >= par + 2; n -= 2) g[n * TT + t] -= up[m * N + n] * g[(n + 2) * TT + t];
-    double acc = g[par * TT + t];
-    for (int n = par + 2; n <= nl; n += 2) acc -= band[m * N + n] * g[n * TT + t];
-    acc /= inv[m * N + par];  // slot `par` of inv holds diag(0) of this parity block
-    g[par * TT + t] = acc;
-    double prev = acc;
-    for (int n = par + 2; n <= nl; n += 2) {
-        const double v = (g[n * TT + t] - A_lo(n, Nb, lam) * prev) * inv[m * N + n];
-        g[n * TT + t] = v;
-        prev = v;
-    }
-}
-
-// d = du/dy for the entries of parity `par` (chebyshev.cpp:672-697); optional d -= sub.
-__device__ __forceinline__ void diff_chain(const double* u, double* d, int N, int TT, int t, int par, double scale,
-                                           const double* sub) {
-    const int Nb = N - 1;
-    const int nl = ((Nb & 1) == par) ? Nb : Nb - 1;
-    double run = 0.0;
-    for (int n = nl; n >= par; n -= 2) {
-        if (n + 1 <= Nb) run = run + scale * (n + 1) * u[(n + 1) * TT + t];
-        double v = run;
-        if (n == 0) { v *= 0.5; }
-        d[n * TT + t] = sub ? v - sub[n * TT + t] : v;
-    }
-}
-
-// eval_b / eval_a of d = du/dy (chebyshev.cpp:405-430 applied to diff): sums run from n = N-1 down to 0.
-__device__ __forceinline__ void dudy_at_walls(const double* u, int N, int TT, int t, double scale, double& at_b, double& at_a) {
-    const int Nb = N - 1;
-    double de = 0.0, dod = 0.0;  // running d[n+2] for even / odd n
-    double sb = 0.0, sa = 0.0;
-    for (int n = Nb; n >= 0; --n) {
-        double& run = (n & 1) ? dod : de;
-        if (n + 1 <= Nb) run = run + scale * (n + 1) * u[(n + 1) * TT + t];
-        double v = run;
-        if (n == 0) v *= 0.5;
-        sb += v;
-        sa += v * ((n % 2 == 0) ? 1 : -1);
-    }
-    at_b = sb;
-    at_a = sa;
-}
 
 __device__ __forceinline__ void mode_of_q(int q, const ModeGeom& g, int& kx, int& kz, long& off) {
     const int nkz = g.Kz + 1, nmx = 2 * g.Kx + 1;
@@ -356,178 +291,178 @@ void tau_btab_host(int N, double* tab) {
 }
 
 // =================================================================================================== setup
-// grid = ntiles; CTA = one tile. Real profiles: smem arrays [n][TM].
-__global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_setup_kernel(const TauData td, const ModeGeom g, const double lambda_t) {
+// NSE::reset_lambda (nse.cpp:673-705) = TauSolver / HelmholtzSolver / BandedTridiag construction for every retained mode
+// (tausolver.cpp:81-176, helmholtz.cpp:18-77, bandedtridiag.cpp:212-229), in two kernels:
+//
+//  tau_factor_kernel   one THREAD per (mode slot, operator, parity) chain.  The UL factorisation is a continued-fraction
+//                      recurrence in n (no data besides n and lambda), so all 4 x modes chains run concurrently, each in the
+//                      reference's own operation order (bit-identical factors); the three values per step go straight to
+//                      the tile's [m][n] rows (the sectors are completed in L2 by the neighbouring steps / the other parity).
+//  tau_profiles_kernel one WARP per mode slot: the six profile solves (P+-, v+-, P0, v0) run on the blocked-scan column
+//                      solver of the solve kernel (col_solve / col_deriv), the wall derivatives for the influence matrix
+//                      come from the closed form sum n^2 v_n accumulated by the last elimination sweep.
+__global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_factor_kernel(const TauData td, const ModeGeom g, const double lambda_t) {
     const int N = td.N, Nb = N - 1, TM = td.TM;
-    const int tid = threadIdx.x, NT = TAU_SETUP_THREADS;
-    const int tl = blockIdx.x;
+    const long chain = (long)blockIdx.x * TAU_SETUP_THREADS + threadIdx.x;
+    // chain -> (slot, par, h): the four chains of a slot sit in consecutive threads
+    const long slot = chain >> 2;
+    if (slot >= (long)td.ntiles * TM) return;
+    const int par = (int)(chain & 1), h = (int)((chain >> 1) & 1);
+    const int tl = (int)(slot / TM), m = (int)(slot - (long)tl * TM);
     int q0, mfirst, mend;
     bool is00_;
     tile_modes(tl, td, q0, mfirst, mend, is00_);   // masked slots are set up as harmless kx = kz = 0 modes
-    double* A1 = dyn_smem<double>();
-    double* A2 = A1 + (size_t)N * TM;
-    double* A3 = A2 + (size_t)N * TM;
-    double* s_lamP = A3 + (size_t)N * TM;
-    double* s_lamV = s_lamP + TM;
-    double* s_w = s_lamV + TM;  // [8][TM]: Ab, Ca, Bb, Da, dplus, dminus, dP0dy_Nb1, spare
-
-    const double scale = 4.0 / (td.b - td.a);
-    const double nusP = 1.0 / (((td.b - td.a) / 2) * ((td.b - td.a) / 2));
-    const double nusV = td.nu / (((td.b - td.a) / 2) * ((td.b - td.a) / 2));
-
-    double* upP = td.tile_arr(tl, TAR_UPP); double* invP = td.tile_arr(tl, TAR_INVP); double* bandP = td.tile_arr(tl, TAR_BANDP);
-    double* upV = td.tile_arr(tl, TAR_UPV); double* invV = td.tile_arr(tl, TAR_INVV); double* bandV = td.tile_arr(tl, TAR_BANDV);
-    double* gPp = td.tile_arr(tl, TAR_PP); double* gvp = td.tile_arr(tl, TAR_VP); double* gPm = td.tile_arr(tl, TAR_PM);
-    double* gvm = td.tile_arr(tl, TAR_VM); double* gP0 = td.tile_arr(tl, TAR_P0); double* gv0 = td.tile_arr(tl, TAR_V0);
-
-    if (tid < TM) {
-        const int q = q0 + tid;
-        int kx = 0, kz = 0;
-        long off;
-        if (tid >= mfirst && tid < mend) mode_of_q(q, g, kx, kz, off);
-        const double kxL = kx / g.Lx, kzL = kz / g.Lz;
-        const double kappa2 = 4 * (PI * PI) * (kxL * kxL + kzL * kzL);
-        const double c = 4.0 * (PI * PI) * td.nu;
-        const double lamV = lambda_t + c * (kxL * kxL + kzL * kzL);
-        s_lamP[tid] = kappa2;
-        s_lamV[tid] = lamV;
-        td.tile_sc(tl, TSC_LAMP)[tid] = kappa2;
-        td.tile_sc(tl, TSC_LAMV)[tid] = lamV;
-        td.tile_sc(tl, TSC_KXX)[tid] = 2 * PI * kx / g.Lx;
-        td.tile_sc(tl, TSC_KZZ)[tid] = 2 * PI * kz / g.Lz;
+    int kx = 0, kz = 0;
+    long off;
+    if (m >= mfirst && m < mend) mode_of_q(q0 + m, g, kx, kz, off);
+    const double kxL = kx / g.Lx, kzL = kz / g.Lz;
+    const double kappa2 = 4 * (PI * PI) * (kxL * kxL + kzL * kzL);
+    const double c = 4.0 * (PI * PI) * td.nu;
+    const double lamV = lambda_t + c * (kxL * kxL + kzL * kzL);
+    if (par == 0 && h == 0) {
+        td.tile_sc(tl, TSC_LAMP)[m] = kappa2;
+        td.tile_sc(tl, TSC_LAMV)[m] = lamV;
+        td.tile_sc(tl, TSC_KXX)[m] = 2 * PI * kx / g.Lx;
+        td.tile_sc(tl, TSC_KZZ)[m] = 2 * PI * kz / g.Lz;
     }
+    const double hl2 = ((td.b - td.a) / 2) * ((td.b - td.a) / 2);
+    const double lam = h ? lamV : kappa2;
+    const double nus = h ? td.nu / hl2 : 1.0 / hl2;
+    double* up = td.tile_arr(tl, h ? TAR_UPV : TAR_UPP) + (size_t)m * N;
+    double* inv = td.tile_arr(tl, h ? TAR_INVV : TAR_INVP) + (size_t)m * N;
+    double* band = td.tile_arr(tl, h ? TAR_BANDV : TAR_BANDP) + (size_t)m * N;
+    // UL factorisation of the parity block (bandedtridiag.cpp:212-229), from the last row upwards
+    const int nl = par ? Nb - 1 : Nb;
+    double dgk = A_dg(nl, Nb, lam, nus);
+    double bandk = 1.0;
+    for (int n = nl; n >= par + 4; n -= 2) {
+        const double Akk = dgk;
+        inv[n] = 1.0 / Akk;
+        const double w = A_lo(n, Nb, lam);
+        const double upm = A_up(n - 2, Nb, lam) / Akk;
+        up[n - 2] = upm;
+        const double dprev = A_dg(n - 2, Nb, lam, nus) - w * upm;
+        const double bk = bandk / Akk;
+        band[n] = bk;
+        bandk = 1.0 - w * bk;
+        dgk = dprev;
+    }
+    const int n1 = par + 2;
+    inv[n1] = 1.0 / dgk;
+    const double b1 = bandk / dgk;
+    band[n1] = b1;
+    inv[par] = 1.0 - A_lo(n1, Nb, lam) * b1;  // diag(0) == band(0)
+}
+
+template <int E>
+__global__ void __launch_bounds__(TAU_THREADS) tau_profiles_kernel(const TauData td) {
+    const int N = td.N, Nb = N - 1, TM = td.TM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TAU_THREADS / 32;
+    const int NP = tau_col_pitch(N, E);
+    double* bt = dyn_smem<double>();  // B rows [3][NP], skewed like the solve kernel's
+    for (int i = tid; i < 3 * NP; i += TAU_THREADS) bt[i] = 0.0;
     __syncthreads();
-
-    // ---- UL factorisation of Ae, Ao for both Helmholtz operators (bandedtridiag.cpp:212-229)
-    for (int c = tid; c < 4 * TM; c += NT) {
-        const int m = c % TM, par = (c / TM) & 1, h = c / (2 * TM);
-        const double lam = h ? s_lamV[m] : s_lamP[m];
-        const double nus = h ? nusV : nusP;
-        double* up = h ? upV : upP;
-        double* inv = h ? invV : invP;
-        double* band = h ? bandV : bandP;
-        const int nl = par ? Nb - 1 : Nb;
-        double dgk = A_dg(nl, Nb, lam, nus);
-        double bandk = 1.0;
-        for (int n = nl; n >= par + 4; n -= 2) {
-            const double Akk = dgk;
-            inv[m * N + n] = 1.0 / Akk;
-            const double w = A_lo(n, Nb, lam);
-            const double upm = A_up(n - 2, Nb, lam) / Akk;
-            up[m * N + n - 2] = upm;
-            const double dprev = A_dg(n - 2, Nb, lam, nus) - w * upm;
-            const double bk = bandk / Akk;
-            band[m * N + n] = bk;
-            bandk = 1.0 - w * bk;
-            dgk = dprev;
-        }
-        const int n1 = par + 2;
-        inv[m * N + n1] = 1.0 / dgk;
-        const double b1 = bandk / dgk;
-        band[m * N + n1] = b1;
-        inv[m * N + par] = 1.0 - A_lo(n1, Nb, lam) * b1;  // diag(0) == band(0)
-    }
-    __syncthreads();
-
-    // ---- P+-, v+- and the influence matrix (tausolver.cpp:117-147)
-    for (int pm = 0; pm < 2; ++pm) {
-        for (int idx = tid; idx < N * TM; idx += NT) {
-            const int n = idx / TM;
-            // P(a)=0,P(b)=1 -> g0 = (ub+ua)/2 = .5, g1 = (ub-ua)/2 = .5 ; P(a)=1,P(b)=0 -> .5, -.5
-            A1[idx] = n == 0 ? 0.5 : (n == 1 ? (pm == 0 ? 0.5 : -0.5) : 0.0);
-        }
-        __syncthreads();
-        for (int c = tid; c < 2 * TM; c += NT) {
-            const int m = c % TM, par = c / TM;
-            ul_solve_chain(A1, N, TM, m, par, upP, invP, bandP, TM, m, s_lamP[m]);
-        }
-        __syncthreads();
-        for (int c = tid; c < 2 * TM; c += NT) diff_chain(A1, A2, N, TM, c % TM, c / TM, scale, nullptr);
-        __syncthreads();
-        bmul(A2, A3, N, TM, 0.0, 0.0, tid, NT);
-        __syncthreads();
-        for (int c = tid; c < 2 * TM; c += NT) {
-            const int m = c % TM, par = c / TM;
-            ul_solve_chain(A3, N, TM, m, par, upV, invV, bandV, TM, m, s_lamV[m]);
-        }
-        __syncthreads();
-        double* gP = pm == 0 ? gPp : gPm;
-        double* gv = pm == 0 ? gvp : gvm;
-        for (int idx = tid; idx < N * TM; idx += NT) {
-            const int n = idx / TM, m = idx - n * TM;
-            gP[m * N + n] = A1[idx];
-            gv[m * N + n] = A3[idx];
-        }
-        if (tid < TM) {
-            double vb, va;
-            dudy_at_walls(A3, N, TM, tid, scale, vb, va);
-            s_w[(2 * pm) * TM + tid] = vb;      // A (plus) / B (minus)
-            s_w[(2 * pm + 1) * TM + tid] = va;  // C (plus) / D (minus)
-        }
-        __syncthreads();
-    }
-    if (tid < TM) {
-        const double A = s_w[0 * TM + tid], C = s_w[1 * TM + tid], B = s_w[2 * TM + tid], D = s_w[3 * TM + tid];
-        const double disc = A * D - B * C;
-        td.tile_sc(tl, TSC_I00)[tid] = D / disc;
-        td.tile_sc(tl, TSC_I01)[tid] = -B / disc;
-        td.tile_sc(tl, TSC_I10)[tid] = -C / disc;
-        td.tile_sc(tl, TSC_I11)[tid] = A / disc;
-    }
-    // ---- tau-correction basis P0, v0, sigma0 (tausolver.cpp:149-175)
     {
+        const double* src = td.btab();
+        for (int i = tid; i < 3 * N; i += TAU_THREADS) {
+            const int r = i >= 2 * N ? 2 : (i >= N ? 1 : 0), n = i - r * N;
+            bt[r * NP + col_addr<E>(n)] = src[i];
+        }
+    }
+    __syncthreads();
+    const long slot = (long)blockIdx.x * NW + warp;
+    if (slot >= (long)td.ntiles * TM) return;
+    const int tl = (int)(slot / TM), m = (int)(slot - (long)tl * TM);
+    const double scale = 4.0 / (td.b - td.a);
+    const double lamP = td.tile_sc(tl, TSC_LAMP)[m], lamV = td.tile_sc(tl, TSC_LAMV)[m];
+    const size_t NM = (size_t)N * TM;
+    const double* fP = td.tile_arr(tl, TAR_UPP) + (size_t)m * N;   // up, inv, band of the pressure operator: fP + {0,1,2} NM
+    const double* fV = td.tile_arr(tl, TAR_UPV) + (size_t)m * N;
+    const int n0 = lane * E;
+    auto store_row = [&](int which, const double (&x)[E]) {
+        double* dst = td.tile_arr(tl, which) + (size_t)m * N + n0;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (n0 + e < N) dst[e] = x[e];
+    };
+    auto load_row = [&](int which, double (&x)[E]) {
+        const double* src = td.tile_arr(tl, which) + (size_t)m * N + n0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] = (n0 + e < N) ? src[e] : 0.0;
+    };
+    // ---- P+-, v+- and the influence matrix (tausolver.cpp:117-147).  Boundary rows g0 = (ub+ua)/2, g1 = (ub-ua)/2
+    // (helmholtz.cpp:86-87): P(a)=0, P(b)=1 -> .5, .5 ; P(a)=1, P(b)=0 -> .5, -.5
+    double vwall[2][2];  // [plus/minus][at b / at a] of dv/dy
+#pragma unroll
+    for (int pm = 0; pm < 2; ++pm) {
+        double r[E], P[E], d[E], v[E], wall[2];
+#pragma unroll
+        for (int e = 0; e < E; ++e) r[e] = 0.0;
+        col_solve<E, false>(r, P, fP, fP + NM, fP + 2 * NM, lamP, bt, N, lane, 0.5, pm == 0 ? 0.5 : -0.5, nullptr);
+        col_deriv<E>(P, d, scale, lane);
+        col_solve<E, false>(d, v, fV, fV + NM, fV + 2 * NM, lamV, bt, N, lane, 0.0, 0.0, wall);
+        store_row(pm == 0 ? TAR_PP : TAR_PM, P);
+        store_row(pm == 0 ? TAR_VP : TAR_VM, v);
+        // v'(b) = (2/L) sum n^2 v_n, v'(a) = (2/L) sum (-1)^(n+1) n^2 v_n  (closed form of eval_b/eval_a of diff(v))
+        vwall[pm][0] = 0.5 * scale * (wall[1] + wall[0]);
+        vwall[pm][1] = 0.5 * scale * (wall[1] - wall[0]);
+    }
+    const double A = vwall[0][0], C = vwall[0][1], B = vwall[1][0], D = vwall[1][1];
+    const double disc = A * D - B * C;
+    const double i00 = D / disc, i01 = -B / disc, i10 = -C / disc, i11 = A / disc;
+    // ---- tau-correction basis P0, v0, sigma0 (tausolver.cpp:149-175)
+    double P0[E], v0[E], dP0_nb1;
+    {
+        double r[E], d[E], wall[2];
         const double cc = 2 / (td.b - td.a);
-        for (int idx = tid; idx < N * TM; idx += NT) {
-            const int i = idx / TM;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = n0 + e;
             int nf;
             if (i == 0) nf = Nb - 1;
             else if (i == Nb) nf = 0;
             else if (i % 2 == 0) nf = 2 * (Nb - 1);
             else nf = 2 * Nb;
-            A1[idx] = cc * nf;
+            r[e] = i < N ? cc * nf : 0.0;
         }
+        col_solve<E, false>(r, P0, fP, fP + NM, fP + 2 * NM, lamP, bt, N, lane, 0.0, 0.0, nullptr);
+        col_deriv<E>(P0, d, scale, lane);
+        {   // dP0/dy at n = Nb-1 (before the influence correction, as in the reference)
+            double t = 0.0;
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if (n0 + e == Nb - 1) t = d[e];
+            dP0_nb1 = warp_sum(t);
+        }
+        col_solve<E, false>(d, v0, fV, fV + NM, fV + 2 * NM, lamV, bt, N, lane, 0.0, 0.0, wall);
+        const double vb = 0.5 * scale * (wall[1] + wall[0]), va = 0.5 * scale * (wall[1] - wall[0]);
+        const double dp = -i00 * vb - i01 * va, dm = -i10 * vb - i11 * va;
+        double Pp[E], Pm[E];
+        __syncwarp();
+        load_row(TAR_PP, Pp); load_row(TAR_PM, Pm);
+#pragma unroll
+        for (int e = 0; e < E; ++e) P0[e] = P0[e] + (dp * Pp[e] + dm * Pm[e]);
+        load_row(TAR_VP, Pp); load_row(TAR_VM, Pm);
+#pragma unroll
+        for (int e = 0; e < E; ++e) v0[e] = v0[e] + (dp * Pp[e] + dm * Pm[e]);
     }
-    __syncthreads();
-    bmul(A1, A2, N, TM, 0.0, 0.0, tid, NT);
-    __syncthreads();
-    for (int c = tid; c < 2 * TM; c += NT) {
-        const int m = c % TM, par = c / TM;
-        ul_solve_chain(A2, N, TM, m, par, upP, invP, bandP, TM, m, s_lamP[m]);
-    }
-    __syncthreads();  // A2 = P0 (before influence correction)
-    for (int c = tid; c < 2 * TM; c += NT) diff_chain(A2, A3, N, TM, c % TM, c / TM, scale, nullptr);
-    __syncthreads();  // A3 = dP0/dy
-    if (tid < TM) s_w[6 * TM + tid] = A3[(Nb - 1) * TM + tid];
-    bmul(A3, A1, N, TM, 0.0, 0.0, tid, NT);
-    __syncthreads();
-    for (int c = tid; c < 2 * TM; c += NT) {
-        const int m = c % TM, par = c / TM;
-        ul_solve_chain(A1, N, TM, m, par, upV, invV, bandV, TM, m, s_lamV[m]);
-    }
-    __syncthreads();  // A1 = v0
-    if (tid < TM) {
-        double vb, va;
-        dudy_at_walls(A1, N, TM, tid, scale, vb, va);
-        s_w[4 * TM + tid] = -td.tile_sc(tl, TSC_I00)[tid] * vb - td.tile_sc(tl, TSC_I01)[tid] * va;
-        s_w[5 * TM + tid] = -td.tile_sc(tl, TSC_I10)[tid] * vb - td.tile_sc(tl, TSC_I11)[tid] * va;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < N * TM; idx += NT) {
-        const int n = idx / TM, m = idx - n * TM, gi = m * N + n;
-        const double dp = s_w[4 * TM + m], dm = s_w[5 * TM + m];
-        const double P0 = A2[idx] + (dp * gPp[gi] + dm * gPm[gi]);
-        const double v0 = A1[idx] + (dp * gvp[gi] + dm * gvm[gi]);
-        A2[idx] = P0;
-        A1[idx] = v0;
-        gP0[gi] = P0;
-        gv0[gi] = v0;
-    }
-    __syncthreads();
-    if (tid < TM) {
-        const double lam = s_lamV[tid];
-        // v0'' has zero coefficients at Nb-1 and Nb, dP0/dy[Nb] == 0 (chebyshev.cpp:688-689)
-        td.tile_sc(tl, TSC_S0NB1)[tid] = lam * A1[(Nb - 1) * TM + tid] + s_w[6 * TM + tid] - td.nu * 0.0;
-        td.tile_sc(tl, TSC_S0NB)[tid] = lam * A1[Nb * TM + tid] + 0.0 - td.nu * 0.0;
+    store_row(TAR_P0, P0);
+    store_row(TAR_V0, v0);
+    {
+        double t1 = 0.0, t0 = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (n0 + e == Nb - 1) t1 = v0[e];
+            if (n0 + e == Nb) t0 = v0[e];
+        }
+        t1 = warp_sum(t1); t0 = warp_sum(t0);
+        if (lane == 0) {
+            double* sc = td.tile_sc(tl, 0);
+            sc[TSC_I00 * TM + m] = i00; sc[TSC_I01 * TM + m] = i01; sc[TSC_I10 * TM + m] = i10; sc[TSC_I11 * TM + m] = i11;
+            // v0'' has zero coefficients at Nb-1 and Nb, dP0/dy[Nb] == 0 (chebyshev.cpp:688-689)
+            sc[TSC_S0NB1 * TM + m] = lamV * t1 + dP0_nb1;
+            sc[TSC_S0NB * TM + m] = lamV * t0;
+        }
     }
 }
 
@@ -875,95 +810,114 @@ __global__ void __launch_bounds__(TAU_THREADS, (E <= 10 ? 2 : 1)) tau_solve_kern
 
 // =================================================================================================== linear
 // NSE::linear (nse.cpp:393-477): L = nu u'' - nu kappa^2 u - grad q  per retained mode (+ mean-mode constants).
-// grid = ceil(nq/TM). smem: Pk, Pyk, X, T, R as [n][t].
-__global__ void __launch_bounds__(TAU_SETUP_THREADS) linear_kernel(const TauSolveParams p, const double* __restrict__ u,
-                                                                   const double* __restrict__ q, double* __restrict__ L) {
+// One CTA per tile of td.TM modes (the tile of the tile-major field layout: its block of u, q and L is contiguous).  The
+// CTA streams u (3 components) and q into skewed shared-memory columns (re / im part of one mode's profile each), then
+// every WARP owns one (component, column): two blocked-scan derivatives (col_deriv) of nu*u in registers, the pressure
+// gradient from the q columns, result back into the column in place; a coalesced store phase mirrors the load.
+template <int E>
+__global__ void __launch_bounds__(TAU_THREADS) linear_kernel(const TauSolveParams p, const double* __restrict__ u,
+                                                             const double* __restrict__ q, double* __restrict__ L) {
     const TauData& td = p.td;
-    const int N = td.N;
-    const int tid = threadIdx.x, NT = TAU_SETUP_THREADS;
+    const int N = td.N, TM = td.TM, TT = 2 * TM;
+    const int tid = threadIdx.x, NT = TAU_THREADS, lane = tid & 31, warp = tid >> 5, NW = TAU_THREADS / 32;
     const double scale = 4.0 / (td.b - td.a);
-    // u, q, L in the reference layout, or all three tile-major with td.TM modes per tile (q: one component)
-    const bool tiled = p.tile_layout != 0;
-    const long rs = tiled ? 2L * td.TM : (long)p.g.Nx * (2 * (p.g.Nz / 2 + 1));
-    const long cs = tiled ? (long)N * td.TM * 2 : rs * p.g.Ny;
-    const int TM = p.TM_lin, TT = 2 * TM;
-    const size_t AS = (size_t)N * TT;
-    double* Pk = dyn_smem<double>();
-    double* Pyk = Pk + AS; double* X = Pyk + AS; double* T = X + AS; double* R = T + AS;
-    double* s_k = R + AS;  // [3][TM]: kappa2, kxx, kzz
-    long* s_off = reinterpret_cast<long*>(s_k + 3 * TM);   // mode offset in a 3-component field (u, L); -1: no mode
-    long* s_offq = s_off + TM;                              // ... in the 1-component field q
+    const int NP = tau_col_pitch(N, E);
+    const int AS = TT * NP;
+    double* U = dyn_smem<double>();   // [3][TT][NP]  nu*u on load, L on store
+    double* Q = U + 3 * AS;           // [TT][NP]
+    double* s_k = Q + AS;             // [3][TM]: kappa2, kxx, kzz
+    long* s_off = reinterpret_cast<long*>(s_k + 3 * TM);  // serial-layout offset of the mode; -1: no mode in this slot
     __shared__ double s_shear[2];
-    const int q0 = blockIdx.x * TM;
+    const int tl = blockIdx.x;
+    const int q0 = tl * TM;
+    const bool tiled = p.tile_layout != 0;
     if (tid < TM) {
         const int qq = q0 + tid;
-        long off = -1, offq = -1;
-        if (qq < td.nq) {
-            int kx, kz;
-            mode_of_q(qq, p.g, kx, kz, off);
-            offq = off;
-            if (tiled) {
-                const long t = qq / td.TM, pos = qq % td.TM;
-                off = t * 3 * N * td.TM * 2 + pos * 2;
-                offq = t * N * td.TM * 2 + pos * 2;
-            }
-        }
+        long off = -1;
+        if (qq < td.nq) { int kx, kz; mode_of_q(qq, p.g, kx, kz, off); }
         s_off[tid] = off;
-        s_offq[tid] = offq;
         const int qs = qq < td.nq ? qq : 0;
         s_k[tid] = td.scq(TSC_LAMP, qs);
         s_k[TM + tid] = td.scq(TSC_KXX, qs);
         s_k[2 * TM + tid] = td.scq(TSC_KZZ, qs);
     }
+    if (tid < 2) s_shear[tid] = 0.0;
     __syncthreads();
-    for (int idx = tid; idx < (int)AS; idx += NT) {
-        const int n = idx / TT, t = idx - n * TT;
-        const long off = s_offq[t >> 1];
-        Pk[idx] = off >= 0 ? q[n * rs + off + (t & 1)] : 0.0;
+    // thread -> (mode m, row slot j0): rows n = j0, j0 + NT/TM, ...
+    const int m_ld = tid % TM, j0 = tid / TM, JS = NT / TM;
+    long off = s_off[m_ld], offq = off;
+    long rs = (long)p.g.Nx * (2 * (p.g.Nz / 2 + 1)), cs = rs * p.g.Ny;
+    if (tiled && off >= 0) {
+        off = ((long)tl * 3 * N * TM + m_ld) * 2; offq = ((long)tl * N * TM + m_ld) * 2;
+        cs = (long)N * TM * 2; rs = TM * 2;
+    }
+    if (off >= 0) {
+        for (int n = j0; n < N; n += JS) {
+            const int a = (2 * m_ld) * NP + col_addr<E>(n);
+#pragma unroll
+            for (int comp = 0; comp < 3; ++comp) {
+                const double2 v = *reinterpret_cast<const double2*>(u + comp * cs + n * rs + off);
+                U[comp * AS + a] = td.nu * v.x;
+                U[comp * AS + a + NP] = td.nu * v.y;
+            }
+            const double2 v = *reinterpret_cast<const double2*>(q + n * rs + offq);
+            Q[a] = v.x;
+            Q[a + NP] = v.y;
+        }
     }
     __syncthreads();
-    for (int c = tid; c < 2 * TT; c += NT) diff_chain(Pk, Pyk, N, TT, c % TT, c / TT, scale, nullptr);
-    __syncthreads();
-    for (int comp = 0; comp < 3; ++comp) {
-        for (int idx = tid; idx < (int)AS; idx += NT) {
-            const int n = idx / TT, t = idx - n * TT;
-            const long off = s_off[t >> 1];
-            X[idx] = off >= 0 ? td.nu * u[comp * cs + n * rs + off + (t & 1)] : 0.0;
+    for (int item = warp; item < 3 * TT; item += NW) {
+        const int comp = item / TT, col = item - comp * TT, m = col >> 1, ri = col & 1;
+        if (s_off[m] < 0) continue;
+        double x[E], d1[E], d2[E], g[E];
+        col_load<E>(U + comp * AS + col * NP, lane, N, x);
+        col_deriv<E>(x, d1, scale, lane);
+        col_deriv<E>(d1, d2, scale, lane);
+        const bool mean00 = td.has00 && q0 + m == 0 && ri == 0;
+        if (comp == 1) {
+            double qc[E];
+            col_load<E>(Q + col * NP, lane, N, qc);
+            col_deriv<E>(qc, g, scale, lane);
+        } else {
+            double qo[E];
+            col_load<E>(Q + (col ^ 1) * NP, lane, N, qo);
+            const double k = s_k[(comp == 0 ? 1 : 2) * TM + m];
+#pragma unroll
+            for (int e = 0; e < E; ++e) g[e] = ri ? k * qo[e] : -(k * qo[e]);
         }
-        __syncthreads();
-        for (int c = tid; c < 2 * TT; c += NT) diff_chain(X, T, N, TT, c % TT, c / TT, scale, nullptr);
-        __syncthreads();
-        if (td.has00 && blockIdx.x == 0 && p.constraint == 1 && comp != 1 && tid == 0) {  // q = 0 is slot 0 of block 0
-            // wall shear of nu*u for the (0,0) mode, real part (t = 0): eval_b - eval_a of d(nu u)/dy
-            double sb = 0.0, sa = 0.0;
-            for (int n = N - 1; n >= 0; --n) { sb += T[n * TT]; sa += T[n * TT] * ((n % 2 == 0) ? 1 : -1); }
-            s_shear[comp / 2] = (sb - sa) / (td.b - td.a);
+        double shear = 0.0;
+        if (mean00 && p.constraint == 1 && comp != 1) {
+            // wall shear of nu*u for the (0,0) mode: (eval_b - eval_a of d(nu u)/dy)/Ly = (2/Ly) sum_{n odd} d1_n
+            double so = 0.0;
+#pragma unroll
+            for (int e = 1; e < E; e += 2) so += d1[e];   // E even: slot parity == parity of n
+            shear = 2.0 * warp_sum(so) / (td.b - td.a);
         }
-        for (int c = tid; c < 2 * TT; c += NT) diff_chain(T, R, N, TT, c % TT, c / TT, scale, nullptr);
-        __syncthreads();
-        for (int idx = tid; idx < (int)AS; idx += NT) {
-            const int n = idx / TT, t = idx - n * TT, m = t >> 1;
-            const long off = s_off[m];
-            if (off < 0) continue;
-            const double kap2 = s_k[m], kxx = s_k[TM + m], kzz = s_k[2 * TM + m];
-            double g;  // component of grad q
-            if (comp == 1) g = Pyk[idx];
-            else {
-                const double k = comp == 0 ? kxx : kzz;
-                g = (t & 1) ? k * Pk[idx - 1] : -k * Pk[idx + 1];
-            }
-            double v = R[idx] - kap2 * X[idx] - g;
-            if (td.has00 && q0 + m == 0 && (t & 1) == 0) {
+        const double kap2 = s_k[m];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int n = lane * E + e;
+            double v = d2[e] - kap2 * x[e] - g[e];
+            if (mean00 && n < N) {
                 if (comp == 0 && p.Ubaseyy) v += td.nu * p.Ubaseyy[n];
                 if (comp == 2 && p.Wbaseyy) v += td.nu * p.Wbaseyy[n];
                 if (n == 0 && comp != 1) {
                     if (p.constraint == 0) v -= comp == 0 ? p.dPdxRef : p.dPdzRef;
-                    else v -= s_shear[comp / 2] + (comp == 0 ? p.lin_base_dPdx : p.lin_base_dPdz);
+                    else v -= shear + (comp == 0 ? p.lin_base_dPdx : p.lin_base_dPdz);
                 }
             }
-            L[comp * cs + n * rs + off + (t & 1)] = v;
+            x[e] = v;
         }
-        __syncthreads();
+        col_store<E>(U + comp * AS + col * NP, lane, N, x);
+    }
+    __syncthreads();
+    if (off >= 0) {
+        for (int n = j0; n < N; n += JS) {
+            const int a = (2 * m_ld) * NP + col_addr<E>(n);
+#pragma unroll
+            for (int comp = 0; comp < 3; ++comp)
+                *reinterpret_cast<double2*>(L + comp * cs + n * rs + off) = make_double2(U[comp * AS + a], U[comp * AS + a + NP]);
+        }
     }
 }
 
@@ -999,33 +953,68 @@ int tau_pick_TM_solve(int N) {
     return TM;
 }
 
+template <int E>
+static int profiles_launch_e(const TauData& td, cudaStream_t stream) {
+    const size_t smem = (size_t)3 * tau_col_pitch(td.N, E) * sizeof(double);
+    const long slots = (long)td.ntiles * td.TM;
+    dim3 grid((unsigned)((slots + TAU_THREADS / 32 - 1) / (TAU_THREADS / 32)));
+    CF_LAUNCH(tau_profiles_kernel<E>, grid, dim3(TAU_THREADS), smem, stream, td);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
 int tau_setup_launch(const TauData& td, const ModeGeom& g, double lambda_t, cudaStream_t stream) {
-    const size_t smem = ((size_t)3 * td.N * td.TM + 10 * td.TM) * sizeof(double);
+    const long chains = 4L * td.ntiles * td.TM;
+    dim3 grid((unsigned)((chains + TAU_SETUP_THREADS - 1) / TAU_SETUP_THREADS));
+    CF_LAUNCH(tau_factor_kernel, grid, dim3(TAU_SETUP_THREADS), 0, stream, td, g, lambda_t);
+    CF_KERNEL_CHECK();
+    switch (tau_pick_E(td.N)) {
+        case 2: return profiles_launch_e<2>(td, stream);
+        case 4: return profiles_launch_e<4>(td, stream);
+        case 6: return profiles_launch_e<6>(td, stream);
+        case 8: return profiles_launch_e<8>(td, stream);
+        case 10: return profiles_launch_e<10>(td, stream);
+        case 12: return profiles_launch_e<12>(td, stream);
+        case 16: return profiles_launch_e<16>(td, stream);
+        case 20: return profiles_launch_e<20>(td, stream);
+    }
+    set_last_error("tau_setup: unsupported Ny");
+    return 1;
+}
+
+template <int E>
+static int linear_launch_e(const TauSolveParams& p, const double* u, const double* q, double* L, cudaStream_t stream) {
+    const int TM = p.td.TM, TT = 2 * TM;
+    const size_t smem = ((size_t)4 * TT * tau_col_pitch(p.td.N, E) + 3 * TM) * sizeof(double) + TM * sizeof(long);
+    if (smem > 227 * 1024 || TAU_THREADS % TM) {
+        set_last_error("linear: Ny too large for the shared-memory tile");
+        return 1;
+    }
     static size_t configured = 0;
-    auto kfn = tau_setup_kernel;
+    auto kfn = linear_kernel<E>;
     if (smem > configured) {
         CF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid(td.ntiles);
-    CF_LAUNCH(kfn, grid, dim3(TAU_SETUP_THREADS), smem, stream, td, g, lambda_t);
+    dim3 grid((p.td.nq + TM - 1) / TM);
+    CF_LAUNCH(kfn, grid, dim3(TAU_THREADS), smem, stream, p, u, q, L);
     CF_KERNEL_CHECK();
     return 0;
 }
 
 int linear_launch(const TauSolveParams& p, const double* u, const double* q, double* L, cudaStream_t stream) {
-    const int TT = 2 * p.TM_lin;
-    const size_t smem = ((size_t)5 * p.td.N * TT + 3 * p.TM_lin) * sizeof(double) + 2 * p.TM_lin * sizeof(long);
-    static size_t configured = 0;
-    auto kfn = linear_kernel;
-    if (smem > configured) {
-        CF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    switch (tau_pick_E(p.td.N)) {
+        case 2: return linear_launch_e<2>(p, u, q, L, stream);
+        case 4: return linear_launch_e<4>(p, u, q, L, stream);
+        case 6: return linear_launch_e<6>(p, u, q, L, stream);
+        case 8: return linear_launch_e<8>(p, u, q, L, stream);
+        case 10: return linear_launch_e<10>(p, u, q, L, stream);
+        case 12: return linear_launch_e<12>(p, u, q, L, stream);
+        case 16: return linear_launch_e<16>(p, u, q, L, stream);
+        case 20: return linear_launch_e<20>(p, u, q, L, stream);
     }
-    dim3 grid((p.td.nq + p.TM_lin - 1) / p.TM_lin);
-    CF_LAUNCH(kfn, grid, dim3(TAU_SETUP_THREADS), smem, stream, p, u, q, L);
-    CF_KERNEL_CHECK();
-    return 0;
+    set_last_error("linear: unsupported Ny");
+    return 1;
 }
 
 template <int E, int NTERMS>

@@ -14,7 +14,9 @@ constexpr double TWO_PI = 6.283185307179586476925286766559;
 static int set_smem(const void* fn, size_t bytes, size_t& configured);
 
 // ------------------------------------------------------------------------------------------------ x inverse
-// grid = (ceil(nkz/TZ), nyn, nfields)   P[src][yl][mxi][kz] -> Q[f][yl][nx][kz], optional d/dx = i 2 pi kx / Lx
+// grid = (nfields, ceil(nkz/TZ), nyn)   P[src][yl][mxi][kz] -> Q[f][yl][nx][kz], optional d/dx = i 2 pi kx / Lx
+// The output field is the FASTEST grid index: the CTAs that share source rows (u, v, w and the three components of curl u
+// read 9 source tiles of 5 distinct fields) run next to each other and the re-reads hit L2 instead of HBM.
 __global__ void __launch_bounds__(XZ_THREADS, 3) xpass_inverse_kernel(const XPassParams p) {
     const int Nx = p.Nx, Kx = p.Kx, TZ = p.TZ;
     const int nmx = 2 * Kx + 1, nkz = p.Kz + 1;
@@ -26,7 +28,7 @@ __global__ void __launch_bounds__(XZ_THREADS, 3) xpass_inverse_kernel(const XPas
     double* kxf = reinterpret_cast<double*>(tws + ntw);  // 2 pi kx / Lx of pencil row mxi
     int* rev = reinterpret_cast<int*>(kxf + nmx);       // digit-reversed row of mode row mx (input side of the DIT transform)
     const int tid = threadIdx.x;
-    const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
+    const int f = p.fsel[blockIdx.x], yl = blockIdx.z, kz0 = blockIdx.y * TZ;
     const int s = p.src[f], oa = p.opa[f], sb = p.srcb[f], ob = p.opb[f];
 
     for (int t = tid; t < Nx; t += XZ_THREADS) {
@@ -556,7 +558,7 @@ int xpass_inverse_launch(const XPassParams& p, cudaStream_t stream) {
     static size_t configured = 0;
     auto kfn = xpass_inverse_kernel;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
-    dim3 grid((nkz + p.TZ - 1) / p.TZ, p.nyn, p.nfields);
+    dim3 grid(p.nfields, (nkz + p.TZ - 1) / p.TZ, p.nyn);
     CF_LAUNCH(kfn, grid, dim3(XZ_THREADS), smem, stream, p);
     CF_KERNEL_CHECK();
     return 0;

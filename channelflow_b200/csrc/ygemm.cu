@@ -4,9 +4,9 @@
 // component and ALL Ny rows: it stages the even/odd (or sum/difference) operand tiles in shared memory once
 // (each HBM element is read exactly once, 512-byte runs; inverse mode uses cp.async so that the whole tile is in
 // flight at once), then its 8 warps -- 4 along the output rows, 2 along the columns -- each own a 32-row x (BN/2)-column
-// output tile of BOTH parity products (E and O accumulators in registers) and issue mma.sync.m16n8k8.f64 (SASS
-// DMMA.16x8x8, 8x fewer instructions than the legacy m8n8k4 shape): per k-step of 8 a warp loads 8 A and BN/8 B
-// fragment registers for BN/8 DMMAs.  A fragments come
+// output tile of BOTH parity products (E and O accumulators in registers) and issue mma.sync.m16n8k8.f64 (ptxas lowers
+// it to four DMMA.8x8x4 on sm_100a -- cuobjdump -sass, profiles/r02_sass_opcodes.txt -- the wide PTX shape only saves
+// fragment bookkeeping): per k-step of 8 a warp loads 8 A and BN/8 B fragment registers for BN/8 MMAs.  A fragments come
 // from L1/L2 (the matrices are a few hundred KB, shared by every CTA) and are register double-buffered one k-step
 // ahead; B fragments come from shared memory (row pitch BN+4 doubles => conflict-free fragment loads).
 // A trailing remainder of at most 2 rows (Ny = 2^k+1 gives 32*m + 1 rows: the self-paired middle point / last
@@ -15,16 +15,20 @@
 // Roofline: tensor (FP64) for Ny >~ 49, HBM below; algorithmic flops = 2*Ny*ceil(Ny/2)*2 per column per output.
 #include "ygemm.cuh"
 
+#include <cstdlib>
+
 namespace cfgpu {
 
-namespace {
-constexpr int YG_THREADS = 256;
-}
+constexpr bool YG_SPLIT_DEFAULT = false;  // set from the A/B measurement (profiles/r02_*)
 
-template <int BN>
-__global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams p) {
+// BN columns per CTA, WN warps along the columns (4 warps along the rows): <64,2> is one 256-thread CTA per SM, <32,1> two
+// independent 128-thread CTAs per SM with the same 32 x 32 warp tile -- one CTA's staging and epilogue overlap the other's
+// DMMA loop.
+template <int BN, int WN>
+__global__ void __launch_bounds__(128 * WN, WN == 1 ? 2 : 1) ygemm_kernel(const YGemmParams p) {
+    constexpr int YG_THREADS = 128 * WN;
     constexpr int LD = BN + 4;
-    constexpr int NT = BN / 16;   // 8-column n-tiles per warp (2 warps along the columns)
+    constexpr int NT = BN / (8 * WN);   // 8-column n-tiles per warp
     const YGemmJob& job = p.job[blockIdx.y];
     const bool two = p.two_inputs != 0;  // launch-wide: second pair of tiles present in shared memory
     double* B1 = dyn_smem<double>();
@@ -114,13 +118,13 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
-    const int wn = warp & 1, wm = warp >> 1;  // 2 warps along the columns, 4 along the rows
+    const int wn = warp % WN, wm = warp / WN;  // WN warps along the columns, 4 along the rows
     const int lr = lane >> 2, lk = lane & 3;  // fragment row / k (A), n / k (B)
     const int Mmax = p.M > p.M2 ? p.M : p.M2;
     const int rem = Mmax & 31;
     const int Mgemm = (rem >= 1 && rem <= 2) ? Mmax - rem : Mmax;  // rows done on the tensor pipe
     const int Mtiles = (Mgemm + 31) / 32;
-    const int ncb = wn * (BN / 2);
+    const int ncb = wn * (BN / WN);
 
     for (int mi = 0; mi < job.nmat; ++mi) {
         const int mat = job.mat0 + mi;
@@ -270,10 +274,11 @@ __global__ void __launch_bounds__(YG_THREADS, 1) ygemm_kernel(const YGemmParams 
     }
 }
 
-template <int BN>
+template <int BN, int WN = 2>
 static int launch_bn(const YGemmParams& p, cudaStream_t stream) {
+    constexpr int YG_THREADS = 128 * WN;
     const size_t smem = (size_t)(p.two_inputs ? 2 : 1) * (p.K1p + p.K2p) * (BN + 4) * sizeof(double) + 2 * BN * sizeof(long);
-    auto kfn = ygemm_kernel<BN>;
+    auto kfn = ygemm_kernel<BN, WN>;
     static size_t configured = 0;
     if (smem > configured) {
         CF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -301,6 +306,10 @@ int ygemm_launch(const YGemmParams& p0, cudaStream_t stream) {
     }
     const size_t rows = (size_t)(p.K1p + p.K2p) * (p.two_inputs ? 2 : 1);
     const size_t limit = 220 * 1024;
+    // two half-width CTAs per SM when one full-width tile would own the SM alone (long profiles): CF_YG_SPLIT=0/1 overrides
+    static const int split = getenv("CF_YG_SPLIT") ? atoi(getenv("CF_YG_SPLIT")) : -1;
+    const bool one_per_sm = rows * 68 * 8 + 1024 > 110 * 1024;
+    if (rows * 36 * 8 + 512 <= 110 * 1024 && (split == 1 || (split < 0 && one_per_sm && YG_SPLIT_DEFAULT))) return launch_bn<32, 1>(p, stream);
     if (rows * 68 * 8 + 1024 <= limit) return launch_bn<64>(p, stream);
     if (rows * 36 * 8 + 512 <= limit) return launch_bn<32>(p, stream);
     if (rows * 20 * 8 + 256 <= limit) return launch_bn<16>(p, stream);
