@@ -29,7 +29,9 @@ cfgpu_field_make_physical_y cfgpu_field_make_spectral_y cfgpu_field_make_physica
 cfgpu_field_make_physical cfgpu_field_make_spectral cfgpu_l2norm2 cfgpu_l2norm2_3d cfgpu_l2dist2 cfgpu_l2ip cfgpu_nse_create
 cfgpu_nse_destroy cfgpu_nse_set_constraint cfgpu_nse_reset_lambda cfgpu_nse_nonlinear cfgpu_nse_solve
 cfgpu_nse_linear cfgpu_nse_cflfactor cfgpu_nse_get_dPd cfgpu_comm_unique_id cfgpu_comm_init_nccl
-cfgpu_comm_init_external cfgpu_comm_rank cfgpu_comm_ranges cfgpu_field_allgather""".split()
+cfgpu_comm_init_external cfgpu_comm_rank cfgpu_comm_ranges cfgpu_field_allgather
+cfgpu_vec_create cfgpu_vec_destroy cfgpu_vec_size cfgpu_vec_upload cfgpu_vec_download cfgpu_vec_copy cfgpu_vec_zero cfgpu_vec_dot
+cfgpu_vec_nrm2 cfgpu_vec_axpy cfgpu_vec_axpby cfgpu_vec_scal cfgpu_field2vector_size cfgpu_field2vector cfgpu_vector2field""".split()
 
 
 class CfgpuError(RuntimeError):
@@ -552,6 +554,56 @@ class DNS:
     def time(self): return self.lib.L.cf_dns_time(self.h)
     def dPdx(self): return self.lib.L.cf_dns_dPdx(self.h)
     def Ubulk(self): return self.lib.L.cf_dns_Ubulk(self.h)
+
+
+class DeviceVector:
+    """Device-resident state vector (cfgpu_vec): dot / norm / axpy on the GPU (nsolver's Krylov algebra)."""
+
+    def __init__(self, lib, n):
+        self.lib = lib
+        L = lib.L
+        L.cf_vec_create.restype = C.c_void_p
+        L.cf_vec_create.argtypes = [C.c_long]
+        L.cf_vec_size.restype = C.c_long
+        for n_ in ("cf_vec_free", "cf_vec_size", "cf_vec_norm"):
+            getattr(L, n_).argtypes = [C.c_void_p]
+        L.cf_vec_dot.restype = L.cf_vec_norm.restype = C.c_double
+        L.cf_vec_dot.argtypes = [C.c_void_p, C.c_void_p]
+        L.cf_vec_upload.argtypes = L.cf_vec_download.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.cf_vec_axpy.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.cf_vec_axpby.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_double]
+        L.cf_vec_scale.argtypes = [C.c_void_p, C.c_double]
+        L.cf_field2vector_dev.argtypes = L.cf_vector2field_dev.argtypes = [C.c_void_p, C.c_void_p]
+        self.h = L.cf_vec_create(n)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.L.cf_vec_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def size(self): return self.lib.L.cf_vec_size(self.h)
+
+    def set(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.size()
+        self.lib.L.cf_vec_upload(self.h, _dp(x))
+        return self
+
+    def get(self):
+        x = np.empty(self.size())
+        self.lib.L.cf_vec_download(self.h, _dp(x))
+        return x
+
+    def dot(self, o): return self.lib.L.cf_vec_dot(self.h, o.h)
+    def norm(self): return self.lib.L.cf_vec_norm(self.h)
+    def axpy(self, a, x): self.lib.L.cf_vec_axpy(self.h, a, x.h)
+    def axpby(self, a, x, b): self.lib.L.cf_vec_axpby(self.h, a, x.h, b)
+    def scale(self, s): self.lib.L.cf_vec_scale(self.h, s)
+    def from_field(self, u): self.lib.L.cf_field2vector_dev(u.h, self.h); return self
+    def to_field(self, u): self.lib.L.cf_vector2field_dev(self.h, u.h); return u
 
 
 def nonlinear(u, flags):

@@ -702,6 +702,15 @@ int cfgpu_field_device_ptr(cfgpu_field f, double** d, long long* n) { CF_TRY(fie
 
 int cfgpu_field_axpby(cfgpu_field y, double a, cfgpu_field x, double b, cfgpu_field z) {
     CF_ARG(same_shape(y, x) && (!z || same_shape(y, z)), "cfgpu_field_axpby: shape mismatch");
+    // Operands that live tile-major and are zero outside their box (nonlinear terms, linear terms: what the RK / CNAB
+    // steppers combine) are combined in place in that layout: no conversion, only the retained modes are touched.
+    auto tiled0 = [](cfgpu_field f) { return f->layout == 1 && f->tile_outside_zero; };
+    if (tiled0(x) && (!z || (tiled0(z) && z->tg.same(x->tg))) && y != x && y != z) {
+        CF_TRY(field_tile(y, x->tg));  // no-op if y is already in this layout; a never-written y becomes an all-zero tile field
+        const long n = (long)(x->tg.ntiles() * x->tile_stride());
+        CF_TRY(axpby_launch(y->dtile, a, x->dtile, b, z ? z->dtile : nullptr, n, y->ctx->stream));
+        return 0;
+    }
     CF_TRY(field_serial(y)); CF_TRY(field_serial(x)); if (z) CF_TRY(field_serial(z));
     CF_TRY(axpby_launch(y->dser, a, x->dser, b, z ? z->dser : nullptr, (long)y->n, y->ctx->stream));
     auto mrg = [](int p, int q) { return (p < 0 || q < 0) ? -1 : (p > q ? p : q); };
@@ -710,7 +719,13 @@ int cfgpu_field_axpby(cfgpu_field y, double a, cfgpu_field x, double b, cfgpu_fi
     return 0;
 }
 int cfgpu_field_scale(cfgpu_field y, double s) {
-    CF_TRY(field_serial(y));
+    if (y->layout == 1) {
+        // the box lives in the tile buffer; whatever the field holds outside it is in the serial buffer
+        CF_TRY(scale_launch(y->dtile, s, (long)(y->tg.ntiles() * y->tile_stride()), y->ctx->stream));
+        if (!y->tile_outside_zero && y->dser) CF_TRY(scale_launch(y->dser, s, (long)y->n, y->ctx->stream));
+        return 0;
+    }
+    if (!y->dser) return 0;  // never written: all zero
     CF_TRY(scale_launch(y->dser, s, (long)y->n, y->ctx->stream));
     return 0;
 }

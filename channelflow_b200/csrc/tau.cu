@@ -354,17 +354,18 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_factor_kernel(const Tau
     inv[par] = 1.0 - A_lo(n1, Nb, lam) * b1;  // diag(0) == band(0)
 }
 
+constexpr int TAU_PROF_THREADS = 128;  // 4 modes per CTA: small CTAs, three or four per SM (the scans are latency bound)
 template <int E>
-__global__ void __launch_bounds__(TAU_THREADS) tau_profiles_kernel(const TauData td) {
+__global__ void __launch_bounds__(TAU_PROF_THREADS, E <= 10 ? 3 : 1) tau_profiles_kernel(const TauData td) {
     const int N = td.N, Nb = N - 1, TM = td.TM;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TAU_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TAU_PROF_THREADS / 32;
     const int NP = tau_col_pitch(N, E);
     double* bt = dyn_smem<double>();  // B rows [3][NP], skewed like the solve kernel's
-    for (int i = tid; i < 3 * NP; i += TAU_THREADS) bt[i] = 0.0;
+    for (int i = tid; i < 3 * NP; i += TAU_PROF_THREADS) bt[i] = 0.0;
     __syncthreads();
     {
         const double* src = td.btab();
-        for (int i = tid; i < 3 * N; i += TAU_THREADS) {
+        for (int i = tid; i < 3 * N; i += TAU_PROF_THREADS) {
             const int r = i >= 2 * N ? 2 : (i >= N ? 1 : 0), n = i - r * N;
             bt[r * NP + col_addr<E>(n)] = src[i];
         }
@@ -957,8 +958,8 @@ template <int E>
 static int profiles_launch_e(const TauData& td, cudaStream_t stream) {
     const size_t smem = (size_t)3 * tau_col_pitch(td.N, E) * sizeof(double);
     const long slots = (long)td.ntiles * td.TM;
-    dim3 grid((unsigned)((slots + TAU_THREADS / 32 - 1) / (TAU_THREADS / 32)));
-    CF_LAUNCH(tau_profiles_kernel<E>, grid, dim3(TAU_THREADS), smem, stream, td);
+    dim3 grid((unsigned)((slots + TAU_PROF_THREADS / 32 - 1) / (TAU_PROF_THREADS / 32)));
+    CF_LAUNCH(tau_profiles_kernel<E>, grid, dim3(TAU_PROF_THREADS), smem, stream, td);
     CF_KERNEL_CHECK();
     return 0;
 }

@@ -24,8 +24,8 @@ constexpr bool YG_SPLIT_DEFAULT = false;  // set from the A/B measurement (profi
 // BN columns per CTA, WN warps along the columns (4 warps along the rows): <64,2> is one 256-thread CTA per SM, <32,1> two
 // independent 128-thread CTAs per SM with the same 32 x 32 warp tile -- one CTA's staging and epilogue overlap the other's
 // DMMA loop.
-template <int BN, int WN>
-__global__ void __launch_bounds__(128 * WN, WN == 1 ? 2 : 1) ygemm_kernel(const YGemmParams p) {
+template <int BN, int WN, int MINB>
+__global__ void __launch_bounds__(128 * WN, MINB) ygemm_kernel(const YGemmParams p) {
     constexpr int YG_THREADS = 128 * WN;
     constexpr int LD = BN + 4;
     constexpr int NT = BN / (8 * WN);   // 8-column n-tiles per warp
@@ -274,11 +274,11 @@ __global__ void __launch_bounds__(128 * WN, WN == 1 ? 2 : 1) ygemm_kernel(const 
     }
 }
 
-template <int BN, int WN = 2>
+template <int BN, int WN = 2, int MINB = 1>
 static int launch_bn(const YGemmParams& p, cudaStream_t stream) {
     constexpr int YG_THREADS = 128 * WN;
     const size_t smem = (size_t)(p.two_inputs ? 2 : 1) * (p.K1p + p.K2p) * (BN + 4) * sizeof(double) + 2 * BN * sizeof(long);
-    auto kfn = ygemm_kernel<BN, WN>;
+    auto kfn = ygemm_kernel<BN, WN, MINB>;
     static size_t configured = 0;
     if (smem > configured) {
         CF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -309,7 +309,8 @@ int ygemm_launch(const YGemmParams& p0, cudaStream_t stream) {
     // two half-width CTAs per SM when one full-width tile would own the SM alone (long profiles): CF_YG_SPLIT=0/1 overrides
     static const int split = getenv("CF_YG_SPLIT") ? atoi(getenv("CF_YG_SPLIT")) : -1;
     const bool one_per_sm = rows * 68 * 8 + 1024 > 110 * 1024;
-    if (rows * 36 * 8 + 512 <= 110 * 1024 && (split == 1 || (split < 0 && one_per_sm && YG_SPLIT_DEFAULT))) return launch_bn<32, 1>(p, stream);
+    if (rows * 36 * 8 + 512 <= 110 * 1024 && (split == 1 || (split < 0 && one_per_sm && YG_SPLIT_DEFAULT))) return launch_bn<32, 1, 2>(p, stream);
+    if (rows * 36 * 8 + 512 <= 110 * 1024 && split == 2) return launch_bn<32, 2, 2>(p, stream);  // 16 warps per SM, 32 x 16 warp tiles
     if (rows * 68 * 8 + 1024 <= limit) return launch_bn<64>(p, stream);
     if (rows * 36 * 8 + 512 <= limit) return launch_bn<32>(p, stream);
     if (rows * 20 * 8 + 256 <= limit) return launch_bn<16>(p, stream);

@@ -79,6 +79,20 @@ void cf_field_axpby(void* y, double a, void* x, double b, void* z) {
 }
 void cf_field_scale(void* y, double s) { *(FlowField*)y *= s; }
 
+// ---- device state vectors (DeviceVector over cfgpu_vec)
+void* cf_vec_create(long n) { return new DeviceVector(n); }
+void cf_vec_free(void* v) { delete (DeviceVector*)v; }
+long cf_vec_size(void* v) { return ((DeviceVector*)v)->size(); }
+void cf_vec_upload(void* v, const double* x) { ((DeviceVector*)v)->upload(x); }
+void cf_vec_download(void* v, double* x) { ((DeviceVector*)v)->download(x); }
+double cf_vec_dot(void* a, void* b) { return ((DeviceVector*)a)->dot(*(DeviceVector*)b); }
+double cf_vec_norm(void* a) { return ((DeviceVector*)a)->norm(); }
+void cf_vec_axpy(void* y, double a, void* x) { ((DeviceVector*)y)->axpy(a, *(DeviceVector*)x); }
+void cf_vec_axpby(void* y, double a, void* x, double b) { ((DeviceVector*)y)->axpby(a, *(DeviceVector*)x, b); }
+void cf_vec_scale(void* y, double s) { ((DeviceVector*)y)->scale(s); }
+void cf_field2vector_dev(void* u, void* v) { field2vector(*(FlowField*)u, *(DeviceVector*)v); }
+void cf_vector2field_dev(void* v, void* u) { vector2field(*(DeviceVector*)v, *(FlowField*)u); }
+
 void cf_nonlinear(void* uh, void* fh, const CfFlags* rf) {
     DNSFlags flags = to_flags(rf);
     FlowField& u = *(FlowField*)uh;

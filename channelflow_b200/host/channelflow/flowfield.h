@@ -176,6 +176,7 @@ class FlowField {
     void upload_from(const Real* data) const;
     cfgpu_field device() const;          // device copy is current on return; host mirror stays valid
     cfgpu_field device_mut();            // as above, and the host mirror is invalidated
+    cfgpu_field device_overwrite();      // the caller overwrites the whole field on the device: nothing is uploaded first
     void raw_upload(const Real* data);   // whole array, reference layout
     void raw_download(Real* data) const;
 
@@ -206,6 +207,34 @@ FlowField operator*(const Real a, const FlowField& w);
 FlowField operator+(const FlowField& v, const FlowField& w);
 FlowField operator-(const FlowField& v, const FlowField& w);
 void swap(FlowField& f, FlowField& g);
+
+// Device-resident vector of reals (cfgpu_vec): the state vectors of the Newton-Krylov / Arnoldi iterations stay in HBM;
+// dot / norm / axpy replace the Eigen VectorXd algebra of nsolver (cfbasics.h:711-780, gmres.cpp:37-102).
+class DeviceVector {
+   public:
+    DeviceVector() {}
+    explicit DeviceVector(long n);
+    DeviceVector(const DeviceVector& o);
+    DeviceVector& operator=(const DeviceVector& o);
+    ~DeviceVector();
+    void resize(long n);  // contents are zeroed
+    long size() const { return n_; }
+    void setToZero();
+    void upload(const Real* x);
+    void download(Real* x) const;
+    Real dot(const DeviceVector& o) const;
+    Real norm() const;
+    void axpy(Real a, const DeviceVector& x);            // this += a x
+    void axpby(Real a, const DeviceVector& x, Real b);   // this = a x + b this
+    void scale(Real s);
+    cfgpu_vec handle() const { return v_; }
+
+   private:
+    cfgpu_vec v_ = nullptr;
+    long n_ = 0;
+};
+void field2vector(const FlowField& u, DeviceVector& x);
+void vector2field(const DeviceVector& x, FlowField& u);
 
 // The field2vector and vector2field functions assume zero divergence and no-slip BCs (reference flowfield.h:617-621).
 // Raw-pointer forms plus adaptors for any vector type with size()/resize()/data() (Eigen::VectorXd, std::vector).

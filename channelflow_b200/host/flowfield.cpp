@@ -114,6 +114,13 @@ cfgpu_field FlowField::device() const {
     push_state();
     return dev_;
 }
+cfgpu_field FlowField::device_overwrite() {
+    if (!dev_) cferror("FlowField: operation on an empty field");
+    dev_valid_ = true;
+    host_valid_ = false;
+    push_state();
+    return dev_;
+}
 cfgpu_field FlowField::device_mut() {
     cfgpu_field d = device();
     host_valid_ = false;

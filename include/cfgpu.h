@@ -22,6 +22,7 @@ extern "C" {
 typedef struct cfgpu_ctx_s* cfgpu_ctx;
 typedef struct cfgpu_field_s* cfgpu_field;
 typedef struct cfgpu_nse_s* cfgpu_nse;
+typedef struct cfgpu_vec_s* cfgpu_vec;
 
 enum { CFGPU_PHYSICAL = 0, CFGPU_SPECTRAL = 1 }; /* cfbasics/mathdefs.h: enum fieldstate */
 
@@ -158,6 +159,28 @@ int cfgpu_nse_linear(cfgpu_nse nse, cfgpu_field u, cfgpu_field q, cfgpu_field L)
 int cfgpu_nse_cflfactor(cfgpu_nse nse, cfgpu_field u, double* out_h);
 /* dPdxAct_/dPdzAct_ computed by the bulk-velocity-constrained solve (nse.cpp:536) */
 int cfgpu_nse_get_dPd(cfgpu_nse nse, double* dPdx_h, double* dPdz_h);
+
+/* ---------------------------------------------------------------- state vectors of nsolver (device resident)
+ * field2vector / vector2field (channelflow/flowfield.cpp:4448-4760 with fixDiri / fixDiriMean, utilfuncs.cpp:712-765): the
+ * map between a divergence-free, no-slip velocity field and the vector of its independent real coefficients, one warp
+ * per Fourier mode; the vector stays in HBM.  cfgpu_vec_dot / nrm2 / axpy / scal replace the Eigen VectorXd algebra of
+ * the Krylov iterations (cfbasics/cfbasics.h:711-780 L2IP / L2Norm, nsolver/gmres.cpp:37-102 modified Gram-Schmidt,
+ * nsolver/arnoldi.cpp).  Vectors are not distributed: one GPU per vector (replicas / one shot per GPU). */
+int cfgpu_vec_create(cfgpu_ctx ctx, long long n, cfgpu_vec* out);
+int cfgpu_vec_destroy(cfgpu_vec v);
+int cfgpu_vec_size(cfgpu_vec v, long long* n);
+int cfgpu_vec_upload(cfgpu_vec v, const double* x_h);
+int cfgpu_vec_download(cfgpu_vec v, double* x_h);
+int cfgpu_vec_copy(cfgpu_vec dst, cfgpu_vec src);
+int cfgpu_vec_zero(cfgpu_vec v);
+int cfgpu_vec_dot(cfgpu_vec x, cfgpu_vec y, double* out_h);
+int cfgpu_vec_nrm2(cfgpu_vec x, double* out_h);
+int cfgpu_vec_axpy(cfgpu_vec y, double a, cfgpu_vec x);           /* y += a x */
+int cfgpu_vec_axpby(cfgpu_vec y, double a, cfgpu_vec x, double b); /* y = a x + b y */
+int cfgpu_vec_scal(cfgpu_vec y, double s);
+int cfgpu_field2vector_size(cfgpu_field u, long long* n);         /* flowfield.cpp:4448-4479 */
+int cfgpu_field2vector(cfgpu_field u, cfgpu_vec x);               /* flowfield.cpp:4481-4563 */
+int cfgpu_vector2field(cfgpu_vec x, cfgpu_field u);               /* flowfield.cpp:4565-4752 */
 
 #ifdef __cplusplus
 }

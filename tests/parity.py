@@ -182,6 +182,33 @@ def golden_pair(lib, nsteps=440):
     return out, ur, u2
 
 
+def device_vectors(lib, cfg):
+    """Device state vectors: field2vector / vector2field kernels against the reference's host loops, and the Krylov
+    algebra (dot / norm / axpy / axpby / scale) against NumPy."""
+    ur = ref_random(cfg, 9)
+    ug = to_gpu(lib, ur)
+    xr = ur.to_vector()
+    n = xr.size
+    x = cf.DeviceVector(lib, n).from_field(ug)
+    out = {"pack_max_abs": float(np.abs(x.get() - xr).max())}
+    rng = np.random.default_rng(3)
+    y_h = xr + 1e-3 * rng.standard_normal(n)
+    y = cf.DeviceVector(lib, n).set(y_h)
+    vr = ur.like().from_vector(y_h)
+    vg = y.to_field(ug.like())
+    out["unpack_rel"] = rel_l2(vg.get(), vr.data)
+    out["dot_rel"] = abs(x.dot(y) - float(xr @ y_h)) / abs(float(xr @ y_h))
+    out["norm_rel"] = abs(y.norm() - float(np.linalg.norm(y_h))) / float(np.linalg.norm(y_h))
+    y.axpy(-0.75, x)
+    out["axpy_max_abs"] = float(np.abs(y.get() - (y_h - 0.75 * xr)).max())
+    y.axpby(2.0, x, 0.5)
+    ref = 2.0 * xr + 0.5 * (y_h - 0.75 * xr)
+    out["axpby_max_abs"] = float(np.abs(y.get() - ref).max())
+    y.scale(-3.0)
+    out["scale_max_abs"] = float(np.abs(y.get() + 3.0 * ref).max())
+    return out
+
+
 def smoke(cf_module=None):
     """One small DNS step of the hot path on cuda:0, checked against the oracle (used by __graft_entry__.smoke)."""
     lib = gpu_lib()

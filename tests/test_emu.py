@@ -181,6 +181,15 @@ def test_laminar_profiles(lib):
         assert np.abs(a - b).max() < 1e-14, kw
 
 
+def test_device_state_vectors(lib):
+    """cfgpu_field2vector / vector2field kernels bit-identical (pack) / 1e-14 (unpack) to the reference's loops
+    (flowfield.cpp:4481-4752); device dot / norm / axpy against NumPy."""
+    r = parity.device_vectors(lib, SMALL)
+    assert r["pack_max_abs"] == 0.0 and r["unpack_rel"] < 1e-14, r
+    assert r["dot_rel"] < 1e-13 and r["norm_rel"] < 1e-14, r
+    assert max(r["axpy_max_abs"], r["axpby_max_abs"], r["scale_max_abs"]) < 1e-15, r
+
+
 def test_field2vector_roundtrip(lib):
     """field2vector / vector2field against the reference's (flowfield.cpp:4448-4752): same vector, same rebuilt field."""
     ur = parity.ref_random(SMALL, 9)
