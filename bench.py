@@ -166,8 +166,8 @@ def box_rows(arr, Nx, Nz, x0, x1):
 def small_case_parity(cf, lib, rank, world):
     """The 48x49x32 plane-Couette case of tests/mp_slab_worker.py, 4 SBDF3 steps on all ranks, against the committed
     fixture tests/golden/mp_slab_48x49x32.npz (computed by the compiled reference, tests/golden/make_mp_fixture.py):
-    once over the peer-memory exchange (stores over NVLink inside the kernels) and once over the staged NCCL
-    send/recv exchange (CFGPU_NO_PEER=1).  Relative L2 error of the all-gathered field, CFL, L2Norm."""
+    over the three exchanges: peer-memory push kernels with device-side flags (the default), stores over NVLink
+    fused into the transform kernels (CFGPU_PEER_MODE=fused), staged NCCL send/recv (CFGPU_NO_PEER=1).  Relative L2 error of the all-gathered field, CFL, L2Norm."""
     fx = np.load(os.path.join(ROOT, "tests", "golden", "mp_slab_48x49x32.npz"))
     Nx, Ny, Nz = int(fx["Nx"]), int(fx["Ny"]), int(fx["Nz"])
     Kx, Kz = Nx // 3 - 1, Nz // 3 - 1
@@ -178,9 +178,11 @@ def small_case_parity(cf, lib, rank, world):
     rows = [(m if m <= Kx else m - (2 * Kx + 1)) % Nx for m in range(2 * Kx + 1)]
     u0[:, :, rows, :Kz + 1] = fx["u0"]
     out = {}
-    for leg in ("peer", "staged"):
+    for leg in ("peer_push", "peer_fused", "staged"):
         if leg == "staged":
             os.environ["CFGPU_NO_PEER"] = "1"
+        if leg == "peer_fused":
+            os.environ["CFGPU_PEER_MODE"] = "fused"
         try:
             ug = cf.FlowField(lib, Nx, Ny, Nz, 3, float(fx["Lx"]), float(fx["Lz"]), float(fx["a"]), float(fx["b"])).set(u0.view(np.float64), padded=True)
             dns = cf.DNS(ug, cf.make_flags(**flags))
@@ -199,6 +201,8 @@ def small_case_parity(cf, lib, rank, world):
             del dns, ug, u1
         finally:
             os.environ.pop("CFGPU_NO_PEER", None)
+            if leg == "peer_fused":
+                os.environ.pop("CFGPU_PEER_MODE", None)
     return out
 
 

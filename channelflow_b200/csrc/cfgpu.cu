@@ -305,7 +305,11 @@ int cfgpu_init(int device, cfgpu_ctx* out) {
     CF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CF_CUDA(cudaEventCreate(&ctx->ev0));
     CF_CUDA(cudaEventCreate(&ctx->ev1));
-    CF_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    {   // the exchange stream outranks the compute stream: its few CTAs are scheduled ahead of the queued transform CTAs
+        int lo = 0, hi = 0;
+        CF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CF_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+    }
     for (int i = 0; i < 4; ++i) {
         CF_CUDA(cudaEventCreateWithFlags(&ctx->ev_cmp[i], cudaEventDisableTiming));
         CF_CUDA(cudaEventCreateWithFlags(&ctx->ev_com[i], cudaEventDisableTiming));
@@ -331,6 +335,8 @@ int cfgpu_finalize(cfgpu_ctx ctx) {
     if (ctx->peerP_gen) comm_close_peers(ctx->comm, ctx->peerP);
     if (ctx->peerS_gen) comm_close_peers(ctx->comm, ctx->peerS);
     if (ctx->ws_S.ptr) cudaFree(ctx->ws_S.ptr);
+    if (ctx->peerF_gen) comm_close_peers(ctx->comm, ctx->peerF);
+    if (ctx->ws_F.ptr) cudaFree(ctx->ws_F.ptr);
     comm_destroy(ctx->comm);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);

@@ -74,6 +74,11 @@ struct cfgpu_ctx_s {
     void* peerP[cfgpu::COMM_MAXRANKS] = {nullptr};
     void* peerS[cfgpu::COMM_MAXRANKS] = {nullptr};
     unsigned long long peerP_gen = 0, peerS_gen = 0;  // generation of ws_P / ws_S the mappings belong to (0: none)
+    // push all-to-all (comm.cuh): flag words [PUSH_SLOTS][COMM_MAXRANKS], a completion counter and an error word per rank
+    cfgpu::Workspace ws_F;
+    void* peerF[cfgpu::COMM_MAXRANKS] = {nullptr};
+    unsigned long long peerF_gen = 0;
+    unsigned long long push_seq[cfgpu::PUSH_SLOTS] = {0};
     std::vector<void*> graphs;  // cudaGraphExec_t
     bool capturing = false;
     // stage profiler

@@ -82,6 +82,61 @@ static int slab_exchange(cfgpu_nse nse, int nf, int dir, const int* fields, int 
     return comm_exchange(cm, msgs.data(), (int)msgs.size(), stream);
 }
 
+// How the all-to-all travels when the ranks can map each other's buffers (CFGPU_PEER_MODE):
+//   push  (default) the transform kernels write locally at full speed; per velocity component a push kernel on a
+//         high-priority stream copies the blocks into the receivers' buffers while the next component is being transformed,
+//         completion is signalled through device-side flags (comm.cuh) -- no NCCL call, no barrier
+//   fused the y-GEMM epilogue / forward x-pass store every row straight into the owning rank's buffer, NCCL barriers
+//         between producer and consumer (the round-1 path: the producers become NVLink-bound, nothing overlaps them)
+enum { PEER_PUSH = 0, PEER_FUSED = 1 };
+static int peer_mode() {  // read per call (like CFGPU_NO_PEER): all ranks must of course agree
+    const char* e = getenv("CFGPU_PEER_MODE");
+    return (e && !strcmp(e, "fused")) ? PEER_FUSED : PEER_PUSH;
+}
+static unsigned long long* flag_words(void* base) { return reinterpret_cast<unsigned long long*>(base); }
+static unsigned int* flag_counter(void* base) { return reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(base) + 2048); }
+static int* flag_error(void* base) { return reinterpret_cast<int*>(reinterpret_cast<char*>(base) + 2048 + 64); }
+
+// push the blocks of the selected fields to every rank (same geometry as slab_exchange) and publish completion in `slot`
+static int slab_push(cfgpu_nse nse, int nf, int dir, const int* fields, int nsel, int slot, cudaStream_t stream) {
+    cfgpu_ctx ctx = nse->ctx;
+    Comm& cm = ctx->comm;
+    const int nmx = 2 * nse->Kx + 1, nkz = nse->Kz + 1;
+    const int nxl = nse->x1 - nse->x0, nyl = nse->y1 - nse->y0;
+    PushParams pp;
+    memset(&pp, 0, sizeof pp);
+    const double2* P = reinterpret_cast<const double2*>(ctx->ws_P.ptr);
+    const double2* S = reinterpret_cast<const double2*>(ctx->ws_S.ptr);
+    for (int r = 0; r < cm.nranks; ++r) {
+        int xa, xb, ya, yb;
+        part_range(nmx, cm.nranks, r, xa, xb);
+        part_range(nse->Ny, cm.nranks, r, ya, yb);
+        for (int k = 0; k < nsel; ++k) {
+            const int f = fields[k];
+            PushMsg& m = pp.msg[pp.nmsg++];
+            if (dir == 0) {  // my rows of r's planes: P -> r's staging S_r[me][f]
+                m.src = P + ((size_t)f * nse->Ny + ya) * nxl * nkz;
+                m.dst = reinterpret_cast<double2*>(ctx->peerS[r]) + (size_t)nkz * ((size_t)nf * (yb - ya) * nse->x0 + (size_t)f * (yb - ya) * nxl);
+                m.n = (long)(yb - ya) * nxl * nkz;
+            } else {         // r's rows of my planes: S[r][f] -> r's pencils P_r[f][my planes]
+                m.src = S + (size_t)nkz * ((size_t)nf * nyl * xa + (size_t)f * nyl * (xb - xa));
+                m.dst = reinterpret_cast<double2*>(ctx->peerP[r]) + ((size_t)f * nse->Ny + nse->y0) * (xb - xa) * nkz;
+                m.n = (long)nyl * (xb - xa) * nkz;
+            }
+        }
+    }
+    for (int r = 0; r < cm.nranks; ++r) pp.flags[r] = flag_words(ctx->peerF[r]);
+    pp.nranks = cm.nranks; pp.rank = cm.rank; pp.slot = slot;
+    pp.seq = ++ctx->push_seq[slot];
+    pp.done_counter = flag_counter(ctx->ws_F.ptr);
+    static const int nctas = getenv("CF_PUSH_CTAS") ? atoi(getenv("CF_PUSH_CTAS")) : 24;
+    return slab_push_launch(pp, nctas, stream);
+}
+static int slab_wait(cfgpu_nse nse, int slot, cudaStream_t stream) {
+    cfgpu_ctx ctx = nse->ctx;
+    return slab_wait_launch(flag_words(ctx->ws_F.ptr), slot, ctx->comm.nranks, ctx->push_seq[slot], flag_error(ctx->ws_F.ptr), stream);
+}
+
 // Peer-memory path (NCCL backend): map every rank's pencil (P) and staging (S) buffers, and build the tables that send
 // each output row of the inverse y-GEMM to the rank owning that y plane.
 // A peer-mapped buffer is only ever replaced collectively: every rank has finished with the old one (barrier), all
@@ -115,6 +170,14 @@ static int peer_workspace(cfgpu_ctx ctx, Workspace& w, size_t bytes, void** peer
 static int ensure_peers(cfgpu_nse nse, size_t Pbytes, size_t Sbytes) {
     cfgpu_ctx ctx = nse->ctx;
     Comm& cm = ctx->comm;
+    if (!ctx->peerF_gen) {
+        CF_TRY(peer_workspace(ctx, ctx->ws_F, 4096, ctx->peerF, ctx->peerF_gen));
+        if (cm.peer_failed) return 0;
+        CF_CUDA(cudaMemsetAsync(ctx->ws_F.ptr, 0, 4096, ctx->stream));
+        for (int k = 0; k < PUSH_SLOTS; ++k) ctx->push_seq[k] = 0;
+        CF_TRY(comm_barrier(cm, ctx->stream));  // nobody publishes a flag before everybody has cleared its buffer
+        CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     CF_TRY(peer_workspace(ctx, ctx->ws_P, Pbytes, ctx->peerP, ctx->peerP_gen));
     if (cm.peer_failed) return 0;
     CF_TRY(peer_workspace(ctx, ctx->ws_S, Sbytes, ctx->peerS, ctx->peerS_gen));
@@ -231,7 +294,8 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         p.job[0].nmat = 2; p.job[0].out[1] = P + 3 * Pf;  // du/dy
         p.job[2].nmat = 2; p.job[2].out[1] = P + 4 * Pf;  // dw/dy
     }
-    if (peer) {
+    const bool fused = peer && peer_mode() == PEER_FUSED;
+    if (fused) {
         // every output row goes straight to the staging buffer of the rank that owns its y plane (stores over NVLink);
         // barriers: the consumers are done with the previous contents / all rows have arrived
         double** tab = nse->d_rows[with_derivs ? 0 : 1];
@@ -256,8 +320,11 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
             CF_CUDA(cudaEventRecord(ctx->ev_cmp[c], ctx->stream));
             CF_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_cmp[c], 0));
             const int fl[2] = {c, c == 0 ? 3 : 4};
-            CF_TRY(slab_exchange(nse, nfP, 0, fl, (with_derivs && c != 1) ? 2 : 1, ctx->comm_stream));
-            CF_CUDA(cudaEventRecord(ctx->ev_com[c], ctx->comm_stream));
+            if (peer) CF_TRY(slab_push(nse, nfP, 0, fl, (with_derivs && c != 1) ? 2 : 1, c, ctx->comm_stream));
+            else {
+                CF_TRY(slab_exchange(nse, nfP, 0, fl, (with_derivs && c != 1) ? 2 : 1, ctx->comm_stream));
+                CF_CUDA(cudaEventRecord(ctx->ev_com[c], ctx->comm_stream));
+            }
         }
     }
 
@@ -283,7 +350,7 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         xp.nfields = 3;
         for (int i = 0; i < 3; ++i) { xp.src[i] = i; xp.opa[i] = 0; xp.srcb[i] = -1; xp.opb[i] = 0; xp.fsel[i] = i; }
     }
-    if (!multi || peer) {
+    if (!multi || fused) {
         StageTimer _t(ctx, 1);
         CF_TRY(xpass_inverse_launch(xp, ctx->stream));
     } else {
@@ -291,7 +358,8 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         // w (+dw/dy) -> {w, omega_x, omega_y}
         const int sel[3][3] = {{0, -1, -1}, {1, 5, -1}, {2, 3, 4}};
         for (int c = 0; c < 3; ++c) {
-            CF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_com[c], 0));
+            if (peer) { StageTimer _t(ctx, 8); CF_TRY(slab_wait(nse, c, ctx->stream)); }
+            else CF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_com[c], 0));
             XPassParams xc = xp;
             xc.nfields = 0;
             if (with_derivs) { for (int k = 0; k < 3; ++k) if (sel[c][k] >= 0) xc.fsel[xc.nfields++] = sel[c][k]; }
@@ -680,7 +748,8 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     fill_xsplit(nse, xp, 3);
     for (int i = 0; i < 3; ++i) { xp.fsel[i] = i; xp.src[i] = i; xp.srcb[i] = -1; }
     const bool peer = multi && comm_peer_capable(ctx->comm);
-    if (peer) {
+    const bool fused = peer && peer_mode() == PEER_FUSED;
+    if (fused) {
         // each kx row is stored straight into its owner's pencil buffer; one barrier before the y-GEMM reads it
         xp.peer_direct = 1;
         for (int r = 0; r < ctx->comm.nranks; ++r) xp.peer_out[r] = reinterpret_cast<double2*>(ctx->peerP[r]);
@@ -697,8 +766,11 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
             { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xc, ctx->stream)); }
             CF_CUDA(cudaEventRecord(ctx->ev_cmp[c], ctx->stream));
             CF_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_cmp[c], 0));
-            CF_TRY(slab_exchange(nse, 3, 1, &c, 1, ctx->comm_stream));
-            CF_CUDA(cudaEventRecord(ctx->ev_com[c], ctx->comm_stream));
+            if (peer) CF_TRY(slab_push(nse, 3, 1, &c, 1, 3 + c, ctx->comm_stream));
+            else {
+                CF_TRY(slab_exchange(nse, 3, 1, &c, 1, ctx->comm_stream));
+                CF_CUDA(cudaEventRecord(ctx->ev_com[c], ctx->comm_stream));
+            }
         }
     }
 
@@ -727,12 +799,13 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         p.job[i].out[0] = fa.base + i * fa.compstride;
         p.job[i].nmat = 1; p.job[i].mat0 = 0;
     }
-    if (!multi || peer) {
+    if (!multi || fused) {
         StageTimer _t(ctx, 4);
         CF_TRY(ygemm_launch(p, ctx->stream));
     } else {
         for (int c = 0; c < 3; ++c) {
-            CF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_com[c], 0));
+            if (peer) { StageTimer _t(ctx, 8); CF_TRY(slab_wait(nse, 3 + c, ctx->stream)); }
+            else CF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_com[c], 0));
             YGemmParams pc = p;
             pc.njobs = 1;
             pc.job[0] = p.job[c];

@@ -240,6 +240,106 @@ int comm_barrier(Comm& c, cudaStream_t stream) {
     return comm_allreduce(c, c.d_bar, 1, 1, stream);
 }
 
+// ------------------------------------------------------------------------------------------------ push all-to-all
+namespace {
+constexpr int PUSH_THREADS = 256;
+constexpr long PUSH_CHUNK = 4096;  // complex elements per work item (64 KB)
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+#ifdef CF_EMU
+    *p = v;
+#else
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+#ifdef CF_EMU
+    return *p;
+#else
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+#ifdef CF_EMU
+    return 0;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+
+__global__ void __launch_bounds__(PUSH_THREADS) slab_push_kernel(const PushParams p) {
+    // work items = 64 KB chunks of all messages, dealt round-robin to the CTAs
+    long item = blockIdx.x;
+    for (int m = 0; m < p.nmsg; ++m) {
+        const long nchunks = (p.msg[m].n + PUSH_CHUNK - 1) / PUSH_CHUNK;
+        const double2* __restrict__ src = p.msg[m].src;
+        double2* __restrict__ dst = p.msg[m].dst;
+        for (; item < nchunks; item += gridDim.x) {
+            const long i0 = item * PUSH_CHUNK;
+            const long i1 = i0 + PUSH_CHUNK < p.msg[m].n ? i0 + PUSH_CHUNK : p.msg[m].n;
+            // four 16-byte elements per thread in flight
+            for (long i = i0 + threadIdx.x; i < i1; i += 4 * PUSH_THREADS) {
+                double2 v[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    if (i + h * PUSH_THREADS < i1) v[h] = src[i + h * PUSH_THREADS];
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    if (i + h * PUSH_THREADS < i1) dst[i + h * PUSH_THREADS] = v[h];
+            }
+        }
+        item -= nchunks;
+    }
+    // completion: every CTA makes its stores visible system-wide, the last one publishes the sequence number
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(p.done_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *p.done_counter = 0;
+            __threadfence_system();
+            for (int r = 0; r < p.nranks; ++r) st_release_sys(p.flags[r] + (size_t)p.slot * COMM_MAXRANKS + p.rank, p.seq);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) slab_wait_kernel(const unsigned long long* flags, int slot, int nranks, unsigned long long seq, int* err) {
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        const unsigned long long* w = flags + (size_t)slot * COMM_MAXRANKS + r;
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(w) < seq) {
+            if (global_ns() - t0 > 20000000000ull) {  // 20 s: a peer died or the call sequences diverged
+                *err = 1;
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+}
+}  // namespace
+
+int slab_push_launch(const PushParams& p, int nctas, cudaStream_t stream) {
+    if (p.nmsg < 0 || p.nmsg > PUSH_MAXMSG || p.slot < 0 || p.slot >= PUSH_SLOTS) {
+        set_last_error("slab_push: bad message count / slot");
+        return 1;
+    }
+    if (nctas < 1) nctas = 1;
+    CF_LAUNCH(slab_push_kernel, dim3(nctas), dim3(PUSH_THREADS), 0, stream, p);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+int slab_wait_launch(const unsigned long long* myflags, int slot, int nranks, unsigned long long seq, int* err_dev, cudaStream_t stream) {
+    CF_LAUNCH(slab_wait_kernel, dim3(1), dim3(32), 0, stream, myflags, slot, nranks, seq, err_dev);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
 int comm_allreduce(Comm& c, double* dev, int n, int op, cudaStream_t stream) {
     if (c.nranks == 1) return 0;
     if (c.ext_allreduce) {

@@ -60,4 +60,30 @@ int comm_close_peers(Comm& c, void** peers);
 // all ranks have executed everything enqueued on `stream` before this point (and their stores are visible)
 int comm_barrier(Comm& c, cudaStream_t stream);
 
+// ---- all-to-all as a push over peer memory with device-side completion flags (no NCCL call, no host round trip):
+// every rank copies its contiguous blocks straight into the other ranks' buffers (16-byte loads / stores, 512 bytes per
+// warp instruction, a few CTAs on a high-priority stream beside the transform kernels) and the last CTA to finish
+// publishes a sequence number in a flag word of every receiver (st.release.sys after __threadfence_system); the consumer
+// stream runs a one-CTA kernel that spins (ld.acquire.sys, bounded by a time-out) until all senders' flags have reached the
+// expected sequence number.  Double buffering is not needed: a rank can only reach the next exchange after it has received
+// the previous one from everybody, and everybody sends only after having consumed (cfgpu_nse.cu).
+constexpr int PUSH_MAXMSG = 2 * COMM_MAXRANKS;
+constexpr int PUSH_SLOTS = 8;
+struct PushMsg {
+    const double2* src;
+    double2* dst;
+    long n;  // complex elements
+};
+struct PushParams {
+    int nmsg;
+    PushMsg msg[PUSH_MAXMSG];
+    unsigned long long* flags[COMM_MAXRANKS];  // every rank's flag buffer as mapped here ([PUSH_SLOTS][COMM_MAXRANKS] words)
+    int nranks, rank, slot;
+    unsigned long long seq;
+    unsigned int* done_counter;  // local, zero between launches
+};
+int slab_push_launch(const PushParams& p, int nctas, cudaStream_t stream);
+// wait until flag word (slot, r) >= seq for every rank r; *err_dev is set to 1 on time-out (never hangs the GPU)
+int slab_wait_launch(const unsigned long long* myflags, int slot, int nranks, unsigned long long seq, int* err_dev, cudaStream_t stream);
+
 }  // namespace cfgpu

@@ -75,6 +75,7 @@ class RungeKuttaDNS : public DNSAlgorithm {
    protected:
     int Nsubsteps_ = 0;
     std::vector<FlowField> Qj1_, Qj_;
+    std::vector<FlowField> lt_;  // linear term work field
     std::vector<Real> A_, B_, C_;
 };
 
@@ -93,6 +94,7 @@ class CNABstyleDNS : public DNSAlgorithm {
     int Nsubsteps_ = 0;
     bool full_ = false;
     std::vector<FlowField> fj1_, fj_;
+    std::vector<FlowField> lt_;  // linear term work field
     std::vector<Real> alpha_, beta_, gamma_, zeta_;
 };
 

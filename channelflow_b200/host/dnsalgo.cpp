@@ -28,9 +28,14 @@ void DNSAlgorithm::endline() const {
         *flags_.logstream << std::endl;
 }
 
+// zero fields of the same shape and state (no device memory is touched until they are first written)
 static std::vector<FlowField> zeros_like(const std::vector<FlowField>& fields) {
-    std::vector<FlowField> z(fields);
-    for (auto& f : z) f.setToZero();
+    std::vector<FlowField> z;
+    z.reserve(fields.size());
+    for (const auto& f : fields) {
+        z.emplace_back(f.Nx(), f.Ny(), f.Nz(), f.Nd(), f.Lx(), f.Lz(), f.a(), f.b(), f.cfmpi(), f.xzstate(), f.ystate());
+        z.back().setPadded(f.padded());
+    }
     return z;
 }
 
@@ -83,7 +88,15 @@ void MultistepDNS::reset_dt(Real dt) {
 
 void MultistepDNS::advance(std::vector<FlowField>& fieldsn, int Nsteps) {
     const int J = order_ - 1;
-    fields_[0] = fieldsn;
+    // The caller's fields become history slot 0 and come back at the end: O(1) handle exchanges instead of the
+    // reference's two deep copies per call (dnsalgo.cpp:207,247); slot 0 is overwritten on entry of the next call anyway.
+    for (int l = 0; l < numfields_; ++l) {
+        if (!fields_[0][l].congruent(fieldsn[l])) fields_[0][l] = fieldsn[l];
+        else {
+            swap(fields_[0][l], fieldsn[l]);
+            fields_[0][l].setPadded(fieldsn[l].padded());  // swap exchanges the data only (as flowfield.cpp:4076-4090)
+        }
+    }
     std::vector<Real> coef(2 * order_);
     std::vector<const FlowField*> terms(2 * order_);
     for (int step = 0; step < Nsteps; ++step) {
@@ -104,7 +117,13 @@ void MultistepDNS::advance(std::vector<FlowField>& fieldsn, int Nsteps) {
         t_ += flags_.dt;
         tick();
     }
-    fieldsn = fields_[0];
+    for (int l = 0; l < numfields_; ++l) {
+        if (!fields_[0][l].congruent(fieldsn[l])) fieldsn[l] = fields_[0][l];
+        else {
+            fieldsn[l].setPadded(fields_[0][l].padded());
+            swap(fields_[0][l], fieldsn[l]);
+        }
+    }
     endline();
 }
 
@@ -126,10 +145,10 @@ bool MultistepDNS::push(const std::vector<FlowField>& fields) {
 // =============================================================================================== Runge-Kutta
 RungeKuttaDNS::RungeKuttaDNS() {}
 RungeKuttaDNS::RungeKuttaDNS(const RungeKuttaDNS& d)
-    : DNSAlgorithm(d), Nsubsteps_(d.Nsubsteps_), Qj1_(d.Qj1_), Qj_(d.Qj_), A_(d.A_), B_(d.B_), C_(d.C_) {}
+    : DNSAlgorithm(d), Nsubsteps_(d.Nsubsteps_), Qj1_(d.Qj1_), Qj_(d.Qj_), lt_(d.lt_), A_(d.A_), B_(d.B_), C_(d.C_) {}
 
 RungeKuttaDNS::RungeKuttaDNS(const std::vector<FlowField>& fields, const std::shared_ptr<NSE>& nse, const DNSFlags& flags)
-    : DNSAlgorithm(fields, nse, flags), Qj1_(zeros_like(fields)), Qj_(zeros_like(fields)) {
+    : DNSAlgorithm(fields, nse, flags), Qj1_(zeros_like(fields)), Qj_(zeros_like(fields)), lt_(zeros_like({fields[0]})) {
     if (flags_.timestepping != CNRK2) cferror("RungeKuttaDNS: flags.timestepping is a non-runge-kutta algorithm");
     order_ = 2; Nsubsteps_ = 3; Ninitsteps_ = 0;
     A_ = {0.0, -5.0 / 9.0, -153.0 / 128.0};
@@ -149,7 +168,7 @@ void RungeKuttaDNS::reset_dt(Real dt) {
     nse_->reset_lambda(lambda_t_);
 }
 void RungeKuttaDNS::advance(std::vector<FlowField>& fields, int Nsteps) {
-    std::vector<FlowField> lt(nse_->createRHS(fields));
+    std::vector<FlowField>& lt = lt_;  // work field of the linear term, allocated once (the reference re-creates it per call)
     for (int n = 0; n < Nsteps; ++n) {
         for (int j = 0; j < Nsubsteps_; ++j) {
             Qj_[0] *= A_[j];
@@ -167,11 +186,11 @@ void RungeKuttaDNS::advance(std::vector<FlowField>& fields, int Nsteps) {
 // =============================================================================================== CNAB style
 CNABstyleDNS::CNABstyleDNS() {}
 CNABstyleDNS::CNABstyleDNS(const CNABstyleDNS& d)
-    : DNSAlgorithm(d), Nsubsteps_(d.Nsubsteps_), full_(d.full_), fj1_(d.fj1_), fj_(d.fj_), alpha_(d.alpha_), beta_(d.beta_),
+    : DNSAlgorithm(d), Nsubsteps_(d.Nsubsteps_), full_(d.full_), fj1_(d.fj1_), fj_(d.fj_), lt_(d.lt_), alpha_(d.alpha_), beta_(d.beta_),
       gamma_(d.gamma_), zeta_(d.zeta_) {}
 
 CNABstyleDNS::CNABstyleDNS(const std::vector<FlowField>& fields, const std::shared_ptr<NSE>& nse, const DNSFlags& flags)
-    : DNSAlgorithm(fields, nse, flags), fj1_(zeros_like(fields)), fj_(zeros_like(fields)) {
+    : DNSAlgorithm(fields, nse, flags), fj1_(zeros_like(fields)), fj_(zeros_like(fields)), lt_(zeros_like({fields[0]})) {
     switch (flags_.timestepping) {
         case CNAB2:
             order_ = 2; Nsubsteps_ = 1; Ninitsteps_ = 1; full_ = false;
@@ -210,7 +229,7 @@ bool CNABstyleDNS::push(const std::vector<FlowField>& fields) {
     return full_;
 }
 void CNABstyleDNS::advance(std::vector<FlowField>& fields, int Nsteps) {
-    std::vector<FlowField> lt(nse_->createRHS(fields));
+    std::vector<FlowField>& lt = lt_;
     for (int n = 0; n < Nsteps; ++n) {
         for (int j = 0; j < Nsubsteps_; ++j) {
             for (int l = 0; l < numfields_; ++l) swap(fj_[l], fj1_[l]);

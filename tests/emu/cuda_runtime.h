@@ -63,6 +63,7 @@ void dmma884(double& c0, double& c1, double a, double b);
 static inline void __syncthreads() { cfemu::sync_block(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { cfemu::sync_warp(); }
 static inline void __threadfence() {}
+static inline void __threadfence_system() {}
 static inline double __shfl_sync(unsigned, double v, int src, int = 32) { return cfemu::shfl_exchange_d(v, src & 31); }
 static inline double __shfl_xor_sync(unsigned, double v, int m, int = 32) {
     return cfemu::shfl_exchange_d(v, ((int)(threadIdx.x & 31)) ^ m);
@@ -152,6 +153,8 @@ static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n)
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = 1; return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = 1; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
