@@ -137,7 +137,8 @@ struct cfgpu_nse_s {
     cfgpu::TileGeom tg;
     long* d_tilestart = nullptr; // device [ntiles]: offset of tile t of a 3-component tile-major field
     double** d_rows[2] = {nullptr, nullptr};  // peer row tables of the inverse y-GEMM outputs (5- and 3-field staging)
-    unsigned long long rows_genS = 0;  // generation of ws_S the row tables were built for
+    double** d_rows_self[2] = {nullptr, nullptr};  // push mode: own planes -> own staging, other rows -> local pencil buffer
+    unsigned long long rows_genS = 0, rows_genP = 0;  // generations of ws_S / ws_P the row tables were built for
     int rows_nranks = 0;
     cfgpu_field s_u = nullptr, s_t = nullptr;  // scratch fields of the non-rotational nonlinear terms (3 and 9 components)
 };

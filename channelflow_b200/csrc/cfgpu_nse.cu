@@ -111,6 +111,7 @@ static int slab_push(cfgpu_nse nse, int nf, int dir, const int* fields, int nsel
         int xa, xb, ya, yb;
         part_range(nmx, cm.nranks, r, xa, xb);
         part_range(nse->Ny, cm.nranks, r, ya, yb);
+        if (r == cm.rank) continue;  // the producers write this rank's own block in place (row tables / self-direct rows)
         for (int k = 0; k < nsel; ++k) {
             const int f = fields[k];
             PushMsg& m = pp.msg[pp.nmsg++];
@@ -187,7 +188,7 @@ static int ensure_peers(cfgpu_nse nse, size_t Pbytes, size_t Sbytes) {
         ctx->ws_P.exported = false;
         return 0;
     }
-    if (nse->rows_genS != ctx->ws_S.gen || nse->rows_nranks != cm.nranks) {
+    if (nse->rows_genS != ctx->ws_S.gen || nse->rows_genP != ctx->ws_P.gen || nse->rows_nranks != cm.nranks) {
         const int nkz = nse->Kz + 1, nxl = nse->x1 - nse->x0;
         for (int v = 0; v < 2; ++v) {
             const int nf = v == 0 ? 5 : 3;
@@ -204,8 +205,18 @@ static int ensure_peers(cfgpu_nse nse, size_t Pbytes, size_t Sbytes) {
             if (!nse->d_rows[v]) CF_CUDA(cudaMalloc((void**)&nse->d_rows[v], tab.size() * sizeof(double*)));
             CF_CUDA(cudaMemcpyAsync(nse->d_rows[v], tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
             CF_CUDA(cudaStreamSynchronize(ctx->stream));
+            // push mode: only the rows of this rank's own planes go straight to (its own) staging, the others stay in the
+            // local pencil buffer P[f][Ny][nxl][nkz] from where the push kernel sends them
+            const size_t Pf = (size_t)nse->Ny * nxl * nkz * 2;
+            for (int f = 0; f < nf; ++f)
+                for (int y = 0; y < nse->Ny; ++y)
+                    if (y < nse->y0 || y >= nse->y1) tab[(size_t)f * nse->Ny + y] = ctx->ws_P.ptr + (size_t)f * Pf + (size_t)y * nxl * nkz * 2;
+            if (!nse->d_rows_self[v]) CF_CUDA(cudaMalloc((void**)&nse->d_rows_self[v], tab.size() * sizeof(double*)));
+            CF_CUDA(cudaMemcpyAsync(nse->d_rows_self[v], tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
+            CF_CUDA(cudaStreamSynchronize(ctx->stream));
         }
         nse->rows_genS = ctx->ws_S.gen;
+        nse->rows_genP = ctx->ws_P.gen;
         nse->rows_nranks = cm.nranks;
     }
     return 0;
@@ -316,6 +327,11 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
             YGemmParams pc = p;
             pc.njobs = 1;
             pc.job[0] = p.job[c];
+            if (peer) {
+                double** tab = nse->d_rows_self[with_derivs ? 0 : 1];
+                pc.job[0].out_rows[0] = tab + (size_t)c * nse->Ny;
+                if (pc.job[0].nmat == 2) pc.job[0].out_rows[1] = tab + (size_t)(c == 0 ? 3 : 4) * nse->Ny;
+            }
             { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(pc, ctx->stream)); }
             CF_CUDA(cudaEventRecord(ctx->ev_cmp[c], ctx->stream));
             CF_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_cmp[c], 0));
@@ -481,6 +497,7 @@ int cfgpu_nse_destroy(cfgpu_nse nse) {
     cudaStreamSynchronize(nse->ctx->stream);
     for (auto& t : nse->tau) cudaFree(t.base);
     for (int v = 0; v < 2; ++v) if (nse->d_rows[v]) cudaFree(nse->d_rows[v]);
+    for (int v = 0; v < 2; ++v) if (nse->d_rows_self[v]) cudaFree(nse->d_rows_self[v]);
     if (nse->s_u) cfgpu_field_destroy(nse->s_u);
     if (nse->s_t) cfgpu_field_destroy(nse->s_t);
     cudaFree(nse->d_base);
@@ -763,6 +780,11 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
             XPassParams xc = xp;
             xc.nfields = 1;
             xc.fsel[0] = c;
+            if (peer) {  // this rank's own kx rows go straight into its pencil buffer, the others into the staging
+                xc.peer_direct = 2;
+                xc.self_rank = ctx->comm.rank;
+                xc.peer_out[ctx->comm.rank] = reinterpret_cast<double2*>(ctx->ws_P.ptr);
+            }
             { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xc, ctx->stream)); }
             CF_CUDA(cudaEventRecord(ctx->ev_cmp[c], ctx->stream));
             CF_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_cmp[c], 0));

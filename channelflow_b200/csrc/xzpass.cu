@@ -121,9 +121,10 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_forward_kernel(const XPassPa
             const double k = p.cb * (p.opb[f] == 1 ? TWO_PI * kx / p.Lx : TWO_PI * kz / p.Lz);
             v = make_double2(v.x - k * w.y, v.y + k * w.x);
         }
-        if (p.peer_direct) {
-            int s;
-            const size_t o = xpass_peer_offset(p, f, p.ny0 + yl, mxi, nkz, s);
+        int s = -1;
+        size_t o = 0;
+        if (p.peer_direct) o = xpass_peer_offset(p, f, p.ny0 + yl, mxi, nkz, s);
+        if (p.peer_direct == 1 || (p.peer_direct == 2 && s == p.self_rank)) {
             p.peer_out[s][o + kz] = v;
         } else {
             p.out[xpass_row_offset(p, f, yl, mxi, nkz) + kz] = v;

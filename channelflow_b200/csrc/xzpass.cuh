@@ -41,7 +41,8 @@ struct XPassParams {
     // forward pass with peer memory: rank s's pencil buffer P_s[f][Ny][mxi - xsplit[s]][kz] mapped into this process; the
     // x-pass stores each kx row straight into its owner's memory (the all-to-all fused into the store). null: staged.
     double2* peer_out[16];
-    int peer_direct;
+    int peer_direct;      // 1: every row to its owner; 2: only the rows owned by self_rank (push mode), the others are staged
+    int self_rank;
 };
 // offset (complex elements) of (field f, global plane y, mxi) inside owner rank s's kx-slab pencil buffer
 __host__ __device__ inline size_t xpass_peer_offset(const XPassParams& p, int f, int y, int mxi, int nkz, int& s) {
