@@ -178,11 +178,12 @@ def small_case_parity(cf, lib, rank, world):
     rows = [(m if m <= Kx else m - (2 * Kx + 1)) % Nx for m in range(2 * Kx + 1)]
     u0[:, :, rows, :Kz + 1] = fx["u0"]
     out = {}
+    saved = {k: os.environ.get(k) for k in ("CFGPU_NO_PEER", "CFGPU_PEER_MODE")}
     for leg in ("peer_push", "peer_fused", "staged"):
+        os.environ.pop("CFGPU_NO_PEER", None)
+        os.environ["CFGPU_PEER_MODE"] = "push" if leg == "peer_push" else "fused"
         if leg == "staged":
             os.environ["CFGPU_NO_PEER"] = "1"
-        if leg == "peer_fused":
-            os.environ["CFGPU_PEER_MODE"] = "fused"
         try:
             ug = cf.FlowField(lib, Nx, Ny, Nz, 3, float(fx["Lx"]), float(fx["Lz"]), float(fx["a"]), float(fx["b"])).set(u0.view(np.float64), padded=True)
             dns = cf.DNS(ug, cf.make_flags(**flags))
@@ -200,9 +201,11 @@ def small_case_parity(cf, lib, rank, world):
                         "norm_rel": abs(norm - float(fx["norm4"])) / float(fx["norm4"])}
             del dns, ug, u1
         finally:
-            os.environ.pop("CFGPU_NO_PEER", None)
-            if leg == "peer_fused":
-                os.environ.pop("CFGPU_PEER_MODE", None)
+            for k, v in saved.items():  # back to what the caller's environment said
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
     return out
 
 

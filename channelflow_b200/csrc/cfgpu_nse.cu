@@ -83,15 +83,15 @@ static int slab_exchange(cfgpu_nse nse, int nf, int dir, const int* fields, int 
 }
 
 // How the all-to-all travels when the ranks can map each other's buffers (CFGPU_PEER_MODE):
-//   push  (default) the transform kernels write locally at full speed; per velocity component a push kernel on a
+//   push  the transform kernels write locally at full speed; per velocity component a push kernel on a
 //         high-priority stream copies the blocks into the receivers' buffers while the next component is being transformed,
 //         completion is signalled through device-side flags (comm.cuh) -- no NCCL call, no barrier
-//   fused the y-GEMM epilogue / forward x-pass store every row straight into the owning rank's buffer, NCCL barriers
-//         between producer and consumer (the round-1 path: the producers become NVLink-bound, nothing overlaps them)
+//   fused (default: measured faster at 2 and 8 GPUs, profiles/r02_*) the y-GEMM epilogue / forward x-pass store every row
+//         straight into the owning rank's buffer; completion travels through the same device-side flags
 enum { PEER_PUSH = 0, PEER_FUSED = 1 };
 static int peer_mode() {  // read per call (like CFGPU_NO_PEER): all ranks must of course agree
     const char* e = getenv("CFGPU_PEER_MODE");
-    return (e && !strcmp(e, "fused")) ? PEER_FUSED : PEER_PUSH;
+    return (e && !strcmp(e, "push")) ? PEER_PUSH : PEER_FUSED;
 }
 static unsigned long long* flag_words(void* base) { return reinterpret_cast<unsigned long long*>(base); }
 static unsigned int* flag_counter(void* base) { return reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(base) + 2048); }
@@ -132,6 +132,18 @@ static int slab_push(cfgpu_nse nse, int nf, int dir, const int* fields, int nsel
     pp.done_counter = flag_counter(ctx->ws_F.ptr);
     static const int nctas = getenv("CF_PUSH_CTAS") ? atoi(getenv("CF_PUSH_CTAS")) : 24;
     return slab_push_launch(pp, nctas, stream);
+}
+// fused mode: this rank's producer kernel (whose stores went straight into the peers' buffers) precedes this call in
+// stream order; publish its completion to every rank
+static int slab_signal(cfgpu_nse nse, int slot, cudaStream_t stream) {
+    cfgpu_ctx ctx = nse->ctx;
+    PushParams pp;
+    memset(&pp, 0, sizeof pp);
+    for (int r = 0; r < ctx->comm.nranks; ++r) pp.flags[r] = flag_words(ctx->peerF[r]);
+    pp.nranks = ctx->comm.nranks; pp.rank = ctx->comm.rank; pp.slot = slot;
+    pp.seq = ++ctx->push_seq[slot];
+    pp.done_counter = flag_counter(ctx->ws_F.ptr);
+    return slab_push_launch(pp, 0, stream);  // no messages: just the flag kernel
 }
 static int slab_wait(cfgpu_nse nse, int slot, cudaStream_t stream) {
     cfgpu_ctx ctx = nse->ctx;
@@ -314,9 +326,17 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
             p.job[i].out_rows[0] = tab + (size_t)i * nse->Ny;
             if (p.job[i].nmat == 2) p.job[i].out_rows[1] = tab + (size_t)(i == 0 ? 3 : 4) * nse->Ny;
         }
-        CF_TRY(comm_barrier(ctx->comm, ctx->stream));
+        // No barrier in front: a rank reaches this point only after it has received the previous exchange from everybody,
+        // and everybody sent it only after having consumed what these stores overwrite (see comm.cuh).  Completion travels
+        // through device-side flags (CFGPU_FLAG_BARRIER=0: the round-1 NCCL barriers).
+        const bool flagbar = !(getenv("CFGPU_FLAG_BARRIER") && atoi(getenv("CFGPU_FLAG_BARRIER")) == 0);
+        if (!flagbar) CF_TRY(comm_barrier(ctx->comm, ctx->stream));
         { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(p, ctx->stream)); }
-        { StageTimer _t(ctx, 8); CF_TRY(comm_barrier(ctx->comm, ctx->stream)); }
+        {
+            StageTimer _t(ctx, 8);
+            if (flagbar) { CF_TRY(slab_signal(nse, 6, ctx->stream)); CF_TRY(slab_wait(nse, 6, ctx->stream)); }
+            else CF_TRY(comm_barrier(ctx->comm, ctx->stream));
+        }
     } else if (!multi) {
         StageTimer _t(ctx, 0);
         CF_TRY(ygemm_launch(p, ctx->stream));
@@ -771,7 +791,13 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         xp.peer_direct = 1;
         for (int r = 0; r < ctx->comm.nranks; ++r) xp.peer_out[r] = reinterpret_cast<double2*>(ctx->peerP[r]);
         { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xp, ctx->stream)); }
-        { StageTimer _t(ctx, 8); CF_TRY(comm_barrier(ctx->comm, ctx->stream)); }
+        {
+            StageTimer _t(ctx, 8);
+            if (!(getenv("CFGPU_FLAG_BARRIER") && atoi(getenv("CFGPU_FLAG_BARRIER")) == 0)) {
+                CF_TRY(slab_signal(nse, 7, ctx->stream));
+                CF_TRY(slab_wait(nse, 7, ctx->stream));
+            } else CF_TRY(comm_barrier(ctx->comm, ctx->stream));
+        }
     } else if (!multi) {
         StageTimer _t(ctx, 3);
         CF_TRY(xpass_forward_launch(xp, ctx->stream));

@@ -307,6 +307,13 @@ __global__ void __launch_bounds__(PUSH_THREADS) slab_push_kernel(const PushParam
     }
 }
 
+// completion flags after copy-engine transfers (the copies precede this kernel in stream order)
+__global__ void __launch_bounds__(32) slab_signal_kernel(const PushParams p) {
+    __threadfence_system();
+    const int r = threadIdx.x;
+    if (r < p.nranks) st_release_sys(p.flags[r] + (size_t)p.slot * COMM_MAXRANKS + p.rank, p.seq);
+}
+
 __global__ void __launch_bounds__(32) slab_wait_kernel(const unsigned long long* flags, int slot, int nranks, unsigned long long seq, int* err) {
     const int r = threadIdx.x;
     if (r < nranks) {
@@ -329,7 +336,15 @@ int slab_push_launch(const PushParams& p, int nctas, cudaStream_t stream) {
         set_last_error("slab_push: bad message count / slot");
         return 1;
     }
-    if (nctas < 1) nctas = 1;
+    if (nctas <= 0) {
+        // copy engines: one DMA transfer per block (they are contiguous on both sides), no SM is taken from the transforms
+        for (int m = 0; m < p.nmsg; ++m)
+            if (p.msg[m].n > 0)
+                CF_CUDA(cudaMemcpyAsync(p.msg[m].dst, p.msg[m].src, (size_t)p.msg[m].n * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+        CF_LAUNCH(slab_signal_kernel, dim3(1), dim3(32), 0, stream, p);
+        CF_KERNEL_CHECK();
+        return 0;
+    }
     CF_LAUNCH(slab_push_kernel, dim3(nctas), dim3(PUSH_THREADS), 0, stream, p);
     CF_KERNEL_CHECK();
     return 0;

@@ -82,6 +82,7 @@ struct PushParams {
     unsigned long long seq;
     unsigned int* done_counter;  // local, zero between launches
 };
+// nctas > 0: SM push kernel with that many CTAs; nctas <= 0: copy engines (cudaMemcpyAsync per block) + a flag kernel
 int slab_push_launch(const PushParams& p, int nctas, cudaStream_t stream);
 // wait until flag word (slot, r) >= seq for every rank r; *err_dev is set to 1 on time-out (never hangs the GPU)
 int slab_wait_launch(const unsigned long long* myflags, int slot, int nranks, unsigned long long seq, int* err_dev, cudaStream_t stream);
