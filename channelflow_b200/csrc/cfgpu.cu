@@ -32,26 +32,29 @@ int ws_reserve(Workspace& w, size_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------- stage profiler
-int stage_begin(cfgpu_ctx ctx, int st) {
+int stage_begin(cfgpu_ctx ctx, int st, cudaStream_t stream) {
     if (!ctx->profiling || ctx->capturing) return 0;
+    if (!stream) stream = ctx->stream;
     if (ctx->prof_used[st] == ctx->prof_ev[st].size()) {
         cudaEvent_t a, b;
         CF_CUDA(cudaEventCreate(&a));
         CF_CUDA(cudaEventCreate(&b));
         ctx->prof_ev[st].push_back({a, b});
     }
-    CF_CUDA(cudaEventRecord(ctx->prof_ev[st][ctx->prof_used[st]].first, ctx->stream));
+    CF_CUDA(cudaEventRecord(ctx->prof_ev[st][ctx->prof_used[st]].first, stream));
     return 0;
 }
-int stage_end(cfgpu_ctx ctx, int st) {
+int stage_end(cfgpu_ctx ctx, int st, cudaStream_t stream) {
     if (!ctx->profiling || ctx->capturing) return 0;
-    CF_CUDA(cudaEventRecord(ctx->prof_ev[st][ctx->prof_used[st]].second, ctx->stream));
+    if (!stream) stream = ctx->stream;
+    CF_CUDA(cudaEventRecord(ctx->prof_ev[st][ctx->prof_used[st]].second, stream));
     ctx->prof_used[st]++;
     ctx->prof_calls[st]++;
     return 0;
 }
 static int prof_collect(cfgpu_ctx ctx) {
     CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(ctx->comm_stream));
     for (int st = 0; st < CFGPU_NSTAGES; ++st) {
         for (size_t i = 0; i < ctx->prof_used[st]; ++i) {
             float ms = 0;

@@ -153,12 +153,12 @@ int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out);
 int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out);
 int get_box(cfgpu_ctx ctx, int Nx, int Nz, int Kx, int Kz, const ModeBox** out);
 int ws_reserve(Workspace& w, size_t bytes);
-int stage_begin(cfgpu_ctx ctx, int stage);
-int stage_end(cfgpu_ctx ctx, int stage);
+int stage_begin(cfgpu_ctx ctx, int stage, cudaStream_t stream = 0);  // 0: the context's compute stream
+int stage_end(cfgpu_ctx ctx, int stage, cudaStream_t stream = 0);
 struct StageTimer {  // RAII bracket around the launches of one pipeline stage
-    cfgpu_ctx ctx; int stage;
-    StageTimer(cfgpu_ctx c, int s) : ctx(c), stage(s) { stage_begin(ctx, stage); }
-    ~StageTimer() { stage_end(ctx, stage); }
+    cfgpu_ctx ctx; int stage; cudaStream_t stream;
+    StageTimer(cfgpu_ctx c, int s, cudaStream_t st = 0) : ctx(c), stage(s), stream(st) { stage_begin(ctx, stage, stream); }
+    ~StageTimer() { stage_end(ctx, stage, stream); }
 };
 // host-side Chebyshev helpers (long double internally)
 void cheb_diff_host(const std::vector<double>& u, std::vector<double>& d, double a, double b);

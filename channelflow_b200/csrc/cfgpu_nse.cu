@@ -145,6 +145,8 @@ static int slab_signal(cfgpu_nse nse, int slot, cudaStream_t stream) {
     pp.done_counter = flag_counter(ctx->ws_F.ptr);
     return slab_push_launch(pp, 0, stream);  // no messages: just the flag kernel
 }
+// fused exchange pipelined per velocity component over two streams (CFGPU_PIPELINE=0: everything on one stream)
+static bool fused_pipelined() { return !(getenv("CFGPU_PIPELINE") && atoi(getenv("CFGPU_PIPELINE")) == 0); }
 static int slab_wait(cfgpu_nse nse, int slot, cudaStream_t stream) {
     cfgpu_ctx ctx = nse->ctx;
     return slab_wait_launch(flag_words(ctx->ws_F.ptr), slot, ctx->comm.nranks, ctx->push_seq[slot], flag_error(ctx->ws_F.ptr), stream);
@@ -330,12 +332,24 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         // and everybody sent it only after having consumed what these stores overwrite (see comm.cuh).  Completion travels
         // through device-side flags (CFGPU_FLAG_BARRIER=0: the round-1 NCCL barriers).
         const bool flagbar = !(getenv("CFGPU_FLAG_BARRIER") && atoi(getenv("CFGPU_FLAG_BARRIER")) == 0);
-        if (!flagbar) CF_TRY(comm_barrier(ctx->comm, ctx->stream));
-        { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(p, ctx->stream)); }
-        {
-            StageTimer _t(ctx, 8);
-            if (flagbar) { CF_TRY(slab_signal(nse, 6, ctx->stream)); CF_TRY(slab_wait(nse, 6, ctx->stream)); }
-            else CF_TRY(comm_barrier(ctx->comm, ctx->stream));
+        if (fused_pipelined()) {
+            // per velocity component: the y-GEMM (NVLink-bound through its remote stores) on the compute stream, its
+            // completion flag; the x-passes of the components that have arrived run beside it on the second stream
+            for (int c = 0; c < 3; ++c) {
+                YGemmParams pc = p;
+                pc.njobs = 1;
+                pc.job[0] = p.job[c];
+                { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(pc, ctx->stream)); }
+                CF_TRY(slab_signal(nse, c, ctx->stream));
+            }
+        } else {
+            if (!flagbar) CF_TRY(comm_barrier(ctx->comm, ctx->stream));
+            { StageTimer _t(ctx, 0); CF_TRY(ygemm_launch(p, ctx->stream)); }
+            {
+                StageTimer _t(ctx, 8);
+                if (flagbar) { CF_TRY(slab_signal(nse, 6, ctx->stream)); CF_TRY(slab_wait(nse, 6, ctx->stream)); }
+                else CF_TRY(comm_barrier(ctx->comm, ctx->stream));
+            }
         }
     } else if (!multi) {
         StageTimer _t(ctx, 0);
@@ -386,7 +400,21 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
         xp.nfields = 3;
         for (int i = 0; i < 3; ++i) { xp.src[i] = i; xp.opa[i] = 0; xp.srcb[i] = -1; xp.opb[i] = 0; xp.fsel[i] = i; }
     }
-    if (!multi || fused) {
+    if (fused && fused_pipelined()) {
+        const int sel[3][3] = {{0, -1, -1}, {1, 5, -1}, {2, 3, 4}};
+        cudaStream_t X = ctx->comm_stream;
+        for (int c = 0; c < 3; ++c) {
+            { StageTimer _t(ctx, 8, X); CF_TRY(slab_wait(nse, c, X)); }
+            XPassParams xc = xp;
+            xc.nfields = 0;
+            if (with_derivs) { for (int k = 0; k < 3; ++k) if (sel[c][k] >= 0) xc.fsel[xc.nfields++] = sel[c][k]; }
+            else xc.fsel[xc.nfields++] = c;
+            StageTimer _t(ctx, 1, X);
+            CF_TRY(xpass_inverse_launch(xc, X));
+        }
+        CF_CUDA(cudaEventRecord(ctx->ev_com[3], X));
+        CF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_com[3], 0));
+    } else if (!multi || fused) {
         StageTimer _t(ctx, 1);
         CF_TRY(xpass_inverse_launch(xp, ctx->stream));
     } else {
@@ -786,12 +814,26 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     for (int i = 0; i < 3; ++i) { xp.fsel[i] = i; xp.src[i] = i; xp.srcb[i] = -1; }
     const bool peer = multi && comm_peer_capable(ctx->comm);
     const bool fused = peer && peer_mode() == PEER_FUSED;
+    bool f_prepared = false;
     if (fused) {
-        // each kx row is stored straight into its owner's pencil buffer; one barrier before the y-GEMM reads it
+        // each kx row is stored straight into its owner's pencil buffer
         xp.peer_direct = 1;
         for (int r = 0; r < ctx->comm.nranks; ++r) xp.peer_out[r] = reinterpret_cast<double2*>(ctx->peerP[r]);
-        { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xp, ctx->stream)); }
-        {
+        if (fused_pipelined()) {
+            // the output field is prepared first so that the forward y-GEMMs on the second stream only depend on the flags
+            CF_TRY(spec_output(nse, f));
+            f_prepared = true;
+            CF_CUDA(cudaEventRecord(ctx->ev_cmp[3], ctx->stream));
+            CF_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_cmp[3], 0));
+            for (int c = 0; c < 3; ++c) {
+                XPassParams xc = xp;
+                xc.nfields = 1;
+                xc.fsel[0] = c;
+                { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xc, ctx->stream)); }
+                CF_TRY(slab_signal(nse, 3 + c, ctx->stream));
+            }
+        } else {
+            { StageTimer _t(ctx, 3); CF_TRY(xpass_forward_launch(xp, ctx->stream)); }
             StageTimer _t(ctx, 8);
             if (!(getenv("CFGPU_FLAG_BARRIER") && atoi(getenv("CFGPU_FLAG_BARRIER")) == 0)) {
                 CF_TRY(slab_signal(nse, 7, ctx->stream));
@@ -824,7 +866,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
 
     // aliased modes of f must be exactly zero (FlowField::zeroPaddedModes, nse.cpp:389-390); the kernels below
     // only ever write retained modes
-    CF_TRY(spec_output(nse, f));
+    if (!f_prepared) CF_TRY(spec_output(nse, f));
 
     const YPlan* yp;
     const ModeBox* bx;
@@ -847,7 +889,19 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
         p.job[i].out[0] = fa.base + i * fa.compstride;
         p.job[i].nmat = 1; p.job[i].mat0 = 0;
     }
-    if (!multi || fused) {
+    if (fused && fused_pipelined()) {
+        cudaStream_t X = ctx->comm_stream;
+        for (int c = 0; c < 3; ++c) {
+            { StageTimer _t(ctx, 8, X); CF_TRY(slab_wait(nse, 3 + c, X)); }
+            YGemmParams pc = p;
+            pc.njobs = 1;
+            pc.job[0] = p.job[c];
+            StageTimer _t(ctx, 4, X);
+            CF_TRY(ygemm_launch(pc, X));
+        }
+        CF_CUDA(cudaEventRecord(ctx->ev_com[3], X));
+        CF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_com[3], 0));
+    } else if (!multi || fused) {
         StageTimer _t(ctx, 4);
         CF_TRY(ygemm_launch(p, ctx->stream));
     } else {
