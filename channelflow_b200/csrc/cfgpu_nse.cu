@@ -145,8 +145,11 @@ static int slab_signal(cfgpu_nse nse, int slot, cudaStream_t stream) {
     pp.done_counter = flag_counter(ctx->ws_F.ptr);
     return slab_push_launch(pp, 0, stream);  // no messages: just the flag kernel
 }
-// fused exchange pipelined per velocity component over two streams (CFGPU_PIPELINE=0: everything on one stream)
-static bool fused_pipelined() { return !(getenv("CFGPU_PIPELINE") && atoi(getenv("CFGPU_PIPELINE")) == 0); }
+// fused exchange pipelined per velocity component over two streams (CFGPU_PIPELINE=1).  Off by default: measured slower
+// than the single-stream form at 2 and 8 GPUs (4.95 vs 4.63 ms and 1.75 vs 1.60 ms per step at 512x257x512,
+// profiles/r02i_*, r02j_*): three launches per transform quantise worse and the co-scheduled kernels share the SMs'
+// store path to the peers, which is what the producers wait on.
+static bool fused_pipelined() { return getenv("CFGPU_PIPELINE") && atoi(getenv("CFGPU_PIPELINE")) == 1; }
 static int slab_wait(cfgpu_nse nse, int slot, cudaStream_t stream) {
     cfgpu_ctx ctx = nse->ctx;
     return slab_wait_launch(flag_words(ctx->ws_F.ptr), slot, ctx->comm.nranks, ctx->push_seq[slot], flag_error(ctx->ws_F.ptr), stream);

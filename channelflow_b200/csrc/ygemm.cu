@@ -19,7 +19,7 @@
 
 namespace cfgpu {
 
-constexpr bool YG_SPLIT_DEFAULT = false;  // set from the A/B measurement (profiles/r02_*)
+constexpr bool YG_SPLIT_DEFAULT = true;   // A/B at 512x257x512 (profiles/r02c_*): inverse 1.71 -> 1.65 ms, forward 1.18 -> 1.14 ms
 
 // BN columns per CTA, WN warps along the columns (4 warps along the rows): <64,2> is one 256-thread CTA per SM, <32,1> two
 // independent 128-thread CTAs per SM with the same 32 x 32 warp tile -- one CTA's staging and epilogue overlap the other's

@@ -248,7 +248,7 @@ ChebyCoeff laminarProfile(Real nu, MeanConstraint constraint, Real dPdx, Real Ub
     const Real dU = ub - ua;
     const Real em = expm1(-mu);
     Real G = dPdx * square(H) / nu;  // dimensionless pressure gradient
-    const std::vector<Real> y = chebypoints(Ny, a, b);
+    const Vector y = chebypoints(Ny, a, b);
     if (std::abs(mu) > 1e-01) {
         if (constraint == BulkVelocity) {
             const Real k = -1.0 / em - 1 / mu;
