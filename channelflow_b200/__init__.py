@@ -30,6 +30,7 @@ cfgpu_field_make_physical cfgpu_field_make_spectral cfgpu_l2norm2 cfgpu_l2norm2_
 cfgpu_nse_destroy cfgpu_nse_set_constraint cfgpu_nse_reset_lambda cfgpu_nse_nonlinear cfgpu_nse_solve
 cfgpu_nse_linear cfgpu_nse_cflfactor cfgpu_nse_get_dPd cfgpu_comm_unique_id cfgpu_comm_init_nccl
 cfgpu_comm_init_external cfgpu_comm_rank cfgpu_comm_ranges cfgpu_field_allgather
+cfgpu_field_copy_component cfgpu_l2form_box cfgpu_bcnorm2 cfgpu_field_diffop cfgpu_field_pointwise
 cfgpu_vec_create cfgpu_vec_destroy cfgpu_vec_size cfgpu_vec_upload cfgpu_vec_download cfgpu_vec_copy cfgpu_vec_zero cfgpu_vec_dot
 cfgpu_vec_nrm2 cfgpu_vec_axpy cfgpu_vec_axpby cfgpu_vec_scal cfgpu_field2vector_size cfgpu_field2vector cfgpu_vector2field""".split()
 

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "cfgpu_internal.h"
+#include "diffops.cuh"
 #include "fieldops.cuh"
 
 namespace cfgpu {
@@ -688,6 +689,19 @@ int cfgpu_field_copy(cfgpu_field dst, cfgpu_field src) {
     dst->Lx = src->Lx; dst->Lz = src->Lz; dst->a = src->a; dst->b = src->b;
     return 0;
 }
+// dst component jd <- src component js (FlowField::operator[](int), flowfield.cpp:1532-1560, and its inverse)
+int cfgpu_field_copy_component(cfgpu_field dst, int jd, cfgpu_field src, int js) {
+    CF_ARG(dst && src && dst != src, "cfgpu_field_copy_component: bad argument");
+    CF_ARG(dst->Nx == src->Nx && dst->Ny == src->Ny && dst->Nz == src->Nz, "cfgpu_field_copy_component: grid mismatch");
+    CF_ARG(jd >= 0 && jd < dst->Nd && js >= 0 && js < src->Nd, "cfgpu_field_copy_component: component out of range");
+    CF_TRY(field_serial(src));
+    CF_TRY(field_serial(dst));
+    CF_CUDA(cudaMemcpyAsync(dst->dser + jd * dst->compstride(), src->dser + js * src->compstride(), src->compstride() * sizeof(double),
+                            cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    auto mrg = [](int p, int q) { return (p < 0 || q < 0) ? -1 : (p > q ? p : q); };
+    dst->clean_Kx = mrg(dst->clean_Kx, src->clean_Kx); dst->clean_Kz = mrg(dst->clean_Kz, src->clean_Kz);
+    return 0;
+}
 int cfgpu_field_swap(cfgpu_field a, cfgpu_field b) {
     CF_ARG(same_shape(a, b), "cfgpu_field_swap: shape mismatch");
     std::swap(a->dser, b->dser);
@@ -871,6 +885,94 @@ static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool pa
     return 0;
 }
 int cfgpu_l2norm2(cfgpu_field u, int normalize, double* out_h) { return l2form(u, nullptr, 0, normalize, u->padded != 0, out_h); }
+
+// L2Norm2 / L2Dist2 / L2InnerProduct restricted to |kx| <= kxmax, kz <= kzmax (diffops.cpp:543-700); cz = 0 sums the stored
+// modes without the factor 2 for kz > 0 (the convention of divNorm2, diffops.cpp:91-116)
+int cfgpu_l2form_box(cfgpu_field u, cfgpu_field v, int mode, int kxmax, int kzmax, int cz, int normalize, double* out_h) {
+    CF_ARG(u && out_h && mode >= 0 && mode <= 2 && (mode == 0 || v), "cfgpu_l2form_box: bad argument");
+    CF_ARG(!v || same_shape(u, v), "cfgpu_l2form_box: shape mismatch");
+    CF_TRY(field_serial(u)); if (v) CF_TRY(field_serial(v));
+    CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "L2 norm: field must be spectral");
+    cfgpu_ctx ctx = u->ctx;
+    CF_ARG(ctx->comm.nranks == 1, "cfgpu_l2form_box: single-GPU call (use the default norms in multi-GPU runs)");
+    const YPlan* pl;
+    CF_TRY(get_yplan(ctx, u->Ny, u->a, u->b, &pl));
+    CF_TRY(ws_reserve(ctx->ws_red, 1 << 20));
+    const double scale = normalize ? 1.0 : (u->b - u->a) * u->Lx * u->Lz;
+    const bool full = kxmax >= u->Nx / 2 && kzmax >= u->Nz / 2;
+    if (!full) CF_ARG(kxmax >= 0 && kxmax < (u->Nx + 1) / 2 && kzmax >= 0 && kzmax <= u->Nz / 2, "cfgpu_l2form_box: box out of range");
+    double* out_dev = ctx->ws_red.ptr;
+    CF_TRY(l2form_launch(u->dser, v ? v->dser : nullptr, mode, pl->Wgram, u->Ny, u->Nx, u->Nz, u->Nd, kxmax, kzmax, full ? 1 : 0, 0,
+                         full ? u->Nx : 2 * kxmax + 1, scale, ctx->ws_red.ptr + 8, ctx->ws_red.bytes / sizeof(double) - 8, out_dev, ctx->stream,
+                         cz ? 2.0 : 1.0));
+    CF_CUDA(cudaMemcpyAsync(out_h, out_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+// bcNorm2 / bcDist2 (diffops.cpp:18-83): sum over components and all modes of |f(a)|^2 + |f(b)|^2
+int cfgpu_bcnorm2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h) {
+    CF_ARG(u && out_h && (!v || same_shape(u, v)), "cfgpu_bcnorm2: bad argument");
+    CF_TRY(field_serial(u)); if (v) CF_TRY(field_serial(v));
+    CF_ARG(u->xzstate == CFGPU_SPECTRAL, "cfgpu_bcnorm2: field must be xz-spectral");
+    cfgpu_ctx ctx = u->ctx;
+    CF_ARG(ctx->comm.nranks == 1, "cfgpu_bcnorm2: single-GPU call");
+    CF_TRY(ws_reserve(ctx->ws_red, 1 << 20));
+    CF_TRY(bcnorm2_launch(u->dser, v ? v->dser : nullptr, u->Nx, u->Ny, u->Nz, u->Nd, u->ystate == CFGPU_SPECTRAL, ctx->ws_red.ptr + 8,
+                          ctx->ws_red.bytes / sizeof(double) - 8, ctx->ws_red.ptr, ctx->stream));
+    double r = 0;
+    CF_CUDA(cudaMemcpyAsync(&r, ctx->ws_red.ptr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out_h = normalize ? r : r * u->Lx * u->Lz;
+    return 0;
+}
+// generic linear differential operator on a spectral field (xdiff/ydiff/zdiff/grad/lapl/curl/div of diffops.cpp)
+int cfgpu_field_diffop(cfgpu_field out, cfgpu_field in, int nterms, const int* out_c, const int* in_c, const int* nx, const int* ny,
+                       const int* nz, const double* coef) {
+    CF_ARG(out && in && out != in && nterms >= 1 && nterms <= DIFF_MAXTERMS, "cfgpu_field_diffop: bad argument");
+    CF_ARG(out->Nx == in->Nx && out->Ny == in->Ny && out->Nz == in->Nz, "cfgpu_field_diffop: grid mismatch");
+    CF_ARG(in->xzstate == CFGPU_SPECTRAL && in->ystate == CFGPU_SPECTRAL, "cfgpu_field_diffop: input must be spectral");
+    CF_TRY(field_serial(in));
+    CF_TRY(field_serial_output(out));
+    DiffOpParams p;
+    memset(&p, 0, sizeof p);
+    p.g = FieldGeom{in->Nx, in->Ny, in->Nz, in->Lx, in->Lz, in->a, in->b};
+    p.nout = out->Nd; p.nterms = nterms;
+    for (int k = 0; k < nterms; ++k) {
+        CF_ARG(in_c[k] >= 0 && in_c[k] < in->Nd && out_c[k] >= 0 && out_c[k] < out->Nd, "cfgpu_field_diffop: component out of range");
+        p.t[k] = DiffTerm{out_c[k], in_c[k], nx[k], ny[k], nz[k], coef[k]};
+    }
+    {   // components without a term must come out zero
+        bool has[64] = {false};
+        for (int k = 0; k < nterms; ++k) has[out_c[k]] = true;
+        for (int c = 0; c < out->Nd; ++c)
+            if (!has[c]) CF_CUDA(cudaMemsetAsync(out->dser + c * out->compstride(), 0, out->compstride() * sizeof(double), out->ctx->stream));
+    }
+    CF_TRY(diffop_launch(in->dser, out->dser, p, in->ctx->stream));
+    out->xzstate = out->ystate = CFGPU_SPECTRAL;
+    out->clean_Kx = in->clean_Kx; out->clean_Kz = in->clean_Kz;
+    out->padded = in->padded;
+    return 0;
+}
+// pointwise products of physical fields (cross/outer/dot/norm/norm2/energy of diffops.cpp); op: PointOp of diffops.cuh
+int cfgpu_field_pointwise(int op, cfgpu_field out, cfgpu_field f, cfgpu_field g) {
+    CF_ARG(out && f && op >= PW_CROSS && op <= PW_MUL, "cfgpu_field_pointwise: bad argument");
+    const bool two = op == PW_CROSS || op == PW_OUTER || op == PW_DOT || op == PW_MUL;
+    CF_ARG(!two || g, "cfgpu_field_pointwise: this operation needs two inputs");
+    CF_ARG(f->xzstate == CFGPU_PHYSICAL && f->ystate == CFGPU_PHYSICAL && (!two || (g->xzstate == CFGPU_PHYSICAL && g->ystate == CFGPU_PHYSICAL)),
+           "cfgpu_field_pointwise: inputs must be physical");
+    const int need = op == PW_CROSS ? 3 : (op == PW_OUTER ? f->Nd * g->Nd : (op == PW_MUL ? f->Nd : 1));
+    CF_ARG(out->Nd == need && out->Nx == f->Nx && out->Ny == f->Ny && out->Nz == f->Nz, "cfgpu_field_pointwise: output shape");
+    CF_ARG(op != PW_CROSS || (f->Nd == 3 && g->Nd == 3), "cfgpu_field_pointwise: cross needs 3-component fields");
+    CF_ARG(!(op == PW_DOT || op == PW_MUL) || f->Nd == g->Nd, "cfgpu_field_pointwise: component mismatch");
+    CF_ARG(out != f && out != g, "cfgpu_field_pointwise: output aliases an input");
+    CF_TRY(field_serial(f)); if (two) CF_TRY(field_serial(g));
+    CF_TRY(field_serial_output(out));
+    CF_TRY(pointwise_launch(op, f->dser, two ? g->dser : nullptr, out->dser, f->Nd, two ? g->Nd : 0, (long)f->compstride(), f->ctx->stream));
+    out->xzstate = out->ystate = CFGPU_PHYSICAL;
+    out->clean_Kx = out->clean_Kz = -1;
+    out->padded = 0;
+    return 0;
+}
 int cfgpu_l2norm2_3d(cfgpu_field u, int normalize, double* out_h) { return l2form(u, nullptr, 0, normalize, u->padded != 0, out_h, true); }
 int cfgpu_l2dist2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h) {
     CF_ARG(same_shape(u, v), "L2Dist2: shape mismatch");

@@ -73,7 +73,7 @@ __global__ void profile_add_kernel(double2* __restrict__ c, long off0, long rs, 
 constexpr int NRM_THREADS = 256;
 __global__ void __launch_bounds__(NRM_THREADS) l2form_kernel(const double* __restrict__ u, const double* __restrict__ v, int mode /*0 norm,1 dist,2 ip*/,
                                                              const double* __restrict__ W, int N, int Nx, int Mz, int Kx, int Kz, int fullbox,
-                                                             int qlo, int nq, int TMn, long rs, long cs, double* __restrict__ partial) {
+                                                             int qlo, int nq, int TMn, long rs, long cs, double czw, double* __restrict__ partial) {
     const int TT = 2 * TMn;
     double* X = dyn_smem<double>();
     double* Y = (mode == 2) ? X + (size_t)N * TT : X;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(NRM_THREADS) l2form_kernel(const double* __res
         const int q = q0 + (t >> 1);
         if (q < nq) {
             const int kz = (qlo + q) % nkz;
-            if (kz > 0) sum *= 2.0;
+            if (kz > 0) sum *= czw;  // 2: the kz < 0 ghost modes (diffops.cpp:417-487); 1: plain sum over stored modes (divNorm2)
         } else sum = 0.0;
     }
     sum = warp_sum(sum);
@@ -241,7 +241,7 @@ int tile_convert_launch(double* ser, double* tile, int Nx, int Ny, int Nz, int N
 }
 
 int l2form_launch(const double* u, const double* v, int mode, const double* W, int N, int Nx, int Nz, int Nd, int Kx, int Kz, int fullbox,
-                  int x0, int x1, double scale, double* partial_dev, size_t partial_cap, double* out_dev, cudaStream_t st) {
+                  int x0, int x1, double scale, double* partial_dev, size_t partial_cap, double* out_dev, cudaStream_t st, double czw) {
     const int Mz = Nz / 2 + 1;
     const int nkz_ = fullbox ? Mz : Kz + 1;
     const int qlo = x0 * nkz_;
@@ -263,7 +263,7 @@ int l2form_launch(const double* u, const double* v, int mode, const double* W, i
         return 1;
     }
     const long rs = (long)Nx * 2 * Mz, cs = rs * N;
-    CF_LAUNCH(kfn, grid, dim3(NRM_THREADS), smem, st, u, v, mode, W, N, Nx, Mz, Kx, Kz, fullbox, qlo, nq, TMn, rs, cs, partial_dev);
+    CF_LAUNCH(kfn, grid, dim3(NRM_THREADS), smem, st, u, v, mode, W, N, Nx, Mz, Kx, Kz, fullbox, qlo, nq, TMn, rs, cs, czw, partial_dev);
     CF_KERNEL_CHECK();
     CF_LAUNCH(sum_partials_kernel, dim3(1), dim3(256), 0, st, (const double*)partial_dev, nparts, scale, out_dev);
     CF_KERNEL_CHECK();

@@ -11,7 +11,7 @@ int profile_add_launch(double* d, long off0_cplx, long rs_cplx, int Ny, const do
 // mode: 0 = sum |u|^2, 1 = sum |u-v|^2, 2 = <u,v>; result (times scale) written to out_dev
 // rows mxi in [x0,x1) only (multi-GPU: the rank's own kx rows)
 int l2form_launch(const double* u, const double* v, int mode, const double* W, int N, int Nx, int Nz, int Nd, int Kx, int Kz, int fullbox,
-                  int x0, int x1, double scale, double* partial_dev, size_t partial_cap, double* out_dev, cudaStream_t st);
+                  int x0, int x1, double scale, double* partial_dev, size_t partial_cap, double* out_dev, cudaStream_t st, double czw = 2.0);
 // copy the retained rows mxi in [x0,x1), kz <= Kz of every (component, my) plane between a field (reference layout) and
 // a compact buffer [row][mxi-x0][kz]; dir 0: field -> buffer, 1: buffer -> field
 int tile_convert_launch(double* ser, double* tile, int Nx, int Ny, int Nz, int Nd, int Kx, int Kz, int x0, int nq, int TM, int dir,

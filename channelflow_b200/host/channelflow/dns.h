@@ -20,6 +20,9 @@ class DNS {
 
     void advance(std::vector<FlowField>& fields, int nSteps = 1);
     void project();
+    // true pressure p <-> the modified pressure q = p + 1/2 |u + Ubase|^2 of the rotational form (dns.cpp:372-444)
+    void uq2p(FlowField u, FlowField q, FlowField& p) const;
+    void up2q(FlowField u, FlowField p, FlowField& q) const;
 
     virtual void reset_dt(Real dt);
     virtual void reset_time(Real t);

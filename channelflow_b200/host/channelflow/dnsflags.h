@@ -6,7 +6,11 @@
 #include <string>
 #include <vector>
 
+#include "cfbasics/arglist.h"
+#include "cfbasics/cfvector.h"
 #include "cfbasics/mathdefs.h"
+#include "channelflow/chebyshev.h"
+#include "channelflow/flowfield.h"
 
 namespace chflow {
 
@@ -36,7 +40,20 @@ std::ostream& operator<<(std::ostream& os, TimeStepMethod t);
 std::ostream& operator<<(std::ostream& os, NonlinearMethod n);
 std::ostream& operator<<(std::ostream& os, Dealiasing d);
 
-class BodyForce;
+std::ostream& operator<<(std::ostream& os, VelocityScale v);
+std::ostream& operator<<(std::ostream& os, Verbosity v);
+
+// A body force f(x,y,z,t).  As in the reference (dnsflags.h:67-78) the time steppers never evaluate it: the class exists
+// so that programs which set DNSFlags::bodyforce compile and run.
+class BodyForce {
+   public:
+    BodyForce() {}
+    virtual ~BodyForce() = default;
+    Vector operator()(Real x, Real y, Real z, Real t);
+    void eval(Real t, FlowField& f);
+    virtual void eval(Real x, Real y, Real z, Real t, Real& fx, Real& fy, Real& fz);
+    virtual bool isOn(Real t);
+};
 
 class DNSFlags {
    public:
@@ -49,7 +66,12 @@ class DNSFlags {
              TimeStepMethod initstepping = SMRK2, NonlinearMethod nonlinearity = Rotational,
              Dealiasing dealiasing = DealiasXZ, BodyForce* bodyforce = 0, bool taucorrection = true,
              Verbosity verbosity = PrintTicks, std::ostream* logstream = &std::cout);
+    DNSFlags(ArgList& args, const bool laurette = false);  // the command-line options of the reference's programs
     virtual ~DNSFlags() = default;
+    void args2BC(ArgList& args);
+    void args2numerics(ArgList& args, const bool laurette = false);
+    virtual void save(const std::string& outdir = "") const;  // dnsflags.txt
+    virtual void load(int taskid, const std::string indir);
 
     bool dealias_xz() const { return dealiasing == DealiasXZ || dealiasing == DealiasXYZ; }
     bool dealias_y() const { return dealiasing == DealiasY || dealiasing == DealiasXYZ; }
@@ -71,6 +93,7 @@ class DNSFlags {
     int symmetryprojectioninterval;
     Verbosity verbosity;
     std::ostream* logstream;
+    std::string symmetries_file;  // -symms <file>: generators of the isotropy group to project onto (see symmetry.h)
 };
 
 std::ostream& operator<<(std::ostream& os, const DNSFlags& flags);

@@ -13,16 +13,12 @@
 #include <string>
 #include <vector>
 
+#include "cfbasics/cfvector.h"
 #include "cfbasics/mathdefs.h"
 #include "cfgpu.h"
+#include "channelflow/basisfunc.h"
 #include "channelflow/cfmpi.h"
 #include "channelflow/chebyshev.h"
-
-#ifndef FFTW_ESTIMATE
-#define FFTW_ESTIMATE (1U << 6)
-#define FFTW_MEASURE (0U)
-#define FFTW_PATIENT (1U << 5)
-#endif
 
 namespace chflow {
 
@@ -69,6 +65,17 @@ class FlowField {
     Complex& cmplx(int mx, int my, int mz, int i, int j) { return cmplx(mx, my, mz, i + Nd_ * j); }
 
     ComplexChebyCoeff profile(int mx, int mz, int i) const;
+    BasisFunc profile(int mx, int mz) const;
+    FlowField operator[](int i) const;                                 // the i-th component as a 1-component field
+    void setComponent(int i, const FlowField& src, int j);             // this[i] = src[j] (same grid and state)
+
+    // random divergence-free, no-slip perturbations on the libc drand48 stream (flowfield.cpp:2060-2177): the rule of
+    // tools/randomfield.cpp; profiles are built on the host, the closing transform round trip runs on the device
+    void perturb(Real magnitude, Real spectralDecay, bool meanflow = true);
+    void addPerturbation(int kx, int kz, Real mag, Real spectralDecay);
+    void addPerturbation1D(int kx, int kz, Real mag, Real spectralDecay);
+    void addPerturbations(int kxmax, int kzmax, Real mag, Real spectralDecay, bool meanflow = true);
+    void addPerturbations(Real magnitude, Real spectralDecay, bool meanflow = true);
 
     void makeSpectral_xz();
     void makePhysical_xz();
@@ -137,8 +144,29 @@ class FlowField {
 
     Complex Dx(int mx) const;
     Complex Dz(int mz) const;
+    Complex Dx(int mx, int n) const;
+    Complex Dz(int mz, int n) const;
+    Vector xgridpts() const;
+    Vector ygridpts() const;
+    Vector zgridpts() const;
+    lint Nxlocmax() const { return Nx_; }
+    lint Nylocpad() const { return Ny_; }
+    lint Nypad() const { return Ny_; }
+    int key0() const { return 0; }
+    int color0() const { return 0; }
+    int taskid_world() const { return 0; }
+    int task_coeffp(int, int) const { return 0; }
+    int task_coeff(int, int, int, int) const { return 0; }
+    MPI_Comm* comm_world() const { static MPI_Comm c = 0; return &c; }
 
     FlowField& operator*=(Real x);
+    FlowField& operator+=(const Real& a);        // u(0,0,0,0) += a
+    FlowField& operator-=(const Real& a);
+    FlowField& operator+=(const ComplexChebyCoeff& U);
+    FlowField& operator-=(const ComplexChebyCoeff& U);
+    FlowField& operator+=(const BasisFunc& U);   // adds U to mode (U.kx, U.kz)
+    FlowField& operator-=(const BasisFunc& U);
+    bool congruent(const BasisFunc& phi) const;
     FlowField& operator+=(const ChebyCoeff& U);  // u(0,*,0,0) += U
     FlowField& operator-=(const ChebyCoeff& U);
     FlowField& operator+=(const std::vector<ChebyCoeff>& UW);
@@ -153,7 +181,15 @@ class FlowField {
     friend void swap(FlowField& f, FlowField& g);
 
     void binarySave(const std::string& filebase) const;
-    void save(const std::string& filebase) const { binarySave(filebase); }
+    void asciiSave(const std::string& filebase) const;
+    void save(const std::string& filebase, std::vector<std::string> component_names = std::vector<std::string>()) const;
+    void saveProfile(int mx, int mz, const std::string& filebase) const;
+    void saveProfile(int mx, int mz, const std::string& filebase, const ChebyTransform& t) const;
+    void saveSpectrum(const std::string& filebase, int i, int ny = -1, bool kxorder = true, bool showpadding = false) const;
+    void saveSpectrum(const std::string& filebase, bool kxorder = true, bool showpadding = false) const;
+    Real energy(bool normalize = true) const;
+    Real energy(int mx, int mz, bool normalize = true) const;
+    void rescale(Real Lx, Real Lz);
 
     Real dudy_a() const;
     Real dudy_b() const;

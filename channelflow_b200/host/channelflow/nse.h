@@ -7,6 +7,7 @@
 #include <memory>
 #include <vector>
 
+#include "channelflow/diffops.h"
 #include "channelflow/dnsflags.h"
 #include "channelflow/flowfield.h"
 

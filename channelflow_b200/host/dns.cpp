@@ -85,6 +85,33 @@ void DNS::advance(std::vector<FlowField>& fields, int Nsteps) {
 
 void DNS::project() {}
 
+// q = p + s/2 (u + U e_x + W e_z)^2 pointwise; everything on the device: base profiles are added to the (0,0) mode, the
+// kinetic energy is one pointwise kernel
+static void modified_pressure(const DNS& dns, FlowField& u, const FlowField& in, FlowField& out, Real sign) {
+    u.makeSpectral();
+    std::vector<ChebyCoeff> UW = {dns.Ubase(), dns.Wbase()};
+    if (UW[0].length() == 0) UW[0] = ChebyCoeff(u.Ny(), u.a(), u.b(), Spectral);
+    if (UW[1].length() == 0) UW[1] = ChebyCoeff(u.Ny(), u.a(), u.b(), Spectral);
+    UW[0].makeSpectral();
+    UW[1].makeSpectral();
+    u += UW;
+    FlowField e;
+    energy(u, e);  // 1/2 |u_tot|^2, spectral on return
+    FlowField tmp(in);
+    tmp.makeSpectral();
+    tmp.add(sign, e);
+    tmp.makeState(in.xzstate(), in.ystate());
+    out = tmp;
+}
+void DNS::uq2p(FlowField u, FlowField q, FlowField& p) const {
+    if (flags().nonlinearity != Rotational) { p = q; return; }
+    modified_pressure(*this, u, q, p, -1.0);
+}
+void DNS::up2q(FlowField u, FlowField p, FlowField& q) const {
+    if (flags().nonlinearity != Rotational) { q = p; return; }
+    modified_pressure(*this, u, p, q, 1.0);
+}
+
 void DNS::reset_dt(Real dt) {
     main_algorithm_->reset_dt(dt);
     if (init_algorithm_) init_algorithm_->reset_dt(dt);

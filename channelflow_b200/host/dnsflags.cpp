@@ -89,6 +89,123 @@ std::ostream& operator<<(std::ostream& os, TimeStepMethod t) { return os << step
 std::ostream& operator<<(std::ostream& os, NonlinearMethod n) { return os << nonlmethod2string(n); }
 std::ostream& operator<<(std::ostream& os, Dealiasing d) { return os << dealiasing2string(d); }
 
+std::ostream& operator<<(std::ostream& os, VelocityScale v) { return os << (v == WallScale ? "WallScale" : "ParabolicScale"); }
+std::ostream& operator<<(std::ostream& os, Verbosity v) {
+    static const char* n[] = {"Silent", "PrintTime", "PrintTicks", "VerifyTauSolve", "PrintAll"};
+    return os << n[(int)v];
+}
+
+// ---- BodyForce (never evaluated by the time steppers, see the header)
+Vector BodyForce::operator()(Real x, Real y, Real z, Real t) {
+    Vector f(3);
+    eval(x, y, z, t, f[0], f[1], f[2]);
+    return f;
+}
+void BodyForce::eval(Real, Real, Real, Real, Real& fx, Real& fy, Real& fz) { fx = fy = fz = 0.0; }
+bool BodyForce::isOn(Real) { return false; }
+void BodyForce::eval(Real t, FlowField& f) {
+    f.makePhysical();
+    for (int ny = 0; ny < f.Ny(); ++ny)
+        for (int nx = 0; nx < f.Nx(); ++nx)
+            for (int nz = 0; nz < f.Nz(); ++nz) eval(f.x(nx), f.y(ny), f.z(nz), t, f(nx, ny, nz, 0), f(nx, ny, nz, 1), f(nx, ny, nz, 2));
+    f.makeSpectral();
+}
+
+// ---- command-line construction: option names, defaults and help texts are the user interface of the reference's
+// programs (dnsflags.cpp:160-264) and are kept verbatim
+DNSFlags::DNSFlags(ArgList& args, const bool laurette) : DNSFlags() {
+    args.section("System parameters");
+    const Real Reynolds = args.getreal("-R", "--Reynolds", 400, "pseudo-Reynolds number == 1/nu");
+    const Real nuarg = args.getreal("-nu", "--nu", 0, "kinematic viscosity (takes precedence over Reynolds, if nonzero)");
+    nu = nuarg != 0 ? nuarg : 1.0 / Reynolds;
+    args2BC(args);
+    args2numerics(args, laurette);
+}
+void DNSFlags::args2BC(ArgList& args) {
+    args.section("Boundary conditions");
+    baseflow = s2baseflow(args.getstr("-bf", "--baseflow", "laminar", "set base flow to one of [zero|laminar|linear|parabolic|suction|arbitrary]"));
+    constraint = s2constraint(args.getstr("-mc", "--meanconstraint", "gradp", "fix one of two flow constraints [gradp|bulkv]"));
+    const Real dPds = args.getreal("-dPds", "--dPds", 0.0, "magnitude of imposed pressure gradient along streamwise s");
+    const Real Ub = args.getreal("-Ubulk", "--Ubulk", 0.0, "magnitude of imposed bulk velocity");
+    Uwall = args.getreal("-Uwall", "--Uwall", 1.0, "magnitude of imposed wall velocity, +/-Uwall at y = +/-h");
+    theta = args.getreal("-theta", "--theta", 0.0, "angle of base flow relative to x-axis");
+    Vsuck = args.getreal("-Vs", "--Vsuck", 0.0, "wall-normal suction velocity");
+    rotation = args.getreal("-rot", "--rotation", 0.0, "rotation around the z-axis");
+    const Real c = cos(theta), sn = sin(theta);
+    ulowerwall = -Uwall * c; uupperwall = Uwall * c;
+    wlowerwall = -Uwall * sn; wupperwall = Uwall * sn;
+    dPdx = dPds * c; dPdz = dPds * sn;
+    Ubulk = Ub * c; Wbulk = Ub * sn;
+}
+void DNSFlags::args2numerics(ArgList& args, const bool laurette) {
+    args.section("Numerical setup");
+    dealiasing = s2dealiasing(args.getstr("-da", "--dealiasing", "DealiasXZ", "define dealiasing behavior, one of [NoDealiasing|DealiasXZ|DealiasY|DealiasXYZ]"));
+    t0 = args.getreal("-T0", "--T0", 0.0, "start time of DNS or period of map f^T(u)");
+    T = args.getreal("-T", "--T1", 20.0, "final time of DNS or period of map f^T(u)");
+    dT = args.getreal("-dT", "--dT", 1.0, "save interval");
+    dt = args.getreal("-dt", "--dt", 0.03125, "timestep");
+    variabledt = args.getbool("-vdt", "--variabledt", true, "adjust dt to keep CFLmin<=CFL<CFLmax");
+    dtmin = args.getreal("-dtmin", "--dtmin", 0.001, "minimum time step");
+    dtmax = args.getreal("-dtmax", "--dtmax", 0.2, "maximum time step");
+    CFLmin = args.getreal("-CFLmin", "--CFLmin", 0.40, "minimum CFL number");
+    CFLmax = args.getreal("-CFLmax", "--CFLmax", 0.60, "maximum CFL number");
+    timestepping = s2stepmethod(args.getstr("-ts", "--timestepping", "sbdf3", "timestepping algorithm,  one of [cnfe1|cnab2|cnrk2|smrk2|sbdf1|sbdf2|sbdf3|sbdf4]"));
+    initstepping = s2stepmethod(args.getstr("-is", "--initstepping", "smrk2",
+                                            "timestepping algorithm for initializing multistep algorithms,  one of [cnfe1|cnrk2|smrk2|sbdf1]"));
+    nonlinearity = s2nonlmethod(args.getstr("-nl", "--nonlinearity", "rot", "method of calculating nonlinearity, one of [rot|conv|div|skew|alt|linear]"));
+    symmetryprojectioninterval = args.getint("-symmpi", "--symmetryprojection", 100, "project onto symmetries at this time interval");
+    const std::string symmstr = args.getstr("-symms", "--symmetries", "",
+                                            "constrain u(t) to invariant symmetric subspace, argument is the filename for a file listing the "
+                                            "generators of the isotropy group");
+    verbosity = Silent;
+    if (!symmstr.empty()) symmetries_file = symmstr;
+    if (laurette) {
+        dT = T; dt = T; dtmax = T;
+        variabledt = false;
+        initstepping = timestepping = SBDF1;
+    }
+}
+// one "value  %name" line per flag, the form DNSFlags::load reads back (dnsflags.cpp:610-740)
+void DNSFlags::save(const std::string& outdir) const {
+    if (mpirank() != 0) return;
+    std::ofstream os((pathfix(outdir) + "dnsflags.txt").c_str());
+    if (!os.good()) cferror("DNSFlags::save(outdir) :  can't open file " + outdir + "dnsflags.txt");
+    os << std::setprecision(REAL_DIGITS);
+    auto line = [&](auto v, const char* name) { os << std::left << std::setw(REAL_IOWIDTH) << v << "  %" << name << "\n"; };
+    line(nu, "nu"); line(Vsuck, "Vsuck"); line(rotation, "rotation"); line(theta, "theta");
+    line(dPdx, "dPdx"); line(dPdz, "dPdz"); line(Ubulk, "Ubulk"); line(Wbulk, "Wbulk"); line(Uwall, "Uwall");
+    line(ulowerwall, "ulowerwall"); line(uupperwall, "uupperwall"); line(wlowerwall, "wlowerwall"); line(wupperwall, "wupperwall");
+    line(t0, "t0"); line(T, "T"); line(dT, "dT"); line(dt, "dt"); line(variabledt, "variabledt");
+    line(dtmin, "dtmin"); line(dtmax, "dtmax"); line(CFLmin, "CFLmin"); line(CFLmax, "CFLmax");
+    line(symmetryprojectioninterval, "symmetryprojectioninterval");
+    line(baseflow, "baseflow"); line(constraint, "constraint"); line(timestepping, "timestepping"); line(initstepping, "initstepping");
+    line(nonlinearity, "nonlinearity"); line(dealiasing, "dealiasing");
+    line(bodyforce ? "nonzero_bodyforce" : "zero_bodyforce", "bodyforce");
+    line(taucorrection, "taucorrection"); line(verbosity, "verbosity");
+}
+void DNSFlags::load(int, const std::string indir) {
+    std::ifstream is((pathfix(indir) + "dnsflags.txt").c_str());
+    if (!is.good()) cferror("DNSFlags::load(taskid, indir): can't open file " + indir + "dnsflags.txt");
+    std::string value, name;
+    while (is >> value >> name) {
+        const Real r = std::atof(value.c_str());
+        if (name == "%nu") nu = r; else if (name == "%Vsuck") Vsuck = r; else if (name == "%rotation") rotation = r;
+        else if (name == "%theta") theta = r; else if (name == "%dPdx") dPdx = r; else if (name == "%dPdz") dPdz = r;
+        else if (name == "%Ubulk") Ubulk = r; else if (name == "%Wbulk") Wbulk = r; else if (name == "%Uwall") Uwall = r;
+        else if (name == "%ulowerwall") ulowerwall = r; else if (name == "%uupperwall") uupperwall = r;
+        else if (name == "%wlowerwall") wlowerwall = r; else if (name == "%wupperwall") wupperwall = r;
+        else if (name == "%t0") t0 = r; else if (name == "%T") T = r; else if (name == "%dT") dT = r; else if (name == "%dt") dt = r;
+        else if (name == "%variabledt") variabledt = value != "0"; else if (name == "%dtmin") dtmin = r; else if (name == "%dtmax") dtmax = r;
+        else if (name == "%CFLmin") CFLmin = r; else if (name == "%CFLmax") CFLmax = r;
+        else if (name == "%symmetryprojectioninterval") symmetryprojectioninterval = (int)r;
+        else if (name == "%baseflow") baseflow = s2baseflow(value); else if (name == "%constraint") constraint = s2constraint(value);
+        else if (name == "%timestepping") timestepping = s2stepmethod(value); else if (name == "%initstepping") initstepping = s2stepmethod(value);
+        else if (name == "%nonlinearity") nonlinearity = s2nonlmethod(value); else if (name == "%dealiasing") dealiasing = s2dealiasing(value);
+        else if (name == "%bodyforce") { if (value != "zero_bodyforce") cferror("bodyforce not zero, this is not implemented for a restart."); }
+        else if (name == "%taucorrection") taucorrection = value != "0"; else if (name == "%verbosity") verbosity = s2verbosity(value);
+    }
+}
+
 std::ostream& operator<<(std::ostream& os, const DNSFlags& f) {
     const char* s = ", ";
     const auto p = os.precision();

@@ -85,6 +85,8 @@ int cfgpu_field_upload_padded(cfgpu_field f, const double* data_h, int ystate);
 int cfgpu_field_download_padded(cfgpu_field f, double* data_h);
 int cfgpu_field_copy(cfgpu_field dst, cfgpu_field src);
 int cfgpu_field_swap(cfgpu_field a, cfgpu_field b);
+/* component js of src -> component jd of dst (FlowField::operator[](int), flowfield.cpp:1532-1560) */
+int cfgpu_field_copy_component(cfgpu_field dst, int jd, cfgpu_field src, int js);
 int cfgpu_field_zero(cfgpu_field f);
 int cfgpu_field_set_state(cfgpu_field f, int xzstate, int ystate);
 int cfgpu_field_get_state(cfgpu_field f, int* xzstate, int* ystate);
@@ -122,6 +124,21 @@ int cfgpu_l2norm2(cfgpu_field u, int normalize, double* out_h);
 int cfgpu_l2norm2_3d(cfgpu_field u, int normalize, double* out_h);
 int cfgpu_l2dist2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h);
 int cfgpu_l2ip(cfgpu_field u, cfgpu_field v, int normalize, double* out_h);
+
+/* L2Norm2 / L2Dist2 / L2InnerProduct (mode 0 / 1 / 2) over the modes |kx| <= kxmax, kz <= kzmax (diffops.cpp:543-700);
+ * cz = 0 drops the factor 2 of the kz > 0 modes (divNorm2's convention, diffops.cpp:91-116) */
+int cfgpu_l2form_box(cfgpu_field u, cfgpu_field v, int mode, int kxmax, int kzmax, int cz, int normalize, double* out_h);
+/* bcNorm2 / bcDist2 (diffops.cpp:18-83); v may be NULL */
+int cfgpu_bcnorm2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h);
+
+/* ---------------------------------------------------------------- whole-field operators (diagnostics, initial data)
+ * Linear differential operator on a spectral field: out[out_c[k]] += coef[k] d^nx/dx^nx d^ny/dy^ny d^nz/dz^nz in[in_c[k]]
+ * (at most 3 terms per output component, ny <= 2): xdiff/ydiff/zdiff/diff, grad, lapl, curl, div of diffops.cpp:1650-2558 */
+int cfgpu_field_diffop(cfgpu_field out, cfgpu_field in, int nterms, const int* out_c, const int* in_c, const int* nx, const int* ny,
+                       const int* nz, const double* coef);
+/* Pointwise products of physical fields: op 0 cross, 1 outer (f_i g_j -> component i*gd+j), 2 dot, 3 |f|^2, 4 |f|, 5 energy
+ * 1/2 |f|^2, 6 componentwise product (diffops.cpp:2336-2700) */
+int cfgpu_field_pointwise(int op, cfgpu_field out, cfgpu_field f, cfgpu_field g /* NULL for ops 3-5 */);
 
 /* ---------------------------------------------------------------- NSE operator (channelflow/nse.h:23-141)
  * enums follow channelflow/dnsflags.h:24-41 */
