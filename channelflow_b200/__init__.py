@@ -31,6 +31,7 @@ cfgpu_nse_destroy cfgpu_nse_set_constraint cfgpu_nse_reset_lambda cfgpu_nse_nonl
 cfgpu_nse_linear cfgpu_nse_cflfactor cfgpu_nse_get_dPd cfgpu_comm_unique_id cfgpu_comm_init_nccl
 cfgpu_comm_init_external cfgpu_comm_rank cfgpu_comm_ranges cfgpu_field_allgather
 cfgpu_field_copy_component cfgpu_l2form_box cfgpu_bcnorm2 cfgpu_field_diffop cfgpu_field_pointwise
+cfgpu_helmholtz_solve cfgpu_tridiag cfgpu_tausolve_mode cfgpu_poisson_solve cfgpu_pressure_neumann
 cfgpu_vec_create cfgpu_vec_destroy cfgpu_vec_size cfgpu_vec_upload cfgpu_vec_download cfgpu_vec_copy cfgpu_vec_zero cfgpu_vec_dot
 cfgpu_vec_nrm2 cfgpu_vec_axpy cfgpu_vec_axpby cfgpu_vec_scal cfgpu_field2vector_size cfgpu_field2vector cfgpu_vector2field""".split()
 
@@ -100,6 +101,11 @@ class GpuLib:
         L.cfgpu_nse_linear.argtypes = [vp, vp, vp, vp]
         L.cfgpu_nse_cflfactor.argtypes = [vp, vp, dpt]
         L.cfgpu_nse_get_dPd.argtypes = [vp, dpt, dpt]
+        L.cfgpu_poisson_solve.argtypes = [vp, vp, vp]
+        L.cfgpu_pressure_neumann.argtypes = [vp, vp, vp, d]
+        L.cfgpu_helmholtz_solve.argtypes = [vp, i, d, d, d, d, i, dpt, dpt, dpt, dpt]
+        L.cfgpu_tridiag.argtypes = [vp, i, i, dpt, dpt, dpt, dpt, i, i, i]
+        L.cfgpu_tausolve_mode.argtypes = [vp, i, i, i, d, d, d, d, d, d, i, i, d, d, dpt, dpt, dpt]
 
     def check(self, status):
         if status != 0:
@@ -133,6 +139,29 @@ class Context:
 
     def field(self, Nx, Ny, Nz, Nd, Lx, Lz, a=-1.0, b=1.0):
         return Field(self, Nx, Ny, Nz, Nd, Lx, Lz, a, b)
+
+    def helmholtz_solve(self, a, b, lam, nu, f, ua, ub):
+        """HelmholtzSolver::solve for the rows of f [ncols][N] (real), Dirichlet data ua[ncols], ub[ncols]."""
+        import numpy as np
+        f = np.ascontiguousarray(np.atleast_2d(f), dtype=np.float64)
+        ua = np.ascontiguousarray(np.broadcast_to(ua, f.shape[:1]), dtype=np.float64)
+        ub = np.ascontiguousarray(np.broadcast_to(ub, f.shape[:1]), dtype=np.float64)
+        u = np.empty_like(f)
+        dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+        self.lib.check(self.lib.L.cfgpu_helmholtz_solve(self.h, f.shape[1], a, b, lam, nu, f.shape[0], dp(f), dp(ua), dp(ub), dp(u)))
+        return u
+
+    def tausolve_mode(self, kx, kz, Lx, Lz, a, b, lam, nu, Rx, Ry, Rz, taucorr=True, bulk=None):
+        """TauSolver::solve for one Fourier mode: complex profiles in, (u, v, w, P[, dPdx, dPdz]) out."""
+        import numpy as np
+        R = np.ascontiguousarray(np.stack([Rx, Ry, Rz]), dtype=np.complex128)
+        out = np.empty((4, R.shape[1]), np.complex128)
+        dPd = np.zeros(2)
+        dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+        um, wm = bulk if bulk is not None else (0.0, 0.0)
+        self.lib.check(self.lib.L.cfgpu_tausolve_mode(self.h, R.shape[1], kx, kz, Lx, Lz, a, b, lam, nu, 1 if taucorr else 0,
+                                                      0 if bulk is None else 1, um, wm, dp(R), dp(out), dp(dPd)))
+        return (out[0], out[1], out[2], out[3]) + ((dPd[0], dPd[1]) if bulk is not None else ())
 
 
 class Field:

@@ -6,6 +6,7 @@
 #include "cfgpu_internal.h"
 #include "diffops.cuh"
 #include "fieldops.cuh"
+#include "tau.cuh"
 
 namespace cfgpu {
 
@@ -923,6 +924,37 @@ int cfgpu_bcnorm2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h) {
     CF_CUDA(cudaMemcpyAsync(&r, ctx->ws_red.ptr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CF_CUDA(cudaStreamSynchronize(ctx->stream));
     *out_h = normalize ? r : r * u->Lx * u->Lz;
+    return 0;
+}
+// PoissonSolver::solve (poissonsolver.cpp:146-202)
+int cfgpu_poisson_solve(cfgpu_field u, cfgpu_field f, cfgpu_field bc) {
+    CF_ARG(u && f && u != f && same_shape(u, f) && (!bc || same_shape(bc, f)), "cfgpu_poisson_solve: bad argument");
+    CF_ARG(f->xzstate == CFGPU_SPECTRAL && f->ystate == CFGPU_SPECTRAL, "cfgpu_poisson_solve: f must be spectral");
+    CF_ARG(!bc || (bc->xzstate == CFGPU_SPECTRAL && bc->ystate == CFGPU_SPECTRAL), "cfgpu_poisson_solve: bc must be spectral");
+    CF_ARG(u->ctx->comm.nranks == 1, "cfgpu_poisson_solve: single-GPU call");
+    CF_TRY(field_serial(f)); if (bc) CF_TRY(field_serial(bc));
+    CF_TRY(field_serial_output(u));
+    CF_TRY(poisson_launch(f->Nx, f->Ny, f->Nz, f->Nd, f->Lx, f->Lz, f->a, f->b, f->dser, bc ? bc->dser : nullptr, u->dser, u->ctx->stream));
+    u->xzstate = u->ystate = CFGPU_SPECTRAL;
+    u->padded = 0;
+    u->clean_Kx = u->clean_Kz = -1;
+    return 0;
+}
+// PressureSolver::solve step II (poissonsolver.cpp:352-431): g = the homogeneous correction for dp/dy = nu v_yy at the walls
+int cfgpu_pressure_neumann(cfgpu_field g, cfgpu_field p, cfgpu_field u, double nu) {
+    CF_ARG(g && p && u && g != p && g->Nd == 1 && p->Nd == 1 && u->Nd == 3, "cfgpu_pressure_neumann: g, p scalar fields, u a 3-vector field");
+    CF_ARG(g->Nx == p->Nx && g->Ny == p->Ny && g->Nz == p->Nz && u->Nx == p->Nx && u->Ny == p->Ny && u->Nz == p->Nz,
+           "cfgpu_pressure_neumann: grid mismatch");
+    CF_ARG(p->xzstate == CFGPU_SPECTRAL && p->ystate == CFGPU_SPECTRAL && u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL,
+           "cfgpu_pressure_neumann: p and u must be spectral");
+    CF_ARG(p->ctx->comm.nranks == 1, "cfgpu_pressure_neumann: single-GPU call");
+    CF_TRY(field_serial(p)); CF_TRY(field_serial(u));
+    CF_TRY(field_serial_output(g));
+    const FieldGeom fg{p->Nx, p->Ny, p->Nz, p->Lx, p->Lz, p->a, p->b};
+    CF_TRY(pressure_neumann_launch(p->dser, u->dser + u->compstride(), nu, fg, g->dser, p->ctx->stream));
+    g->xzstate = CFGPU_SPECTRAL; g->ystate = CFGPU_PHYSICAL;
+    g->padded = 0;
+    g->clean_Kx = g->clean_Kz = -1;
     return 0;
 }
 // generic linear differential operator on a spectral field (xdiff/ydiff/zdiff/grad/lapl/curl/div of diffops.cpp)

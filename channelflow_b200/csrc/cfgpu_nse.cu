@@ -1010,6 +1010,99 @@ int cfgpu_nse_cflfactor(cfgpu_nse nse, cfgpu_field u, double* out_h) {
     return 0;
 }
 
+// ---- single systems for the host classes HelmholtzSolver / BandedTridiag / TauSolver (tests, tools): host arrays in and
+// out, the arithmetic on the device
+struct MinLaneBlock {  // see tau_pick_E: longer per-lane chains for the single-system classes, restored on scope exit
+    int old;
+    explicit MinLaneBlock(int e) : old(tau_set_min_E(e)) {}
+    ~MinLaneBlock() { tau_set_min_E(old); }
+};
+static int scratch(cfgpu_ctx ctx, size_t doubles, double** p) {
+    CF_TRY(ws_reserve(ctx->ws_red, (1 << 20) > doubles * 8 ? (1 << 20) : doubles * 8));
+    *p = ctx->ws_red.ptr;
+    return 0;
+}
+int cfgpu_helmholtz_solve(cfgpu_ctx ctx, int N, double a, double b, double lambda, double nu, int ncols, const double* f_h,
+                          const double* ua_h, const double* ub_h, double* u_h) {
+    CF_ARG(ctx && f_h && ua_h && ub_h && u_h && ncols >= 1, "cfgpu_helmholtz_solve: bad argument");
+    double* d;
+    const size_t nf = (size_t)ncols * N;
+    MinLaneBlock sequential_chains(8);
+    CF_TRY(scratch(ctx, 2 * nf + 2 * ncols, &d));
+    double *df = d, *du = d + nf, *dua = du + nf, *dub = dua + ncols;
+    CF_CUDA(cudaMemcpyAsync(df, f_h, nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CF_CUDA(cudaMemcpyAsync(dua, ua_h, ncols * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CF_CUDA(cudaMemcpyAsync(dub, ub_h, ncols * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CF_TRY(helmholtz_batch_launch(N, a, b, lambda, nu, ncols, df, dua, dub, du, ctx->stream));
+    CF_CUDA(cudaMemcpyAsync(u_h, du, nf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cfgpu_tridiag(cfgpu_ctx ctx, int op, int M, double* a_h, double* invdiag_h, double* x_h, double* y_h, int nx, int offset, int stride) {
+    CF_ARG(ctx && a_h && invdiag_h && M >= 2 && op >= 0 && op <= 2, "cfgpu_tridiag: bad argument");
+    CF_ARG(op == 0 || (x_h && nx >= offset + stride * (M - 1) + 1 && (offset == 0 || offset == 1) && (stride == 1 || stride == 2)),
+           "cfgpu_tridiag: offset must be 0 or 1, stride 1 or 2");
+    double* d;
+    const size_t na = 4 * (size_t)M - 2;
+    CF_TRY(scratch(ctx, na + M + 2 * (size_t)(nx > 0 ? nx : 1), &d));
+    double *da = d, *di = d + na, *dx = di + M, *dy = dx + (nx > 0 ? nx : 1);
+    CF_CUDA(cudaMemcpyAsync(da, a_h, na * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CF_CUDA(cudaMemcpyAsync(di, invdiag_h, M * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (op != 0) CF_CUDA(cudaMemcpyAsync(dx, x_h, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (op == 2) CF_CUDA(cudaMemcpyAsync(dy, y_h, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));  // untouched entries survive
+    CF_TRY(tridiag_launch(op, M, da, di, dx, dy, offset, stride, ctx->stream));
+    if (op == 0) {
+        CF_CUDA(cudaMemcpyAsync(a_h, da, na * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CF_CUDA(cudaMemcpyAsync(invdiag_h, di, M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (op == 1) CF_CUDA(cudaMemcpyAsync(x_h, dx, nx * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    else CF_CUDA(cudaMemcpyAsync(y_h, dy, nx * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+// TauSolver::solve for ONE Fourier mode (tausolver.cpp:347-450) through the batched kernels: a throw-away operator on the
+// smallest grid that holds the mode (un-dealiased: every mode below the Nyquist ones is solved), the right-hand side in
+// that mode.  constraint 1: mean mode with prescribed bulk velocities (helmholtz.cpp:158-213), returns dPdx, dPdz.
+int cfgpu_tausolve_mode(cfgpu_ctx ctx, int N, int kx, int kz, double Lx, double Lz, double a, double b, double lambda, double nu,
+                        int taucorrection, int constraint, double umean, double wmean, const double* R_h, double* out_h, double* dPd_h) {
+    CF_ARG(ctx && R_h && out_h && kz >= 0, "cfgpu_tausolve_mode: bad argument (kz >= 0: the stored half of the spectrum)");
+    CF_ARG(ctx->comm.nranks == 1, "cfgpu_tausolve_mode: single-GPU call");
+    const int ak = kx < 0 ? -kx : kx;
+    const int Nx = 2 * ak + 4, Nz = 2 * kz + 4;
+    MinLaneBlock sequential_chains(8);
+    cfgpu_nse_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.nu = nu; cfg.nonlinearity = 0; cfg.dealias_xz = 0; cfg.dealias_y = 0; cfg.taucorrection = taucorrection;
+    cfg.constraint = constraint; cfg.UbulkRef_minus_base = umean; cfg.WbulkRef_minus_base = wmean;
+    cfgpu_nse nse = nullptr;
+    cfgpu_field R = nullptr, U = nullptr, Q = nullptr;
+    int rc = 1;
+    do {
+        if (cfgpu_nse_create(ctx, Nx, N, Nz, Lx, Lz, a, b, &cfg, nullptr, nullptr, &nse)) break;
+        const double PI = 3.14159265358979323846264338327950288;
+        const double lam_t = lambda - 4.0 * (PI * PI) * nu * ((kx / Lx) * (kx / Lx) + (kz / Lz) * (kz / Lz));
+        if (cfgpu_nse_reset_lambda(nse, &lam_t, 1)) break;
+        if (cfgpu_field_create(ctx, Nx, N, Nz, 3, Lx, Lz, a, b, &R) || cfgpu_field_create(ctx, Nx, N, Nz, 3, Lx, Lz, a, b, &U) ||
+            cfgpu_field_create(ctx, Nx, N, Nz, 1, Lx, Lz, a, b, &Q))
+            break;
+        const int mx = kx >= 0 ? kx : Nx + kx;
+        bool ok = true;
+        for (int i = 0; i < 3 && ok; ++i) ok = cfgpu_field_add_profile(R, mx, kz, i, R_h + (size_t)i * 2 * N, 1.0) == 0;
+        if (!ok) break;
+        const double one = 1.0;
+        if (cfgpu_nse_solve(nse, 0, 1, &one, &R, U, Q)) break;
+        for (int i = 0; i < 3 && ok; ++i) ok = cfgpu_field_get_profile(U, mx, kz, i, out_h + (size_t)i * 2 * N) == 0;
+        ok = ok && cfgpu_field_get_profile(Q, mx, kz, 0, out_h + (size_t)3 * 2 * N) == 0;
+        if (!ok) break;
+        if (dPd_h) { if (cfgpu_nse_get_dPd(nse, dPd_h, dPd_h + 1)) break; }
+        rc = 0;
+    } while (false);
+    if (R) cfgpu_field_destroy(R);
+    if (U) cfgpu_field_destroy(U);
+    if (Q) cfgpu_field_destroy(Q);
+    if (nse) cfgpu_nse_destroy(nse);
+    return rc;
+}
+
 int cfgpu_nse_get_dPd(cfgpu_nse nse, double* dPdx_h, double* dPdz_h) {
     double v[2];
     if (nse->ctx->comm.nranks > 1) {  // only the owner of the (0,0) mode computed them; the others hold zeros

@@ -204,6 +204,57 @@ int pointwise_launch(int op, const double* f, const double* g, double* out, int 
     CF_KERNEL_CHECK();
     return 0;
 }
+// PressureSolver::solve, step II (poissonsolver.cpp:352-431): the homogeneous correction that turns the Dirichlet solution of
+// lapl p = -div N(u) into the one with dp/dy = nu d2v/dy2 at both walls.  Per Fourier mode (not the mean mode):
+//   alpha = nu v''(a) - p'(a),  beta = nu v''(b) - p'(b),  mu = sqrt(lambda),  H = b - a,
+//   g(y) = c exp(-mu (y-a)) + d exp(mu (y-b)),  c = (-alpha + beta e^{-mu H}) / delta,  d = (beta - alpha e^{-mu H}) / delta,
+//   delta = mu (1 - e^{-2 mu H}).
+// Wall derivatives from the Chebyshev coefficients in closed form: T_n'(+-1) = (+-1)^{n+1} n^2, T_n''(+-1) = (+-1)^n n^2 (n^2-1)/3.
+// One thread per (kx, kz) column, adjacent threads adjacent in kz: coalesced.  g is written at the Gauss-Lobatto points
+// (y-physical, xz-spectral); the caller transforms it with the y-GEMM and adds it to p.
+__global__ void __launch_bounds__(DO_THREADS) pressure_neumann_kernel(const double2* __restrict__ p, const double2* __restrict__ v, double nu,
+                                                                      FieldGeom g, double2* __restrict__ out) {
+    const int Mz = g.Nz / 2 + 1, N = g.Ny;
+    const long ncol = (long)g.Nx * Mz;
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    const int mz = (int)(c % Mz), mx = (int)(c / Mz);
+    const int kx = mx <= g.Nx / 2 ? mx : mx - g.Nx;
+    const long rs = ncol;
+    if (mx == 0 && mz == 0) {
+        for (int j = 0; j < N; ++j) out[j * rs + c] = make_double2(0.0, 0.0);
+        return;
+    }
+    const double H = g.b - g.a, s1 = 2.0 / H, s2 = s1 * s1;
+    double2 pa = {0, 0}, pb = {0, 0}, va = {0, 0}, vb = {0, 0};
+    for (int n = N - 1; n >= 1; --n) {
+        const double n2 = (double)n * n, w1 = s1 * n2, w2 = s2 * n2 * (n2 - 1.0) / 3.0;
+        const double sg = (n & 1) ? -1.0 : 1.0;  // (-1)^n
+        const double2 pc = p[n * rs + c], vc = v[n * rs + c];
+        pb.x += w1 * pc.x; pb.y += w1 * pc.y;
+        pa.x -= sg * w1 * pc.x; pa.y -= sg * w1 * pc.y;
+        vb.x += w2 * vc.x; vb.y += w2 * vc.y;
+        va.x += sg * w2 * vc.x; va.y += sg * w2 * vc.y;
+    }
+    const double2 alpha = make_double2(nu * va.x - pa.x, nu * va.y - pa.y), beta = make_double2(nu * vb.x - pb.x, nu * vb.y - pb.y);
+    const double lambda = TWO_PI * TWO_PI * ((kx / g.Lx) * (kx / g.Lx) + (mz / g.Lz) * (mz / g.Lz));
+    const double mu = sqrt(lambda), em = exp(-mu * H), delta = mu * (1.0 - exp(-2.0 * mu * H));
+    const double2 cc = make_double2((-alpha.x + beta.x * em) / delta, (-alpha.y + beta.y * em) / delta);
+    const double2 dd = make_double2((beta.x - alpha.x * em) / delta, (beta.y - alpha.y * em) / delta);
+    const double PI_ = 0.5 * TWO_PI;
+    for (int j = 0; j < N; ++j) {
+        const double y = 0.5 * ((g.b + g.a) + (g.b - g.a) * cos(PI_ * j / (N - 1)));
+        const double ea = exp(-mu * (y - g.a)), eb = exp(mu * (y - g.b));
+        out[j * rs + c] = make_double2(cc.x * ea + dd.x * eb, cc.y * ea + dd.y * eb);
+    }
+}
+int pressure_neumann_launch(const double* p, const double* v, double nu, const FieldGeom& g, double* out, cudaStream_t st) {
+    const long ncol = (long)g.Nx * (g.Nz / 2 + 1);
+    CF_LAUNCH(pressure_neumann_kernel, dim3((unsigned)((ncol + DO_THREADS - 1) / DO_THREADS)), dim3(DO_THREADS), 0, st,
+              reinterpret_cast<const double2*>(p), reinterpret_cast<const double2*>(v), nu, g, reinterpret_cast<double2*>(out));
+    CF_KERNEL_CHECK();
+    return 0;
+}
 int bcnorm2_launch(const double* u, const double* v, int Nx, int Ny, int Nz, int Nd, int yspectral, double* partial, size_t cap,
                    double* out_dev, cudaStream_t st) {
     const int Mz = Nz / 2 + 1;

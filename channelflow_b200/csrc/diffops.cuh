@@ -26,5 +26,8 @@ int pointwise_launch(int op, const double* f, const double* g, double* out, int 
 // sum over components and all (mx, mz) of |u(a) - v(a)|^2 + |u(b) - v(b)|^2 (v may be null); ystate: 1 spectral, 0 physical
 int bcnorm2_launch(const double* u, const double* v, int Nx, int Ny, int Nz, int Nd, int yspectral, double* partial, size_t cap,
                    double* out_dev, cudaStream_t st);
+// homogeneous Neumann correction of the pressure Poisson problem (poissonsolver.cpp:352-431): p, v spectral scalar fields
+// (serial layout), out = g at the Gauss-Lobatto points (xz-spectral, y-physical)
+int pressure_neumann_launch(const double* p, const double* v, double nu, const FieldGeom& g, double* out, cudaStream_t st);
 
 }  // namespace cfgpu

@@ -922,6 +922,273 @@ __global__ void __launch_bounds__(TAU_THREADS) linear_kernel(const TauSolveParam
     }
 }
 
+// =================================================================================================== 1-d solver classes
+// Device back ends of the host classes HelmholtzSolver (helmholtz.cpp:18-95) and BandedTridiag (bandedtridiag.cpp:212-333)
+// for single systems / small batches (tests, tools): the same column solver as the time-stepping kernels, with the
+// operator's UL factors built in shared memory by the CTA itself.
+
+// ncols real right-hand sides f[c][N] -> solutions u[c][N] of  nu u'' - lambda u = f, u(a) = ua[c], u(b) = ub[c]
+template <int E>
+__global__ void __launch_bounds__(TAU_THREADS) helmholtz_batch_kernel(int N, double a, double b, double lambda, double nu, int ncols,
+                                                                      const double* __restrict__ f, const double* __restrict__ ua,
+                                                                      const double* __restrict__ ub, double* __restrict__ u) {
+    const int Nb = N - 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TAU_THREADS / 32;
+    const int NP = tau_col_pitch(N, E);
+    double* up = dyn_smem<double>();      // skewed columns: up, inv, band, then the B rows [3][NP]
+    double* inv = up + NP; double* band = inv + NP; double* bt = band + NP;
+    for (int i = tid; i < 6 * NP; i += TAU_THREADS) up[i] = 0.0;
+    __syncthreads();
+    for (int n = tid; n < N; n += TAU_THREADS) {
+        const int s = col_addr<E>(n);
+        bt[s] = n >= 2 ? B_lo(n, Nb) : 0.0;
+        bt[NP + s] = n >= 2 ? B_dg(n, Nb) : 0.0;
+        bt[2 * NP + s] = n >= 2 ? B_up(n, Nb) : 0.0;
+    }
+    if (tid < 2) {  // UL factorisation of the even / odd block (bandedtridiag.cpp:212-229), reference operation order
+        const int par = tid;
+        const double hl2 = ((b - a) / 2) * ((b - a) / 2), nus = nu / hl2;
+        const int nl = par ? Nb - 1 : Nb;
+        double dgk = A_dg(nl, Nb, lambda, nus), bandk = 1.0;
+        for (int n = nl; n >= par + 4; n -= 2) {
+            const double Akk = dgk;
+            inv[col_addr<E>(n)] = 1.0 / Akk;
+            const double w = A_lo(n, Nb, lambda);
+            const double upm = A_up(n - 2, Nb, lambda) / Akk;
+            up[col_addr<E>(n - 2)] = upm;
+            dgk = A_dg(n - 2, Nb, lambda, nus) - w * upm;
+            const double bk = bandk / Akk;
+            band[col_addr<E>(n)] = bk;
+            bandk = 1.0 - w * bk;
+        }
+        const int n1 = par + 2;
+        inv[col_addr<E>(n1)] = 1.0 / dgk;
+        const double b1 = bandk / dgk;
+        band[col_addr<E>(n1)] = b1;
+        inv[col_addr<E>(par)] = 1.0 - A_lo(n1, Nb, lambda) * b1;
+    }
+    __syncthreads();
+    for (int c = blockIdx.x * NW + warp; c < ncols; c += gridDim.x * NW) {
+        double r[E], x[E];
+        const double* fc = f + (size_t)c * N;
+#pragma unroll
+        for (int e = 0; e < E; ++e) r[e] = (lane * E + e < N) ? fc[lane * E + e] : 0.0;
+        col_solve<E, true>(r, x, up, inv, band, lambda, bt, N, lane, 0.5 * (ub[c] + ua[c]), 0.5 * (ub[c] - ua[c]), nullptr);
+        double* uc = u + (size_t)c * N;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (lane * E + e < N) uc[lane * E + e] = x[e];
+    }
+}
+
+// BandedTridiag on the device: storage a[4M-2] as in bandedtridiag.h:79-117 (row 0 reversed in front of the (up,diag,lo)
+// triplets), invdiag[M].  One warp; the recurrences are walked by lane 0 in the reference's order, the dense first row is
+// a warp reduction.  op 0: UL decomposition in place, 1: solve in place on x[offset + stride*i], 2: y = A x (strided).
+__global__ void __launch_bounds__(32) tridiag_kernel(int op, int M, double* __restrict__ a, double* __restrict__ invdiag, double* __restrict__ x,
+                                                     double* __restrict__ y, int offset, int stride) {
+    const int lane = threadIdx.x, Mb = M - 1;
+    double* d = a + Mb;
+    auto band = [&](int j) -> double& { return a[Mb - j]; };
+    auto diag = [&](int i) -> double& { return d[3 * i]; };
+    auto updiag = [&](int i) -> double& { return d[3 * i - 1]; };
+    auto lodiag = [&](int i) -> double& { return d[3 * i + 1]; };
+    auto X = [&](int i) -> double& { return x[offset + stride * i]; };
+    if (op == 0) {
+        if (lane == 0) {
+            for (int k = Mb; k > 1; --k) {
+                const double Akk = diag(k), w = lodiag(k);
+                updiag(k - 1) /= Akk;
+                diag(k - 1) -= w * updiag(k - 1);
+                band(k) /= Akk;
+                band(k - 1) -= w * band(k);
+            }
+            band(1) /= diag(1);
+            band(0) -= lodiag(1) * band(1);
+        }
+        __syncwarp();
+        for (int i = lane; i < M; i += 32) invdiag[i] = 1.0 / diag(i);
+    } else if (op == 1) {
+        if (lane == 0)
+            for (int i = Mb - 1; i > 0; --i) X(i) -= updiag(i) * X(i + 1);
+        __syncwarp();
+        double s = 0.0;
+        for (int j = 1 + lane; j < M; j += 32) s += band(j) * X(j);
+        s = warp_sum(s);
+        if (lane == 0) {
+            X(0) = (X(0) - s) / diag(0);
+            for (int i = 1; i < M; ++i) X(i) = (X(i) - lodiag(i) * X(i - 1)) * invdiag[i];
+        }
+    } else {
+        double s = 0.0;
+        for (int j = lane; j < M; j += 32) s += band(j) * X(j);
+        s = warp_sum(s);
+        if (lane == 0) y[offset] = s;
+        for (int i = 1 + lane; i < M; i += 32) {
+            double v = lodiag(i) * X(i - 1) + diag(i) * X(i);
+            if (i < Mb) v += updiag(i) * X(i + 1);
+            y[offset + stride * i] = v;
+        }
+    }
+}
+
+template <int E>
+static int helmholtz_launch_e(int N, double a, double b, double lambda, double nu, int ncols, const double* f, const double* ua,
+                              const double* ub, double* u, cudaStream_t stream) {
+    const size_t smem = (size_t)6 * tau_col_pitch(N, E) * sizeof(double);
+    const int NW = TAU_THREADS / 32;
+    int grid = (ncols + NW - 1) / NW;
+    if (grid > 148) grid = 148;  // every CTA factorises the operator once: no more CTAs than SMs
+    CF_LAUNCH(helmholtz_batch_kernel<E>, dim3(grid), dim3(TAU_THREADS), smem, stream, N, a, b, lambda, nu, ncols, f, ua, ub, u);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+int helmholtz_batch_launch(int N, double a, double b, double lambda, double nu, int ncols, const double* f, const double* ua,
+                           const double* ub, double* u, cudaStream_t stream) {
+    if (N < 5 || N % 2 == 0) { set_last_error("helmholtz: the number of Chebyshev modes must be odd and >= 5 (helmholtz.cpp:31)"); return 1; }
+    switch (tau_pick_E(N)) {
+        case 2: return helmholtz_launch_e<2>(N, a, b, lambda, nu, ncols, f, ua, ub, u, stream);
+        case 4: return helmholtz_launch_e<4>(N, a, b, lambda, nu, ncols, f, ua, ub, u, stream);
+        case 6: return helmholtz_launch_e<6>(N, a, b, lambda, nu, ncols, f, ua, ub, u, stream);
+        case 8: return helmholtz_launch_e<8>(N, a, b, lambda, nu, ncols, f, ua, ub, u, stream);
+        case 10: return helmholtz_launch_e<10>(N, a, b, lambda, nu, ncols, f, ua, ub, u, stream);
+        case 12: return helmholtz_launch_e<12>(N, a, b, lambda, nu, ncols, f, ua, ub, u, stream);
+        case 16: return helmholtz_launch_e<16>(N, a, b, lambda, nu, ncols, f, ua, ub, u, stream);
+        case 20: return helmholtz_launch_e<20>(N, a, b, lambda, nu, ncols, f, ua, ub, u, stream);
+    }
+    set_last_error("helmholtz: unsupported number of modes");
+    return 1;
+}
+int tridiag_launch(int op, int M, double* a, double* invdiag, double* x, double* y, int offset, int stride, cudaStream_t stream) {
+    CF_LAUNCH(tridiag_kernel, dim3(1), dim3(32), 0, stream, op, M, a, invdiag, x, y, offset, stride);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
+// =================================================================================================== Poisson solver
+// PoissonSolver::solve (poissonsolver.cpp:146-202): lapl u = f on every stored Fourier mode of every component, i.e. one
+// Helmholtz problem u'' - kappa^2 u = f per (component, mx, mz) with kappa^2 = 4 pi^2 (kx^2/Lx^2 + kz^2/Lz^2), Dirichlet
+// data zero or taken from the wall values of a third field bc.  One WARP per mode: lanes 0/1 run the even/odd UL
+// factorisation chains of that mode's operator into the warp's shared-memory columns (bandedtridiag.cpp:212-229, reference
+// operation order), then the warp solves the real and the imaginary column with the column solver of the tau kernels.
+// The warps of a CTA take adjacent mz, so the 16-byte accesses of one n combine to full 128-byte lines.
+template <int E>
+__global__ void __launch_bounds__(TAU_THREADS) poisson_kernel(int Nx, int N, int Nz, int Nd, double Lx, double Lz, double a, double b,
+                                                              const double2* __restrict__ f, const double2* __restrict__ bc,
+                                                              double2* __restrict__ u) {
+    const int Nb = N - 1, Mz = Nz / 2 + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = TAU_THREADS / 32;
+    const int NP = tau_col_pitch(N, E);
+    double* bt = dyn_smem<double>();             // B rows [3][NP], shared by the CTA
+    double* fac = bt + 3 * NP + warp * 3 * NP;   // this warp's up, inv, band
+    for (int i = tid; i < (3 + 3 * NW) * NP; i += TAU_THREADS) bt[i] = 0.0;
+    __syncthreads();
+    for (int n = tid; n < N; n += TAU_THREADS) {
+        const int s = col_addr<E>(n);
+        bt[s] = n >= 2 ? B_lo(n, Nb) : 0.0;
+        bt[NP + s] = n >= 2 ? B_dg(n, Nb) : 0.0;
+        bt[2 * NP + s] = n >= 2 ? B_up(n, Nb) : 0.0;
+    }
+    __syncthreads();
+    double* up = fac; double* inv = fac + NP; double* band = fac + 2 * NP;
+    const long rs = (long)Nx * Mz, cs = rs * N, items = (long)Nd * rs;
+    const double hl2 = ((b - a) / 2) * ((b - a) / 2), nus = 1.0 / hl2;
+    for (long it = (long)blockIdx.x * NW + warp; it < items; it += (long)gridDim.x * NW) {
+        const int mz = (int)(it % Mz), mx = (int)((it / Mz) % Nx), ic = (int)(it / rs);
+        const int kx = mx <= Nx / 2 ? mx : mx - Nx;
+        const double lambda = 4.0 * (PI * PI) * ((kx / Lx) * (kx / Lx) + (mz / Lz) * (mz / Lz));
+        __syncwarp();
+        if (lane < 2) {
+            const int par = lane;
+            const int nl = par ? Nb - 1 : Nb;
+            double dgk = A_dg(nl, Nb, lambda, nus), bandk = 1.0;
+            for (int n = nl; n >= par + 4; n -= 2) {
+                const double Akk = dgk;
+                inv[col_addr<E>(n)] = 1.0 / Akk;
+                const double w = A_lo(n, Nb, lambda);
+                const double upm = A_up(n - 2, Nb, lambda) / Akk;
+                up[col_addr<E>(n - 2)] = upm;
+                dgk = A_dg(n - 2, Nb, lambda, nus) - w * upm;
+                const double bk = bandk / Akk;
+                band[col_addr<E>(n)] = bk;
+                bandk = 1.0 - w * bk;
+            }
+            const int n1 = par + 2;
+            inv[col_addr<E>(n1)] = 1.0 / dgk;
+            const double b1 = bandk / dgk;
+            band[col_addr<E>(n1)] = b1;
+            inv[col_addr<E>(par)] = 1.0 - A_lo(n1, Nb, lambda) * b1;
+        }
+        __syncwarp();
+        const long col = ic * cs + (long)mx * Mz + mz;
+        double fr[E], fi[E], x[E];
+        double bsum[4] = {0.0, 0.0, 0.0, 0.0};  // wall values of bc: sum c_n and sum (-1)^n c_n, re and im
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int n = lane * E + e;
+            double2 v = make_double2(0.0, 0.0);
+            if (n < N) {
+                v = f[col + n * rs];
+                if (bc) {
+                    const double2 c = bc[col + n * rs];
+                    const double sg = (n & 1) ? -1.0 : 1.0;
+                    bsum[0] += c.x; bsum[1] += c.y; bsum[2] += sg * c.x; bsum[3] += sg * c.y;
+                }
+            }
+            fr[e] = v.x; fi[e] = v.y;
+        }
+        if (bc) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bsum[k] = warp_sum(bsum[k]);
+        }
+        // u(b) = sum c_n (upper wall), u(a) = sum (-1)^n c_n; boundary rows g0 = (ub+ua)/2, g1 = (ub-ua)/2 (helmholtz.cpp:86-87)
+        col_solve<E, true>(fr, x, up, inv, band, lambda, bt, N, lane, 0.5 * (bsum[0] + bsum[2]), 0.5 * (bsum[0] - bsum[2]), nullptr);
+#pragma unroll
+        for (int e = 0; e < E; ++e) fr[e] = x[e];
+        col_solve<E, true>(fi, x, up, inv, band, lambda, bt, N, lane, 0.5 * (bsum[1] + bsum[3]), 0.5 * (bsum[1] - bsum[3]), nullptr);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int n = lane * E + e;
+            if (n < N) u[col + n * rs] = make_double2(fr[e], x[e]);
+        }
+    }
+}
+
+template <int E>
+static int poisson_launch_e(int Nx, int N, int Nz, int Nd, double Lx, double Lz, double a, double b, const double* f, const double* bc,
+                            double* u, cudaStream_t stream) {
+    const int NW = TAU_THREADS / 32;
+    const size_t smem = (size_t)(3 + 3 * NW) * tau_col_pitch(N, E) * sizeof(double);
+    static size_t configured = 0;
+    auto kfn = poisson_kernel<E>;
+    if (smem > configured) {
+        CF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const long items = (long)Nd * Nx * (Nz / 2 + 1);
+    long grid = (items + NW - 1) / NW;
+    if (grid > 148 * 8) grid = 148 * 8;
+    CF_LAUNCH(kfn, dim3((unsigned)grid), dim3(TAU_THREADS), smem, stream, Nx, N, Nz, Nd, Lx, Lz, a, b, (const double2*)f, (const double2*)bc,
+              (double2*)u);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+int poisson_launch(int Nx, int N, int Nz, int Nd, double Lx, double Lz, double a, double b, const double* f, const double* bc, double* u,
+                   cudaStream_t stream) {
+    if (N < 5 || N % 2 == 0) { set_last_error("poisson: the number of Chebyshev modes must be odd and >= 5 (helmholtz.cpp:31)"); return 1; }
+    switch (tau_pick_E(N)) {
+        case 2: return poisson_launch_e<2>(Nx, N, Nz, Nd, Lx, Lz, a, b, f, bc, u, stream);
+        case 4: return poisson_launch_e<4>(Nx, N, Nz, Nd, Lx, Lz, a, b, f, bc, u, stream);
+        case 6: return poisson_launch_e<6>(Nx, N, Nz, Nd, Lx, Lz, a, b, f, bc, u, stream);
+        case 8: return poisson_launch_e<8>(Nx, N, Nz, Nd, Lx, Lz, a, b, f, bc, u, stream);
+        case 10: return poisson_launch_e<10>(Nx, N, Nz, Nd, Lx, Lz, a, b, f, bc, u, stream);
+        case 12: return poisson_launch_e<12>(Nx, N, Nz, Nd, Lx, Lz, a, b, f, bc, u, stream);
+        case 16: return poisson_launch_e<16>(Nx, N, Nz, Nd, Lx, Lz, a, b, f, bc, u, stream);
+        case 20: return poisson_launch_e<20>(Nx, N, Nz, Nd, Lx, Lz, a, b, f, bc, u, stream);
+    }
+    set_last_error("poisson: unsupported number of modes");
+    return 1;
+}
+
 // =================================================================================================== launchers
 int tau_pick_TM(int N, int bytes_per_mode_row) {
     const size_t budget = 190 * 1024;
@@ -931,8 +1198,21 @@ int tau_pick_TM(int N, int bytes_per_mode_row) {
 }
 
 // lane block size of the warp-parallel column solver: smallest instantiated even E with 32*E >= N
+// Lane block E: the smallest one that covers N with 32 lanes -- the most parallel choice, used by the time stepper.  A
+// larger E means fewer active lanes with longer sequential chains, i.e. arithmetic closer to the reference's sequential
+// recurrences: for spectra that decay fast the log-step scan of the forward elimination adds terms much larger than the
+// result, which shows as ~20x more round-off noise in the tau-correction amplitudes (harmless for the DNS: parity <= 1e-12;
+// visible in tausolverTest's residual measure, whose tolerance is 7x the reference's own worst case).  The single-system
+// classes (TauSolver, HelmholtzSolver) therefore ask for E >= 8 through tau_set_min_E.
+static int g_min_E = 0;
+int tau_set_min_E(int e) {
+    const int old = g_min_E;
+    g_min_E = e;
+    return old;
+}
 int tau_pick_E(int N) {
-    const int need = 2 * ((N + 63) / 64);
+    int need = 2 * ((N + 63) / 64);
+    if (need < g_min_E) need = g_min_E;
     const int avail[] = {2, 4, 6, 8, 10, 12, 16, 20};
     for (int e : avail)
         if (e >= need) return e;

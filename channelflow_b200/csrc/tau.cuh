@@ -86,8 +86,18 @@ struct TauSolveParams {
 int tau_setup_launch(const TauData& td, const ModeGeom& g, double lambda_t, cudaStream_t stream);
 void tau_btab_host(int N, double* tab /* [3*N] */);
 int tau_solve_launch(const TauSolveParams& p, cudaStream_t stream);
+// batched real Helmholtz solves with one operator (HelmholtzSolver::solve, helmholtz.cpp:79-95); all pointers device
+int helmholtz_batch_launch(int N, double a, double b, double lambda, double nu, int ncols, const double* f, const double* ua,
+                           const double* ub, double* u, cudaStream_t stream);
+// BandedTridiag::ULdecomp / ULsolveStrided / multiplyStrided (bandedtridiag.cpp:212-333): op 0 / 1 / 2; device pointers
+int tridiag_launch(int op, int M, double* a, double* invdiag, double* x, double* y, int offset, int stride, cudaStream_t stream);
+// PoissonSolver::solve (poissonsolver.cpp:146-202): lapl u = f mode by mode, Dirichlet data zero (bc == nullptr) or the wall
+// values of bc; serial-layout spectral fields [Nd][N][Nx][Nz/2+1] complex, device pointers
+int poisson_launch(int Nx, int N, int Nz, int Nd, double Lx, double Lz, double a, double b, const double* f, const double* bc, double* u,
+                   cudaStream_t stream);
 int tau_pick_TM(int N, int narrays_bytes_per_mode_row);
 int tau_pick_TM_solve(int N);
 int tau_pick_E(int N);
+int tau_set_min_E(int e);  // returns the previous setting (0 = most parallel)
 
 }  // namespace cfgpu

@@ -13,6 +13,8 @@
 
 namespace chflow {
 
+void navierstokesNL(const FlowField& u, ChebyCoeff Ubase, ChebyCoeff Wbase, FlowField& f, FlowField& tmp, DNSFlags& flags);
+
 class NSE {
    public:
     NSE();

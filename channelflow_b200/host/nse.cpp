@@ -217,6 +217,32 @@ Real NSE::cflfactor_of(const FlowField& u, const ChebyCoeff& U, const ChebyCoeff
     return r;
 }
 
+// The nonlinear term as a free function (nse.cpp:12-91): f = N(u + Ubase e_x + Wbase e_z - Vsuck e_y) in the form
+// flags.nonlinearity names, NOT de-aliased (NSE::nonlinear does that afterwards, nse.cpp:383-391); the Alternating forms
+// toggle flags.nonlinearity as in the reference.  tmp is scratch of the reference's host algorithm: unused, the device
+// pipeline owns its pencils.
+void navierstokesNL(const FlowField& u, ChebyCoeff Ubase, ChebyCoeff Wbase, FlowField& f, FlowField&, DNSFlags& flags) {
+    assert(u.xzstate() == Spectral && u.ystate() == Spectral && Ubase.state() == Spectral && Wbase.state() == Spectral);
+    cfgpu_nse_config c;
+    c.nu = flags.nu; c.Vsuck = flags.Vsuck; c.rotation = flags.rotation;
+    c.nonlinearity = (int)flags.nonlinearity;
+    c.dealias_xz = 0; c.dealias_y = 0; c.taucorrection = 1; c.constraint = 0;
+    c.dPdxRef = c.dPdzRef = c.UbulkRef_minus_base = c.WbulkRef_minus_base = 0;
+    std::vector<Real> Uc(u.Ny(), 0.0), Wc(u.Ny(), 0.0);
+    for (int n = 0; n < u.Ny() && n < Ubase.length(); ++n) Uc[n] = Ubase[n];
+    for (int n = 0; n < u.Ny() && n < Wbase.length(); ++n) Wc[n] = Wbase[n];
+    cfgpu_nse h = nullptr;
+    CK(cfgpu_nse_create(cfgpu_context(), u.Nx(), u.Ny(), u.Nz(), u.Lx(), u.Lz(), u.a(), u.b(), &c, Uc.data(), Wc.data(), &h));
+    if (!u.geomCongruent(f) || f.Nd() != 3) f.resize(u.Nx(), u.Ny(), u.Nz(), 3, u.Lx(), u.Lz(), u.a(), u.b(), u.cfmpi());
+    const int rc = cfgpu_nse_nonlinear(h, u.device(), f.device_overwrite());
+    cfgpu_nse_destroy(h);
+    CK(rc);
+    f.setState(Spectral, Spectral);
+    f.setPadded(false);
+    if (flags.nonlinearity == Alternating) flags.nonlinearity = Alternating_;
+    else if (flags.nonlinearity == Alternating_) flags.nonlinearity = Alternating;
+}
+
 // ---------------------------------------------------------------------------------------------- free functions
 Real viscosity(Real Reynolds, VelocityScale vscale, MeanConstraint constraint, Real dPdx, Real Ubulk, Real Uwall, Real h) {
     if (vscale == WallScale) return fabs(Uwall) * h / Reynolds;

@@ -140,6 +140,13 @@ int cfgpu_field_diffop(cfgpu_field out, cfgpu_field in, int nterms, const int* o
  * 1/2 |f|^2, 6 componentwise product (diffops.cpp:2336-2700) */
 int cfgpu_field_pointwise(int op, cfgpu_field out, cfgpu_field f, cfgpu_field g /* NULL for ops 3-5 */);
 
+/* PoissonSolver::solve (poissonsolver.cpp:146-202): lapl u = f for every stored Fourier mode of every component, Dirichlet
+ * data zero (bc == NULL) or the wall values of bc (poissonsolver.cpp:173-202) */
+int cfgpu_poisson_solve(cfgpu_field u, cfgpu_field f, cfgpu_field bc);
+/* PressureSolver::solve, step II (poissonsolver.cpp:352-431): g (xz-spectral, y-physical scalar field) = the homogeneous
+ * solution whose addition to the Dirichlet pressure p gives dp/dy = nu d2v/dy2 at both walls */
+int cfgpu_pressure_neumann(cfgpu_field g, cfgpu_field p, cfgpu_field u, double nu);
+
 /* ---------------------------------------------------------------- NSE operator (channelflow/nse.h:23-141)
  * enums follow channelflow/dnsflags.h:24-41 */
 typedef struct {
@@ -176,6 +183,18 @@ int cfgpu_nse_linear(cfgpu_nse nse, cfgpu_field u, cfgpu_field q, cfgpu_field L)
 int cfgpu_nse_cflfactor(cfgpu_nse nse, cfgpu_field u, double* out_h);
 /* dPdxAct_/dPdzAct_ computed by the bulk-velocity-constrained solve (nse.cpp:536) */
 int cfgpu_nse_get_dPd(cfgpu_nse nse, double* dPdx_h, double* dPdz_h);
+
+/* ---------------------------------------------------------------- 1-d solver classes (tests, tools; host arrays in and out)
+ * HelmholtzSolver::solve (helmholtz.cpp:79-95): ncols real systems nu u'' - lambda u = f, u(a) = ua, u(b) = ub */
+int cfgpu_helmholtz_solve(cfgpu_ctx ctx, int N, double a, double b, double lambda, double nu, int ncols, const double* f_h /* [ncols][N] */,
+                          const double* ua_h, const double* ub_h, double* u_h);
+/* BandedTridiag (bandedtridiag.cpp:212-333) on its own storage a[4M-2], invdiag[M]: op 0 ULdecomp (in place), 1 ULsolveStrided
+ * (x in place), 2 multiplyStrided (y = A x) */
+int cfgpu_tridiag(cfgpu_ctx ctx, int op, int M, double* a_h, double* invdiag_h, double* x_h, double* y_h, int nx, int offset, int stride);
+/* TauSolver::solve for one Fourier mode (tausolver.cpp:347-450): R_h = Rx, Ry, Rz as [3][N] complex, out_h = u, v, w, P as
+ * [4][N] complex; constraint 1 = mean mode with bulk velocities umean, wmean, returning dPdx, dPdz in dPd_h[2] */
+int cfgpu_tausolve_mode(cfgpu_ctx ctx, int N, int kx, int kz, double Lx, double Lz, double a, double b, double lambda, double nu,
+                        int taucorrection, int constraint, double umean, double wmean, const double* R_h, double* out_h, double* dPd_h);
 
 /* ---------------------------------------------------------------- state vectors of nsolver (device resident)
  * field2vector / vector2field (channelflow/flowfield.cpp:4448-4760 with fixDiri / fixDiriMean, utilfuncs.cpp:712-765): the

@@ -21,5 +21,7 @@ if [ ! -f "$o" ] || [ "$ROOT/tests/emu/cfemu.cpp" -nt "$o" ] || [ "$ROOT/tests/e
   pids+=($!)
 fi
 for p in "${pids[@]}"; do wait $p; done
-$CXX -shared -Wl,-Bsymbolic -o "$OUT/libcfgpu_emu.so" "$OUT"/obj/*.o -lpthread
+if [ ! -f "$OUT/libcfgpu_emu.so" ] || [ -n "$(find "$OUT/obj" -name '*.o' -newer "$OUT/libcfgpu_emu.so" | head -1)" ]; then
+  $CXX -shared -Wl,-Bsymbolic -o "$OUT/libcfgpu_emu.so" "$OUT"/obj/*.o -lpthread
+fi
 echo "built $OUT/libcfgpu_emu.so"

@@ -1,0 +1,137 @@
+"""Drop-in check of the class API: the reference's OWN test programs and example, compiled UNMODIFIED from
+/root/reference against channelflow_b200/host (tests/refprogs/Makefile), must pass at their own tolerances.
+
+  -m gpu        tests/_refprogs/gpu/*   linked with the product libraries, run on the B200
+  -m "not gpu"  tests/_refprogs/emu/*   linked with the CPU emulation build of the same CUDA sources (a fast subset)
+
+The binaries are built in the container that has /root/reference and travel to the GPU box (tests/_refprogs is
+git-ignored, not gpurun-ignored); nothing here reads /root/reference at run time.  Test matrix = the reference's ctest
+registrations (tests/CMakeLists.txt:57-111)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROGS = os.path.join(ROOT, "tests", "_refprogs")
+REF = "/root/reference"
+
+
+def _build(flavour):
+    if os.path.isdir(REF):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "refprogs"), flavour, "-j8"], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-4000:]
+
+
+def _write_os_data(d):
+    """tests/data/os_*.asc|cmplx (Orr-Sommerfeld eigenfunction, 65 modes, Re 7500) from the committed fixture."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "os_eig.npz"))
+    os.makedirs(d, exist_ok=True)
+    two_pi = "6.2831853071795862"
+    for name, arr, nd in (("os_ueig10_65.asc", g["ueig"], 3), ("os_peig10_65.asc", g["peig"], 1)):
+        with open(os.path.join(d, name), "w") as f:
+            f.write("%% %d 65 1 0 %s %s -1 1 P\n" % (nd, two_pi, two_pi))
+            for row in arr:
+                f.write(" ".join(repr(float(x)) for x in row) + "\n")
+    with open(os.path.join(d, "os_omega10_65.cmplx"), "w") as f:
+        f.write("%r %r\n" % (float(g["omega"][0]), float(g["omega"][1])))
+
+
+def _run(flavour, prog, args, tmp_path, timeout):
+    exe = os.path.join(PROGS, flavour, prog)
+    if not os.path.exists(exe):
+        pytest.skip("%s not built (needs /root/reference at build time)" % exe)
+    run = tmp_path / "run"
+    run.mkdir()
+    _write_os_data(str(tmp_path / "data"))
+    r = subprocess.run([exe] + list(args), cwd=str(run), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    return r
+
+
+# the reference's ctest list; the DNS programs take (algorithm, mean constraint[, base/fluctuation]) switches
+UNIT = [("tridiagTest", ()), ("chebyTest", ()), ("laminarTest", ()), ("helmholtzTest", ()), ("tausolverTest", ()),
+        ("poissonTest", ()), ("pressureTest", ())]
+ALGS = ["--cnfe1", "--cnab2", "--cnrk2", "--smrk2", "--sbdf2", "--sbdf3", "--sbdf4"]
+DNS_ZERO = [("dnsZeroTest", (a, c)) for a in ALGS for c in ("--bulkv", "--gradp")]
+DNS_PARA = [("dnsParabolaTest", (a, f, c)) for a in ALGS for f in ("--fluc", "--base") for c in ("--bulkv", "--gradp")]
+DNS_SIN = [("dnsSinusoidTest", (a, f, c)) for a in ("--cnrk2", "--sbdf3") for f in ("--zero", "--parab") for c in ("--bulkv", "--gradp")]
+
+
+def _id(p):
+    return p[0] + "".join(p[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", UNIT + DNS_ZERO + DNS_PARA + DNS_SIN, ids=_id)
+def test_reference_program_passes_on_gpu(prog, tmp_path):
+    _build("gpu")
+    r = _run("gpu", prog[0], prog[1], tmp_path, 600)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-1500:])
+    assert "pass" in r.stderr
+
+
+@pytest.mark.gpu
+def test_orr_sommerfeld_program_matches_reference_number(tmp_path):
+    """dnsOrrsommTest is commented out of the reference's ctest list: run as shipped (no arguments) it ends with
+    FinalError 1.0844443950667e-07 against its own bound 1e-07 in the reference build as well (oracle/_ref/bin).  The
+    drop-in build must print the same number."""
+    _build("gpu")
+    r = _run("gpu", "dnsOrrsommTest", (), tmp_path, 900)
+    line = [l for l in r.stdout.splitlines() if "FinalError ==" in l]
+    assert line, r.stdout[-2000:]
+    err = float(line[-1].split("FinalError ==")[1].split()[0])
+    assert abs(err - 1.0844443950667e-07) < 1e-12, err
+
+
+@pytest.mark.gpu
+def test_couette_example_runs_on_gpu(tmp_path):
+    """examples/couette.cpp: the reference's documented minimal program (DNS of a perturbed Couette flow)."""
+    _build("gpu")
+    r = _run("gpu", "couette", (), tmp_path, 900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-1500:])
+    _compare_couette(r.stdout)
+
+
+def _couette_series(text):
+    vals = {}
+    for key in ("CFL", "L2Norm(u)", "Ubulk"):
+        vals[key] = [float(l.split("==")[1]) for l in text.splitlines() if l.strip().startswith(key + " ==")]
+    return vals
+
+
+def _compare_couette(out, upto=None):
+    """Every printed time unit against the reference's own run of the same program (tests/golden/couette_ref.txt,
+    6 printed digits): 30 time units = 960 SBDF3 steps of a perturbed Couette flow."""
+    ref = _couette_series(open(os.path.join(ROOT, "tests", "golden", "couette_ref.txt")).read())
+    got = _couette_series(out)
+    n = len(ref["L2Norm(u)"]) if upto is None else upto
+    assert len(got["L2Norm(u)"]) >= n and n >= 1
+    for key in ("CFL", "L2Norm(u)"):
+        np.testing.assert_allclose(got[key][:n], ref[key][:n], rtol=2e-5)
+    np.testing.assert_allclose(got["Ubulk"][:n], ref["Ubulk"][:n], rtol=2e-4, atol=1e-9)
+
+
+EMU_FAST = [("tridiagTest", ()), ("chebyTest", ()), ("laminarTest", ()), ("helmholtzTest", ()), ("poissonTest", ()),
+            ("dnsZeroTest", ("--sbdf3", "--gradp")), ("pressureTest", ())]
+
+
+@pytest.mark.parametrize("prog", EMU_FAST, ids=_id)
+def test_reference_program_passes_on_emulation(prog, tmp_path):
+    from tests import parity
+    parity.emu_lib()
+    _build("emu")
+    r = _run("emu", prog[0], prog[1], tmp_path, 900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-1500:])
+    assert "pass" in r.stderr
+
+
+@pytest.mark.slow
+@pytest.mark.skipif(not os.environ.get("CF_SLOW_TESTS"), reason="70 s on the CPU emulation; set CF_SLOW_TESTS=1 (the GPU run covers it)")
+def test_tausolver_program_passes_on_emulation(tmp_path):
+    from tests import parity
+    parity.emu_lib()
+    _build("emu")
+    r = _run("emu", "tausolverTest", (), tmp_path, 1800)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-1500:])
