@@ -21,7 +21,7 @@ PHYSICAL, SPECTRAL = 0, 1
 
 # every symbol include/cfgpu.h declares
 CFGPU_SYMBOLS = """cfgpu_last_error cfgpu_version cfgpu_init cfgpu_finalize cfgpu_sync cfgpu_launch_count cfgpu_timer_start
-cfgpu_timer_stop cfgpu_profile_enable cfgpu_profile_read cfgpu_graph_begin cfgpu_graph_end cfgpu_graph_launch cfgpu_field_create cfgpu_field_destroy
+cfgpu_timer_stop cfgpu_profile_enable cfgpu_profile_read cfgpu_graph_begin cfgpu_graph_end cfgpu_graph_launch cfgpu_graph_abort cfgpu_graph_destroy cfgpu_field_create cfgpu_field_destroy
 cfgpu_host_alloc cfgpu_host_free cfgpu_field_upload cfgpu_field_download cfgpu_field_upload_padded cfgpu_field_download_padded cfgpu_field_copy cfgpu_field_swap cfgpu_field_zero cfgpu_field_set_state
 cfgpu_field_get_state cfgpu_field_set_padded cfgpu_field_get_padded cfgpu_field_device_ptr cfgpu_field_axpby
 cfgpu_field_scale cfgpu_field_get_profile cfgpu_field_add_profile cfgpu_field_zero_padded_modes
@@ -72,6 +72,8 @@ class GpuLib:
         L.cfgpu_graph_begin.argtypes = [vp]
         L.cfgpu_graph_end.argtypes = [vp, C.POINTER(i)]
         L.cfgpu_graph_launch.argtypes = [vp, i]
+        L.cfgpu_graph_abort.argtypes = [vp]
+        L.cfgpu_graph_destroy.argtypes = [vp, i]
         L.cfgpu_field_create.argtypes = [vp, i, i, i, i, d, d, d, d, C.POINTER(vp)]
         for n in ("destroy", "zero", "zero_padded_modes", "make_physical_y", "make_spectral_y", "make_physical_xz",
                   "make_spectral_xz", "make_physical", "make_spectral"):

@@ -390,33 +390,73 @@ int cfgpu_profile_read(cfgpu_ctx ctx, double* ms_h, long long* calls_h, int rese
 }
 
 #ifndef CF_EMU
+// CUDA-graph replay of a fixed launch sequence (the launch-bound small grids: `order` consecutive SBDF steps return every
+// history buffer to its role, so the captured sequence can be replayed; host/dnsalgo.cpp:MultistepDNS::advance).  The
+// caller runs the sequence once eagerly first (work spaces get allocated), then once between begin/end: nothing executes
+// during capture, cfgpu_graph_launch executes it.  A synchronising or allocating call inside the capture fails with the
+// CUDA capture error and the capture is discarded.
+struct GraphSlot { cudaGraphExec_t exec; long long kernels; };
+static long long g_capture_launches0 = 0;
 int cfgpu_graph_begin(cfgpu_ctx ctx) {
-    CF_ARG(!ctx->capturing, "graph capture already active");
+    CF_ARG(ctx && !ctx->capturing, "graph capture already active");
+    CF_ARG(ctx->comm.nranks == 1, "cfgpu_graph_begin: single-GPU contexts only (the slab exchange runs on several streams)");
+    CF_ARG(!ctx->profiling, "cfgpu_graph_begin: per-stage profiling is on (its event timers cannot be replayed)");
     CF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     ctx->capturing = true;
+    g_capture_launches0 = g_launches;
     return 0;
 }
 int cfgpu_graph_end(cfgpu_ctx ctx, int* graph_id) {
-    CF_ARG(ctx->capturing, "no graph capture active");
+    CF_ARG(ctx && ctx->capturing && graph_id, "no graph capture active");
     cudaGraph_t g = nullptr;
     ctx->capturing = false;
+    const long long kernels = g_launches - g_capture_launches0;
+    g_launches = g_capture_launches0;  // nothing ran: the launches are counted when the graph is launched
     CF_CUDA(cudaStreamEndCapture(ctx->stream, &g));
     cudaGraphExec_t ge = nullptr;
-    CF_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    const cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
     cudaGraphDestroy(g);
-    ctx->graphs.push_back((void*)ge);
+    CF_CUDA(e);
+    GraphSlot* slot = new GraphSlot{ge, kernels};
+    for (size_t i = 0; i < ctx->graphs.size(); ++i)
+        if (!ctx->graphs[i]) { ctx->graphs[i] = slot; *graph_id = (int)i; return 0; }
+    ctx->graphs.push_back((void*)slot);
     *graph_id = (int)ctx->graphs.size() - 1;
     return 0;
 }
+int cfgpu_graph_abort(cfgpu_ctx ctx) {
+    CF_ARG(ctx, "cfgpu_graph_abort: bad argument");
+    if (!ctx->capturing) return 0;
+    ctx->capturing = false;
+    g_launches = g_capture_launches0;
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(ctx->stream, &g);  // invalidated captures return an error and no graph: both fine here
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return 0;
+}
 int cfgpu_graph_launch(cfgpu_ctx ctx, int graph_id) {
-    CF_ARG(graph_id >= 0 && graph_id < (int)ctx->graphs.size(), "bad graph id");
-    CF_CUDA(cudaGraphLaunch((cudaGraphExec_t)ctx->graphs[graph_id], ctx->stream));
+    CF_ARG(ctx && graph_id >= 0 && graph_id < (int)ctx->graphs.size() && ctx->graphs[graph_id], "bad graph id");
+    GraphSlot* slot = (GraphSlot*)ctx->graphs[graph_id];
+    CF_CUDA(cudaGraphLaunch(slot->exec, ctx->stream));
+    g_launches += slot->kernels;
+    return 0;
+}
+int cfgpu_graph_destroy(cfgpu_ctx ctx, int graph_id) {
+    CF_ARG(ctx && graph_id >= 0 && graph_id < (int)ctx->graphs.size() && ctx->graphs[graph_id], "bad graph id");
+    GraphSlot* slot = (GraphSlot*)ctx->graphs[graph_id];
+    CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaGraphExecDestroy(slot->exec);
+    delete slot;
+    ctx->graphs[graph_id] = nullptr;
     return 0;
 }
 #else
 int cfgpu_graph_begin(cfgpu_ctx) { set_last_error("graphs unavailable in the emulation build"); return 1; }
 int cfgpu_graph_end(cfgpu_ctx, int*) { set_last_error("graphs unavailable in the emulation build"); return 1; }
 int cfgpu_graph_launch(cfgpu_ctx, int) { set_last_error("graphs unavailable in the emulation build"); return 1; }
+int cfgpu_graph_abort(cfgpu_ctx) { return 0; }
+int cfgpu_graph_destroy(cfgpu_ctx, int) { set_last_error("graphs unavailable in the emulation build"); return 1; }
 #endif
 
 // ------------------------------------------------------------------------------------------------ multi-GPU

@@ -340,34 +340,49 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 4 : 2) zpas
     }
     const double idx_ = (double)Nx / p.Lx, idz_ = (double)Nz / p.Lz, idy_ = p.inv_dy ? p.inv_dy[ny] : 0.0;
     double cmax = 0.0;
-    for (int idx = tid; idx < Nz * TL; idx += NT) {
-        const int l = idx / Nz, z = idx - l * Nz;
-        if (nx0 + l >= Nx) continue;
-        const int zs = fft_skew2(z);
-        double2* r = buf + (size_t)l * NP + zs;
-        const size_t js = (size_t)TL * NP;  // stride between transforms of one line
-        if (rot) {
-            const double2 z0 = r[0], z1 = r[js], z2 = r[2 * js];
-            const double u = z0.x, v = z0.y, w = z1.x;
-            const double ut = u + U, vt = v - p.Vsuck, wt = w + W;
-            const double ox = z1.y + Wy;   // curl of the total velocity: the base flow adds (W', 0, -U')
-            const double oy = z2.x;
-            const double oz = z2.y - Uy;
-            double fx = oy * wt - oz * vt;
-            double fy = oz * ut - ox * wt;
-            const double fz = ox * vt - oy * ut;
-            if (p.rotation != 0.0) {
-                fx -= p.rotation * vt;
-                fy += p.rotation * ut;
+    const size_t js = (size_t)TL * NP;  // stride between transforms of one line
+    // The third component of the product is real: the f_z lines of TWO neighbouring x-lines share one forward transform
+    // (f_z(l) + i f_z(l+1), separated again by the conjugate symmetry in the store), so a pair of lines costs three forward
+    // transforms instead of four.  One thread owns point z of both lines of a pair: it reads every input of the two lines
+    // before it writes, and the pair's f_z goes to the transform-1 slot of the pair's first line, which only it reads.
+    const int NLP = (TL + 1) >> 1;
+    if (rot) {
+        for (int idx = tid; idx < Nz * NLP; idx += NT) {
+            const int lp = idx / Nz, z = idx - lp * Nz;
+            const int zs = fft_skew2(z);
+            double fzv[2] = {0.0, 0.0};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int l = 2 * lp + h;
+                if (l >= TL || nx0 + l >= Nx) continue;
+                double2* r = buf + (size_t)l * NP + zs;
+                const double2 z0 = r[0], z1 = r[js], z2 = r[2 * js];
+                const double u = z0.x, v = z0.y, w = z1.x;
+                const double ut = u + U, vt = v - p.Vsuck, wt = w + W;
+                const double ox = z1.y + Wy;   // curl of the total velocity: the base flow adds (W', 0, -U')
+                const double oy = z2.x;
+                const double oz = z2.y - Uy;
+                double fx = oy * wt - oz * vt;
+                double fy = oz * ut - ox * wt;
+                fzv[h] = ox * vt - oy * ut;
+                if (p.rotation != 0.0) {
+                    fx -= p.rotation * vt;
+                    fy += p.rotation * ut;
+                }
+                r[0] = make_double2(fx, fy);
+                double m = ut * idx_;
+                const double m2 = v * idy_, m3 = wt * idz_;
+                m = m2 > m ? m2 : m;
+                m = m3 > m ? m3 : m;
+                cmax = m > cmax ? m : cmax;
             }
-            r[0] = make_double2(fx, fy);
-            r[js] = make_double2(fz, 0.0);
-            double m = ut * idx_;
-            const double m2 = v * idy_, m3 = wt * idz_;
-            m = m2 > m ? m2 : m;
-            m = m3 > m ? m3 : m;
-            cmax = m > cmax ? m : cmax;
-        } else {
+            buf[(size_t)(TL + 2 * lp) * NP + zs] = make_double2(fzv[0], fzv[1]);
+        }
+    } else {
+        for (int idx = tid; idx < Nz * TL; idx += NT) {
+            const int l = idx / Nz, z = idx - l * Nz;
+            if (nx0 + l >= Nx) continue;
+            const double2* r = buf + (size_t)l * NP + fft_skew2(z);
             const double2 z0 = r[0], z1 = r[js];
             double m = (z0.x + U) * idx_;
             const double m2 = z0.y * idy_, m3 = (z1.x + W) * idz_;
@@ -388,23 +403,27 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 4 : 2) zpas
     }
     if (!rot) return;
     __syncthreads();
-    for (int j = warp; j < 2 * TL; j += (NT >> 5)) warp_fft_dif<-1, NZ>(buf + (size_t)j * NP, tws, lane);
+    for (int j = warp; j < TL + NLP; j += (NT >> 5)) {
+        const int slot = j < TL ? j : TL + 2 * (j - TL);
+        warp_fft_dif<-1, NZ>(buf + (size_t)slot * NP, tws, lane);
+    }
     __syncthreads();
 
     double2* __restrict__ F = p.F + (size_t)yl * Nx * nkz;
-    const double sc = p.scale, hs = 0.5 * p.scale;
+    const double hs = 0.5 * p.scale;
     for (int idx = tid; idx < TL * nkz; idx += NT) {
         const int l = idx / nkz, k = idx - l * nkz;
         const int nx = nx0 + l;
         if (nx >= Nx) continue;
-        const double2* g = buf + (size_t)l * NP;                // transform 0 of line l: fx + i fy
-        const double2* h = buf + (size_t)(TL + l) * NP;         // transform 1: fz
+        const double2* g = buf + (size_t)l * NP;                        // transform 0 of line l: fx + i fy
+        const double2* h = buf + (size_t)(TL + (l & ~1)) * NP;          // f_z of the pair: fz(even line) + i fz(odd line)
         const int ks = fft_skew2(fft_digit_rev<NZ>(k)), kn = fft_skew2(fft_digit_rev<NZ>(k == 0 ? 0 : Nz - k));  // DIF outputs
-        const double2 gk = g[ks], gn = g[kn], hk = h[ks];
+        const double2 gk = g[ks], gn = g[kn], hk = h[ks], hn = h[kn];
         const size_t off = (size_t)nx * nkz + k;
-        F[off] = make_double2(hs * (gk.x + gn.x), hs * (gk.y - gn.y));
-        F[fstride + off] = make_double2(hs * (gk.y + gn.y), -hs * (gk.x - gn.x));
-        F[2 * fstride + off] = make_double2(sc * hk.x, sc * hk.y);
+        const double2 re = make_double2(hs * (gk.x + gn.x), hs * (gk.y - gn.y)), im = make_double2(hs * (gk.y + gn.y), -hs * (gk.x - gn.x));
+        F[off] = re;
+        F[fstride + off] = im;
+        F[2 * fstride + off] = (l & 1) ? make_double2(hs * (hk.y + hn.y), -hs * (hk.x - hn.x)) : make_double2(hs * (hk.x + hn.x), hs * (hk.y - hn.y));
     }
 }
 

@@ -44,10 +44,15 @@ int cfgpu_timer_stop(cfgpu_ctx ctx, double* ms);
 #define CFGPU_NSTAGES 9
 int cfgpu_profile_enable(cfgpu_ctx ctx, int on);
 int cfgpu_profile_read(cfgpu_ctx ctx, double* ms_h /* [CFGPU_NSTAGES] */, long long* calls_h /* [CFGPU_NSTAGES] */, int reset);
-/* CUDA-graph capture of a sequence of calls on the context's stream (launch-bound small grids) */
+/* CUDA-graph replay of a fixed sequence of calls on the context's stream (launch-bound small grids: `order` consecutive
+ * SBDF steps, dnsalgo.cpp:195-260, return every history buffer to its role).  Between begin and end the calls are recorded,
+ * not executed; a call that allocates or synchronises fails and the capture must be dropped with cfgpu_graph_abort.
+ * Single-GPU contexts only. */
 int cfgpu_graph_begin(cfgpu_ctx ctx);
 int cfgpu_graph_end(cfgpu_ctx ctx, int* graph_id);
+int cfgpu_graph_abort(cfgpu_ctx ctx);
 int cfgpu_graph_launch(cfgpu_ctx ctx, int graph_id);
+int cfgpu_graph_destroy(cfgpu_ctx ctx, int graph_id);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU)
  * replaces CfMPI (cfmpi.cpp:66-127) and the FFTW-MPI transposes inside makePhysical/makeSpectral (flowfield.cpp:577-667,

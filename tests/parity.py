@@ -302,3 +302,30 @@ def layout_equivalence(lib, cfg, nsteps=4, junk=True, **flag_over):
             "junk_kept": bool(np.array_equal(ut[alias], c0[alias] if junk else 0 * c0[alias])) and
                          bool(np.array_equal(us[alias], c0[alias] if junk else 0 * c0[alias])),
             "moved": float(np.abs(ut[~alias] - c0[~alias]).max())}
+
+
+def graph_equivalence(lib, cfg, nsteps=100, **flag_over):
+    """CUDA-graph replay of the SBDF step sequence (MultistepDNS::advance, CFGPU_GRAPH) against the eager launches:
+    same kernels, same arguments, same order => the same bits; also returns the launch counts and the wall times."""
+    import os
+    import time
+    fl = dict(cfg["flags"]); fl.update(flag_over)
+    ur = ref_random(cfg, 11)
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["CFGPU_GRAPH"] = mode
+        try:
+            gd = cf.DNS(to_gpu(lib, ur), cf.make_flags(**fl))
+            gd.advance(4)  # initial steps of the start-up scheme + first eager steps
+            ctx_l0 = lib.launch_count() if hasattr(lib, "launch_count") else 0
+            t0 = time.perf_counter()
+            gd.advance(nsteps)
+            u, q = gd.get()
+            a = u.get().copy()
+            dt = time.perf_counter() - t0
+            res[mode] = dict(u=a, q=q.get().copy(), cfl=gd.cfl(), sec=dt, launches=(lib.launch_count() if hasattr(lib, "launch_count") else 0) - ctx_l0)
+        finally:
+            os.environ.pop("CFGPU_GRAPH", None)
+    return {"u_identical": bool(np.array_equal(res["0"]["u"], res["1"]["u"])), "q_identical": bool(np.array_equal(res["0"]["q"], res["1"]["q"])),
+            "cfl_identical": res["0"]["cfl"] == res["1"]["cfl"], "sec_eager": res["0"]["sec"], "sec_graph": res["1"]["sec"],
+            "launches_eager": res["0"]["launches"], "launches_graph": res["1"]["launches"]}

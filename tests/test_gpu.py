@@ -259,3 +259,12 @@ def test_tile_layout_is_transparent(lib, junk):
     assert r["u_equal"] and r["q_equal"] and r["junk_kept"] and r["moved"] > 0, r
     r = parity.layout_equivalence(lib, parity.C1, nsteps=3, junk=junk, timestepping="cnab2")
     assert r["u_equal"] and r["q_equal"] and r["junk_kept"], r
+
+
+@pytest.mark.parametrize("cfgname", ["C1", "GOLD"])
+def test_cuda_graph_replay_is_bit_identical(lib, cfgname):
+    """Launch-bound grids replay `order` SBDF steps as one CUDA graph (host/dnsalgo.cpp): identical bits to eager launches."""
+    cfg = parity.C1 if cfgname == "C1" else dict(parity.C1, Nx=48, Ny=35, Nz=48, Lx=2 * np.pi / 1.14, Lz=2 * np.pi / 2.5)
+    r = parity.graph_equivalence(lib, cfg)
+    assert r["u_identical"] and r["q_identical"] and r["cfl_identical"], r
+    print("graph replay:", {k: v for k, v in r.items() if "sec" in k or "launch" in k})
