@@ -31,7 +31,7 @@ cfgpu_nse_destroy cfgpu_nse_set_constraint cfgpu_nse_reset_lambda cfgpu_nse_nonl
 cfgpu_nse_linear cfgpu_nse_cflfactor cfgpu_nse_get_dPd cfgpu_comm_unique_id cfgpu_comm_init_nccl
 cfgpu_comm_init_external cfgpu_comm_rank cfgpu_comm_ranges cfgpu_field_allgather
 cfgpu_field_copy_component cfgpu_l2form_box cfgpu_bcnorm2 cfgpu_field_diffop cfgpu_field_pointwise
-cfgpu_helmholtz_solve cfgpu_tridiag cfgpu_tausolve_mode cfgpu_poisson_solve cfgpu_pressure_neumann
+cfgpu_helmholtz_solve cfgpu_tridiag cfgpu_tausolve_mode cfgpu_poisson_solve cfgpu_pressure_neumann cfgpu_field_symmetry
 cfgpu_vec_create cfgpu_vec_destroy cfgpu_vec_size cfgpu_vec_upload cfgpu_vec_download cfgpu_vec_copy cfgpu_vec_zero cfgpu_vec_dot
 cfgpu_vec_nrm2 cfgpu_vec_axpy cfgpu_vec_axpby cfgpu_vec_scal cfgpu_field2vector_size cfgpu_field2vector cfgpu_vector2field""".split()
 
@@ -104,6 +104,7 @@ class GpuLib:
         L.cfgpu_nse_cflfactor.argtypes = [vp, vp, dpt]
         L.cfgpu_nse_get_dPd.argtypes = [vp, dpt, dpt]
         L.cfgpu_poisson_solve.argtypes = [vp, vp, vp]
+        L.cfgpu_field_symmetry.argtypes = [vp, i, i, i, i, d, d]
         L.cfgpu_pressure_neumann.argtypes = [vp, vp, vp, d]
         L.cfgpu_helmholtz_solve.argtypes = [vp, i, d, d, d, d, i, dpt, dpt, dpt, dpt]
         L.cfgpu_tridiag.argtypes = [vp, i, i, dpt, dpt, dpt, dpt, i, i, i]
@@ -383,6 +384,8 @@ class HostLib:
         L.cf_field_get_state.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
         L.cf_field_set_padded.argtypes = [vp, i]
         L.cf_field_copy.argtypes = [vp, vp]
+        L.cf_field_symmetry.argtypes = [vp, i, i, i, i, d, d]
+        L.cf_hookstep_search.argtypes = [vp, C.POINTER(Flags), d, d, dpt, dpt, dpt, i]
         L.cf_cmplx_get.argtypes = [vp, i, i, i, i, i]
         L.cf_cmplx_set.argtypes = [vp, i, i, i, i, d, d]
         L.cf_l2norm2.argtypes = [vp, i]
@@ -523,6 +526,7 @@ class FlowField:
     def make_physical_xz(self): self.lib.L.cf_make_physical_xz(self.h)
     def make_spectral_xz(self): self.lib.L.cf_make_spectral_xz(self.h)
     def zero_padded_modes(self): self.lib.L.cf_zero_padded_modes(self.h)
+    def symmetry(self, s, sx, sy, sz, ax, az): self.lib.L.cf_field_symmetry(self.h, s, sx, sy, sz, ax, az)
     def l2norm(self): return self.lib.L.cf_l2norm(self.h)
 
     def l2norm3d(self):
@@ -553,6 +557,22 @@ class FlowField:
     def save(self, filebase): self.lib.L.cf_field_save(self.h, filebase.encode())
     def axpby(self, a, x, b=0.0, z=None): self.lib.L.cf_field_axpby(self.h, a, x.h, b, z.h if z is not None else None)
     def scale(self, s): self.lib.L.cf_field_scale(self.h, s)
+
+
+def hookstep_search(u, flags, T, dt, sigma=(1, 1, 1, 1, 0.0, 0.0), epsSearch=1e-13, epsGMRES=1e-3, epsDx=1e-7, delta=0.01, Nnewton=20,
+                    Ngmres=120, Nhook=20, Tnormalize=False, verbose=False, xrelative=False, zrelative=False):
+    """Newton-Krylov-hookstep search for sigma f^T(u) - u = 0 on the device (host/devicesearch.cpp); u (a FlowField) is the
+    initial guess and is overwritten by the result.  Returns a dict with the convergence record."""
+    import numpy as np
+    sg = np.array(sigma, dtype=np.float64)
+    par = np.array([epsSearch, epsGMRES, epsDx, delta, Nnewton, Ngmres, Nhook, 1.0 if Tnormalize else 0.0, 1.0 if verbose else 0.0,
+                    1.0 if xrelative else 0.0, 1.0 if zrelative else 0.0])
+    out = np.full(6 + Nnewton + 1, -1.0)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+    u.lib.L.cf_hookstep_search(u.h, C.byref(flags), float(T), float(dt), dp(sg), dp(par), dp(out), len(out))
+    hist = [float(v) for v in out[6:] if v >= 0]
+    return dict(converged=bool(out[0]), newton_steps=int(out[1]), fevals=int(out[2]), gmres_iterations=int(out[3]), residual=float(out[4]),
+                steps_per_eval=float(out[5]), history=hist, ax=float(sg[4]), az=float(sg[5]))
 
 
 class DNS:

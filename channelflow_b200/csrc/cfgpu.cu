@@ -333,6 +333,8 @@ int cfgpu_finalize(cfgpu_ctx ctx) {
     }
     for (auto& kv : ctx->fftplans) cudaFree(kv.second.tw);
     for (auto& kv : ctx->boxes) cudaFree(kv.second.runstart_full);
+    for (auto& kv : ctx->pool_free_blocks) cudaFree(kv.second);
+    ctx->pool_free_blocks.clear();
     if (ctx->ws_P.ptr) cudaFree(ctx->ws_P.ptr);
     if (ctx->ws_Q.ptr) cudaFree(ctx->ws_Q.ptr);
     if (ctx->ws_red.ptr) cudaFree(ctx->ws_red.ptr);
@@ -492,14 +494,55 @@ int cfgpu_comm_ranges(cfgpu_ctx ctx, int nmx, int Ny, int rank, int* x0, int* x1
 }  // extern "C"
 
 namespace cfgpu {
+// ------------------------------------------------------------------------------------------------ pooled device memory
+static constexpr size_t POOL_MAX_BLOCK = (size_t)64 << 20, POOL_MAX_CACHED = (size_t)2 << 30;
+int dev_alloc(cfgpu_ctx ctx, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    const bool pooled = ctx->comm.nranks == 1 && bytes <= POOL_MAX_BLOCK && !getenv("CFGPU_NO_POOL");
+    if (pooled) {
+        auto it = ctx->pool_free_blocks.find(bytes);
+        if (it != ctx->pool_free_blocks.end()) {
+            *p = it->second;
+            ctx->pool_free_blocks.erase(it);
+            ctx->pool_cached_bytes -= bytes;
+            return 0;
+        }
+    }
+    if (cudaMalloc(p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        // give the cache back and try once more
+        for (auto& kv : ctx->pool_free_blocks) { ctx->pool_sizes.erase(kv.second); cudaFree(kv.second); }
+        ctx->pool_free_blocks.clear();
+        ctx->pool_cached_bytes = 0;
+        if (cudaMalloc(p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            *p = nullptr;
+            return 1;
+        }
+    }
+    if (pooled) ctx->pool_sizes[*p] = bytes;
+    return 0;
+}
+void dev_free(cfgpu_ctx ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->pool_sizes.find(p);
+    if (it != ctx->pool_sizes.end() && ctx->pool_cached_bytes + it->second <= POOL_MAX_CACHED) {
+        ctx->pool_free_blocks.emplace(it->second, p);
+        ctx->pool_cached_bytes += it->second;
+        return;
+    }
+    if (it != ctx->pool_sizes.end()) ctx->pool_sizes.erase(it);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+}
+
 // ------------------------------------------------------------------------------------------------ field layouts
 // The serial buffer is allocated on first use: hot-path fields of a multi-GPU run live in their tile-major buffer only
 // (this rank's modes), so a rank's footprint scales with 1/nranks.  A field without a serial buffer is all zero outside
 // whatever its tile buffer holds.
 int field_ser_alloc(cfgpu_field f) {
     if (f->dser) return 0;
-    if (cudaMalloc((void**)&f->dser, f->n * sizeof(double)) != cudaSuccess) {
-        cudaGetLastError();
+    if (dev_alloc(f->ctx, (void**)&f->dser, f->n * sizeof(double))) {
         set_last_error("field: cudaMalloc of the serial buffer failed");
         return 1;
     }
@@ -515,8 +558,8 @@ int field_serial_output(cfgpu_field f) {
 static int tile_alloc(cfgpu_field f, const TileGeom& g) {
     const long long need = g.ntiles() * (long long)f->Ny * g.TM * 2 * f->Nd;
     if (!f->dtile || f->ntile < need) {
-        if (f->dtile) { CF_CUDA(cudaStreamSynchronize(f->ctx->stream)); cudaFree(f->dtile); f->dtile = nullptr; }
-        if (cudaMalloc((void**)&f->dtile, need * sizeof(double)) != cudaSuccess) {
+        if (f->dtile) { dev_free(f->ctx, f->dtile); f->dtile = nullptr; }
+        if (dev_alloc(f->ctx, (void**)&f->dtile, need * sizeof(double))) {
             set_last_error("field: cudaMalloc of the tile-major buffer failed");
             return 1;
         }
@@ -623,9 +666,8 @@ int cfgpu_field_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, int Nd, double Lx,
 }
 int cfgpu_field_destroy(cfgpu_field f) {
     if (!f) return 0;
-    cudaStreamSynchronize(f->ctx->stream);
-    if (f->dser) cudaFree(f->dser);
-    if (f->dtile) cudaFree(f->dtile);
+    dev_free(f->ctx, f->dser);
+    dev_free(f->ctx, f->dtile);
     delete f;
     return 0;
 }
@@ -815,6 +857,18 @@ int cfgpu_field_add_profile(cfgpu_field f, int mx, int mz, int i, const double* 
     const long off0 = (long)i * f->Ny * f->Nx * f->Mz() + mz + (long)f->Mz() * mx;
     CF_TRY(profile_add_launch(f->dser, off0, (long)f->Nx * f->Mz(), f->Ny, ctx->ws_red.ptr, scale, ctx->stream));
     CF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+// FlowField::operator*=(const FieldSymmetry&) (flowfield.cpp:1274-1433); spectral state, in place
+int cfgpu_field_symmetry(cfgpu_field f, int s, int sx, int sy, int sz, double ax, double az) {
+    CF_ARG(f && (s == 1 || s == -1) && (sx == 1 || sx == -1) && (sy == 1 || sy == -1) && (sz == 1 || sz == -1), "cfgpu_field_symmetry: signs must be +-1");
+    CF_ARG(f->xzstate == CFGPU_SPECTRAL && f->ystate == CFGPU_SPECTRAL, "cfgpu_field_symmetry: field must be spectral");
+    CF_ARG(f->ctx->comm.nranks == 1, "cfgpu_field_symmetry: single-GPU call");
+    CF_ARG(f->Nd == 1 || f->Nd == 3, "cfgpu_field_symmetry: scalar and 3-vector fields (tensor sign rules are not carried)");
+    CF_TRY(field_serial(f));
+    const int Kxhi = f->padded ? f->Nx / 3 - 1 : f->Nx / 2, Kxlo = f->padded ? -(f->Nx / 3 - 1) : f->Nx / 2 + 1 - f->Nx;
+    const int Kz = f->padded ? f->Nz / 3 - 1 : f->Nz / 2;
+    CF_TRY(symmetry_launch(f->dser, f->Nx, f->Ny, f->Nz, f->Nd, Kxlo, Kxhi, Kz, s, sx, sy, sz, ax, az, f->ctx->stream));
     return 0;
 }
 int cfgpu_field_zero_padded_modes(cfgpu_field f) {

@@ -79,7 +79,13 @@ struct cfgpu_ctx_s {
     void* peerF[cfgpu::COMM_MAXRANKS] = {nullptr};
     unsigned long long peerF_gen = 0;
     unsigned long long push_seq[cfgpu::PUSH_SLOTS] = {0};
-    std::vector<void*> graphs;  // cudaGraphExec_t
+    std::vector<void*> graphs;  // GraphSlot*
+    // Block cache of the small device allocations (dev_alloc / dev_free below): exact-size free lists.  A Newton-Krylov
+    // search builds and drops a DNS (fields, tau tables, vectors: ~50 allocations) per Krylov vector; cudaMalloc / cudaFree
+    // are device-synchronising and cost more than the 320 time steps between them on the grids those searches use.
+    std::multimap<size_t, void*> pool_free_blocks;
+    std::map<void*, size_t> pool_sizes;   // every live or cached pooled block
+    size_t pool_cached_bytes = 0;
     bool capturing = false;
     // stage profiler
     bool profiling = false;
@@ -146,6 +152,11 @@ struct cfgpu_nse_s {
 namespace cfgpu {
 int field_serial(cfgpu_field f);                                           // make dser current (tile -> serial if needed)
 int field_ser_alloc(cfgpu_field f);                                        // allocate the (zero-filled) serial buffer if absent
+// Device memory for fields, vectors and operator tables.  Blocks of at most POOL_MAX_BLOCK bytes of a single-GPU context are
+// recycled through the context's free lists (stream order on ctx->stream makes reuse safe); larger ones, and everything in a
+// multi-GPU context (peer-mapped, several streams), go straight to cudaMalloc / cudaFree.
+int dev_alloc(cfgpu_ctx ctx, void** p, size_t bytes);
+void dev_free(cfgpu_ctx ctx, void* p);
 int field_serial_output(cfgpu_field f);                                    // dser becomes current, contents to be written
 int field_tile(cfgpu_field f, const TileGeom& g);                          // make dtile current (serial -> tile if needed)
 int field_tile_output(cfgpu_field f, const TileGeom& g, bool outside_zero);  // dtile becomes current, contents to be written

@@ -546,7 +546,7 @@ int cfgpu_nse_create(cfgpu_ctx ctx, int Nx, int Ny, int Nz, double Lx, double Lz
 int cfgpu_nse_destroy(cfgpu_nse nse) {
     if (!nse) return 0;
     cudaStreamSynchronize(nse->ctx->stream);
-    for (auto& t : nse->tau) cudaFree(t.base);
+    for (auto& t : nse->tau) dev_free(nse->ctx, t.base);
     for (int v = 0; v < 2; ++v) if (nse->d_rows[v]) cudaFree(nse->d_rows[v]);
     for (int v = 0; v < 2; ++v) if (nse->d_rows_self[v]) cudaFree(nse->d_rows_self[v]);
     if (nse->s_u) cfgpu_field_destroy(nse->s_u);
@@ -574,7 +574,7 @@ int cfgpu_nse_reset_lambda(cfgpu_nse nse, const double* lambda_t_h, int nsub) {
         td.ntiles = TauData::num_tiles(td.nq, td.TM, td.has00);
         td.nu = nse->cfg.nu; td.a = nse->a; td.b = nse->b;
         const size_t n = TauData::doubles(td.N, td.nq, td.TM, td.has00);
-        if (cudaMalloc((void**)&td.base, n * sizeof(double)) != cudaSuccess) {
+        if (dev_alloc(ctx, (void**)&td.base, n * sizeof(double))) {
             set_last_error("cfgpu_nse_reset_lambda: cudaMalloc failed");
             return 1;
         }

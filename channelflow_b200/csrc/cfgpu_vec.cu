@@ -43,8 +43,7 @@ int cfgpu_vec_create(cfgpu_ctx ctx, long long n, cfgpu_vec* out) {
     cfgpu_vec v = new cfgpu_vec_s();
     v->ctx = ctx; v->n = n;
     if (n > 0) {
-        if (cudaMalloc((void**)&v->d, (size_t)n * sizeof(double)) != cudaSuccess) {
-            cudaGetLastError();
+        if (dev_alloc(ctx, (void**)&v->d, (size_t)n * sizeof(double))) {
             delete v;
             set_last_error("cfgpu_vec_create: cudaMalloc failed");
             return 1;
@@ -56,8 +55,7 @@ int cfgpu_vec_create(cfgpu_ctx ctx, long long n, cfgpu_vec* out) {
 }
 int cfgpu_vec_destroy(cfgpu_vec v) {
     if (!v) return 0;
-    cudaStreamSynchronize(v->ctx->stream);
-    if (v->d) cudaFree(v->d);
+    dev_free(v->ctx, v->d);
     delete v;
     return 0;
 }

@@ -53,6 +53,44 @@ __global__ void __launch_bounds__(EW_THREADS) zero_padded_kernel(double2* __rest
     }
 }
 
+// FlowField *= FieldSymmetry (flowfield.cpp:1274-1433):  (u,v,w)(x,y,z) -> s (sx u, sy v, sz w)(sx x + ax Lx, sy y, sz z + az Lz)
+// on a spectral field, in place.  In Fourier-Chebyshev coefficients (kz >= 0 stored, u(-kx,-kz) = conj u(kx,kz)):
+//   sx sz = +1 :  u(kx,kz) <- c(kx)  [u or conj u](kx,kz)                      (conj when sx = sz = -1)
+//   sx sz = -1 :  u(kx,kz) <- c(kx)  [u or conj u](-kx,kz), both rows of a +-kx pair exchanged by one thread
+//   c(kx) = s s_i (sy)^n exp(i 2 pi (ax sx kx + az sz kz)),  s_i = the sign of component i (sx, sy, sz for a vector)
+// One thread per (component, kx >= 0 pair, kz) sweeping n; adjacent threads adjacent in kz.  Modes outside [Kxlo..Kxhi] x
+// [0..Kz] (the de-aliased box of a padded field, else every mode) are left alone, and so is the unpaired kx = Nx/2 row of
+// the exchanging case, as in the reference.
+__global__ void __launch_bounds__(EW_THREADS) symmetry_kernel(double2* __restrict__ c, int Nx, int Ny, int Mz, int Nd, int Kxlo, int Kxhi,
+                                                              int Kz, int s, int sx, int sy, int sz, double ax, double az) {
+    const int nkz = Kz + 1, npos = Kxhi + 1;  // pairs kx = 0 .. Kxhi (kx = 0 pairs with itself)
+    const long items = (long)Nd * npos * nkz;
+    const long it = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= items) return;
+    const int kz = (int)(it % nkz), kx = (int)((it / nkz) % npos), i = (int)(it / ((long)nkz * npos));
+    const int si = Nd == 3 ? (i == 0 ? sx : i == 1 ? sy : sz) : 1;  // sign_i (flowfield.cpp:1066-1093), vectors and scalars
+    const double TWO_PI_ = 6.283185307179586476925286766559;
+    const long rs = (long)Nx * Mz, cs = rs * Ny;
+    const bool exchange = sx + sz == 0, conj_ = exchange ? sx == 1 : sx == -1;
+    const int kxm = -kx;
+    const bool have_m = kx > 0 && kxm >= Kxlo;  // the -kx row exists in the range
+    if (exchange && kx > 0 && !have_m) return;  // unpaired Nyquist row
+    double2 cp, cm;
+    sincos(TWO_PI_ * (ax * sx * kx + az * sz * kz), &cp.y, &cp.x);
+    sincos(TWO_PI_ * (ax * sx * kxm + az * sz * kz), &cm.y, &cm.x);
+    double2* colp = c + i * cs + (long)kx * Mz + kz;
+    double2* colm = c + i * cs + (long)(kxm < 0 ? Nx + kxm : kxm) * Mz + kz;
+    for (int n = 0; n < Ny; ++n) {
+        const double sg = (double)(s * si * ((sy == -1 && (n & 1)) ? -1 : 1));
+        double2 up = colp[n * rs], um = make_double2(0.0, 0.0);
+        if (have_m) um = colm[n * rs];
+        if (conj_) { up.y = -up.y; um.y = -um.y; }
+        const double2 srcp = exchange ? (kx == 0 ? up : um) : up, srcm = exchange ? up : um;
+        colp[n * rs] = make_double2(sg * (cp.x * srcp.x - cp.y * srcp.y), sg * (cp.x * srcp.y + cp.y * srcp.x));
+        if (have_m) colm[n * rs] = make_double2(sg * (cm.x * srcm.x - cm.y * srcm.y), sg * (cm.x * srcm.y + cm.y * srcm.x));
+    }
+}
+
 // out[n] = (re, im) of mode (mx,mz) component i  /  add
 __global__ void profile_get_kernel(const double2* __restrict__ c, long off0, long rs, int Ny, double2* __restrict__ out) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,6 +190,14 @@ int grid_for(long n) {
 int axpby_launch(double* y, double a, const double* x, double b, const double* z, long n, cudaStream_t st) {
     const long n2 = n / 2;  // field sizes are always even (Nzpad even)
     CF_LAUNCH(axpby_kernel, dim3(grid_for(n2)), dim3(EW_THREADS), 0, st, y, a, x, b, z, n2);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+int symmetry_launch(double* d, int Nx, int Ny, int Nz, int Nd, int Kxlo, int Kxhi, int Kz, int s, int sx, int sy, int sz, double ax, double az,
+                    cudaStream_t st) {
+    const long items = (long)Nd * (Kxhi + 1) * (Kz + 1);
+    CF_LAUNCH(symmetry_kernel, dim3((unsigned)((items + EW_THREADS - 1) / EW_THREADS)), dim3(EW_THREADS), 0, st, reinterpret_cast<double2*>(d),
+              Nx, Ny, Nz / 2 + 1, Nd, Kxlo, Kxhi, Kz, s, sx, sy, sz, ax, az);
     CF_KERNEL_CHECK();
     return 0;
 }

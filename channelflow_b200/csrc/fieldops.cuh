@@ -5,6 +5,9 @@
 namespace cfgpu {
 int axpby_launch(double* y, double a, const double* x, double b, const double* z, long n, cudaStream_t st);
 int scale_launch(double* y, double s, long n, cudaStream_t st);
+// FlowField *= FieldSymmetry on a spectral field in the reference layout, modes kx in [Kxlo, Kxhi], kz in [0, Kz]
+int symmetry_launch(double* d, int Nx, int Ny, int Nz, int Nd, int Kxlo, int Kxhi, int Kz, int s, int sx, int sy, int sz, double ax, double az,
+                    cudaStream_t st);
 int zero_padded_launch(double* d, int Nx, int Ny, int Nz, int Nd, int Kx, int Kz, cudaStream_t st);
 int profile_get_launch(const double* d, long off0_cplx, long rs_cplx, int Ny, double* out_dev, cudaStream_t st);
 int profile_add_launch(double* d, long off0_cplx, long rs_cplx, int Ny, const double* in_dev, double s, cudaStream_t st);

@@ -6,6 +6,8 @@
 
 #include "channelflow/diffops.h"
 #include "channelflow/dns.h"
+#include "channelflow/devicesearch.h"
+#include "channelflow/symmetry.h"
 
 using namespace chflow;
 
@@ -58,6 +60,7 @@ void cf_make_spectral_y(void* h) { ((FlowField*)h)->makeSpectral_y(); }
 void cf_make_physical_xz(void* h) { ((FlowField*)h)->makePhysical_xz(); }
 void cf_make_spectral_xz(void* h) { ((FlowField*)h)->makeSpectral_xz(); }
 void cf_zero_padded_modes(void* h) { ((FlowField*)h)->zeroPaddedModes(); }
+void cf_field_symmetry(void* h, int s, int sx, int sy, int sz, double ax, double az) { *((FlowField*)h) *= FieldSymmetry(sx, sy, sz, ax, az, s); }
 double cf_cmplx_get(void* h, int mx, int my, int mz, int i, int part) {
     const FlowField& u = *(FlowField*)h;
     const Complex c = u.cmplx(mx, my, mz, i);
@@ -187,6 +190,32 @@ double cf_timer_stop() {
 void cf_profile_enable(int on) { cfgpu_profile_enable(cfgpu_context(), on); }
 void cf_profile_read(double* ms, long long* calls, int reset) { cfgpu_profile_read(cfgpu_context(), ms, calls, reset); }
 
+// Newton-Krylov-hookstep search on the device (channelflow/devicesearch.h): u is the initial guess and receives the solution.
+// sigma = {s, sx, sy, sz, ax, az} (ax, az updated on return); par = {epsSearch, epsGMRES, epsDx, delta, Nnewton, Ngmres, Nhook,
+// Tnormalize, verbose, xrelative, zrelative};
+// out = {converged, newtonSteps, fevals, gmresIterations, residual, steps_per_eval, history[0..]} (at most nout entries)
+void cf_hookstep_search(void* uh, const CfFlags* rf, double T, double dt, double* sigma, const double* par, double* out, int nout) {
+    FlowField& u = *(FlowField*)uh;
+    DNSFlags flags = to_flags(rf);
+    flags.dt = dt;
+    TimeStep ts(dt, dt, dt, 1.0, 0.0, 1e9, false);
+    FieldSymmetry sg((int)sigma[1], (int)sigma[2], (int)sigma[3], sigma[4], sigma[5], (int)sigma[0]);
+    DeviceSearchFlags sf;
+    sf.epsSearch = par[0]; sf.epsGMRES = par[1]; sf.epsDx = par[2]; sf.delta = par[3];
+    sf.Nnewton = (int)par[4]; sf.Ngmres = (int)par[5]; sf.Nhook = (int)par[6];
+    std::ostringstream sink;
+    if (par[8] == 0) sf.logstream = &sink;
+    u.makeSpectral();
+    DeviceDSI dsi(u, flags, ts, sg, T, par[7] != 0, par[9] != 0, par[10] != 0);
+    DeviceVector x;
+    dsi.makeVector(u, x);
+    const DeviceSearchResult r = hookstepSearch(dsi, x, sf);
+    dsi.extractVector(x, u);
+    sigma[4] = dsi.sigma().ax();
+    sigma[5] = dsi.sigma().az();
+    const double head[6] = {r.converged ? 1.0 : 0.0, (double)r.newtonSteps, (double)r.fevals, (double)r.gmresIterations, r.residual, dsi.steps_per_eval()};
+    for (int i = 0; i < nout; ++i) out[i] = i < 6 ? head[i] : (i - 6 < (int)r.history.size() ? r.history[i - 6] : -1.0);
+}
 void cf_laminar_profile(const CfFlags* rf, double a, double b, int Ny, double* U) {
     DNSFlags flags = to_flags(rf);
     ChebyCoeff u = laminarProfile(flags, a, b, Ny);

@@ -41,6 +41,8 @@ struct PinnedAllocator {
     template <class U> bool operator!=(const PinnedAllocator<U>&) const { return false; }
 };
 
+class FieldSymmetry;
+
 class FlowField {
    public:
     FlowField();
@@ -160,6 +162,7 @@ class FlowField {
     MPI_Comm* comm_world() const { static MPI_Comm c = 0; return &c; }
 
     FlowField& operator*=(Real x);
+    FlowField& operator*=(const FieldSymmetry& s);  // u <- s(u), on the device (symmetry.cpp)
     FlowField& operator+=(const Real& a);        // u(0,0,0,0) += a
     FlowField& operator-=(const Real& a);
     FlowField& operator+=(const ComplexChebyCoeff& U);

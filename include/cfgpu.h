@@ -145,6 +145,9 @@ int cfgpu_field_diffop(cfgpu_field out, cfgpu_field in, int nterms, const int* o
  * 1/2 |f|^2, 6 componentwise product (diffops.cpp:2336-2700) */
 int cfgpu_field_pointwise(int op, cfgpu_field out, cfgpu_field f, cfgpu_field g /* NULL for ops 3-5 */);
 
+/* FlowField::operator*=(const FieldSymmetry&) (flowfield.cpp:1274-1433), spectral field, in place:
+ * (u,v,w)(x,y,z) -> s (sx u, sy v, sz w)(sx x + ax Lx, sy y, sz z + az Lz) */
+int cfgpu_field_symmetry(cfgpu_field f, int s, int sx, int sy, int sz, double ax, double az);
 /* PoissonSolver::solve (poissonsolver.cpp:146-202): lapl u = f for every stored Fourier mode of every component, Dirichlet
  * data zero (bc == NULL) or the wall values of bc (poissonsolver.cpp:173-202) */
 int cfgpu_poisson_solve(cfgpu_field u, cfgpu_field f, cfgpu_field bc);

@@ -15,6 +15,7 @@
 #include "channelflow/dns.h"
 #include "channelflow/dnsflags.h"
 #include "channelflow/flowfield.h"
+#include "channelflow/symmetry.h"
 #include "channelflow/helmholtz.h"
 #include "channelflow/nse.h"
 #include "channelflow/tausolver.h"
@@ -91,6 +92,8 @@ void ref_make_spectral_y(void* h) { ((FlowField*)h)->makeSpectral_y(); }
 void ref_make_physical_xz(void* h) { ((FlowField*)h)->makePhysical_xz(); }
 void ref_make_spectral_xz(void* h) { ((FlowField*)h)->makeSpectral_xz(); }
 void ref_zero_padded_modes(void* h) { ((FlowField*)h)->zeroPaddedModes(); }
+// flowfield.cpp:1274-1433
+void ref_field_symmetry(void* h, int s, int sx, int sy, int sz, double ax, double az) { *((FlowField*)h) *= FieldSymmetry(sx, sy, sz, ax, az, s); }
 
 // tools/randomfield.cpp:50-67
 void ref_randomfield(void* h, int seed, double magn, double smooth, int meanflow) {

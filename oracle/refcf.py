@@ -80,6 +80,7 @@ def lib():
         L.ref_field_get_state.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
         L.ref_field_set_padded.argtypes = [vp, i]
         L.ref_field_copy.argtypes = [vp, vp]
+        L.ref_field_symmetry.argtypes = [vp, i, i, i, i, d, d]
         L.ref_randomfield.argtypes = [vp, i, d, d, i]
         L.ref_load_padded_physical.argtypes = [vp, dp, i, i]
         L.ref_field2vector.argtypes = [vp, dp]
@@ -167,6 +168,7 @@ class RefField:
     def make_physical_xz(self): lib().ref_make_physical_xz(self.h)
     def make_spectral_xz(self): lib().ref_make_spectral_xz(self.h)
     def zero_padded_modes(self): lib().ref_zero_padded_modes(self.h)
+    def symmetry(self, s, sx, sy, sz, ax, az): lib().ref_field_symmetry(self.h, s, sx, sy, sz, ax, az)
     def l2norm(self): return lib().ref_l2norm(self.h)
     def l2norm3d(self):
         lib().ref_l2norm3d.restype = C.c_double

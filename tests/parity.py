@@ -329,3 +329,60 @@ def graph_equivalence(lib, cfg, nsteps=100, **flag_over):
     return {"u_identical": bool(np.array_equal(res["0"]["u"], res["1"]["u"])), "q_identical": bool(np.array_equal(res["0"]["q"], res["1"]["q"])),
             "cfl_identical": res["0"]["cfl"] == res["1"]["cfl"], "sec_eager": res["0"]["sec"], "sec_graph": res["1"]["sec"],
             "launches_eager": res["0"]["launches"], "launches_graph": res["1"]["launches"]}
+
+
+SYMMETRIES = ((1, 1, 1, 1, 0.3, 0.1), (1, -1, 1, 1, 0.2, 0.0), (1, 1, -1, 1, 0.0, 0.0), (1, 1, 1, -1, 0.0, 0.37), (-1, -1, -1, -1, 0.5, 0.5),
+              (1, -1, -1, 1, 0.5, 0.0), (-1, 1, 1, -1, 0.25, 0.5), (1, -1, 1, -1, 0.1, 0.2))
+
+
+def symmetry_ops(lib, cfg, syms=SYMMETRIES):
+    """FlowField *= FieldSymmetry on the device against flowfield.cpp:1274-1433, padded (de-aliased box) and full spectra."""
+    worst = 0.0
+    for padded in (True, False):
+        for sym in syms:
+            ur = ref_random(cfg, 3)
+            if not padded:
+                rng = np.random.default_rng(1)
+                ur.data[...] = 1e-2 * rng.standard_normal(ur.data.shape)
+                ur.set_padded(False)
+                ur.set_state(0, 0)
+                ur.make_spectral()   # a consistent full spectrum (all modes, Nyquist rows included)
+            ug = to_gpu(lib, ur, padded=padded)
+            ur.symmetry(*sym)
+            ug.symmetry(*sym)
+            worst = max(worst, rel_l2(ug.get(), ur.data))
+    return worst
+
+
+def load_eq(lib, scale=1.0):
+    """tests/golden/eq.npz (reference tests/data/eq.nc, 24x33x24): the solution findsolnTest.cpp searches for, on the device."""
+    g = np.load(os.path.join(GOLDEN, "eq.npz"))
+    geo = dict(Nx=int(g["Nx"]), Ny=int(g["Ny"]), Nz=int(g["Nz"]), Lx=float(g["Lx"]), Lz=float(g["Lz"]), a=float(g["a"]), b=float(g["b"]))
+    ur = refcf.RefField(geo["Nx"], geo["Ny"], geo["Nz"], 3, geo["Lx"], geo["Lz"], geo["a"], geo["b"]).load_padded_physical(g["u"])
+    ur.make_spectral()
+    ug = to_gpu(lib, ur)
+    if scale != 1.0:
+        ug.scale(scale)
+    return ug, ur
+
+
+EQ_SIGMA = (1, 1, 1, 1, 0.28168880386692519, 0.0)   # reference tests/data/sigmabest.asc
+
+
+def findsoln_eq(lib, Nnewton=6, epsSearch=1e-11):
+    """tests/findsolnTest.cpp (`findsoln -eqb -xrel -T 10 -sigma sigmabest`): perturb the stored travelling wave by 1.001 and
+    let the Newton-Krylov-hookstep search pull it back (plane Couette Re 400, the x phase shift is an unknown of the search).
+    Returns the search record and the distance to the stored field."""
+    import time
+    ug, ur = load_eq(lib, 1.001)
+    fl = dict(C1["flags"])
+    t0 = time.perf_counter()
+    r = cf.hookstep_search(ug, cf.make_flags(**fl), 10.0, 0.03125, sigma=EQ_SIGMA, Nnewton=Nnewton, epsSearch=epsSearch, xrelative=True)
+    r["seconds"] = time.perf_counter() - t0
+    r["dist_to_stored"] = rel_l2(ug.get(), ur.data) * float(np.linalg.norm(ur.data.ravel())) / max(float(np.linalg.norm(ug.get().ravel())), 1e-300)
+    sol = refcf.RefField(ur.Nx, ur.Ny, ur.Nz, 3, ur.Lx, ur.Lz, ur.a, ur.b)
+    sol.data[...] = ug.get()
+    sol.set_padded(True)
+    r["l2dist_to_stored"] = sol.l2dist(ur)
+    r["div_bc"] = (sol.divnorm(), sol.bcnorm())
+    return r

@@ -271,3 +271,19 @@ def test_tile_layout_is_transparent(lib, junk):
     assert r["u_equal"] and r["q_equal"] and r["junk_kept"] and r["moved"] > 0, r
     r = parity.layout_equivalence(lib, parity.C1, nsteps=3, junk=junk, timestepping="cnab2")
     assert r["u_equal"] and r["q_equal"] and r["junk_kept"], r
+
+
+def test_field_symmetry_ops(lib):
+    assert parity.symmetry_ops(lib, SMALL, parity.SYMMETRIES[:6]) < 1e-14
+    assert parity.symmetry_ops(lib, ODD, parity.SYMMETRIES[5:]) < 1e-14
+
+
+def test_hookstep_search_mechanics(lib):
+    """Newton-GMRES-hookstep on the device vectors: near the laminar state (G(0) = 0) one Newton step from a 5-vector Krylov
+    space must reduce |G| exactly as its linear model predicts (finite-difference Jacobian, Arnoldi, SVD of the Hessenberg
+    problem).  The full search on the stored equilibrium runs on the GPU (test_gpu.py)."""
+    cfg = dict(parity.C1, Nx=8, Ny=13, Nz=8)
+    ug = parity.to_gpu(lib, parity.ref_random(cfg, 3, magn=1e-3))
+    r = cf.hookstep_search(ug, cf.make_flags(**cfg["flags"]), 0.25, 0.03125, Nnewton=1, Ngmres=5, epsSearch=1e-12, delta=0.1)
+    assert r["newton_steps"] == 1 and r["fevals"] == 7 and r["gmres_iterations"] == 5, r
+    assert r["history"][1] < 0.8 * r["history"][0], r

@@ -268,3 +268,19 @@ def test_cuda_graph_replay_is_bit_identical(lib, cfgname):
     r = parity.graph_equivalence(lib, cfg)
     assert r["u_identical"] and r["q_identical"] and r["cfl_identical"], r
     print("graph replay:", {k: v for k, v in r.items() if "sec" in k or "launch" in k})
+
+
+def test_field_symmetry_ops(lib):
+    for cfg in (dict(parity.C1, Nx=16, Ny=17, Nz=12), dict(parity.C1, Nx=12, Ny=21, Nz=18, Lx=5.5, Lz=2.5), parity.C1):
+        assert parity.symmetry_ops(lib, cfg) < 1e-14
+
+
+def test_findsoln_reconverges_to_the_stored_solution(lib):
+    """North-star gate: the Newton-Krylov-hookstep search (device vectors, one DNS integration per Krylov vector) converges
+    from the perturbed guess of tests/findsolnTest.cpp to residual <= 1e-10, and lands on the stored solution (the
+    reference test's own tolerance for that distance is 1e-5, findsolnTest.cpp:129)."""
+    r = parity.findsoln_eq(lib)
+    print("findsoln:", {k: v for k, v in r.items()})
+    assert r["residual"] <= 1e-10, r
+    assert r["l2dist_to_stored"] < 1e-5, r
+    assert max(r["div_bc"]) < 1e-10, r
