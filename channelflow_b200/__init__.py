@@ -31,7 +31,7 @@ cfgpu_nse_destroy cfgpu_nse_set_constraint cfgpu_nse_reset_lambda cfgpu_nse_nonl
 cfgpu_nse_linear cfgpu_nse_cflfactor cfgpu_nse_get_dPd cfgpu_comm_unique_id cfgpu_comm_init_nccl
 cfgpu_comm_init_external cfgpu_comm_rank cfgpu_comm_ranges cfgpu_field_allgather
 cfgpu_field_copy_component cfgpu_l2form_box cfgpu_bcnorm2 cfgpu_field_diffop cfgpu_field_pointwise
-cfgpu_helmholtz_solve cfgpu_tridiag cfgpu_tausolve_mode cfgpu_poisson_solve cfgpu_pressure_neumann cfgpu_field_symmetry
+cfgpu_helmholtz_solve cfgpu_tridiag cfgpu_tausolve_mode cfgpu_poisson_solve cfgpu_pressure_neumann cfgpu_field_symmetry cfgpu_chebyform
 cfgpu_vec_create cfgpu_vec_destroy cfgpu_vec_size cfgpu_vec_upload cfgpu_vec_download cfgpu_vec_copy cfgpu_vec_zero cfgpu_vec_dot
 cfgpu_vec_nrm2 cfgpu_vec_axpy cfgpu_vec_axpby cfgpu_vec_scal cfgpu_field2vector_size cfgpu_field2vector cfgpu_vector2field""".split()
 
@@ -105,6 +105,7 @@ class GpuLib:
         L.cfgpu_nse_get_dPd.argtypes = [vp, dpt, dpt]
         L.cfgpu_poisson_solve.argtypes = [vp, vp, vp]
         L.cfgpu_field_symmetry.argtypes = [vp, i, i, i, i, d, d]
+        L.cfgpu_chebyform.argtypes = [vp, vp, i, i, dpt]
         L.cfgpu_pressure_neumann.argtypes = [vp, vp, vp, d]
         L.cfgpu_helmholtz_solve.argtypes = [vp, i, d, d, d, d, i, dpt, dpt, dpt, dpt]
         L.cfgpu_tridiag.argtypes = [vp, i, i, dpt, dpt, dpt, dpt, i, i, i]

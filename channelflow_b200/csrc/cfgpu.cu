@@ -177,6 +177,11 @@ int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out) {
         }
     CF_TRY(upload(Ce, &pl.Ce)); CF_TRY(upload(Co, &pl.Co)); CF_TRY(upload(CDe, &pl.CDe)); CF_TRY(upload(CDo, &pl.CDo));
     CF_TRY(upload(Fe, &pl.Fe)); CF_TRY(upload(Fo, &pl.Fo)); CF_TRY(upload(W, &pl.Wgram));
+    {   // pi/2 c_n on the diagonal, c_0 = 2 (the weight-1/sqrt(1-y^2) inner product of T_m, T_n)
+        std::vector<double> Wc((size_t)N * N, 0.0);
+        for (int n = 0; n < N; ++n) Wc[(size_t)n * N + n] = 0.5 * 3.14159265358979323846264338327950288 * (n == 0 ? 2.0 : 1.0);
+        CF_TRY(upload(Wc, &pl.Wcheb));
+    }
     for (int h = 0; h < 2; ++h) { CF_TRY(upload(GDe[h], &pl.GDe[h])); CF_TRY(upload(GDo[h], &pl.GDo[h])); }
     auto res = ctx->yplans.emplace(key, pl);
     *out = &res.first->second;
@@ -328,7 +333,7 @@ int cfgpu_finalize(cfgpu_ctx ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->yplans) {
         YPlan& p = kv.second;
-        cudaFree(p.Ce); cudaFree(p.Co); cudaFree(p.CDe); cudaFree(p.CDo); cudaFree(p.Fe); cudaFree(p.Fo); cudaFree(p.Wgram);
+        cudaFree(p.Ce); cudaFree(p.Co); cudaFree(p.CDe); cudaFree(p.CDo); cudaFree(p.Fe); cudaFree(p.Fo); cudaFree(p.Wgram); cudaFree(p.Wcheb);
         for (int h = 0; h < 2; ++h) { cudaFree(p.GDe[h]); cudaFree(p.GDo[h]); }
     }
     for (auto& kv : ctx->fftplans) cudaFree(kv.second.tw);
@@ -953,7 +958,7 @@ int cfgpu_field_make_spectral(cfgpu_field f) {
 }
 
 // ------------------------------------------------------------------------------------------------ norms
-static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool padded, double* out_h, bool skip_kx0 = false) {
+static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool padded, double* out_h, bool skip_kx0 = false, bool cheby = false) {
     CF_TRY(field_serial(u)); if (v) CF_TRY(field_serial(v));
     CF_ARG(u->xzstate == CFGPU_SPECTRAL && u->ystate == CFGPU_SPECTRAL, "L2 norm: field must be spectral");
     cfgpu_ctx ctx = u->ctx;
@@ -972,7 +977,7 @@ static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool pa
         part_range(2 * Kx + 1, ctx->comm.nranks, ctx->comm.rank, x0, x1);
     }
     if (skip_kx0 && x0 < 1) x0 = 1;  // row 0 is kx = 0 in both enumerations
-    CF_TRY(l2form_launch(u->dser, v ? v->dser : nullptr, mode, pl->Wgram, u->Ny, u->Nx, u->Nz, u->Nd, Kx, Kz, padded ? 0 : 1, x0, x1, scale,
+    CF_TRY(l2form_launch(u->dser, v ? v->dser : nullptr, mode, cheby ? pl->Wcheb : pl->Wgram, u->Ny, u->Nx, u->Nz, u->Nd, Kx, Kz, padded ? 0 : 1, x0, x1, scale,
                          partial, cap, out_dev, ctx->stream));
     CF_TRY(comm_allreduce(ctx->comm, out_dev, 1, 0, ctx->stream));
     CF_CUDA(cudaMemcpyAsync(out_h, out_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -980,6 +985,11 @@ static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool pa
     return 0;
 }
 int cfgpu_l2norm2(cfgpu_field u, int normalize, double* out_h) { return l2form(u, nullptr, 0, normalize, u->padded != 0, out_h); }
+// chebyNorm2 / chebyDist2 / chebyInnerProduct (diffops.cpp:259-350): mode 0 / 1 / 2, v NULL for the norm
+int cfgpu_chebyform(cfgpu_field u, cfgpu_field v, int mode, int normalize, double* out_h) {
+    CF_ARG(u && out_h && mode >= 0 && mode <= 2 && (mode == 0 || v), "cfgpu_chebyform: bad argument");
+    return l2form(u, mode == 0 ? nullptr : v, mode, normalize, u->padded != 0, out_h, false, true);
+}
 
 // L2Norm2 / L2Dist2 / L2InnerProduct restricted to |kx| <= kxmax, kz <= kzmax (diffops.cpp:543-700); cz = 0 sums the stored
 // modes without the factor 2 for kz > 0 (the convention of divNorm2, diffops.cpp:91-116)

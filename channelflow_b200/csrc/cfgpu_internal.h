@@ -27,6 +27,7 @@ struct YPlan {
     // tile ([0]: times 1, [1]: times 1/2 for the skew-symmetric form)
     double *GDe[2] = {nullptr, nullptr}, *GDo[2] = {nullptr, nullptr};
     double* Wgram = nullptr;  // [N][N] Chebyshev Gram weights for the L2 norms
+    double* Wcheb = nullptr;  // [N][N] diagonal weights of the Chebyshev-weighted norm (chebyNorm2, diffops.cpp:260-300)
 };
 
 struct FftPlanHost {

@@ -282,47 +282,47 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 4 : 2) zpas
     for (int t = tid; t < NTW; t += NT) tws[t] = __ldg(&p.plan.tw[t]);
     // rows nkz .. Nz-nkz (the de-aliased band and the Nyquist mode) are not written by the packing loop below
     const int nzero = Nz - 2 * nkz + 1;
-    for (int idx = tid; idx < nzero * njobs; idx += NT) {
-        const int j = idx / nzero, k = nkz + (idx - j * nzero);
-        buf[(size_t)j * NP + fft_skew2(fft_digit_rev<NZ>(k))] = make_double2(0.0, 0.0);
+    for (int k = nkz + tid; k < nkz + nzero; k += NT) {   // (no runtime divisions in the index arithmetic of this kernel)
+        const int a = fft_skew2(fft_digit_rev<NZ>(k));
+        for (int j = 0; j < njobs; ++j) buf[(size_t)j * NP + a] = make_double2(0.0, 0.0);
     }
     const double2* __restrict__ Q = p.Q + (size_t)yl * Nx * nkz;
-    // two (line, kz) items per thread in flight: all loads are issued before the first use
-    for (int i0 = tid; i0 < TL * nkz; i0 += 2 * NT) {
-        double2 fa[2][3], fb[2][3];
+    // item = (line l, mode k): thread t takes mode k = t (+ NT ...) of two lines at a time, so that two items are in flight
+    // (all loads issued before the first use) and the digit-reversed slot of k is computed once per pair
+    for (int k = tid; k < nkz; k += NT) {
+        const int ka = fft_skew2(fft_digit_rev<NZ>(k)), kb = fft_skew2(fft_digit_rev<NZ>(k > 0 ? Nz - k : 0));  // inputs of the DIT transform
+        for (int l0 = 0; l0 < TL; l0 += 2) {
+            double2 fa[2][3], fb[2][3];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int idx = i0 + h * NT;
-            const int l = idx / nkz, k = idx - l * nkz;
-            const int nx = nx0 + l;
+            for (int h = 0; h < 2; ++h) {
+                const int l = l0 + h, nx = nx0 + l;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) fa[h][q] = fb[h][q] = make_double2(0.0, 0.0);
-            if (idx < TL * nkz && nx < Nx) {
-                const size_t off = (size_t)nx * nkz + k;
-                if (rot) {
-                    fa[h][0] = Q[off];               fb[h][0] = Q[fstride + off];       // u, v
-                    fa[h][1] = Q[2 * fstride + off]; fb[h][1] = Q[3 * fstride + off];   // w, omega_x
-                    fa[h][2] = Q[4 * fstride + off]; fb[h][2] = Q[5 * fstride + off];   // omega_y, omega_z
-                } else {
-                    fa[h][0] = Q[off];               fb[h][0] = Q[fstride + off];
-                    fa[h][1] = Q[2 * fstride + off];
+                for (int q = 0; q < 3; ++q) fa[h][q] = fb[h][q] = make_double2(0.0, 0.0);
+                if (l < TL && nx < Nx) {
+                    const size_t off = (size_t)nx * nkz + k;
+                    if (rot) {
+                        fa[h][0] = Q[off];               fb[h][0] = Q[fstride + off];       // u, v
+                        fa[h][1] = Q[2 * fstride + off]; fb[h][1] = Q[3 * fstride + off];   // w, omega_x
+                        fa[h][2] = Q[4 * fstride + off]; fb[h][2] = Q[5 * fstride + off];   // omega_y, omega_z
+                    } else {
+                        fa[h][0] = Q[off];               fb[h][0] = Q[fstride + off];
+                        fa[h][1] = Q[2 * fstride + off];
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int idx = i0 + h * NT;
-            if (idx >= TL * nkz) break;
-            const int l = idx / nkz, k = idx - l * nkz;
-            const int ka = fft_skew2(fft_digit_rev<NZ>(k)), kb = fft_skew2(fft_digit_rev<NZ>(k > 0 ? Nz - k : 0));  // inputs of the DIT transform
+            for (int h = 0; h < 2; ++h) {
+                const int l = l0 + h;
+                if (l >= TL) break;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                if (q >= npair) break;
-                double2 a = fa[h][q], b = fb[h][q];
-                if (k == 0) { a.y = 0.0; b.y = 0.0; }  // c2r ignores the imaginary part of the mean mode
-                double2* line = buf + (size_t)(q * TL + l) * NP;
-                line[ka] = make_double2(a.x - b.y, a.y + b.x);
-                if (k > 0) line[kb] = make_double2(a.x + b.y, b.x - a.y);
+                for (int q = 0; q < 3; ++q) {
+                    if (q >= npair) break;
+                    double2 a = fa[h][q], b = fb[h][q];
+                    if (k == 0) { a.y = 0.0; b.y = 0.0; }  // c2r ignores the imaginary part of the mean mode
+                    double2* line = buf + (size_t)(q * TL + l) * NP;
+                    line[ka] = make_double2(a.x - b.y, a.y + b.x);
+                    if (k > 0) line[kb] = make_double2(a.x + b.y, b.x - a.y);
+                }
             }
         }
     }
@@ -411,19 +411,19 @@ __global__ void __launch_bounds__(NZ == 512 ? 192 : 320, NZ == 512 ? 4 : 2) zpas
 
     double2* __restrict__ F = p.F + (size_t)yl * Nx * nkz;
     const double hs = 0.5 * p.scale;
-    for (int idx = tid; idx < TL * nkz; idx += NT) {
-        const int l = idx / nkz, k = idx - l * nkz;
-        const int nx = nx0 + l;
-        if (nx >= Nx) continue;
-        const double2* g = buf + (size_t)l * NP;                        // transform 0 of line l: fx + i fy
-        const double2* h = buf + (size_t)(TL + (l & ~1)) * NP;          // f_z of the pair: fz(even line) + i fz(odd line)
+    for (int k = tid; k < nkz; k += NT) {
         const int ks = fft_skew2(fft_digit_rev<NZ>(k)), kn = fft_skew2(fft_digit_rev<NZ>(k == 0 ? 0 : Nz - k));  // DIF outputs
-        const double2 gk = g[ks], gn = g[kn], hk = h[ks], hn = h[kn];
-        const size_t off = (size_t)nx * nkz + k;
-        const double2 re = make_double2(hs * (gk.x + gn.x), hs * (gk.y - gn.y)), im = make_double2(hs * (gk.y + gn.y), -hs * (gk.x - gn.x));
-        F[off] = re;
-        F[fstride + off] = im;
-        F[2 * fstride + off] = (l & 1) ? make_double2(hs * (hk.y + hn.y), -hs * (hk.x - hn.x)) : make_double2(hs * (hk.x + hn.x), hs * (hk.y - hn.y));
+        for (int l = 0; l < TL; ++l) {
+            const int nx = nx0 + l;
+            if (nx >= Nx) break;
+            const double2* g = buf + (size_t)l * NP;                        // transform 0 of line l: fx + i fy
+            const double2* h = buf + (size_t)(TL + (l & ~1)) * NP;          // f_z of the pair: fz(even line) + i fz(odd line)
+            const double2 gk = g[ks], gn = g[kn], hk = h[ks], hn = h[kn];
+            const size_t off = (size_t)nx * nkz + k;
+            F[off] = make_double2(hs * (gk.x + gn.x), hs * (gk.y - gn.y));
+            F[fstride + off] = make_double2(hs * (gk.y + gn.y), -hs * (gk.x - gn.x));
+            F[2 * fstride + off] = (l & 1) ? make_double2(hs * (hk.y + hn.y), -hs * (hk.x - hn.x)) : make_double2(hs * (hk.x + hn.x), hs * (hk.y - hn.y));
+        }
     }
 }
 

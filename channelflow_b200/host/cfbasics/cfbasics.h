@@ -156,10 +156,10 @@ inline void rename(const std::string& oldname, const std::string& newname) {
     if (mpirank() == 0) ::rename(oldname.c_str(), newname.c_str());
 }
 inline std::string pathfix(const std::string& path) { return (!path.empty() && path.back() != '/') ? path + "/" : path; }
-inline std::string t2s(Real t, bool decimals) {
+inline std::string t2s(Real t, bool inttime) {  // the reference declares the flag as `decimals` and defines it as `inttime`
     char b[32];
-    if (decimals) std::snprintf(b, sizeof b, "%.3f", t);
-    else std::snprintf(b, sizeof b, "%d", iround(t));
+    if (inttime) std::snprintf(b, sizeof b, "%d", iround(t));
+    else std::snprintf(b, sizeof b, "%.3f", t);
     return b;
 }
 inline std::string clip(const std::string& filename, const std::string& ext) { return removeSuffix(filename, ext); }

@@ -19,6 +19,10 @@ Real L2Norm(const FlowField& f, bool normalize = true);
 Real L2Norm2(const FlowField& f, bool normalize = true);
 Real L2Dist(const FlowField& f, const FlowField& g, bool normalize = true);
 Real L2Dist2(const FlowField& f, const FlowField& g, bool normalize = true);
+Real chebyNorm(const FlowField& f, bool normalize = true);
+Real chebyNorm2(const FlowField& f, bool normalize = true);
+Real chebyDist(const FlowField& f, const FlowField& g, bool normalize = true);
+Real chebyDist2(const FlowField& f, const FlowField& g, bool normalize = true);
 Real bcNorm(const FlowField& f, bool normalize = true);
 Real bcNorm2(const FlowField& f, bool normalize = true);
 Real bcDist(const FlowField& f, const FlowField& g, bool normalize = true);

@@ -65,6 +65,19 @@ Real L2InnerProduct(const FlowField& u, const FlowField& v, bool normalize) {
     cfgpu_check(cfgpu_l2ip(u.device(), v.device(), normalize ? 1 : 0, &r), "cfgpu_l2ip");
     return r;
 }
+// Chebyshev-weighted norms (diffops.cpp:259-350): the y inner product with weight 1/sqrt(1-y^2), diagonal in the coefficients
+Real chebyNorm2(const FlowField& u, bool normalize) {
+    Real r = 0;
+    cfgpu_check(cfgpu_chebyform(u.device(), nullptr, 0, normalize ? 1 : 0, &r), "cfgpu_chebyform");
+    return r;
+}
+Real chebyNorm(const FlowField& u, bool normalize) { return sqrt(chebyNorm2(u, normalize)); }
+Real chebyDist2(const FlowField& u, const FlowField& v, bool normalize) {
+    Real r = 0;
+    cfgpu_check(cfgpu_chebyform(u.device(), v.device(), 1, normalize ? 1 : 0, &r), "cfgpu_chebyform");
+    return r;
+}
+Real chebyDist(const FlowField& u, const FlowField& v, bool normalize) { return sqrt(chebyDist2(u, v, normalize)); }
 static void default_box(const FlowField& f, int& kxmax, int& kzmax, bool zero_means_default) {
     if (kxmax < 0 || kxmax > f.kxmax() || (zero_means_default && kxmax == 0)) kxmax = f.padded() ? f.kxmaxDealiased() : f.kxmax();
     if (kzmax < 0 || kzmax > f.kzmax() || (zero_means_default && kzmax == 0)) kzmax = f.padded() ? f.kzmaxDealiased() : f.kzmax();

@@ -210,10 +210,15 @@ std::ostream& operator<<(std::ostream& os, const DNSFlags& f) {
     const char* s = ", ";
     const auto p = os.precision();
     os.precision(16);
-    os << "nu==" << f.nu << s << "Vsuck==" << f.Vsuck << s << "rotation==" << f.rotation << s << "dPdx==" << f.dPdx << s
-       << "Ubulk==" << f.Ubulk << s << "dt==" << f.dt << s << f.baseflow << s << f.constraint << s << f.timestepping << s
-       << f.initstepping << s << f.nonlinearity << s << f.dealiasing << s
-       << (f.taucorrection ? "TauCorrection" : "NoTauCorrection");
+    // one record per run in the reference's field order (dnsflags.cpp:976-993): logs of the two builds can be diffed
+    const std::pair<const char*, Real> nums[] = {{"nu", f.nu}, {"Vsuck", f.Vsuck}, {"rotation", f.rotation}, {"theta", f.theta}, {"dPdx", f.dPdx},
+        {"dPdz", f.dPdz}, {"Ubulk", f.Ubulk}, {"Wbulk", f.Wbulk}, {"uwall", f.Uwall}, {"uupper", f.uupperwall}, {"ulower", f.ulowerwall},
+        {"wupper", f.wupperwall}, {"wlower", f.wlowerwall}, {"t0", f.t0}, {"dT", f.dT}, {"dt", f.dt}};
+    for (const auto& kv : nums) os << kv.first << "==" << kv.second << s;
+    os << "variabledt==" << f.variabledt << s << "dtmin==" << f.dtmin << s << "dtmax==" << f.dtmax << s << "CFLmin==" << f.CFLmin << s
+       << "CFLmax==" << f.CFLmax << s << f.baseflow << s << f.constraint << s << f.timestepping << s << f.initstepping << s << f.nonlinearity
+       << s << f.dealiasing << s << (f.bodyforce ? "nonzero_bodyforce" : "zero_bodyforce") << s
+       << (f.taucorrection ? "TauCorrection" : "NoTauCorrection") << s << f.verbosity;
     os.precision(p);
     return os;
 }

@@ -129,6 +129,8 @@ int cfgpu_l2norm2(cfgpu_field u, int normalize, double* out_h);
 int cfgpu_l2norm2_3d(cfgpu_field u, int normalize, double* out_h);
 int cfgpu_l2dist2(cfgpu_field u, cfgpu_field v, int normalize, double* out_h);
 int cfgpu_l2ip(cfgpu_field u, cfgpu_field v, int normalize, double* out_h);
+/* chebyNorm2 / chebyDist2 / chebyInnerProduct (diffops.cpp:259-350): mode 0 / 1 / 2 with the Chebyshev weight in y */
+int cfgpu_chebyform(cfgpu_field u, cfgpu_field v, int mode, int normalize, double* out_h);
 
 /* L2Norm2 / L2Dist2 / L2InnerProduct (mode 0 / 1 / 2) over the modes |kx| <= kxmax, kz <= kzmax (diffops.cpp:543-700);
  * cz = 0 drops the factor 2 of the kz > 0 modes (divNorm2's convention, diffops.cpp:91-116) */

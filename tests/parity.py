@@ -386,3 +386,34 @@ def findsoln_eq(lib, Nnewton=6, epsSearch=1e-11):
     r["l2dist_to_stored"] = sol.l2dist(ur)
     r["div_bc"] = (sol.divnorm(), sol.bcnorm())
     return r
+
+
+def variable_dt_loop(lib, cfg, nintervals=4, dT=0.25, dt0=0.02, CFLmin=0.4, CFLmax=0.6, **flag_over):
+    """The variable-time-step loop of simulateflow (programs/simulateflow.cpp:117-143; BASELINE configs[1]):
+        CFL = dns.CFL(u); dns.advance(fields, dt.n()); if (dt.adjust(CFL)) dns.reset_dt(dt);
+    on the reference and on the device with the same TimeStep object (this package's, fed with the device CFL).  Returns the
+    relative CFL mismatch per interval, the number of dt changes, and the final field error."""
+    fl = dict(cfg["flags"]); fl.update(flag_over); fl["dt"] = dt0
+    ur = ref_random(cfg, 5, magn=float(cfg.get("magn", 0.2)))
+    rd = refcf.RefDNS(ur, refcf.make_flags(**fl))
+    gd = cf.DNS(to_gpu(lib, ur), cf.make_flags(**fl))
+    L = lib.L
+    ts = L.cf_timestep_create(dt0, 1e-4, 0.2, dT, CFLmin, CFLmax, 1)
+    out = {"cfl_rel": [], "dt": [], "changes": 0, "steps": 0}
+    for _ in range(nintervals):
+        cg, cr = gd.cfl(), rd.cfl()
+        out["cfl_rel"].append(abs(cg - cr) / max(abs(cr), 1e-300))
+        n = L.cf_timestep_n(ts)
+        rd.advance(n); gd.advance(n)
+        out["steps"] += n
+        out["dt"].append(L.cf_timestep_dt(ts))
+        if L.cf_timestep_adjust(ts, cg):
+            out["changes"] += 1
+            dt = L.cf_timestep_dt(ts)
+            rd.reset_dt(dt); gd.reset_dt(dt)
+    L.cf_timestep_free(ts)
+    u1, q1 = rd.get(); u2, q2 = gd.get()
+    out["u_rel"] = rel_l2(u2.get(), u1.data)
+    out["q_rel"] = rel_l2(q2.get(), q1.data)
+    out["dPdx"] = abs(gd.dPdx() - rd.dPdx())
+    return out

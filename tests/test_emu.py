@@ -287,3 +287,11 @@ def test_hookstep_search_mechanics(lib):
     r = cf.hookstep_search(ug, cf.make_flags(**cfg["flags"]), 0.25, 0.03125, Nnewton=1, Ngmres=5, epsSearch=1e-12, delta=0.1)
     assert r["newton_steps"] == 1 and r["fevals"] == 7 and r["gmres_iterations"] == 5, r
     assert r["history"][1] < 0.8 * r["history"][0], r
+
+
+def test_variable_dt_loop(lib):
+    """TimeStep::adjust -> DNS::reset_dt loop against the reference (small grid; the C2-sized run is in test_gpu.py)."""
+    r = parity.variable_dt_loop(lib, dict(SMALL, magn=0.5), nintervals=3, dT=0.1, dt0=0.0125, nonlinearity="skew", constraint="bulkv",
+                                Ubulk=2.0 / 3, ulowerwall=0.0, uupperwall=0.0, nu=1 / 1800.0)
+    assert r["changes"] >= 1, r
+    assert max(r["cfl_rel"]) < 1e-11 and r["u_rel"] < 1e-11 and r["dPdx"] < 1e-11, r

@@ -284,3 +284,15 @@ def test_findsoln_reconverges_to_the_stored_solution(lib):
     assert r["residual"] <= 1e-10, r
     assert r["l2dist_to_stored"] < 1e-5, r
     assert max(r["div_bc"]) < 1e-10, r
+
+
+def test_c2_variable_dt_loop(lib):
+    """BASELINE configs[1]: plane Poiseuille at fixed flux, skew-symmetric form, variable dt -- the TimeStep::adjust ->
+    DNS::reset_dt loop (every change rebuilds the tau operators and restarts SBDF3 with its SMRK2 initial steps) at
+    128x97x128 against the compiled reference."""
+    cfg = dict(parity.C1, Nx=128, Ny=97, Nz=128, Lx=2 * np.pi, Lz=np.pi, magn=0.3)
+    r = parity.variable_dt_loop(lib, cfg, nintervals=4, dT=0.1, dt0=0.004, nonlinearity="skew", constraint="bulkv", Ubulk=2.0 / 3,
+                                ulowerwall=0.0, uupperwall=0.0, nu=1 / 1800.0)
+    print("variable dt:", r)
+    assert r["changes"] >= 1 and r["steps"] >= 20, r
+    assert max(r["cfl_rel"]) < 1e-10 and r["u_rel"] < 1e-10 and r["dPdx"] < 1e-10, r

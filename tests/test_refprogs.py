@@ -135,3 +135,114 @@ def test_tausolver_program_passes_on_emulation(tmp_path):
     _build("emu")
     r = _run("emu", "tausolverTest", (), tmp_path, 1800)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-1500:])
+
+
+# ---------------------------------------------------------------------------------------------- simulateflow, unchanged
+ORACLE_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+
+
+def _simulateflow_pair(flavour, tmp_path, grid, T, timeout):
+    """BASELINE configs[0]: the reference's programs/simulateflow.cpp and tools/randomfield.cpp, compiled UNMODIFIED against
+    the drop-in headers, next to the same two programs of the compiled reference (oracle/_ref/bin) on the same command line:
+    plane Couette Re 400, SBDF3, rotational, 2/3 dealiasing, dt = 0.02.  Returns (relative L2 difference of the saved final
+    fields, the two stdout logs)."""
+    import channelflow_b200 as cf
+    from tests import parity
+    for exe in ("simulateflow", "randomfield"):
+        if not os.path.exists(os.path.join(PROGS, flavour, exe)) or not os.path.exists(os.path.join(ORACLE_BIN, exe)):
+            pytest.skip("simulateflow/randomfield binaries not built (need /root/reference at build time)")
+    Nx, Ny, Nz = grid
+    rf = ["-Nx", str(Nx), "-Ny", str(Ny), "-Nz", str(Nz), "-lx", "1", "-lz", "0.5", "-sd", "1", "-s", "0.4", "-m", "0.2", "u0"]
+    sim = ["-R", "400", "-T", str(T), "-dt", "0.02", "-vdt", "false", "-dT", "1", "-l2", "-cfl", "-dv", "u0"]
+    logs = {}
+    for side, bindir in (("ref", ORACLE_BIN), ("new", os.path.join(PROGS, flavour))):
+        d = tmp_path / side
+        d.mkdir()
+        r = subprocess.run([os.path.join(bindir, "randomfield")] + rf, cwd=str(d), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+        assert r.returncode == 0, r.stdout[-2000:]
+        r = subprocess.run([os.path.join(bindir, "simulateflow")] + sim, cwd=str(d), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+        assert r.returncode == 0, r.stdout[-3000:]
+        logs[side] = r.stdout
+        assert os.path.exists(str(d / "data" / ("u%d.ff" % T))), os.listdir(str(d / "data"))
+    lib = parity.gpu_lib() if flavour == "gpu" else parity.emu_lib()
+
+    def load(path):
+        h = lib.L.cf_field_load(path.encode())
+        return cf.FlowField(lib, Nx, Ny, Nz, 3, 2 * np.pi, np.pi, handle=h).get()
+    out = {}
+    for name in ("u0", "data/u%d" % T):
+        a, b = load(str(tmp_path / "ref" / name)), load(str(tmp_path / "new" / name))
+        out[name] = float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(a.ravel()))
+    return out, logs
+
+
+def _diag_lines(log, key):
+    return [float(l.split("==")[1].split()[0]) for l in log.splitlines() if l.strip().startswith(key + " ==")]
+
+
+@pytest.mark.gpu
+def test_simulateflow_runs_unchanged_c1(tmp_path):
+    """north_star: `simulateflow` runs unchanged on top of the B200 path; C1 = 32x33x32, 100 steps: the saved field agrees with
+    the reference run to <= 1e-9 (parity gate after 100 steps), the initial field from `randomfield` to round-off."""
+    _build("gpu")
+    d, logs = _simulateflow_pair("gpu", tmp_path, (32, 33, 32), 2, 900)
+    print("simulateflow C1:", d)
+    assert d["u0"] < 1e-14 and d["data/u2"] < 1e-9, d
+    for key in ("L2Norm(u)", "CFL"):
+        np.testing.assert_allclose(_diag_lines(logs["new"], key), _diag_lines(logs["ref"], key), rtol=1e-5)
+
+
+def test_simulateflow_runs_unchanged_emulation(tmp_path):
+    from tests import parity
+    parity.emu_lib()
+    _build("emu")
+    d, logs = _simulateflow_pair("emu", tmp_path, (16, 17, 16), 1, 900)
+    assert d["u0"] < 1e-14 and d["data/u1"] < 1e-11, d
+    assert _diag_lines(logs["new"], "L2Norm(u)") == _diag_lines(logs["ref"], "L2Norm(u)")
+
+
+# ------------------------------------------------------------------- the golden pair through the reference's own programs
+def _write_golden_ff(lib, d):
+    """data/uinit.ff, data/ufinal.ff (reference tests/data/u{init,final}.nc, 48x35x48) from the committed fixture, written by
+    this package's own .ff writer (the reference reads and writes .ff when it is built without NetCDF)."""
+    from oracle import refcf
+    from tests import parity
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_pair.npz"))
+    geo = [int(g["Nx"]), int(g["Ny"]), int(g["Nz"]), 3, float(g["Lx"]), float(g["Lz"]), float(g["a"]), float(g["b"])]
+    os.makedirs(d, exist_ok=True)
+    for name in ("uinit", "ufinal"):
+        ur = refcf.RefField(*geo).load_padded_physical(g[name])
+        ur.make_spectral()
+        parity.to_gpu(lib, ur).save(os.path.join(d, name))
+
+
+@pytest.mark.gpu
+def test_time_integration_program_golden_pair(tmp_path):
+    """tests/timeIntegrationTest.cpp, unmodified: uinit -> 440 SBDF3 steps -> L2Dist to ufinal below its own 1e-13."""
+    from tests import parity
+    _build("gpu")
+    _write_golden_ff(parity.gpu_lib(), str(tmp_path / "data"))
+    exe = os.path.join(PROGS, "gpu", "timeIntegrationTest")
+    r = subprocess.run([exe], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-1500:])
+    assert "pass" in r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_benchmark_tool(tmp_path):
+    """tools/benchmark.cpp -- the reference's own timing harness (mean wall time per 40-step time unit of the golden-pair
+    run, first unit discarded) -- unmodified on the B200, next to the compiled reference on one host core."""
+    from tests import parity
+    _build("gpu")
+    _write_golden_ff(parity.gpu_lib(), str(tmp_path))
+    res = {}
+    for side, exe in (("b200", os.path.join(PROGS, "gpu", "benchmark")), ("reference_1core", os.path.join(ROOT, "oracle", "_ref", "bin", "benchmark"))):
+        if not os.path.exists(exe):
+            pytest.skip("benchmark binary not built")
+        r = subprocess.run([exe, "-d", str(tmp_path)], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:]
+        avg = [l for l in r.stdout.splitlines() if "Average time/timeunit" in l]
+        dist = [l for l in r.stdout.splitlines() if "L2Dist" in l]
+        res[side] = (float(avg[-1].split(":")[1].strip().rstrip("s")), dist[-1].strip() if dist else "")
+    print("reference benchmark tool (s per time unit of 40 steps, 48x35x48):", res)
+    assert res["b200"][0] < res["reference_1core"][0]
