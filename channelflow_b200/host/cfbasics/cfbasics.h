@@ -209,6 +209,11 @@ inline void printout(const std::string& message, int taskid, bool newline = true
 inline void printout(const std::string& message, bool newline = true, std::ostream& os = std::cout) {
     printout(message, mpirank(), newline, os);
 }
+inline void printout(const std::string& message, std::ostream& os) { printout(message, true, os); }
+inline void printout(const std::stringstream& sstr, std::ostream& os = std::cout) { printout(sstr.str(), false, os); }
+inline std::string FillSpaces(int i, int n) { return i2s(i, n, ' '); }   // FillSpaces(12, 5) = "   12"
+inline std::string FillSpaces(Real t, int n) { return FillSpaces((int)t, n); }
+inline std::string fuzzyless(Real x, Real eps) { return x < eps ? "TRUE  " : (x < std::sqrt(eps) ? "APPROX" : "false "); }
 inline std::ostream& operator<<(std::ostream& os, HookstepPhase p) {
     static const char* n[] = {"ConstantDelta", "ReducingDelta", "IncreasingDelta", "Finished"};
     return os << n[(int)p];

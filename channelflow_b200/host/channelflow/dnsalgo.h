@@ -19,7 +19,8 @@ class DNSAlgorithm {
     virtual ~DNSAlgorithm();
 
     virtual void advance(std::vector<FlowField>& fields, int nSteps = 1) = 0;
-    virtual void project() {}
+    virtual void project() {}  // project the state the algorithm holds onto the symmetric subspace of the flags
+    cfarray<FieldSymmetry> symmetries(int ifield) const { return symmetries_[ifield]; }
     virtual void reset_dt(Real dt) = 0;
     virtual bool push(const std::vector<FlowField>& fields);
     virtual bool full() const;
@@ -41,6 +42,7 @@ class DNSAlgorithm {
     Real t_ = 0;
     std::vector<Real> lambda_t_;
     std::shared_ptr<NSE> nse_;
+    std::vector<cfarray<FieldSymmetry>> symmetries_;  // per field (velocity, pressure)
     void tick() const;
     void endline() const;
 };
@@ -51,6 +53,7 @@ class MultistepDNS : public DNSAlgorithm {
     MultistepDNS(const MultistepDNS& dns);
     MultistepDNS(const std::vector<FlowField>& fields, const std::shared_ptr<NSE>& nse, const DNSFlags& flags);
     void advance(std::vector<FlowField>& fields, int nSteps = 1) override;
+    void project() override;
     void reset_dt(Real dt) override;
     bool push(const std::vector<FlowField>& fields) override;
     bool full() const override { return countdown_ == 0; }

@@ -11,6 +11,7 @@
 #include "cfbasics/mathdefs.h"
 #include "channelflow/chebyshev.h"
 #include "channelflow/flowfield.h"
+#include "channelflow/symmetry.h"
 
 namespace chflow {
 
@@ -93,6 +94,7 @@ class DNSFlags {
     int symmetryprojectioninterval;
     Verbosity verbosity;
     std::ostream* logstream;
+    cfarray<FieldSymmetry> symmetries;  // restrict u(t) to these symmetries (projection every symmetryprojectioninterval)
     std::string symmetries_file;  // -symms <file>: generators of the isotropy group to project onto (see symmetry.h)
 };
 

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "cfbasics/cfarray.h"
 #include "cfbasics/cfvector.h"
 #include "cfbasics/mathdefs.h"
 #include "cfgpu.h"
@@ -163,6 +164,8 @@ class FlowField {
 
     FlowField& operator*=(Real x);
     FlowField& operator*=(const FieldSymmetry& s);  // u <- s(u), on the device (symmetry.cpp)
+    FlowField& project(const FieldSymmetry& s);      // u <- (u + s u)/2
+    FlowField& project(const cfarray<FieldSymmetry>& s);
     FlowField& operator+=(const Real& a);        // u(0,0,0,0) += a
     FlowField& operator-=(const Real& a);
     FlowField& operator+=(const ComplexChebyCoeff& U);

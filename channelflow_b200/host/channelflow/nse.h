@@ -32,6 +32,7 @@ class NSE {
 
     virtual void reset_lambda(const std::vector<Real> lambda_t);
     virtual std::vector<FlowField> createRHS(const std::vector<FlowField>& fields) const;
+    virtual std::vector<cfarray<FieldSymmetry>> createSymmVec() const;  // symmetries confining (u, q) to a subspace
 
     int taskid() const { return 0; }
     void reset_gradp(Real dPdx, Real dPdz);

@@ -73,8 +73,12 @@ void DNS::advance(std::vector<FlowField>& fields, int Nsteps) {
         if (!fields[j].geomCongruent(fields[0]))
             fields[j].resize(fields[0].Nx(), fields[0].Ny(), fields[0].Nz(), fields[j].Nd(), fields[0].Lx(), fields[0].Lz(),
                              fields[0].a(), fields[0].b(), fields[0].cfmpi());
-    // symmetry projection (dns.cpp:152-156) is the identity unless DNSFlags::symmetries is set; not carried yet
     int n = 0;
+    // every symmetryprojectioninterval time units the state is projected back onto the symmetric subspace (dns.cpp:152-156)
+    if (flags().symmetries.length() > 0 && (int)(main_algorithm_->time()) % (int)(flags().symmetryprojectioninterval) == 0) {
+        main_algorithm_->project();
+        for (size_t j = 0; j < fields.size(); ++j) fields[j].project(main_algorithm_->symmetries((int)j));
+    }
     while (!main_algorithm_->full() && n < Nsteps) {
         main_algorithm_->push(fields);
         init_algorithm_->advance(fields, 1);

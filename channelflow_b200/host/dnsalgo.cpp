@@ -7,9 +7,9 @@ namespace chflow {
 DNSAlgorithm::DNSAlgorithm() {}
 DNSAlgorithm::DNSAlgorithm(const DNSAlgorithm& d)
     : flags_(d.flags_), order_(d.order_), numfields_(d.numfields_), Ninitsteps_(d.Ninitsteps_), t_(d.t_),
-      lambda_t_(d.lambda_t_), nse_(d.nse_) {}
+      lambda_t_(d.lambda_t_), nse_(d.nse_), symmetries_(d.symmetries_) {}
 DNSAlgorithm::DNSAlgorithm(const std::vector<FlowField>& fields, const std::shared_ptr<NSE>& nse, const DNSFlags& flags)
-    : flags_(flags), numfields_((int)fields.size()), t_(flags.t0), nse_(nse) {}
+    : flags_(flags), numfields_((int)fields.size()), t_(flags.t0), nse_(nse), symmetries_(nse->createSymmVec()) {}
 DNSAlgorithm::~DNSAlgorithm() {}
 bool DNSAlgorithm::push(const std::vector<FlowField>&) { return true; }
 bool DNSAlgorithm::full() const { return true; }
@@ -163,6 +163,15 @@ void MultistepDNS::advance(std::vector<FlowField>& fieldsn, int Nsteps) {
         }
     }
     endline();
+}
+
+// dnsalgo.cpp:255-262: the whole history is projected
+void MultistepDNS::project() {
+    for (int n = 0; n < order_; ++n)
+        for (int m = 0; m < numfields_; ++m) {
+            fields_[n][m].project(symmetries_[m]);
+            nonlf_[n][m].project(symmetries_[m]);
+        }
 }
 
 bool MultistepDNS::push(const std::vector<FlowField>& fields) {

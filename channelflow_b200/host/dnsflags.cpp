@@ -158,7 +158,10 @@ void DNSFlags::args2numerics(ArgList& args, const bool laurette) {
                                             "constrain u(t) to invariant symmetric subspace, argument is the filename for a file listing the "
                                             "generators of the isotropy group");
     verbosity = Silent;
-    if (!symmstr.empty()) symmetries_file = symmstr;
+    if (!symmstr.empty()) {
+        symmetries_file = symmstr;
+        symmetries = SymmetryList(symmstr);
+    }
     if (laurette) {
         dT = T; dt = T; dtmax = T;
         variabledt = false;

@@ -167,6 +167,13 @@ void NSE::solve_lincomb(std::vector<FlowField>& outfields, const std::vector<Rea
 
 std::vector<FlowField> NSE::createRHS(const std::vector<FlowField>& fields) const { return {fields[0]}; }
 
+// velocity: the flags' symmetries; pressure: the identity (nse.cpp:578-587)
+std::vector<cfarray<FieldSymmetry>> NSE::createSymmVec() const {
+    cfarray<FieldSymmetry> usym = SymmetryList(1), psym = SymmetryList(1);
+    if (flags_.symmetries.length() > 0) usym = flags_.symmetries;
+    return {usym, psym};
+}
+
 Real NSE::dPdx() const {
     if (dPd_on_device_) {
         CK(cfgpu_nse_get_dPd(dev_, &dPdxAct_, &dPdzAct_));

@@ -66,6 +66,19 @@ FlowField& FlowField::operator*=(const FieldSymmetry& sigma) {
     return *this;
 }
 
+FlowField& FlowField::project(const FieldSymmetry& sigma) {  // flowfield.cpp:1095-1266: P u = (u + sigma u)/2
+    if (sigma.isIdentity()) return *this;
+    FlowField su(*this);
+    su *= sigma;
+    add(1.0, su);
+    *this *= 0.5;
+    return *this;
+}
+FlowField& FlowField::project(const cfarray<FieldSymmetry>& sigma) {
+    for (int n = 0; n < sigma.length(); ++n) project(sigma[n]);
+    return *this;
+}
+
 // ---- lists: "% N" header, one symmetry per line
 SymmetryList::SymmetryList(const string& filebase) {
     ifstream is;

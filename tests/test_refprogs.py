@@ -141,7 +141,7 @@ def test_tausolver_program_passes_on_emulation(tmp_path):
 ORACLE_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 
 
-def _simulateflow_pair(flavour, tmp_path, grid, T, timeout):
+def _simulateflow_pair(flavour, tmp_path, grid, T, timeout, symms=False):
     """BASELINE configs[0]: the reference's programs/simulateflow.cpp and tools/randomfield.cpp, compiled UNMODIFIED against
     the drop-in headers, next to the same two programs of the compiled reference (oracle/_ref/bin) on the same command line:
     plane Couette Re 400, SBDF3, rotational, 2/3 dealiasing, dt = 0.02.  Returns (relative L2 difference of the saved final
@@ -153,11 +153,15 @@ def _simulateflow_pair(flavour, tmp_path, grid, T, timeout):
             pytest.skip("simulateflow/randomfield binaries not built (need /root/reference at build time)")
     Nx, Ny, Nz = grid
     rf = ["-Nx", str(Nx), "-Ny", str(Ny), "-Nz", str(Nz), "-lx", "1", "-lz", "0.5", "-sd", "1", "-s", "0.4", "-m", "0.2", "u0"]
-    sim = ["-R", "400", "-T", str(T), "-dt", "0.02", "-vdt", "false", "-dT", "1", "-l2", "-cfl", "-dv", "u0"]
+    sim = ["-R", "400", "-T", str(T), "-dt", "0.02", "-vdt", "false", "-dT", "1", "-l2", "-cfl", "-dv"]
+    if symms:  # confine the flow to the shift-reflect subspace, projecting every time unit (dns.cpp:152-156)
+        sim += ["-symms", "sigma.asc", "-symmpi", "1"]
+    sim += ["u0"]
     logs = {}
     for side, bindir in (("ref", ORACLE_BIN), ("new", os.path.join(PROGS, flavour))):
         d = tmp_path / side
         d.mkdir()
+        open(str(d / "sigma.asc"), "w").write("% 1\n1 1 1 -1 0.5 0\n")
         r = subprocess.run([os.path.join(bindir, "randomfield")] + rf, cwd=str(d), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
         assert r.returncode == 0, r.stdout[-2000:]
         r = subprocess.run([os.path.join(bindir, "simulateflow")] + sim, cwd=str(d), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
@@ -181,6 +185,14 @@ def _diag_lines(log, key):
 
 
 @pytest.mark.gpu
+def test_simulateflow_with_symmetry_projection(tmp_path):
+    _build("gpu")
+    d, logs = _simulateflow_pair("gpu", tmp_path, (32, 33, 32), 2, 900, symms=True)
+    assert d["data/u2"] < 1e-9, d
+    assert _diag_lines(logs["new"], "L2Norm(u)") == _diag_lines(logs["ref"], "L2Norm(u)")
+
+
+@pytest.mark.gpu
 def test_simulateflow_runs_unchanged_c1(tmp_path):
     """north_star: `simulateflow` runs unchanged on top of the B200 path; C1 = 32x33x32, 100 steps: the saved field agrees with
     the reference run to <= 1e-9 (parity gate after 100 steps), the initial field from `randomfield` to round-off."""
@@ -196,7 +208,7 @@ def test_simulateflow_runs_unchanged_emulation(tmp_path):
     from tests import parity
     parity.emu_lib()
     _build("emu")
-    d, logs = _simulateflow_pair("emu", tmp_path, (16, 17, 16), 1, 900)
+    d, logs = _simulateflow_pair("emu", tmp_path, (16, 17, 16), 1, 900, symms=True)
     assert d["u0"] < 1e-14 and d["data/u1"] < 1e-11, d
     assert _diag_lines(logs["new"], "L2Norm(u)") == _diag_lines(logs["ref"], "L2Norm(u)")
 
