@@ -41,9 +41,11 @@ static int pick_TZ(int Nx) {
 // ... the forward x-pass keeps the two-buffer Stockham transform (its in-place variant measured slower: 0.92 against
 // 0.67 ms) and therefore half the columns (measured at Nx = 512: 2 -> 1.93 ms, 4 -> 1.77 ms, 6 -> 1.87 ms, 8 -> 2.70 ms)
 static int pick_TZ_forward(int Nx) {
+    static const int forced = getenv("CF_XPF_TZ") ? atoi(getenv("CF_XPF_TZ")) : 0;
+    if (forced > 0) return forced;
     int tz = 2304 / Nx;
     int p = 16;
-    while (p > tz && p > 2) p >>= 1;
+    while (p > tz && p > 1) p >>= 1;  // one column per CTA for Nx > 2304 (weak scaling of the C4 grid: Nx = 4096 at 8 GPUs)
     return p;
 }
 static int pick_TL(int Nx, int Nz, int npair) {
