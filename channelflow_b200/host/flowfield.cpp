@@ -381,9 +381,17 @@ void FlowField::binarySave(const std::string& filebase) const {
     }
 }
 
+bool read_netcdf_field(const std::string& filename, FlowField& u, CfMPI* cfmpi);  // ncfile.cpp
+
+// filebase, filebase.ff (the reference's binary format) or filebase.nc (NetCDF-4 as written by stock Channelflow); with no
+// suffix given .nc is tried first, as in flowfield.cpp:130-190
 FlowField::FlowField(const std::string& filebase, CfMPI* cfmpi) {
+    const bool want_nc = hasSuffix(filebase, ".nc"), want_ff = hasSuffix(filebase, ".ff");
+    if (hasSuffix(filebase, ".h5")) cferror("FlowField(filebase) : HDF5 field files are not supported, convert with fieldconvert: " + filebase);
+    if (!want_ff && read_netcdf_field(want_nc ? filebase : filebase + ".nc", *this, cfmpi)) return;
+    if (want_nc) cferror("FlowField(filebase) : can't open " + filebase);
     std::ifstream is(with_ff(filebase).c_str(), std::ios::in | std::ios::binary);
-    if (!is.good()) cferror("FlowField(filebase) : can't open " + with_ff(filebase));
+    if (!is.good()) cferror("FlowField(filebase) : can't open " + with_ff(filebase) + " or " + filebase + ".nc");
     rd_int(is); rd_int(is); rd_int(is);
     const int Nx = rd_int(is), Ny = rd_int(is), Nz = rd_int(is), Nd = rd_int(is);
     const fieldstate xz = rd_char(is) == 'S' ? Spectral : Physical;

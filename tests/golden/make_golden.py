@@ -5,6 +5,7 @@
                     440 steps, tolerance 1e-13): physical-space velocity on the I/O grid + grid attributes.
   eq.npz          : tests/data/eq.nc (24x33x24 equilibrium used by findsolnTest.cpp)
   os_eig.npz      : Orr-Sommerfeld eigen data tests/data/os_{ueig,peig}10_65.asc, os_omega10_65.cmplx
+  eq.nc           : tests/data/eq.nc unchanged (a NetCDF-4 file as stock Channelflow writes it)
   couette_ref.txt : what the reference's examples/couette.cpp prints (compiled reference, oracle/_ref/bin/couette)
 """
 import os
@@ -35,6 +36,9 @@ def main():
     peig = read_cplx_asc(os.path.join(REF, "os_peig10_65.asc"))
     om = open(os.path.join(REF, "os_omega10_65.cmplx")).read().replace("(", " ").replace(")", " ").replace(",", " ").split()
     np.savez_compressed(os.path.join(OUT, "os_eig.npz"), ueig=ueig, peig=peig, omega=np.array([float(om[0]), float(om[1])]))
+    # the file itself, byte for byte, as input of the C++ NetCDF-4 reader test (host/ncfile.cpp)
+    import shutil
+    shutil.copyfile(os.path.join(REF, "eq.nc"), os.path.join(OUT, "eq.nc"))
     # stdout of the reference's examples/couette.cpp (oracle/_ref/bin/couette, `make -C oracle reftests`): t, CFL, L2Norm(u), ...
     # every time unit of a 30-unit run, 6 significant digits
     import subprocess, tempfile

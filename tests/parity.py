@@ -417,3 +417,13 @@ def variable_dt_loop(lib, cfg, nintervals=4, dT=0.25, dt0=0.02, CFLmin=0.4, CFLm
     out["q_rel"] = rel_l2(q2.get(), q1.data)
     out["dPdx"] = abs(gd.dPdx() - rd.dPdx())
     return out
+
+
+def netcdf_reader(lib):
+    """FlowField("file.nc") through the library-free NetCDF-4 reader (host/ncfile.cpp) on a file written by stock Channelflow
+    (tests/golden/eq.nc = reference tests/data/eq.nc: de-aliased I/O grid 16x33x16 of a 24x33x24 field) against the
+    reference's own embedding of the same values (addPaddedModes, flowfield.cpp:2991-3190)."""
+    h = lib.L.cf_field_load(os.path.join(GOLDEN, "eq.nc").encode())
+    _, ur = load_eq(lib)
+    v = cf.FlowField(lib, ur.Nx, ur.Ny, ur.Nz, 3, ur.Lx, ur.Lz, ur.a, ur.b, handle=h)
+    return {"rel": rel_l2(v.get(), ur.data), "padded": v.padded()}

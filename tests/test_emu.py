@@ -295,3 +295,8 @@ def test_variable_dt_loop(lib):
                                 Ubulk=2.0 / 3, ulowerwall=0.0, uupperwall=0.0, nu=1 / 1800.0)
     assert r["changes"] >= 1, r
     assert max(r["cfl_rel"]) < 1e-11 and r["u_rel"] < 1e-11 and r["dPdx"] < 1e-11, r
+
+
+def test_netcdf4_field_reader(lib):
+    r = parity.netcdf_reader(lib)
+    assert r["padded"] and r["rel"] < 1e-14, r

@@ -296,3 +296,8 @@ def test_c2_variable_dt_loop(lib):
     print("variable dt:", r)
     assert r["changes"] >= 1 and r["steps"] >= 20, r
     assert max(r["cfl_rel"]) < 1e-10 and r["u_rel"] < 1e-10 and r["dPdx"] < 1e-10, r
+
+
+def test_netcdf4_field_reader(lib):
+    r = parity.netcdf_reader(lib)
+    assert r["padded"] and r["rel"] < 1e-14, r
