@@ -258,3 +258,51 @@ def test_reference_benchmark_tool(tmp_path):
         res[side] = (float(avg[-1].split(":")[1].strip().rstrip("s")), dist[-1].strip() if dist else "")
     print("reference benchmark tool (s per time unit of 40 steps, 48x35x48):", res)
     assert res["b200"][0] < res["reference_1core"][0]
+
+
+# ---------------------------------------------------------------------------------------------- the reference's tools
+TOOL_CHAIN = [("randomfield", "-Nx {Nx} -Ny {Ny} -Nz {Nz} -lx 1 -lz 0.5 -sd 1 u0"), ("perturbfield", "-sd 3 -m 0.05 u0 u1"),
+              ("symmetryop", "-sx -ax 0.25 u1 u2"), ("addfields", "-lc 0.3 u1 0.7 u2 u3"), ("pressure", "-nl rot u3 p3"),
+              ("fieldconvert", "u3 u3copy.ff")]
+
+
+def _tool_chain(flavour, tmp_path, grid):
+    """tools/{randomfield,perturbfield,symmetryop,addfields,pressure,fieldconvert}.cpp, unmodified, chained on the drop-in build
+    and on the compiled reference with the same command lines; every output file compared."""
+    import channelflow_b200 as cf
+    from tests import parity
+    Nx, Ny, Nz = grid
+    for side, bindir in (("ref", ORACLE_BIN), ("new", os.path.join(PROGS, flavour))):
+        d = tmp_path / side
+        d.mkdir()
+        for exe, args in TOOL_CHAIN:
+            path = os.path.join(bindir, exe)
+            if not os.path.exists(path):
+                pytest.skip("%s not built (needs /root/reference at build time)" % path)
+            r = subprocess.run([path] + args.format(Nx=Nx, Ny=Ny, Nz=Nz).split(), cwd=str(d), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                               text=True, timeout=600)
+            assert r.returncode == 0, (exe, r.stdout[-2000:])
+    lib = parity.gpu_lib() if flavour == "gpu" else parity.emu_lib()
+    out = {}
+    for name, Nd in (("u1", 3), ("u2", 3), ("u3", 3), ("p3", 1), ("u3copy", 3)):
+        arrs = []
+        for side in ("ref", "new"):
+            h = lib.L.cf_field_load(str(tmp_path / side / name).encode())
+            arrs.append(cf.FlowField(lib, Nx, Ny, Nz, Nd, 2 * np.pi, np.pi, handle=h).get())
+        out[name] = float(np.linalg.norm((arrs[0] - arrs[1]).ravel()) / np.linalg.norm(arrs[0].ravel()))
+    return out
+
+
+@pytest.mark.gpu
+def test_reference_tools_chain_on_gpu(tmp_path):
+    _build("gpu")
+    r = _tool_chain("gpu", tmp_path, (32, 33, 32))
+    assert max(r.values()) < 1e-13, r
+
+
+def test_reference_tools_chain_on_emulation(tmp_path):
+    from tests import parity
+    parity.emu_lib()
+    _build("emu")
+    r = _tool_chain("emu", tmp_path, (16, 17, 16))
+    assert max(r.values()) < 1e-13, r
