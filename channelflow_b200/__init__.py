@@ -386,6 +386,7 @@ class HostLib:
         L.cf_field_set_padded.argtypes = [vp, i]
         L.cf_field_copy.argtypes = [vp, vp]
         L.cf_field_symmetry.argtypes = [vp, i, i, i, i, d, d]
+        L.cf_randomfield.argtypes = [vp, i, d, d, i]
         L.cf_hookstep_search.argtypes = [vp, C.POINTER(Flags), d, d, dpt, dpt, dpt, i]
         L.cf_cmplx_get.argtypes = [vp, i, i, i, i, i]
         L.cf_cmplx_set.argtypes = [vp, i, i, i, i, d, d]
@@ -558,6 +559,13 @@ class FlowField:
     def save(self, filebase): self.lib.L.cf_field_save(self.h, filebase.encode())
     def axpby(self, a, x, b=0.0, z=None): self.lib.L.cf_field_axpby(self.h, a, x.h, b, z.h if z is not None else None)
     def scale(self, s): self.lib.L.cf_field_scale(self.h, s)
+
+
+def randomfield(lib, Nx, Ny, Nz, Lx, Lz, a=-1.0, b=1.0, seed=1, magn=0.2, smooth=0.4, meanflow=False):
+    """The reference's `randomfield` rule (tools/randomfield.cpp:49-64) generated by this package's own FlowField."""
+    u = FlowField(lib, Nx, Ny, Nz, 3, Lx, Lz, a, b)
+    lib.L.cf_randomfield(u.h, int(seed), float(magn), float(smooth), 1 if meanflow else 0)
+    return u
 
 
 def hookstep_search(u, flags, T, dt, sigma=(1, 1, 1, 1, 0.0, 0.0), epsSearch=1e-13, epsGMRES=1e-3, epsDx=1e-7, delta=0.01, Nnewton=20,

@@ -40,10 +40,15 @@ static int pick_TZ(int Nx) {
 }
 // ... the forward x-pass keeps the two-buffer Stockham transform (its in-place variant measured slower: 0.92 against
 // 0.67 ms) and therefore half the columns (measured at Nx = 512: 2 -> 1.93 ms, 4 -> 1.77 ms, 6 -> 1.87 ms, 8 -> 2.70 ms)
+// long lines: the in-place kernel (one buffer) takes twice the columns of the Stockham one
+static bool forward_inplace(int Nx) {
+    static const int forced = getenv("CF_XPF_INPLACE") ? atoi(getenv("CF_XPF_INPLACE")) : -1;
+    return forced >= 0 ? forced != 0 : Nx >= 1024;
+}
 static int pick_TZ_forward(int Nx) {
     static const int forced = getenv("CF_XPF_TZ") ? atoi(getenv("CF_XPF_TZ")) : 0;
     if (forced > 0) return forced;
-    int tz = 2304 / Nx;
+    int tz = (forward_inplace(Nx) ? 4608 : 2304) / Nx;
     int p = 16;
     while (p > tz && p > 1) p >>= 1;  // one column per CTA for Nx > 2304 (weak scaling of the C4 grid: Nx = 4096 at 8 GPUs)
     return p;
@@ -681,6 +686,7 @@ static int nonlinear_fused_general(cfgpu_nse nse, cfgpu_field u, cfgpu_field f, 
             xp.opb[i] = 1;
         }
         xp.TZ = pick_TZ_forward(nse->Nx);
+        xp.inplace = forward_inplace(nse->Nx) ? 1 : 0;
         if (prod) xp.TZ = xp.TZ > 1 ? xp.TZ / 2 : 1;
         StageTimer _t(ctx, 3);
         CF_TRY(xpass_forward_launch(xp, ctx->stream));
@@ -808,6 +814,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     memset(&xp, 0, sizeof xp);
     xp.Nx = nse->Nx; xp.Ny = nse->Ny; xp.Kx = nse->Kx; xp.Kz = nse->Kz;
     xp.TZ = pick_TZ_forward(nse->Nx);
+    xp.inplace = forward_inplace(nse->Nx) ? 1 : 0;
     xp.Lx = nse->Lx;
     xp.plan = *fx;
     xp.nfields = 3;

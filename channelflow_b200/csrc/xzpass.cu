@@ -132,6 +132,59 @@ __global__ void __launch_bounds__(XZ_THREADS) xpass_forward_kernel(const XPassPa
     }
 }
 
+// In-place variant for long x-lines (Nx >= 1024): one shared-memory buffer instead of the Stockham pair, hence twice the kz
+// columns per CTA for the same footprint -- the global-memory pieces, not the transform, limit the pass there (weak scaling
+// along x: 2 -> 4 columns at Nx = 1024, 1 -> 2 at 2048).  Rows are written to their digit-reversed places while loading and
+// the decimation-in-time passes run in place, as in the inverse pass.  At Nx = 512 the Stockham kernel is faster (0.67 vs 0.92 ms).
+__global__ void __launch_bounds__(XZ_THREADS) xpass_forward_inplace_kernel(const XPassParams p) {
+    const int Nx = p.Nx, Kx = p.Kx, TZ = p.TZ;
+    const int nmx = 2 * Kx + 1, nkz = p.Kz + 1;
+    const int tid = threadIdx.x;
+    const int f = p.fsel[blockIdx.z], yl = blockIdx.y, kz0 = blockIdx.x * TZ;
+    const int sa = p.src[f], sb = p.srcb[f];
+    const int C = sb >= 0 ? 2 * TZ : TZ;  // columns: TZ of the first source, then TZ of the second
+    const int ntw = fft_plan_ntw(p.plan);
+    double2* a = dyn_smem<double2>();                    // [Nx][C], transformed in place
+    double2* tws = a + (size_t)Nx * C;
+    int* rev = reinterpret_cast<int*>(tws + ntw);
+    for (int t = tid; t < Nx; t += XZ_THREADS) {
+        if (t < ntw) tws[t] = __ldg(&p.plan.tw[t]);
+        rev[t] = __ldg(&p.plan.rev[t]);
+    }
+    __syncthreads();
+    const double2* __restrict__ ina = p.in + ((size_t)sa * p.nyn + yl) * Nx * nkz;
+    const double2* __restrict__ inb = p.in + ((size_t)(sb >= 0 ? sb : 0) * p.nyn + yl) * Nx * nkz;
+    for (int idx = tid; idx < Nx * C; idx += XZ_THREADS) {
+        const int nx = idx / C, c = idx - nx * C;
+        const int kz = kz0 + (c < TZ ? c : c - TZ);
+        a[rev[nx] * C + c] = kz < nkz ? (c < TZ ? ina : inb)[(size_t)nx * nkz + kz] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    fft_smem_inplace<-1, false, true>(a, p.plan, tws, C, tid, XZ_THREADS);
+    const double2* res = a;
+    for (int idx = tid; idx < nmx * TZ; idx += XZ_THREADS) {
+        const int mxi = idx / TZ, c = idx - mxi * TZ;
+        const int kz = kz0 + c;
+        const int kx = mxi <= Kx ? mxi : mxi - nmx;
+        const int mx = kx >= 0 ? kx : Nx + kx;
+        if (kz >= nkz) continue;
+        double2 v = res[mx * C + c];
+        if (sb >= 0) {
+            const double2 w = res[mx * C + TZ + c];
+            const double k = p.cb * (p.opb[f] == 1 ? TWO_PI * kx / p.Lx : TWO_PI * kz / p.Lz);
+            v = make_double2(v.x - k * w.y, v.y + k * w.x);
+        }
+        int s = -1;
+        size_t o = 0;
+        if (p.peer_direct) o = xpass_peer_offset(p, f, p.ny0 + yl, mxi, nkz, s);
+        if (p.peer_direct == 1 || (p.peer_direct == 2 && s == p.self_rank)) {
+            p.peer_out[s][o + kz] = v;
+        } else {
+            p.out[xpass_row_offset(p, f, yl, mxi, nkz) + kz] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ z pass
 // grid = (ceil(Nx/TL), nyn).  Two real fields share one complex transform (Z = A + iB with the Hermitian
 // extension written explicitly), so the rotational term (u, v, w, curl u) needs 3 inverse + 2 forward complex FFTs per line.
@@ -588,11 +641,20 @@ int xpass_forward_launch(const XPassParams& p, cudaStream_t stream) {
     const int nkz = p.Kz + 1;
     bool two = false;
     for (int i = 0; i < p.nfields; ++i) two = two || p.srcb[p.fsel[i]] >= 0;
+    dim3 grid((nkz + p.TZ - 1) / p.TZ, p.nyn, p.nfields);
+    if (p.inplace) {
+        const size_t smem = (size_t)p.Nx * p.TZ * (two ? 2 : 1) * sizeof(double2) + (size_t)fft_plan_ntw(p.plan) * sizeof(double2) + (size_t)p.Nx * sizeof(int);
+        static size_t configured_ip = 0;
+        auto kfn = xpass_forward_inplace_kernel;
+        CF_TRY(set_smem((const void*)kfn, smem, configured_ip));
+        CF_LAUNCH(kfn, grid, dim3(XZ_THREADS), smem, stream, p);
+        CF_KERNEL_CHECK();
+        return 0;
+    }
     const size_t smem = 2 * (size_t)p.Nx * p.TZ * (two ? 2 : 1) * sizeof(double2);
     static size_t configured = 0;
     auto kfn = xpass_forward_kernel;
     CF_TRY(set_smem((const void*)kfn, smem, configured));
-    dim3 grid((nkz + p.TZ - 1) / p.TZ, p.nyn, p.nfields);
     CF_LAUNCH(kfn, grid, dim3(XZ_THREADS), smem, stream, p);
     CF_KERNEL_CHECK();
     return 0;

@@ -19,6 +19,7 @@ namespace cfgpu {
 struct XPassParams {
     int Nx, Ny, Kx, Kz;   // Kx,Kz: retained |kx|<=Kx, kz<=Kz ; nmx = 2Kx+1, nkz = Kz+1
     int TZ;               // kz columns per CTA
+    int inplace;          // forward pass only: one-buffer in-place transform (long x-lines), see xpass_forward_inplace_kernel
     double Lx;
     FftPlanDev plan;      // length Nx
     int nfields;          // fields this launch handles: output slots fsel[0..nfields)

@@ -216,6 +216,17 @@ void cf_hookstep_search(void* uh, const CfFlags* rf, double T, double dt, double
     const double head[6] = {r.converged ? 1.0 : 0.0, (double)r.newtonSteps, (double)r.fevals, (double)r.gmresIterations, r.residual, dsi.steps_per_eval()};
     for (int i = 0; i < nout; ++i) out[i] = i < 6 ? head[i] : (i - 6 < (int)r.history.size() ? r.history[i - 6] : -1.0);
 }
+// tools/randomfield.cpp:49-64: the reference's random initial condition (serial drand48 stream, seed, Gaussian coefficients with
+// spectral decay 1 - smooth over the whole retained box, divergence-free, no-slip, rescaled to L2Norm magn)
+void cf_randomfield(void* h, int seed, double magn, double smooth, int meanflow) {
+    FlowField& u = *(FlowField*)h;
+    srand48(seed);
+    u.setToZero();
+    u.setState(Spectral, Spectral);
+    u.addPerturbations(u.kxmaxDealiased(), u.kzmaxDealiased(), 1.0, 1.0 - smooth, meanflow != 0);
+    u *= magn / L2Norm(u);
+    u.setPadded(true);
+}
 void cf_laminar_profile(const CfFlags* rf, double a, double b, int Ny, double* U) {
     DNSFlags flags = to_flags(rf);
     ChebyCoeff u = laminarProfile(flags, a, b, Ny);

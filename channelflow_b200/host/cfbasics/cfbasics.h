@@ -225,4 +225,42 @@ inline std::ostream& operator<<(std::ostream& os, ResidualImprovement i) {
 inline std::ostream& operator<<(std::ostream& os, SolutionType s) { return os << (s == Equilibrium ? "Equilibrium" : "PeriodicOrbit"); }
 
 }  // namespace chflow
+
+// ---- vector helpers of the reference header for Eigen::VectorXd (cfbasics.h:97-115, 711-780), available when an
+// <Eigen/Dense> is on the include path (the real one, or channelflow_b200/host/compat)
+#if defined(__has_include)
+#if __has_include(<Eigen/Dense>)
+#include <Eigen/Dense>
+namespace chflow {
+inline void setToZero(Eigen::VectorXd& x) { x.setZero(); }
+inline Real L2Norm2(const Eigen::VectorXd& x, int cutoff = 0) {
+    Real s = 0;
+    for (long i = 0; i < (long)x.size() - cutoff; ++i) s += x(i) * x(i);
+    return s;
+}
+inline Real L2Norm(const Eigen::VectorXd& x, int cutoff = 0) { return std::sqrt(L2Norm2(x, cutoff)); }
+inline Real L2Dist2(const Eigen::VectorXd& x, const Eigen::VectorXd& y, int cutoff = 0) {
+    Real s = 0;
+    for (long i = 0; i < (long)x.size() - cutoff; ++i) s += (x(i) - y(i)) * (x(i) - y(i));
+    return s;
+}
+inline Real L2Dist(const Eigen::VectorXd& x, const Eigen::VectorXd& y, int cutoff = 0) { return std::sqrt(L2Dist2(x, y, cutoff)); }
+inline Real L2IP(const Eigen::VectorXd& x, const Eigen::VectorXd& y) { Real s = 0; for (long i = 0; i < (long)x.size(); ++i) s += x(i) * y(i); return s; }
+inline void print(const Eigen::VectorXd& x) { for (long i = 0; i < (long)x.size(); ++i) std::cout << x(i) << '\n'; }
+inline void save(const Eigen::VectorXd& x, const std::string& filebase) {
+    std::ofstream os(appendSuffix(filebase, ".asc").c_str());
+    os << std::setprecision(17) << x.size() << '\n';
+    for (long i = 0; i < (long)x.size(); ++i) os << x(i) << '\n';
+}
+inline void load(Eigen::VectorXd& x, const std::string& filebase) {
+    std::ifstream is(appendSuffix(filebase, ".asc").c_str());
+    long n = 0;
+    is >> n;
+    x.resize(n);
+    for (long i = 0; i < n; ++i) is >> x(i);
+}
+}  // namespace chflow
+#endif
+#endif
+
 #endif

@@ -89,6 +89,7 @@ class FlowField {
     void makeState(fieldstate xzstate, fieldstate ystate);
 
     void setToZero();
+    void interpolate(FlowField f);   // spectral interpolation of f onto this grid (same box), flowfield.cpp:691-792
 
     int numXmodes() const { return Nx_; }
     int numYmodes() const { return Ny_; }

@@ -176,6 +176,39 @@ void FlowField::perturb(Real mag, Real decay, bool meanflow) {
     addPerturbations(padded() ? kxmaxDealiased() : kxmax(), padded() ? kzmaxDealiased() : kzmax(), mag, decay, meanflow);
 }
 
+// Spectral interpolation onto this grid (flowfield.cpp:691-792): Fourier modes kxmin <= kx < kxmax, kz <= kzmax common to both
+// grids are carried over (the upper bound in kx is exclusive, as in the reference), Chebyshev coefficients are copied when
+// this grid has at least as many (zero-extended) and re-sampled through ChebyCoeff::interpolate otherwise; when this grid is
+// wider in x the source's kx = kxmax row also feeds the -kxmax row.  A grid-change utility (I/O class): runs on the host mirror.
+void FlowField::interpolate(FlowField f) {
+    FlowField& g = *this;
+    if (f.Lx() != g.Lx() || f.Lz() != g.Lz() || f.a() != g.a() || f.b() != g.b() || f.Nd() != g.Nd())
+        cferror("FlowField::interpolate(const FlowField& f) error:\nFlowField doesn't match argument f geometrically.\n");
+    const fieldstate gxz = g.xzstate(), gy = g.ystate();
+    const int fNy = f.Ny(), gNy = g.Ny();
+    f.makeSpectral();
+    g.setState(Spectral, Spectral);
+    g.setToZero();
+    const int kxhi = lesser(f.kxmax(), g.kxmax()), kzhi = lesser(f.kzmax(), g.kzmax()), kxlo = Greater(f.kxmin(), g.kxmin());
+    ComplexChebyCoeff fprof(fNy, a_, b_, Spectral), gprof(gNy, a_, b_, Spectral);
+    auto carry = [&](int i, int fmx, int fmz, int gmx, int gmz) {
+        if (fNy <= gNy) {
+            for (int ny = 0; ny < fNy; ++ny) g.cmplx(gmx, ny, gmz, i) = f.cmplx(fmx, ny, fmz, i);
+        } else {
+            for (int ny = 0; ny < fNy; ++ny) fprof.set(ny, f.cmplx(fmx, ny, fmz, i));
+            gprof.interpolate(fprof);
+            for (int ny = 0; ny < gNy; ++ny) g.cmplx(gmx, ny, gmz, i) = gprof[ny];
+        }
+    };
+    for (int i = 0; i < Nd_; ++i) {
+        for (int kx = kxlo; kx < kxhi; ++kx)
+            for (int kz = 0; kz <= kzhi; ++kz) carry(i, f.mx(kx), f.mz(kz), g.mx(kx), g.mz(kz));
+        if (g.Nx() > f.Nx())
+            for (int kz = f.kzmin(); kz <= f.kzmax(); ++kz) carry(i, f.mx(f.kxmax()), f.mz(kz), g.mx(-f.kxmax()), g.mz(kz));
+    }
+    g.makeState(gxz, gy);
+}
+
 // ------------------------------------------------------------------------------------------------ small utilities
 FlowField FlowField::operator[](int i) const {
     assert(i >= 0 && i < Nd_);

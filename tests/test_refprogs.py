@@ -52,7 +52,7 @@ def _run(flavour, prog, args, tmp_path, timeout):
 
 # the reference's ctest list; the DNS programs take (algorithm, mean constraint[, base/fluctuation]) switches
 UNIT = [("tridiagTest", ()), ("chebyTest", ()), ("laminarTest", ()), ("helmholtzTest", ()), ("tausolverTest", ()),
-        ("poissonTest", ()), ("pressureTest", ())]
+        ("poissonTest", ()), ("pressureTest", ()), ("ioTest", ())]
 ALGS = ["--cnfe1", "--cnab2", "--cnrk2", "--smrk2", "--sbdf2", "--sbdf3", "--sbdf4"]
 DNS_ZERO = [("dnsZeroTest", (a, c)) for a in ALGS for c in ("--bulkv", "--gradp")]
 DNS_PARA = [("dnsParabolaTest", (a, f, c)) for a in ALGS for f in ("--fluc", "--base") for c in ("--bulkv", "--gradp")]
@@ -114,7 +114,7 @@ def _compare_couette(out, upto=None):
 
 
 EMU_FAST = [("tridiagTest", ()), ("chebyTest", ()), ("laminarTest", ()), ("helmholtzTest", ()), ("poissonTest", ()),
-            ("dnsZeroTest", ("--sbdf3", "--gradp")), ("pressureTest", ())]
+            ("dnsZeroTest", ("--sbdf3", "--gradp")), ("pressureTest", ()), ("ioTest", ())]
 
 
 @pytest.mark.parametrize("prog", EMU_FAST, ids=_id)
@@ -306,3 +306,29 @@ def test_reference_tools_chain_on_emulation(tmp_path):
     _build("emu")
     r = _tool_chain("emu", tmp_path, (16, 17, 16))
     assert max(r.values()) < 1e-13, r
+
+
+# ------------------------------------------------------------------------------------------------ field2vector program
+def _vector2field_program(flavour, tmp_path, lib):
+    """tests/vector2fieldTest.cpp, unmodified (Eigen::VectorXd from the stand-in header host/compat/Eigen/Dense, Eigen3 is not
+    installed here): field -> vector -> field -> vector round trips of the golden-pair initial field, own tolerance 2e-16."""
+    _write_golden_ff(lib, str(tmp_path / "data"))
+    exe = os.path.join(PROGS, flavour, "vector2fieldTest")
+    if not os.path.exists(exe):
+        pytest.skip("vector2fieldTest not built")
+    r = subprocess.run([exe], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and "pass" in r.stderr, (r.stdout[-2000:], r.stderr[-800:])
+
+
+@pytest.mark.gpu
+def test_vector2field_program_on_gpu(tmp_path):
+    from tests import parity
+    _build("gpu")
+    _vector2field_program("gpu", tmp_path, parity.gpu_lib())
+
+
+def test_vector2field_program_on_emulation(tmp_path):
+    from tests import parity
+    lib = parity.emu_lib()
+    _build("emu")
+    _vector2field_program("emu", tmp_path, lib)
