@@ -301,3 +301,25 @@ def test_c2_variable_dt_loop(lib):
 def test_netcdf4_field_reader(lib):
     r = parity.netcdf_reader(lib)
     assert r["padded"] and r["rel"] < 1e-14, r
+
+
+def test_findsoln_program(lib, tmp_path):
+    """channelflow_b200/bin/findsoln_b200 (the reference's findsoln options, fixed-T subset): reads the reference's own NetCDF
+    file, re-converges the travelling wave with the x phase shift as an unknown, writes ubest / sigmabest."""
+    import os
+    import shutil
+    import subprocess
+    exe = os.path.join(parity.ROOT, "channelflow_b200", "bin", "findsoln_b200")
+    if not os.path.exists(exe):
+        pytest.skip("findsoln_b200 not built")
+    shutil.copyfile(os.path.join(parity.GOLDEN, "eq.nc"), str(tmp_path / "eq.nc"))
+    open(str(tmp_path / "sigma.asc"), "w").write("1 1 1 1 0.28168880386692519 0\n")
+    r = subprocess.run([exe, "-eqb", "-xrel", "-T", "10", "-dt", "0.03125", "-vdt", "false", "-R", "400", "-sigma", "sigma.asc", "-Nn", "5",
+                        "-es", "1e-12", "eq"], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+    last = [l for l in r.stdout.splitlines() if "L2Norm(G) ==" in l][-1]
+    print(last)
+    assert "converged" in last, r.stdout[-1500:]
+    assert os.path.exists(str(tmp_path / "ubest.ff")) and os.path.exists(str(tmp_path / "sigmabest.asc"))
+    hist = [float(x) for x in open(str(tmp_path / "convergence.asc")).read().split("\n")[1:] if x.strip()]
+    assert hist[-1] < 1e-12 and hist[-1] < 1e-4 * hist[0], hist
