@@ -100,7 +100,8 @@ extern "C" int cfgpu_xz_generic(cfgpu_field f, int to_physical) {
     CF_TRY(get_fftplan(ctx, f->Nz, &fz));
     const int Mz = f->Mz();
     int TZ = 2304 / f->Nx;
-    { int p = 16; while (p > TZ && p > 2) p >>= 1; TZ = p; }
+    { int p = 16; while (p > TZ && p > 1) p >>= 1; TZ = p; }  // a single column per CTA for Nx > 2304
+    if (getenv("CF_XGEN_TZ")) TZ = atoi(getenv("CF_XGEN_TZ"));
     int TP = 8;
     while (TP > 1 && (size_t)2 * f->Nz * TP * 16 > 96 * 1024) TP >>= 1;
     const size_t smx = 2 * (size_t)f->Nx * TZ * sizeof(double2);
