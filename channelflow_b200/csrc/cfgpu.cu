@@ -964,7 +964,11 @@ static int l2form(cfgpu_field u, cfgpu_field v, int mode, int normalize, bool pa
     cfgpu_ctx ctx = u->ctx;
     const YPlan* pl;
     CF_TRY(get_yplan(ctx, u->Ny, u->a, u->b, &pl));
-    CF_TRY(ws_reserve(ctx->ws_red, 1 << 20));
+    {   // one partial sum per (tile of <= 16 modes, component)
+        const size_t modes = (size_t)u->Nx * u->Mz() * u->Nd;
+        const size_t need = (modes + 64) * sizeof(double);  // bound for one mode per tile
+        CF_TRY(ws_reserve(ctx->ws_red, need > ((size_t)1 << 20) ? need : ((size_t)1 << 20)));
+    }
     double scale = 1.0;
     if (!normalize) scale = (u->b - u->a) * u->Lx * u->Lz;
     const int Kx = u->Nx / 3 - 1, Kz = u->Nz / 3 - 1;
