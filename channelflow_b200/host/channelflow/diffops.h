@@ -105,5 +105,13 @@ std::string fieldstatsheader_t(const std::string tname = "t");
 std::string fieldstats(const FlowField& u);
 std::string fieldstatsheader();
 
+// The nonlinear term of a (total) velocity field in its different forms (diffops.cpp:2852-3365): one device pipeline each
+// (cfgpu_nse_nonlinear with a zero base flow); tmp is scratch of the reference's host algorithm and is not used.
+void rotationalNL(const FlowField& u, FlowField& f, FlowField& tmp, const fieldstate finalstate = Spectral);
+void convectionNL(const FlowField& u, FlowField& f, FlowField& tmp, const fieldstate finalstate = Spectral);
+void divergenceNL(const FlowField& u, FlowField& f, FlowField& tmp, const fieldstate finalstate = Spectral);
+void skewsymmetricNL(const FlowField& u, FlowField& f, FlowField& tmp, const fieldstate finalstate = Spectral);
+void linearizedNL(const FlowField& u, const ChebyCoeff& U, const ChebyCoeff& W, FlowField& f, const fieldstate finalstate = Spectral);
+
 }  // namespace chflow
 #endif

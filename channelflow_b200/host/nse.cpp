@@ -250,6 +250,27 @@ void navierstokesNL(const FlowField& u, ChebyCoeff Ubase, ChebyCoeff Wbase, Flow
     else if (flags.nonlinearity == Alternating_) flags.nonlinearity = Alternating;
 }
 
+// ---- the forms of the nonlinear term as free functions (diffops.h:226-231)
+static void nl_form(NonlinearMethod m, const FlowField& u, const ChebyCoeff& U, const ChebyCoeff& W, FlowField& f, fieldstate finalstate) {
+    DNSFlags flags;
+    flags.nonlinearity = m;
+    flags.Vsuck = 0.0;
+    FlowField tmp;
+    navierstokesNL(u, U, W, f, tmp, flags);
+    if (finalstate == Physical) f.makePhysical();
+}
+static ChebyCoeff zero_profile(const FlowField& u) { return ChebyCoeff(u.Ny(), u.a(), u.b(), Spectral); }
+void rotationalNL(const FlowField& u, FlowField& f, FlowField&, const fieldstate fs) { nl_form(Rotational, u, zero_profile(u), zero_profile(u), f, fs); }
+void convectionNL(const FlowField& u, FlowField& f, FlowField&, const fieldstate fs) { nl_form(Convection, u, zero_profile(u), zero_profile(u), f, fs); }
+void divergenceNL(const FlowField& u, FlowField& f, FlowField&, const fieldstate fs) { nl_form(Divergence, u, zero_profile(u), zero_profile(u), f, fs); }
+void skewsymmetricNL(const FlowField& u, FlowField& f, FlowField&, const fieldstate fs) { nl_form(SkewSymmetric, u, zero_profile(u), zero_profile(u), f, fs); }
+void linearizedNL(const FlowField& u, const ChebyCoeff& U, const ChebyCoeff& W, FlowField& f, const fieldstate fs) {
+    ChebyCoeff Us(U), Ws(W);
+    Us.makeSpectral();
+    Ws.makeSpectral();
+    nl_form(LinearAboutProfile, u, Us, Ws, f, fs);
+}
+
 // ---------------------------------------------------------------------------------------------- free functions
 Real viscosity(Real Reynolds, VelocityScale vscale, MeanConstraint constraint, Real dPdx, Real Ubulk, Real Uwall, Real h) {
     if (vscale == WallScale) return fabs(Uwall) * h / Reynolds;
