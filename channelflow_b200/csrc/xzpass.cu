@@ -679,6 +679,7 @@ static int zpass_warp_launch(const ZPassParams& p0, cudaStream_t stream) {
     dim3 grid((p.Nx + TL - 1) / TL, p.nyn);
     int nt = 32 * npair * TL;
     if (nt < 128) nt = 128;
+    if (getenv("CF_ZP_THREADS")) nt = atoi(getenv("CF_ZP_THREADS"));  // experiment knob (<= the kernel's launch bound)
     CF_LAUNCH(kfn, grid, dim3(nt), smem, stream, p);
     CF_KERNEL_CHECK();
     return 0;
