@@ -19,7 +19,7 @@ namespace cfgpu {
 namespace {
 
 constexpr int TAU_THREADS = 256;
-constexpr int TAU_SETUP_THREADS = 128;
+constexpr int TAU_SETUP_THREADS = 64;   // two independent warps per CTA (24 KB of staging each CTA)
 constexpr double PI = 3.14159265358979323846264338327950288;
 
 __host__ __device__ __forceinline__ double cN(int m, int Nb) { return (m == 0 || m == Nb) ? 2.0 : 1.0; }
@@ -296,8 +296,8 @@ void tau_btab_host(int N, double* tab) {
 //
 //  tau_factor_kernel   one THREAD per (mode slot, operator, parity) chain.  The UL factorisation is a continued-fraction
 //                      recurrence in n (no data besides n and lambda), so all 4 x modes chains run concurrently, each in the
-//                      reference's own operation order (bit-identical factors); the three values per step go straight to
-//                      the tile's [m][n] rows (the sectors are completed in L2 by the neighbouring steps / the other parity).
+//                      reference's own operation order (bit-identical factors); the three values per step are staged in
+//                      shared memory per warp and leave as 256-byte row segments of the tile's [m][n] rows.
 //  tau_profiles_kernel one WARP per mode slot: the six profile solves (P+-, v+-, P0, v0) run on the blocked-scan column
 //                      solver of the solve kernel (col_solve / col_deriv), the wall derivatives for the influence matrix
 //                      come from the closed form sum n^2 v_n accumulated by the last elimination sweep.
@@ -305,8 +305,9 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_factor_kernel(const Tau
     const int N = td.N, Nb = N - 1, TM = td.TM;
     const long chain = (long)blockIdx.x * TAU_SETUP_THREADS + threadIdx.x;
     // chain -> (slot, par, h): the four chains of a slot sit in consecutive threads
-    const long slot = chain >> 2;
-    if (slot >= (long)td.ntiles * TM) return;
+    const long slot_raw = chain >> 2;
+    const bool active = slot_raw < (long)td.ntiles * TM;    // (every thread takes part in the staged write-out below)
+    const long slot = active ? slot_raw : 0;
     const int par = (int)(chain & 1), h = (int)((chain >> 1) & 1);
     const int tl = (int)(slot / TM), m = (int)(slot - (long)tl * TM);
     int q0, mfirst, mend;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_factor_kernel(const Tau
     const double kappa2 = 4 * (PI * PI) * (kxL * kxL + kzL * kzL);
     const double c = 4.0 * (PI * PI) * td.nu;
     const double lamV = lambda_t + c * (kxL * kxL + kzL * kzL);
-    if (par == 0 && h == 0) {
+    if (active && par == 0 && h == 0) {
         td.tile_sc(tl, TSC_LAMP)[m] = kappa2;
         td.tile_sc(tl, TSC_LAMV)[m] = lamV;
         td.tile_sc(tl, TSC_KXX)[m] = 2 * PI * kx / g.Lx;
@@ -328,30 +329,67 @@ __global__ void __launch_bounds__(TAU_SETUP_THREADS) tau_factor_kernel(const Tau
     const double hl2 = ((td.b - td.a) / 2) * ((td.b - td.a) / 2);
     const double lam = h ? lamV : kappa2;
     const double nus = h ? td.nu / hl2 : 1.0 / hl2;
-    double* up = td.tile_arr(tl, h ? TAR_UPV : TAR_UPP) + (size_t)m * N;
-    double* inv = td.tile_arr(tl, h ? TAR_INVV : TAR_INVP) + (size_t)m * N;
-    double* band = td.tile_arr(tl, h ? TAR_BANDV : TAR_BANDP) + (size_t)m * N;
-    // UL factorisation of the parity block (bandedtridiag.cpp:212-229), from the last row upwards
+    // UL factorisation of the parity block (bandedtridiag.cpp:212-229), from the last row upwards.  A chain produces one
+    // inv / band / up value per step, 16 bytes apart in its own [m][n] row: written straight from the registers that is one
+    // 8-byte L2 transaction per value and lane.  Each warp stages 16 steps (= 32 consecutive n of a row, both parities) of its
+    // 32 chains in shared memory and writes them out as 256-byte row segments (no CTA-wide barrier).
+    __shared__ double st[3][TAU_SETUP_THREADS / 2][32];   // [inv, band, up(n-2)][(slot, h)][Nb - n - 32 block]
+    const int row = threadIdx.x >> 1;                       // (slot, h) pair of this chain: threads 4s+{0,1} -> h 0, 4s+{2,3} -> h 1
+    __shared__ double* rowbase[TAU_SETUP_THREADS / 2];     // up row of the (slot, h) pair; inv, band = + NM, + 2 NM
+    const size_t NM = (size_t)N * TM;
+    double* const up_row = td.tile_arr(tl, h ? TAR_UPV : TAR_UPP) + (size_t)m * N;
+    if (par == 0) rowbase[row] = active ? up_row : nullptr;
+    const double* __restrict__ blo = td.btab();             // B_lo(n): A_lo = -(lambda B_lo), as in the solve kernel
     const int nl = par ? Nb - 1 : Nb;
     double dgk = A_dg(nl, Nb, lam, nus);
     double bandk = 1.0;
-    for (int n = nl; n >= par + 4; n -= 2) {
-        const double Akk = dgk;
-        inv[n] = 1.0 / Akk;
-        const double w = A_lo(n, Nb, lam);
-        const double upm = A_up(n - 2, Nb, lam) / Akk;
-        up[n - 2] = upm;
-        const double dprev = A_dg(n - 2, Nb, lam, nus) - w * upm;
-        const double bk = bandk / Akk;
-        band[n] = bk;
-        bandk = 1.0 - w * bk;
-        dgk = dprev;
+    int n = nl;
+    const int nblocks = Nb / 32 + 1;
+    for (int blk = 0; blk < nblocks; ++blk) {
+        const int ntop = Nb - 32 * blk;                     // n of staging column 0
+        if (active) {
+            for (int k = 0; k < 16 && n >= par + 4; ++k, n -= 2) {
+                const double Akk = dgk;
+                const double w = A_lo_from_B(__ldg(blo + n), lam);
+                const double upm = A_up(n - 2, Nb, lam) / Akk;
+                const double dprev = A_dg(n - 2, Nb, lam, nus) - w * upm;
+                const double bk = bandk / Akk;
+                const int col = (ntop - n + 2 * row) & 31;   // rotated by the row: the 32 chains of a warp hit 32 columns
+                st[0][row][col] = 1.0 / Akk;
+                st[1][row][col] = bk;
+                st[2][row][col] = upm;
+                bandk = 1.0 - w * bk;
+                dgk = dprev;
+            }
+        }
+        __syncwarp();
+        // write-out: warp w owns rows 16w .. 16w+15 -- its own chains'; per row and array one 256-byte segment per instruction
+        {
+            const int lane = threadIdx.x & 31, r0 = (threadIdx.x >> 5) * 16;
+            const int nn = ntop - lane;                      // the step's n; its parity is the chain's
+            if (nn >= (nn & 1) + 4) {                        // produced by the main loop
+#pragma unroll 4
+                for (int rr = 0; rr < 16; ++rr) {
+                    const int r = r0 + rr, col = (lane + 2 * r) & 31;
+                    double* pb = rowbase[r];
+                    if (pb) {
+                        pb[NM + nn] = st[0][r][col];
+                        pb[2 * NM + nn] = st[1][r][col];
+                        pb[nn - 2] = st[2][r][col];
+                    }
+                }
+            }
+        }
+        __syncwarp();
     }
+    if (!active) return;
+    double* inv = up_row + NM;
+    double* band = up_row + 2 * NM;
     const int n1 = par + 2;
     inv[n1] = 1.0 / dgk;
     const double b1 = bandk / dgk;
     band[n1] = b1;
-    inv[par] = 1.0 - A_lo(n1, Nb, lam) * b1;  // diag(0) == band(0)
+    inv[par] = 1.0 - A_lo_from_B(__ldg(blo + n1), lam) * b1;  // diag(0) == band(0)
 }
 
 constexpr int TAU_PROF_THREADS = 128;  // 4 modes per CTA: small CTAs, three or four per SM (the scans are latency bound)
