@@ -388,6 +388,8 @@ class HostLib:
         L.cf_field_symmetry.argtypes = [vp, i, i, i, i, d, d]
         L.cf_randomfield.argtypes = [vp, i, d, d, i]
         L.cf_hookstep_search.argtypes = [vp, C.POINTER(Flags), d, d, dpt, dpt, dpt, i]
+        L.cf_dns_symmetry.argtypes = [vp, i, i, i, i, d, d]
+        L.cf_poincare_search.argtypes = [vp, vp, C.POINTER(Flags), i, vp, vp, i, i, i, d, d, dpt, vp, vp]
         L.cf_cmplx_get.argtypes = [vp, i, i, i, i, i]
         L.cf_cmplx_set.argtypes = [vp, i, i, i, i, d, d]
         L.cf_l2norm2.argtypes = [vp, i]
@@ -584,6 +586,21 @@ def hookstep_search(u, flags, T, dt, sigma=(1, 1, 1, 1, 0.0, 0.0), epsSearch=1e-
                 steps_per_eval=float(out[5]), history=hist, ax=float(sg[4]), az=float(sg[5]))
 
 
+def poincare_search(u, q, flags, nSteps, maxstrides, ustar=None, estar=None, crosssign=0, Tmin=0.0, epsilon=1e-13):
+    """DNSPoincare::advanceToSection in strides of nSteps until the section h(u) = 0 is crossed (host/poincare.cpp).
+    h = (u, estar) - (ustar, estar) when estar is given, wallshear - dissipation otherwise.  u, q are advanced in place.
+    Returns a dict (found, t, h, sign, strides, hcurrent, ucrossing, pcrossing)."""
+    import numpy as np
+    out = np.zeros(6)
+    uc, pc = u.like(), q.like()
+    kind = 1 if estar is not None else 0
+    u.lib.L.cf_poincare_search(u.h, q.h, C.byref(flags), kind, ustar.h if kind else None, estar.h if kind else None, int(nSteps),
+                               int(maxstrides), int(crosssign), float(Tmin), float(epsilon),
+                               out.ctypes.data_as(C.POINTER(C.c_double)), uc.h, pc.h)
+    return dict(found=bool(out[0]), t=float(out[1]), h=float(out[2]), sign=int(out[3]), strides=int(out[4]), hcurrent=float(out[5]),
+                ucrossing=uc, pcrossing=pc)
+
+
 class DNS:
     """chflow::DNS of this package (reference dns.cpp:22-163 semantics) owning copies of (u, q)."""
 
@@ -610,6 +627,7 @@ class DNS:
         return u, q
 
     def set(self, u=None, q=None): self.lib.L.cf_dns_set(self.h, u.h if u else None, q.h if q else None)
+    def symmetry(self, s, sx, sy, sz, ax, az): self.lib.L.cf_dns_symmetry(self.h, s, sx, sy, sz, ax, az)
     def cfl(self): return self.lib.L.cf_dns_cfl(self.h)
     def reset_dt(self, dt): self.lib.L.cf_dns_reset_dt(self.h, dt)
     def time(self): return self.lib.L.cf_dns_time(self.h)

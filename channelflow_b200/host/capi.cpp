@@ -147,6 +147,13 @@ void cf_dns_set(void* h, void* uh, void* qh) {
     if (uh) d->fields[0] = *(FlowField*)uh;
     if (qh) d->fields[1] = *(FlowField*)qh;
 }
+// u <- sigma u on the DNS' own velocity field and on the time-stepping history (DNS::operator*=, dns.cpp:175-180)
+void cf_dns_symmetry(void* h, int s, int sx, int sy, int sz, double ax, double az) {
+    CfDNS* d = (CfDNS*)h;
+    const FieldSymmetry sigma(sx, sy, sz, ax, az, s);
+    d->fields[0] *= sigma;
+    *d->dns *= std::vector<FieldSymmetry>{sigma, FieldSymmetry()};
+}
 double cf_dns_cfl(void* h) {
     CfDNS* d = (CfDNS*)h;
     return d->dns->CFL(d->fields[0]);
@@ -189,6 +196,34 @@ double cf_timer_stop() {
 
 void cf_profile_enable(int on) { cfgpu_profile_enable(cfgpu_context(), on); }
 void cf_profile_read(double* ms, long long* calls, int reset) { cfgpu_profile_read(cfgpu_context(), ms, calls, reset); }
+
+// Poincare section search (channelflow/dns.h: DNSPoincare): strides of nSteps steps from (u, q) until the section is crossed
+// (at most maxstrides).  kind 0: h = wallshear - dissipation (DragDissipation); kind 1: h = (u, estar) - (ustar, estar)
+// (PlaneIntersection).  u, q end at the last stride's state; ucross / pcross (may be null) receive the crossing.
+// out = {found, tcrossing, hcrossing, scrossing, strides taken, hcurrent}
+void cf_poincare_search(void* uh, void* qh, const CfFlags* rf, int kind, void* ustar, void* estar, int nSteps, int maxstrides,
+                        int crosssign, double Tmin, double eps, double* out, void* ucross, void* pcross) {
+    FlowField& u = *(FlowField*)uh;
+    FlowField& q = *(FlowField*)qh;
+    std::unique_ptr<PoincareCondition> h;
+    if (kind == 0) h.reset(new DragDissipation());
+    else h.reset(new PlaneIntersection(*(FlowField*)ustar, *(FlowField*)estar));
+    DNSPoincare dns(u, h.get(), to_flags(rf));
+    bool found = false;
+    int n = 0;
+    while (n < maxstrides && !found) {
+        found = dns.advanceToSection(u, q, nSteps, crosssign, Tmin, eps);
+        ++n;
+    }
+    out[0] = found ? 1.0 : 0.0;
+    out[1] = found ? dns.tcrossing() : 0.0;
+    out[2] = found ? dns.hcrossing() : 0.0;
+    out[3] = found ? dns.scrossing() : 0.0;
+    out[4] = n;
+    out[5] = dns.hcurrent();
+    if (found && ucross) *(FlowField*)ucross = dns.ucrossing();
+    if (found && pcross) *(FlowField*)pcross = dns.pcrossing();
+}
 
 // Newton-Krylov-hookstep search on the device (channelflow/devicesearch.h): u is the initial guess and receives the solution.
 // sigma = {s, sx, sy, sz, ax, az} (ax, az updated on return); par = {epsSearch, epsGMRES, epsDx, delta, Nnewton, Ngmres, Nhook,

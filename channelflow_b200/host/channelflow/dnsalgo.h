@@ -20,6 +20,7 @@ class DNSAlgorithm {
 
     virtual void advance(std::vector<FlowField>& fields, int nSteps = 1) = 0;
     virtual void project() {}  // project the state the algorithm holds onto the symmetric subspace of the flags
+    virtual void operator*=(const std::vector<FieldSymmetry>&) {}  // map the stored history (dnsalgo.cpp:50, 264-272)
     cfarray<FieldSymmetry> symmetries(int ifield) const { return symmetries_[ifield]; }
     virtual void reset_dt(Real dt) = 0;
     virtual bool push(const std::vector<FlowField>& fields);
@@ -54,6 +55,7 @@ class MultistepDNS : public DNSAlgorithm {
     MultistepDNS(const std::vector<FlowField>& fields, const std::shared_ptr<NSE>& nse, const DNSFlags& flags);
     void advance(std::vector<FlowField>& fields, int nSteps = 1) override;
     void project() override;
+    void operator*=(const std::vector<FieldSymmetry>& sigma) override;
     void reset_dt(Real dt) override;
     bool push(const std::vector<FlowField>& fields) override;
     bool full() const override { return countdown_ == 0; }

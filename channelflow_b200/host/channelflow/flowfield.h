@@ -186,6 +186,12 @@ class FlowField {
     bool geomCongruent(const FlowField& f, Real eps = 1e-13) const;
     bool congruent(const FlowField& f, Real eps = 1e-13) const;
     friend void swap(FlowField& f, FlowField& g);
+// Lagrange interpolant sum_n w_n(mu) un[n] through (mun[n], un[n]), box lengths and wall positions interpolated alike
+// (flowfield.cpp:4136-4287; there point by point on the physical grid -- the interpolant is linear in the data, so here it
+// is length(un) axpy's on the device in whatever state the fields are in).  The result is spectral, padded modes zeroed
+// when the inputs' are.
+FlowField quadraticInterpolate(cfarray<FlowField>& un, const cfarray<Real>& mun, Real mu, Real eps = 1e-13);
+FlowField polynomialInterpolate(cfarray<FlowField>& un, cfarray<Real>& mun, Real mu);
 
     void binarySave(const std::string& filebase) const;
     void asciiSave(const std::string& filebase) const;

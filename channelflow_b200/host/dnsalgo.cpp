@@ -174,6 +174,15 @@ void MultistepDNS::project() {
         }
 }
 
+void MultistepDNS::operator*=(const std::vector<FieldSymmetry>& sigma) {
+    assert((int)sigma.size() == numfields_);
+    for (int n = 0; n < order_; ++n)
+        for (int m = 0; m < numfields_; ++m) {
+            fields_[n][m] *= sigma[m];
+            nonlf_[n][m] *= sigma[m];
+        }
+}
+
 bool MultistepDNS::push(const std::vector<FlowField>& fields) {
     for (int j = order_ - 1; j > 0; --j)
         for (int l = 0; l < numfields_; ++l) {

@@ -134,6 +134,8 @@ double ref_l2norm3d(void* h) { return L2Norm3d(*(FlowField*)h); }
 double ref_l2dist(void* a, void* b) { return L2Dist(*(FlowField*)a, *(FlowField*)b); }
 double ref_l2ip(void* a, void* b) { return L2InnerProduct(*(FlowField*)a, *(FlowField*)b); }
 double ref_divnorm(void* h) { return divNorm(*(FlowField*)h); }
+double ref_wallshear(void* h) { return wallshear(*(FlowField*)h); }
+double ref_dissipation(void* h) { return dissipation(*(FlowField*)h); }
 double ref_bcnorm(void* h) { return bcNorm(*(FlowField*)h); }
 
 int ref_field2vector_size(void* h) { return field2vector_size(*(FlowField*)h); }

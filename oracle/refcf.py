@@ -73,6 +73,9 @@ def lib():
         for n in ("ref_l2norm", "ref_l2dist", "ref_l2ip", "ref_divnorm", "ref_bcnorm", "ref_l2norm2", "ref_dns_cfl",
                   "ref_dns_time", "ref_dns_dPdx", "ref_dns_Ubulk"):
             getattr(L, n).restype = d
+        for n in ("ref_wallshear", "ref_dissipation"):
+            getattr(L, n).argtypes = [vp]
+            getattr(L, n).restype = d
         L.ref_l2norm2.argtypes = [vp, i]
         L.ref_l2dist.argtypes = [vp, vp]
         L.ref_l2ip.argtypes = [vp, vp]
@@ -178,6 +181,8 @@ class RefField:
     def l2dist(self, o): return lib().ref_l2dist(self.h, o.h)
     def l2ip(self, o): return lib().ref_l2ip(self.h, o.h)
     def divnorm(self): return lib().ref_divnorm(self.h)
+    def wallshear(self): return lib().ref_wallshear(self.h)
+    def dissipation(self): return lib().ref_dissipation(self.h)
     def bcnorm(self): return lib().ref_bcnorm(self.h)
 
     def to_vector(self):

@@ -427,3 +427,99 @@ def netcdf_reader(lib):
     _, ur = load_eq(lib)
     v = cf.FlowField(lib, ur.Nx, ur.Ny, ur.Nz, 3, ur.Lx, ur.Lz, ur.a, ur.b, handle=h)
     return {"rel": rel_l2(v.get(), ur.data), "padded": v.padded()}
+
+
+def poincare_section(lib, cfg, kind="plane", nstride=5, maxstrides=40, frac=0.97, seed=7, crosssign=0, **flag_over):
+    """DNSPoincare::advanceToSection (host/poincare.cpp) against a restatement of the documented algorithm (dns.cpp:520-700)
+    that uses the compiled reference for everything it is built from: the reference's DNS for the coarse strides and the
+    step-by-step second pass, the reference's L2IP / wallshear / dissipation for h, numpy for the quadratic interpolant in
+    time and the Newton iteration.  (The reference's own advanceToSection advances a copy of its arguments, dns.cpp:526-528,
+    and therefore never sees a crossing; see channelflow/dns.h in this package.)  Returns times, h and the field mismatch."""
+    fl = dict(cfg["flags"]); fl.update(flag_over)
+    dt = fl["dt"]
+    u0 = ref_random(cfg, seed, magn=float(cfg.get("magn", 0.2)))
+    if kind == "plane":
+        e = u0.copy()
+        c = frac * u0.l2ip(e)
+        h = lambda f: f.l2ip(e) - c  # noqa: E731
+    else:
+        # I - D of the total velocity: zero base flow, the laminar profile y carried by the field itself
+        fl["baseflow"] = "zero"
+        u0.cdata[0, 1, 0, 0] += 1.0
+        h = lambda f: f.wallshear() - f.dissipation()  # noqa: E731
+    # ---- device
+    ug = to_gpu(lib, u0); qg = ug.like(Nd=1)
+    if kind == "plane":
+        eg = to_gpu(lib, u0); sg = to_gpu(lib, u0); sg.scale(frac)
+        res = cf.poincare_search(ug, qg, cf.make_flags(**fl), nstride, maxstrides, ustar=sg, estar=eg, crosssign=crosssign)
+    else:
+        res = cf.poincare_search(ug, qg, cf.make_flags(**fl), nstride, maxstrides, crosssign=crosssign)
+    out = {"found": res["found"], "t": res["t"], "h": res["h"], "sign": res["sign"], "strides": res["strides"]}
+    # ---- restatement on the reference
+    def lagr(xs, x):
+        w = np.ones(len(xs))
+        for i in range(len(xs)):
+            for j in range(len(xs)):
+                if j != i:
+                    w[i] *= (x - xs[j]) / (xs[i] - xs[j])
+        return w
+    rd = refcf.RefDNS(u0, refcf.make_flags(**fl))
+    tmp = u0.copy()
+    def h_of(arr):
+        tmp.data[...] = arr
+        return h(tmp)
+    ref = {"found": False, "strides": 0}
+    us, qs = u0.copy(), u0.like(Nd=1)
+    for stride in range(maxstrides):
+        rd.advance(nstride)
+        ue, qe = rd.get()
+        ref["strides"] += 1
+        h0, h1 = h(us), h(ue)
+        up, down = h0 < 0 <= h1, h0 > 0 >= h1
+        if (crosssign > 0 and up) or (crosssign < 0 and down) or (crosssign == 0 and (up or down)):
+            tstart = rd.time() - dt * nstride
+            fl2 = dict(fl); fl2["t0"] = tstart
+            fd = refcf.RefDNS(us, refcf.make_flags(**fl2), q=qs)
+            ts, hs, ua = [tstart], [h0], [us.data.copy()]
+            for k in range(nstride + 2):
+                fd.advance(1)
+                uk, _ = fd.get()
+                ts.insert(0, tstart + (k + 1) * dt); hs.insert(0, h(uk)); ua.insert(0, uk.data.copy())
+                ts, hs, ua = ts[:3], hs[:3], ua[:3]
+                if len(ts) == 3 and ((hs[2] < 0 <= hs[0]) or (hs[2] > 0 >= hs[0])):
+                    s = float(np.dot(lagr(hs, 0.0), ts))
+                    for it in range(6):
+                        v = sum(w * a for w, a in zip(lagr(ts, s), ua))
+                        g = h_of(v)
+                        if abs(g) < 0.5e-13 or it == 5:
+                            break
+                        vd = sum(w * a for w, a in zip(lagr(ts, s + 1e-9 * s), ua))
+                        s -= g / ((h_of(vd) - g) / (1e-9 * s))
+                    ref.update(found=True, t=s, h=g, sign=1 if h0 < 0 else -1, u=v)
+                    break
+            break
+        us, qs = ue, qe
+    out["ref_found"] = ref["found"]; out["ref_strides"] = ref["strides"]
+    if ref["found"] and res["found"]:
+        out["ref_t"] = ref["t"]; out["ref_sign"] = ref["sign"]; out["ref_h"] = ref["h"]
+        out["dt_cross"] = abs(ref["t"] - res["t"])
+        out["u_rel"] = rel_l2(res["ucrossing"].get(), ref["u"])
+        # h of the device crossing field measured by the reference
+        out["h_by_ref"] = h_of(np.asarray(res["ucrossing"].get()).reshape(tmp.data.shape))
+    return out
+
+
+def dns_equivariance(lib, cfg, sym=(1, -1, -1, 1, 0.5, 0.0), n1=6, n2=6, seed=3, **flag_over):
+    """DNS::operator*= (dns.cpp:175-180, dnsalgo.cpp:264-272): for a symmetry sigma of plane Couette flow, mapping the running
+    multistep DNS (state and history) after n1 steps and taking n2 more must equal sigma of the unmapped run after n1 + n2
+    steps.  Also returns what happens when only the state is mapped (the history matters)."""
+    fl = dict(cfg["flags"]); fl.update(flag_over)
+    u0 = to_gpu(lib, ref_random(cfg, seed, magn=float(cfg.get("magn", 0.2))))
+    a = cf.DNS(u0, cf.make_flags(**fl)); a.advance(n1 + n2)
+    ua, _ = a.get(); ua.symmetry(*sym)
+    b = cf.DNS(u0, cf.make_flags(**fl)); b.advance(n1); b.symmetry(*sym); b.advance(n2)
+    ub, _ = b.get()
+    c = cf.DNS(u0, cf.make_flags(**fl)); c.advance(n1)
+    uc, qc = c.get(); uc.symmetry(*sym); c.set(uc, None); c.advance(n2)   # state only: the history is stale
+    uc, _ = c.get()
+    return {"mapped": rel_l2(ub.get(), ua.get()), "state_only": rel_l2(uc.get(), ua.get())}

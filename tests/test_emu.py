@@ -300,3 +300,19 @@ def test_variable_dt_loop(lib):
 def test_netcdf4_field_reader(lib):
     r = parity.netcdf_reader(lib)
     assert r["padded"] and r["rel"] < 1e-14, r
+
+
+def test_poincare_section_plane(lib):
+    """DNSPoincare::advanceToSection (PlaneIntersection) against the restatement on the compiled reference, 16x17x16."""
+    cfg = dict(parity.C1); cfg.update(Nx=16, Ny=17, Nz=16)
+    r = parity.poincare_section(lib, cfg, kind="plane", nstride=4, maxstrides=30)
+    assert r["found"] and r["ref_found"] and r["strides"] == r["ref_strides"] and r["sign"] == r["ref_sign"] == -1, r
+    assert r["dt_cross"] < 1e-10 and r["u_rel"] < 1e-10 and abs(r["h"]) < 1e-13 and abs(r["h_by_ref"]) < 1e-12, r
+
+
+def test_dns_symmetry_map_equivariance(lib):
+    """DNS::operator*= maps the multistep history as well as the state (6 + 6 SBDF3 steps, sigma = rotation about z + half-box
+    shift): the mapped run equals sigma of the unmapped one to round-off; mapping the state alone does not."""
+    cfg = dict(parity.C1); cfg.update(Nx=16, Ny=17, Nz=16)
+    r = parity.dns_equivariance(lib, cfg)
+    assert r["mapped"] < 1e-12 and r["state_only"] > 1e3 * max(r["mapped"], 1e-14), r

@@ -323,3 +323,28 @@ def test_findsoln_program(lib, tmp_path):
     assert os.path.exists(str(tmp_path / "ubest.ff")) and os.path.exists(str(tmp_path / "sigmabest.asc"))
     hist = [float(x) for x in open(str(tmp_path / "convergence.asc")).read().split("\n")[1:] if x.strip()]
     assert hist[-1] < 1e-12 and hist[-1] < 1e-4 * hist[0], hist
+
+
+def test_poincare_section_plane(lib):
+    """DNSPoincare::advanceToSection with a PlaneIntersection condition against the restatement on the compiled reference
+    (tests/parity.py:poincare_section).  Tolerances: crossing time 1e-10, crossing field 1e-10 relative, |h| <= 1e-13."""
+    r = parity.poincare_section(lib, parity.C1, kind="plane", nstride=5, maxstrides=40)
+    print("poincare plane:", r)
+    assert r["found"] and r["ref_found"] and r["strides"] == r["ref_strides"] and r["sign"] == r["ref_sign"] == -1, r
+    assert r["dt_cross"] < 1e-10 and r["u_rel"] < 1e-10 and abs(r["h"]) < 1e-13 and abs(r["h_by_ref"]) < 1e-12, r
+
+
+def test_poincare_section_drag_dissipation(lib):
+    """The I - D = 0 section (DragDissipation: wallshear - dissipation on the device) crossed downwards at t ~ 5 on a 16x17x16 box."""
+    cfg = dict(parity.C1); cfg.update(Nx=16, Ny=17, Nz=16)
+    r = parity.poincare_section(lib, cfg, kind="drag", nstride=5, maxstrides=80, crosssign=-1)
+    print("poincare I-D:", r)
+    assert r["found"] and r["ref_found"] and r["strides"] == r["ref_strides"] > 40 and r["sign"] == -1, r
+    assert r["dt_cross"] < 1e-8 and r["u_rel"] < 1e-9 and abs(r["h"]) < 1e-12, r
+
+
+def test_dns_symmetry_map_equivariance(lib):
+    """DNS::operator*= maps the multistep history as well as the state (6 + 6 SBDF3 steps, sigma = rotation about z + half-box
+    shift): the mapped run equals sigma of the unmapped one to round-off; mapping the state alone does not."""
+    r = parity.dns_equivariance(lib, parity.C1)
+    assert r["mapped"] < 1e-12 and r["state_only"] > 1e3 * max(r["mapped"], 1e-14), r
