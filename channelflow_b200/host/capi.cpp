@@ -69,7 +69,7 @@ double cf_cmplx_get(void* h, int mx, int my, int mz, int i, int part) {
 void cf_cmplx_set(void* h, int mx, int my, int mz, int i, double re, double im) {
     ((FlowField*)h)->cmplx(mx, my, mz, i) = Complex(re, im);
 }
-void cf_field_save(void* h, const char* filebase) { ((FlowField*)h)->binarySave(filebase); }
+void cf_field_save(void* h, const char* filebase) { ((FlowField*)h)->save(filebase); }  // suffix picks .ff (default) / .nc / .asc
 void* cf_field_load(const char* filebase) { return new FlowField(std::string(filebase)); }
 
 double cf_l2norm(void* h) { return L2Norm(*(FlowField*)h); }

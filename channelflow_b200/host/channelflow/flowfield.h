@@ -196,6 +196,8 @@ FlowField polynomialInterpolate(cfarray<FlowField>& un, cfarray<Real>& mun, Real
     void binarySave(const std::string& filebase) const;
     void asciiSave(const std::string& filebase) const;
     void save(const std::string& filebase, std::vector<std::string> component_names = std::vector<std::string>()) const;
+    // NetCDF with the reference's dimensions / variables / attributes (flowfield.cpp:3225-3597), classic CDF-2 container (ncfile.cpp)
+    void writeNetCDF(const std::string& filebase, std::vector<std::string> component_names = std::vector<std::string>()) const;
     void saveProfile(int mx, int mz, const std::string& filebase) const;
     void saveProfile(int mx, int mz, const std::string& filebase, const ChebyTransform& t) const;
     void saveSpectrum(const std::string& filebase, int i, int ny = -1, bool kxorder = true, bool showpadding = false) const;

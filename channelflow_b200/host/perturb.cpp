@@ -382,10 +382,13 @@ void FlowField::saveSpectrum(const std::string& filebase, bool kxorder, bool sho
     if (kxorder) for (int k = Kxmin; k <= Kxmax; ++k) row(mx(k));
     else for (int m = 0; m < Mx(); ++m) if (kx(m) >= Kxmin && kx(m) <= Kxmax) row(m);
 }
-void FlowField::save(const std::string& filebase, std::vector<std::string>) const {
+// flowfield.cpp:2598-2650: the suffix picks the format; without one the reference writes NetCDF when it was built with the
+// library and .ff otherwise -- this build keeps the native .ff as the default
+void FlowField::save(const std::string& filebase, std::vector<std::string> component_names) const {
     if (hasSuffix(filebase, ".asc")) asciiSave(filebase);
-    else if (hasSuffix(filebase, ".nc") || hasSuffix(filebase, ".h5"))
-        cferror("FlowField::save(filename) error : this build writes Channelflow's native .ff files (and .asc); filename == " + filebase);
+    else if (hasSuffix(filebase, ".nc")) writeNetCDF(filebase, component_names);
+    else if (hasSuffix(filebase, ".h5"))
+        cferror("FlowField::save(filename) error : can't save to HDF5 file because HDF5 libraries are not installed. filename == " + filebase);
     else binarySave(filebase);
 }
 

@@ -523,3 +523,60 @@ def dns_equivariance(lib, cfg, sym=(1, -1, -1, 1, 0.5, 0.0), n1=6, n2=6, seed=3,
     uc, qc = c.get(); uc.symmetry(*sym); c.set(uc, None); c.advance(n2)   # state only: the history is stale
     uc, _ = c.get()
     return {"mapped": rel_l2(ub.get(), ua.get()), "state_only": rel_l2(uc.get(), ua.get())}
+
+
+def netcdf_writer(lib, tmpdir):
+    """FlowField::writeNetCDF (host/ncfile.cpp: the reference's dimensions, variables and attributes in the classic CDF-2
+    container).  The field of the reference's own eq.nc is loaded and written back; scipy.io.netcdf_file -- an independent
+    implementation of the format -- must find the reference's schema and the values stock Channelflow wrote (eq.npz holds
+    them), and this package's reader must return the same field from both files.  Also the full-grid (unpadded) case."""
+    from scipy.io import netcdf_file
+    g = np.load(os.path.join(GOLDEN, "eq.npz"))
+    src = os.path.join(GOLDEN, "eq.nc")
+    h = lib.L.cf_field_load(src.encode())
+    ug, ur = load_eq(lib)
+    v = cf.FlowField(lib, ur.Nx, ur.Ny, ur.Nz, 3, ur.Lx, ur.Lz, ur.a, ur.b, handle=h)
+    out = os.path.join(str(tmpdir), "eq_out.nc")
+    v.save(out)
+    res = {}
+    with netcdf_file(out, "r", mmap=False) as nc:
+        res["dims"] = {k: int(n) for k, n in nc.dimensions.items()}
+        res["vars"] = list(nc.variables.keys())
+        res["attrs"] = {k: getattr(nc, k) for k in ("Nx", "Ny", "Nz", "Lx", "Lz", "a", "b")}
+        res["title"] = nc.title.decode() if isinstance(nc.title, bytes) else str(nc.title)
+        vals = np.stack([np.array(nc.variables[n][:]) for n in ("Velocity_X", "Velocity_Y", "Velocity_Z")])
+        res["var_dims"] = nc.variables["Velocity_X"].dimensions
+        res["grid_err"] = max(float(np.abs(np.array(nc.variables["X"][:]) - np.arange(res["dims"]["X"]) * ur.Lx / res["dims"]["X"]).max()),
+                              float(np.abs(np.array(nc.variables["Y"][:]) - np.cos(np.pi * np.arange(ur.Ny) / (ur.Ny - 1))).max()))
+    res["values_abs"] = float(np.abs(vals - np.asarray(g["u"]).reshape(vals.shape)).max())
+    h2 = lib.L.cf_field_load(out.encode())
+    v2 = cf.FlowField(lib, ur.Nx, ur.Ny, ur.Nz, 3, ur.Lx, ur.Lz, ur.a, ur.b, handle=h2)
+    res["reread_rel"] = rel_l2(v2.get(), v.get())
+    res["reread_padded"] = v2.padded()
+    # full grid: an unpadded field keeps every mode
+    w = to_gpu(lib, ref_random(C1, 4), padded=False)
+    out2 = os.path.join(str(tmpdir), "full.nc")
+    w.save(out2)
+    h3 = lib.L.cf_field_load(out2.encode())
+    w2 = cf.FlowField(lib, C1["Nx"], C1["Ny"], C1["Nz"], 3, C1["Lx"], C1["Lz"], C1["a"], C1["b"], handle=h3)
+    res["full_rel"] = rel_l2(w2.get(), w.get())
+    res["full_padded"] = w2.padded()
+    with netcdf_file(out2, "r", mmap=False) as nc:
+        res["full_dims"] = {k: int(n) for k, n in nc.dimensions.items()}
+    # a classic file written by scipy (CDF-1 container) with the same schema is readable too
+    out3 = os.path.join(str(tmpdir), "scipy.nc")
+    with netcdf_file(out3, "w", version=1) as nc:
+        for k in ("Nx", "Ny", "Nz"):
+            setattr(nc, k, np.int32(getattr(ur, k)))
+        for k in ("Lx", "Lz", "a", "b"):
+            setattr(nc, k, np.float64(getattr(ur, k)))
+        nz, ny, nx = vals.shape[1:]
+        nc.createDimension("X", nx); nc.createDimension("Y", ny); nc.createDimension("Z", nz)
+        for n, ln in (("X", nx), ("Y", ny), ("Z", nz)):
+            nc.createVariable(n, "d", (n,))[:] = np.zeros(ln)
+        for i, n in enumerate(("Velocity_X", "Velocity_Y", "Velocity_Z")):
+            nc.createVariable(n, "d", ("Z", "Y", "X"))[:] = np.asarray(g["u"]).reshape(vals.shape)[i]
+    h4 = lib.L.cf_field_load(out3.encode())
+    v4 = cf.FlowField(lib, ur.Nx, ur.Ny, ur.Nz, 3, ur.Lx, ur.Lz, ur.a, ur.b, handle=h4)
+    res["scipy_rel"] = rel_l2(v4.get(), ur.data)
+    return res

@@ -348,3 +348,15 @@ def test_dns_symmetry_map_equivariance(lib):
     shift): the mapped run equals sigma of the unmapped one to round-off; mapping the state alone does not."""
     r = parity.dns_equivariance(lib, parity.C1)
     assert r["mapped"] < 1e-12 and r["state_only"] > 1e3 * max(r["mapped"], 1e-14), r
+
+
+def test_netcdf_field_writer(lib, tmp_path):
+    """FlowField::save("x.nc"): reference schema in the classic container, checked with scipy's independent reader against
+    the values stock Channelflow wrote (1e-14 absolute), re-read by this package (1e-14), full-grid and CDF-1 variants."""
+    r = parity.netcdf_writer(lib, tmp_path)
+    assert r["dims"] == {"X": 16, "Y": 33, "Z": 16} and r["var_dims"] == ("Z", "Y", "X") and r["title"] == "FlowField", r
+    assert r["vars"] == ["X", "Y", "Z", "Velocity_X", "Velocity_Y", "Velocity_Z"], r
+    assert (int(r["attrs"]["Nx"]), int(r["attrs"]["Ny"]), int(r["attrs"]["Nz"])) == (24, 33, 24) and float(r["attrs"]["a"]) == -1.0, r
+    assert r["grid_err"] < 1e-14 and r["values_abs"] < 1e-14 and r["reread_rel"] < 1e-14 and r["reread_padded"], r
+    assert r["full_rel"] < 1e-14 and not r["full_padded"] and r["full_dims"] == {"X": 32, "Y": 33, "Z": 32}, r
+    assert r["scipy_rel"] < 1e-14, r

@@ -282,8 +282,16 @@ def _tool_chain(flavour, tmp_path, grid):
             r = subprocess.run([path] + args.format(Nx=Nx, Ny=Ny, Nz=Nz).split(), cwd=str(d), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                text=True, timeout=600)
             assert r.returncode == 0, (exe, r.stdout[-2000:])
+    # NetCDF out and back in through the unmodified fieldconvert on the drop-in build (the compiled reference has no NetCDF)
+    for args in ("u3 u3nc.nc", "u3nc.nc u3back.ff"):
+        r = subprocess.run([os.path.join(PROGS, flavour, "fieldconvert")] + args.split(), cwd=str(tmp_path / "new"), stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, (args, r.stdout[-2000:])
     lib = parity.gpu_lib() if flavour == "gpu" else parity.emu_lib()
     out = {}
+    a = [cf.FlowField(lib, Nx, Ny, Nz, 3, 2 * np.pi, np.pi, handle=lib.L.cf_field_load(str(tmp_path / "new" / n).encode())).get()
+         for n in ("u3", "u3back")]
+    out["u3_via_nc"] = float(np.linalg.norm((a[0] - a[1]).ravel()) / np.linalg.norm(a[0].ravel()))
     for name, Nd in (("u1", 3), ("u2", 3), ("u3", 3), ("p3", 1), ("u3copy", 3)):
         arrs = []
         for side in ("ref", "new"):
