@@ -188,6 +188,15 @@ int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out) {
     return 0;
 }
 
+// FFT plan for the y-transform of Ny points (yfft.cu) or null: unsupported length, or CF_YFFT=0 (the DMMA contraction)
+const FftPlanDev* yfft_plan(cfgpu_ctx ctx, int Ny) {
+    static const int on = getenv("CF_YFFT") ? atoi(getenv("CF_YFFT")) : 1;
+    if (!on || !yfft_length_supported(Ny)) return nullptr;
+    const FftPlanDev* pl = nullptr;
+    if (get_fftplan(ctx, 2 * (Ny - 1), &pl)) return nullptr;
+    return pl;
+}
+
 int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out) {
     auto it = ctx->fftplans.find(N);
     if (it != ctx->fftplans.end()) {
@@ -895,6 +904,7 @@ static int y_transform(cfgpu_field f, int mode) {
         YGemmParams p;
         memset(&p, 0, sizeof p);
         p.N = f->Ny; p.mode = mode;
+        p.fft = yfft_plan(f->ctx, f->Ny); p.ya = f->a; p.yb = f->b;
         if (mode == 0) {
             p.M = p.M2 = pl->Nh; p.K1 = pl->Ne; p.K2 = pl->No; p.K1p = pl->invK1p; p.K2p = pl->invK2p;
             p.A1[0] = pl->Ce; p.A2[0] = pl->Co; p.sgn[0] = 1.0;

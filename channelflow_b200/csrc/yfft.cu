@@ -1,0 +1,217 @@
+// Chebyshev y-transform as a shared-memory FFT: the same jobs as ygemm.cu (YGemmParams), for the profile lengths whose
+// even extension 2(Ny-1) factors into 2, 3, 5.
+//
+// The transform of the reference (flowfield.cpp:1888-1987, FFTW REDFT00) is a DCT-I of length Ny = M+1.  The two real
+// profiles of one Fourier mode (re, im) form one complex sequence z_n; its even extension e (length L = 2M, e_n = e_{L-n})
+// has the transform  FFT(e)_j = z_0 + (-1)^j z_M + 2 sum_{0<n<M} z_n cos(pi j n / M),  real part = DCT of re, imaginary part
+// = DCT of im.  So one complex FFT of length L per mode does both profiles; only its outputs 0..M are kept.
+//   inverse : u_j = sum_n c_n cos(pi j n/M)                    -> e_0 = c_0, e_M = c_M, e_n = c_n/2 otherwise; u = FFT(e)
+//   forward : c_n = w_n sum_j g_j x_j cos(pi j n/M)            -> e = x (even extension);  c_n = w_n FFT(e)_n,
+//             w_n = 1/M (1/(2M) at n = 0, M), g_j = 2 (1 at the ends)      (flowfield.cpp:1913-1934)
+//   d/dy    : coefficients d_n = (4/(b-a)) (1/2 at n = 0) sum_{m>n, m-n odd} m c_m   (chebyshev.cpp:672-697), formed in shared
+//             memory by a chunked suffix sum over n before the second FFT of the same input.
+// Against the DMMA contraction this is O(L log L) instead of O(Ny^2/2) flops per profile: at Ny = 257 the contraction is
+// bound by the FP64 tensor pipe (1.65 ms inverse, 1.14 ms forward at 512x257x512), the FFT by HBM.
+//
+// CTA = C complex columns (modes) of one job; shared memory a[L][C] (in-place transform, digit-reversed input rows) plus the
+// plan's twiddle and row tables.  A row piece of C = 8 columns is 128 contiguous bytes in HBM.
+#include "fft_smem.cuh"
+#include "ygemm.cuh"
+
+namespace cfgpu {
+
+namespace {
+
+constexpr int YF_THREADS = 256;
+
+// CH = rows per thread: thread (c, t) owns column c and the rows [t ch, t ch + ch), ch = ceil(N / (YF_THREADS / C)) <= CH.  It
+// loads them into registers (a warp reads 32/C row pieces of 16 C contiguous bytes per instruction); the suffix sums of
+// m c_m for the derivative need each coefficient twice.
+// One CTA = one transform: the units of work are (job, value) and (job, derivative) pairs, numbered fastest along the grid
+// so that the two CTAs that read the same coefficients run side by side (the second read hits L2).
+struct YfftUnits {
+    int n;
+    unsigned char job[2 * YG_MAXJOB], der[2 * YG_MAXJOB];
+};
+
+template <int C, int CH>
+__global__ void __launch_bounds__(YF_THREADS, 3) yfft_kernel(const YGemmParams p, const FftPlanDev pl, const double dscale,
+                                                             const YfftUnits un) {
+    const int N = p.N, M = N - 1, L = 2 * M;
+    const int tid = threadIdx.x;
+    const int unit = blockIdx.x % un.n;
+    const long cblock = blockIdx.x / un.n;
+    const YGemmJob& jb = p.job[un.job[unit]];
+    const bool is_der = un.der[unit] != 0;
+    constexpr int TPC = YF_THREADS / C;  // threads per column
+    const int ntw = fft_plan_ntw(pl);
+    double2* a = dyn_smem<double2>();      // [L][C]
+    double2* stw = a + (size_t)L * C;      // [ntw] twiddles the passes touch
+    double2* part = stw + ntw;             // [2][TPC][C] chunk sums of the derivative
+    int* rev = reinterpret_cast<int*>(part + 2 * TPC * C);   // [L] digit-reversed rows
+    const int c = tid % C, t = tid / C;
+    const long col = cblock * C + c;                  // complex column
+    const bool cvalid = 2 * col < p.ncols;
+    const long dc = 2 * col;
+    const long inoff = !cvalid ? 0 : (p.in_runstart ? p.in_runstart[dc / p.in_runlen] + dc % p.in_runlen : dc);
+    const long outoff = !cvalid ? 0 : (p.out_runstart ? p.out_runstart[dc / p.out_runlen] + dc % p.out_runlen : dc);
+    const double2 zero = make_double2(0.0, 0.0);
+    const int ch = (N + TPC - 1) / TPC;
+    const int n0 = t * ch;
+
+    // the thread's rows first (the longest latency), the tables behind them
+    double2 v[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const int n = n0 + i;
+        v[i] = zero;
+        if (i < ch && n < N && cvalid) {
+            const double* src = jb.in + (size_t)n * p.in_ld + inoff;
+            v[i] = make_double2(src[0], src[1]);
+        }
+    }
+    for (int i = tid; i < L; i += YF_THREADS) rev[i] = pl.rev[i];
+    for (int i = tid; i < ntw; i += YF_THREADS) stw[i] = pl.tw[i];
+    __syncthreads();
+
+    auto store = [&](int m, int r, double2 x) {
+        if (!cvalid) return;
+        double* dst = (jb.out_rows[m] ? jb.out_rows[m][r] : jb.out[m] + (size_t)r * p.out_ld) + outoff;
+        dst[0] = x.x;
+        dst[1] = x.y;
+    };
+    // even extension of the thread's rows, halved away from the ends (inverse) or as they are (forward)
+    auto scatter = [&](const double2 (&x)[CH], bool halve) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int n = n0 + i;
+            if (i < ch && n < N) {
+                const double h = (halve && n != 0 && n != M) ? 0.5 : 1.0;
+                const double2 e = make_double2(h * x[i].x, h * x[i].y);
+                a[(size_t)rev[n] * C + c] = e;
+                if (n > 0 && n < M) a[(size_t)rev[L - n] * C + c] = e;
+            }
+        }
+    };
+
+    if (p.mode == 1) {
+        // ---- forward: c_n = w_n FFT_n of the even extension of the physical profile
+        scatter(v, false);
+        __syncthreads();
+        fft_smem_inplace<-1, false, true>(a, pl, stw, C, tid, YF_THREADS);
+        const double w = 1.0 / M;
+        for (int n = t; n < N; n += TPC) {
+            const double wn = (n == 0 || n == M) ? 0.5 * w : w;
+            const double2 x = a[(size_t)n * C + c];
+            store(0, n, make_double2(wn * x.x, wn * x.y));
+        }
+        return;
+    }
+
+    // ---- inverse: values (matrix 0) or y-derivative (matrix 1)
+    if (!is_der) {
+        scatter(v, true);
+        __syncthreads();
+        fft_smem_inplace<-1, false, true>(a, pl, stw, C, tid, YF_THREADS);
+        for (int j = t; j < N; j += TPC) store(0, j, a[(size_t)j * C + c]);
+        return;
+    }
+    {
+        // sums of m c_m over the even and the odd m of the thread's rows, the totals of the chunks above, the walk down
+        double2 se = zero, so = zero;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int m = n0 + i;   // (rows past the end hold zeros)
+            if (m & 1) { so.x += m * v[i].x; so.y += m * v[i].y; }
+            else { se.x += m * v[i].x; se.y += m * v[i].y; }
+        }
+        part[(size_t)t * C + c] = se;
+        part[(size_t)(TPC + t) * C + c] = so;
+        __syncthreads();
+        se = zero; so = zero;
+        for (int tt = TPC - 1; tt > t; --tt) {
+            const double2 pe = part[(size_t)tt * C + c], po = part[(size_t)(TPC + tt) * C + c];
+            se.x += pe.x; se.y += pe.y;
+            so.x += po.x; so.y += po.y;
+        }
+#pragma unroll
+        for (int i = CH - 1; i >= 0; --i) {
+            const int n = n0 + i;
+            const double2 sm = (n & 1) ? se : so;   // sum over m > n of the other parity
+            const double f = (n == 0) ? 0.5 * dscale : dscale;
+            if (n & 1) { so.x += n * v[i].x; so.y += n * v[i].y; }
+            else { se.x += n * v[i].x; se.y += n * v[i].y; }
+            v[i] = make_double2(f * sm.x, f * sm.y);
+        }
+        scatter(v, true);
+        __syncthreads();
+        fft_smem_inplace<-1, false, true>(a, pl, stw, C, tid, YF_THREADS);
+        const int mder = jb.mat0 == 0 ? 1 : 0;   // output slot of the derivative
+        for (int j = t; j < N; j += TPC) store(mder, j, a[(size_t)j * C + c]);
+    }
+}
+
+template <int C, int CH>
+int launch_c(const YGemmParams& p, const FftPlanDev& pl, double dscale, cudaStream_t stream) {
+    const int N = p.N, L = 2 * (N - 1);
+    const size_t smem = ((size_t)L * C + fft_plan_ntw(pl) + 2 * YF_THREADS) * sizeof(double2) + (size_t)L * sizeof(int);
+    auto kfn = yfft_kernel<C, CH>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    YfftUnits un;
+    un.n = 0;
+    for (int j = 0; j < p.njobs; ++j) {
+        if (p.mode == 1 || p.job[j].mat0 == 0) { un.job[un.n] = (unsigned char)j; un.der[un.n++] = 0; }
+        if (p.mode == 0 && p.job[j].mat0 + p.job[j].nmat > 1) { un.job[un.n] = (unsigned char)j; un.der[un.n++] = 1; }
+    }
+    const long ccols = p.ncols / 2;
+    const long nblk = ((ccols + C - 1) / C) * un.n;
+    if (nblk > 0x7fffffffL) return -1;
+    CF_LAUNCH(kfn, dim3((unsigned)nblk), dim3(YF_THREADS), smem, stream, p, pl, dscale, un);
+    CF_KERNEL_CHECK();
+    return 0;
+}
+
+template <int C>
+int launch_ch(const YGemmParams& p, const FftPlanDev& pl, double dscale, cudaStream_t stream) {
+    const int ch = (p.N + YF_THREADS / C - 1) / (YF_THREADS / C);
+    if (ch <= 3) return launch_c<C, 3>(p, pl, dscale, stream);
+    if (ch <= 5) return launch_c<C, 5>(p, pl, dscale, stream);
+    if (ch <= 9) return launch_c<C, 9>(p, pl, dscale, stream);
+    if (ch <= 17) return launch_c<C, 17>(p, pl, dscale, stream);
+    return -1;
+}
+
+}  // namespace
+
+bool yfft_length_supported(int N) {
+    if (N < 3) return false;
+    int m = 2 * (N - 1);
+    for (int r : {2, 3, 5})
+        while (m % r == 0) m /= r;
+    return m == 1;
+}
+
+// p as for ygemm_launch; handles the jobs without a second input (in2).  Returns -1 when the parameters need the contraction.
+int yfft_launch(const YGemmParams& p, const FftPlanDev& pl, double a, double b, cudaStream_t stream) {
+    if (pl.N != 2 * (p.N - 1)) return -1;
+    for (int j = 0; j < p.njobs; ++j)
+        if (p.job[j].in2 || (p.mode == 1 && (p.job[j].nmat != 1 || p.job[j].mat0 != 0))) return -1;
+    if ((p.in_runstart && (p.in_runlen & 1)) || (p.out_runstart && (p.out_runlen & 1)) || (p.in_ld & 1) || (p.out_ld & 1) || (p.ncols & 1)) return -1;
+    if (p.ncols <= 0 || p.njobs <= 0) return 0;
+    static const int cw = getenv("CF_YFFT_C") ? atoi(getenv("CF_YFFT_C")) : 8;
+    const double dscale = 4.0 / (b - a);
+    const size_t need8 = ((size_t)pl.N * 8 + pl.N + 2 * YF_THREADS) * sizeof(double2);
+    if (cw != 4 && need8 <= 200 * 1024) {
+        const int rc = launch_ch<8>(p, pl, dscale, stream);
+        if (rc >= 0) return rc;
+    }
+    const size_t need4 = ((size_t)pl.N * 4 + pl.N + 2 * YF_THREADS) * sizeof(double2);
+    if (need4 > 200 * 1024) return -1;
+    return launch_ch<4>(p, pl, dscale, stream);
+}
+
+}  // namespace cfgpu

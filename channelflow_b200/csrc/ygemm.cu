@@ -13,6 +13,7 @@
 // coefficient) is not worth a 32-row tile and is evaluated as plain dot products instead.
 // Each output element is written exactly once.
 // Roofline: tensor (FP64) for Ny >~ 49, HBM below; algorithmic flops = 2*Ny*ceil(Ny/2)*2 per column per output.
+#include "fft_smem.cuh"
 #include "ygemm.cuh"
 
 #include <cstdlib>
@@ -293,6 +294,10 @@ static int launch_bn(const YGemmParams& p, cudaStream_t stream) {
 int ygemm_launch(const YGemmParams& p0, cudaStream_t stream) {
     YGemmParams p = p0;
     if (p.ncols <= 0 || p.njobs <= 0) return 0;
+    if (p.fft) {
+        const int rc = yfft_launch(p, *p.fft, p.ya, p.yb, stream);
+        if (rc >= 0) return rc;
+    }
     p.two_inputs = 0;
     for (int j = 0; j < p.njobs; ++j)
         if (p.job[j].in2) p.two_inputs = 1;

@@ -14,6 +14,7 @@
 
 namespace cfgpu {
 
+struct FftPlanDev;
 constexpr int YG_MAXJOB = 9;
 constexpr int YG_MAXMAT = 2;
 
@@ -49,11 +50,16 @@ struct YGemmParams {
     const long* out_runstart;
     long out_ld;
     int two_inputs;               // some job has in2 (set by the launcher: doubles the operand tiles in shared memory)
+    const FftPlanDev* fft;        // host pointer, may be null: FFT plan of length 2(N-1) -- the jobs then run as shared-memory
+    double ya, yb;                // FFTs (yfft.cu) where that kernel covers them; wall positions for its d/dy scale
     int njobs;
     YGemmJob job[YG_MAXJOB];
 };
 
 // launches on `stream`; returns 0 on success
 int ygemm_launch(const YGemmParams& p, cudaStream_t stream);
+// yfft.cu: the same jobs as FFTs; -1 = not covered (second inputs, unsupported length), the caller falls back to the contraction
+bool yfft_length_supported(int N);
+int yfft_launch(const YGemmParams& p, const FftPlanDev& pl, double a, double b, cudaStream_t stream);
 
 }  // namespace cfgpu
