@@ -428,15 +428,26 @@ def main():
             stages[name] = {"ms_per_step": per, "calls_per_step": c / args.steps}
             if name in STAGE_W:
                 stages[name]["algorithmic_GBps"] = STAGE_W[name] * Wbytes / world / (per * 1e-3) / 1e9  # this rank's share
-    # y-GEMM stages are FP64 tensor-pipe (DMMA) work: flops of the even/odd-split contractions the kernels perform
+    # The y stages (named *_y_gemm after their first implementation) run as shared-memory FFTs (csrc/yfft.cu, HBM-bound) when
+    # 2(Ny-1) factors into 2, 3, 5 and CF_YFFT is not 0; otherwise as FP64 tensor-pipe (DMMA) contractions, for which the flops
+    # of the even/odd-split contractions are reported against cuBLAS DGEMM.
+    def _smooth(n):
+        for r in (2, 3, 5):
+            while n % r == 0:
+                n //= r
+        return n == 1
+    y_as_fft = os.environ.get("CF_YFFT", "1") != "0" and w["Ny"] >= 3 and _smooth(2 * (w["Ny"] - 1))
     Kx_, Kz_ = w["Nx"] // 3 - 1, w["Nz"] // 3 - 1
     ncols = 2 * (2 * Kx_ + 1) * (Kz_ + 1) / world            # real columns of this rank
     rot = STAGE_W is STAGE_W_ROT
-    gemm_flops = {"inv_y_gemm": 5 if rot else 6, "fwd_y_gemm": 3 if rot else 6}   # matrices applied per step
+    gemm_flops = {} if y_as_fft else {"inv_y_gemm": 5 if rot else 6, "fwd_y_gemm": 3 if rot else 6}   # matrices applied per step
     for k_, nm in gemm_flops.items():
         if k_ in stages:
             fl = nm * 2.0 * w["Ny"] * ((w["Ny"] + 1) // 2) * ncols
             stages[k_]["TFLOPs"] = fl / (stages[k_]["ms_per_step"] * 1e-3) / 1e12
+    for k_ in ("inv_y_gemm", "fwd_y_gemm"):
+        if k_ in stages:
+            stages[k_]["kernel"] = "yfft_half_kernel (shared-memory FFT, hbm-bound)" if y_as_fft else "ygemm_kernel (DMMA contraction, fp64-tensor-bound)"
     # The roofline object describes the quantity the target is stated on: transforms + nonlinear term (36 W of
     # the 61 W rotational step) against the HBM roofline; `kernel` names the slowest of those stages.  Every stage's own
     # figure is in `stages`.
@@ -463,7 +474,7 @@ def main():
     for k_ in stages:  # every stage against its own bound, so the next kernel to work on can be read off the line
         if k_ in STAGE_W and k_ not in gemm_flops:
             stages[k_]["frac_of_hbm_peak"] = stages[k_]["algorithmic_GBps"] / hbm_peak
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and gemm_flops:
         # FP64 tensor yard-stick for the y-GEMM stages: cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no FP64 figure)
         try:
             n_ = 8192

@@ -197,6 +197,13 @@ const FftPlanDev* yfft_plan(cfgpu_ctx ctx, int Ny) {
     return pl;
 }
 
+const FftPlanDev* yfft_half_plan(cfgpu_ctx ctx, int Ny) {
+    if (!yfft_plan(ctx, Ny) || (Ny - 1) % 2) return nullptr;
+    const FftPlanDev* pl = nullptr;
+    if (get_fftplan(ctx, Ny - 1, &pl)) return nullptr;
+    return pl;
+}
+
 int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out) {
     auto it = ctx->fftplans.find(N);
     if (it != ctx->fftplans.end()) {
@@ -904,7 +911,7 @@ static int y_transform(cfgpu_field f, int mode) {
         YGemmParams p;
         memset(&p, 0, sizeof p);
         p.N = f->Ny; p.mode = mode;
-        p.fft = yfft_plan(f->ctx, f->Ny); p.ya = f->a; p.yb = f->b;
+        p.fft = yfft_plan(f->ctx, f->Ny); p.fft_half = yfft_half_plan(f->ctx, f->Ny); p.ya = f->a; p.yb = f->b;
         if (mode == 0) {
             p.M = p.M2 = pl->Nh; p.K1 = pl->Ne; p.K2 = pl->No; p.K1p = pl->invK1p; p.K2p = pl->invK2p;
             p.A1[0] = pl->Ce; p.A2[0] = pl->Co; p.sgn[0] = 1.0;

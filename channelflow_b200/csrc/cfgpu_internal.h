@@ -164,6 +164,7 @@ int field_tile_output(cfgpu_field f, const TileGeom& g, bool outside_zero);  // 
 int get_yplan(cfgpu_ctx ctx, int N, double a, double b, const YPlan** out);
 int get_fftplan(cfgpu_ctx ctx, int N, const FftPlanDev** out);
 const FftPlanDev* yfft_plan(cfgpu_ctx ctx, int Ny);
+const FftPlanDev* yfft_half_plan(cfgpu_ctx ctx, int Ny);
 int get_box(cfgpu_ctx ctx, int Nx, int Nz, int Kx, int Kz, const ModeBox** out);
 int ws_reserve(Workspace& w, size_t bytes);
 int stage_begin(cfgpu_ctx ctx, int stage, cudaStream_t stream = 0);  // 0: the context's compute stream

@@ -311,7 +311,7 @@ static int inverse_to_Q(cfgpu_nse nse, cfgpu_field u, bool with_derivs) {
     YGemmParams p;
     memset(&p, 0, sizeof p);
     p.N = nse->Ny; p.mode = 0;
-    p.fft = yfft_plan(ctx, nse->Ny); p.ya = nse->a; p.yb = nse->b;
+    p.fft = yfft_plan(ctx, nse->Ny); p.fft_half = yfft_half_plan(ctx, nse->Ny); p.ya = nse->a; p.yb = nse->b;
     p.M = p.M2 = yp->Nh; p.K1 = yp->Ne; p.K2 = yp->No; p.K1p = yp->invK1p; p.K2p = yp->invK2p;
     p.A1[0] = yp->Ce; p.A2[0] = yp->Co; p.sgn[0] = 1.0;
     p.A1[1] = yp->CDe; p.A2[1] = yp->CDo; p.sgn[1] = -1.0;
@@ -626,7 +626,7 @@ static int nonlinear_fused_general(cfgpu_nse nse, cfgpu_field u, cfgpu_field f, 
         YGemmParams p;
         memset(&p, 0, sizeof p);
         p.N = nse->Ny; p.mode = 0;
-        p.fft = yfft_plan(ctx, nse->Ny); p.ya = nse->a; p.yb = nse->b;
+        p.fft = yfft_plan(ctx, nse->Ny); p.fft_half = yfft_half_plan(ctx, nse->Ny); p.ya = nse->a; p.yb = nse->b;
         p.M = p.M2 = yp->Nh; p.K1 = yp->Ne; p.K2 = yp->No; p.K1p = yp->invK1p; p.K2p = yp->invK2p;
         p.A1[0] = yp->Ce; p.A2[0] = yp->Co; p.sgn[0] = 1.0;
         p.A1[1] = yp->CDe; p.A2[1] = yp->CDo; p.sgn[1] = -1.0;
@@ -699,7 +699,7 @@ static int nonlinear_fused_general(cfgpu_nse nse, cfgpu_field u, cfgpu_field f, 
         YGemmParams p;
         memset(&p, 0, sizeof p);
         p.N = nse->Ny; p.mode = 1;
-        p.fft = yfft_plan(ctx, nse->Ny); p.ya = nse->a; p.yb = nse->b;
+        p.fft = yfft_plan(ctx, nse->Ny); p.fft_half = yfft_half_plan(ctx, nse->Ny); p.ya = nse->a; p.yb = nse->b;
         p.M = yp->Ne; p.M2 = yp->No; p.K1 = p.K2 = yp->Nh; p.K1p = p.K2p = yp->fwdKp;
         p.A1[0] = yp->Fe; p.A2[0] = yp->Fo; p.sgn[0] = 1.0;
         p.A1b = yp->GDe[cd == 0.5 ? 1 : 0]; p.A2b = yp->GDo[cd == 0.5 ? 1 : 0];
@@ -892,7 +892,7 @@ int cfgpu_nse_nonlinear(cfgpu_nse nse, cfgpu_field u, cfgpu_field f) {
     YGemmParams p;
     memset(&p, 0, sizeof p);
     p.N = nse->Ny; p.mode = 1;
-    p.fft = yfft_plan(ctx, nse->Ny); p.ya = nse->a; p.yb = nse->b;
+    p.fft = yfft_plan(ctx, nse->Ny); p.fft_half = yfft_half_plan(ctx, nse->Ny); p.ya = nse->a; p.yb = nse->b;
     p.M = yp->Ne; p.M2 = yp->No; p.K1 = p.K2 = yp->Nh; p.K1p = p.K2p = yp->fwdKp;
     p.A1[0] = yp->Fe; p.A2[0] = yp->Fo; p.sgn[0] = 1.0;
     p.ncols = (long)nxl * nkz * 2;

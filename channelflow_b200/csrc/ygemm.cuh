@@ -50,6 +50,7 @@ struct YGemmParams {
     const long* out_runstart;
     long out_ld;
     int two_inputs;               // some job has in2 (set by the launcher: doubles the operand tiles in shared memory)
+    const FftPlanDev* fft_half;   // host pointer, may be null: plan of length N-1 for the half-length variant of the same
     const FftPlanDev* fft;        // host pointer, may be null: FFT plan of length 2(N-1) -- the jobs then run as shared-memory
     double ya, yb;                // FFTs (yfft.cu) where that kernel covers them; wall positions for its d/dy scale
     int njobs;
