@@ -360,3 +360,23 @@ def test_netcdf_field_writer(lib, tmp_path):
     assert r["grid_err"] < 1e-14 and r["values_abs"] < 1e-14 and r["reread_rel"] < 1e-14 and r["reread_padded"], r
     assert r["full_rel"] < 1e-14 and not r["full_padded"] and r["full_dims"] == {"X": 32, "Y": 33, "Z": 32}, r
     assert r["scipy_rel"] < 1e-14, r
+
+
+# profile lengths: 2(Ny-1) smooth in 2, 3, 5 -> half-length FFT kernel (csrc/yfft.cu), radix mixes 2/3/4/5/8 and the short
+# edge cases; Ny = 15, 23 -> the DMMA contraction (2(Ny-1) has the factor 7 / 11)
+Y_LENGTHS = [5, 7, 9, 11, 13, 15, 21, 23, 25, 31, 41, 49, 51, 61, 65, 97, 101]
+
+
+@pytest.mark.parametrize("Ny", Y_LENGTHS)
+def test_y_transform_lengths(lib, Ny):
+    cfg = dict(parity.C1); cfg.update(Nx=8, Ny=Ny, Nz=8)
+    r = parity.transforms(lib, cfg)
+    assert max(r.values()) < 2e-14, r
+
+
+@pytest.mark.parametrize("Ny", [9, 21, 31, 41, 61])
+def test_nonlinear_y_lengths(lib, Ny):
+    """the rotational term needs u_y, w_y: the derivative unit of the y-transform (suffix sums + transform) at other lengths"""
+    cfg = dict(parity.C1); cfg.update(Nx=12, Ny=Ny, Nz=12)
+    r = parity.nonlinear(lib, cfg)
+    assert r["nonlinear"] < 2e-14, r
