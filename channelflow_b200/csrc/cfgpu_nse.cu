@@ -702,7 +702,7 @@ static int nonlinear_fused_general(cfgpu_nse nse, cfgpu_field u, cfgpu_field f, 
         p.fft = yfft_plan(ctx, nse->Ny); p.fft_half = yfft_half_plan(ctx, nse->Ny); p.ya = nse->a; p.yb = nse->b;
         p.M = yp->Ne; p.M2 = yp->No; p.K1 = p.K2 = yp->Nh; p.K1p = p.K2p = yp->fwdKp;
         p.A1[0] = yp->Fe; p.A2[0] = yp->Fo; p.sgn[0] = 1.0;
-        p.A1b = yp->GDe[cd == 0.5 ? 1 : 0]; p.A2b = yp->GDo[cd == 0.5 ? 1 : 0];
+        p.A1b = yp->GDe[cd == 0.5 ? 1 : 0]; p.A2b = yp->GDo[cd == 0.5 ? 1 : 0]; p.in2_scale = cd == 0.5 ? 0.5 : 1.0;
         p.ncols = (long)nmx * nkz * 2;
         p.in_runlen = 1; p.in_runstart = nullptr; p.in_ld = (long)nmx * nkz * 2;
         p.out_runlen = fa.runlen; p.out_runstart = fa.runstart; p.out_ld = fa.ld;

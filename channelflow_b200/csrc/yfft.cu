@@ -11,7 +11,9 @@
 //   d/dy    : coefficients d_n = (4/(b-a)) (1/2 at n = 0) sum_{m>n, m-n odd} m c_m   (chebyshev.cpp:672-697), formed in shared
 //             memory by a chunked suffix sum over n before the second FFT of the same input.
 // Against the DMMA contraction this is O(L log L) instead of O(Ny^2/2) flops per profile: at Ny = 257 the contraction is
-// bound by the FP64 tensor pipe (1.65 ms inverse, 1.14 ms forward at 512x257x512), the FFT by HBM.
+// bound by the FP64 tensor pipe (1.65 ms inverse, 1.14 ms forward at 512x257x512), the FFT by memory latency (1.11 / 0.59 ms).
+// Two kernels: yfft_kernel transforms the full even extension (length 2M); yfft_half_kernel -- the default -- reduces it to ONE
+// complex FFT of length M per mode (see its comment) and also serves the forward jobs with a second input.
 //
 // CTA = C complex columns (modes) of one job; shared memory a[L][C] (in-place transform, digit-reversed input rows) plus the
 // plan's twiddle and row tables.  A row piece of C = 8 columns is 128 contiguous bytes in HBM.
@@ -176,7 +178,8 @@ __global__ void __launch_bounds__(YF_THREADS, 3) yfft_half_kernel(const YGemmPar
     double2* a = dyn_smem<double2>();      // [M][C]
     double2* stw = a + (size_t)M * C;      // [ntw] twiddles of the length-M plan
     double2* part = stw + ntw;             // [4 TPC][C] chunk sums
-    int* rev = reinterpret_cast<int*>(part + 4 * TPC * C);   // [M]
+    double2* cbuf = part + 4 * TPC * C;    // [N][C] d/dy coefficients of the second input (forward with in2 only)
+    int* rev = reinterpret_cast<int*>(cbuf + (p.two_inputs ? (size_t)N * C : 0));   // [M]
     const int c = tid % C, t = tid / C;
     const long col = cblock * C + c;
     const bool cvalid = 2 * col < p.ncols;
@@ -187,6 +190,11 @@ __global__ void __launch_bounds__(YF_THREADS, 3) yfft_half_kernel(const YGemmPar
     const int ch = (H + 1 + TPC - 1) / TPC;   // pairs per thread
     const int j0 = t * ch;
 
+    // Forward jobs with a second input (f = F x + cd D F x2, the divergence / skew-symmetric forms): pass 0 transforms x2 and
+    // leaves the coefficients of its y-derivative in cbuf, pass 1 transforms x and adds them.  Everything else: pass 1 only.
+    const bool two = p.mode == 1 && jb.in2 != nullptr;
+    for (int pass = two ? 0 : 1; pass < 2; ++pass) {
+    const double* __restrict__ inp = pass == 0 ? jb.in2 : jb.in;
     // rows j (lo) and M-j (hi) of the thread's pairs; the self-paired row M/2 is loaded once
     double2 lo[CH], hi[CH];
 #pragma unroll
@@ -194,16 +202,18 @@ __global__ void __launch_bounds__(YF_THREADS, 3) yfft_half_kernel(const YGemmPar
         const int j = j0 + i;
         lo[i] = zero; hi[i] = zero;
         if (i < ch && j <= H && cvalid) {
-            const double* s0 = jb.in + (size_t)j * p.in_ld + inoff;
+            const double* s0 = inp + (size_t)j * p.in_ld + inoff;
             lo[i] = make_double2(s0[0], s0[1]);
             if (j < H) {
-                const double* s1 = jb.in + (size_t)(M - j) * p.in_ld + inoff;
+                const double* s1 = inp + (size_t)(M - j) * p.in_ld + inoff;
                 hi[i] = make_double2(s1[0], s1[1]);
             }
         }
     }
-    for (int i = tid; i < M; i += YF_THREADS) rev[i] = pl.rev[i];
-    for (int i = tid; i < ntw; i += YF_THREADS) stw[i] = pl.tw[i];
+    if (pass == (two ? 0 : 1)) {   // first pass: the plan's tables
+        for (int i = tid; i < M; i += YF_THREADS) rev[i] = pl.rev[i];
+        for (int i = tid; i < ntw; i += YF_THREADS) stw[i] = pl.tw[i];
+    }
 
     if (is_der) {
         // coefficients of the derivative in place of the input: suffix sums of m c_m by parity (see the full-length kernel).
@@ -315,8 +325,10 @@ __global__ void __launch_bounds__(YF_THREADS, 3) yfft_half_kernel(const YGemmPar
     double* const obase = jb.out[mslot] + outoff;
     const bool fwd = p.mode == 1;
     auto store = [&](int r, double2 x) {
-        if (!cvalid) return;
         if (fwd) { const double wn = (r == 0 || r == M) ? 0.5 * w : w; x.x *= wn; x.y *= wn; }
+        if (pass == 0) { cbuf[r * C + c] = x; return; }
+        if (two) { const double2 d = cbuf[r * C + c]; x.x += d.x; x.y += d.y; }
+        if (!cvalid) return;
         double* dst = orows ? orows[r] + outoff : obase + (size_t)r * p.out_ld;
         dst[0] = x.x;
         dst[1] = x.y;
@@ -328,12 +340,43 @@ __global__ void __launch_bounds__(YF_THREADS, 3) yfft_half_kernel(const YGemmPar
         store(2 * k + 1, odd);
     }
     if (t == TPC - 1) store(M, a[H * C + c]);   // T_M = Y_{M/2}
+    if (pass == 0) {
+        // cbuf: coefficients c of x2 -> d_n = in2_scale (4/(b-a)) (1/2 at n = 0) sum_{m>n, m-n odd} m c_m, in place
+        __syncthreads();
+        const double d2 = p.in2_scale * dscale;
+        const int chn = (N + TPC - 1) / TPC;
+        const int n0 = t * chn, n1 = (n0 + chn < N) ? n0 + chn : N;
+        double2 se = zero, so = zero;
+        for (int m = n0; m < n1; ++m) {
+            const double2 v = cbuf[m * C + c];
+            if (m & 1) { so.x += m * v.x; so.y += m * v.y; } else { se.x += m * v.x; se.y += m * v.y; }
+        }
+        part[(2 * t) * C + c] = se;
+        part[(2 * t + 1) * C + c] = so;
+        __syncthreads();
+        se = zero; so = zero;
+        for (int q = TPC - 1; q > t; --q) {
+            const double2 pe = part[(2 * q) * C + c], po = part[(2 * q + 1) * C + c];
+            se.x += pe.x; se.y += pe.y; so.x += po.x; so.y += po.y;
+        }
+        for (int n = n1 - 1; n >= n0; --n) {
+            const double2 sm = (n & 1) ? se : so;
+            const double f = (n == 0) ? 0.5 * d2 : d2;
+            const double2 v = cbuf[n * C + c];
+            if (n & 1) { so.x += n * v.x; so.y += n * v.y; } else { se.x += n * v.x; se.y += n * v.y; }
+            cbuf[n * C + c] = make_double2(f * sm.x, f * sm.y);
+        }
+        __syncthreads();
+    }
+    }   // pass
 }
 
 template <int C, int CH>
 int launch_half_c(const YGemmParams& p, const FftPlanDev& plM, const double2* twL, double dscale, cudaStream_t stream) {
     const int M = p.N - 1;
-    const size_t smem = ((size_t)M * C + fft_plan_ntw(plM) + 4 * YF_THREADS) * sizeof(double2) + (size_t)M * sizeof(int);
+    const size_t smem = ((size_t)M * C + fft_plan_ntw(plM) + 4 * YF_THREADS + (p.two_inputs ? (size_t)p.N * C : 0)) * sizeof(double2) +
+                        (size_t)M * sizeof(int);
+    if (smem > 200 * 1024) return -1;
     auto kfn = yfft_half_kernel<C, CH>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -409,11 +452,16 @@ bool yfft_length_supported(int N) {
     return m == 1;
 }
 
-// p as for ygemm_launch; handles the jobs without a second input (in2).  Returns -1 when the parameters need the contraction.
-int yfft_launch(const YGemmParams& p, const FftPlanDev& pl, double a, double b, cudaStream_t stream) {
-    if (pl.N != 2 * (p.N - 1)) return -1;
-    for (int j = 0; j < p.njobs; ++j)
-        if (p.job[j].in2 || (p.mode == 1 && (p.job[j].nmat != 1 || p.job[j].mat0 != 0))) return -1;
+// p as for ygemm_launch.  Returns -1 when the parameters need the contraction.
+int yfft_launch(const YGemmParams& p_in, const FftPlanDev& pl, double a, double b, cudaStream_t stream) {
+    if (pl.N != 2 * (p_in.N - 1)) return -1;
+    YGemmParams p = p_in;
+    p.two_inputs = 0;
+    for (int j = 0; j < p.njobs; ++j) {
+        if (p.mode == 1 && (p.job[j].nmat != 1 || p.job[j].mat0 != 0)) return -1;
+        if (p.job[j].in2) p.two_inputs = 1;
+    }
+    if (p.two_inputs && (p.mode != 1 || p.in2_scale == 0.0)) return -1;
     if ((p.in_runstart && (p.in_runlen & 1)) || (p.out_runstart && (p.out_runlen & 1)) || (p.in_ld & 1) || (p.out_ld & 1) || (p.ncols & 1)) return -1;
     if (p.ncols >= 0x7fffffffL) return -1;
     if (p.ncols <= 0 || p.njobs <= 0) return 0;
@@ -428,6 +476,7 @@ int yfft_launch(const YGemmParams& p, const FftPlanDev& pl, double a, double b, 
         if (rc < 0) rc = launch_half_ch<4>(p, *p.fft_half, pl.tw, dscale, stream);
         if (rc >= 0) return rc;
     }
+    if (p.two_inputs) return -1;   // (the full-length kernel has no second-input path)
     const size_t need8 = ((size_t)pl.N * 8 + pl.N + 2 * YF_THREADS) * sizeof(double2);
     if (cw != 4 && need8 <= 200 * 1024) {
         const int rc = launch_ch<8>(p, pl, dscale, stream);

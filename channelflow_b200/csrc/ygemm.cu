@@ -297,6 +297,9 @@ int ygemm_launch(const YGemmParams& p0, cudaStream_t stream) {
     if (p.fft) {
         const int rc = yfft_launch(p, *p.fft, p.ya, p.yb, stream);
         if (rc >= 0) return rc;
+        // CF_YFFT_STRICT=1 (tests): a job the FFT kernels do not cover is an error instead of a contraction
+        static const int strict = getenv("CF_YFFT_STRICT") ? atoi(getenv("CF_YFFT_STRICT")) : 0;
+        if (strict) { set_last_error("ygemm: y-transform parameters not covered by the FFT kernels (CF_YFFT_STRICT)"); return 1; }
     }
     p.two_inputs = 0;
     for (int j = 0; j < p.njobs; ++j)

@@ -40,6 +40,7 @@ struct YGemmParams {
     const double* A1[YG_MAXMAT];  // [Mp x K1p] row major, Mp = M rounded up to 8, zero padded
     const double* A2[YG_MAXMAT];  // [Mp x K2p]
     double sgn[YG_MAXMAT];        // inverse: sign of the reflected row
+    double in2_scale;             // factor of the in2 term (what A1b/A2b carry: 1, or 1/2 for the skew-symmetric average)
     const double* A1b;            // [Mp x K1p]: even output rows from the difference tile of in2
     const double* A2b;            // [Mp x K1p]: odd output rows from the sum tile of in2
     long ncols;                   // number of (double) columns
