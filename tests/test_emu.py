@@ -348,3 +348,13 @@ def test_nonlinear_y_lengths(lib, Ny):
     cfg = dict(parity.C1); cfg.update(Nx=12, Ny=Ny, Nz=12)
     r = parity.nonlinear(lib, cfg)
     assert r["nonlinear"] < 2e-14, r
+
+
+@pytest.mark.parametrize("nl", ["div", "skew"])
+@pytest.mark.parametrize("Ny", [15, 33])
+def test_nonlinear_forms_second_input(lib, nl, Ny):
+    """forward y-transform with a second input (d/dy of u_i v added in coefficient space) through the fused pipeline: Ny = 15
+    runs the DMMA contraction with its derivative matrices (2(Ny-1) = 28 has the factor 7), Ny = 33 the two-pass FFT kernel"""
+    cfg = dict(parity.C1); cfg.update(Nx=16, Ny=Ny, Nz=16)
+    r = parity.nonlinear(lib, cfg, nonlinearity=nl)
+    assert r["nonlinear"] < 1e-12, r
