@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(YF_THREADS, 3) yfft_kernel(const YGemmParams p
 // where T_k = x_0 + (-1)^k x_M + 2 sum_{0<j<M} x_j cos(pi j k/M) is what the full-length transform returns at k <= M.
 // Thread (c, t) loads the row PAIRS (j, M-j) of its chunk of j <= M/2, so y_j, y_{M-j} and its share of T_1 come from its own
 // registers; after the transform it owns a chunk of k: T_{2k}, D_k from a[k], a[M-k], the odd rows by a chunked prefix sum.
-template <int C, int CH>   // CH >= pairs per thread
+template <int C, int CH, bool TWO>   // CH >= pairs per thread; TWO: the launch has forward jobs with a second input
 __global__ void __launch_bounds__(YF_THREADS, 3) yfft_half_kernel(const YGemmParams p, const FftPlanDev pl, const double2* __restrict__ twL,
                                                                   const double dscale, const YfftUnits un) {
     const int N = p.N, M = N - 1, H = M / 2;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(YF_THREADS, 3) yfft_half_kernel(const YGemmPar
 
     // Forward jobs with a second input (f = F x + cd D F x2, the divergence / skew-symmetric forms): pass 0 transforms x2 and
     // leaves the coefficients of its y-derivative in cbuf, pass 1 transforms x and adds them.  Everything else: pass 1 only.
-    const bool two = p.mode == 1 && jb.in2 != nullptr;
+    const bool two = TWO && p.mode == 1 && jb.in2 != nullptr;   // (TWO = false: one pass, no trace of the second in the code)
     for (int pass = two ? 0 : 1; pass < 2; ++pass) {
     const double* __restrict__ inp = pass == 0 ? jb.in2 : jb.in;
     // rows j (lo) and M-j (hi) of the thread's pairs; the self-paired row M/2 is loaded once
@@ -377,11 +377,11 @@ int launch_half_c(const YGemmParams& p, const FftPlanDev& plM, const double2* tw
     const size_t smem = ((size_t)M * C + fft_plan_ntw(plM) + 4 * YF_THREADS + (p.two_inputs ? (size_t)p.N * C : 0)) * sizeof(double2) +
                         (size_t)M * sizeof(int);
     if (smem > 200 * 1024) return -1;
-    auto kfn = yfft_half_kernel<C, CH>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    auto kfn = p.two_inputs ? yfft_half_kernel<C, CH, true> : yfft_half_kernel<C, CH, false>;
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[p.two_inputs ? 1 : 0]) {
         CF_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[p.two_inputs ? 1 : 0] = smem;
     }
     YfftUnits un;
     un.n = 0;
